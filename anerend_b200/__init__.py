@@ -1,0 +1,69 @@
+"""anerend_b200 — B200-native DDGI irradiance-probe update behind AneRend's pass interface.
+
+The product is the C-ABI library `libanerend_cuda_ddgi.so` (csrc/, include/anerend_cuda_ddgi.h): hand-written
+sm_100a CUDA for the chain IrradianceProbeTrans -> IrradianceProbeRT -> IrradianceProbeConvolve.  This package
+is the thin host side: ctypes binding (`Ddgi`), the reference-shaped pass objects (`passes`), synthetic scene
+generators (`scenes`) and the multi-GPU slab helper (`sharding`).
+
+There is no CPU fallback: creating a `Ddgi` without the built library or without a CUDA device raises.
+"""
+import ctypes as _C
+import os as _os
+
+from . import layouts, scenes  # noqa: F401
+from .capi import DdgiError, DdgiHandle, make_params  # noqa: F401
+
+_HERE = _os.path.dirname(_os.path.abspath(__file__))
+LIB_PATH = _os.path.join(_HERE, "libanerend_cuda_ddgi.so")
+_LIB = None
+
+
+def load_library():
+    """Loads the CUDA library; fails loudly when it has not been built (`python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _LIB
+    if _LIB is None:
+        if not _os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+                               "(there is no CPU fallback for the DDGI probe update)")
+        _LIB = _C.CDLL(LIB_PATH)
+        _LIB.anerend_cuda_ddgi_version.restype = _C.c_char_p
+    return _LIB
+
+
+class Ddgi(DdgiHandle):
+    """The CUDA DDGI probe volume (anerend_cuda_ddgi_* entry points)."""
+
+    def __init__(self, params):
+        super().__init__(load_library(), "anerend_cuda_ddgi_", params)
+
+    def timings(self):
+        from .capi import Timings
+        t = Timings()
+        self._call("get_timings", _C.byref(t))
+        return {k: getattr(t, k) for k, _ in t._fields_}
+
+    def atlas_device_ptr(self):
+        p, n = _C.c_void_p(), _C.c_size_t()
+        self._call("atlas_device_ptr", _C.byref(p), _C.byref(n))
+        return p.value, n.value
+
+    def stream(self):
+        s = _C.c_void_p()
+        self._call("stream", _C.byref(s))
+        return s.value or 0
+
+    def set_peer_atlases(self, ptrs):
+        arr = (_C.c_void_p * len(ptrs))(*ptrs)
+        self._call("set_peer_atlases", arr, _C.c_uint32(len(ptrs)))
+
+    def refit_accel_device(self, d_ptr, count):
+        self._call("refit_accel_device", _C.c_void_p(d_ptr), _C.c_uint32(count))
+
+    def download_bvh(self):
+        import numpy as np
+        info = self.bvh_info()
+        nodes = np.empty(info.num_nodes * info.node_bytes, np.uint8)
+        tris = np.empty(info.num_triangles * info.tri_bytes, np.uint8)
+        self._call("download_bvh", nodes.ctypes.data_as(_C.c_void_p), _C.c_size_t(nodes.nbytes),
+                   tris.ctypes.data_as(_C.c_void_p), _C.c_size_t(tris.nbytes))
+        return nodes, tris

@@ -1,0 +1,235 @@
+"""ctypes binding of the anerend_cuda_ddgi_* C ABI (include/anerend_cuda_ddgi.h).
+
+`DdgiHandle` is prefix-generic: the CPU oracle (test infrastructure, oracle/binding.py) exports the same
+functions under `ddgi_oracle_*`, so parity tests drive both sides with identical calls.  The product
+itself never touches the oracle: `anerend_b200.Ddgi` always binds libanerend_cuda_ddgi.so.
+"""
+import ctypes as C
+import numpy as np
+
+from . import layouts as L
+
+
+class Params(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("num_probes_xz", C.c_int32), ("num_probes_y", C.c_int32),
+                ("rays_per_probe", C.c_int32), ("probe_step", C.c_float * 3), ("t_min", C.c_float),
+                ("t_max", C.c_float), ("hysteresis", C.c_float), ("flags", C.c_uint32),
+                ("slab_begin", C.c_int32), ("slab_end", C.c_int32), ("device", C.c_int32)]
+
+
+class Timings(C.Structure):
+    _fields_ = [("trans_ms", C.c_float), ("rt_ms", C.c_float), ("convolve_ms", C.c_float),
+                ("accel_ms", C.c_float), ("total_ms", C.c_float), ("kernel_launches", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("primary_rays", C.c_uint64), ("primary_hits", C.c_uint64), ("shadow_rays", C.c_uint64),
+                ("primary_nodes_visited", C.c_uint64), ("primary_tris_tested", C.c_uint64),
+                ("shadow_nodes_visited", C.c_uint64), ("shadow_tris_tested", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class BvhInfo(C.Structure):
+    _fields_ = [("num_triangles", C.c_uint32), ("num_nodes", C.c_uint32), ("node_bytes", C.c_uint32),
+                ("tri_bytes", C.c_uint32), ("num_instances", C.c_uint32),
+                ("bounds_min", C.c_float * 3), ("bounds_max", C.c_float * 3)]
+
+
+class DdgiError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+
+
+def make_params(num_probes_xz, num_probes_y, rays_per_probe, probe_step=(1.0, 2.0, 1.0), t_min=0.1, t_max=50.0,
+                hysteresis=0.96, flags=0, slab=None, device=-1):
+    """Defaults are the reference's compile-time constants (probe_helpers.glsl:1-7, rgen:91-92, probe_conv.comp:85)."""
+    p = Params()
+    p.struct_size = C.sizeof(Params)
+    p.num_probes_xz, p.num_probes_y, p.rays_per_probe = num_probes_xz, num_probes_y, rays_per_probe
+    p.probe_step = (C.c_float * 3)(*probe_step)
+    p.t_min, p.t_max, p.hysteresis, p.flags = t_min, t_max, hysteresis, flags
+    p.slab_begin, p.slab_end = slab if slab is not None else (0, num_probes_y)
+    p.device = device
+    return p
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _c(a, dtype):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a
+
+
+class DdgiHandle:
+    """One DDGI probe volume: state of the three passes plus the scene/acceleration structure."""
+
+    def __init__(self, lib, prefix, params):
+        self._lib, self._pfx = lib, prefix
+        self.params = params
+        self._h = C.c_void_p()
+        rc = self._fn("create")(C.byref(params), C.byref(self._h))
+        if rc != 0:
+            raise DdgiError(rc, f"{prefix}create failed (invalid parameters or no CUDA device)")
+        w, h = C.c_int32(), C.c_int32()
+        self._call("atlas_dims", C.byref(w), C.byref(h))
+        self.atlas_width, self.atlas_height = w.value, h.value
+        sx, sy = C.c_int32(), C.c_int32()
+        self._call("ray_tile", C.byref(sx), C.byref(sy))
+        self.ray_tile = (sx.value, sy.value)
+        self.n_xz, self.n_y, self.n_rays = params.num_probes_xz, params.num_probes_y, params.rays_per_probe
+
+    def _fn(self, name):
+        f = getattr(self._lib, self._pfx + name)
+        f.restype = C.c_int
+        return f
+
+    def _call(self, name, *args):
+        rc = self._fn(name)(self._h, *args)
+        if rc != 0:
+            e = getattr(self._lib, self._pfx + "last_error")
+            e.restype = C.c_char_p
+            raise DdgiError(rc, (e(self._h) or b"").decode())
+        return rc
+
+    def close(self):
+        if self._h:
+            self._fn("destroy")(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- scene ---------------------------------------------------------------------------------
+    def upload_scene(self, scene):
+        s = scene
+        self._keep = s
+        self._call("upload_scene",
+                   _ptr(s.vertices), C.c_uint32(len(s.vertices)), _ptr(s.indices), C.c_uint32(len(s.indices)),
+                   _ptr(s.meshes), _ptr(s.mesh_num_indices), C.c_uint32(len(s.meshes)),
+                   _ptr(s.materials), C.c_uint32(len(s.materials)),
+                   _ptr(s.renderables), C.c_uint32(len(s.renderables)),
+                   _ptr(s.model_indices), C.c_uint32(len(s.model_indices)),
+                   _ptr(s.material_indices), C.c_uint32(len(s.material_indices)),
+                   _ptr(s.lights), C.c_uint32(len(s.lights)))
+
+    def set_scene_ubo(self, ubo):
+        ubo = _c(ubo, L.SCENE_UBO)
+        self._call("set_scene_ubo", _ptr(ubo))
+
+    def build_accel(self):
+        self._call("build_accel")
+
+    def refit_accel(self, renderables=None):
+        if renderables is None:
+            self._call("refit_accel", None, C.c_uint32(0))
+        else:
+            r = _c(renderables, L.RENDERABLE)
+            self._call("refit_accel", _ptr(r), C.c_uint32(len(r)))
+
+    def bvh_info(self):
+        b = BvhInfo()
+        self._call("get_bvh_info", C.byref(b))
+        return b
+
+    # ---- passes ----------------------------------------------------------------------------------
+    def reset(self):
+        self._call("reset")
+
+    def translate(self):
+        self._call("translate")
+
+    def trace_layer(self, layer, rot):
+        rot = _c(rot, np.float32).reshape(16)
+        self._call("trace_layer", C.c_int32(layer), _ptr(rot))
+
+    def convolve_layer(self, layer):
+        self._call("convolve_layer", C.c_int32(layer))
+
+    def update(self, layer, rots):
+        rots = _c(rots, np.float32).reshape(-1)
+        need = 16 if layer >= 0 else 16 * self.n_y
+        if rots.size != need:
+            raise ValueError(f"update(layer={layer}) needs {need} floats of rotation, got {rots.size}")
+        self._call("update", C.c_int32(layer), _ptr(rots))
+
+    def frame(self, rot):
+        rot = _c(rot, np.float32).reshape(16)
+        layer = C.c_int32(-1)
+        self._call("frame", _ptr(rot), C.byref(layer))
+        return layer.value
+
+    def sync(self):
+        if hasattr(self._lib, self._pfx + "sync"):
+            self._call("sync")
+
+    # ---- results ---------------------------------------------------------------------------------
+    def download_atlas(self, out=None):
+        """ProbeRaysConvTex as uint16 [H, W, 4] (RGBA16F bit patterns)."""
+        if out is None:
+            out = np.empty((self.atlas_height, self.atlas_width, 4), np.uint16)
+        self._call("download_atlas", _ptr(out), C.c_size_t(out.nbytes))
+        return out
+
+    def upload_atlas(self, atlas):
+        a = _c(atlas, np.uint16)
+        self._call("upload_atlas", _ptr(a), C.c_size_t(a.nbytes))
+
+    def download_rays(self, layer):
+        """(ProbeRaysIrrTex, ProbeRaysDirTex) of `layer` as uint16 [S_y*nXZ, S_x*nXZ, 4]."""
+        sx, sy = self.ray_tile
+        irr = np.empty((sy * self.n_xz, sx * self.n_xz, 4), np.uint16)
+        dr = np.empty_like(irr)
+        self._call("download_rays", C.c_int32(layer), _ptr(irr), _ptr(dr), C.c_size_t(irr.nbytes))
+        return irr, dr
+
+    def download_ray_records(self, layer):
+        out = np.empty(self.n_xz * self.n_xz * self.n_rays, L.RAY_RECORD)
+        self._call("download_ray_records", C.c_int32(layer), _ptr(out), C.c_size_t(len(out)))
+        return out.reshape(self.n_xz * self.n_xz, self.n_rays)
+
+    def download_texel_records(self):
+        out = np.empty((self.atlas_height, self.atlas_width, 4), np.float32)
+        self._call("download_texel_records", _ptr(out), C.c_size_t(out.nbytes))
+        return out
+
+    def stats(self):
+        s = Stats()
+        self._call("get_stats", C.byref(s))
+        return s.as_dict()
+
+    def reset_stats(self):
+        self._call("reset_stats")
+
+    # ---- helpers -----------------------------------------------------------------------------------
+    def make_rotation(self, axis, angle_deg):
+        out = np.empty(16, np.float32)
+        f = getattr(self._lib, self._pfx + "make_rotation")
+        f.restype = C.c_int
+        rc = f(C.c_int32(int(axis)), C.c_float(float(angle_deg)), _ptr(out))
+        if rc != 0:
+            raise DdgiError(rc, "make_rotation: bad axis")
+        return out
+
+    def rotations(self, axis_angle_list):
+        return np.stack([self.make_rotation(a, d) for a, d in axis_angle_list])
+
+    def fibonacci_dirs(self, n):
+        out = np.empty((n, 3), np.float32)
+        f = getattr(self._lib, self._pfx + "fibonacci_dirs")
+        f.restype = C.c_int
+        f(C.c_int32(n), _ptr(out))
+        return out

@@ -1,0 +1,209 @@
+/*
+ * anerend_cuda_ddgi.h — C ABI of the B200-native DDGI irradiance-probe update.
+ *
+ * This is the drop-in boundary for AneRend's frame-graph pass chain
+ *     IrradianceProbeTrans -> IrradianceProbeRT -> IrradianceProbeConvolve
+ * (src/anerend/render/passes/IrradianceProbe{Translation,RayTracing,Convolve}Pass.cpp).
+ * The reference records Vulkan commands (vkCmdCopyImage / vkCmdTraceRaysKHR /
+ * vkCmdDispatch); B200 has no RT pipeline, so each pass exe calls one entry point
+ * below instead.  INTEGRATION.md shows the pass-side binding.
+ *
+ * Conventions: every function returns 0 on success or a negative ANEREND_DDGI_E_*
+ * code (never throws, no global state besides the opaque handle);
+ * anerend_cuda_ddgi_last_error(h) returns a human-readable message for the last
+ * failure on that handle.  A handle is not thread-safe; all device work of a
+ * handle is issued on one CUDA stream in call order and is asynchronous with
+ * respect to the host until _sync or a _download_* call.  Host pointers passed in
+ * are only read during the call.  There is NO CPU fallback: every entry point that
+ * computes needs a CUDA device and fails with ANEREND_DDGI_E_CUDA otherwise.
+ */
+#ifndef ANEREND_CUDA_DDGI_H
+#define ANEREND_CUDA_DDGI_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "anerend_ddgi_layouts.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ANEREND_DDGI_OK            0
+#define ANEREND_DDGI_E_INVALID    -1   /* bad argument / unsupported parameter   */
+#define ANEREND_DDGI_E_CUDA       -2   /* CUDA runtime error / no device         */
+#define ANEREND_DDGI_E_STATE      -3   /* call order (e.g. trace before build)   */
+#define ANEREND_DDGI_E_UNSUPPORTED -4  /* scene feature outside the path's scope */
+
+/* params.flags */
+#define ANEREND_DDGI_FLAG_POINT_LIGHTS  (1u << 0) /* extension E1: shade enabled point lights, each gated by an any-hit shadow ray */
+#define ANEREND_DDGI_FLAG_RAY_RECORDS   (1u << 1) /* keep a 32-byte fp32 debug record per ray (parity tests)                       */
+#define ANEREND_DDGI_FLAG_TEXEL_RECORDS (1u << 2) /* keep the fp32 pre-quantisation value of every convolved texel (parity tests)  */
+#define ANEREND_DDGI_FLAG_COUNTERS      (1u << 3) /* count BVH nodes visited / triangles tested (roofline bytes); slower kernels    */
+
+/*
+ * Parameters that are compile-time constants in the reference
+ * (assets/shaders/probe_helpers.glsl:1-7, probe_conv.comp:85, irradiance_probe_update.rgen:91-92).
+ */
+typedef struct anerend_ddgi_params {
+  uint32_t struct_size;       /* = sizeof(anerend_ddgi_params_t)                            */
+  int32_t  num_probes_xz;     /* NUM_PROBES_PER_PLANE            (reference 64)              */
+  int32_t  num_probes_y;      /* NUM_PROBE_PLANES                (reference 8)               */
+  int32_t  rays_per_probe;    /* NUM_RAYS_PER_PROBE, multiple of 32 in [32,1024] (ref. 256)  */
+  float    probe_step[3];     /* PROBE_STEP                      (reference 1,2,1)           */
+  float    t_min;             /* ray tMin                        (reference 0.1)             */
+  float    t_max;             /* ray tMax                        (reference 50)              */
+  float    hysteresis;        /* probe_conv.comp:85              (reference 0.96)            */
+  uint32_t flags;             /* ANEREND_DDGI_FLAG_*                                          */
+  int32_t  slab_begin;        /* first Y-layer this handle updates in a full-grid update     */
+  int32_t  slab_end;          /* one past the last; (0, num_probes_y) = whole grid           */
+  int32_t  device;            /* CUDA device ordinal, -1 = current device                    */
+} anerend_ddgi_params_t;
+
+/* 32-byte per-ray debug record (ANEREND_DDGI_FLAG_RAY_RECORDS). */
+typedef struct anerend_ddgi_ray_record {
+  uint32_t prim;              /* flattened world triangle id, 0xFFFFFFFF = miss              */
+  float    t, u, v;           /* hit distance and barycentrics (rchit `bary`)                */
+  float    radiance[3];       /* fp32 radiance before the rgba16f store (rgen:109)           */
+  uint32_t lit_mask;          /* bit0 sun unoccluded; bit(1+i) point light i unoccluded (E1) */
+} anerend_ddgi_ray_record_t;
+
+/* Device-time breakdown of the most recent call, named like the reference's per-pass GPU timers
+ * (FrameGraphBuilder.cpp:276-278; group "IrradianceProbe"). */
+typedef struct anerend_ddgi_timings {
+  float trans_ms;             /* "IrradianceProbeTrans"    */
+  float rt_ms;                /* "IrradianceProbeRT"       */
+  float convolve_ms;          /* "IrradianceProbeConvolve" */
+  float accel_ms;             /* last _build_accel/_refit_accel ("TLASUpdate"+"BLASUpdate")   */
+  float total_ms;             /* first to last event of the last call                         */
+  uint32_t kernel_launches;   /* kernels launched by the last call                            */
+} anerend_ddgi_timings_t;
+
+/* Traversal statistics (ANEREND_DDGI_FLAG_COUNTERS); totals since the last _reset_stats. */
+typedef struct anerend_ddgi_stats {
+  uint64_t primary_rays;
+  uint64_t primary_hits;
+  uint64_t shadow_rays;            /* any-hit rays actually traced */
+  uint64_t primary_nodes_visited;  /* BVH8 nodes fetched by closest-hit traversal */
+  uint64_t primary_tris_tested;
+  uint64_t shadow_nodes_visited;
+  uint64_t shadow_tris_tested;
+} anerend_ddgi_stats_t;
+
+typedef struct anerend_ddgi_bvh_info {
+  uint32_t num_triangles;     /* flattened world triangles                                   */
+  uint32_t num_nodes;         /* BVH8 nodes                                                  */
+  uint32_t node_bytes;        /* bytes per compressed node (80)                              */
+  uint32_t tri_bytes;         /* bytes per traversal triangle record (48)                    */
+  uint32_t num_instances;     /* (renderable, mesh) pairs that passed tlas_update.comp's test */
+  float    bounds_min[3];
+  float    bounds_max[3];
+} anerend_ddgi_bvh_info_t;
+
+typedef struct anerend_ddgi anerend_ddgi_t;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+
+/* Allocates the atlas "ProbeRaysConvTex" ((8+2)*nXZ x (8+2)*nXZ*nY RGBA16F, cleared to (0,0,0,1) like
+ * clearConvTex, IrradianceProbeConvolvePass.cpp:9-47), "TempProbeTex" and the ray buffers that replace
+ * "ProbeRaysIrrTex"/"ProbeRaysDirTex" (IrradianceProbeRayTracingPass.cpp:42-74). */
+int anerend_cuda_ddgi_create(const anerend_ddgi_params_t* params, anerend_ddgi_t** out);
+int anerend_cuda_ddgi_destroy(anerend_ddgi_t* h);
+/* Mirrors re-registration on swap-chain recreation (VulkanRenderer.cpp:1962-2000): atlas re-cleared,
+ * _currentLayer = 0 (IrradianceProbeRayTracingPass.cpp:39), _lastProbeIdx = (0,0). */
+int anerend_cuda_ddgi_reset(anerend_ddgi_t* h);
+const char* anerend_cuda_ddgi_last_error(const anerend_ddgi_t* h);
+int anerend_cuda_ddgi_sync(anerend_ddgi_t* h);
+
+/* ---- scene (bindless set 0: bindings 2,3,6,7,8,9,10,11; bindless.glsl:123-179) ---------- */
+
+/* mesh_num_indices carries InternalMesh::_numIndices (internal/InternalMesh.h:12), which GPUMeshInfo lacks
+ * (primitiveCount = _numIndices/3, VulkanRenderer.cpp:1313).  Materials must be texture-free
+ * (bindless_indices == -1) — bindless textures are outside this path's scope (E_UNSUPPORTED). */
+int anerend_cuda_ddgi_upload_scene(anerend_ddgi_t* h,
+    const anerend_vertex_t* vertices, uint32_t num_vertices,
+    const uint32_t* indices, uint32_t num_indices,
+    const anerend_mesh_info_t* meshes, const uint32_t* mesh_num_indices, uint32_t num_meshes,
+    const anerend_material_info_t* materials, uint32_t num_materials,
+    const anerend_renderable_t* renderables, uint32_t num_renderables,
+    const uint32_t* model_indices, uint32_t num_model_indices,      /* binding 8: rendModelBuffer    */
+    const uint32_t* material_indices, uint32_t num_material_indices,/* binding 7: rendMatIndexBuffer */
+    const anerend_light_t* lights, uint32_t num_lights);
+
+/* Binding 0 (scene_ubo.glsl:14-37).  Fields read: cameraPos, lightDir, skyColor, sunIntensity,
+ * skyIntensity, flags (DDGI, DDGI_MULTI, RT_ON, BAKE_MODE_ON). */
+int anerend_cuda_ddgi_set_scene_ubo(anerend_ddgi_t* h, const anerend_scene_ubo_t* ubo);
+
+/* Replaces tlas_update.comp + the TLAS/BLAS builds (UpdateTLASPass.cpp:128-248, VulkanRenderer.cpp:1267-1417):
+ * instance selection (visible bit set, cull bit clear), flatten to world-space triangles, LBVH, BVH8. */
+int anerend_cuda_ddgi_build_accel(anerend_ddgi_t* h);
+/* Moving nodes: new renderable buffer (same count, same visibility) -> re-flatten + bottom-up refit.
+ * renderables may be NULL to refit with the current buffer.  `_device` takes a device pointer (the
+ * reference's RenderableBuffer is GPU-written earlier in the frame, cull.comp:303). */
+int anerend_cuda_ddgi_refit_accel(anerend_ddgi_t* h, const anerend_renderable_t* renderables, uint32_t num_renderables);
+int anerend_cuda_ddgi_refit_accel_device(anerend_ddgi_t* h, const void* d_renderables, uint32_t num_renderables);
+int anerend_cuda_ddgi_get_bvh_info(anerend_ddgi_t* h, anerend_ddgi_bvh_info_t* out);
+/* Debug/validation: copies the BVH8 nodes (num_nodes*80 B) and traversal triangles (num_triangles*48 B). */
+int anerend_cuda_ddgi_download_bvh(anerend_ddgi_t* h, void* nodes, size_t nodes_bytes, void* tris, size_t tris_bytes);
+
+/* ---- the three passes ------------------------------------------------------------------- */
+
+/* "IrradianceProbeTrans" exe (IrradianceProbeTranslationPass.cpp:56-186).  Reads cameraPos from the UBO,
+ * keeps _lastProbeIdx in the handle.  No-op when DDGI is off or bake mode is on. */
+int anerend_cuda_ddgi_translate(anerend_ddgi_t* h);
+/* "IrradianceProbeRT" exe for one layer (IrradianceProbeRayTracingPass.cpp:95-165 + rgen/rchit/rmiss):
+ * rot = the push-constant `randomRot` (column-major mat4).  Reads the current atlas (multi-bounce). */
+int anerend_cuda_ddgi_trace_layer(anerend_ddgi_t* h, int32_t layer, const float rot[16]);
+/* "IrradianceProbeConvolve" exe for one layer (IrradianceProbeConvolvePass.cpp:109-143 + probe_conv.comp). */
+int anerend_cuda_ddgi_convolve_layer(anerend_ddgi_t* h, int32_t layer);
+/* layer >= 0: trace_layer + convolve_layer (one reference execution).
+ * layer  < 0: full-grid update of layers [slab_begin, slab_end): every layer is traced against the SAME
+ *             previous atlas, then all are convolved ("jacobi" mode); rots = num_probes_y matrices,
+ *             indexed by absolute layer. */
+int anerend_cuda_ddgi_update(anerend_ddgi_t* h, int32_t layer, const float* rots);
+/* One frame at the reference's cadence: translate, trace+convolve layer `_currentLayer`, advance it
+ * (IrradianceProbeRayTracingPass.cpp:112,158-164).  *layer_out receives blackboard "ProbeLayer". */
+int anerend_cuda_ddgi_frame(anerend_ddgi_t* h, const float rot[16], int32_t* layer_out);
+
+/* ---- results / state -------------------------------------------------------------------- */
+
+int anerend_cuda_ddgi_atlas_dims(const anerend_ddgi_t* h, int32_t* width, int32_t* height);
+/* "ProbeRaysConvTex" as row-major RGBA16F, width*height*8 bytes (mirrors downloadDDGIAtlas,
+ * VulkanRenderer.cpp:2706-2771). */
+int anerend_cuda_ddgi_download_atlas(anerend_ddgi_t* h, void* rgba16f, size_t bytes);
+int anerend_cuda_ddgi_upload_atlas(anerend_ddgi_t* h, const void* rgba16f, size_t bytes);
+/* Device pointer of the atlas for consumers on the same device (deferred lighting, NCCL all-gather of slabs).
+ * Rows [10*nXZ*slab_begin, 10*nXZ*slab_end) are the rows this handle writes. */
+int anerend_cuda_ddgi_atlas_device_ptr(anerend_ddgi_t* h, void** d_ptr, size_t* bytes);
+/* Fused atlas all-gather: device pointers to the peers' atlases (cudaIpc-opened or P2P-enabled).  When set,
+ * the convolution stores every finished texel into all peers as well, replacing the separate collective. */
+int anerend_cuda_ddgi_set_peer_atlases(anerend_ddgi_t* h, void* const* d_peers, uint32_t num_peers);
+/* CUDA stream (cudaStream_t) all work of this handle is issued on. */
+int anerend_cuda_ddgi_stream(anerend_ddgi_t* h, void** stream);
+
+/* "ProbeRaysIrrTex"/"ProbeRaysDirTex" of the last trace of `layer`, in the reference's image layout:
+ * (S_x*nXZ) x (S_y*nXZ) RGBA16F, pixel (probeX*S_x+px, probeZ*S_y+py), rayIndex = py*S_x+px  (rgen:51-58). */
+int anerend_cuda_ddgi_ray_tile(const anerend_ddgi_t* h, int32_t* sx, int32_t* sy);
+int anerend_cuda_ddgi_download_rays(anerend_ddgi_t* h, int32_t layer, void* irr_rgba16f, void* dir_rgba16f, size_t bytes_each);
+/* nXZ*nXZ*rays records, index (probeZ*nXZ+probeX)*rays + rayIndex.  Needs FLAG_RAY_RECORDS. */
+int anerend_cuda_ddgi_download_ray_records(anerend_ddgi_t* h, int32_t layer, anerend_ddgi_ray_record_t* out, size_t count);
+/* fp32 RGBA per atlas texel (same addressing as the atlas) of the last convolution.  Needs FLAG_TEXEL_RECORDS. */
+int anerend_cuda_ddgi_download_texel_records(anerend_ddgi_t* h, float* rgba32f, size_t bytes);
+
+int anerend_cuda_ddgi_get_timings(anerend_ddgi_t* h, anerend_ddgi_timings_t* out);
+int anerend_cuda_ddgi_get_stats(anerend_ddgi_t* h, anerend_ddgi_stats_t* out);
+int anerend_cuda_ddgi_reset_stats(anerend_ddgi_t* h);
+
+/* ---- host helpers shared by pass code --------------------------------------------------- */
+
+/* randomRot = glm::rotate(mat4(1), radians(angle_deg), axis∈{0:x,1:y,2:z})
+ * (IrradianceProbeRayTracingPass.cpp:115-133; glm/ext/matrix_transform.inl:18-46). Column-major. */
+int anerend_cuda_ddgi_make_rotation(int32_t axis, float angle_deg, float out[16]);
+/* worldDirFromFibonacciIndex for i in [0,n) (rgen:35-46); out = n*3 floats.  The same host table is what the
+ * kernels consume, so directions do not depend on device sin/cos range reduction. */
+int anerend_cuda_ddgi_fibonacci_dirs(int32_t n, float* out);
+const char* anerend_cuda_ddgi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

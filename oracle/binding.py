@@ -1,0 +1,131 @@
+"""ctypes binding of the CPU oracle (oracle/ddgi_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  Nothing under anerend_b200/ imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from anerend_b200.capi import DdgiHandle, make_params  # generic prefix-agnostic wrapper (product -> oracle never)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    """Compile liboracle with the committed Makefile (g++ only; no dependency on /root/reference)."""
+    so = os.path.join(_HERE, "libddgi_oracle.so")
+    src = os.path.join(_HERE, "ddgi_oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s", "libddgi_oracle.so"],
+                              stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.ddgi_oracle_half_to_float.restype = C.c_float
+        _LIB.ddgi_oracle_half_to_float.argtypes = [C.c_uint16]
+        _LIB.ddgi_oracle_float_to_half.restype = C.c_uint16
+        _LIB.ddgi_oracle_float_to_half.argtypes = [C.c_float]
+    return _LIB
+
+
+class Oracle(DdgiHandle):
+    def __init__(self, params):
+        super().__init__(lib(), "ddgi_oracle_", params)
+
+    def set_threads(self, n):
+        return self._fn("set_threads")(self._h, C.c_int32(n))
+
+    def set_brute_force(self, on):
+        self._call("set_brute_force", C.c_int32(1 if on else 0))
+
+    def set_rays(self, layer, irr, dr):
+        irr = np.ascontiguousarray(irr, np.uint16)
+        dr = np.ascontiguousarray(dr, np.uint16)
+        self._call("set_rays", C.c_int32(layer), irr.ctypes.data_as(C.c_void_p), dr.ctypes.data_as(C.c_void_p),
+                   C.c_size_t(irr.nbytes))
+
+    def world_triangles(self):
+        n = self.bvh_info().num_triangles
+        out = np.empty((n, 3, 3), np.float32)
+        self._call("download_world_triangles", out.ctypes.data_as(C.c_void_p), C.c_size_t(n))
+        return out
+
+    def calc_indirect(self, normal, albedo, metallic, roughness, world_pos, view_pos):
+        f3 = lambda v: (C.c_float * 3)(*[float(x) for x in v])
+        out = (C.c_float * 3)()
+        self._call("calc_indirect", f3(normal), f3(albedo), C.c_float(metallic), C.c_float(roughness), f3(world_pos),
+                   f3(view_pos), out)
+        return np.array(out[:], np.float32)
+
+
+# ---- single shader functions (KATs) ----------------------------------------------------------------
+def _f(n, v):
+    return (C.c_float * n)(*[float(x) for x in v])
+
+
+def oct_encode(v):
+    out = (C.c_float * 2)()
+    lib().ddgi_oracle_oct_encode(_f(3, v), out)
+    return np.array(out[:], np.float32)
+
+
+def oct_decode(o):
+    out = (C.c_float * 3)()
+    lib().ddgi_oracle_oct_decode(_f(2, o), out)
+    return np.array(out[:], np.float32)
+
+
+def to_linear(c):
+    out = (C.c_float * 3)()
+    lib().ddgi_oracle_to_linear(_f(3, c), out)
+    return np.array(out[:], np.float32)
+
+
+def fibonacci_dirs(n):
+    out = np.empty((n, 3), np.float32)
+    lib().ddgi_oracle_fibonacci_dirs(C.c_int32(n), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def make_rotation(axis, deg):
+    out = np.empty(16, np.float32)
+    rc = lib().ddgi_oracle_make_rotation(C.c_int32(axis), C.c_float(deg), out.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return out
+
+
+def float_to_half(f):
+    return int(lib().ddgi_oracle_float_to_half(C.c_float(f)))
+
+
+def half_to_float(h):
+    return float(lib().ddgi_oracle_half_to_float(C.c_uint16(h)))
+
+
+def calc_light(normal, albedo, metallic, roughness, world_pos, view_pos, light_dir, sun_intensity, light=None):
+    out = (C.c_float * 3)()
+    lp = None
+    directional = 1
+    if light is not None:
+        arr = np.ascontiguousarray(light)
+        lp = arr.ctypes.data_as(C.c_void_p)
+        directional = 0
+    lib().ddgi_oracle_calc_light(_f(3, normal), _f(3, albedo), C.c_float(metallic), C.c_float(roughness),
+                                 _f(3, world_pos), _f(3, view_pos), lp, C.c_int32(directional), _f(3, light_dir),
+                                 C.c_float(sun_intensity), out)
+    return np.array(out[:], np.float32)
+
+
+def intersect(orig, d, v0, v1, v2, tmin=0.1, tmax=50.0):
+    t, u, v = C.c_float(), C.c_float(), C.c_float()
+    hit = lib().ddgi_oracle_intersect(_f(3, orig), _f(3, d), _f(3, v0), _f(3, v1), _f(3, v2), C.c_float(tmin),
+                                      C.c_float(tmax), C.byref(t), C.byref(u), C.byref(v))
+    return bool(hit), t.value, u.value, v.value

@@ -1,0 +1,93 @@
+/*
+ * ddgi_oracle.h — C API of the CPU oracle for the DDGI probe-update path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  The oracle is a CPU restatement (multithreaded C++17) of the reference's
+ * shaders and pass code; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load it.  The product (anerend_b200/) never links, imports or calls anything in oracle/.
+ *
+ * PARITY UNPINNED: the reference holds no golden vectors, tests or CPU path for this chain,
+ * and its ray/triangle intersection lives in the Vulkan driver.  The oracle is pinned instead by known-answer
+ * tests derived from the shader formulas (tests/test_oracle_kat.py).
+ *
+ * The API mirrors include/anerend_cuda_ddgi.h one to one (same parameter struct, same buffer formats), so a
+ * parity test drives both sides with identical calls.
+ */
+#ifndef DDGI_ORACLE_H
+#define DDGI_ORACLE_H
+
+#include "../include/anerend_cuda_ddgi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ddgi_oracle ddgi_oracle_t;
+
+int ddgi_oracle_create(const anerend_ddgi_params_t* params, ddgi_oracle_t** out);
+int ddgi_oracle_destroy(ddgi_oracle_t* h);
+int ddgi_oracle_reset(ddgi_oracle_t* h);
+const char* ddgi_oracle_last_error(const ddgi_oracle_t* h);
+/* 0 = hardware_concurrency(); returns the thread count in use. */
+int ddgi_oracle_set_threads(ddgi_oracle_t* h, int32_t n);
+/* 1 = brute-force ray/triangle loops instead of the oracle's own BVH (validates that BVH). */
+int ddgi_oracle_set_brute_force(ddgi_oracle_t* h, int32_t on);
+
+int ddgi_oracle_upload_scene(ddgi_oracle_t* h,
+    const anerend_vertex_t* vertices, uint32_t num_vertices,
+    const uint32_t* indices, uint32_t num_indices,
+    const anerend_mesh_info_t* meshes, const uint32_t* mesh_num_indices, uint32_t num_meshes,
+    const anerend_material_info_t* materials, uint32_t num_materials,
+    const anerend_renderable_t* renderables, uint32_t num_renderables,
+    const uint32_t* model_indices, uint32_t num_model_indices,
+    const uint32_t* material_indices, uint32_t num_material_indices,
+    const anerend_light_t* lights, uint32_t num_lights);
+int ddgi_oracle_set_scene_ubo(ddgi_oracle_t* h, const anerend_scene_ubo_t* ubo);
+int ddgi_oracle_build_accel(ddgi_oracle_t* h);
+int ddgi_oracle_refit_accel(ddgi_oracle_t* h, const anerend_renderable_t* renderables, uint32_t num_renderables);
+int ddgi_oracle_get_bvh_info(ddgi_oracle_t* h, anerend_ddgi_bvh_info_t* out);
+/* World-space flattened triangles, 9 floats each (v0, v1, v2), in global triangle-id order. */
+int ddgi_oracle_download_world_triangles(ddgi_oracle_t* h, float* out, size_t count);
+
+int ddgi_oracle_translate(ddgi_oracle_t* h);
+int ddgi_oracle_trace_layer(ddgi_oracle_t* h, int32_t layer, const float rot[16]);
+int ddgi_oracle_convolve_layer(ddgi_oracle_t* h, int32_t layer);
+int ddgi_oracle_update(ddgi_oracle_t* h, int32_t layer, const float* rots);
+int ddgi_oracle_frame(ddgi_oracle_t* h, const float rot[16], int32_t* layer_out);
+
+int ddgi_oracle_atlas_dims(const ddgi_oracle_t* h, int32_t* width, int32_t* height);
+int ddgi_oracle_download_atlas(ddgi_oracle_t* h, void* rgba16f, size_t bytes);
+int ddgi_oracle_upload_atlas(ddgi_oracle_t* h, const void* rgba16f, size_t bytes);
+int ddgi_oracle_ray_tile(const ddgi_oracle_t* h, int32_t* sx, int32_t* sy);
+int ddgi_oracle_download_rays(ddgi_oracle_t* h, int32_t layer, void* irr_rgba16f, void* dir_rgba16f, size_t bytes_each);
+int ddgi_oracle_download_ray_records(ddgi_oracle_t* h, int32_t layer, anerend_ddgi_ray_record_t* out, size_t count);
+int ddgi_oracle_download_texel_records(ddgi_oracle_t* h, float* rgba32f, size_t bytes);
+int ddgi_oracle_get_stats(ddgi_oracle_t* h, anerend_ddgi_stats_t* out);
+int ddgi_oracle_reset_stats(ddgi_oracle_t* h);
+
+/* Convolution alone (BASELINE config 1): radiance/direction images supplied by the caller in the reference's
+ * image layout (RGBA16F, (S_x*nXZ) x (S_y*nXZ)), then probe_conv.comp over `layer`. */
+int ddgi_oracle_set_rays(ddgi_oracle_t* h, int32_t layer, const void* irr_rgba16f, const void* dir_rgba16f, size_t bytes_each);
+
+/* ---- single shader functions, exported for the known-answer tests ------------------------ */
+int  ddgi_oracle_make_rotation(int32_t axis, float angle_deg, float out[16]);          /* glm::rotate */
+int  ddgi_oracle_fibonacci_dirs(int32_t n, float* out);                                /* rgen:35-46 */
+void ddgi_oracle_oct_encode(const float v[3], float out[2]);                           /* octahedron_helpers.glsl:10-20 */
+void ddgi_oracle_oct_decode(const float o[2], float out[3]);                           /* octahedron_helpers.glsl:25-34 */
+void ddgi_oracle_to_linear(const float srgb[3], float out[3]);                         /* bindless.glsl:240-247 */
+uint16_t ddgi_oracle_float_to_half(float f);
+float    ddgi_oracle_half_to_float(uint16_t h);
+/* calcLight (pbr_light.glsl:98-166). directional=1: sun from light_dir/sun_intensity; 0: `light`. */
+void ddgi_oracle_calc_light(const float normal[3], const float albedo[3], float metallic, float roughness,
+                            const float world_pos[3], const float view_pos[3], const anerend_light_t* light,
+                            int32_t directional, const float light_dir[3], float sun_intensity, float out[3]);
+/* calcIndirectDiffuseLight against the handle's current atlas/UBO (pbr_light.glsl:365-388). */
+int  ddgi_oracle_calc_indirect(ddgi_oracle_t* h, const float normal[3], const float albedo[3], float metallic,
+                               float roughness, const float world_pos[3], const float view_pos[3], float out[3]);
+/* Möller–Trumbore exactly as DESIGN.md specifies; returns 1 on hit with t in (tmin,tmax). */
+int  ddgi_oracle_intersect(const float orig[3], const float dir[3], const float v0[3], const float v1[3],
+                           const float v2[3], float tmin, float tmax, float* t, float* u, float* v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
