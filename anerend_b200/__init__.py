@@ -58,12 +58,3 @@ class Ddgi(DdgiHandle):
 
     def refit_accel_device(self, d_ptr, count):
         self._call("refit_accel_device", _C.c_void_p(d_ptr), _C.c_uint32(count))
-
-    def download_bvh(self):
-        import numpy as np
-        info = self.bvh_info()
-        nodes = np.empty(info.num_nodes * info.node_bytes, np.uint8)
-        tris = np.empty(info.num_triangles * info.tri_bytes, np.uint8)
-        self._call("download_bvh", nodes.ctypes.data_as(_C.c_void_p), _C.c_size_t(nodes.nbytes),
-                   tris.ctypes.data_as(_C.c_void_p), _C.c_size_t(tris.nbytes))
-        return nodes, tris

@@ -1,8 +1,8 @@
 """ctypes binding of the anerend_cuda_ddgi_* C ABI (include/anerend_cuda_ddgi.h).
 
-`DdgiHandle` is prefix-generic: the CPU oracle (test infrastructure, oracle/binding.py) exports the same
-functions under `ddgi_oracle_*`, so parity tests drive both sides with identical calls.  The product
-itself never touches the oracle: `anerend_b200.Ddgi` always binds libanerend_cuda_ddgi.so.
+`DdgiHandle` is prefix-generic (library handle + symbol prefix are constructor arguments), so the test
+infrastructure can drive a second implementation of the same ABI with identical calls.  The product
+itself only ever binds its own library: `anerend_b200.Ddgi` always binds libanerend_cuda_ddgi.so.
 """
 import ctypes as C
 import numpy as np
@@ -205,6 +205,14 @@ class DdgiHandle:
         out = np.empty((self.atlas_height, self.atlas_width, 4), np.float32)
         self._call("download_texel_records", _ptr(out), C.c_size_t(out.nbytes))
         return out
+
+    def download_bvh(self):
+        """(nodes uint8[num_nodes*80], tris uint8[num_triangles*48]) — the BVH8 exactly as the traversal kernel reads it."""
+        info = self.bvh_info()
+        nodes = np.empty(info.num_nodes * info.node_bytes, np.uint8)
+        tris = np.empty(info.num_triangles * info.tri_bytes, np.uint8)
+        self._call("download_bvh", _ptr(nodes), C.c_size_t(nodes.nbytes), _ptr(tris), C.c_size_t(tris.nbytes))
+        return nodes, tris
 
     def stats(self):
         s = Stats()

@@ -1,0 +1,610 @@
+// ddgi_api.cu — the C ABI (include/anerend_cuda_ddgi.h) and the host side of the three passes.
+//
+// Host-side restatement of the reference's pass code:
+//   IrradianceProbeTranslationPass.cpp:56-186  -> translate()
+//   IrradianceProbeRayTracingPass.cpp:95-165   -> traceLayers()   (+ rgen/rchit/rmiss in ddgi_kernels.cuh)
+//   IrradianceProbeConvolvePass.cpp:109-143    -> convolveLayers() (+ probe_conv.comp)
+//   tlas_update.comp:37-99 instance selection  -> selectInstances()
+// Compiled by nvcc into libanerend_cuda_ddgi.so.  (With -DDDGI_HOST_EMU the same file builds the serial debug
+// harness under tests/host_emu/, exported as anerend_emu_ddgi_*; it is never part of the product library.)
+#include "ddgi_launch.h"
+
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+using namespace ddgi;
+
+// ------------------------------------------------------------------------------------------------ kernels
+DDGI_KERNEL(k_inst_xform, inst_xform_body, BuildCtx)
+DDGI_KERNEL(k_flatten_scene, flatten_tri_body, BuildCtx)
+DDGI_KERNEL(k_morton_codes, morton_body, BuildCtx)
+DDGI_KERNEL(k_lbvh_hierarchy, karras_body, BuildCtx)
+DDGI_KERNEL(k_lbvh_fit, fit_body, BuildCtx)
+DDGI_KERNEL(k_bvh8_collapse, collapse_body, BuildCtx)
+DDGI_KERNEL(k_refit_tris, refit_tris_body, BuildCtx)
+DDGI_KERNEL(k_refit_nodes, refit_node_body, BuildCtx)
+DDGI_KERNEL(k_probe_trace, trace_ray_body<false>, TraceCtx)
+DDGI_KERNEL(k_probe_trace_counted, trace_ray_body<true>, TraceCtx)
+DDGI_KERNEL(k_probe_convolve, conv_texel_body, ConvCtx)
+DDGI_KERNEL(k_probe_translate, translate_body, TransCtx)
+DDGI_KERNEL(k_atlas_clear, clear_body, ClearCtx)
+
+// ------------------------------------------------------------------------------------------------ handle
+struct anerend_ddgi {
+  anerend_ddgi_params_t p{};
+  Backend be;
+  std::string err;
+  int nXZ = 0, nY = 0, N = 0, Sx = 0, Sy = 0, W = 0, H = 0, P = 0;
+
+  // host copies needed for instance selection
+  std::vector<anerend_renderable_t> renderables;
+  std::vector<anerend_mesh_info_t> meshes;
+  std::vector<uint32_t> meshNumIndices, modelIdx, matIdx;
+  std::vector<DInstance> instances;
+  uint32_t numVertices = 0, numIndices = 0, numMaterials = 0, numLights = 0;
+  anerend_scene_ubo_t ubo{};
+  bool haveScene = false, haveUbo = false, haveAccel = false;
+
+  // device scene
+  anerend_vertex_t* dVertices = nullptr; uint32_t* dIndices = nullptr; anerend_material_info_t* dMaterials = nullptr;
+  anerend_renderable_t* dRenderables = nullptr; anerend_light_t* dLights = nullptr;
+  DInstance* dInstances = nullptr; InstXform* dXforms = nullptr; uint32_t* dTriInstance = nullptr;
+  // acceleration structure
+  uint32_t numTris = 0, numNodes = 0, bvhDepth = 0;
+  float4* dWtri = nullptr; float4* dTriLo = nullptr; float4* dTriHi = nullptr; int* dSceneBounds = nullptr;
+  uint4* dNodes = nullptr; float4* dBvhTris = nullptr; uint32_t* dNodeParent = nullptr; float4* dNodeLo = nullptr; float4* dNodeHi = nullptr;
+  uint32_t* dNodePending = nullptr; uint32_t* dVisit = nullptr; uint32_t* dCounters = nullptr;
+  float boundsMin[3] = {0, 0, 0}, boundsMax[3] = {0, 0, 0};
+
+  // pass resources
+  uint2* dAtlas = nullptr; uint2* dTemp = nullptr;        // ProbeRaysConvTex, TempProbeTex
+  uint2* dRayIrr = nullptr;                                // ProbeRaysIrrTex for all layers, linear [layer][probe][ray]
+  float4* dDirs = nullptr; float4* hDirs = nullptr;        // [nY][N] rotated directions (ProbeRaysDirTex is derived from it)
+  uint16_t* dRayOrder = nullptr;
+  anerend_ddgi_ray_record_t* dRecords = nullptr; float4* dTexelRecords = nullptr; unsigned long long* dStats = nullptr;
+  std::vector<float> fib;                                  // N*3
+  std::vector<uint8_t> layerTraced;
+  uint2* peers[8] = {nullptr}; int numPeers = 0;
+
+  int currentLayer = 0;                                    // IrradianceProbeRayTracingPass::_currentLayer
+  int lastProbeIdx[2] = {0, 0};                            // IrradianceProbeTranslationPass::_lastProbeIdx
+  anerend_ddgi_timings_t timings{};
+  bool timed[4] = {false, false, false, false};
+  float accelMs = 0.0f;
+};
+
+namespace {
+
+int fail(anerend_ddgi* h, int code, const std::string& msg) { h->err = msg; return code; }
+#define BE_CHECK(h, expr) do { if (!(expr)) return fail((h), ANEREND_DDGI_E_CUDA, std::string(#expr ": ") + (h)->be.errStr()); } while (0)
+
+int rayTile(int n, int& sx, int& sy) { sx = 1; while (sx * sx < n) sx *= 2; sy = n / sx; return (sx * sy == n) ? 0 : -1; }
+
+// rgen:35-46 worldDirFromFibonacciIndex, evaluated once on the host in fp32
+void fibonacciDir(uint32_t idx, uint32_t n, float out[3]) {
+  const float PI = 3.14159265359f, GOLDEN_RATIO = 1.6180339887f;
+  float theta = 2.0f * PI * float(idx) / GOLDEN_RATIO;
+  float phi = acosf(1.0f - 2.0f * (float(idx) + 0.5f) / float(n));
+  float x = cosf(theta) * sinf(phi), y = sinf(theta) * sinf(phi), z = cosf(phi);
+  float inv = 1.0f / sqrtf(x * x + y * y + z * z);
+  out[0] = x * inv; out[1] = y * inv; out[2] = z * inv;
+}
+
+bool ddgiOn(const anerend_ddgi* h) {   // IrradianceProbeRayTracingPass.cpp:97-98 via the UBO flags (VulkanRenderer.cpp:1222-1232)
+  return (h->ubo.flags & ANEREND_UBO_RT_ON_FLAG) && (h->ubo.flags & ANEREND_UBO_DDGI_FLAG);
+}
+
+// tlas_update.comp:37-99: which (renderable, mesh) pairs enter the acceleration structure, in renderable order
+int selectInstances(anerend_ddgi* h, std::vector<DInstance>& out, uint32_t& numTris) {
+  out.clear(); numTris = 0;
+  for (uint32_t idx = 0; idx < h->renderables.size(); ++idx) {
+    const anerend_renderable_t& r = h->renderables[idx];
+    bool visible = (r.visible & 1u) != 0, culled = ((r.visible >> 1) & 1u) != 0;
+    if (!visible || culled) continue;
+    for (uint32_t i = 0; i < r.num_meshes; ++i) {
+      if (r.model_offset + i >= h->modelIdx.size()) return fail(h, ANEREND_DDGI_E_INVALID, "model index out of range");
+      uint32_t meshIndex = h->modelIdx[r.model_offset + i];
+      if (r.first_material_index + i >= h->matIdx.size()) return fail(h, ANEREND_DDGI_E_INVALID, "material index out of range");
+      uint32_t matIndex = h->matIdx[r.first_material_index + i];
+      if (r.dynamic_model_offset > 0) {
+        if (r.dynamic_model_offset + i >= h->modelIdx.size()) return fail(h, ANEREND_DDGI_E_INVALID, "dynamic model index out of range");
+        meshIndex = h->modelIdx[r.dynamic_model_offset + i];
+      }
+      uint32_t custom = (matIndex & ~(0x3FFFu << 10)) | ((meshIndex & 0x3FFFu) << 10);   // 10 bits material | 14 bits mesh
+      DInstance in{};
+      in.renderable = idx; in.material = custom & 0x3FFu; in.mesh = (custom >> 10) & 0x3FFFu;
+      if (in.mesh >= h->meshes.size() || in.material >= h->numMaterials) return fail(h, ANEREND_DDGI_E_INVALID, "mesh/material id out of range");
+      in.firstTri = numTris; in.numTris = h->meshNumIndices[in.mesh] / 3;
+      in.vertexOffset = h->meshes[in.mesh].vertex_offset; in.indexOffset = h->meshes[in.mesh].index_offset;
+      if ((uint64_t)in.indexOffset + 3ull * in.numTris > h->numIndices) return fail(h, ANEREND_DDGI_E_INVALID, "mesh indices out of range");
+      numTris += in.numTris; out.push_back(in);
+    }
+  }
+  return 0;
+}
+
+BuildCtx buildCtx(anerend_ddgi* h) {
+  BuildCtx c{};
+  c.vertices = h->dVertices; c.indices = h->dIndices; c.renderables = h->dRenderables;
+  c.instances = h->dInstances; c.xforms = h->dXforms; c.triInstance = h->dTriInstance;
+  c.numTris = h->numTris; c.numInstances = (uint32_t)h->instances.size();
+  c.wtri = h->dWtri; c.triLo = h->dTriLo; c.triHi = h->dTriHi; c.sceneBounds = h->dSceneBounds;
+  c.nodes = h->dNodes; c.bvhTris = h->dBvhTris; c.nodeParent = h->dNodeParent; c.nodeLo = h->dNodeLo; c.nodeHi = h->dNodeHi;
+  c.nodePending = h->dNodePending; c.visit = h->dVisit; c.counters = h->dCounters;
+  return c;
+}
+
+void freeAccel(anerend_ddgi* h) {
+  Backend& be = h->be;
+  be.free(h->dInstances); be.free(h->dXforms); be.free(h->dTriInstance); be.free(h->dWtri); be.free(h->dTriLo); be.free(h->dTriHi);
+  be.free(h->dNodes); be.free(h->dBvhTris); be.free(h->dNodeParent); be.free(h->dNodeLo); be.free(h->dNodeHi); be.free(h->dNodePending); be.free(h->dVisit);
+  h->dInstances = nullptr; h->dXforms = nullptr; h->dTriInstance = nullptr; h->dWtri = nullptr; h->dTriLo = nullptr; h->dTriHi = nullptr;
+  h->dNodes = nullptr; h->dBvhTris = nullptr; h->dNodeParent = nullptr; h->dNodeLo = nullptr; h->dNodeHi = nullptr; h->dNodePending = nullptr; h->dVisit = nullptr;
+  h->haveAccel = false; h->numTris = 0; h->numNodes = 0;
+}
+void freeScene(anerend_ddgi* h) {
+  Backend& be = h->be;
+  be.free(h->dVertices); be.free(h->dIndices); be.free(h->dMaterials); be.free(h->dRenderables); be.free(h->dLights);
+  h->dVertices = nullptr; h->dIndices = nullptr; h->dMaterials = nullptr; h->dRenderables = nullptr; h->dLights = nullptr;
+  h->haveScene = false;
+}
+
+int clearAtlas(anerend_ddgi* h) {
+  ClearCtx c{h->dAtlas, h->dTemp};
+  DDGI_LAUNCH(h->be, k_atlas_clear, clear_body, (uint32_t)(h->W * h->H), c, 256);
+  if (h->dTexelRecords) BE_CHECK(h, h->be.zero(h->dTexelRecords, (size_t)h->W * h->H * sizeof(float4)));
+  BE_CHECK(h, h->be.check());
+  return 0;
+}
+
+// flatten + LBVH + BVH8 collapse
+int buildAccel(anerend_ddgi* h) {
+  Backend& be = h->be;
+  freeAccel(h);
+  std::vector<DInstance> inst; uint32_t n = 0;
+  int rc = selectInstances(h, inst, n); if (rc) return rc;
+  h->instances = inst; h->numTris = n;
+  const uint32_t ni = (uint32_t)inst.size();
+  BE_CHECK(h, be.alloc(&h->dInstances, ni)); BE_CHECK(h, be.alloc(&h->dXforms, ni)); BE_CHECK(h, be.alloc(&h->dTriInstance, n));
+  BE_CHECK(h, be.h2d(h->dInstances, inst.data(), ni * sizeof(DInstance)));
+  { std::vector<uint32_t> ti(n); for (uint32_t i = 0; i < ni; ++i) for (uint32_t t = 0; t < inst[i].numTris; ++t) ti[inst[i].firstTri + t] = i;
+    BE_CHECK(h, be.h2d(h->dTriInstance, ti.data(), n * sizeof(uint32_t))); BE_CHECK(h, be.sync()); }
+  if (n == 0) { h->numNodes = 0; h->bvhDepth = 0; h->haveAccel = true; return 0; }
+  const uint32_t nodeCap = n;   // every BVH8 node has >= 4 triangles below it and >= 2 children
+  BE_CHECK(h, be.alloc(&h->dWtri, 3 * (size_t)n)); BE_CHECK(h, be.alloc(&h->dTriLo, n)); BE_CHECK(h, be.alloc(&h->dTriHi, n));
+  BE_CHECK(h, be.alloc(&h->dNodes, 5 * (size_t)nodeCap)); BE_CHECK(h, be.alloc(&h->dBvhTris, 3 * (size_t)n));
+  BE_CHECK(h, be.alloc(&h->dNodeParent, nodeCap)); BE_CHECK(h, be.alloc(&h->dNodeLo, nodeCap)); BE_CHECK(h, be.alloc(&h->dNodeHi, nodeCap));
+  BE_CHECK(h, be.alloc(&h->dNodePending, nodeCap)); BE_CHECK(h, be.alloc(&h->dVisit, (size_t)n + 1));
+  // build-only scratch
+  uint32_t *keys = nullptr, *ids = nullptr, *skeys = nullptr, *sids = nullptr, *left = nullptr, *right = nullptr, *parent = nullptr, *rf = nullptr, *rl = nullptr;
+  float4 *blo = nullptr, *bhi = nullptr; CItem *qa = nullptr, *qb = nullptr;
+  BE_CHECK(h, be.alloc(&keys, n)); BE_CHECK(h, be.alloc(&ids, n)); BE_CHECK(h, be.alloc(&skeys, n)); BE_CHECK(h, be.alloc(&sids, n));
+  BE_CHECK(h, be.alloc(&left, n)); BE_CHECK(h, be.alloc(&right, n)); BE_CHECK(h, be.alloc(&parent, 2 * (size_t)n)); BE_CHECK(h, be.alloc(&rf, n)); BE_CHECK(h, be.alloc(&rl, n));
+  BE_CHECK(h, be.alloc(&blo, 2 * (size_t)n)); BE_CHECK(h, be.alloc(&bhi, 2 * (size_t)n)); BE_CHECK(h, be.alloc(&qa, n)); BE_CHECK(h, be.alloc(&qb, n));
+  auto freeScratch = [&]() { be.free(keys); be.free(ids); be.free(skeys); be.free(sids); be.free(left); be.free(right); be.free(parent); be.free(rf); be.free(rl);
+                             be.free(blo); be.free(bhi); be.free(qa); be.free(qb); };
+  int initBounds[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+  BE_CHECK(h, be.h2d(h->dSceneBounds, initBounds, sizeof(initBounds)));
+  BuildCtx c = buildCtx(h);
+  c.mortonKeys = keys; c.triIds = ids; c.sortedKeys = skeys; c.sortedIds = sids; c.left = left; c.right = right; c.parent = parent;
+  c.rangeFirst = rf; c.rangeLast = rl; c.blo = blo; c.bhi = bhi;
+  be.mark(4);
+  DDGI_LAUNCH(be, k_inst_xform, inst_xform_body, ni, c, 128);
+  DDGI_LAUNCH(be, k_flatten_scene, flatten_tri_body, n, c, 256);
+  DDGI_LAUNCH(be, k_morton_codes, morton_body, n, c, 256);
+  if (!be.sortPairs(keys, skeys, ids, sids, n)) { freeScratch(); return fail(h, ANEREND_DDGI_E_CUDA, std::string("radix sort: ") + be.errStr()); }
+  BE_CHECK(h, be.zero(h->dVisit, ((size_t)n + 1) * sizeof(uint32_t)));
+  if (n > 1) DDGI_LAUNCH(be, k_lbvh_hierarchy, karras_body, n - 1, c, 256);
+  DDGI_LAUNCH(be, k_lbvh_fit, fit_body, n, c, 256);
+  // collapse, one launch per BVH8 level
+  uint32_t counters[3] = {1u, 0u, 0u};
+  BE_CHECK(h, be.h2d(h->dCounters, counters, sizeof(counters)));
+  CItem root; root.ref = 0u; root.node = 0u;
+  BE_CHECK(h, be.h2d(qa, &root, sizeof(root)));
+  uint32_t missParent = DDGI_MISS;
+  BE_CHECK(h, be.h2d(h->dNodeParent, &missParent, sizeof(uint32_t)));
+  uint32_t qlen = 1, depth = 0;
+  while (qlen > 0) {
+    uint32_t zero = 0; BE_CHECK(h, be.h2d(h->dCounters + 2, &zero, sizeof(uint32_t)));
+    c.qin = qa; c.qout = qb;
+    DDGI_LAUNCH(be, k_bvh8_collapse, collapse_body, qlen, c, 64);
+    if (!be.check() || !be.d2h(counters, h->dCounters, sizeof(counters))) { freeScratch(); return fail(h, ANEREND_DDGI_E_CUDA, std::string("bvh8 collapse: ") + be.errStr()); }
+    qlen = counters[2]; std::swap(qa, qb); ++depth;
+    if (depth > 1000) break;
+  }
+  be.mark(5);
+  int bounds[6];
+  bool okc = be.d2h(bounds, h->dSceneBounds, sizeof(bounds));
+  freeScratch();
+  if (!okc) return fail(h, ANEREND_DDGI_E_CUDA, std::string("build: ") + be.errStr());
+  for (int k = 0; k < 3; ++k) { h->boundsMin[k] = ordered_to_float(bounds[k]); h->boundsMax[k] = ordered_to_float(bounds[3 + k]); }
+  h->numNodes = counters[0]; h->bvhDepth = depth;
+  if (counters[1] != n) return fail(h, ANEREND_DDGI_E_CUDA, "bvh8 collapse lost triangles");
+  if (depth > DDGI_STACK) return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "BVH8 deeper than the traversal stack");
+  h->accelMs = be.elapsed(4, 5);
+  h->haveAccel = true;
+  return 0;
+}
+
+int refitAccel(anerend_ddgi* h) {
+  Backend& be = h->be;
+  if (h->numTris == 0) return 0;
+  BuildCtx c = buildCtx(h);
+  c.sceneBounds = nullptr;
+  be.mark(4);
+  DDGI_LAUNCH(be, k_inst_xform, inst_xform_body, (uint32_t)h->instances.size(), c, 128);
+  DDGI_LAUNCH(be, k_flatten_scene, flatten_tri_body, h->numTris, c, 256);
+  DDGI_LAUNCH(be, k_refit_tris, refit_tris_body, h->numTris, c, 256);
+  BE_CHECK(h, be.zero(h->dVisit, ((size_t)h->numTris + 1) * sizeof(uint32_t)));
+  DDGI_LAUNCH(be, k_refit_nodes, refit_node_body, h->numNodes, c, 128);
+  be.mark(5);
+  BE_CHECK(h, be.check());
+  h->timed[3] = true;
+  return 0;
+}
+
+// mat3(randomRot) * dir for every ray of `layer` into the pinned staging table (rgen:87-88)
+void rotateDirs(anerend_ddgi* h, int layer, const float* m) {
+  float4* out = h->hDirs + (size_t)layer * h->N;
+  for (int i = 0; i < h->N; ++i) {
+    float x = h->fib[3 * i], y = h->fib[3 * i + 1], z = h->fib[3 * i + 2];
+    out[i] = make_float4(m[0] * x + m[4] * y + m[8] * z, m[1] * x + m[5] * y + m[9] * z, m[2] * x + m[6] * y + m[10] * z, 1.0f);
+  }
+}
+
+int traceLayers(anerend_ddgi* h, int layerBegin, int numLayers, const float* rots /* indexed from layerBegin */) {
+  Backend& be = h->be;
+  if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "trace before build_accel");
+  if (!h->haveUbo) return fail(h, ANEREND_DDGI_E_STATE, "trace before set_scene_ubo");
+  be.waitCopy();            // previous H2D of the staging table must be done before it is rewritten
+  for (int l = 0; l < numLayers; ++l) rotateDirs(h, layerBegin + l, rots + 16 * (size_t)l);
+  BE_CHECK(h, be.h2d(h->dDirs + (size_t)layerBegin * h->N, h->hDirs + (size_t)layerBegin * h->N, (size_t)numLayers * h->N * sizeof(float4)));
+  be.markCopy();
+  TraceCtx c{};
+  c.nodes = h->dNodes; c.bvhTris = h->dBvhTris; c.numNodes = h->numNodes;
+  c.vertices = h->dVertices; c.indices = h->dIndices; c.materials = h->dMaterials;
+  c.instances = h->dInstances; c.xforms = h->dXforms; c.triInstance = h->dTriInstance;
+  c.lights = h->dLights; c.numLights = h->numLights;
+  c.dirs = h->dDirs + (size_t)layerBegin * h->N; c.rayOrder = h->dRayOrder; c.atlas = h->dAtlas; c.rayIrr = h->dRayIrr;
+  c.records = h->dRecords; c.stats = h->dStats;
+  c.nXZ = h->nXZ; c.nY = h->nY; c.N = h->N; c.W = h->W; c.H = h->H; c.layerBegin = layerBegin; c.numLayers = numLayers;
+  // camOffset (rgen:75-81, pbr_light.glsl:295-301): int() truncates toward zero (quirk Q1)
+  const float* step = h->p.probe_step;
+  int cix = (int)(h->ubo.camera_pos[0] / step[0]), ciz = (int)(h->ubo.camera_pos[2] / step[2]);
+  c.camOff = mk3(float(cix) * step[0] - step[0] * float(h->nXZ) / 2.0f, 0.0f, float(ciz) * step[2] - step[2] * float(h->nXZ) / 2.0f);
+  c.step = mk3(step[0], step[1], step[2]);
+  // rmiss:20 toLinear(skyIntensity * skyColor), constant per frame
+  { float s[3]; for (int k = 0; k < 3; ++k) { float v = h->ubo.sky_intensity * h->ubo.sky_color[k];
+      float higher = powf((v + 0.055f) / 1.055f, 2.4f), lower = v / 12.92f; s[k] = (v < 0.04045f) ? lower : higher; }
+    c.sky = mk3(s[0], s[1], s[2]); }
+  c.lightDir = mk3(h->ubo.light_dir[0], h->ubo.light_dir[1], h->ubo.light_dir[2]);
+  c.tmin = h->p.t_min; c.tmax = h->p.t_max; c.sunIntensity = h->ubo.sun_intensity;
+  c.uboFlags = h->ubo.flags; c.flags = h->p.flags;
+  const uint32_t n = (uint32_t)numLayers * (uint32_t)h->P * (uint32_t)h->N;
+  if (h->p.flags & ANEREND_DDGI_FLAG_COUNTERS) DDGI_LAUNCH(be, k_probe_trace_counted, trace_ray_body<true>, n, c, 128);
+  else DDGI_LAUNCH(be, k_probe_trace, trace_ray_body<false>, n, c, 128);
+  BE_CHECK(h, be.check());
+  for (int l = 0; l < numLayers; ++l) h->layerTraced[layerBegin + l] = 1;
+  return 0;
+}
+
+int convolveLayers(anerend_ddgi* h, int layerBegin, int numLayers) {
+  Backend& be = h->be;
+  for (int l = 0; l < numLayers; ++l) if (!h->layerTraced[layerBegin + l]) return fail(h, ANEREND_DDGI_E_STATE, "convolve before trace of this layer");
+  ConvCtx c{};
+  c.rayIrr = h->dRayIrr; c.dirs = h->dDirs + (size_t)layerBegin * h->N; c.atlas = h->dAtlas; c.texelRecords = h->dTexelRecords;
+  for (int i = 0; i < h->numPeers; ++i) c.peers[i] = h->peers[i];
+  c.numPeers = h->numPeers;
+  c.nXZ = h->nXZ; c.nY = h->nY; c.N = h->N; c.Sx = h->Sx; c.Sy = h->Sy; c.W = h->W; c.H = h->H; c.layerBegin = layerBegin; c.numLayers = numLayers;
+  c.hysteresis = h->p.hysteresis;
+  DDGI_LAUNCH(be, k_probe_convolve, conv_texel_body, (uint32_t)numLayers * (uint32_t)h->P * 64u, c, 128);
+  BE_CHECK(h, be.check());
+  return 0;
+}
+
+int translate(anerend_ddgi* h) {
+  Backend& be = h->be;
+  if (!h->haveUbo) return fail(h, ANEREND_DDGI_E_STATE, "translate before set_scene_ubo");
+  if ((h->ubo.flags & ANEREND_UBO_DDGI_FLAG) != ANEREND_UBO_DDGI_FLAG) return 0;            // :57
+  if ((h->ubo.flags & ANEREND_UBO_BAKE_MODE_ON_FLAG) == ANEREND_UBO_BAKE_MODE_ON_FLAG) return 0;   // :58
+  int ix = (int)(h->ubo.camera_pos[0] / h->p.probe_step[0]), iz = (int)(h->ubo.camera_pos[2] / h->p.probe_step[2]);   // :64
+  int dx = ix - h->lastProbeIdx[0], dz = iz - h->lastProbeIdx[1];
+  if (dx == 0 && dz == 0) return 0;
+  h->lastProbeIdx[0] = ix; h->lastProbeIdx[1] = iz;
+  BE_CHECK(h, be.d2d(h->dTemp, h->dAtlas, (size_t)h->W * h->H * sizeof(uint2)));   // first vkCmdCopyImage (:92-99)
+  ++be.launches;
+  TransCtx c{};
+  c.temp = h->dTemp; c.atlas = h->dAtlas; c.W = h->W; c.nXZ = h->nXZ; c.nY = h->nY; c.dx = dx; c.dz = dz;
+  c.ew = dx != 0 ? h->W - 10 : h->W; c.eh = dz != 0 ? h->W - 10 : h->W;
+  DDGI_LAUNCH(be, k_probe_translate, translate_body, (uint32_t)c.ew * (uint32_t)c.eh * (uint32_t)h->nY, c, 256);
+  BE_CHECK(h, be.check());
+  return 0;
+}
+
+void destroyHandle(anerend_ddgi* h) {
+  if (!h) return;
+  Backend& be = h->be;
+  be.sync();
+  freeAccel(h); freeScene(h);
+  be.free(h->dAtlas); be.free(h->dTemp); be.free(h->dRayIrr); be.free(h->dDirs); be.freeHostPinned(h->hDirs); be.free(h->dRayOrder);
+  be.free(h->dRecords); be.free(h->dTexelRecords); be.free(h->dStats); be.free(h->dSceneBounds); be.free(h->dCounters);
+  be.destroy();
+  delete h;
+}
+
+void beginCall(anerend_ddgi* h) { h->be.launches = 0; h->timed[0] = h->timed[1] = h->timed[2] = false; h->be.mark(0); }
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int DDGI_API(create)(const anerend_ddgi_params_t* params, anerend_ddgi_t** out) {
+  if (!params || !out || params->struct_size != sizeof(anerend_ddgi_params_t)) return ANEREND_DDGI_E_INVALID;
+  const anerend_ddgi_params_t& q = *params;
+  if (q.num_probes_xz < 1 || q.num_probes_y < 1 || q.rays_per_probe < 32 || q.rays_per_probe > 1024 || (q.rays_per_probe % 32)) return ANEREND_DDGI_E_INVALID;
+  int sx, sy; if (rayTile(q.rays_per_probe, sx, sy)) return ANEREND_DDGI_E_INVALID;
+  if (q.slab_begin < 0 || q.slab_end > q.num_probes_y || q.slab_begin >= q.slab_end) return ANEREND_DDGI_E_INVALID;
+  if (!(q.probe_step[0] > 0.0f && q.probe_step[1] > 0.0f && q.probe_step[2] > 0.0f)) return ANEREND_DDGI_E_INVALID;
+  anerend_ddgi* h = new anerend_ddgi();
+  h->p = q; h->nXZ = q.num_probes_xz; h->nY = q.num_probes_y; h->N = q.rays_per_probe; h->Sx = sx; h->Sy = sy;
+  h->W = 10 * h->nXZ; h->H = 10 * h->nXZ * h->nY; h->P = h->nXZ * h->nXZ;
+  Backend& be = h->be;
+  if (!be.init(q.device)) { delete h; return ANEREND_DDGI_E_CUDA; }   // no CUDA device: there is no CPU fallback
+  const size_t texels = (size_t)h->W * h->H, rays = (size_t)h->nY * h->P * h->N;
+  bool ok = be.alloc(&h->dAtlas, texels) && be.alloc(&h->dTemp, texels) && be.alloc(&h->dRayIrr, rays) &&
+            be.alloc(&h->dDirs, (size_t)h->nY * h->N) && be.allocHostPinned(&h->hDirs, (size_t)h->nY * h->N) &&
+            be.alloc(&h->dSceneBounds, 6) && be.alloc(&h->dCounters, 4) && be.alloc(&h->dStats, 8);
+  if (ok && (q.flags & ANEREND_DDGI_FLAG_RAY_RECORDS)) ok = be.alloc(&h->dRecords, rays);
+  if (ok && (q.flags & ANEREND_DDGI_FLAG_TEXEL_RECORDS)) ok = be.alloc(&h->dTexelRecords, texels);
+  if (ok) ok = be.zero(h->dStats, 8 * sizeof(unsigned long long)) && be.zero(h->dRayIrr, rays * sizeof(uint2));
+  if (!ok) { destroyHandle(h); return ANEREND_DDGI_E_CUDA; }
+  h->fib.resize((size_t)h->N * 3);
+  for (int i = 0; i < h->N; ++i) fibonacciDir((uint32_t)i, (uint32_t)h->N, &h->fib[3 * i]);
+  h->layerTraced.assign(h->nY, 0);
+  if (clearAtlas(h) || !be.sync()) { destroyHandle(h); return ANEREND_DDGI_E_CUDA; }
+  *out = h;
+  return 0;
+}
+
+int DDGI_API(destroy)(anerend_ddgi_t* h) {
+  destroyHandle(h);
+  return 0;
+}
+
+int DDGI_API(reset)(anerend_ddgi_t* h) {
+  h->currentLayer = 0; h->lastProbeIdx[0] = h->lastProbeIdx[1] = 0;
+  std::fill(h->layerTraced.begin(), h->layerTraced.end(), 0);
+  return clearAtlas(h);
+}
+const char* DDGI_API(last_error)(const anerend_ddgi_t* h) { return h ? h->err.c_str() : "null handle"; }
+int DDGI_API(sync)(anerend_ddgi_t* h) { BE_CHECK(h, h->be.sync()); return 0; }
+
+int DDGI_API(upload_scene)(anerend_ddgi_t* h,
+    const anerend_vertex_t* vertices, uint32_t nv, const uint32_t* indices, uint32_t ni,
+    const anerend_mesh_info_t* meshes, const uint32_t* meshNumIndices, uint32_t nm,
+    const anerend_material_info_t* materials, uint32_t nmat,
+    const anerend_renderable_t* renderables, uint32_t nr,
+    const uint32_t* modelIdx, uint32_t nmi, const uint32_t* matIdx, uint32_t nmti,
+    const anerend_light_t* lights, uint32_t nl) {
+  Backend& be = h->be;
+  for (uint32_t i = 0; i < nmat; ++i) for (int k = 0; k < 4; ++k)
+    if (materials[i].bindless_indices[k] != -1) return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "textured materials are outside the path's scope");
+  if ((h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) && nl > 31) return fail(h, ANEREND_DDGI_E_INVALID, "at most 31 point lights with FLAG_POINT_LIGHTS");
+  for (uint32_t i = 0; i < nm; ++i) {
+    if ((uint64_t)meshes[i].index_offset + meshNumIndices[i] > ni) return fail(h, ANEREND_DDGI_E_INVALID, "mesh index range exceeds the index buffer");
+  }
+  { // every index must address a vertex inside the giga vertex buffer
+    for (uint32_t m = 0; m < nm; ++m) { const uint32_t vo = meshes[m].vertex_offset;
+      for (uint32_t k = 0; k < meshNumIndices[m]; ++k) if ((uint64_t)vo + indices[meshes[m].index_offset + k] >= nv) return fail(h, ANEREND_DDGI_E_INVALID, "vertex index out of range"); } }
+  BE_CHECK(h, be.sync());
+  freeAccel(h); freeScene(h);
+  BE_CHECK(h, be.alloc(&h->dVertices, nv)); BE_CHECK(h, be.alloc(&h->dIndices, ni)); BE_CHECK(h, be.alloc(&h->dMaterials, nmat));
+  BE_CHECK(h, be.alloc(&h->dRenderables, nr)); BE_CHECK(h, be.alloc(&h->dLights, nl));
+  BE_CHECK(h, be.h2d(h->dVertices, vertices, (size_t)nv * sizeof(*vertices))); BE_CHECK(h, be.h2d(h->dIndices, indices, (size_t)ni * 4));
+  BE_CHECK(h, be.h2d(h->dMaterials, materials, (size_t)nmat * sizeof(*materials))); BE_CHECK(h, be.h2d(h->dRenderables, renderables, (size_t)nr * sizeof(*renderables)));
+  BE_CHECK(h, be.h2d(h->dLights, lights, (size_t)nl * sizeof(*lights)));
+  BE_CHECK(h, be.sync());
+  h->renderables.assign(renderables, renderables + nr); h->meshes.assign(meshes, meshes + nm);
+  h->meshNumIndices.assign(meshNumIndices, meshNumIndices + nm); h->modelIdx.assign(modelIdx, modelIdx + nmi); h->matIdx.assign(matIdx, matIdx + nmti);
+  h->numVertices = nv; h->numIndices = ni; h->numMaterials = nmat; h->numLights = nl;
+  h->haveScene = true;
+  return 0;
+}
+
+int DDGI_API(set_scene_ubo)(anerend_ddgi_t* h, const anerend_scene_ubo_t* ubo) {
+  if (!ubo) return fail(h, ANEREND_DDGI_E_INVALID, "null ubo");
+  h->ubo = *ubo; h->haveUbo = true; return 0;
+}
+
+int DDGI_API(build_accel)(anerend_ddgi_t* h) {
+  if (!h->haveScene) return fail(h, ANEREND_DDGI_E_STATE, "build_accel before upload_scene");
+  return buildAccel(h);
+}
+
+static int refitCommon(anerend_ddgi_t* h) {
+  // visibility must be unchanged: the topology of the acceleration structure is kept
+  std::vector<DInstance> inst; uint32_t n = 0;
+  int rc = selectInstances(h, inst, n); if (rc) return rc;
+  bool same = n == h->numTris && inst.size() == h->instances.size();
+  for (size_t i = 0; same && i < inst.size(); ++i) same = inst[i].renderable == h->instances[i].renderable && inst[i].mesh == h->instances[i].mesh && inst[i].material == h->instances[i].material;
+  if (!same) { h->haveAccel = false; return fail(h, ANEREND_DDGI_E_STATE, "visibility changed: rebuild required"); }
+  return refitAccel(h);
+}
+int DDGI_API(refit_accel)(anerend_ddgi_t* h, const anerend_renderable_t* renderables, uint32_t nr) {
+  if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "refit before build_accel");
+  if (renderables) {
+    if (nr != h->renderables.size()) return fail(h, ANEREND_DDGI_E_INVALID, "renderable count changed");
+    h->renderables.assign(renderables, renderables + nr);
+    BE_CHECK(h, h->be.sync());
+    BE_CHECK(h, h->be.h2d(h->dRenderables, h->renderables.data(), (size_t)nr * sizeof(anerend_renderable_t)));
+  }
+  return refitCommon(h);
+}
+int DDGI_API(refit_accel_device)(anerend_ddgi_t* h, const void* dRenderables, uint32_t nr) {
+  if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "refit before build_accel");
+  if (!dRenderables || nr != h->renderables.size()) return fail(h, ANEREND_DDGI_E_INVALID, "renderable count changed");
+  // device-written RenderableBuffer (cull.comp:303, particle_update.comp:84-85): transforms are taken as they are,
+  // visibility is assumed unchanged since build_accel
+  BE_CHECK(h, h->be.d2d(h->dRenderables, dRenderables, (size_t)nr * sizeof(anerend_renderable_t)));
+  return refitAccel(h);
+}
+
+int DDGI_API(get_bvh_info)(anerend_ddgi_t* h, anerend_ddgi_bvh_info_t* o) {
+  memset(o, 0, sizeof(*o));
+  o->num_triangles = h->numTris; o->num_nodes = h->numNodes; o->node_bytes = 80; o->tri_bytes = 48; o->num_instances = (uint32_t)h->instances.size();
+  for (int k = 0; k < 3; ++k) { o->bounds_min[k] = h->boundsMin[k]; o->bounds_max[k] = h->boundsMax[k]; }
+  return 0;
+}
+int DDGI_API(download_bvh)(anerend_ddgi_t* h, void* nodes, size_t nb, void* tris, size_t tb) {
+  if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "no acceleration structure");
+  if (nb != (size_t)h->numNodes * 80 || tb != (size_t)h->numTris * 48) return fail(h, ANEREND_DDGI_E_INVALID, "size mismatch");
+  BE_CHECK(h, h->be.d2h(nodes, h->dNodes, nb)); BE_CHECK(h, h->be.d2h(tris, h->dBvhTris, tb));
+  return 0;
+}
+
+int DDGI_API(translate)(anerend_ddgi_t* h) {
+  beginCall(h);
+  int rc = translate(h); h->be.mark(1); h->timed[0] = true;
+  return rc;
+}
+int DDGI_API(trace_layer)(anerend_ddgi_t* h, int32_t layer, const float rot[16]) {
+  if (h->haveUbo && !ddgiOn(h)) return 0;
+  if (layer < 0 || layer >= h->nY || !rot) return fail(h, ANEREND_DDGI_E_INVALID, "layer out of range");
+  beginCall(h); h->be.mark(1);
+  int rc = traceLayers(h, layer, 1, rot); h->be.mark(2); h->timed[1] = true;
+  return rc;
+}
+int DDGI_API(convolve_layer)(anerend_ddgi_t* h, int32_t layer) {
+  if (h->haveUbo && !ddgiOn(h)) return 0;
+  if (layer < 0 || layer >= h->nY) return fail(h, ANEREND_DDGI_E_INVALID, "layer out of range");
+  beginCall(h); h->be.mark(2);
+  int rc = convolveLayers(h, layer, 1); h->be.mark(3); h->timed[2] = true;
+  return rc;
+}
+int DDGI_API(update)(anerend_ddgi_t* h, int32_t layer, const float* rots) {
+  if (h->haveUbo && !ddgiOn(h)) return 0;
+  if (!rots || layer >= h->nY) return fail(h, ANEREND_DDGI_E_INVALID, "bad update arguments");
+  beginCall(h); h->be.mark(1);
+  int lb = layer >= 0 ? layer : h->p.slab_begin, nl = layer >= 0 ? 1 : h->p.slab_end - h->p.slab_begin;
+  int rc = traceLayers(h, lb, nl, layer >= 0 ? rots : rots + 16 * (size_t)lb);
+  h->be.mark(2); h->timed[1] = true;
+  if (rc) return rc;
+  rc = convolveLayers(h, lb, nl);
+  h->be.mark(3); h->timed[2] = true;
+  return rc;
+}
+int DDGI_API(frame)(anerend_ddgi_t* h, const float rot[16], int32_t* layerOut) {
+  beginCall(h);
+  int rc = translate(h); h->be.mark(1); h->timed[0] = true;
+  if (rc) return rc;
+  if (!ddgiOn(h)) return 0;
+  const int layer = h->currentLayer;                                   // IrradianceProbeRayTracingPass.cpp:112
+  rc = traceLayers(h, layer, 1, rot); h->be.mark(2); h->timed[1] = true;
+  if (rc) return rc;
+  if (layerOut) *layerOut = layer;                                     // blackboard "ProbeLayer" (:158)
+  h->currentLayer = (h->currentLayer + 1 >= h->nY) ? 0 : h->currentLayer + 1;   // :160-164
+  rc = convolveLayers(h, layer, 1); h->be.mark(3); h->timed[2] = true;
+  return rc;
+}
+
+int DDGI_API(atlas_dims)(const anerend_ddgi_t* h, int32_t* w, int32_t* hh) { *w = h->W; *hh = h->H; return 0; }
+int DDGI_API(download_atlas)(anerend_ddgi_t* h, void* out, size_t bytes) {
+  if (bytes != (size_t)h->W * h->H * 8) return fail(h, ANEREND_DDGI_E_INVALID, "atlas size mismatch");
+  BE_CHECK(h, h->be.d2h(out, h->dAtlas, bytes)); return 0;
+}
+int DDGI_API(upload_atlas)(anerend_ddgi_t* h, const void* in, size_t bytes) {
+  if (bytes != (size_t)h->W * h->H * 8) return fail(h, ANEREND_DDGI_E_INVALID, "atlas size mismatch");
+  BE_CHECK(h, h->be.sync()); BE_CHECK(h, h->be.h2d(h->dAtlas, in, bytes)); BE_CHECK(h, h->be.sync()); return 0;
+}
+int DDGI_API(atlas_device_ptr)(anerend_ddgi_t* h, void** p, size_t* bytes) { *p = h->dAtlas; *bytes = (size_t)h->W * h->H * 8; return 0; }
+int DDGI_API(set_peer_atlases)(anerend_ddgi_t* h, void* const* peers, uint32_t n) {
+  if (n > 8) return fail(h, ANEREND_DDGI_E_INVALID, "at most 8 peers");
+  for (uint32_t i = 0; i < n; ++i) h->peers[i] = (uint2*)peers[i];
+  h->numPeers = (int)n; return 0;
+}
+int DDGI_API(stream)(anerend_ddgi_t* h, void** s) { *s = (void*)h->be.stream; return 0; }
+
+int DDGI_API(ray_tile)(const anerend_ddgi_t* h, int32_t* sx, int32_t* sy) { *sx = h->Sx; *sy = h->Sy; return 0; }
+int DDGI_API(download_rays)(anerend_ddgi_t* h, int32_t layer, void* irrOut, void* dirOut, size_t bytesEach) {
+  if (layer < 0 || layer >= h->nY || !h->layerTraced[layer]) return fail(h, ANEREND_DDGI_E_STATE, "no rays for this layer");
+  const size_t n = (size_t)h->P * h->N;
+  if (bytesEach != n * 8) return fail(h, ANEREND_DDGI_E_INVALID, "ray image size mismatch");
+  std::vector<uint2> lin(n); std::vector<float4> dirs(h->N);
+  BE_CHECK(h, h->be.d2h(lin.data(), h->dRayIrr + (size_t)layer * n, n * 8));
+  BE_CHECK(h, h->be.d2h(dirs.data(), h->dDirs + (size_t)layer * h->N, (size_t)h->N * sizeof(float4)));
+  const int IW = h->Sx * h->nXZ;
+  for (int probe = 0; probe < h->P; ++probe) for (int ray = 0; ray < h->N; ++ray) {
+    int px = ray % h->Sx, py = ray / h->Sx, X = (probe % h->nXZ) * h->Sx + px, Y = (probe / h->nXZ) * h->Sy + py;   // rgen:51-58
+    size_t o = (size_t)Y * IW + X;
+    if (irrOut) ((uint2*)irrOut)[o] = lin[(size_t)probe * h->N + ray];
+    if (dirOut) { const float4 d = dirs[ray];                                                                          // rgen:108
+      ((uint2*)dirOut)[o] = make_uint2((uint32_t)f2h(d.x) | ((uint32_t)f2h(d.y) << 16), (uint32_t)f2h(d.z) | (0x3C00u << 16)); }
+  }
+  return 0;
+}
+int DDGI_API(download_ray_records)(anerend_ddgi_t* h, int32_t layer, anerend_ddgi_ray_record_t* out, size_t count) {
+  if (!h->dRecords) return fail(h, ANEREND_DDGI_E_STATE, "FLAG_RAY_RECORDS not set");
+  if (layer < 0 || layer >= h->nY || count != (size_t)h->P * h->N || !h->layerTraced[layer]) return fail(h, ANEREND_DDGI_E_INVALID, "no records for this layer / count mismatch");
+  BE_CHECK(h, h->be.d2h(out, h->dRecords + (size_t)layer * count, count * sizeof(*out))); return 0;
+}
+int DDGI_API(download_texel_records)(anerend_ddgi_t* h, float* out, size_t bytes) {
+  if (!h->dTexelRecords) return fail(h, ANEREND_DDGI_E_STATE, "FLAG_TEXEL_RECORDS not set");
+  if (bytes != (size_t)h->W * h->H * 16) return fail(h, ANEREND_DDGI_E_INVALID, "size mismatch");
+  BE_CHECK(h, h->be.d2h(out, h->dTexelRecords, bytes)); return 0;
+}
+
+int DDGI_API(get_timings)(anerend_ddgi_t* h, anerend_ddgi_timings_t* o) {
+  BE_CHECK(h, h->be.sync());
+  memset(o, 0, sizeof(*o));
+  if (h->timed[0]) o->trans_ms = h->be.elapsed(0, 1);
+  if (h->timed[1]) o->rt_ms = h->be.elapsed(1, 2);
+  if (h->timed[2]) o->convolve_ms = h->be.elapsed(2, 3);
+  if (h->timed[3]) { h->accelMs = h->be.elapsed(4, 5); h->timed[3] = false; }
+  o->accel_ms = h->accelMs;
+  o->total_ms = o->trans_ms + o->rt_ms + o->convolve_ms;
+  o->kernel_launches = h->be.launches;
+  return 0;
+}
+int DDGI_API(get_stats)(anerend_ddgi_t* h, anerend_ddgi_stats_t* o) {
+  unsigned long long s[8];
+  BE_CHECK(h, h->be.d2h(s, h->dStats, sizeof(s)));
+  o->primary_rays = s[0]; o->primary_hits = s[1]; o->shadow_rays = s[2]; o->primary_nodes_visited = s[3]; o->primary_tris_tested = s[4];
+  o->shadow_nodes_visited = s[5]; o->shadow_tris_tested = s[6];
+  return 0;
+}
+int DDGI_API(reset_stats)(anerend_ddgi_t* h) { BE_CHECK(h, h->be.zero(h->dStats, 8 * sizeof(unsigned long long))); return 0; }
+
+// glm::rotate(mat4(1), radians(deg), axis) (IrradianceProbeRayTracingPass.cpp:133; glm/ext/matrix_transform.inl:18-46)
+int DDGI_API(make_rotation)(int32_t axisIdx, float deg, float out[16]) {
+  if (axisIdx < 0 || axisIdx > 2 || !out) return ANEREND_DDGI_E_INVALID;
+  const float a = deg * 0.01745329251994329576923690768489f;
+  const float c = cosf(a), s = sinf(a);
+  float axis[3] = {0.0f, 0.0f, 0.0f}; axis[axisIdx] = 1.0f;
+  const float temp[3] = {(1.0f - c) * axis[0], (1.0f - c) * axis[1], (1.0f - c) * axis[2]};
+  float R[3][3];
+  R[0][0] = c + temp[0] * axis[0]; R[0][1] = temp[0] * axis[1] + s * axis[2]; R[0][2] = temp[0] * axis[2] - s * axis[1];
+  R[1][0] = temp[1] * axis[0] - s * axis[2]; R[1][1] = c + temp[1] * axis[1]; R[1][2] = temp[1] * axis[2] + s * axis[0];
+  R[2][0] = temp[2] * axis[0] + s * axis[1]; R[2][1] = temp[2] * axis[1] - s * axis[0]; R[2][2] = c + temp[2] * axis[2];
+  const float m[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+  for (int i = 0; i < 3; ++i) for (int r = 0; r < 4; ++r) out[i * 4 + r] = m[0][r] * R[i][0] + m[1][r] * R[i][1] + m[2][r] * R[i][2];
+  for (int r = 0; r < 4; ++r) out[12 + r] = m[3][r];
+  return 0;
+}
+int DDGI_API(fibonacci_dirs)(int32_t n, float* out) {
+  if (n < 1 || !out) return ANEREND_DDGI_E_INVALID;
+  for (int i = 0; i < n; ++i) fibonacciDir((uint32_t)i, (uint32_t)n, out + 3 * i);
+  return 0;
+}
+const char* DDGI_API(version)(void) {
+#ifdef DDGI_HOST_EMU
+  return "anerend_ddgi host-emu debug harness (not the product)";
+#else
+  return "anerend_cuda_ddgi 0.1 (sm_100a)";
+#endif
+}
+
+}  // extern "C"

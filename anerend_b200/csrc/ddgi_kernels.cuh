@@ -1,0 +1,765 @@
+// ddgi_kernels.cuh — per-thread bodies of every kernel on the DDGI probe-update path.
+//
+// Each `*_body(i, ctx)` is the work of ONE thread of the named kernel; ddgi_launch.h wraps them in
+// __global__ kernels (product) or serial loops (tests/host_emu).  Reference citations are relative to the
+// AneRend repository (shaders in assets/shaders/).  This translation unit is compiled with --fmad=false:
+// arithmetic is evaluated left to right without contraction, the only fused multiply-adds are the explicit
+// fmaf calls (triangle test, quantised box test), so hit ids match the CPU oracle bit for bit.
+#pragma once
+#include "platform.h"
+#include "../../include/anerend_cuda_ddgi.h"
+
+namespace ddgi {
+
+// ----------------------------------------------------------------------------------------------------
+// small vector maths
+// ----------------------------------------------------------------------------------------------------
+struct V3 { float x, y, z; };
+HD V3 mk3(float x, float y, float z) { V3 v; v.x = x; v.y = y; v.z = z; return v; }
+HD V3 mk3(float s) { return mk3(s, s, s); }
+HD V3 operator+(V3 a, V3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+HD V3 operator-(V3 a, V3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+HD V3 operator*(V3 a, V3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+HD V3 operator/(V3 a, V3 b) { return mk3(a.x / b.x, a.y / b.y, a.z / b.z); }
+HD V3 operator*(V3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+HD V3 operator*(float s, V3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
+HD V3 operator/(V3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+HD V3 operator-(V3 a) { return mk3(-a.x, -a.y, -a.z); }
+HD float dot3(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+HD V3 normalize3(V3 v) { float inv = 1.0f / sqrtf(dot3(v, v)); return v * inv; }
+HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+HD V3 clamp3(V3 v, float lo, float hi) { return mk3(clampf(v.x, lo, hi), clampf(v.y, lo, hi), clampf(v.z, lo, hi)); }
+HD V3 min3(V3 a, V3 b) { return mk3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
+HD V3 max3(V3 a, V3 b) { return mk3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
+HD float mixf(float x, float y, float a) { return x * (1.0f - a) + y * a; }
+HD V3 mix3(V3 x, V3 y, float a) { return mk3(mixf(x.x, y.x, a), mixf(x.y, y.y, a), mixf(x.z, y.z, a)); }
+HD float pow5(float x) { float x2 = x * x; return (x2 * x2) * x; }
+HD int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+#define DDGI_PI 3.14159265359f
+#define DDGI_MISS 0xFFFFFFFFu
+
+// ----------------------------------------------------------------------------------------------------
+// device-side scene representation
+// ----------------------------------------------------------------------------------------------------
+struct DInstance {            // one (renderable, mesh) pair accepted by tlas_update.comp:37-99
+  uint32_t renderable, mesh, material, firstTri, numTris, vertexOffset, indexOffset, _pad;
+};
+struct InstXform {            // gl_ObjectToWorldEXT (4 columns x 3 rows) and the 3x3 of gl_WorldToObjectEXT
+  float o2w[12];              // o2w[c*3+r]
+  float w2o[9];               // w2o[c*3+r]
+  float _pad[3];
+};
+struct CItem { uint32_t ref, node; };   // BVH8 collapse work item: binary subtree `ref` becomes BVH8 node `node`
+
+struct BuildCtx {
+  const anerend_vertex_t* vertices; const uint32_t* indices; const anerend_renderable_t* renderables;
+  const DInstance* instances; InstXform* xforms; const uint32_t* triInstance;
+  uint32_t numTris, numInstances;
+  float4* wtri;               // 3 x float4 per world triangle, global-id order: (v0,e1.x) (e1.yz,e2.xy) (e2.z,id,0,0)
+  float4* triLo; float4* triHi;   // padded AABB per triangle
+  int* sceneBounds;           // 6 order-preserving ints: min xyz, max xyz
+  uint32_t* mortonKeys; uint32_t* triIds;          // unsorted
+  uint32_t* sortedKeys; uint32_t* sortedIds;       // after the radix sort
+  uint32_t* left; uint32_t* right; uint32_t* parent; uint32_t* rangeFirst; uint32_t* rangeLast; uint32_t* visit;
+  float4* blo; float4* bhi;   // boxes of the 2n-1 binary refs (ref >= n-1: leaf at sorted position ref-(n-1))
+  uint4* nodes; float4* bvhTris; uint32_t* nodeParent; float4* nodeLo; float4* nodeHi; uint32_t* nodePending;
+  uint32_t* counters;         // [0] BVH8 nodes allocated, [1] triangle slots allocated, [2] next queue length
+  const CItem* qin; CItem* qout;
+};
+
+// ----------------------------------------------------------------------------------------------------
+// instance transforms + flatten (replaces tlas_update.comp's instance write and the driver BLAS/TLAS build inputs)
+// ----------------------------------------------------------------------------------------------------
+HD void inst_xform_body(uint32_t i, const BuildCtx& c) {
+  const float* m = c.renderables[c.instances[i].renderable].transform;   // column-major mat4
+  InstXform x;
+  for (int col = 0; col < 4; ++col) for (int r = 0; r < 3; ++r) x.o2w[col * 3 + r] = m[col * 4 + r];
+  // inverse of the upper 3x3: adjugate / determinant
+  float a = m[0], b = m[4], cc = m[8], d = m[1], e = m[5], f = m[9], g = m[2], h = m[6], k = m[10];
+  float A = e * k - f * h, B = -(d * k - f * g), C = d * h - e * g;
+  float det = a * A + b * B + cc * C;
+  float inv = 1.0f / det;
+  float r00 = A * inv, r01 = -(b * k - cc * h) * inv, r02 = (b * f - cc * e) * inv;
+  float r10 = B * inv, r11 = (a * k - cc * g) * inv, r12 = -(a * f - cc * d) * inv;
+  float r20 = C * inv, r21 = -(a * h - b * g) * inv, r22 = (a * e - b * d) * inv;
+  x.w2o[0] = r00; x.w2o[1] = r10; x.w2o[2] = r20;
+  x.w2o[3] = r01; x.w2o[4] = r11; x.w2o[5] = r21;
+  x.w2o[6] = r02; x.w2o[7] = r12; x.w2o[8] = r22;
+  x._pad[0] = x._pad[1] = x._pad[2] = 0.0f;
+  c.xforms[i] = x;
+}
+
+// gl_ObjectToWorldEXT * vec4(p,1): c0*x + c1*y + c2*z + c3, left to right
+HD V3 xform_point(const float* o2w, V3 p) {
+  return mk3(o2w[0] * p.x + o2w[3] * p.y + o2w[6] * p.z + o2w[9],
+             o2w[1] * p.x + o2w[4] * p.y + o2w[7] * p.z + o2w[10],
+             o2w[2] * p.x + o2w[5] * p.y + o2w[8] * p.z + o2w[11]);
+}
+
+HD int float_to_ordered(float f) { int i = (int)f2u(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
+HD float ordered_to_float(int i) { return u2f((uint32_t)(i >= 0 ? i : i ^ 0x7FFFFFFF)); }
+
+HD void flatten_tri_body(uint32_t t, const BuildCtx& c) {
+  uint32_t ii = c.triInstance[t];
+  const DInstance in = c.instances[ii];
+  const float* o2w = c.xforms[ii].o2w;
+  uint32_t prim = t - in.firstTri;
+  V3 w[3];
+  for (int k = 0; k < 3; ++k) {
+    uint32_t vi = in.vertexOffset + c.indices[in.indexOffset + 3 * prim + k];
+    const float* p = c.vertices[vi].pos;
+    w[k] = xform_point(o2w, mk3(p[0], p[1], p[2]));
+  }
+  V3 e1 = w[1] - w[0], e2 = w[2] - w[0];
+  c.wtri[3 * (size_t)t + 0] = make_float4(w[0].x, w[0].y, w[0].z, e1.x);
+  c.wtri[3 * (size_t)t + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
+  c.wtri[3 * (size_t)t + 2] = make_float4(e2.z, u2f(t), 0.0f, 0.0f);
+  // AABB of what the triangle test actually sees (v0, v0+e1, v0+e2), padded so that neither the e1/e2 round trip
+  // nor slab-test rounding can cull a true hit
+  V3 q1 = w[0] + e1, q2 = w[0] + e2;
+  V3 lo = min3(min3(w[0], min3(w[1], w[2])), min3(q1, q2)), hi = max3(max3(w[0], max3(w[1], w[2])), max3(q1, q2));
+  V3 pad = mk3(1e-5f * fmaxf(1.0f, fmaxf(fabsf(lo.x), fabsf(hi.x))), 1e-5f * fmaxf(1.0f, fmaxf(fabsf(lo.y), fabsf(hi.y))),
+               1e-5f * fmaxf(1.0f, fmaxf(fabsf(lo.z), fabsf(hi.z))));
+  lo = lo - pad; hi = hi + pad;
+  c.triLo[t] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+  c.triHi[t] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+  if (c.sceneBounds) {
+    atomMin(&c.sceneBounds[0], float_to_ordered(lo.x)); atomMin(&c.sceneBounds[1], float_to_ordered(lo.y)); atomMin(&c.sceneBounds[2], float_to_ordered(lo.z));
+    atomMax(&c.sceneBounds[3], float_to_ordered(hi.x)); atomMax(&c.sceneBounds[4], float_to_ordered(hi.y)); atomMax(&c.sceneBounds[5], float_to_ordered(hi.z));
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// LBVH: 30-bit Morton codes -> (radix sort) -> Karras 2012 hierarchy -> bottom-up AABB fit
+// ----------------------------------------------------------------------------------------------------
+HD uint32_t expand_bits10(uint32_t v) {
+  v = (v * 0x00010001u) & 0xFF0000FFu; v = (v * 0x00000101u) & 0x0F00F00Fu;
+  v = (v * 0x00000011u) & 0xC30C30C3u; v = (v * 0x00000005u) & 0x49249249u; return v;
+}
+HD void morton_body(uint32_t t, const BuildCtx& c) {
+  V3 lo = mk3(ordered_to_float(c.sceneBounds[0]), ordered_to_float(c.sceneBounds[1]), ordered_to_float(c.sceneBounds[2]));
+  V3 hi = mk3(ordered_to_float(c.sceneBounds[3]), ordered_to_float(c.sceneBounds[4]), ordered_to_float(c.sceneBounds[5]));
+  float4 a = c.triLo[t], b = c.triHi[t];
+  V3 cen = mk3(0.5f * (a.x + b.x), 0.5f * (a.y + b.y), 0.5f * (a.z + b.z));
+  V3 ext = max3(hi - lo, mk3(1e-20f));
+  V3 u = (cen - lo) / ext;
+  uint32_t x = (uint32_t)fminf(fmaxf(u.x * 1024.0f, 0.0f), 1023.0f);
+  uint32_t y = (uint32_t)fminf(fmaxf(u.y * 1024.0f, 0.0f), 1023.0f);
+  uint32_t z = (uint32_t)fminf(fmaxf(u.z * 1024.0f, 0.0f), 1023.0f);
+  c.mortonKeys[t] = (expand_bits10(x) << 2) | (expand_bits10(y) << 1) | expand_bits10(z);
+  c.triIds[t] = t;
+}
+
+// common-prefix length of sorted keys i and j (duplicates broken by index); -1 outside the array
+HD int lbvh_delta(const uint32_t* keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  uint32_t a = keys[i], b = keys[j];
+  if (a == b) return 32 + clz32((uint32_t)i ^ (uint32_t)j);
+  return clz32(a ^ b);
+}
+HD void karras_body(uint32_t idx, const BuildCtx& c) {
+  const int n = (int)c.numTris, i = (int)idx;
+  const uint32_t* keys = c.sortedKeys;
+  int d = (lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  int dmin = lbvh_delta(keys, n, i, i - d);
+  int lmax = 2;
+  while (lbvh_delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+  int l = 0;
+  for (int t = lmax / 2; t >= 1; t /= 2) if (lbvh_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+  int j = i + l * d;
+  int dnode = lbvh_delta(keys, n, i, j);
+  int s = 0;
+  for (int t = (l + 1) / 2;; t = (t + 1) / 2) {
+    if (lbvh_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    if (t == 1) break;
+  }
+  int gamma = i + s * d + (d < 0 ? -1 : 0);
+  int first = i < j ? i : j, last = i < j ? j : i;
+  uint32_t L = (first == gamma) ? (uint32_t)(n - 1 + gamma) : (uint32_t)gamma;
+  uint32_t R = (last == gamma + 1) ? (uint32_t)(n - 1 + gamma + 1) : (uint32_t)(gamma + 1);
+  c.left[i] = L; c.right[i] = R; c.parent[L] = (uint32_t)i; c.parent[R] = (uint32_t)i;
+  c.rangeFirst[i] = (uint32_t)first; c.rangeLast[i] = (uint32_t)last;
+  if (i == 0) c.parent[0] = DDGI_MISS;
+}
+HD void fit_body(uint32_t leaf, const BuildCtx& c) {
+  const uint32_t n = c.numTris;
+  uint32_t ref = n - 1 + leaf, gid = c.sortedIds[leaf];
+  float4 lo = c.triLo[gid], hi = c.triHi[gid];
+  c.blo[ref] = lo; c.bhi[ref] = hi;
+  if (n == 1) return;
+  memFence();
+  uint32_t p = c.parent[ref];
+  while (p != DDGI_MISS) {
+    if (atomAdd(&c.visit[p], 1u) == 0u) return;     // first child to arrive leaves; the second one merges
+    memFence();
+    uint32_t l = c.left[p], r = c.right[p];
+#ifdef __CUDA_ARCH__
+    float4 a0 = __ldcg(&c.blo[l]), a1 = __ldcg(&c.bhi[l]), b0 = __ldcg(&c.blo[r]), b1 = __ldcg(&c.bhi[r]);
+#else
+    float4 a0 = c.blo[l], a1 = c.bhi[l], b0 = c.blo[r], b1 = c.bhi[r];
+#endif
+    c.blo[p] = make_float4(fminf(a0.x, b0.x), fminf(a0.y, b0.y), fminf(a0.z, b0.z), 0.0f);
+    c.bhi[p] = make_float4(fmaxf(a1.x, b1.x), fmaxf(a1.y, b1.y), fmaxf(a1.z, b1.z), 0.0f);
+    memFence();
+    p = c.parent[p];
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// BVH8: 80-byte compressed wide node (layout after Ylitie, Karras, Laine 2017)
+//   word0: p.x p.y p.z | ex,ey,ez,imask      p = node box min, e* = biased fp32 exponents of the per-axis grid
+//   word1: childBase, triBase, meta[0..3], meta[4..7]
+//          meta: 0 empty | internal: 0b001'11sss (low 5 bits = 24+slot) | leaf: unary count<<5 | first tri offset
+//   word2: qlo.x[0..7] qlo.y[0..7]   word3: qlo.z[0..7] qhi.x[0..7]   word4: qhi.y[0..7] qhi.z[0..7]
+// Child boxes are quantised outwards to 8 bits on the node's grid, so they stay conservative.
+// ----------------------------------------------------------------------------------------------------
+HD uint32_t grid_exponent(float ext) {
+  float s = ext / 254.0f;                    // 254, not 255: margin so that ceil() never needs 256
+  uint32_t bits = f2u(s), eb = (bits >> 23) & 0xFFu;
+  if (bits & 0x7FFFFFu) eb += 1;
+  if (eb < 1u) eb = 1u;
+  if (eb > 253u) eb = 253u;
+  return eb;
+}
+HD void encode_node(uint4* out, V3 nlo, V3 nhi, const V3* clo, const V3* chi, const uint8_t* meta, uint32_t imask,
+                    uint32_t childBase, uint32_t triBase) {
+  V3 ext = nhi - nlo;
+  uint32_t ex = grid_exponent(ext.x), ey = grid_exponent(ext.y), ez = grid_exponent(ext.z);
+  float ix = u2f((254u - ex) << 23), iy = u2f((254u - ey) << 23), iz = u2f((254u - ez) << 23);
+  uint32_t q[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // lox lo/hi, loy lo/hi, loz lo/hi, hix.., hiy.., hiz..
+  uint32_t m[2] = {0, 0};
+  for (int s = 0; s < 8; ++s) {
+    if (!meta[s]) continue;
+    uint32_t sh = 8u * (uint32_t)(s & 3); int w = s >> 2;
+    m[w] |= (uint32_t)meta[s] << sh;
+    uint32_t lx = (uint32_t)clampf(floorf((clo[s].x - nlo.x) * ix), 0.0f, 255.0f);
+    uint32_t ly = (uint32_t)clampf(floorf((clo[s].y - nlo.y) * iy), 0.0f, 255.0f);
+    uint32_t lz = (uint32_t)clampf(floorf((clo[s].z - nlo.z) * iz), 0.0f, 255.0f);
+    uint32_t hx = (uint32_t)clampf(ceilf((chi[s].x - nlo.x) * ix), 0.0f, 255.0f);
+    uint32_t hy = (uint32_t)clampf(ceilf((chi[s].y - nlo.y) * iy), 0.0f, 255.0f);
+    uint32_t hz = (uint32_t)clampf(ceilf((chi[s].z - nlo.z) * iz), 0.0f, 255.0f);
+    q[0 + w] |= lx << sh; q[2 + w] |= ly << sh; q[4 + w] |= lz << sh;
+    q[6 + w] |= hx << sh; q[8 + w] |= hy << sh; q[10 + w] |= hz << sh;
+  }
+  out[0] = make_uint4(f2u(nlo.x), f2u(nlo.y), f2u(nlo.z), ex | (ey << 8) | (ez << 16) | (imask << 24));
+  out[1] = make_uint4(childBase, triBase, m[0], m[1]);
+  out[2] = make_uint4(q[0], q[1], q[2], q[3]);
+  out[3] = make_uint4(q[4], q[5], q[6], q[7]);
+  out[4] = make_uint4(q[8], q[9], q[10], q[11]);
+}
+
+HD V3 f4v(float4 f) { return mk3(f.x, f.y, f.z); }
+HD float half_area(V3 lo, V3 hi) { V3 e = hi - lo; return e.x * e.y + e.y * e.z + e.z * e.x; }
+
+// One BVH8 node from one binary subtree (greedy surface-area collapse), children assigned to slots by octant so the
+// traversal can order them with a XOR (Ylitie 2017 §3.2); internal children and leaf triangles are stored contiguously.
+HD void collapse_body(uint32_t i, const BuildCtx& c) {
+  const uint32_t n = c.numTris;
+  const CItem it = c.qin[i];
+  auto isInternal = [&](uint32_t r) { return r < n - 1; };
+  auto count = [&](uint32_t r) -> uint32_t { return isInternal(r) ? c.rangeLast[r] - c.rangeFirst[r] + 1u : 1u; };
+  uint32_t ch[8]; int nch = 1; ch[0] = it.ref;
+  for (int phase = 0; phase < 2; ++phase) {
+    const uint32_t minCount = phase == 0 ? 4u : 2u;
+    while (nch < 8) {
+      int best = -1; float bestA = -1.0f;
+      for (int k = 0; k < nch; ++k) {
+        if (!isInternal(ch[k]) || count(ch[k]) < minCount) continue;
+        float a = half_area(f4v(c.blo[ch[k]]), f4v(c.bhi[ch[k]]));
+        if (a > bestA) { bestA = a; best = k; }
+      }
+      if (best < 0) break;
+      uint32_t r = ch[best];
+      ch[best] = c.left[r]; ch[nch++] = c.right[r];
+    }
+  }
+  V3 nlo = f4v(c.blo[it.ref]), nhi = f4v(c.bhi[it.ref]);
+  V3 ncen = (nlo + nhi) * 0.5f;
+  // greedy child -> slot assignment: slot bit k set = child lies towards +axis k
+  float cost[8][8]; int slotOf[8]; bool slotUsed[8], childDone[8];
+  for (int k = 0; k < 8; ++k) { slotOf[k] = -1; slotUsed[k] = false; childDone[k] = false; }
+  for (int k = 0; k < nch; ++k) {
+    V3 d = (f4v(c.blo[ch[k]]) + f4v(c.bhi[ch[k]])) * 0.5f - ncen;
+    for (int s = 0; s < 8; ++s) cost[k][s] = ((s & 1) ? d.x : -d.x) + ((s & 2) ? d.y : -d.y) + ((s & 4) ? d.z : -d.z);
+  }
+  for (int round = 0; round < nch; ++round) {
+    int bk = -1, bs = -1; float bc = -3.0e38f;
+    for (int k = 0; k < nch; ++k) { if (childDone[k]) continue;
+      for (int s = 0; s < 8; ++s) { if (slotUsed[s]) continue; if (cost[k][s] > bc) { bc = cost[k][s]; bk = k; bs = s; } } }
+    slotOf[bk] = bs; slotUsed[bs] = true; childDone[bk] = true;
+  }
+  int childAt[8]; for (int s = 0; s < 8; ++s) childAt[s] = -1;
+  for (int k = 0; k < nch; ++k) childAt[slotOf[k]] = k;
+  uint32_t nInternal = 0, nLeafTris = 0, imask = 0;
+  for (int s = 0; s < 8; ++s) { int k = childAt[s]; if (k < 0) continue;
+    if (isInternal(ch[k]) && count(ch[k]) >= 4u) { imask |= 1u << s; ++nInternal; } else nLeafTris += count(ch[k]); }
+  uint32_t childBase = nInternal ? atomAdd(&c.counters[0], nInternal) : 0u;
+  uint32_t triBase = nLeafTris ? atomAdd(&c.counters[1], nLeafTris) : 0u;
+  V3 clo[8], chi[8]; uint8_t meta[8];
+  uint32_t rank = 0, toff = 0;
+  for (int s = 0; s < 8; ++s) {
+    int k = childAt[s]; meta[s] = 0;
+    if (k < 0) continue;
+    uint32_t r = ch[k];
+    clo[s] = f4v(c.blo[r]); chi[s] = f4v(c.bhi[r]);
+    if (imask & (1u << s)) {
+      meta[s] = (uint8_t)(0x20u | (24u + (uint32_t)s));
+      uint32_t child = childBase + rank++;
+      c.nodeParent[child] = it.node;
+      uint32_t qi = atomAdd(&c.counters[2], 1u);
+      CItem o; o.ref = r; o.node = child; c.qout[qi] = o;
+    } else {
+      uint32_t cnt = count(r), first = isInternal(r) ? c.rangeFirst[r] : r - (n - 1);
+      meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | toff);
+      for (uint32_t j = 0; j < cnt; ++j) {
+        uint32_t gid = c.sortedIds[first + j]; size_t slot = (size_t)triBase + toff + j;
+        c.bvhTris[3 * slot + 0] = c.wtri[3 * (size_t)gid + 0];
+        c.bvhTris[3 * slot + 1] = c.wtri[3 * (size_t)gid + 1];
+        c.bvhTris[3 * slot + 2] = c.wtri[3 * (size_t)gid + 2];
+      }
+      toff += cnt;
+    }
+  }
+  encode_node(c.nodes + 5 * (size_t)it.node, nlo, nhi, clo, chi, meta, imask, childBase, triBase);
+  c.nodeLo[it.node] = make_float4(nlo.x, nlo.y, nlo.z, 0.0f);
+  c.nodeHi[it.node] = make_float4(nhi.x, nhi.y, nhi.z, 0.0f);
+  c.nodePending[it.node] = nInternal;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// refit (replaces tlas_update.comp + TLAS rebuild for moving nodes): topology kept, boxes recomputed bottom-up
+// ----------------------------------------------------------------------------------------------------
+HD void refit_tris_body(uint32_t slot, const BuildCtx& c) {
+  uint32_t gid = f2u(c.bvhTris[3 * (size_t)slot + 2].y);
+  c.bvhTris[3 * (size_t)slot + 0] = c.wtri[3 * (size_t)gid + 0];
+  c.bvhTris[3 * (size_t)slot + 1] = c.wtri[3 * (size_t)gid + 1];
+  c.bvhTris[3 * (size_t)slot + 2] = c.wtri[3 * (size_t)gid + 2];
+}
+// thread per BVH8 node; nodes without internal children start, the last child to finish continues with the parent.
+// c.visit[node] (zeroed before launch) counts finished internal children.
+HD void refit_node_body(uint32_t node0, const BuildCtx& c) {
+  if (c.nodePending[node0] != 0u) return;
+  uint32_t node = node0;
+  for (;;) {
+    uint4* nd = c.nodes + 5 * (size_t)node;
+#ifdef __CUDA_ARCH__
+    uint4 w0 = __ldcg(nd), w1 = __ldcg(nd + 1);
+#else
+    uint4 w0 = nd[0], w1 = nd[1];
+#endif
+    uint32_t imask = w0.w >> 24, childBase = w1.x, triBase = w1.y;
+    V3 clo[8], chi[8]; uint8_t meta[8];
+    V3 nlo = mk3(3.0e38f), nhi = mk3(-3.0e38f);
+    for (int s = 0; s < 8; ++s) {
+      uint32_t mt = ((s < 4 ? w1.z : w1.w) >> (8 * (s & 3))) & 0xFFu; meta[s] = (uint8_t)mt;
+      if (!mt) continue;
+      if (imask & (1u << s)) {
+        uint32_t child = childBase + (uint32_t)popc32(imask & ((1u << s) - 1u));
+#ifdef __CUDA_ARCH__
+        clo[s] = f4v(__ldcg(&c.nodeLo[child])); chi[s] = f4v(__ldcg(&c.nodeHi[child]));
+#else
+        clo[s] = f4v(c.nodeLo[child]); chi[s] = f4v(c.nodeHi[child]);
+#endif
+      } else {
+        uint32_t off = mt & 0x1Fu, cnt = (uint32_t)popc32(mt >> 5);
+        V3 lo = mk3(3.0e38f), hi = mk3(-3.0e38f);
+        for (uint32_t j = 0; j < cnt; ++j) {
+          uint32_t gid = f2u(c.bvhTris[3 * ((size_t)triBase + off + j) + 2].y);
+          lo = min3(lo, f4v(c.triLo[gid])); hi = max3(hi, f4v(c.triHi[gid]));
+        }
+        clo[s] = lo; chi[s] = hi;
+      }
+      nlo = min3(nlo, clo[s]); nhi = max3(nhi, chi[s]);
+    }
+    encode_node(nd, nlo, nhi, clo, chi, meta, imask, childBase, triBase);
+    c.nodeLo[node] = make_float4(nlo.x, nlo.y, nlo.z, 0.0f);
+    c.nodeHi[node] = make_float4(nhi.x, nhi.y, nhi.z, 0.0f);
+    if (node == 0u) return;
+    memFence();
+    uint32_t par = c.nodeParent[node];
+    if (atomAdd(&c.visit[par], 1u) + 1u != c.nodePending[par]) return;
+    memFence();
+    node = par;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// traversal (replaces traceRayEXT, rgen:96 and rchit:55).  Per-thread short-stack walk of the BVH8.
+// ----------------------------------------------------------------------------------------------------
+struct Hit { float t, u, v; uint32_t prim; };
+
+HD float dotF(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+HD V3 crossF(V3 a, V3 b) { return mk3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x))); }
+// Möller–Trumbore on (v0,e1,e2), two-sided, tmin < t < tmax exclusive — identical association to the oracle's.
+HD bool tri_intersect(V3 o, V3 d, V3 v0, V3 e1, V3 e2, float tmin, float tmax, float& t, float& u, float& v) {
+  V3 p = crossF(d, e2);
+  float det = dotF(e1, p);
+  if (det == 0.0f) return false;
+  float inv = 1.0f / det;
+  V3 tv = o - v0;
+  u = dotF(tv, p) * inv;
+  if (!(u >= 0.0f && u <= 1.0f)) return false;
+  V3 q = crossF(tv, e1);
+  v = dotF(d, q) * inv;
+  if (!(v >= 0.0f && u + v <= 1.0f)) return false;
+  t = dotF(e2, q) * inv;
+  return t > tmin && t < tmax;
+}
+
+#define DDGI_STACK 48
+HD float safe_dir(float d) { return fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d; }
+HD uint32_t byte_of(uint32_t lo, uint32_t hi, int i) { return ((i < 4 ? lo : hi) >> (8 * (i & 3))) & 0xFFu; }
+
+template <bool ANY, bool CNT>
+HD bool traverse(const uint4* __restrict__ nodes, const float4* __restrict__ tris, uint32_t numNodes, V3 o, V3 d,
+                 float tmin, float tmax, Hit& hit, uint32_t& cntNodes, uint32_t& cntTris) {
+  hit.prim = DDGI_MISS; hit.t = tmax; hit.u = 0.0f; hit.v = 0.0f;
+  if (numNodes == 0u) return false;
+  const float idx = 1.0f / safe_dir(d.x), idy = 1.0f / safe_dir(d.y), idz = 1.0f / safe_dir(d.z);
+  const uint32_t octinv = 7u - ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
+  uint2 stack[DDGI_STACK]; int sp = 0;
+  uint2 ng = make_uint2(0u, 0x80000000u);
+  for (;;) {
+    uint2 tg = make_uint2(0u, 0u);
+    if (ng.y & 0xFF000000u) {
+      const int bit = msb32(ng.y);
+      ng.y &= ~(1u << bit);
+      if (ng.y & 0xFF000000u) { if (sp < DDGI_STACK) stack[sp++] = ng; }
+      const uint32_t slot = ((uint32_t)bit - 24u) ^ octinv;
+      const uint32_t rel = (uint32_t)popc32(ng.y & ~(0xFFFFFFFFu << slot) & 0xFFu);
+      const uint4* nd = nodes + 5 * (size_t)(ng.x + rel);
+      const uint4 n0 = nd[0], n1 = nd[1], n2 = nd[2], n3 = nd[3], n4 = nd[4];
+      if (CNT) ++cntNodes;
+      const float adjx = u2f((n0.w & 0xFFu) << 23) * idx, adjy = u2f(((n0.w >> 8) & 0xFFu) << 23) * idy, adjz = u2f(((n0.w >> 16) & 0xFFu) << 23) * idz;
+      const float orgx = (u2f(n0.x) - o.x) * idx, orgy = (u2f(n0.y) - o.y) * idy, orgz = (u2f(n0.z) - o.z) * idz;
+      const float tcur = hit.t;
+      uint32_t hitmask = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t meta = byte_of(n1.z, n1.w, i);
+        if (!meta) continue;
+        const float tlx = fmaf((float)byte_of(n2.x, n2.y, i), adjx, orgx), thx = fmaf((float)byte_of(n3.z, n3.w, i), adjx, orgx);
+        const float tly = fmaf((float)byte_of(n2.z, n2.w, i), adjy, orgy), thy = fmaf((float)byte_of(n4.x, n4.y, i), adjy, orgy);
+        const float tlz = fmaf((float)byte_of(n3.x, n3.y, i), adjz, orgz), thz = fmaf((float)byte_of(n4.z, n4.w, i), adjz, orgz);
+        const float tn = fmaxf(fmaxf(fminf(tlx, thx), fminf(tly, thy)), fmaxf(fminf(tlz, thz), tmin));
+        const float tfb = fminf(fminf(fmaxf(tlx, thx), fmaxf(tly, thy)), fmaxf(tlz, thz)) * 1.0000004f;
+        const float tf = fminf(tfb, tcur);
+        if (tn <= tf) {
+          if ((meta & 0x1Fu) >= 24u) hitmask |= 1u << (24u + ((meta & 7u) ^ octinv));
+          else hitmask |= (meta >> 5) << (meta & 0x1Fu);
+        }
+      }
+      ng = make_uint2(n1.x, (hitmask & 0xFF000000u) | (n0.w >> 24));
+      tg = make_uint2(n1.y, hitmask & 0x00FFFFFFu);
+    } else { tg = ng; ng = make_uint2(0u, 0u); }
+    while (tg.y) {
+      const int b = msb32(tg.y & (0u - tg.y));   // lowest set bit
+      tg.y &= tg.y - 1u;
+      const float4* tp = tris + 3 * (size_t)(tg.x + (uint32_t)b);
+      const float4 a = tp[0], bb = tp[1], cc = tp[2];
+      if (CNT) ++cntTris;
+      float t, u, v;
+      if (tri_intersect(o, d, mk3(a.x, a.y, a.z), mk3(a.w, bb.x, bb.y), mk3(bb.z, bb.w, cc.x), tmin, tmax, t, u, v)) {
+        if (ANY) { hit.t = t; hit.prim = f2u(cc.y); return true; }
+        const uint32_t prim = f2u(cc.y);
+        if (t < hit.t || (t == hit.t && prim < hit.prim)) { hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; }
+      }
+    }
+    if ((ng.y & 0xFF000000u) == 0u) {
+      if (sp == 0) break;
+      ng = stack[--sp];
+    }
+  }
+  return hit.prim != DDGI_MISS;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// shading: irradiance_probe_update.rchit + pbr_light.glsl + bindless.glsl + octahedron_helpers.glsl
+// ----------------------------------------------------------------------------------------------------
+struct TraceCtx {
+  const uint4* nodes; const float4* bvhTris; uint32_t numNodes;
+  const anerend_vertex_t* vertices; const uint32_t* indices; const anerend_material_info_t* materials;
+  const DInstance* instances; const InstXform* xforms; const uint32_t* triInstance;
+  const anerend_light_t* lights; uint32_t numLights;
+  const float4* dirs;          // [numLayers][N]: mat3(randomRot) * fibonacci dir, computed on the host (rgen:87-88)
+  const uint16_t* rayOrder;    // [N] slot -> ray index (direction-binned order), or null
+  const uint2* atlas;          // ProbeRaysConvTex, RGBA16F texels
+  uint2* rayIrr;               // ProbeRaysIrrTex replacement: [nY][P][N] RGBA16F
+  anerend_ddgi_ray_record_t* records;   // [nY][P][N] or null
+  unsigned long long* stats;   // 7 counters or null
+  int nXZ, nY, N, W, H;
+  int layerBegin, numLayers;
+  V3 camOff, step, sky, lightDir;
+  float tmin, tmax, sunIntensity;
+  uint32_t uboFlags, flags;
+};
+
+HD float sign_not_zero(float k) { return (k >= 0.0f) ? 1.0f : -1.0f; }            // octahedron_helpers.glsl:1-3
+HD void oct_encode(V3 v, float& ox, float& oy) {                                    // octahedron_helpers.glsl:10-20
+  V3 t = v; v.y = t.z; v.z = t.y;
+  float l1 = fabsf(v.x) + fabsf(v.y) + fabsf(v.z);
+  float inv = 1.0f / l1;
+  float rx = v.x * inv, ry = v.y * inv;
+  if (v.z < 0.0f) { float nx = (1.0f - fabsf(ry)) * sign_not_zero(rx), ny = (1.0f - fabsf(rx)) * sign_not_zero(ry); rx = nx; ry = ny; }
+  ox = rx; oy = ry;
+}
+HD V3 oct_decode(float ox, float oy) {                                              // octahedron_helpers.glsl:25-34
+  V3 v = mk3(ox, oy, 1.0f - fabsf(ox) - fabsf(oy));
+  if (v.z < 0.0f) { float nx = (1.0f - fabsf(v.y)) * sign_not_zero(v.x), ny = (1.0f - fabsf(v.x)) * sign_not_zero(v.y); v.x = nx; v.y = ny; }
+  V3 t = v; v.y = t.z; v.z = t.y;
+  return normalize3(v);
+}
+HD float to_linear1(float c) {                                                      // bindless.glsl:240-247
+  float higher = powf((c + 0.055f) / 1.055f, 2.4f), lower = c / 12.92f;
+  return (c < 0.04045f) ? lower : higher;
+}
+
+// pbr_light.glsl:10-43
+HD float distribution_ggx(V3 N, V3 Hh, float roughness) {
+  float a = roughness * roughness, a2 = a * a;
+  float NdotH = fmaxf(dot3(N, Hh), 0.0f), NdotH2 = NdotH * NdotH;
+  float num = a2 + 0.001f;
+  float denom = (NdotH2 * (a2 - 1.0f) + 1.0f);
+  denom = DDGI_PI * denom * denom;
+  return num / denom;
+}
+HD float geometry_schlick_ggx(float NdotV, float roughness) {
+  float r = (roughness + 1.0f), k = (r * r) / 8.0f;
+  return NdotV / (NdotV * (1.0f - k) + k);
+}
+HD float geometry_smith(V3 N, V3 V, V3 L, float roughness) {
+  float NdotV = fmaxf(dot3(N, V), 0.0f), NdotL = fmaxf(dot3(N, L), 0.0f);
+  float ggx2 = geometry_schlick_ggx(NdotV, roughness), ggx1 = geometry_schlick_ggx(NdotL, roughness);
+  return ggx1 * ggx2;
+}
+// pbr_light.glsl:98-166.  directional: the sun (L, radiance given); point light: caller passes L and radiance too.
+HD V3 calc_light(V3 N, V3 albedo, float metallic, float roughness, V3 worldPos, V3 viewPos, V3 L, V3 radiance) {
+  V3 V = normalize3(viewPos - worldPos);
+  V3 F0 = mix3(mk3(0.04f), albedo, metallic);
+  V3 Hh = normalize3(V + L);
+  float NDF = distribution_ggx(N, Hh, roughness);
+  float G = geometry_smith(N, V, L, roughness);
+  V3 F = F0 + (mk3(1.0f) - F0) * pow5(clampf(1.0f - fmaxf(dot3(Hh, V), 0.0f), 0.0f, 1.0f));   // fresnelSchlick :88-91
+  V3 kD = mk3(1.0f) - F; kD = kD * (1.0f - metallic);
+  float NdotL = fmaxf(dot3(N, L), 0.0f), NdotV = fmaxf(dot3(N, V), 0.0f);
+  V3 numerator = NDF * G * F;
+  float denominator = 4.0f * NdotV * NdotL + 0.0001f;
+  V3 specular = clamp3(numerator / denominator, 0.0f, 1.0f);
+  return mk3(0.0f) + (kD * albedo / DDGI_PI + specular) * radiance * NdotL;
+}
+
+// texel fetch + manual bilinear: VK_FILTER_LINEAR with REPEAT addressing (PipelineUtil.h:98-112), fp32 weights
+HD V3 atlas_texel(const TraceCtx& c, int x, int y) {
+  x %= c.W; if (x < 0) x += c.W; y %= c.H; if (y < 0) y += c.H;
+#ifdef __CUDA_ARCH__
+  uint2 t = __ldg(&c.atlas[(size_t)y * c.W + x]);
+#else
+  uint2 t = c.atlas[(size_t)y * c.W + x];
+#endif
+  return mk3(h2f((uint16_t)(t.x & 0xFFFFu)), h2f((uint16_t)(t.x >> 16)), h2f((uint16_t)(t.y & 0xFFFFu)));
+}
+HD V3 atlas_bilinear(const TraceCtx& c, float u, float v) {
+  float x = u * (float)c.W - 0.5f, y = v * (float)c.H - 0.5f;
+  float fx0 = floorf(x), fy0 = floorf(y);
+  float fx = x - fx0, fy = y - fy0; int ix = (int)fx0, iy = (int)fy0;
+  V3 t00 = atlas_texel(c, ix, iy), t10 = atlas_texel(c, ix + 1, iy), t01 = atlas_texel(c, ix, iy + 1), t11 = atlas_texel(c, ix + 1, iy + 1);
+  float w00 = (1.0f - fx) * (1.0f - fy), w10 = fx * (1.0f - fy), w01 = (1.0f - fx) * fy, w11 = fx * fy;
+  return t00 * w00 + t10 * w10 + t01 * w01 + t11 * w11;
+}
+// pbr_light.glsl:168-188 with octEncode(normalize(normal)) hoisted by the caller (same value for all 8 probes)
+HD V3 sample_single_probe(const TraceCtx& c, int px, int py, int pz, float o0, float o1) {
+  int startX = (8 + 2) * px + 1, startY = (8 + 2) * c.nXZ * py + (8 + 2) * pz + 1;
+  int endX = startX + 8 - 1, endY = startY + 8 - 1;
+  float tsx = (2.0f * (float)startX + 1.0f) / (2.0f * (float)c.W), tsy = (2.0f * (float)startY + 1.0f) / (2.0f * (float)c.H);
+  float tex = (2.0f * (float)endX + 1.0f) / (2.0f * (float)c.W), tey = (2.0f * (float)endY + 1.0f) / (2.0f * (float)c.H);
+  return atlas_bilinear(c, tsx + (tex - tsx) * o0, tsy + (tey - tsy) * o1);
+}
+// pbr_light.glsl:240-363 (live-grid branch :294-308) + weightProbe :190-238
+HD V3 sample_probe(const TraceCtx& c, V3 worldPos, V3 normal) {
+  int px = clampi((int)floorf((worldPos.x - c.camOff.x) / c.step.x), 0, c.nXZ - 1);
+  int py = clampi((int)floorf(worldPos.y / c.step.y), 0, c.nY - 1);
+  int pz = clampi((int)floorf((worldPos.z - c.camOff.z) / c.step.z), 0, c.nXZ - 1);
+  V3 base = mk3((float)px, (float)py, (float)pz) * c.step + c.camOff;
+  V3 alpha = clamp3((worldPos - base) / c.step, 0.0f, 1.0f);
+  float o0, o1; oct_encode(normalize3(normal), o0, o1);
+  o0 = (o0 + 1.0f) * 0.5f; o1 = (o1 + 1.0f) * 0.5f;
+  float sumW = 0.0f; V3 sum = mk3(0.0f);
+  // corner order of the source: 000,111,110,100,011,010,001,101 packed as x | y<<1 | z<<2 per nibble
+  const uint32_t order = 0x0u | (0x7u << 4) | (0x3u << 8) | (0x1u << 12) | (0x6u << 16) | (0x2u << 20) | (0x4u << 24) | (0x5u << 28);
+  for (int k = 0; k < 8; ++k) {
+    uint32_t o = (order >> (4 * k)) & 7u; int ox = (int)(o & 1u), oy = (int)((o >> 1) & 1u), oz = (int)((o >> 2) & 1u);
+    V3 probePos = (k == 0) ? base : base + mk3((float)ox, (float)oy, (float)oz) * c.step;
+    V3 tri = mk3(mixf(1.0f - alpha.x, alpha.x, (float)ox), mixf(1.0f - alpha.y, alpha.y, (float)oy), mixf(1.0f - alpha.z, alpha.z, (float)oz));
+    float weight = 1.0f;
+    V3 toProbe = normalize3(probePos - worldPos);
+    float wb = fmaxf(0.0001f, (dot3(toProbe, normal) + 1.0f) * 0.5f);
+    weight *= wb * wb + 0.2f;
+    weight = fmaxf(0.000001f, weight);
+    if (weight < 0.2f) weight *= weight * weight * (1.0f / (0.2f * 0.2f));    // dead code kept verbatim (:221-224)
+    weight *= tri.x * tri.y * tri.z;
+    V3 irr = sample_single_probe(c, px + ox, py + oy, pz + oz, o0, o1);
+    irr = mk3(sqrtf(irr.x), sqrtf(irr.y), sqrtf(irr.z));
+    sum = sum + weight * irr; sumW += weight;
+  }
+  V3 net = sum / sumW;
+  net = net * net;
+  return net * .5f * 3.1415926f;
+}
+HD V3 calc_indirect(const TraceCtx& c, V3 normal, V3 albedo, float metallic, float roughness, V3 worldPos, V3 viewPos) {   // :365-388
+  V3 V = normalize3(viewPos - worldPos);
+  V3 F0 = mix3(mk3(0.04f), albedo, metallic);
+  float rr = roughness * roughness;
+  V3 kS = F0 + (max3(mk3(1.0f - rr), F0) - F0) * pow5(clampf(1.0f - fmaxf(dot3(normal, V), 0.0f), 0.0f, 1.0f));   // fresnelSchlickRoughness :93-96
+  V3 kD = mk3(1.0f) - kS; kD = kD * (1.0f - metallic);
+  V3 irradiance = sample_probe(c, worldPos, normal);
+  return kD * (irradiance * albedo);
+}
+
+// rgen main + rchit main + rmiss main for one probe ray (rgen:48-111, rchit:24-111, rmiss:17-21)
+template <bool CNT>
+HD void trace_ray_body(uint32_t idx, const TraceCtx& c) {
+  const int P = c.nXZ * c.nXZ;
+  const uint32_t slot = idx % (uint32_t)c.N, probeLin = idx / (uint32_t)c.N;
+  const int layerLocal = (int)(probeLin / (uint32_t)P), probe = (int)(probeLin % (uint32_t)P);
+  const int layer = c.layerBegin + layerLocal;
+  const uint32_t ray = c.rayOrder ? (uint32_t)c.rayOrder[slot] : slot;
+  const int probeX = probe % c.nXZ, probeZ = probe / c.nXZ;
+  const V3 origin = mk3((float)probeX, (float)layer, (float)probeZ) * c.step + c.camOff;      // rgen:83
+  const float4 d4 = c.dirs[(size_t)layerLocal * c.N + ray];
+  const V3 d = mk3(d4.x, d4.y, d4.z);
+  uint32_t cn[2] = {0, 0}, ct[2] = {0, 0}, nShadow = 0, lit = 0;
+  Hit hit;
+  V3 rad;
+  if (traverse<false, CNT>(c.nodes, c.bvhTris, c.numNodes, origin, d, c.tmin, c.tmax, hit, cn[0], ct[0])) {
+    const uint32_t ii = c.triInstance[hit.prim];
+    const DInstance in = c.instances[ii];
+    const InstXform& xf = c.xforms[ii];
+    const uint32_t prim = hit.prim - in.firstTri;                                            // gl_PrimitiveID
+    const anerend_vertex_t* v0 = &c.vertices[in.vertexOffset + c.indices[in.indexOffset + 3 * prim + 0]];
+    const anerend_vertex_t* v1 = &c.vertices[in.vertexOffset + c.indices[in.indexOffset + 3 * prim + 1]];
+    const anerend_vertex_t* v2 = &c.vertices[in.vertexOffset + c.indices[in.indexOffset + 3 * prim + 2]];
+    const float b0 = 1.0f - hit.u - hit.v, b1 = hit.u, b2 = hit.v;
+    V3 pos = mk3(v0->pos[0], v0->pos[1], v0->pos[2]) * b0 + mk3(v1->pos[0], v1->pos[1], v1->pos[2]) * b1 + mk3(v2->pos[0], v2->pos[1], v2->pos[2]) * b2;
+    pos = xform_point(xf.o2w, pos);                                                          // rchit:42
+    V3 normal = normalize3(mk3(v0->normal[0], v0->normal[1], v0->normal[2]) * b0 + mk3(v1->normal[0], v1->normal[1], v1->normal[2]) * b1 +
+                           mk3(v2->normal[0], v2->normal[1], v2->normal[2]) * b2);
+    normal = normalize3(mk3(normal.x * xf.w2o[0] + normal.y * xf.w2o[1] + normal.z * xf.w2o[2],
+                            normal.x * xf.w2o[3] + normal.y * xf.w2o[4] + normal.z * xf.w2o[5],
+                            normal.x * xf.w2o[6] + normal.y * xf.w2o[7] + normal.z * xf.w2o[8]));   // rchit:73
+    V3 color = mk3(v0->color[0], v0->color[1], v0->color[2]) * b0 + mk3(v1->color[0], v1->color[1], v1->color[2]) * b1 +
+               mk3(v2->color[0], v2->color[1], v2->color[2]) * b2;
+    color = mk3(to_linear1(color.x), to_linear1(color.y), to_linear1(color.z));              // rchit:75
+    // getSurfaceDataFromMat, texture-free branches (bindless.glsl:181-237)
+    const anerend_material_info_t* m = &c.materials[in.material];
+    V3 albedo = color;
+    if (m->base_col_fac[0] + m->base_col_fac[1] + m->base_col_fac[2] > 0.1f) albedo = mk3(m->base_col_fac[0], m->base_col_fac[1], m->base_col_fac[2]);
+    const float metallic = m->met_rough[0], roughness = m->met_rough[1];
+    const V3 emissive = mk3(m->emissive[0], m->emissive[1], m->emissive[2]) * m->emissive[3];
+    // sun shadow ray (rchit:45-66): any-hit, origin = hit position without offset
+    const V3 sunL = normalize3(-c.lightDir);
+    Hit sh;
+    ++nShadow;
+    const bool occluded = traverse<true, CNT>(c.nodes, c.bvhTris, c.numNodes, pos, sunL, c.tmin, c.tmax, sh, cn[1], ct[1]);
+    V3 irradiance = mk3(0.0f);
+    if (!occluded) { lit |= 1u; irradiance = calc_light(normal, albedo, metallic, roughness, pos, origin, sunL, c.sunIntensity * mk3(1.0f) * 1.0f); }
+    if (c.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) {
+      // extension E1: enabled point lights, calcLight(directional = 0) gated by an any-hit ray pos -> light
+      for (uint32_t li = 0; li < c.numLights; ++li) {
+        const anerend_light_t* lt = &c.lights[li];
+        if (!(lt->color[3] > 0.5f)) continue;
+        const V3 lp = mk3(lt->world_pos[0], lt->world_pos[1], lt->world_pos[2]);
+        const V3 dv = lp - pos; const float dist = sqrtf(dot3(dv, dv)), range = lt->world_pos[3];
+        if (!(dist < range)) continue;
+        const V3 L = normalize3(lp - pos);
+        if (!(dot3(normal, L) > 0.0f)) continue;
+        ++nShadow;
+        if (traverse<true, CNT>(c.nodes, c.bvhTris, c.numNodes, pos, L, c.tmin, dist, sh, cn[1], ct[1])) continue;
+        lit |= 1u << (1u + li);
+        const float dd = fminf(dist, range);
+        const float att = (1.0f - dd / range) * (1.0f - dd / range) * 1.0f;
+        irradiance = irradiance + calc_light(normal, albedo, metallic, roughness, pos, origin, L, mk3(lt->color[0], lt->color[1], lt->color[2]) * att);
+      }
+    }
+    if ((c.uboFlags & ANEREND_UBO_DDGI_MULTI_FLAG) == ANEREND_UBO_DDGI_MULTI_FLAG)
+      irradiance = irradiance + calc_indirect(c, normal, albedo, metallic, roughness, pos, origin);   // rchit:98-107
+    rad = irradiance + emissive;                                                                      // rchit:109
+  } else {
+    rad = c.sky;                                                                                      // rmiss:20
+  }
+  const size_t o = ((size_t)layer * P + probe) * c.N + ray;
+  c.rayIrr[o] = make_uint2((uint32_t)f2h(rad.x) | ((uint32_t)f2h(rad.y) << 16), (uint32_t)f2h(rad.z) | (0x3C00u << 16));   // rgen:109
+  if (c.records) {
+    anerend_ddgi_ray_record_t r;
+    r.prim = hit.prim; r.t = hit.prim == DDGI_MISS ? 0.0f : hit.t; r.u = hit.u; r.v = hit.v;
+    r.radiance[0] = rad.x; r.radiance[1] = rad.y; r.radiance[2] = rad.z; r.lit_mask = lit;
+    c.records[o] = r;
+  }
+  if (CNT && c.stats) {
+    atomAdd64(&c.stats[0], 1ull); atomAdd64(&c.stats[1], hit.prim != DDGI_MISS ? 1ull : 0ull); atomAdd64(&c.stats[2], nShadow);
+    atomAdd64(&c.stats[3], cn[0]); atomAdd64(&c.stats[4], ct[0]); atomAdd64(&c.stats[5], cn[1]); atomAdd64(&c.stats[6], ct[1]);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// probe_conv.comp main (probe_conv.comp:21-90), live mode.  Thread per interior atlas texel.
+// ----------------------------------------------------------------------------------------------------
+struct ConvCtx {
+  const uint2* rayIrr; const float4* dirs;   // dirs: [numLayers][N] fp32, rounded to fp16 here like the rgba16f store (rgen:108)
+  uint2* atlas; float4* texelRecords;        // atlas written in place (or to every peer's copy, see peers)
+  uint2* peers[8]; int numPeers;
+  int nXZ, nY, N, Sx, Sy, W, H, layerBegin, numLayers;
+  float hysteresis;
+};
+HD void conv_texel_body(uint32_t idx, const ConvCtx& c) {
+  const int P = c.nXZ * c.nXZ;
+  const int texel = (int)(idx & 63u); const uint32_t probeLin = idx >> 6;
+  const int layerLocal = (int)(probeLin / (uint32_t)P), probe = (int)(probeLin % (uint32_t)P), layer = c.layerBegin + layerLocal;
+  const int i = texel & 7, j = texel >> 3, probeX = probe % c.nXZ, probeZ = probe / c.nXZ;
+  float ux = (2.0f * (float)i + 1.0f) / (2.0f * 8.0f), uy = (2.0f * (float)j + 1.0f) / (2.0f * 8.0f);     // pixelToUv, helpers.glsl:1-4
+  ux = ux * 2.0f - 1.0f; uy = uy * 2.0f - 1.0f;
+  const V3 octDir = oct_decode(ux, uy);
+  const uint2* irr = c.rayIrr + ((size_t)layer * P + probe) * c.N;
+  const float4* dirs = c.dirs + (size_t)layerLocal * c.N;
+  float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f, r3 = 0.0f;
+  for (int x = 0; x < c.Sx; ++x) for (int y = 0; y < c.Sy; ++y) {        // x outer, y inner (probe_conv.comp:49-50)
+    const int ray = y * c.Sx + x;
+    const uint2 rr = irr[ray]; const float4 d4 = dirs[ray];
+    const V3 rad = mk3(h2f((uint16_t)(rr.x & 0xFFFFu)), h2f((uint16_t)(rr.x >> 16)), h2f((uint16_t)(rr.y & 0xFFFFu)));
+    const V3 d = mk3(h2f(f2h(d4.x)), h2f(f2h(d4.y)), h2f(f2h(d4.z)));
+    const float w = fmaxf(0.0f, dot3(d, octDir));
+    if (w > 1e-6f) { r0 += w * rad.x; r1 += w * rad.y; r2 += w * rad.z; r3 += w; }
+  }
+  const int ax = 10 * probeX + 1 + i, ay = 10 * c.nXZ * layer + 10 * probeZ + 1 + j;       // pixOffset + pixel (:42,:64)
+  const size_t ti = (size_t)ay * c.W + ax;
+  const uint2 ot = c.atlas[ti];
+  const float o0 = h2f((uint16_t)(ot.x & 0xFFFFu)), o1 = h2f((uint16_t)(ot.x >> 16)), o2 = h2f((uint16_t)(ot.y & 0xFFFFu)), o3 = h2f((uint16_t)(ot.y >> 16));
+  if (r3 > 1e-6f) { r0 /= r3; r1 /= r3; r2 /= r3; }
+  const float hy = c.hysteresis;
+  const float n0 = r0 * (1.0f - hy) + o0 * hy, n1 = r1 * (1.0f - hy) + o1 * hy, n2 = r2 * (1.0f - hy) + o2 * hy, n3 = r3 * (1.0f - hy) + o3 * hy;
+  const uint2 nt = make_uint2((uint32_t)f2h(n0) | ((uint32_t)f2h(n1) << 16), (uint32_t)f2h(n2) | ((uint32_t)f2h(n3) << 16));
+  c.atlas[ti] = nt;
+  for (int p = 0; p < c.numPeers; ++p) c.peers[p][ti] = nt;               // fused all-gather: store into every peer's atlas
+  if (c.texelRecords) c.texelRecords[ti] = make_float4(n0, n1, n2, n3);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// IrradianceProbeTranslationPass.cpp:92-168: second vkCmdCopyImage (TempProbeTex -> atlas, shifted by one probe)
+// ----------------------------------------------------------------------------------------------------
+struct TransCtx { const uint2* temp; uint2* atlas; int W, nXZ, nY, dx, dz, ew, eh; };
+HD void translate_body(uint32_t idx, const TransCtx& c) {
+  const int x = (int)(idx % (uint32_t)c.ew); const uint32_t r = idx / (uint32_t)c.ew;
+  const int y = (int)(r % (uint32_t)c.eh), layer = (int)(r / (uint32_t)c.eh);
+  const int pps = 10, planeY = layer * pps * c.nXZ;
+  int sx = 0, sy = planeY, dxo = 0, dyo = planeY;
+  if (c.dx > 0) sx = pps; else if (c.dx < 0) dxo = pps;
+  if (c.dz > 0) sy += pps; else if (c.dz < 0) dyo += pps;
+  c.atlas[(size_t)(dyo + y) * c.W + dxo + x] = c.temp[(size_t)(sy + y) * c.W + sx + x];
+}
+struct ClearCtx { uint2* atlas; uint2* temp; };
+HD void clear_body(uint32_t idx, const ClearCtx& c) {     // clearConvTex: (0,0,0,1), IrradianceProbeConvolvePass.cpp:20-24
+  c.atlas[idx] = make_uint2(0u, 0x3C000000u);
+  c.temp[idx] = make_uint2(0u, 0x3C000000u);
+}
+
+}  // namespace ddgi

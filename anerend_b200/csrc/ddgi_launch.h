@@ -1,0 +1,109 @@
+// ddgi_launch.h — backend shim: CUDA runtime (product) or serial host loops (tests/host_emu debug harness).
+#pragma once
+#include "ddgi_kernels.cuh"
+
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+
+#ifndef DDGI_HOST_EMU
+// ---------------------------------------------------------------------------------------------- CUDA
+#include <cub/device/device_radix_sort.cuh>
+#define DDGI_API(name) anerend_cuda_ddgi_##name
+
+#define DDGI_KERNEL(kname, body, CtxT)                                                   \
+  __global__ void __launch_bounds__(256) kname(uint32_t n, const CtxT ctx) {             \
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;                                  \
+    if (i < n) body(i, ctx);                                                             \
+  }
+#define DDGI_LAUNCH(be, kname, body, n, ctx, block)                                      \
+  do { if ((n) > 0) { kname<<<((n) + (block) - 1) / (block), (block), 0, (be).stream>>>((uint32_t)(n), ctx); ++(be).launches; } } while (0)
+
+namespace ddgi {
+struct Backend {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t evCopy = nullptr; bool copyPending = false;
+  uint32_t launches = 0;
+  cudaError_t lastErr = cudaSuccess;
+  bool ok(cudaError_t e) { if (e != cudaSuccess) { lastErr = e; return false; } return true; }
+  const char* errStr() const { return cudaGetErrorString(lastErr); }
+  bool init(int device) {
+    int cnt = 0;
+    if (!ok(cudaGetDeviceCount(&cnt)) || cnt == 0) return false;
+    if (device >= 0 && !ok(cudaSetDevice(device))) return false;
+    if (!ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking))) return false;
+    for (auto& e : ev) if (!ok(cudaEventCreate(&e))) return false;
+    return ok(cudaEventCreateWithFlags(&evCopy, cudaEventDisableTiming));
+  }
+  void destroy() { for (auto& e : ev) if (e) cudaEventDestroy(e); if (evCopy) cudaEventDestroy(evCopy); if (stream) cudaStreamDestroy(stream); }
+  void waitCopy() { if (copyPending) { cudaEventSynchronize(evCopy); copyPending = false; } }
+  void markCopy() { cudaEventRecord(evCopy, stream); copyPending = true; }
+  template <class T> bool alloc(T** p, size_t count) { *p = nullptr; return ok(cudaMalloc((void**)p, (count ? count : 1) * sizeof(T))); }
+  void free(void* p) { if (p) cudaFree(p); }
+  template <class T> bool allocHostPinned(T** p, size_t count) { return ok(cudaMallocHost((void**)p, (count ? count : 1) * sizeof(T))); }
+  void freeHostPinned(void* p) { if (p) cudaFreeHost(p); }
+  bool h2d(void* dst, const void* src, size_t bytes) { return bytes == 0 || ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream)); }
+  bool d2h(void* dst, const void* src, size_t bytes) {
+    return bytes == 0 || (ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream)) && ok(cudaStreamSynchronize(stream)));
+  }
+  bool d2d(void* dst, const void* src, size_t bytes) { return bytes == 0 || ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream)); }
+  bool zero(void* p, size_t bytes) { return bytes == 0 || ok(cudaMemsetAsync(p, 0, bytes, stream)); }
+  bool sync() { return ok(cudaStreamSynchronize(stream)); }
+  bool check() { return ok(cudaGetLastError()); }
+  void mark(int i) { cudaEventRecord(ev[i], stream); }
+  float elapsed(int a, int b) { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev[a], ev[b]) != cudaSuccess) { cudaGetLastError(); return 0.0f; } return ms; }
+  bool sortPairs(const uint32_t* kin, uint32_t* kout, const uint32_t* vin, uint32_t* vout, uint32_t n) {
+    // 30-bit Morton keys.  CUB's DeviceRadixSort is the onesweep (single-pass, decoupled look-back) radix sort.
+    size_t bytes = 0; void* tmp = nullptr;
+    if (!ok(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, 30, stream))) return false;
+    if (!ok(cudaMalloc(&tmp, bytes ? bytes : 1))) return false;
+    bool r = ok(cub::DeviceRadixSort::SortPairs(tmp, bytes, kin, kout, vin, vout, (int)n, 0, 30, stream));
+    launches += 4;
+    cudaStreamSynchronize(stream); cudaFree(tmp);
+    return r;
+  }
+};
+}  // namespace ddgi
+
+#else
+// ------------------------------------------------------------------------------------------ host emu
+#include <algorithm>
+#include <numeric>
+#include <vector>
+#define DDGI_API(name) anerend_emu_ddgi_##name
+#define DDGI_KERNEL(kname, body, CtxT)
+#define DDGI_LAUNCH(be, kname, body, n, ctx, block) \
+  do { for (uint32_t i_ = 0; i_ < (uint32_t)(n); ++i_) body(i_, ctx); ++(be).launches; } while (0)
+
+namespace ddgi {
+struct Backend {
+  void* stream = nullptr;
+  uint32_t launches = 0;
+  std::chrono::steady_clock::time_point tp[6];
+  const char* errStr() const { return "host emulation"; }
+  bool init(int) { return true; }
+  void destroy() {}
+  void waitCopy() {}
+  void markCopy() {}
+  template <class T> bool alloc(T** p, size_t count) { *p = (T*)calloc(count ? count : 1, sizeof(T)); return *p != nullptr; }
+  void free(void* p) { ::free(p); }
+  template <class T> bool allocHostPinned(T** p, size_t count) { return alloc(p, count); }
+  void freeHostPinned(void* p) { ::free(p); }
+  bool h2d(void* d, const void* s, size_t b) { if (b) memcpy(d, s, b); return true; }
+  bool d2h(void* d, const void* s, size_t b) { if (b) memcpy(d, s, b); return true; }
+  bool d2d(void* d, const void* s, size_t b) { if (b) memcpy(d, s, b); return true; }
+  bool zero(void* p, size_t b) { if (b) memset(p, 0, b); return true; }
+  bool sync() { return true; }
+  bool check() { return true; }
+  void mark(int i) { tp[i] = std::chrono::steady_clock::now(); }
+  float elapsed(int a, int b) { return std::chrono::duration<float, std::milli>(tp[b] - tp[a]).count(); }
+  bool sortPairs(const uint32_t* kin, uint32_t* kout, const uint32_t* vin, uint32_t* vout, uint32_t n) {
+    std::vector<uint32_t> idx(n); std::iota(idx.begin(), idx.end(), 0u);
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return kin[a] < kin[b]; });
+    for (uint32_t i = 0; i < n; ++i) { kout[i] = kin[idx[i]]; vout[i] = vin[idx[i]]; }
+    return true;
+  }
+};
+}  // namespace ddgi
+#endif

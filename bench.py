@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py — DDGI probe-update throughput (BASELINE.json metric) on N B200s of one node.
+
+A "step" is one full-grid DDGI probe update (translate if needed -> trace+shade all layers -> convolve) of one
+synthetic workload:
+    c3 (default at N=1): Sponza-scale mesh (~262k tris, 64 materials, 8 lights), 24x12x24 probes x 256 rays + shadow rays
+    c5 (default at N>1): large volume (~2M tris), 64x32x64 probes x 256 rays, Y-slab sharded + atlas all-gather
+    c2                 : Cornell box (~10k tris), 16x8x16 probes x 128 rays
+`value` = primary probe rays of all ranks / device time (CUDA events on the handle's stream, max over ranks), inputs
+resident in HBM.  `e2e` = the same through the public API with host buffers: per step the scene UBO + rotation matrices
+go host->device and the atlas comes back to pinned host memory, wall-clocked.  `--impl reference` times the CPU oracle
+(the reference has no CPU path; the oracle is its shader transliteration) on the box's host cores instead.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ddgi_probe_update_primary_mrays_per_s"
+UNIT = "Mrays/s"
+
+
+def build_workload(name):
+    from anerend_b200 import scenes
+    if name == "c2":
+        return scenes.cornell_box(), (16, 8, 128), 2
+    if name == "c3":
+        return scenes.sponza_like(), (24, 12, 256), 3
+    if name == "c5":
+        return scenes.large_volume(), (64, 32, 256), 5
+    raise SystemExit(f"unknown workload {name}")
+
+
+def workload_desc(name, scene, grid, world):
+    nxz, ny, nr = grid
+    return {"workload": name, "scene": scene.name, "triangles": int(scene.num_triangles),
+            "probes": f"{nxz}x{ny}x{nxz}", "rays_per_probe": nr, "primary_rays_per_update": nxz * nxz * ny * nr,
+            "lights": int(len(scene.lights)), "point_lights_E1": True, "multi_bounce": True,
+            "mode": "jacobi full-grid update", "parallelism": f"y-slab x{world}" if world > 1 else "single GPU"}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz, self._stop_evt, self.index = [], set(), None, threading.Event(), index
+
+    def run(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                     0x80: "hw_power_brake_slowdown"}
+            while not self._stop_evt.is_set():
+                self.samples.append(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
+                try:
+                    r = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.01)
+        except Exception as e:  # NVML unavailable: report that instead of guessing
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def algorithmic_bytes(stats, rays):
+    """80 B per BVH8 node fetched + 48 B per triangle tested (closest-hit and any-hit), per hit
+    12 B indices + 288 B vertices + 64 B material + 256 B of previous-atlas texels, per ray 8 B RGBA16F radiance out."""
+    nodes = stats["primary_nodes_visited"] + stats["shadow_nodes_visited"]
+    tris = stats["primary_tris_tested"] + stats["shadow_tris_tested"]
+    return 80 * nodes + 48 * tris + stats["primary_hits"] * (12 + 288 + 64 + 256) + rays * 8
+
+
+def run_oracle_sample(scene, grid, layers, threads=0, point_lights=True):
+    """Times the CPU oracle on `layers` of the workload; returns (rays, seconds, threads)."""
+    from anerend_b200 import layouts as L, make_params, scenes
+    from oracle import binding as ob
+    nxz, ny, nr = grid
+    o = ob.Oracle(make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS if point_lights else 0))
+    nthreads = o.set_threads(threads)
+    o.upload_scene(scene)
+    o.set_scene_ubo(scene.ubo)
+    o.build_accel()
+    rots = o.rotations(scenes.rotation_sequence(scene.seed, ny))
+    t0 = time.perf_counter()
+    for layer in layers:
+        o.update(layer, rots[layer])
+    dt = time.perf_counter() - t0
+    o.close()
+    return len(layers) * nxz * nxz * nr, dt, nthreads
+
+
+def reference_arm(args, rank, world):
+    """The reference's CPU implementation of the path = the oracle (there is no oracle/_ref: GLSL + Vulkan RT cannot
+    be built here).  Rank 0 alone runs; each step is a bounded sample (one Y-layer) of the workload."""
+    if rank != 0:
+        return
+    name = args.workload or ("c3" if world == 1 else "c5")
+    scene, grid, _ = build_workload(name)
+    from anerend_b200 import layouts as L, make_params, scenes
+    from oracle import binding as ob
+    nxz, ny, nr = grid
+    o = ob.Oracle(make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS))
+    threads = o.set_threads(0)
+    o.upload_scene(scene)
+    o.set_scene_ubo(scene.ubo)
+    o.build_accel()
+    rots = o.rotations(scenes.rotation_sequence(scene.seed, ny))
+    per_step = nxz * nxz * nr
+    for w in range(args.warmup):
+        o.update(w % ny, rots[w % ny])
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        o.update(k % ny, rots[k % ny])
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt / 1e6
+    sample = f"{args.steps} steps x 1 Y-layer ({per_step} primary rays + their shadow rays) of {name}"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_desc(name, scene, grid, 1),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, choices=[None, "c2", "c3", "c5"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fused-gather", action="store_true", help="convolution stores texels into peers' atlases (no NCCL call)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import anerend_b200 as A
+    from anerend_b200 import layouts as L, scenes, sharding
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    name = args.workload or ("c3" if world == 1 else "c5")
+    scene, grid, seed = build_workload(name)
+    nxz, ny, nr = grid
+    slab = sharding.slab_for_rank(ny, rank, world)
+    flags = L.FLAG_POINT_LIGHTS
+    h = A.Ddgi(A.make_params(nxz, ny, nr, flags=flags, slab=slab, device=local_rank))
+    h.upload_scene(scene)
+    h.set_scene_ubo(scene.ubo)
+    h.build_accel()
+    accel_ms = h.timings()["accel_ms"]
+    info = h.bvh_info()
+    stream = torch.cuda.ExternalStream(h.stream(), device=torch.device("cuda", local_rank))
+    ptr, nbytes = h.atlas_device_ptr()
+    atlas_t = torch.as_tensor(sharding.DeviceArray(ptr, (h.atlas_height, h.atlas_width, 4)), device=f"cuda:{local_rank}")
+    row_b, row_e = sharding.slab_rows(nxz, slab)
+    host_atlas = torch.empty((h.atlas_height, h.atlas_width, 4), dtype=torch.int16, pin_memory=True)   # pinned result buffer
+    host_np = host_atlas.numpy().view(np.uint16)
+
+    total_steps = args.warmup + args.steps
+    seq = scenes.rotation_sequence(seed, ny * total_steps)
+    rots = h.rotations(seq).reshape(total_steps, ny, 16)
+    my_rays = nxz * nxz * (slab[1] - slab[0]) * nr
+    all_rays = nxz * nxz * ny * nr
+
+    # working set vs L2 (126 MB): flush between timed iterations when everything would stay cached
+    working_set = info.num_nodes * 80 + info.num_triangles * 48 + scene.vertices.nbytes + scene.indices.nbytes + nbytes + my_rays * 8
+    flush = working_set < 256e6
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}") if flush else None
+
+    def gather():
+        if world > 1 and not args.fused_gather:
+            with torch.cuda.stream(stream):
+                sharding.all_gather_atlas(atlas_t, nxz, ny, rank, world)
+
+    def step(k):
+        h.set_scene_ubo(scene.ubo)
+        h.translate()
+        h.update(-1, rots[k])
+        gather()
+
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.warmup):
+        step(k)
+    h.sync()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    rt_ms, conv_ms, launches = [], [], 0
+    for k in range(args.steps):
+        if flush:
+            with torch.cuda.stream(stream):
+                flush_buf.fill_(k & 0xFF)
+        ev[k][0].record(stream)
+        step(args.warmup + k)
+        ev[k][1].record(stream)
+        t = h.timings()                      # synchronises the handle's stream
+        rt_ms.append(t["rt_ms"])
+        conv_ms.append(t["convolve_ms"])
+        launches += t["kernel_launches"] + (1 if world > 1 and not args.fused_gather else 0)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    if world > 1:
+        tt = torch.tensor([dev_ms], device=f"cuda:{local_rank}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms = float(tt.item())
+    ms_per_step = dev_ms / args.steps
+    value = all_rays / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e: host buffers in, atlas back to pinned host memory, wall clock ---------------------------------
+    e2e_steps = max(3, min(args.steps, 50))
+    h.sync()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        step(args.warmup + (k % args.steps))
+        h.download_atlas(host_np)            # D2H of the result (synchronous)
+    h.sync()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], device=f"cuda:{local_rank}")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_value = all_rays * e2e_steps / e2e_s / 1e6
+    h2d_bytes = (slab[1] - slab[0]) * nr * 16 + 568 + 64 * ny
+    d2h_bytes = nbytes
+
+    line = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel (k_probe_trace): counted, untimed run of the same update ----------
+        hc = A.Ddgi(A.make_params(nxz, ny, nr, flags=flags | L.FLAG_COUNTERS, slab=slab, device=local_rank))
+        hc.upload_scene(scene)
+        hc.set_scene_ubo(scene.ubo)
+        hc.build_accel()
+        hc.update(-1, rots[args.warmup])
+        stats = hc.stats()
+        hc.close()
+        peak, peak_src = peaks()
+        abytes = algorithmic_bytes(stats, my_rays)
+        rt_avg = float(np.mean(rt_ms))
+        achieved = abytes / (rt_avg * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(name, {}).get("k_probe_trace_dram_bytes_per_launch")
+        roofline = {"bound": "hbm", "kernel": "k_probe_trace", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": abytes, "kernel_ms_avg": rt_avg,
+                    "kernel_share_of_step": rt_avg / ms_per_step,
+                    "nodes_per_primary_ray": stats["primary_nodes_visited"] / max(1, stats["primary_rays"]),
+                    "tris_per_primary_ray": stats["primary_tris_tested"] / max(1, stats["primary_rays"]),
+                    "shadow_rays_per_primary": stats["shadow_rays"] / max(1, stats["primary_rays"]),
+                    "hit_fraction": stats["primary_hits"] / max(1, stats["primary_rays"])}
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            layers = list(range(ny)) if name != "c5" else list(range(0, ny, 8))
+            rays, secs, threads = run_oracle_sample(scene, grid, layers)
+            cpu_baseline = {"value": rays / secs / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+                            "sample": f"{len(layers)} of {ny} Y-layers of {name} ({rays} primary rays + shadow rays), "
+                                      f"{secs:.2f} s, multithreaded C++ oracle (shader transliteration)"}
+        cfg = workload_desc(name, scene, grid, world)
+        cfg.update({"l2": "flushed between timed iterations (256 MiB write)" if flush else "working set larger than L2, no flush",
+                    "bvh8_nodes": int(info.num_nodes), "accel_build_ms": accel_ms,
+                    "atlas_exchange": ("fused peer stores" if args.fused_gather else "nccl all_gather") if world > 1 else "none"})
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                        "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps},
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "update_ms": {"trace": rt_avg, "convolve": float(np.mean(conv_ms)), "full_grid": ms_per_step}}
+    h.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,206 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes), against the CPU oracle on the same seeded
+inputs — hit primitive ids bit-exact, per-ray radiance and convolved texels within 1e-4 relative (north_star), stored
+RGBA16F within one half ulp — plus size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+
+from anerend_b200 import layouts as L, make_params, scenes
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+ALL = L.FLAG_RAY_RECORDS | L.FLAG_POINT_LIGHTS | L.FLAG_TEXEL_RECORDS | L.FLAG_COUNTERS
+
+SCENES = {
+    "cornell_small": lambda: (scenes.cornell_box(grid=(8, 4, 64), wall_res=10, box_res=3), (8, 4, 64)),
+    "soup11": lambda: (scenes.random_soup(11), (4, 3, 64)),
+    "soup12_128rays": lambda: (scenes.random_soup(12, ntris=900, grid=(3, 2, 128)), (3, 2, 128)),
+    "soup13_256rays": lambda: (scenes.random_soup(13, ntris=5000, grid=(5, 2, 256)), (5, 2, 256)),
+    "quad": lambda: (scenes.quad_scene(second_quad=True), (4, 2, 64)),
+    "empty": lambda: (scenes.empty_scene(grid=(4, 2, 64)), (4, 2, 64)),
+}
+
+
+def _check_update(o, g, ny, mismatch_frac=0.0):
+    total_mism = 0
+    for layer in range(ny):
+        total_mism += parity.compare_records(o.download_ray_records(layer), g.download_ray_records(layer), mismatch_frac)
+        io, do = o.download_rays(layer)
+        ig, dg = g.download_rays(layer)
+        assert np.array_equal(do, dg), "ProbeRaysDirTex differs"
+        d = parity.half_ulp_distance(io, ig)
+        assert (d > 1).mean() <= mismatch_frac, "ProbeRaysIrrTex differs by more than one half ulp"
+    return total_mism
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_full_update_matches_oracle(name, oracle, make_gpu):
+    scene, (nxz, ny, nr) = SCENES[name]()
+    p = make_params(nxz, ny, nr, flags=ALL)
+    o, g = oracle.Oracle(p), make_gpu(p)
+    rots = parity.setup_pair(scene, (o, g), seed=3)
+    assert o.bvh_info().num_triangles == g.bvh_info().num_triangles == scene.num_triangles
+    for it in range(3):
+        for h in (o, g):
+            h.translate()
+            h.update(-1, rots)
+        _check_update(o, g, ny)
+        parity.compare_atlas(o.download_atlas(), g.download_atlas())
+        err = parity.rel_err(g.download_texel_records(), o.download_texel_records(), floor=1e-4)
+        assert err.max() <= parity.TEXEL_REL_TOL, f"texel rel err {err.max():.3e}"
+    st = g.stats()
+    assert st["primary_rays"] == 3 * nxz * nxz * ny * nr
+    so = o.stats()
+    assert st["primary_hits"] == so["primary_hits"] and st["shadow_rays"] == so["shadow_rays"]
+    o.close()
+    g.close()
+
+
+def test_without_debug_flags_gives_the_same_atlas(oracle, make_gpu):
+    """The measured configuration (no records, no counters) must produce the same stored atlas as the checked one."""
+    scene = scenes.cornell_box(grid=(8, 4, 64), wall_res=10, box_res=3)
+    pa, pb = make_params(8, 4, 64, flags=ALL), make_params(8, 4, 64, flags=L.FLAG_POINT_LIGHTS)
+    a, b = make_gpu(pa), make_gpu(pb)
+    rots = parity.setup_pair(scene, (a, b), seed=9)
+    for _ in range(3):
+        a.update(-1, rots)
+        b.update(-1, rots)
+    assert np.array_equal(a.download_atlas(), b.download_atlas())
+    a.close()
+    b.close()
+
+
+def test_config2_cornell_full(oracle, make_gpu):
+    """BASELINE config C2: ~10k-triangle Cornell box, 16x8x16 probes x 128 rays, sun + 1 point light (E1)."""
+    scene = scenes.cornell_box()
+    p = make_params(16, 8, 128, flags=ALL)
+    o, g = oracle.Oracle(p), make_gpu(p)
+    rots = parity.setup_pair(scene, (o, g), seed=2)
+    for it in range(2):
+        for h in (o, g):
+            h.translate()
+            h.update(-1, rots)
+    _check_update(o, g, 8)
+    parity.compare_atlas(o.download_atlas(), g.download_atlas())
+    # faithful subset (sun only, reference rchit) separately from extension E1
+    p2 = make_params(16, 8, 128, flags=L.FLAG_RAY_RECORDS | L.FLAG_TEXEL_RECORDS)
+    o2, g2 = oracle.Oracle(p2), make_gpu(p2)
+    rots = parity.setup_pair(scene, (o2, g2), seed=2)
+    for h in (o2, g2):
+        h.update(-1, rots)
+    _check_update(o2, g2, 8)
+    parity.compare_atlas(o2.download_atlas(), g2.download_atlas())
+    for h in (o, g, o2, g2):
+        h.close()
+
+
+def test_sequential_layers_frame_cadence_and_translation(oracle, make_gpu):
+    scene = scenes.random_soup(21, ntris=600)
+    p = make_params(4, 3, 64, flags=ALL)
+    o, g = oracle.Oracle(p), make_gpu(p)
+    rots = parity.setup_pair(scene, (o, g), seed=4)
+    rng = np.random.RandomState(0)
+    cam = np.array([0.3, 2.0, -0.2])
+    for f in range(9):
+        cam = cam + rng.uniform(-0.9, 0.9, 3) * (1, 0, 1)
+        ubo = scene.with_camera(cam)
+        for h in (o, g):
+            h.set_scene_ubo(ubo)
+        lo, lg = o.frame(rots[f % 3]), g.frame(rots[f % 3])
+        assert lo == lg == f % 3
+        parity.compare_atlas(o.download_atlas(), g.download_atlas())
+    g.trace_layer(1, rots[1])
+    g.convolve_layer(1)
+    o.update(1, rots[1])
+    parity.compare_atlas(o.download_atlas(), g.download_atlas())
+    g.reset()
+    o.reset()
+    assert np.array_equal(o.download_atlas(), g.download_atlas())
+    o.close()
+    g.close()
+
+
+def test_bvh8_structure_and_refit(oracle, make_gpu):
+    scene = scenes.sponza_like(seed=4, grid=(6, 3, 64), movers=6, curtain_res=6)
+    keep = list(range(0, 12)) + [m[0] for m in scene.movers]
+    vis = np.zeros(len(scene.renderables), np.uint32)
+    vis[keep] = 1
+    scene.renderables["visible"] = vis
+    p = make_params(6, 3, 64, flags=ALL)
+    o, g = oracle.Oracle(p), make_gpu(p)
+    rots = parity.setup_pair(scene, (o, g), seed=6)
+    nodes, tris = g.download_bvh()
+    parity.validate_bvh8(nodes, tris, g.bvh_info().num_triangles)
+    for k in range(3):
+        rend = scene.animated_renderables(0.4 * (k + 1))
+        for h in (o, g):
+            h.refit_accel(rend)
+            h.update(-1, rots)
+        _check_update(o, g, 3)
+        parity.compare_atlas(o.download_atlas(), g.download_atlas())
+    nodes, tris = g.download_bvh()
+    parity.validate_bvh8(nodes, tris, g.bvh_info().num_triangles)
+    o.close()
+    g.close()
+
+
+def test_config3_sponza_scale_layers_and_properties(oracle, make_gpu):
+    """BASELINE config C3 at full size: 24x12x24 probes x 256 rays over ~262k triangles.  Three layers are compared ray
+    by ray with the oracle; the whole grid is checked through size-independent properties."""
+    scene = scenes.sponza_like()
+    assert abs(scene.num_triangles - 262144) / 262144 < 0.02
+    p = make_params(24, 12, 256, flags=ALL)
+    o, g = oracle.Oracle(p), make_gpu(p)
+    rots = parity.setup_pair(scene, (o, g), seed=3)
+    g.update(-1, rots)                                        # whole grid on the GPU
+    total, mism = 0, 0
+    for layer in (0, 2, 5):
+        o.trace_layer(layer, rots[layer])                     # the cleared atlas is what both sides sampled
+        ro, rg = o.download_ray_records(layer), g.download_ray_records(layer)
+        mism += parity.compare_records(ro, rg, allow_mismatch_frac=1e-5)
+        total += ro.size
+        o.convolve_layer(layer)
+    ao, ag = o.download_atlas(), g.download_atlas()
+    W = 240
+    for layer in (0, 2, 5):
+        rows = slice(layer * W, (layer + 1) * W)
+        d = parity.half_ulp_distance(ao[rows], ag[rows])
+        assert (d > 1).mean() <= 1e-5
+    # properties of the whole grid
+    a = ag.view(np.float16).astype(np.float32)
+    mask = parity.interior_mask(24, 12)
+    assert np.isfinite(a).all() and (a[..., :3] >= 0).all()
+    assert np.all(ag[~mask][:, :3] == 0) and np.all(ag[~mask][:, 3] == 0x3C00)      # borders untouched
+    # alpha channel carries 0.04*sum(w) + 0.96*1 (quirk Q9); sum(w) ~ N/4 for every texel
+    alpha = a[..., 3][mask]
+    assert np.all(np.abs(alpha - (0.04 * 64.0 + 0.96)) < 0.05)
+    st = g.stats()
+    assert st["primary_rays"] == 24 * 24 * 12 * 256
+    # a second update must brighten shadowed texels (multi-bounce reads the previous atlas) and stay finite
+    g.update(-1, rots)
+    a2 = g.download_atlas().view(np.float16).astype(np.float32)
+    assert np.isfinite(a2).all() and a2[..., :3][mask].sum() > a[..., :3][mask].sum()
+    print(f"C3: compared {total} rays, {mism} hit-id mismatches; stats {st}")
+    o.close()
+    g.close()
+
+
+def test_slab_handles_assemble_the_full_atlas(oracle, make_gpu):
+    """Multi-GPU sharding on one device: two handles owning disjoint Y-slabs produce, after exchanging slabs, exactly the
+    atlas a single full-grid handle produces (jacobi semantics)."""
+    scene = scenes.cornell_box(grid=(8, 4, 64), wall_res=10, box_res=3)
+    full = make_gpu(make_params(8, 4, 64, flags=L.FLAG_POINT_LIGHTS))
+    parts = [make_gpu(make_params(8, 4, 64, flags=L.FLAG_POINT_LIGHTS, slab=s)) for s in ((0, 2), (2, 4))]
+    rots = parity.setup_pair(scene, [full] + parts, seed=8)
+    W = 80
+    for it in range(3):
+        full.update(-1, rots)
+        for h in parts:
+            h.update(-1, rots)
+        slabs = [h.download_atlas() for h in parts]
+        merged = slabs[0].copy()
+        merged[2 * W:] = slabs[1][2 * W:]
+        for h in parts:
+            h.upload_atlas(merged)                           # what the all-gather does
+        assert np.array_equal(merged, full.download_atlas())
+    for h in [full] + parts:
+        h.close()

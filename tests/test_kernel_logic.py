@@ -1,0 +1,159 @@
+"""CPU checks of the product's kernel LOGIC: the per-thread kernel bodies (csrc/ddgi_kernels.cuh) compiled for the
+host by the debug harness tests/host_emu, compared with the oracle.  The harness shares no code with oracle/; it is
+the product's own flatten / LBVH / BVH8-collapse / traversal / shading / convolution / translation run serially.
+The `-m gpu` tests repeat these comparisons with the real CUDA kernels through the C ABI.
+"""
+import numpy as np
+import pytest
+
+from anerend_b200 import layouts as L, make_params, scenes
+from tests import parity
+
+ALL = L.FLAG_RAY_RECORDS | L.FLAG_POINT_LIGHTS | L.FLAG_TEXEL_RECORDS | L.FLAG_COUNTERS
+
+SCENES = {
+    "cornell": lambda: (scenes.cornell_box(grid=(8, 4, 64), wall_res=10, box_res=3), (8, 4, 64)),
+    "soup11": lambda: (scenes.random_soup(11), (4, 3, 64)),
+    "soup12_128rays": lambda: (scenes.random_soup(12, ntris=900, grid=(3, 2, 128)), (3, 2, 128)),
+    "quad": lambda: (scenes.quad_scene(second_quad=True), (4, 2, 64)),
+    "empty": lambda: (scenes.empty_scene(grid=(4, 2, 64)), (4, 2, 64)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_full_update_matches_oracle(name, oracle, make_emu):
+    scene, (nxz, ny, nr) = SCENES[name]()
+    p = make_params(nxz, ny, nr, flags=ALL)
+    o, e = oracle.Oracle(p), make_emu(p)
+    rots = parity.setup_pair(scene, (o, e), seed=3)
+    assert o.bvh_info().num_triangles == e.bvh_info().num_triangles == scene.num_triangles
+    for it in range(2):                       # 2nd update reads a non-trivial previous atlas (multi-bounce)
+        for h in (o, e):
+            h.translate()
+            h.update(-1, rots)
+        for layer in range(ny):
+            parity.compare_records(o.download_ray_records(layer), e.download_ray_records(layer))
+            io, do = o.download_rays(layer)
+            ie, de = e.download_rays(layer)
+            assert np.array_equal(do, de)
+            assert parity.half_ulp_distance(io, ie).max() <= 1
+        assert parity.compare_atlas(o.download_atlas(), e.download_atlas()) > 0.99
+        err = parity.rel_err(e.download_texel_records(), o.download_texel_records(), floor=1e-4)
+        assert err.max() <= parity.TEXEL_REL_TOL
+    st = e.stats()
+    assert st["primary_rays"] == 2 * nxz * nxz * ny * nr and st["primary_hits"] <= st["primary_rays"]
+    o.close()
+    e.close()
+
+
+def test_sequential_layer_mode_and_frame_cadence(oracle, make_emu):
+    scene = scenes.random_soup(21, ntris=600)
+    p = make_params(4, 3, 64, flags=ALL)
+    o, e = oracle.Oracle(p), make_emu(p)
+    rots = parity.setup_pair(scene, (o, e), seed=4)
+    seen = []
+    for f in range(7):                        # reference cadence: one layer per frame, round-robin (RayTracingPass.cpp:112,160-164)
+        lo, le = o.frame(rots[f % 3]), e.frame(rots[f % 3])
+        assert lo == le == f % 3
+        seen.append(le)
+        assert parity.compare_atlas(o.download_atlas(), e.download_atlas()) > 0.99
+    # separate trace/convolve calls == update(layer)
+    e.trace_layer(1, rots[1])
+    e.convolve_layer(1)
+    o.update(1, rots[1])
+    parity.compare_atlas(o.download_atlas(), e.download_atlas())
+    o.close()
+    e.close()
+
+
+def test_translation_matches_oracle(oracle, make_emu):
+    scene = scenes.random_soup(31, ntris=400)
+    p = make_params(4, 2, 64)
+    o, e = oracle.Oracle(p), make_emu(p)
+    rots = parity.setup_pair(scene, (o, e), seed=5)
+    rng = np.random.RandomState(0)
+    cam = np.array([0.3, 2.0, -0.2])
+    for step in range(8):
+        cam = cam + rng.uniform(-1.3, 1.3, 3) * (1, 0, 1)
+        ubo = scene.with_camera(cam)
+        for h in (o, e):
+            h.set_scene_ubo(ubo)
+            h.translate()
+            h.update(-1, rots)
+        assert parity.compare_atlas(o.download_atlas(), e.download_atlas()) > 0.99
+    o.close()
+    e.close()
+
+
+def test_bvh8_structure(make_emu):
+    for scene in (scenes.random_soup(41, ntris=700), scenes.cornell_box(grid=(4, 2, 64), wall_res=6, box_res=2)):
+        p = make_params(4, 2, 64)
+        e = make_emu(p)
+        e.upload_scene(scene)
+        e.set_scene_ubo(scene.ubo)
+        e.build_accel()
+        info = e.bvh_info()
+        assert info.node_bytes == 80 and info.tri_bytes == 48 and info.num_triangles == scene.num_triangles
+        nodes, tris = e.download_bvh()
+        parity.validate_bvh8(nodes, tris, info.num_triangles)
+        e.close()
+
+
+def test_refit_moving_nodes(oracle, make_emu):
+    scene = scenes.sponza_like(seed=4, grid=(4, 2, 64), movers=4, curtain_res=4)
+    # shrink: keep only the movers and a few big static pieces so the CPU harness stays fast
+    keep = [0, 1, 2, 3, 4] + [m[0] for m in scene.movers]
+    vis = np.zeros(len(scene.renderables), np.uint32)
+    vis[keep] = 1
+    scene.renderables["visible"] = vis
+    p = make_params(4, 2, 64, flags=ALL)
+    o, e = oracle.Oracle(p), make_emu(p)
+    rots = parity.setup_pair(scene, (o, e), seed=6)
+    for k in range(3):
+        rend = scene.animated_renderables(0.4 * (k + 1))
+        for h in (o, e):
+            h.refit_accel(rend)
+            h.update(-1, rots)
+        nodes, tris = e.download_bvh()
+        parity.validate_bvh8(nodes, tris, e.bvh_info().num_triangles)
+        for layer in range(2):
+            parity.compare_records(o.download_ray_records(layer), e.download_ray_records(layer))
+        parity.compare_atlas(o.download_atlas(), e.download_atlas())
+    # a visibility change needs a rebuild, like the reference's per-frame TLAS build would pick up
+    rend = scene.animated_renderables(2.0)
+    rend["visible"][keep[-1]] = 0
+    with pytest.raises(Exception):
+        e.refit_accel(rend)
+    o.close()
+    e.close()
+
+
+def test_error_behaviour(make_emu):
+    p = make_params(4, 2, 64)
+    e = make_emu(p)
+    scene = scenes.quad_scene()
+    with pytest.raises(Exception):
+        e.build_accel()                                   # before upload_scene
+    e.upload_scene(scene)
+    e.set_scene_ubo(scene.ubo)
+    with pytest.raises(Exception):
+        e.trace_layer(0, np.eye(4, dtype=np.float32))     # before build_accel
+    e.build_accel()
+    with pytest.raises(Exception):
+        e.convolve_layer(1)                               # layer never traced
+    with pytest.raises(Exception):
+        e.trace_layer(5, np.eye(4, dtype=np.float32))     # layer out of range
+    bad = scenes.quad_scene()
+    bad.materials["bindless_indices"][0, 1] = 3           # textured material: outside the path's scope
+    with pytest.raises(Exception):
+        e.upload_scene(bad)
+    # DDGI off: the passes are no-ops (IrradianceProbeRayTracingPass.cpp:97-98)
+    off = scene.ubo.copy()
+    off["flags"] = 0
+    e.set_scene_ubo(off)
+    before = e.download_atlas()
+    e.update(-1, np.tile(np.eye(4, dtype=np.float32).ravel(), 2))
+    assert np.array_equal(before, e.download_atlas())
+    e.close()
+    with pytest.raises(Exception):
+        make_emu(make_params(4, 2, 48))                   # rays per probe must tile

@@ -1,0 +1,311 @@
+"""Known-answer tests that pin the oracle's transliteration of the shaders.
+
+The reference has no tests, golden vectors or CPU path for this chain ("parity unpinned"); these KATs are derived
+from the shader formulas themselves, each citing the function it pins.
+"""
+import numpy as np
+import pytest
+
+from anerend_b200 import layouts as L, make_params, scenes
+
+
+def test_fibonacci_directions(oracle):
+    # irradiance_probe_update.rgen:35-46
+    d = oracle.fibonacci_dirs(256)
+    np.testing.assert_allclose(d[0], [0.088302, 0.0, 0.996094], atol=2e-6)
+    np.testing.assert_allclose(d[1], [-0.112555, -0.103109, 0.988281], atol=2e-6)
+    np.testing.assert_allclose(d[255], [-0.071870, -0.051303, -0.996094], atol=2e-6)
+    np.testing.assert_allclose(oracle.fibonacci_dirs(64)[0], [0.176085, 0.0, 0.984375], atol=2e-6)
+    np.testing.assert_allclose(oracle.fibonacci_dirs(128)[0], [0.124756, 0.0, 0.992188], atol=2e-6)
+    for n in (64, 128, 256):
+        d = oracle.fibonacci_dirs(n).astype(np.float64)
+        np.testing.assert_allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-6)
+        np.testing.assert_allclose(d[:, 2], 1.0 - 2.0 * (np.arange(n) + 0.5) / n, atol=1e-6)   # cos(phi)
+        assert np.abs(d.mean(0)).max() < 0.02                                                   # near-uniform over the sphere
+
+
+def test_oct_decode_texel_centres_and_round_trip(oracle):
+    # octahedron_helpers.glsl:10-34, helpers.glsl:1-4
+    want = {(0, 0): (-0.162221, -0.973329, -0.162221), (3, 3): (-0.162221, 0.973329, -0.162221),
+            (4, 4): (0.162221, 0.973329, 0.162221), (7, 7): (0.162221, -0.973329, 0.162221)}
+    for (i, j), v in want.items():
+        o = [((2 * i + 1) / 16.0) * 2 - 1, ((2 * j + 1) / 16.0) * 2 - 1]
+        np.testing.assert_allclose(oracle.oct_decode(o), v, atol=2e-6)
+    for i in range(8):
+        for j in range(8):
+            o = np.array([((2 * i + 1) / 16.0) * 2 - 1, ((2 * j + 1) / 16.0) * 2 - 1], np.float32)
+            np.testing.assert_allclose(oracle.oct_encode(oracle.oct_decode(o)), o, atol=1e-6)
+    rng = np.random.RandomState(0)
+    for _ in range(200):
+        v = rng.normal(size=3)
+        v /= np.linalg.norm(v)
+        np.testing.assert_allclose(oracle.oct_decode(oracle.oct_encode(v)), v, atol=2e-6)
+
+
+def test_to_linear(oracle):
+    # bindless.glsl:240-247 and rmiss:20 with RenderOptions defaults
+    np.testing.assert_allclose(oracle.to_linear([0.2, 0.5, 0.7]), [0.033105, 0.214041, 0.447988], atol=1e-6)
+    assert np.array_equal(oracle.to_linear([1, 1, 1]), np.ones(3, np.float32))
+    lo = oracle.to_linear([0.04044, 0.0, 0.0])[0]
+    hi = oracle.to_linear([0.04045, 0.0, 0.0])[0]
+    assert lo == pytest.approx(0.04044 / 12.92, rel=1e-6)
+    assert hi == pytest.approx(((0.04045 + 0.055) / 1.055) ** 2.4, rel=1e-6)
+
+
+def test_half_conversion_matches_ieee(oracle):
+    rng = np.random.RandomState(1)
+    vals = np.concatenate([rng.uniform(-70000, 70000, 2000), rng.uniform(-1, 1, 2000) * 10.0 ** rng.uniform(-9, 0, 2000),
+                           [0.0, -0.0, 65504.0, 65519.9, 65520.0, 2.0 ** -24, 2.0 ** -25, 2.0 ** -25 * 1.0001, 1.0, 0.1]]).astype(np.float32)
+    with np.errstate(over="ignore"):
+        want = vals.astype(np.float16).view(np.uint16)
+    got = np.array([oracle.float_to_half(float(v)) for v in vals], np.uint16)
+    assert np.array_equal(got, want)
+    allh = np.arange(0, 0x7C00, 7, dtype=np.uint16)
+    back = np.array([oracle.half_to_float(int(h)) for h in allh], np.float32)
+    assert np.array_equal(back, allh.view(np.float16).astype(np.float32))
+
+
+def test_rotation_matches_glm_rotate(oracle):
+    # glm::rotate(mat4(1), radians(a), axis): column-major; axis = z -> columns (c,s,0),(-s,c,0),(0,0,1)
+    m = oracle.make_rotation(2, 30.0).reshape(4, 4)     # rows of this view are glm columns
+    c, s = np.cos(np.radians(30.0)), np.sin(np.radians(30.0))
+    np.testing.assert_allclose(m, [[c, s, 0, 0], [-s, c, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]], atol=1e-7)
+    mx = oracle.make_rotation(0, 90.0).reshape(4, 4)
+    np.testing.assert_allclose(mx, [[1, 0, 0, 0], [0, 0, 1, 0], [0, -1, 0, 0], [0, 0, 0, 1]], atol=1e-7)
+    for ax in range(3):
+        r = oracle.make_rotation(ax, 123.4).reshape(4, 4)[:3, :3].astype(np.float64)
+        np.testing.assert_allclose(r @ r.T, np.eye(3), atol=1e-6)
+
+
+def test_intersection_analytic(oracle):
+    # KAT 9: axis-aligned quad; Vulkan interval is exclusive at both ends
+    v0, v1, v2 = [0, 0, 5], [4, 0, 5], [0, 4, 5]
+    hit, t, u, v = oracle.intersect([1, 1, 0], [0, 0, 1], v0, v1, v2)
+    assert hit and t == 5.0 and u == 0.25 and v == 0.25
+    assert oracle.intersect([1, 1, 10], [0, 0, -1], v0, v1, v2)[0]                   # two-sided
+    assert not oracle.intersect([3, 3, 0], [0, 0, 1], v0, v1, v2)[0]                 # u+v > 1
+    assert not oracle.intersect([1, 1, 0], [1, 0, 0], v0, v1, v2)[0]                 # parallel: det == 0
+    assert not oracle.intersect([1, 1, 4.95], [0, 0, 1], v0, v1, v2, 0.1, 50)[0]     # t = 0.05 < tMin
+    assert not oracle.intersect([1, 1, 0], [0, 0, 1], v0, v1, v2, 0.1, 5.0)[0]       # t == tMax excluded
+    assert not oracle.intersect([1, 1, 0], [0, 0, 1], v0, v1, v2, 5.0, 50.0)[0]      # t == tMin excluded
+
+
+def _conv_setup(oracle, n_xz, n_y, n_rays, seed):
+    p = make_params(n_xz, n_y, n_rays, flags=L.FLAG_TEXEL_RECORDS)
+    o = oracle.Oracle(p)
+    sx, sy = o.ray_tile
+    rot = oracle.make_rotation(*scenes.rotation_sequence(seed, 1)[0])
+    fib = oracle.fibonacci_dirs(n_rays).astype(np.float32)
+    R = rot.reshape(4, 4)[:3, :3].T                       # math matrix from column-major storage
+    dirs = (fib @ R.T).astype(np.float32)
+    dir_img = np.zeros((sy * n_xz, sx * n_xz, 4), np.float16)
+    for ray in range(n_rays):
+        px, py = ray % sx, ray // sx
+        dir_img[py::sy, px::sx, :3] = dirs[ray]
+    dir_img[..., 3] = 1.0
+    return o, dir_img, dirs
+
+
+def test_convolution_sum_of_weights_and_uniform_radiance(oracle):
+    # KAT 3 + KAT 4: probe_conv.comp:49-87
+    for n_rays, want in ((64, 16.0184), (128, 31.9457), (256, 64.0239)):
+        p = make_params(2, 1, n_rays, flags=L.FLAG_TEXEL_RECORDS)
+        o = oracle.Oracle(p)
+        sx, sy = o.ray_tile
+        fib = oracle.fibonacci_dirs(n_rays)
+        # identity rotation, fp32 directions -> emulate by computing the expected sum directly
+        octdir = oracle.oct_decode([((2 * 3 + 1) / 16.0) * 2 - 1] * 2).astype(np.float64)
+        w = np.maximum(0.0, fib.astype(np.float64) @ octdir)
+        assert w[w > 1e-6].sum() == pytest.approx(want, abs=2e-3)
+        o.close()
+    o, dir_img, _ = _conv_setup(oracle, 4, 2, 256, seed=1)
+    L0 = np.array([0.75, 1.5, 0.25], np.float16)
+    irr = np.zeros_like(dir_img)
+    irr[..., :3] = L0
+    irr[..., 3] = 1.0
+    for layer in range(2):
+        o.set_rays(layer, irr.view(np.uint16), dir_img.view(np.uint16))
+    mask = np.broadcast_to(__import__("tests.parity", fromlist=["x"]).interior_mask(4, 2)[..., None], (80, 40, 4))
+    prev = np.zeros(3)
+    for k in range(1, 6):
+        for layer in range(2):
+            o.convolve_layer(layer)
+        rec = o.download_texel_records()
+        rgb = rec[..., :3][mask[..., :3]].reshape(-1, 3)
+        # normalised result == L exactly for uniform radiance, so rgb follows 0.04*L + 0.96*old on half-rounded olds
+        want = L0.astype(np.float64) * (1 - 0.96 ** k)
+        np.testing.assert_allclose(rgb, np.broadcast_to(want, rgb.shape), rtol=2e-3)
+        assert np.all(rgb.mean(0) > prev)
+        prev = rgb.mean(0)
+    # borders are never written: still (0,0,0,1)
+    a = o.download_atlas()
+    border = ~mask[..., 0]
+    assert np.all(a[border][:, :3] == 0) and np.all(a[border][:, 3] == 0x3C00)
+    o.close()
+
+
+def test_config1_convolution_runs_single_thread(oracle):
+    # BASELINE config 1: 8x8x8 probes x 64 rays, synthetic radiance U[0,4)^3 seed 1, one update of all layers
+    o, dir_img, dirs = _conv_setup(oracle, 8, 8, 64, seed=1)
+    o.set_threads(1)
+    rng = np.random.RandomState(1)
+    for layer in range(8):
+        irr = np.ones(dir_img.shape, np.float16)
+        irr[..., :3] = rng.uniform(0, 4, irr[..., :3].shape)
+        o.set_rays(layer, irr.view(np.uint16), dir_img.view(np.uint16))
+        o.convolve_layer(layer)
+        if layer == 0:
+            # independent numpy restatement for probe (0,0), texel (i,j): probe_conv.comp:43-87
+            irr0 = irr[:8, :8, :3].reshape(64, 3).astype(np.float64)       # ray = py*8+px
+            d16 = dir_img[:8, :8, :3].reshape(64, 3).astype(np.float64)
+            rec = o.download_texel_records()
+            for (i, j) in ((0, 0), (3, 5), (7, 7)):
+                od = oracle.oct_decode([((2 * i + 1) / 16.0) * 2 - 1, ((2 * j + 1) / 16.0) * 2 - 1]).astype(np.float64)
+                w = np.maximum(0, d16 @ od)
+                w[w <= 1e-6] = 0
+                want_rgb = (w[:, None] * irr0).sum(0) / w.sum() * 0.04
+                want_a = w.sum() * (1.0 - np.float32(0.96)) + 1.0 * np.float32(0.96)
+                np.testing.assert_allclose(rec[1 + j, 1 + i, :3], want_rgb, rtol=2e-5)
+                assert rec[1 + j, 1 + i, 3] == pytest.approx(want_a, rel=2e-5)
+    a = o.download_atlas().view(np.float16)
+    assert np.isfinite(a.astype(np.float32)).all() and a[..., :3].max() > 0
+    o.close()
+
+
+def test_empty_scene_gives_sky_everywhere(oracle):
+    # KAT 5: every ray misses -> rmiss:20 -> atlas = 0.04 * sky after one update
+    s = scenes.empty_scene(grid=(4, 2, 64))
+    p = make_params(4, 2, 64, flags=L.FLAG_RAY_RECORDS | L.FLAG_TEXEL_RECORDS)
+    o = oracle.Oracle(p)
+    o.upload_scene(s)
+    o.set_scene_ubo(s.ubo)
+    o.build_accel()
+    rots = o.rotations(scenes.rotation_sequence(5, 2))
+    o.update(-1, rots)
+    sky = oracle.to_linear([0.2, 0.5, 0.7])
+    for layer in range(2):
+        rec = o.download_ray_records(layer)
+        assert np.all(rec["prim"] == L.MISS)
+        assert np.array_equal(rec["radiance"], np.broadcast_to(sky, rec["radiance"].shape))
+    from tests.parity import interior_mask
+    tex = o.download_texel_records()[interior_mask(4, 2)]
+    skyh = sky.astype(np.float16).astype(np.float64)
+    np.testing.assert_allclose(tex[:, :3], np.broadcast_to(skyh * (1.0 - np.float32(0.96)), tex[:, :3].shape), rtol=1e-5)
+    o.close()
+
+
+def test_atlas_addressing_and_translation(oracle):
+    # KAT 7 + KAT 8: probe (x,y,z) texel (i,j) <-> pixel (10x+1+i, 10*nXZ*y+10z+1+j); translation by one probe
+    n_xz, n_y = 4, 2
+    p = make_params(n_xz, n_y, 64)
+    o = oracle.Oracle(p)
+    W, H = 10 * n_xz, 10 * n_xz * n_y
+    a = np.zeros((H, W, 4), np.uint16)
+    yy, xx = np.mgrid[0:H, 0:W]
+    a[..., 0] = xx
+    a[..., 1] = yy
+    s = scenes.empty_scene(grid=(n_xz, n_y, 64))
+    o.set_scene_ubo(s.with_camera((0.5, 1.0, 0.5)))
+    o.translate()
+    o.upload_atlas(a)
+    o.set_scene_ubo(s.with_camera((1.5, 1.0, 0.5)))          # dx = +1
+    o.translate()
+    b = o.download_atlas()
+    assert np.array_equal(b[:, :W - 10], a[:, 10:]) and np.array_equal(b[:, W - 10:], a[:, W - 10:])   # last block unchanged (Q7)
+    o.set_scene_ubo(s.with_camera((1.5, 1.0, -1.2)))         # dz = int(-1.2) - 0 = -1 (truncation toward zero, Q1)
+    o.upload_atlas(a)
+    o.translate()
+    b = o.download_atlas()
+    for layer in range(n_y):
+        y0 = layer * 10 * n_xz
+        assert np.array_equal(b[y0 + 10:y0 + 10 * n_xz], a[y0:y0 + 10 * n_xz - 10])
+        assert np.array_equal(b[y0:y0 + 10], a[y0:y0 + 10])
+    o.set_scene_ubo(s.with_camera((1.9, 1.0, -1.9)))         # same integer cell: no-op
+    o.upload_atlas(a)
+    o.translate()
+    assert np.array_equal(o.download_atlas(), a)
+    o.set_scene_ubo(s.with_camera((5.5, 1.0, -1.9)))         # |dx| = 4 still shifts by exactly one probe (Q7)
+    o.translate()
+    b = o.download_atlas()
+    assert np.array_equal(b[:, :W - 10], a[:, 10:])
+    o.close()
+
+
+def test_quad_scene_analytic_hits_and_shadow_split(oracle):
+    # KAT 9: floor quad at y=-1.5 below a probe at (px, 0, pz): straight-down ray hits at t = 1.5
+    s = scenes.quad_scene(grid=(4, 2, 64), second_quad=True)
+    p = make_params(4, 2, 64, flags=L.FLAG_RAY_RECORDS)
+    o = oracle.Oracle(p)
+    o.upload_scene(s)
+    o.set_scene_ubo(s.ubo)
+    o.build_accel()
+    rot = np.eye(4, dtype=np.float32).ravel()
+    o.trace_layer(0, rot)
+    rec = o.download_ray_records(0)
+    fib = oracle.fibonacci_dirs(64)
+    down = fib[:, 1] < -0.2
+    # with identity rotation the hit distance to the floor plane is -1.5 / d.y for rays that reach the 20 m quad
+    for probe in (0, 5, 15):
+        r = rec[probe]
+        hit_floor = (r["prim"] < 2)
+        assert hit_floor[down].mean() > 0.5
+        np.testing.assert_allclose(r["t"][hit_floor], (-1.5 / fib[hit_floor, 1]), rtol=1e-5)
+    # the second quad (y = 6, x in [-10,0]) shadows the sun (from -x,+y,-z) for part of the floor only
+    lit = rec["lit_mask"][rec["prim"] < 2] & 1
+    assert 0.05 < lit.mean() < 0.95
+    o.close()
+
+
+def test_bvh_equals_brute_force(oracle):
+    for seed in (11, 12):
+        s = scenes.random_soup(seed, ntris=1500)
+        p = make_params(3, 2, 64, flags=L.FLAG_RAY_RECORDS | L.FLAG_POINT_LIGHTS)
+        a, b = oracle.Oracle(p), oracle.Oracle(p)
+        b.set_brute_force(True)
+        for h in (a, b):
+            h.upload_scene(s)
+            h.set_scene_ubo(s.ubo)
+            h.build_accel()
+        rots = a.rotations(scenes.rotation_sequence(seed, 2))
+        for h in (a, b):
+            h.update(-1, rots)
+        for layer in range(2):
+            ra, rb = a.download_ray_records(layer), b.download_ray_records(layer)
+            assert np.array_equal(ra["prim"], rb["prim"]) and np.array_equal(ra["lit_mask"], rb["lit_mask"])
+            assert np.array_equal(ra["radiance"], rb["radiance"])
+        assert np.array_equal(a.download_atlas(), b.download_atlas())
+        a.close()
+        b.close()
+
+
+def test_white_furnace_energy(oracle):
+    # KAT 10: closed box, all probes inside, sun off, emissive-free: atlas rgb stays exactly 0
+    b = scenes.SceneBuilder("furnace", 0)
+    cube = b.add_mesh(*scenes.box(4))
+    mat = b.add_material((0.8, 0.8, 0.8))
+    b.add_renderable(scenes.translate((0.0, 3.0, 0.0)) @ scenes.scale((30.0, 30.0, 30.0)), cube, mat)
+    s = b.finish((0.0, 3.0, 0.0), (4, 2, 64))
+    s.ubo["sun_intensity"] = 0.0
+    p = make_params(4, 2, 64, flags=L.FLAG_RAY_RECORDS)
+    o = oracle.Oracle(p)
+    o.upload_scene(s)
+    o.set_scene_ubo(s.ubo)
+    o.build_accel()
+    rots = o.rotations(scenes.rotation_sequence(3, 2))
+    for _ in range(3):
+        o.update(-1, rots)
+    a = o.download_atlas().view(np.float16)
+    from tests.parity import interior_mask
+    assert np.all(a[interior_mask(4, 2)][:, :3] == 0)
+    # with emissive walls and multi-bounce the atlas grows monotonically towards E/(1-rho*c)
+    s.materials["emissive"][0] = (1.0, 1.0, 1.0, 0.5)
+    o.upload_scene(s)
+    o.build_accel()
+    o.reset()
+    prev = 0.0
+    for _ in range(4):
+        o.update(-1, rots)
+        m = o.download_atlas().view(np.float16)[interior_mask(4, 2)][:, :3].astype(np.float64).mean()
+        assert m > prev
+        prev = m
+    o.close()
