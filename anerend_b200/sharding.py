@@ -34,9 +34,12 @@ class DeviceArray:
 def all_gather_atlas(atlas, num_probes_xz, num_probes_y, rank, world, group=None):
     """In-place all-gather of the atlas slabs.  `atlas` is a torch tensor [H, W, 4] (any device); every rank
     contributes the rows of its own slab and receives all the others."""
+    import torch
     import torch.distributed as dist
     if world == 1:
         return atlas
+    full = atlas
+    atlas = atlas.view(torch.uint8)          # bit copy; uint8 is supported by both NCCL and gloo
     slabs = [slab_for_rank(num_probes_y, r, world) for r in range(world)]
     rows = [slab_rows(num_probes_xz, s) for s in slabs]
     sizes = {e - b for b, e in rows}
@@ -45,9 +48,10 @@ def all_gather_atlas(atlas, num_probes_xz, num_probes_y, rank, world, group=None
         b, e = rows[rank]
         dist.all_gather_into_tensor(atlas.view(-1), atlas[b:e].reshape(-1), group=group)
     else:
-        outs = [atlas[b:e] for b, e in rows]
-        dist.all_gather(outs, atlas[rows[rank][0]:rows[rank][1]].clone(), group=group)
-    return atlas
+        # unequal slabs (nY not divisible by R): one in-place broadcast of each rank's rows
+        for r, (b, e) in enumerate(rows):
+            dist.broadcast(atlas[b:e], src=r, group=group)
+    return full
 
 
 def merge_slabs_numpy(slab_atlases, num_probes_xz, num_probes_y):

@@ -1,0 +1,78 @@
+"""Host-side logic of the Y-slab sharding on CPU: slab arithmetic, and a world_size-2 gloo run in which
+each rank updates only its slab with the host-emu harness, all-gathers the atlas, and ends with the single-rank atlas."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from anerend_b200 import sharding
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_slab_arithmetic():
+    for ny, world in ((8, 1), (8, 2), (12, 4), (32, 8), (12, 8), (5, 2)):
+        slabs = [sharding.slab_for_rank(ny, r, world) for r in range(world)]
+        assert slabs[0][0] == 0 and slabs[-1][1] == ny
+        assert all(a[1] == b[0] for a, b in zip(slabs, slabs[1:])) and all(e > b for b, e in slabs)
+        assert max(e - b for b, e in slabs) - min(e - b for b, e in slabs) <= 1
+    assert sharding.slab_rows(24, (3, 6)) == (720, 1440)
+    with pytest.raises(ValueError):
+        sharding.slab_for_rank(4, 0, 8)
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    from anerend_b200 import layouts as L, make_params, scenes
+    from anerend_b200.capi import DdgiHandle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    emu = ctypes.CDLL(g.build_host_emu())
+    nxz, ny, nr = 4, 3, 64                       # 3 layers over 2 ranks: unequal slabs (2 + 1)
+    scene = scenes.random_soup(51, ntris=400, grid=(nxz, ny, nr))
+    slab = sharding.slab_for_rank(ny, rank, world)
+    h = DdgiHandle(emu, "anerend_emu_ddgi_", make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS, slab=slab))
+    h.upload_scene(scene)
+    h.set_scene_ubo(scene.ubo)
+    h.build_accel()
+    rots = h.rotations(scenes.rotation_sequence(9, ny))
+    for it in range(3):
+        h.update(-1, rots)
+        atlas = torch.from_numpy(h.download_atlas().view(np.int16).copy())
+        sharding.all_gather_atlas(atlas, nxz, ny, rank, world)
+        h.upload_atlas(atlas.numpy().view(np.uint16))
+    np.save(os.path.join(out_dir, f"atlas_{rank}.npy"), h.download_atlas())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_slab_update_equals_single_rank(tmp_path, make_emu):
+    import torch.multiprocessing as mp
+    from anerend_b200 import layouts as L, make_params, scenes
+    import __graft_entry__ as g
+    g.build_host_emu()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    nxz, ny, nr = 4, 3, 64
+    scene = scenes.random_soup(51, ntris=400, grid=(nxz, ny, nr))
+    h = make_emu(make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS))
+    h.upload_scene(scene)
+    h.set_scene_ubo(scene.ubo)
+    h.build_accel()
+    rots = h.rotations(scenes.rotation_sequence(9, ny))
+    for it in range(3):
+        h.update(-1, rots)
+    want = h.download_atlas()
+    a0, a1 = np.load(tmp_path / "atlas_0.npy"), np.load(tmp_path / "atlas_1.npy")
+    assert np.array_equal(a0, a1) and np.array_equal(a0, want)
+    merged = sharding.merge_slabs_numpy([a0, a1], nxz, ny)
+    assert np.array_equal(merged, want)
