@@ -8,7 +8,11 @@
 // Compiled by nvcc into libanerend_cuda_ddgi.so.  (With -DDDGI_HOST_EMU the same file builds the serial debug
 // harness under tests/host_emu/, exported as anerend_emu_ddgi_*; it is never part of the product library.)
 #include "ddgi_launch.h"
+#ifndef DDGI_HOST_EMU
+#include "ddgi_fast.cuh"
+#endif
 
+#include <algorithm>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -68,6 +72,9 @@ struct anerend_ddgi {
   std::vector<float> fib;                                  // N*3
   std::vector<uint8_t> layerTraced;
   uint2* peers[8] = {nullptr}; int numPeers = 0;
+  // wavefront (fast) path scratch: hit records, surface records, visibility masks, per-light shadow queues
+  float4* dHits = nullptr; float4* dSurf = nullptr; uint32_t* dLit = nullptr; uint32_t* dQueues = nullptr; uint32_t* dQcount = nullptr;
+  size_t fastRays = 0; uint32_t fastQueues = 0; int gridPrimary[2] = {0, 0}, gridShadow[2] = {0, 0};
 
   int currentLayer = 0;                                    // IrradianceProbeRayTracingPass::_currentLayer
   int lastProbeIdx[2] = {0, 0};                            // IrradianceProbeTranslationPass::_lastProbeIdx
@@ -255,6 +262,44 @@ void rotateDirs(anerend_ddgi* h, int layer, const float* m) {
   }
 }
 
+#ifndef DDGI_HOST_EMU
+// Wavefront path: k_trace_primary -> k_shade_prep -> k_trace_shadow -> k_shade (ddgi_fast.cuh)
+int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
+  Backend& be = h->be;
+  const uint32_t nq = 1u + ((h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) ? h->numLights : 0u);
+  const size_t slabRays = (size_t)(h->p.slab_end - h->p.slab_begin) * h->P * h->N;
+  const size_t need = n > slabRays ? n : slabRays;
+  if (h->fastRays < need || h->fastQueues < nq) {
+    BE_CHECK(h, be.sync());
+    be.free(h->dHits); be.free(h->dSurf); be.free(h->dLit); be.free(h->dQueues); be.free(h->dQcount);
+    h->dHits = nullptr; h->dSurf = nullptr; h->dLit = nullptr; h->dQueues = nullptr; h->dQcount = nullptr; h->fastRays = 0;
+    BE_CHECK(h, be.alloc(&h->dHits, need)); BE_CHECK(h, be.alloc(&h->dSurf, 3 * need)); BE_CHECK(h, be.alloc(&h->dLit, need));
+    BE_CHECK(h, be.alloc(&h->dQueues, (size_t)nq * need)); BE_CHECK(h, be.alloc(&h->dQcount, 34));
+    h->fastRays = need; h->fastQueues = nq;
+  }
+  if (h->gridPrimary[0] == 0) {
+    int dev = 0, sms = 0, nb = 0;
+    BE_CHECK(h, be.ok(cudaGetDevice(&dev))); BE_CHECK(h, be.ok(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)));
+    BE_CHECK(h, be.ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_primary<false>, 128, 0))); h->gridPrimary[0] = sms * (nb > 0 ? nb : 1);
+    BE_CHECK(h, be.ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_primary<true>, 128, 0))); h->gridPrimary[1] = sms * (nb > 0 ? nb : 1);
+    BE_CHECK(h, be.ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_shadow<false>, 128, 0))); h->gridShadow[0] = sms * (nb > 0 ? nb : 1);
+    BE_CHECK(h, be.ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_shadow<true>, 128, 0))); h->gridShadow[1] = sms * (nb > 0 ? nb : 1);
+  }
+  FastCtx f{};
+  f.t = c; f.hits = h->dHits; f.surf = h->dSurf; f.lit = h->dLit; f.queues = h->dQueues; f.qcount = h->dQcount; f.totalRays = n; f.numQueues = nq;
+  BE_CHECK(h, be.zero(h->dQcount, 34 * sizeof(uint32_t)));
+  const bool cnt = (h->p.flags & ANEREND_DDGI_FLAG_COUNTERS) != 0;
+  const uint32_t blocks = (n + 127u) / 128u;
+  if (cnt) k_trace_primary<true><<<h->gridPrimary[1], 128, 0, be.stream>>>(f); else k_trace_primary<false><<<h->gridPrimary[0], 128, 0, be.stream>>>(f);
+  k_shade_prep<<<blocks, 128, 0, be.stream>>>(f);
+  if (cnt) k_trace_shadow<true><<<h->gridShadow[1], 128, 0, be.stream>>>(f); else k_trace_shadow<false><<<h->gridShadow[0], 128, 0, be.stream>>>(f);
+  k_shade<<<blocks, 128, 0, be.stream>>>(f);
+  be.launches += 5;
+  BE_CHECK(h, be.check());
+  return 0;
+}
+#endif
+
 int traceLayers(anerend_ddgi* h, int layerBegin, int numLayers, const float* rots /* indexed from layerBegin */) {
   Backend& be = h->be;
   if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "trace before build_accel");
@@ -284,9 +329,14 @@ int traceLayers(anerend_ddgi* h, int layerBegin, int numLayers, const float* rot
   c.tmin = h->p.t_min; c.tmax = h->p.t_max; c.sunIntensity = h->ubo.sun_intensity;
   c.uboFlags = h->ubo.flags; c.flags = h->p.flags;
   const uint32_t n = (uint32_t)numLayers * (uint32_t)h->P * (uint32_t)h->N;
-  if (h->p.flags & ANEREND_DDGI_FLAG_COUNTERS) DDGI_LAUNCH(be, k_probe_trace_counted, trace_ray_body<true>, n, c, 128);
-  else DDGI_LAUNCH(be, k_probe_trace, trace_ray_body<false>, n, c, 128);
-  BE_CHECK(h, be.check());
+#ifndef DDGI_HOST_EMU
+  if (!(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS)) { int rc = traceFast(h, c, n); if (rc) return rc; } else
+#endif
+  {
+    if (h->p.flags & ANEREND_DDGI_FLAG_COUNTERS) DDGI_LAUNCH(be, k_probe_trace_counted, trace_ray_body<true>, n, c, 128);
+    else DDGI_LAUNCH(be, k_probe_trace, trace_ray_body<false>, n, c, 128);
+    BE_CHECK(h, be.check());
+  }
   for (int l = 0; l < numLayers; ++l) h->layerTraced[layerBegin + l] = 1;
   return 0;
 }
@@ -331,6 +381,7 @@ void destroyHandle(anerend_ddgi* h) {
   freeAccel(h); freeScene(h);
   be.free(h->dAtlas); be.free(h->dTemp); be.free(h->dRayIrr); be.free(h->dDirs); be.freeHostPinned(h->hDirs); be.free(h->dRayOrder);
   be.free(h->dRecords); be.free(h->dTexelRecords); be.free(h->dStats); be.free(h->dSceneBounds); be.free(h->dCounters);
+  be.free(h->dHits); be.free(h->dSurf); be.free(h->dLit); be.free(h->dQueues); be.free(h->dQcount);
   be.destroy();
   delete h;
 }
@@ -365,6 +416,22 @@ int DDGI_API(create)(const anerend_ddgi_params_t* params, anerend_ddgi_t** out) 
   h->fib.resize((size_t)h->N * 3);
   for (int i = 0; i < h->N; ++i) fibonacciDir((uint32_t)i, (uint32_t)h->N, &h->fib[3 * i]);
   h->layerTraced.assign(h->nY, 0);
+  { // ray binning: slot -> ray index, sorted by the Morton code of the octahedral mapping of the (unrotated) direction;
+    // a rotation is rigid, so 32 consecutive slots (one warp) stay a compact cone of directions
+    std::vector<std::pair<uint32_t, uint16_t>> keyed(h->N);
+    for (int i = 0; i < h->N; ++i) {
+      float x = h->fib[3 * i], y = h->fib[3 * i + 1], z = h->fib[3 * i + 2];
+      float l1 = fabsf(x) + fabsf(y) + fabsf(z); float u = x / l1, v = y / l1;
+      if (z < 0.0f) { float nu = (1.0f - fabsf(v)) * (u >= 0.0f ? 1.0f : -1.0f), nv = (1.0f - fabsf(u)) * (v >= 0.0f ? 1.0f : -1.0f); u = nu; v = nv; }
+      // hemisphere first (keeps the two z-halves apart), then 2-D Morton inside the square
+      uint32_t qu = (uint32_t)fminf(fmaxf((u * 0.5f + 0.5f) * 1024.0f, 0.0f), 1023.0f), qv = (uint32_t)fminf(fmaxf((v * 0.5f + 0.5f) * 1024.0f, 0.0f), 1023.0f);
+      uint32_t m = 0; for (int b = 0; b < 10; ++b) m |= ((qu >> b) & 1u) << (2 * b) | ((qv >> b) & 1u) << (2 * b + 1);
+      keyed[i] = std::make_pair((z < 0.0f ? (1u << 20) : 0u) | m, (uint16_t)i);
+    }
+    std::sort(keyed.begin(), keyed.end());
+    std::vector<uint16_t> order(h->N); for (int i = 0; i < h->N; ++i) order[i] = keyed[i].second;
+    if (!be.alloc(&h->dRayOrder, h->N) || !be.h2d(h->dRayOrder, order.data(), h->N * sizeof(uint16_t)) || !be.sync()) { destroyHandle(h); return ANEREND_DDGI_E_CUDA; }
+  }
   if (clearAtlas(h) || !be.sync()) { destroyHandle(h); return ANEREND_DDGI_E_CUDA; }
   *out = h;
   return 0;

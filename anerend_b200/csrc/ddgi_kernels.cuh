@@ -233,12 +233,12 @@ HD void encode_node(uint4* out, V3 nlo, V3 nhi, const V3* clo, const V3* chi, co
     if (!meta[s]) continue;
     uint32_t sh = 8u * (uint32_t)(s & 3); int w = s >> 2;
     m[w] |= (uint32_t)meta[s] << sh;
-    uint32_t lx = (uint32_t)clampf(floorf((clo[s].x - nlo.x) * ix), 0.0f, 255.0f);
-    uint32_t ly = (uint32_t)clampf(floorf((clo[s].y - nlo.y) * iy), 0.0f, 255.0f);
-    uint32_t lz = (uint32_t)clampf(floorf((clo[s].z - nlo.z) * iz), 0.0f, 255.0f);
-    uint32_t hx = (uint32_t)clampf(ceilf((chi[s].x - nlo.x) * ix), 0.0f, 255.0f);
-    uint32_t hy = (uint32_t)clampf(ceilf((chi[s].y - nlo.y) * iy), 0.0f, 255.0f);
-    uint32_t hz = (uint32_t)clampf(ceilf((chi[s].z - nlo.z) * iz), 0.0f, 255.0f);
+    uint32_t lx = (uint32_t)clampf(floorf((clo[s].x - nlo.x) * ix - 0.02f), 0.0f, 255.0f);   // 0.02 grid steps of slack:
+    uint32_t ly = (uint32_t)clampf(floorf((clo[s].y - nlo.y) * iy - 0.02f), 0.0f, 255.0f);   // the PRMT-based decode of the
+    uint32_t lz = (uint32_t)clampf(floorf((clo[s].z - nlo.z) * iz - 0.02f), 0.0f, 255.0f);   // fast kernels is exact to ~1/512 step
+    uint32_t hx = (uint32_t)clampf(ceilf((chi[s].x - nlo.x) * ix + 0.02f), 0.0f, 255.0f);
+    uint32_t hy = (uint32_t)clampf(ceilf((chi[s].y - nlo.y) * iy + 0.02f), 0.0f, 255.0f);
+    uint32_t hz = (uint32_t)clampf(ceilf((chi[s].z - nlo.z) * iz + 0.02f), 0.0f, 255.0f);
     q[0 + w] |= lx << sh; q[2 + w] |= ly << sh; q[4 + w] |= lz << sh;
     q[6 + w] |= hx << sh; q[8 + w] |= hy << sh; q[10 + w] |= hz << sh;
   }

@@ -43,5 +43,6 @@ FLAG_POINT_LIGHTS = 1 << 0
 FLAG_RAY_RECORDS = 1 << 1
 FLAG_TEXEL_RECORDS = 1 << 2
 FLAG_COUNTERS = 1 << 3
+FLAG_SIMPLE_KERNELS = 1 << 4
 
 MISS = 0xFFFFFFFF

@@ -39,6 +39,7 @@ extern "C" {
 #define ANEREND_DDGI_FLAG_RAY_RECORDS   (1u << 1) /* keep a 32-byte fp32 debug record per ray (parity tests)                       */
 #define ANEREND_DDGI_FLAG_TEXEL_RECORDS (1u << 2) /* keep the fp32 pre-quantisation value of every convolved texel (parity tests)  */
 #define ANEREND_DDGI_FLAG_COUNTERS      (1u << 3) /* count BVH nodes visited / triangles tested (roofline bytes); slower kernels    */
+#define ANEREND_DDGI_FLAG_SIMPLE_KERNELS (1u << 4) /* one-thread-per-ray reference kernel instead of the wavefront kernels (debug)    */
 
 /*
  * Parameters that are compile-time constants in the reference

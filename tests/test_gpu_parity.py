@@ -32,10 +32,13 @@ def _check_update(o, g, ny, mismatch_frac=0.0):
     return total_mism
 
 
+@pytest.mark.parametrize("kernels", ["wavefront", "simple"])
 @pytest.mark.parametrize("name", sorted(SCENES))
-def test_full_update_matches_oracle(name, oracle, make_gpu):
+def test_full_update_matches_oracle(name, kernels, oracle, make_gpu):
+    """Both kernel families — the production wavefront kernels (csrc/ddgi_fast.cuh) and the one-thread-per-ray reference
+    kernel (FLAG_SIMPLE_KERNELS) — against the oracle."""
     scene, (nxz, ny, nr) = SCENES[name]()
-    p = make_params(nxz, ny, nr, flags=ALL)
+    p = make_params(nxz, ny, nr, flags=ALL | (L.FLAG_SIMPLE_KERNELS if kernels == "simple" else 0))
     o, g = oracle.Oracle(p), make_gpu(p)
     rots = parity.setup_pair(scene, (o, g), seed=3)
     assert o.bvh_info().num_triangles == g.bvh_info().num_triangles == scene.num_triangles
