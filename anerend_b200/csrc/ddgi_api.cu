@@ -74,6 +74,7 @@ struct anerend_ddgi {
   uint2* peers[8] = {nullptr}; int numPeers = 0;
   // wavefront (fast) path scratch: hit records, surface records, visibility masks, per-light shadow queues
   float4* dHits = nullptr; float4* dSurf = nullptr; uint32_t* dLit = nullptr; uint32_t* dQueues = nullptr; uint32_t* dQcount = nullptr;
+  uint32_t* dHitq = nullptr; float4* dShadeTris = nullptr; float* dConvW = nullptr;
   size_t fastRays = 0; uint32_t fastQueues = 0; int gridPrimary[2] = {0, 0}, gridShadow[2] = {0, 0};
 
   int currentLayer = 0;                                    // IrradianceProbeRayTracingPass::_currentLayer
@@ -141,6 +142,7 @@ BuildCtx buildCtx(anerend_ddgi* h) {
   c.wtri = h->dWtri; c.triLo = h->dTriLo; c.triHi = h->dTriHi; c.sceneBounds = h->dSceneBounds;
   c.nodes = h->dNodes; c.bvhTris = h->dBvhTris; c.nodeParent = h->dNodeParent; c.nodeLo = h->dNodeLo; c.nodeHi = h->dNodeHi;
   c.nodePending = h->dNodePending; c.visit = h->dVisit; c.counters = h->dCounters;
+  c.shadeTris = nullptr;
   return c;
 }
 
@@ -148,6 +150,7 @@ void freeAccel(anerend_ddgi* h) {
   Backend& be = h->be;
   be.free(h->dInstances); be.free(h->dXforms); be.free(h->dTriInstance); be.free(h->dWtri); be.free(h->dTriLo); be.free(h->dTriHi);
   be.free(h->dNodes); be.free(h->dBvhTris); be.free(h->dNodeParent); be.free(h->dNodeLo); be.free(h->dNodeHi); be.free(h->dNodePending); be.free(h->dVisit);
+  be.free(h->dShadeTris); h->dShadeTris = nullptr;
   h->dInstances = nullptr; h->dXforms = nullptr; h->dTriInstance = nullptr; h->dWtri = nullptr; h->dTriLo = nullptr; h->dTriHi = nullptr;
   h->dNodes = nullptr; h->dBvhTris = nullptr; h->dNodeParent = nullptr; h->dNodeLo = nullptr; h->dNodeHi = nullptr; h->dNodePending = nullptr; h->dVisit = nullptr;
   h->haveAccel = false; h->numTris = 0; h->numNodes = 0;
@@ -185,6 +188,7 @@ int buildAccel(anerend_ddgi* h) {
   BE_CHECK(h, be.alloc(&h->dNodes, 5 * (size_t)nodeCap)); BE_CHECK(h, be.alloc(&h->dBvhTris, 3 * (size_t)n));
   BE_CHECK(h, be.alloc(&h->dNodeParent, nodeCap)); BE_CHECK(h, be.alloc(&h->dNodeLo, nodeCap)); BE_CHECK(h, be.alloc(&h->dNodeHi, nodeCap));
   BE_CHECK(h, be.alloc(&h->dNodePending, nodeCap)); BE_CHECK(h, be.alloc(&h->dVisit, (size_t)n + 1));
+  BE_CHECK(h, be.alloc(&h->dShadeTris, 5 * (size_t)n));
   // build-only scratch
   uint32_t *keys = nullptr, *ids = nullptr, *skeys = nullptr, *sids = nullptr, *left = nullptr, *right = nullptr, *parent = nullptr, *rf = nullptr, *rl = nullptr;
   float4 *blo = nullptr, *bhi = nullptr; CItem *qa = nullptr, *qb = nullptr;
@@ -197,7 +201,7 @@ int buildAccel(anerend_ddgi* h) {
   BE_CHECK(h, be.h2d(h->dSceneBounds, initBounds, sizeof(initBounds)));
   BuildCtx c = buildCtx(h);
   c.mortonKeys = keys; c.triIds = ids; c.sortedKeys = skeys; c.sortedIds = sids; c.left = left; c.right = right; c.parent = parent;
-  c.rangeFirst = rf; c.rangeLast = rl; c.blo = blo; c.bhi = bhi;
+  c.rangeFirst = rf; c.rangeLast = rl; c.blo = blo; c.bhi = bhi; c.shadeTris = h->dShadeTris;
   be.mark(4);
   DDGI_LAUNCH(be, k_inst_xform, inst_xform_body, ni, c, 128);
   DDGI_LAUNCH(be, k_flatten_scene, flatten_tri_body, n, c, 256);
@@ -271,10 +275,10 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   const size_t need = n > slabRays ? n : slabRays;
   if (h->fastRays < need || h->fastQueues < nq) {
     BE_CHECK(h, be.sync());
-    be.free(h->dHits); be.free(h->dSurf); be.free(h->dLit); be.free(h->dQueues); be.free(h->dQcount);
-    h->dHits = nullptr; h->dSurf = nullptr; h->dLit = nullptr; h->dQueues = nullptr; h->dQcount = nullptr; h->fastRays = 0;
+    be.free(h->dHits); be.free(h->dSurf); be.free(h->dLit); be.free(h->dQueues); be.free(h->dQcount); be.free(h->dHitq);
+    h->dHits = nullptr; h->dSurf = nullptr; h->dLit = nullptr; h->dQueues = nullptr; h->dQcount = nullptr; h->dHitq = nullptr; h->fastRays = 0;
     BE_CHECK(h, be.alloc(&h->dHits, need)); BE_CHECK(h, be.alloc(&h->dSurf, 3 * need)); BE_CHECK(h, be.alloc(&h->dLit, need));
-    BE_CHECK(h, be.alloc(&h->dQueues, (size_t)nq * need)); BE_CHECK(h, be.alloc(&h->dQcount, 34));
+    BE_CHECK(h, be.alloc(&h->dQueues, (size_t)nq * need)); BE_CHECK(h, be.alloc(&h->dQcount, FAST_QC_SIZE)); BE_CHECK(h, be.alloc(&h->dHitq, need));
     h->fastRays = need; h->fastQueues = nq;
   }
   if (h->gridPrimary[0] == 0) {
@@ -286,14 +290,15 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
     BE_CHECK(h, be.ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_shadow<true>, 128, 0))); h->gridShadow[1] = sms * (nb > 0 ? nb : 1);
   }
   FastCtx f{};
-  f.t = c; f.hits = h->dHits; f.surf = h->dSurf; f.lit = h->dLit; f.queues = h->dQueues; f.qcount = h->dQcount; f.totalRays = n; f.numQueues = nq;
-  BE_CHECK(h, be.zero(h->dQcount, 34 * sizeof(uint32_t)));
+  f.t = c; f.shadeTris = h->dShadeTris; f.hits = h->dHits; f.surf = h->dSurf; f.lit = h->dLit; f.queues = h->dQueues; f.hitq = h->dHitq;
+  f.qcount = h->dQcount; f.totalRays = n; f.numQueues = nq;
+  BE_CHECK(h, be.zero(h->dQcount, FAST_QC_SIZE * sizeof(uint32_t)));
   const bool cnt = (h->p.flags & ANEREND_DDGI_FLAG_COUNTERS) != 0;
   const uint32_t blocks = (n + 127u) / 128u;
   if (cnt) k_trace_primary<true><<<h->gridPrimary[1], 128, 0, be.stream>>>(f); else k_trace_primary<false><<<h->gridPrimary[0], 128, 0, be.stream>>>(f);
   k_shade_prep<<<blocks, 128, 0, be.stream>>>(f);
   if (cnt) k_trace_shadow<true><<<h->gridShadow[1], 128, 0, be.stream>>>(f); else k_trace_shadow<false><<<h->gridShadow[0], 128, 0, be.stream>>>(f);
-  k_shade<<<blocks, 128, 0, be.stream>>>(f);
+  BE_CHECK(h, be.ok((h->p.flags & ANEREND_DDGI_FLAG_FAST_MATH) ? launch_shade_fast(f, be.stream) : launch_shade_exact(f, be.stream)));
   be.launches += 5;
   BE_CHECK(h, be.check());
   return 0;
@@ -350,6 +355,13 @@ int convolveLayers(anerend_ddgi* h, int layerBegin, int numLayers) {
   c.numPeers = h->numPeers;
   c.nXZ = h->nXZ; c.nY = h->nY; c.N = h->N; c.Sx = h->Sx; c.Sy = h->Sy; c.W = h->W; c.H = h->H; c.layerBegin = layerBegin; c.numLayers = numLayers;
   c.hysteresis = h->p.hysteresis;
+#ifndef DDGI_HOST_EMU
+  if (!(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS)) {
+    ConvFastCtx f{}; f.c = c; f.weights = h->dConvW;
+    BE_CHECK(h, be.ok((h->p.flags & ANEREND_DDGI_FLAG_FAST_MATH) ? launch_convolve_fast(f, be.stream) : launch_convolve_exact(f, be.stream)));
+    be.launches += 2;
+  } else
+#endif
   DDGI_LAUNCH(be, k_probe_convolve, conv_texel_body, (uint32_t)numLayers * (uint32_t)h->P * 64u, c, 128);
   BE_CHECK(h, be.check());
   return 0;
@@ -381,7 +393,7 @@ void destroyHandle(anerend_ddgi* h) {
   freeAccel(h); freeScene(h);
   be.free(h->dAtlas); be.free(h->dTemp); be.free(h->dRayIrr); be.free(h->dDirs); be.freeHostPinned(h->hDirs); be.free(h->dRayOrder);
   be.free(h->dRecords); be.free(h->dTexelRecords); be.free(h->dStats); be.free(h->dSceneBounds); be.free(h->dCounters);
-  be.free(h->dHits); be.free(h->dSurf); be.free(h->dLit); be.free(h->dQueues); be.free(h->dQcount);
+  be.free(h->dHits); be.free(h->dSurf); be.free(h->dLit); be.free(h->dQueues); be.free(h->dQcount); be.free(h->dHitq); be.free(h->dConvW);
   be.destroy();
   delete h;
 }
@@ -408,7 +420,8 @@ int DDGI_API(create)(const anerend_ddgi_params_t* params, anerend_ddgi_t** out) 
   const size_t texels = (size_t)h->W * h->H, rays = (size_t)h->nY * h->P * h->N;
   bool ok = be.alloc(&h->dAtlas, texels) && be.alloc(&h->dTemp, texels) && be.alloc(&h->dRayIrr, rays) &&
             be.alloc(&h->dDirs, (size_t)h->nY * h->N) && be.allocHostPinned(&h->hDirs, (size_t)h->nY * h->N) &&
-            be.alloc(&h->dSceneBounds, 6) && be.alloc(&h->dCounters, 4) && be.alloc(&h->dStats, 8);
+            be.alloc(&h->dSceneBounds, 6) && be.alloc(&h->dCounters, 4) && be.alloc(&h->dStats, 8) &&
+            be.alloc(&h->dConvW, (size_t)h->nY * h->N * 64);
   if (ok && (q.flags & ANEREND_DDGI_FLAG_RAY_RECORDS)) ok = be.alloc(&h->dRecords, rays);
   if (ok && (q.flags & ANEREND_DDGI_FLAG_TEXEL_RECORDS)) ok = be.alloc(&h->dTexelRecords, texels);
   if (ok) ok = be.zero(h->dStats, 8 * sizeof(unsigned long long)) && be.zero(h->dRayIrr, rays * sizeof(uint2));

@@ -14,19 +14,9 @@
 #ifndef __CUDACC__
 #error "ddgi_fast.cuh is CUDA-only"
 #endif
-#include "ddgi_kernels.cuh"
+#include "ddgi_wavefront.h"
 
 namespace ddgi {
-
-struct FastCtx {
-  TraceCtx t;
-  float4* hits;            // [rays] t,u,v,prim   (launch order: idx = (layerLocal*P + probe)*N + slot)
-  float4* surf;            // [rays][3] pos.xyz,n.x | n.yz,albedo.xy | albedo.z,material,-,-
-  uint32_t* lit;           // [rays] visibility bits written by k_trace_shadow
-  uint32_t* queues;        // [numQueues][rays] ray indices needing a shadow ray towards light q (0 = sun)
-  uint32_t* qcount;        // [numQueues] entries, [32] primary fetch cursor, [33] shadow fetch cursor
-  uint32_t totalRays, numQueues;
-};
 
 #define FAST_FETCH_THRESHOLD 22     // refill the warp when fewer lanes than this still have a ray
 
@@ -143,7 +133,7 @@ __global__ void __launch_bounds__(128) k_trace_primary(const FastCtx c) {
     const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
     if (idle && !exhausted) {
       uint32_t base = 0;
-      if (lane == (uint32_t)(__ffs((int)idle) - 1)) base = atomicAdd(&c.qcount[32], (uint32_t)__popc(idle));
+      if (lane == (uint32_t)(__ffs((int)idle) - 1)) base = atomicAdd(&c.qcount[FAST_QC_PRIMARY], (uint32_t)__popc(idle));
       base = __shfl_sync(0xFFFFFFFFu, base, __ffs((int)idle) - 1);
       if (base + (uint32_t)__popc(idle) >= c.totalRays) exhausted = true;
       if (!active) {
@@ -208,30 +198,35 @@ __global__ void __launch_bounds__(128) k_shade_prep(const FastCtx c) {
     const uint32_t hp = __float_as_uint(h.w);
     if (hp != DDGI_MISS) {
       isHit = true;
-      const uint32_t ii = t.triInstance[hp];
-      const DInstance in = t.instances[ii];
+      // rchit:27-38 through the per-triangle record (five independent 16-byte loads instead of the index/vertex gather)
+      const float4* st = c.shadeTris + 5 * (size_t)hp;
+      const float4 s0 = __ldg(st), s1 = __ldg(st + 1), s2 = __ldg(st + 2), s3 = __ldg(st + 3), s4 = __ldg(st + 4);
+      const uint32_t ii = __float_as_uint(s4.z), material = __float_as_uint(s4.w);
       const InstXform& xf = t.xforms[ii];
-      const uint32_t prim = hp - in.firstTri;                                                       // gl_PrimitiveID
-      const anerend_vertex_t* v0 = &t.vertices[in.vertexOffset + t.indices[in.indexOffset + 3 * prim + 0]];
-      const anerend_vertex_t* v1 = &t.vertices[in.vertexOffset + t.indices[in.indexOffset + 3 * prim + 1]];
-      const anerend_vertex_t* v2 = &t.vertices[in.vertexOffset + t.indices[in.indexOffset + 3 * prim + 2]];
       const float b0 = 1.0f - h.y - h.z, b1 = h.y, b2 = h.z;
-      pos = mk3(v0->pos[0], v0->pos[1], v0->pos[2]) * b0 + mk3(v1->pos[0], v1->pos[1], v1->pos[2]) * b1 + mk3(v2->pos[0], v2->pos[1], v2->pos[2]) * b2;
+      pos = mk3(s0.x, s0.y, s0.z) * b0 + mk3(s0.w, s1.x, s1.y) * b1 + mk3(s1.z, s1.w, s2.x) * b2;
       pos = xform_point(xf.o2w, pos);
-      normal = normalize3(mk3(v0->normal[0], v0->normal[1], v0->normal[2]) * b0 + mk3(v1->normal[0], v1->normal[1], v1->normal[2]) * b1 +
-                          mk3(v2->normal[0], v2->normal[1], v2->normal[2]) * b2);
+      normal = normalize3(mk3(s2.y, s2.z, s2.w) * b0 + mk3(s3.x, s3.y, s3.z) * b1 + mk3(s3.w, s4.x, s4.y) * b2);
       normal = normalize3(mk3(normal.x * xf.w2o[0] + normal.y * xf.w2o[1] + normal.z * xf.w2o[2],
                               normal.x * xf.w2o[3] + normal.y * xf.w2o[4] + normal.z * xf.w2o[5],
                               normal.x * xf.w2o[6] + normal.y * xf.w2o[7] + normal.z * xf.w2o[8]));
-      V3 color = mk3(v0->color[0], v0->color[1], v0->color[2]) * b0 + mk3(v1->color[0], v1->color[1], v1->color[2]) * b1 +
-                 mk3(v2->color[0], v2->color[1], v2->color[2]) * b2;
-      const anerend_material_info_t* m = &t.materials[in.material];
+      const anerend_material_info_t* m = &t.materials[material];
       V3 albedo;
       if (m->base_col_fac[0] + m->base_col_fac[1] + m->base_col_fac[2] > 0.1f) albedo = mk3(m->base_col_fac[0], m->base_col_fac[1], m->base_col_fac[2]);
-      else albedo = mk3(to_linear1(color.x), to_linear1(color.y), to_linear1(color.z));            // rchit:75; unused when the factor wins
+      else {
+        // vertex colour decides (rchit:71,75; bindless.glsl:187-194): rare, so the colours stay in the vertex buffer
+        const DInstance in = t.instances[ii];
+        const uint32_t prim = hp - in.firstTri;                                                     // gl_PrimitiveID
+        const anerend_vertex_t* v0 = &t.vertices[in.vertexOffset + t.indices[in.indexOffset + 3 * prim + 0]];
+        const anerend_vertex_t* v1 = &t.vertices[in.vertexOffset + t.indices[in.indexOffset + 3 * prim + 1]];
+        const anerend_vertex_t* v2 = &t.vertices[in.vertexOffset + t.indices[in.indexOffset + 3 * prim + 2]];
+        const V3 color = mk3(v0->color[0], v0->color[1], v0->color[2]) * b0 + mk3(v1->color[0], v1->color[1], v1->color[2]) * b1 +
+                         mk3(v2->color[0], v2->color[1], v2->color[2]) * b2;
+        albedo = mk3(to_linear1(color.x), to_linear1(color.y), to_linear1(color.z));
+      }
       c.surf[3 * (size_t)idx + 0] = make_float4(pos.x, pos.y, pos.z, normal.x);
       c.surf[3 * (size_t)idx + 1] = make_float4(normal.y, normal.z, albedo.x, albedo.y);
-      c.surf[3 * (size_t)idx + 2] = make_float4(albedo.z, __uint_as_float(in.material), 0.0f, 0.0f);
+      c.surf[3 * (size_t)idx + 2] = make_float4(albedo.z, __uint_as_float(material), 0.0f, 0.0f);
       c.lit[idx] = 0u;
     } else {
       // rmiss:20 + rgen:109
@@ -242,6 +237,16 @@ __global__ void __launch_bounds__(128) k_shade_prep(const FastCtx c) {
       t.rayIrr[o] = make_uint2((uint32_t)f2h(t.sky.x) | ((uint32_t)f2h(t.sky.y) << 16), (uint32_t)f2h(t.sky.z) | (0x3C00u << 16));
       if (t.records) { anerend_ddgi_ray_record_t rr; rr.prim = DDGI_MISS; rr.t = 0.0f; rr.u = 0.0f; rr.v = 0.0f;
                        rr.radiance[0] = t.sky.x; rr.radiance[1] = t.sky.y; rr.radiance[2] = t.sky.z; rr.lit_mask = 0u; t.records[o] = rr; }
+    }
+  }
+  { // compacted list of the rays that hit: k_shade runs over it with full warps
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, isHit);
+    if (m) {
+      const int leader = __ffs((int)m) - 1;
+      uint32_t base = 0;
+      if ((int)lane == leader) base = atomicAdd(&c.qcount[FAST_QC_HITS], (uint32_t)__popc(m));
+      base = __shfl_sync(0xFFFFFFFFu, base, leader);
+      if (isHit) c.hitq[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = idx;
     }
   }
   // sun shadow ray for every hit (rchit:45-66); point-light rays (extension E1) only where the light can contribute
@@ -282,7 +287,7 @@ __global__ void __launch_bounds__(128) k_trace_shadow(const FastCtx c) {
     const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
     if (idle && !exhausted) {
       uint32_t base = 0;
-      if (lane == (uint32_t)(__ffs((int)idle) - 1)) base = atomicAdd(&c.qcount[33], (uint32_t)__popc(idle));
+      if (lane == (uint32_t)(__ffs((int)idle) - 1)) base = atomicAdd(&c.qcount[FAST_QC_SHADOW], (uint32_t)__popc(idle));
       base = __shfl_sync(0xFFFFFFFFu, base, __ffs((int)idle) - 1);
       if (base + (uint32_t)__popc(idle) >= total) exhausted = true;
       if (!active) {
@@ -319,53 +324,6 @@ __global__ void __launch_bounds__(128) k_trace_shadow(const FastCtx c) {
   if (CNT && t.stats) {
     for (int o = 16; o; o >>= 1) { cn += __shfl_xor_sync(0xFFFFFFFFu, cn, o); ct += __shfl_xor_sync(0xFFFFFFFFu, ct, o); nRays += __shfl_xor_sync(0xFFFFFFFFu, nRays, o); }
     if (lane == 0) { atomicAdd(&t.stats[2], (unsigned long long)nRays); atomicAdd(&t.stats[5], (unsigned long long)cn); atomicAdd(&t.stats[6], (unsigned long long)ct); }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// k_shade: rchit:83-109 for every hit ray, then the RGBA16F store of rgen:109
-// ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_shade(const FastCtx c) {
-  const TraceCtx& t = c.t;
-  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= c.totalRays) return;
-  const float4 h = c.hits[idx];
-  const uint32_t hp = __float_as_uint(h.w);
-  if (hp == DDGI_MISS) return;                       // k_shade_prep already stored the sky radiance
-  const int P = t.nXZ * t.nXZ;
-  const uint32_t slot = idx % (uint32_t)t.N, probeLin = idx / (uint32_t)t.N;
-  const int layerLocal = (int)(probeLin / (uint32_t)P), probe = (int)(probeLin % (uint32_t)P), layer = t.layerBegin + layerLocal;
-  const uint32_t ray = t.rayOrder ? (uint32_t)t.rayOrder[slot] : slot;
-  const V3 origin = mk3((float)(probe % t.nXZ), (float)layer, (float)(probe / t.nXZ)) * t.step + t.camOff;
-  const float4 s0 = c.surf[3 * (size_t)idx], s1 = c.surf[3 * (size_t)idx + 1], s2 = c.surf[3 * (size_t)idx + 2];
-  const V3 pos = mk3(s0.x, s0.y, s0.z), normal = mk3(s0.w, s1.x, s1.y), albedo = mk3(s1.z, s1.w, s2.x);
-  const anerend_material_info_t* m = &t.materials[__float_as_uint(s2.y)];
-  const float metallic = m->met_rough[0], roughness = m->met_rough[1];
-  const V3 emissive = mk3(m->emissive[0], m->emissive[1], m->emissive[2]) * m->emissive[3];
-  const uint32_t lit = c.lit[idx];
-  V3 irradiance = mk3(0.0f);
-  if (lit & 1u) irradiance = calc_light(normal, albedo, metallic, roughness, pos, origin, normalize3(-t.lightDir), t.sunIntensity * mk3(1.0f) * 1.0f);
-  if (t.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) {
-    for (uint32_t li = 0; li < t.numLights; ++li) {
-      if (!(lit & (1u << (1u + li)))) continue;
-      const anerend_light_t* lt = &t.lights[li];
-      const V3 lp = mk3(lt->world_pos[0], lt->world_pos[1], lt->world_pos[2]);
-      const V3 dv = lp - pos; const float dist = sqrtf(dot3(dv, dv)), range = lt->world_pos[3];
-      const V3 L = normalize3(lp - pos);
-      const float dd = fminf(dist, range);
-      const float att = (1.0f - dd / range) * (1.0f - dd / range) * 1.0f;
-      irradiance = irradiance + calc_light(normal, albedo, metallic, roughness, pos, origin, L, mk3(lt->color[0], lt->color[1], lt->color[2]) * att);
-    }
-  }
-  if ((t.uboFlags & ANEREND_UBO_DDGI_MULTI_FLAG) == ANEREND_UBO_DDGI_MULTI_FLAG)
-    irradiance = irradiance + calc_indirect(t, normal, albedo, metallic, roughness, pos, origin);
-  const V3 rad = irradiance + emissive;
-  const size_t o = ((size_t)layer * P + probe) * t.N + ray;
-  t.rayIrr[o] = make_uint2((uint32_t)f2h(rad.x) | ((uint32_t)f2h(rad.y) << 16), (uint32_t)f2h(rad.z) | (0x3C00u << 16));
-  if (t.records) {
-    anerend_ddgi_ray_record_t rr;
-    rr.prim = hp; rr.t = h.x; rr.u = h.y; rr.v = h.z; rr.radiance[0] = rad.x; rr.radiance[1] = rad.y; rr.radiance[2] = rad.z; rr.lit_mask = lit;
-    t.records[o] = rr;
   }
 }
 

@@ -27,6 +27,9 @@ HD V3 operator/(V3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
 HD V3 operator-(V3 a) { return mk3(-a.x, -a.y, -a.z); }
 HD float dot3(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 HD V3 normalize3(V3 v) { float inv = 1.0f / sqrtf(dot3(v, v)); return v * inv; }
+// exact variants (see platform.h xmul..): same values as dot3/normalize3 under --fmad=false, immune to fast-math flags
+HD float dot3x(V3 a, V3 b) { return xadd(xadd(xmul(a.x, b.x), xmul(a.y, b.y)), xmul(a.z, b.z)); }
+HD V3 normalize3x(V3 v) { float inv = xdiv(1.0f, xsqrt(dot3x(v, v))); return mk3(xmul(v.x, inv), xmul(v.y, inv), xmul(v.z, inv)); }
 HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 HD V3 clamp3(V3 v, float lo, float hi) { return mk3(clampf(v.x, lo, hi), clampf(v.y, lo, hi), clampf(v.z, lo, hi)); }
 HD V3 min3(V3 a, V3 b) { return mk3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
@@ -66,6 +69,7 @@ struct BuildCtx {
   uint4* nodes; float4* bvhTris; uint32_t* nodeParent; float4* nodeLo; float4* nodeHi; uint32_t* nodePending;
   uint32_t* counters;         // [0] BVH8 nodes allocated, [1] triangle slots allocated, [2] next queue length
   const CItem* qin; CItem* qout;
+  float4* shadeTris;          // [numTris][5] object-space shading record (ddgi_wavefront.h ShadeTri) or null
 };
 
 // ----------------------------------------------------------------------------------------------------
@@ -106,10 +110,19 @@ HD void flatten_tri_body(uint32_t t, const BuildCtx& c) {
   const float* o2w = c.xforms[ii].o2w;
   uint32_t prim = t - in.firstTri;
   V3 w[3];
+  float sr[18];
   for (int k = 0; k < 3; ++k) {
     uint32_t vi = in.vertexOffset + c.indices[in.indexOffset + 3 * prim + k];
-    const float* p = c.vertices[vi].pos;
+    const float* p = c.vertices[vi].pos; const float* nn = c.vertices[vi].normal;
     w[k] = xform_point(o2w, mk3(p[0], p[1], p[2]));
+    sr[3 * k] = p[0]; sr[3 * k + 1] = p[1]; sr[3 * k + 2] = p[2];
+    sr[9 + 3 * k] = nn[0]; sr[9 + 3 * k + 1] = nn[1]; sr[9 + 3 * k + 2] = nn[2];
+  }
+  if (c.shadeTris) {     // rchit:27-38 inputs, gathered once per build instead of once per hit
+    float4* o = c.shadeTris + 5 * (size_t)t;
+    o[0] = make_float4(sr[0], sr[1], sr[2], sr[3]); o[1] = make_float4(sr[4], sr[5], sr[6], sr[7]);
+    o[2] = make_float4(sr[8], sr[9], sr[10], sr[11]); o[3] = make_float4(sr[12], sr[13], sr[14], sr[15]);
+    o[4] = make_float4(sr[16], sr[17], u2f(ii), u2f(in.material));
   }
   V3 e1 = w[1] - w[0], e2 = w[2] - w[0];
   c.wtri[3 * (size_t)t + 0] = make_float4(w[0].x, w[0].y, w[0].z, e1.x);
@@ -498,10 +511,10 @@ struct TraceCtx {
 HD float sign_not_zero(float k) { return (k >= 0.0f) ? 1.0f : -1.0f; }            // octahedron_helpers.glsl:1-3
 HD void oct_encode(V3 v, float& ox, float& oy) {                                    // octahedron_helpers.glsl:10-20
   V3 t = v; v.y = t.z; v.z = t.y;
-  float l1 = fabsf(v.x) + fabsf(v.y) + fabsf(v.z);
-  float inv = 1.0f / l1;
-  float rx = v.x * inv, ry = v.y * inv;
-  if (v.z < 0.0f) { float nx = (1.0f - fabsf(ry)) * sign_not_zero(rx), ny = (1.0f - fabsf(rx)) * sign_not_zero(ry); rx = nx; ry = ny; }
+  float l1 = xadd(xadd(fabsf(v.x), fabsf(v.y)), fabsf(v.z));
+  float inv = xdiv(1.0f, l1);
+  float rx = xmul(v.x, inv), ry = xmul(v.y, inv);
+  if (v.z < 0.0f) { float nx = xmul(xsub(1.0f, fabsf(ry)), sign_not_zero(rx)), ny = xmul(xsub(1.0f, fabsf(rx)), sign_not_zero(ry)); rx = nx; ry = ny; }
   ox = rx; oy = ry;
 }
 HD V3 oct_decode(float ox, float oy) {                                              // octahedron_helpers.glsl:25-34
@@ -517,12 +530,13 @@ HD float to_linear1(float c) {                                                  
 
 // pbr_light.glsl:10-43
 HD float distribution_ggx(V3 N, V3 Hh, float roughness) {
-  float a = roughness * roughness, a2 = a * a;
-  float NdotH = fmaxf(dot3(N, Hh), 0.0f), NdotH2 = NdotH * NdotH;
-  float num = a2 + 0.001f;
-  float denom = (NdotH2 * (a2 - 1.0f) + 1.0f);
-  denom = DDGI_PI * denom * denom;
-  return num / denom;
+  // denom cancels to ~a2 when N.H -> 1 (a2 = 0.0016 at roughness 0.2): kept in the oracle's exact sequence
+  float a = xmul(roughness, roughness), a2 = xmul(a, a);
+  float NdotH = fmaxf(dot3x(N, Hh), 0.0f), NdotH2 = xmul(NdotH, NdotH);
+  float num = xadd(a2, 0.001f);
+  float denom = xadd(xmul(NdotH2, xsub(a2, 1.0f)), 1.0f);
+  denom = xmul(xmul(DDGI_PI, denom), denom);
+  return xdiv(num, denom);
 }
 HD float geometry_schlick_ggx(float NdotV, float roughness) {
   float r = (roughness + 1.0f), k = (r * r) / 8.0f;
@@ -535,9 +549,9 @@ HD float geometry_smith(V3 N, V3 V, V3 L, float roughness) {
 }
 // pbr_light.glsl:98-166.  directional: the sun (L, radiance given); point light: caller passes L and radiance too.
 HD V3 calc_light(V3 N, V3 albedo, float metallic, float roughness, V3 worldPos, V3 viewPos, V3 L, V3 radiance) {
-  V3 V = normalize3(viewPos - worldPos);
+  V3 V = normalize3x(mk3(xsub(viewPos.x, worldPos.x), xsub(viewPos.y, worldPos.y), xsub(viewPos.z, worldPos.z)));
   V3 F0 = mix3(mk3(0.04f), albedo, metallic);
-  V3 Hh = normalize3(V + L);
+  V3 Hh = normalize3x(mk3(xadd(V.x, L.x), xadd(V.y, L.y), xadd(V.z, L.z)));
   float NDF = distribution_ggx(N, Hh, roughness);
   float G = geometry_smith(N, V, L, roughness);
   V3 F = F0 + (mk3(1.0f) - F0) * pow5(clampf(1.0f - fmaxf(dot3(Hh, V), 0.0f), 0.0f, 1.0f));   // fresnelSchlick :88-91
@@ -560,9 +574,10 @@ HD V3 atlas_texel(const TraceCtx& c, int x, int y) {
   return mk3(h2f((uint16_t)(t.x & 0xFFFFu)), h2f((uint16_t)(t.x >> 16)), h2f((uint16_t)(t.y & 0xFFFFu)));
 }
 HD V3 atlas_bilinear(const TraceCtx& c, float u, float v) {
-  float x = u * (float)c.W - 0.5f, y = v * (float)c.H - 0.5f;
+  // texel coordinates reach 10*nXZ*nY (2880 at C3): one ulp there is 2.4e-4 texels, so the address math stays exact
+  float x = xsub(xmul(u, (float)c.W), 0.5f), y = xsub(xmul(v, (float)c.H), 0.5f);
   float fx0 = floorf(x), fy0 = floorf(y);
-  float fx = x - fx0, fy = y - fy0; int ix = (int)fx0, iy = (int)fy0;
+  float fx = xsub(x, fx0), fy = xsub(y, fy0); int ix = (int)fx0, iy = (int)fy0;
   V3 t00 = atlas_texel(c, ix, iy), t10 = atlas_texel(c, ix + 1, iy), t01 = atlas_texel(c, ix, iy + 1), t11 = atlas_texel(c, ix + 1, iy + 1);
   float w00 = (1.0f - fx) * (1.0f - fy), w10 = fx * (1.0f - fy), w01 = (1.0f - fx) * fy, w11 = fx * fy;
   return t00 * w00 + t10 * w10 + t01 * w01 + t11 * w11;
@@ -571,9 +586,9 @@ HD V3 atlas_bilinear(const TraceCtx& c, float u, float v) {
 HD V3 sample_single_probe(const TraceCtx& c, int px, int py, int pz, float o0, float o1) {
   int startX = (8 + 2) * px + 1, startY = (8 + 2) * c.nXZ * py + (8 + 2) * pz + 1;
   int endX = startX + 8 - 1, endY = startY + 8 - 1;
-  float tsx = (2.0f * (float)startX + 1.0f) / (2.0f * (float)c.W), tsy = (2.0f * (float)startY + 1.0f) / (2.0f * (float)c.H);
-  float tex = (2.0f * (float)endX + 1.0f) / (2.0f * (float)c.W), tey = (2.0f * (float)endY + 1.0f) / (2.0f * (float)c.H);
-  return atlas_bilinear(c, tsx + (tex - tsx) * o0, tsy + (tey - tsy) * o1);
+  float tsx = xdiv(xadd(xmul(2.0f, (float)startX), 1.0f), xmul(2.0f, (float)c.W)), tsy = xdiv(xadd(xmul(2.0f, (float)startY), 1.0f), xmul(2.0f, (float)c.H));
+  float tex = xdiv(xadd(xmul(2.0f, (float)endX), 1.0f), xmul(2.0f, (float)c.W)), tey = xdiv(xadd(xmul(2.0f, (float)endY), 1.0f), xmul(2.0f, (float)c.H));
+  return atlas_bilinear(c, xadd(tsx, xmul(xsub(tex, tsx), o0)), xadd(tsy, xmul(xsub(tey, tsy), o1)));
 }
 // pbr_light.glsl:240-363 (live-grid branch :294-308) + weightProbe :190-238
 HD V3 sample_probe(const TraceCtx& c, V3 worldPos, V3 normal) {
@@ -582,8 +597,8 @@ HD V3 sample_probe(const TraceCtx& c, V3 worldPos, V3 normal) {
   int pz = clampi((int)floorf((worldPos.z - c.camOff.z) / c.step.z), 0, c.nXZ - 1);
   V3 base = mk3((float)px, (float)py, (float)pz) * c.step + c.camOff;
   V3 alpha = clamp3((worldPos - base) / c.step, 0.0f, 1.0f);
-  float o0, o1; oct_encode(normalize3(normal), o0, o1);
-  o0 = (o0 + 1.0f) * 0.5f; o1 = (o1 + 1.0f) * 0.5f;
+  float o0, o1; oct_encode(normalize3x(normal), o0, o1);
+  o0 = xmul(xadd(o0, 1.0f), 0.5f); o1 = xmul(xadd(o1, 1.0f), 0.5f);
   float sumW = 0.0f; V3 sum = mk3(0.0f);
   // corner order of the source: 000,111,110,100,011,010,001,101 packed as x | y<<1 | z<<2 per nibble
   const uint32_t order = 0x0u | (0x7u << 4) | (0x3u << 8) | (0x1u << 12) | (0x6u << 16) | (0x2u << 20) | (0x4u << 24) | (0x5u << 28);

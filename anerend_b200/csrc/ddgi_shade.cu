@@ -1,0 +1,210 @@
+// ddgi_shade.cu — radiance and convolution kernels of the wavefront path (sm_100a).  Compiled TWICE
+// (__graft_entry__.py NVCC_TU_FLAGS):
+//   -DDDGI_SHADE_EXACT  --fmad=false                                   -> launch_shade_exact / launch_convolve_exact
+//        the oracle's fp32 sequence operation for operation: ProbeRaysIrrTex and the atlas come out bit-identical
+//   (fast)              --fmad=true -prec-div=false -prec-sqrt=false   -> launch_shade_fast / launch_convolve_fast
+//        ANEREND_DDGI_FLAG_FAST_MATH: contraction and approximate div/sqrt (<= 2 ulp), ill-conditioned spots kept exact
+//        with the x* operations of platform.h; within BASELINE.json's 1e-4 relative bar, not bit-identical
+//
+//   k_shade                 rchit:83-109 (calcLight, calcIndirectDiffuseLight, emissive) + the RGBA16F store of rgen:109,
+//                           one thread per HIT ray through the compacted hit list, so warps stay full
+//   k_conv_weights          per layer: W[ray][texel] = max(0, dot(half(dir), octDecode(texel)))   (probe_conv.comp:43-58)
+//   k_probe_convolve_fast   per probe: out[texel] = sum_ray W[ray][texel] * (rad.rgb, 1), normalise, hysteresis blend,
+//                           RGBA16F store (probe_conv.comp:49-89); radiances staged once per block in shared memory as fp32
+#ifndef DDGI_HOST_EMU
+#include "ddgi_wavefront.h"
+
+#ifdef DDGI_SHADE_EXACT
+#define SHADE_NS exact
+#else
+#define SHADE_NS fast
+#endif
+
+namespace ddgi {
+namespace SHADE_NS {
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_shade(const FastCtx c) {
+  const TraceCtx& t = c.t;
+  const uint32_t nHits = c.qcount[FAST_QC_HITS];
+  const int P = t.nXZ * t.nXZ;
+  const V3 sunL = normalize3x(-t.lightDir);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nHits; i += gridDim.x * blockDim.x) {
+    const uint32_t idx = c.hitq[i];
+    const uint32_t slot = idx % (uint32_t)t.N, probeLin = idx / (uint32_t)t.N;
+    const int layerLocal = (int)(probeLin / (uint32_t)P), probe = (int)(probeLin % (uint32_t)P), layer = t.layerBegin + layerLocal;
+    const uint32_t ray = t.rayOrder ? (uint32_t)t.rayOrder[slot] : slot;
+    const V3 origin = mk3((float)(probe % t.nXZ), (float)layer, (float)(probe / t.nXZ)) * t.step + t.camOff;
+    const float4 s0 = c.surf[3 * (size_t)idx], s1 = c.surf[3 * (size_t)idx + 1], s2 = c.surf[3 * (size_t)idx + 2];
+    const V3 pos = mk3(s0.x, s0.y, s0.z), normal = mk3(s0.w, s1.x, s1.y), albedo = mk3(s1.z, s1.w, s2.x);
+    const anerend_material_info_t* m = &t.materials[__float_as_uint(s2.y)];
+    const float metallic = m->met_rough[0], roughness = m->met_rough[1];
+    const V3 emissive = mk3(m->emissive[0], m->emissive[1], m->emissive[2]) * m->emissive[3];
+    const uint32_t lit = c.lit[idx];
+    V3 irradiance = mk3(0.0f);
+    if (lit & 1u) irradiance = calc_light(normal, albedo, metallic, roughness, pos, origin, sunL, t.sunIntensity * mk3(1.0f) * 1.0f);
+    if (t.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) {
+      for (uint32_t li = 0; li < t.numLights; ++li) {
+        if (!(lit & (1u << (1u + li)))) continue;
+        const anerend_light_t* lt = &t.lights[li];
+        const V3 lp = mk3(lt->world_pos[0], lt->world_pos[1], lt->world_pos[2]);
+        const V3 dv = lp - pos; const float dist = sqrtf(dot3(dv, dv)), range = lt->world_pos[3];
+        const V3 L = normalize3x(lp - pos);
+        const float dd = fminf(dist, range);
+        const float att = (1.0f - dd / range) * (1.0f - dd / range) * 1.0f;
+        irradiance = irradiance + calc_light(normal, albedo, metallic, roughness, pos, origin, L, mk3(lt->color[0], lt->color[1], lt->color[2]) * att);
+      }
+    }
+    if ((t.uboFlags & ANEREND_UBO_DDGI_MULTI_FLAG) == ANEREND_UBO_DDGI_MULTI_FLAG)
+      irradiance = irradiance + calc_indirect(t, normal, albedo, metallic, roughness, pos, origin);
+    const V3 rad = irradiance + emissive;
+    const size_t o = ((size_t)layer * P + probe) * t.N + ray;
+    t.rayIrr[o] = make_uint2((uint32_t)f2h(rad.x) | ((uint32_t)f2h(rad.y) << 16), (uint32_t)f2h(rad.z) | (0x3C00u << 16));
+    if (t.records) {
+      const float4 h = c.hits[idx];
+      anerend_ddgi_ray_record_t rr;
+      rr.prim = __float_as_uint(h.w); rr.t = h.x; rr.u = h.y; rr.v = h.z; rr.radiance[0] = rad.x; rr.radiance[1] = rad.y; rr.radiance[2] = rad.z; rr.lit_mask = lit;
+      t.records[o] = rr;
+    }
+  }
+}
+
+static cudaError_t launch_shade_impl(const FastCtx& f, cudaStream_t s) {
+  static int maxBlocks = 0;
+  if (!maxBlocks) {
+    int dev = 0, sms = 0, nb = 0;
+    cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade, 128, 0);
+    maxBlocks = sms * (nb > 0 ? nb : 1);
+  }
+  // the hit count lives on the device: size the grid for the worst case (every ray hits), capped at one resident wave
+  uint32_t blocks = (f.totalRays + 127u) / 128u;
+  if (blocks > (uint32_t)maxBlocks) blocks = (uint32_t)maxBlocks;
+  if (blocks == 0) return cudaSuccess;
+  k_shade<<<blocks, 128, 0, s>>>(f);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_conv_weights(const ConvFastCtx f) {
+  const ConvCtx& c = f.c;
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (uint32_t)c.numLayers * (uint32_t)c.N) return;
+  // position p in the reference's loop order (x outer, y inner; probe_conv.comp:49-50) <-> ray index y*Sx + x
+  const uint32_t layerLocal = idx / (uint32_t)c.N, pos = idx % (uint32_t)c.N;
+  const uint32_t ray = (pos % (uint32_t)c.Sy) * (uint32_t)c.Sx + pos / (uint32_t)c.Sy;
+  const float4 d4 = c.dirs[layerLocal * (uint32_t)c.N + ray];      // [numLayers][N]
+  const V3 d = mk3(h2f(f2h(d4.x)), h2f(f2h(d4.y)), h2f(f2h(d4.z)));  // what the rgba16f ProbeRaysDirTex holds (rgen:108)
+  float4* out = (float4*)(f.weights + (size_t)idx * 64);
+#pragma unroll 1
+  for (int j = 0; j < 8; ++j) {
+    float w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float ux = (2.0f * (float)i + 1.0f) / (2.0f * 8.0f), uy = (2.0f * (float)j + 1.0f) / (2.0f * 8.0f);   // pixelToUv
+      ux = ux * 2.0f - 1.0f; uy = uy * 2.0f - 1.0f;
+      const V3 octDir = oct_decode(ux, uy);
+      const float ww = fmaxf(0.0f, dot3(d, octDir));
+      w[i] = ww > 1e-6f ? ww : 0.0f;                                // probe_conv.comp:55
+    }
+    out[2 * j] = make_float4(w[0], w[1], w[2], w[3]);
+    out[2 * j + 1] = make_float4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+#define CONV_PPT 4                    // probes per thread
+#define CONV_G (4 * CONV_PPT)         // probes per block (256 threads = 64 texels x 4 probe groups)
+#define CONV_CHUNK 128                // rays staged per pass through shared memory
+
+__global__ void __launch_bounds__(256) k_probe_convolve_fast(const ConvFastCtx f) {
+  const ConvCtx& c = f.c;
+  __shared__ float4 sRad[CONV_G * CONV_CHUNK];                      // 32 KB
+  const int P = c.nXZ * c.nXZ;
+  const int blocksPerLayer = (P + CONV_G - 1) / CONV_G;
+  const int layerLocal = (int)blockIdx.x / blocksPerLayer, g0 = ((int)blockIdx.x % blocksPerLayer) * CONV_G;
+  const int layer = c.layerBegin + layerLocal;
+  const int texel = (int)threadIdx.x & 63, sub = (int)threadIdx.x >> 6;
+  float acc[CONV_PPT][4];
+#pragma unroll
+  for (int k = 0; k < CONV_PPT; ++k) { acc[k][0] = 0.0f; acc[k][1] = 0.0f; acc[k][2] = 0.0f; acc[k][3] = 0.0f; }
+  const float* W = f.weights + (size_t)layerLocal * c.N * 64 + texel;
+  for (int r0 = 0; r0 < c.N; r0 += CONV_CHUNK) {
+    const int nr = min(CONV_CHUNK, c.N - r0);
+    __syncthreads();
+    for (int e = (int)threadIdx.x; e < CONV_G * CONV_CHUNK; e += 256) {
+      const int g = e / CONV_CHUNK, r = e % CONV_CHUNK;
+      float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      if (g0 + g < P && r < nr) {
+        const int pos = r0 + r, ray = (pos % c.Sy) * c.Sx + pos / c.Sy;      // reference loop order
+        const uint2 rr = __ldg(&c.rayIrr[((size_t)layer * P + g0 + g) * c.N + ray]);
+        v = make_float4(h2f((uint16_t)(rr.x & 0xFFFFu)), h2f((uint16_t)(rr.x >> 16)), h2f((uint16_t)(rr.y & 0xFFFFu)), 1.0f);
+      }
+      sRad[e] = v;
+    }
+    __syncthreads();
+    const float4* myRad = sRad + sub * CONV_PPT * CONV_CHUNK;
+#pragma unroll 4
+    for (int r = 0; r < nr; ++r) {
+      const float w = __ldg(W + (size_t)(r0 + r) * 64);
+#pragma unroll
+      for (int k = 0; k < CONV_PPT; ++k) {
+        const float4 v = myRad[k * CONV_CHUNK + r];
+#ifdef DDGI_SHADE_EXACT
+        // the oracle's sequence: result += (w*rad, w) in loop order; w == 0 where the shader skips (adds +0)
+        acc[k][0] = acc[k][0] + w * v.x; acc[k][1] = acc[k][1] + w * v.y; acc[k][2] = acc[k][2] + w * v.z; acc[k][3] += w;
+#else
+        acc[k][0] = fmaf(w, v.x, acc[k][0]); acc[k][1] = fmaf(w, v.y, acc[k][1]);
+        acc[k][2] = fmaf(w, v.z, acc[k][2]); acc[k][3] += w;
+#endif
+      }
+    }
+  }
+  const int i = texel & 7, j = texel >> 3;
+  const float hy = c.hysteresis;
+#pragma unroll
+  for (int k = 0; k < CONV_PPT; ++k) {
+    const int probe = g0 + sub * CONV_PPT + k;
+    if (probe >= P) continue;
+    const int probeX = probe % c.nXZ, probeZ = probe / c.nXZ;
+    const int ax = 10 * probeX + 1 + i, ay = 10 * c.nXZ * layer + 10 * probeZ + 1 + j;       // pixOffset + pixel (:42,:64)
+    const size_t ti = (size_t)ay * c.W + ax;
+    const uint2 ot = c.atlas[ti];
+    const float o0 = h2f((uint16_t)(ot.x & 0xFFFFu)), o1 = h2f((uint16_t)(ot.x >> 16)), o2 = h2f((uint16_t)(ot.y & 0xFFFFu)), o3 = h2f((uint16_t)(ot.y >> 16));
+    float r0 = acc[k][0], r1 = acc[k][1], r2 = acc[k][2];
+    const float r3 = acc[k][3];
+#ifdef DDGI_SHADE_EXACT
+    if (r3 > 1e-6f) { r0 /= r3; r1 /= r3; r2 /= r3; }
+#else
+    if (r3 > 1e-6f) { const float inv = 1.0f / r3; r0 *= inv; r1 *= inv; r2 *= inv; }
+#endif
+    const float n0 = r0 * (1.0f - hy) + o0 * hy, n1 = r1 * (1.0f - hy) + o1 * hy, n2 = r2 * (1.0f - hy) + o2 * hy, n3 = r3 * (1.0f - hy) + o3 * hy;
+    const uint2 nt = make_uint2((uint32_t)f2h(n0) | ((uint32_t)f2h(n1) << 16), (uint32_t)f2h(n2) | ((uint32_t)f2h(n3) << 16));
+    c.atlas[ti] = nt;
+    for (int p = 0; p < c.numPeers; ++p) c.peers[p][ti] = nt;               // fused all-gather: store into every peer's atlas
+    if (c.texelRecords) c.texelRecords[ti] = make_float4(n0, n1, n2, n3);
+  }
+}
+
+static cudaError_t launch_convolve_impl(const ConvFastCtx& f, cudaStream_t s) {
+  const ConvCtx& c = f.c;
+  const uint32_t nw = (uint32_t)c.numLayers * (uint32_t)c.N;
+  if (nw == 0) return cudaSuccess;
+  k_conv_weights<<<(nw + 127u) / 128u, 128, 0, s>>>(f);
+  const int P = c.nXZ * c.nXZ;
+  const uint32_t blocks = (uint32_t)c.numLayers * (uint32_t)((P + CONV_G - 1) / CONV_G);
+  k_probe_convolve_fast<<<blocks, 256, 0, s>>>(f);
+  return cudaGetLastError();
+}
+
+}  // namespace SHADE_NS
+
+#ifdef DDGI_SHADE_EXACT
+cudaError_t launch_shade_exact(const FastCtx& f, cudaStream_t s) { return exact::launch_shade_impl(f, s); }
+cudaError_t launch_convolve_exact(const ConvFastCtx& f, cudaStream_t s) { return exact::launch_convolve_impl(f, s); }
+#else
+cudaError_t launch_shade_fast(const FastCtx& f, cudaStream_t s) { return fast::launch_shade_impl(f, s); }
+cudaError_t launch_convolve_fast(const ConvFastCtx& f, cudaStream_t s) { return fast::launch_convolve_impl(f, s); }
+#endif
+
+}  // namespace ddgi
+#endif  // DDGI_HOST_EMU

@@ -1,0 +1,59 @@
+// ddgi_wavefront.h — shared declarations of the production (wavefront) kernels for sm_100a.
+//
+// Translation units:
+//   ddgi_api.cu   (--fmad=false)  traversal + hit attributes (ddgi_fast.cuh): everything that decides WHICH triangle a
+//                                 ray hits and where shadow rays start is the oracle's fp32 sequence bit for bit
+//   ddgi_shade.cu                 radiance (rchit:83-109, pbr_light.glsl) and the convolution (probe_conv.comp), built twice:
+//                                 exact (--fmad=false, default: bit-identical atlas) and fast (ANEREND_DDGI_FLAG_FAST_MATH:
+//                                 contraction + approximate div/sqrt, inside BASELINE.json's 1e-4 relative bar)
+#pragma once
+#ifndef __CUDACC__
+#error "ddgi_wavefront.h is CUDA-only"
+#endif
+#include "ddgi_kernels.cuh"
+
+namespace ddgi {
+
+// per-triangle shading record, written once by k_flatten_scene in global-triangle-id order (object space, so a refit
+// of moving nodes leaves it valid): replaces the 4-deep gather triInstance -> instance -> indices -> 3 x 96 B vertices
+// of rchit:27-38 by five independent 16-byte loads
+struct ShadeTri {
+  float p0[3], p1[3], p2[3];      // object-space positions   (rchit:40-41)
+  float n0[3], n1[3], n2[3];      // object-space normals     (rchit:72)
+  uint32_t instance;              // index into instances / xforms
+  uint32_t flags;                 // bit0: material factor decides the albedo (vertex colours not needed)
+};
+static_assert(sizeof(ShadeTri) == 80, "ShadeTri is five float4");
+
+#define FAST_QC_PRIMARY 32         // qcount slots: [0..31] per-light shadow queues, then cursors / hit count
+#define FAST_QC_SHADOW 33
+#define FAST_QC_HITS 34
+#define FAST_QC_SIZE 36
+
+struct FastCtx {
+  TraceCtx t;
+  const float4* shadeTris;  // [numTris] ShadeTri
+  float4* hits;             // [rays] t,u,v,prim   (launch order: idx = (layerLocal*P + probe)*N + slot)
+  float4* surf;             // [rays][3] pos.xyz,n.x | n.yz,albedo.xy | albedo.z,material,-,-
+  uint32_t* lit;            // [rays] visibility bits written by k_trace_shadow
+  uint32_t* queues;         // [numQueues][rays] ray indices needing a shadow ray towards light q (0 = sun)
+  uint32_t* hitq;           // [rays] compacted indices of the rays that hit (k_shade runs over these with full warps)
+  uint32_t* qcount;         // FAST_QC_SIZE counters
+  uint32_t totalRays, numQueues;
+};
+
+// W[layer][ray][texel] = max(0, dot(half(dir), octDir(texel))), zero where <= 1e-6 (probe_conv.comp:53-58).  The
+// rotation is shared by every probe of a layer execution, so the convolution is the contraction
+// [probes*4 x N] . [N x 64] — done in fp32 on the CUDA cores (0.9 GFLOP at C3: not tensor-worthy).
+struct ConvFastCtx {
+  ConvCtx c;
+  float* weights;           // [numLayers][N][64], N in the reference's loop order (x outer, y inner)
+};
+
+// launchers implemented in ddgi_shade.cu (one pair per build of that file)
+cudaError_t launch_shade_exact(const FastCtx& f, cudaStream_t s);
+cudaError_t launch_convolve_exact(const ConvFastCtx& f, cudaStream_t s);
+cudaError_t launch_shade_fast(const FastCtx& f, cudaStream_t s);
+cudaError_t launch_convolve_fast(const ConvFastCtx& f, cudaStream_t s);
+
+}  // namespace ddgi

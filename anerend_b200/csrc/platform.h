@@ -23,6 +23,24 @@ inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return
 
 namespace ddgi {
 
+// Single-rounded fp32 operations that no compiler flag may fuse or approximate.  The radiance kernels (ddgi_shade.cu)
+// are built with contraction and approximate div/sqrt; where a result is ill-conditioned (atlas texel addresses: one
+// ulp of a coordinate near 2880 is 2e-4 texels; the GGX denominator at low roughness) the oracle's exact sequence is
+// kept with these.  Everywhere else in device code compiled with --fmad=false they equal the plain operators.
+#ifdef __CUDA_ARCH__
+HD float xmul(float a, float b) { return __fmul_rn(a, b); }
+HD float xadd(float a, float b) { return __fadd_rn(a, b); }
+HD float xsub(float a, float b) { return __fsub_rn(a, b); }
+HD float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+HD float xsqrt(float a) { return __fsqrt_rn(a); }
+#else
+HD float xmul(float a, float b) { return a * b; }
+HD float xadd(float a, float b) { return a + b; }
+HD float xsub(float a, float b) { return a - b; }
+HD float xdiv(float a, float b) { return a / b; }
+HD float xsqrt(float a) { return sqrtf(a); }
+#endif
+
 HD uint32_t f2u(float f) {
 #ifdef __CUDA_ARCH__
   return __float_as_uint(f);

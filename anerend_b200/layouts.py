@@ -44,5 +44,6 @@ FLAG_RAY_RECORDS = 1 << 1
 FLAG_TEXEL_RECORDS = 1 << 2
 FLAG_COUNTERS = 1 << 3
 FLAG_SIMPLE_KERNELS = 1 << 4
+FLAG_FAST_MATH = 1 << 5
 
 MISS = 0xFFFFFFFF

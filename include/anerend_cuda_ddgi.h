@@ -40,6 +40,9 @@ extern "C" {
 #define ANEREND_DDGI_FLAG_TEXEL_RECORDS (1u << 2) /* keep the fp32 pre-quantisation value of every convolved texel (parity tests)  */
 #define ANEREND_DDGI_FLAG_COUNTERS      (1u << 3) /* count BVH nodes visited / triangles tested (roofline bytes); slower kernels    */
 #define ANEREND_DDGI_FLAG_SIMPLE_KERNELS (1u << 4) /* one-thread-per-ray reference kernel instead of the wavefront kernels (debug)    */
+#define ANEREND_DDGI_FLAG_FAST_MATH     (1u << 5) /* radiance + convolution with contracted / approximate fp32 (<= 1e-4 relative per
+                                                     update instead of bit-identical to the oracle's defined arithmetic); hit ids,
+                                                     shadow-ray results and hit positions are unaffected                            */
 
 /*
  * Parameters that are compile-time constants in the reference
