@@ -294,9 +294,9 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   f.qcount = h->dQcount; f.totalRays = n; f.numQueues = nq;
   BE_CHECK(h, be.zero(h->dQcount, FAST_QC_SIZE * sizeof(uint32_t)));
   const bool cnt = (h->p.flags & ANEREND_DDGI_FLAG_COUNTERS) != 0;
-  const uint32_t blocks = (n + 127u) / 128u;
+  const uint32_t blocks = (n + PREP_BLOCK - 1u) / PREP_BLOCK;
   if (cnt) k_trace_primary<true><<<h->gridPrimary[1], 128, 0, be.stream>>>(f); else k_trace_primary<false><<<h->gridPrimary[0], 128, 0, be.stream>>>(f);
-  k_shade_prep<<<blocks, 128, 0, be.stream>>>(f);
+  k_shade_prep<<<blocks, PREP_BLOCK, 0, be.stream>>>(f);
   if (cnt) k_trace_shadow<true><<<h->gridShadow[1], 128, 0, be.stream>>>(f); else k_trace_shadow<false><<<h->gridShadow[0], 128, 0, be.stream>>>(f);
   BE_CHECK(h, be.ok((h->p.flags & ANEREND_DDGI_FLAG_FAST_MATH) ? launch_shade_fast(f, be.stream) : launch_shade_exact(f, be.stream)));
   be.launches += 5;

@@ -176,17 +176,9 @@ __global__ void __launch_bounds__(128) k_trace_primary(const FastCtx c) {
 // ------------------------------------------------------------------------------------------------------------
 // k_shade_prep: rchit:27-42,70-77 (hit attributes + surface) and the decision which shadow rays exist
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void enqueue(const FastCtx& c, uint32_t q, bool need, uint32_t idx, uint32_t lane) {
-  const uint32_t m = __ballot_sync(0xFFFFFFFFu, need);
-  if (!m) return;
-  const int leader = __ffs((int)m) - 1;
-  uint32_t base = 0;
-  if ((int)lane == leader) base = atomicAdd(&c.qcount[q], (uint32_t)__popc(m));
-  base = __shfl_sync(0xFFFFFFFFu, base, leader);
-  if (need) c.queues[(size_t)q * c.totalRays + base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = idx;
-}
-
-__global__ void __launch_bounds__(128) k_shade_prep(const FastCtx c) {
+#define PREP_BLOCK 256
+#define PREP_WARPS (PREP_BLOCK / 32)
+__global__ void __launch_bounds__(PREP_BLOCK) k_shade_prep(const FastCtx c) {
   const TraceCtx& t = c.t;
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
   const bool inRange = idx < c.totalRays;
@@ -239,30 +231,43 @@ __global__ void __launch_bounds__(128) k_shade_prep(const FastCtx c) {
                        rr.radiance[0] = t.sky.x; rr.radiance[1] = t.sky.y; rr.radiance[2] = t.sky.z; rr.lit_mask = 0u; t.records[o] = rr; }
     }
   }
-  { // compacted list of the rays that hit: k_shade runs over it with full warps
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, isHit);
-    if (m) {
-      const int leader = __ffs((int)m) - 1;
-      uint32_t base = 0;
-      if ((int)lane == leader) base = atomicAdd(&c.qcount[FAST_QC_HITS], (uint32_t)__popc(m));
-      base = __shfl_sync(0xFFFFFFFFu, base, leader);
-      if (isHit) c.hitq[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = idx;
+  // Which queues does this ray enter?  bit q: shadow ray towards light q (0 = sun, rchit:45-66: every hit; point
+  // lights, extension E1: only where the light can contribute); bit 32: the compacted hit list k_shade runs over.
+  uint32_t needMask = isHit ? 1u : 0u;
+  if (isHit && (t.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS)) {
+    for (uint32_t li = 0; li < t.numLights; ++li) {
+      const anerend_light_t* lt = &t.lights[li];
+      if (lt->color[3] > 0.5f) {
+        const V3 lp = mk3(lt->world_pos[0], lt->world_pos[1], lt->world_pos[2]);
+        const V3 dv = lp - pos; const float dist = sqrtf(dot3(dv, dv));
+        if (dist < lt->world_pos[3]) { const V3 L = normalize3(lp - pos); if (dot3(normal, L) > 0.0f) needMask |= 1u << (1u + li); }
+      }
     }
   }
-  // sun shadow ray for every hit (rchit:45-66); point-light rays (extension E1) only where the light can contribute
-  enqueue(c, 0u, isHit, idx, lane);
-  if (t.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) {
-    for (uint32_t li = 0; li < t.numLights; ++li) {
-      bool need = false;
-      if (isHit) {
-        const anerend_light_t* lt = &t.lights[li];
-        if (lt->color[3] > 0.5f) {
-          const V3 lp = mk3(lt->world_pos[0], lt->world_pos[1], lt->world_pos[2]);
-          const V3 dv = lp - pos; const float dist = sqrtf(dot3(dv, dv));
-          if (dist < lt->world_pos[3]) { const V3 L = normalize3(lp - pos); need = dot3(normal, L) > 0.0f; }
-        }
-      }
-      enqueue(c, 1u + li, need, idx, lane);
+  // block-aggregated append: one atomic per queue per block (a per-warp atomic on nine neighbouring counters was the
+  // whole cost of this kernel), order inside the block = ray order
+  __shared__ uint32_t sCnt[33][PREP_WARPS];
+  __shared__ uint32_t sBase[33];
+  const uint32_t warp = threadIdx.x >> 5, nq = c.numQueues;
+  for (uint32_t q = 0; q <= nq; ++q) {
+    const bool need = q < nq ? ((needMask >> q) & 1u) != 0u : isHit;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, need);
+    if (lane == 0) sCnt[q][warp] = (uint32_t)__popc(m);
+  }
+  __syncthreads();
+  if (threadIdx.x <= nq) {
+    const uint32_t q = threadIdx.x;
+    uint32_t sum = 0;
+    for (uint32_t w = 0; w < PREP_WARPS; ++w) { const uint32_t v = sCnt[q][w]; sCnt[q][w] = sum; sum += v; }
+    sBase[q] = sum ? atomicAdd(&c.qcount[q < nq ? FAST_QC(q) : FAST_QC_HITS], sum) : 0u;
+  }
+  __syncthreads();
+  for (uint32_t q = 0; q <= nq; ++q) {
+    const bool need = q < nq ? ((needMask >> q) & 1u) != 0u : isHit;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, need);
+    if (need) {
+      const uint32_t o = sBase[q] + sCnt[q][warp] + (uint32_t)__popc(m & ((1u << lane) - 1u));
+      if (q < nq) c.queues[(size_t)q * c.totalRays + o] = idx; else c.hitq[o] = idx;
     }
   }
 }
@@ -274,7 +279,7 @@ template <bool CNT>
 __global__ void __launch_bounds__(128) k_trace_shadow(const FastCtx c) {
   const TraceCtx& t = c.t;
   __shared__ uint32_t sPrefix[34];
-  if (threadIdx.x == 0) { uint32_t s = 0; for (uint32_t q = 0; q < c.numQueues; ++q) { sPrefix[q] = s; s += c.qcount[q]; } sPrefix[c.numQueues] = s; }
+  if (threadIdx.x == 0) { uint32_t s = 0; for (uint32_t q = 0; q < c.numQueues; ++q) { sPrefix[q] = s; s += c.qcount[FAST_QC(q)]; } sPrefix[c.numQueues] = s; }
   __syncthreads();
   const uint32_t total = sPrefix[c.numQueues];
   const uint32_t lane = threadIdx.x & 31u;

@@ -25,10 +25,14 @@ struct ShadeTri {
 };
 static_assert(sizeof(ShadeTri) == 80, "ShadeTri is five float4");
 
-#define FAST_QC_PRIMARY 32         // qcount slots: [0..31] per-light shadow queues, then cursors / hit count
-#define FAST_QC_SHADOW 33
-#define FAST_QC_HITS 34
-#define FAST_QC_SIZE 36
+// qcount: one counter per 256 bytes (same-line atomics serialise in one L2 slice): [0..31] per-light shadow queue
+// lengths, then the fetch cursors of the persistent kernels and the hit count
+#define FAST_QC_STRIDE 64
+#define FAST_QC(q) ((q) * FAST_QC_STRIDE)
+#define FAST_QC_PRIMARY FAST_QC(32)
+#define FAST_QC_SHADOW FAST_QC(33)
+#define FAST_QC_HITS FAST_QC(34)
+#define FAST_QC_SIZE FAST_QC(35)
 
 struct FastCtx {
   TraceCtx t;
