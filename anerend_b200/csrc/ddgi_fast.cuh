@@ -4,10 +4,10 @@
 // (irradiance_probe_update.rgen:48-111, .rchit:24-111, .rmiss:17-21).  A one-thread-per-ray transcription of that
 // (k_probe_trace in ddgi_kernels.cuh) keeps only ~8 of 32 lanes busy (profiles/r01_*), so the pass is split into
 // stages that each keep warps full:
-//   k_trace_primary  persistent warps, closest-hit BVH8 traversal, rays re-fetched with __ballot when lanes drain
+//   k_trace<false>   persistent warps, closest-hit BVH8 traversal of the probe rays
 //   k_shade_prep     hit attributes (rchit:27-42,70-77) -> surface record; shadow rays binned into one queue per light
-//   k_trace_shadow   persistent warps, any-hit traversal over the per-light queues (coherent direction / target)
-//   k_shade          calcLight + calcIndirectDiffuseLight + emissive (rchit:83-109), RGBA16F store (rgen:109)
+//   k_trace<true>    persistent warps, any-hit traversal over the per-light queues (coherent direction / target)
+//   k_shade          calcLight + calcIndirectDiffuseLight + emissive (rchit:83-109), RGBA16F store (rgen:109)  [ddgi_shade.cu]
 // Per-ray arithmetic is the same sequence of fp32 operations as the simple path and the oracle (the box test differs,
 // but boxes are conservative and the triangle test decides), so results stay bit-identical.
 #pragma once
@@ -18,30 +18,90 @@
 
 namespace ddgi {
 
-#define FAST_FETCH_THRESHOLD 22     // refill the warp when fewer lanes than this still have a ray
+// Tunables of the persistent traversal kernels (FastCtx::tune; DDGI_TUNE="a,b,c" overrides them for sweeps)
+#define TUNE_TRI_TRIGGER 0          // run a triangle round when at least this many lanes hold untested triangles
+#define FAST_CHUNK 64               // ray indices taken per atomic on the global cursor (two staged batches)
 
+// Node-phase state of a ray lives in registers; everything only the triangle rounds touch (direction, parked triangle
+// groups, hit attributes, ray tag) lives in shared memory, so the box test keeps 8 blocks of 128 threads on an SM.
 struct RayState {
-  float ox, oy, oz, dx, dy, dz, idx, idy, idz, tmin, tmax, hu, hv;
-  uint32_t octinv, prim;
-  uint2 ng, tg;
+  float ox, oy, oz, idx, idy, idz, tmax;
+  uint32_t octm;                    // XOR-permutation masks of the ray's octant: 0x55/0x33/0x0F in bytes 0/1/2 where the
+                                    // direction is POSITIVE on x/y/z (bit index ^ octinv), octinv itself in bits 24..26
+  uint2 ng;                         // current node group: child base | hit-children bits (ray order) << 24 | imask
   int sp;
+  uint32_t npend;                   // parked triangle groups (0..2)
 };
 
-__device__ __forceinline__ void ray_begin(RayState& r, V3 o, V3 d, float tmin, float tmax) {
-  r.ox = o.x; r.oy = o.y; r.oz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
-  r.idx = 1.0f / safe_dir(d.x); r.idy = 1.0f / safe_dir(d.y); r.idz = 1.0f / safe_dir(d.z);
-  r.tmin = tmin; r.tmax = tmax; r.hu = 0.0f; r.hv = 0.0f; r.prim = DDGI_MISS;
-  r.octinv = 7u - ((r.idx < 0.0f ? 1u : 0u) | (r.idy < 0.0f ? 2u : 0u) | (r.idz < 0.0f ? 4u : 0u));   // sign of the SAFE inverse (d = -0 -> negative)
-  r.ng = make_uint2(0u, 0x80000000u); r.tg = make_uint2(0u, 0u); r.sp = 0;
+#define LS_DIR 0                    // per-lane shared state, SoA [field][lane] of 16 bytes: (d.xyz, tag)
+#define LS_RES 1                    //   (t | hu | hv | prim) closest hit so far;  any-hit: (-,-,-, aux = light bit)
+#define LS_PEND_A 2                 //   (triBase, hit bits, triMask, -)
+#define LS_PEND_B 3
+#define LS_FIELDS 4
+
+// staged ray (shared memory, 3 x float4): (o.xyz, tmax) (d.xyz, tag) (1/d.xyz, aux)
+__device__ __forceinline__ void ray_stage(float4* s, V3 o, V3 d, float tmax, uint32_t tag, uint32_t aux) {
+  s[0] = make_float4(o.x, o.y, o.z, tmax);
+  s[1] = make_float4(d.x, d.y, d.z, __uint_as_float(tag));
+  s[2] = make_float4(1.0f / safe_dir(d.x), 1.0f / safe_dir(d.y), 1.0f / safe_dir(d.z), __uint_as_float(aux));
 }
 
-// 8 quantised child boxes against the ray.  Plane bytes become floats 1+q/32768 with one PRMT each (no I2F);
-// near/far planes are picked by the direction sign, so no per-child min/max between lo and hi is needed.
-__device__ __forceinline__ void node_step(const uint4* __restrict__ nodes, RayState& r, uint2* stack) {
+// Two plane bytes of q -> floats 1024+q: ONE PRMT (alu pipe) builds the half2 {0x64:q_a, 0x64:q_b}, the two
+// half->float conversions issue on the fma pipe.  profiles/r02_ncu_trace_v2: the box test was alu-pipe bound
+// (alu 68 %, fma 20 % busy) with one PRMT per plane byte.  k64 = 0x64646464 is a kernel ARGUMENT: a literal would be
+// folded into the immediate slot and the selector re-materialised in a register for every PRMT.
+template <int PAIR>
+__device__ __forceinline__ float2 planes2(uint32_t q, uint32_t k64) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(q), "r"(k64), "n"(PAIR ? 0x4342 : 0x4140));
+  return __half22float2(*reinterpret_cast<const __half2*>(&d));
+}
+
+#define CHILD_CONST(S) ((7u << (3 * (S))) | (1u << (24 + (S))))
+
+// One word of four children per axis side -> hit bits of those four children (slot order).
+template <int W>
+__device__ __forceinline__ uint32_t four_children(const uint32_t qnx, const uint32_t qny, const uint32_t qnz, const uint32_t qfx, const uint32_t qfy,
+                                                  const uint32_t qfz, const float ax, const float ay, const float az, const float bx, const float by,
+                                                  const float bz, const float axf, const float ayf, const float azf, const float bxf, const float byf,
+                                                  const float bzf, const float tmin, const float tmax, const uint32_t k64) {
+  uint32_t acc = 0;
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const float2 nx = p ? planes2<1>(qnx, k64) : planes2<0>(qnx, k64), ny = p ? planes2<1>(qny, k64) : planes2<0>(qny, k64),
+                 nz = p ? planes2<1>(qnz, k64) : planes2<0>(qnz, k64);
+    const float2 fx = p ? planes2<1>(qfx, k64) : planes2<0>(qfx, k64), fy = p ? planes2<1>(qfy, k64) : planes2<0>(qfy, k64),
+                 fz = p ? planes2<1>(qfz, k64) : planes2<0>(qfz, k64);
+    {
+      const float tn = fmaxf(fmaxf(fmaf(nx.x, ax, bx), fmaf(ny.x, ay, by)), fmaxf(fmaf(nz.x, az, bz), tmin));
+      const float tf = fminf(fminf(fmaf(fx.x, axf, bxf), fmaf(fy.x, ayf, byf)), fminf(fmaf(fz.x, azf, bzf), tmax));
+      acc |= (tn <= tf) ? CHILD_CONST(4 * W + 2 * p) : 0u;
+    }
+    {
+      const float tn = fmaxf(fmaxf(fmaf(nx.y, ax, bx), fmaf(ny.y, ay, by)), fmaxf(fmaf(nz.y, az, bz), tmin));
+      const float tf = fminf(fminf(fmaf(fx.y, axf, bxf), fmaf(fy.y, ayf, byf)), fminf(fmaf(fz.y, azf, bzf), tmax));
+      acc |= (tn <= tf) ? CHILD_CONST(4 * W + 2 * p + 1) : 0u;
+    }
+  }
+  return acc;
+}
+
+// bit s of the 8-bit mask x -> bit s ^ octinv (children in the order this ray meets them, Ylitie 2017 §3.2)
+__device__ __forceinline__ uint32_t octant_permute(uint32_t x, uint32_t octm) {
+  uint32_t t = ((x >> 1) ^ x) & octm & 0x55u; x ^= t | (t << 1);
+  t = ((x >> 2) ^ x) & (octm >> 8) & 0x33u; x ^= t | (t << 2);
+  t = ((x >> 4) ^ x) & (octm >> 16) & 0x0Fu; x ^= t | (t << 4);
+  return x;
+}
+
+// 8 quantised child boxes against the ray; near/far planes are picked by the direction sign, so no per-child min/max
+// between lo and hi is needed.  Consumes the front child of r.ng (ray order), leaves the hit internal children in r.ng
+// and returns (triBase, hit triangle bits, triMask).
+__device__ __forceinline__ uint4 node_step(const uint4* __restrict__ nodes, RayState& r, uint2* stack, const float tmin, const uint32_t k64) {
   const int bit = 31 - __clz((int)r.ng.y);
   r.ng.y &= ~(1u << bit);
   if (r.ng.y & 0xFF000000u) stack[r.sp++] = r.ng;
-  const uint32_t slot = ((uint32_t)bit - 24u) ^ r.octinv;
+  const uint32_t slot = ((uint32_t)bit - 24u) ^ (r.octm >> 24);
   const uint32_t rel = (uint32_t)__popc(r.ng.y & ~(0xFFFFFFFFu << slot) & 0xFFu);
   const uint4* nd = nodes + 5 * (size_t)(r.ng.x + rel);
   const uint4 n0 = __ldg(nd), n1 = __ldg(nd + 1), n2 = __ldg(nd + 2), n3 = __ldg(nd + 3), n4 = __ldg(nd + 4);
@@ -50,126 +110,181 @@ __device__ __forceinline__ void node_step(const uint4* __restrict__ nodes, RaySt
   const uint32_t nearx0 = nx ? n3.z : n2.x, nearx1 = nx ? n3.w : n2.y, farx0 = nx ? n2.x : n3.z, farx1 = nx ? n2.y : n3.w;
   const uint32_t neary0 = ny ? n4.x : n2.z, neary1 = ny ? n4.y : n2.w, fary0 = ny ? n2.z : n4.x, fary1 = ny ? n2.w : n4.y;
   const uint32_t nearz0 = nz ? n4.z : n3.x, nearz1 = nz ? n4.w : n3.y, farz0 = nz ? n3.x : n4.z, farz1 = nz ? n3.y : n4.w;
-  const float ax = __uint_as_float((n0.w & 0xFFu) << 23) * r.idx * 32768.0f;
-  const float ay = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * r.idy * 32768.0f;
-  const float az = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * r.idz * 32768.0f;
-  const float bx = (__uint_as_float(n0.x) - r.ox) * r.idx - ax;
-  const float by = (__uint_as_float(n0.y) - r.oy) * r.idy - ay;
-  const float bz = (__uint_as_float(n0.z) - r.oz) * r.idz - az;
+  // t(q) = (p + q*2^e - o) / d = (1024 + q) * a + b  with a = 2^e / d,  b = (p - o) / d - 1024 a
+  const float ax = __uint_as_float((n0.w & 0xFFu) << 23) * r.idx;
+  const float ay = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * r.idy;
+  const float az = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * r.idz;
+  const float bx = fmaf(-1024.0f, ax, (__uint_as_float(n0.x) - r.ox) * r.idx);
+  const float by = fmaf(-1024.0f, ay, (__uint_as_float(n0.y) - r.oy) * r.idy);
+  const float bz = fmaf(-1024.0f, az, (__uint_as_float(n0.z) - r.oz) * r.idz);
   const float kF = 1.0000004f;          // far side widened: conservative against rounding in the slab arithmetic
   const float axf = ax * kF, ayf = ay * kF, azf = az * kF, bxf = bx * kF, byf = by * kF, bzf = bz * kF;
-  // meta bytes -> per-child hit bits (internal: 1 << (24 + (slot ^ octinv)); leaf: unary count << first triangle)
-  const uint32_t octinv4 = r.octinv * 0x01010101u;
-  uint32_t hitmask = 0;
-#pragma unroll
-  for (int w = 0; w < 2; ++w) {
-    const uint32_t mw = w ? n1.w : n1.z;
-    const uint32_t isInner = (mw & (mw << 1)) & 0x10101010u;
-    const uint32_t innerMask = (isInner >> 4) * 0xFFu;
-    const uint32_t bitIndex = (mw ^ (octinv4 & innerMask)) & 0x1F1F1F1Fu;
-    const uint32_t childBits = (mw >> 5) & 0x07070707u;
-    const uint32_t qnx = w ? nearx1 : nearx0, qny = w ? neary1 : neary0, qnz = w ? nearz1 : nearz0;
-    const uint32_t qfx = w ? farx1 : farx0, qfy = w ? fary1 : fary0, qfz = w ? farz1 : farz0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t sel = 0x7604u | ((uint32_t)i << 4);
-      const float tnx = fmaf(__uint_as_float(__byte_perm(qnx, 0x3F800000u, sel)), ax, bx);
-      const float tny = fmaf(__uint_as_float(__byte_perm(qny, 0x3F800000u, sel)), ay, by);
-      const float tnz = fmaf(__uint_as_float(__byte_perm(qnz, 0x3F800000u, sel)), az, bz);
-      const float tfx = fmaf(__uint_as_float(__byte_perm(qfx, 0x3F800000u, sel)), axf, bxf);
-      const float tfy = fmaf(__uint_as_float(__byte_perm(qfy, 0x3F800000u, sel)), ayf, byf);
-      const float tfz = fmaf(__uint_as_float(__byte_perm(qfz, 0x3F800000u, sel)), azf, bzf);
-      const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
-      const float tf = fminf(fminf(tfx, tfy), fminf(tfz, r.tmax));
-      const uint32_t cb = (childBits >> (8 * i)) & 0xFFu, bi = (bitIndex >> (8 * i)) & 0xFFu;
-      if (tn <= tf) hitmask |= cb << bi;        // empty slots are encoded lo=255 > hi=0 and never pass
-    }
-  }
-  r.ng = make_uint2(n1.x, (hitmask & 0xFF000000u) | (n0.w >> 24));
-  r.tg = make_uint2(n1.y, hitmask & 0x00FFFFFFu);
+  const uint32_t acc = four_children<0>(nearx0, neary0, nearz0, farx0, fary0, farz0, ax, ay, az, bx, by, bz, axf, ayf, azf, bxf, byf, bzf, tmin, r.tmax, k64) |
+                       four_children<1>(nearx1, neary1, nearz1, farx1, fary1, farz1, ax, ay, az, bx, by, bz, axf, ayf, azf, bxf, byf, bzf, tmin, r.tmax, k64);
+  const uint32_t imask = n0.w >> 24;
+  r.ng = make_uint2(n1.x, (octant_permute((acc >> 24) & imask, r.octm) << 24) | imask);
+  return make_uint4(n1.y, acc & n1.z, n1.z, 0u);
 }
 
-// One traversal iteration for this lane.  Returns false when the ray is finished.
+// ------------------------------------------------------------------------------------------------------------
+// k_trace<ANY>: persistent warps, one ray per lane.
+//   ANY = false  closest hit for the probe rays                 (rgen:51-106)   -> hits[ray]
+//   ANY = true   any-hit over the per-light shadow-ray queues   (rchit:48-66)   -> lit[ray] |= 1 << light
+// Work distribution: ray set-up runs 32 lanes wide into a shared-memory batch and idle lanes refill from it every
+// iteration; one atomic on the global cursor per FAST_CHUNK rays.  Triangles found by the box tests are parked in
+// shared memory (two groups per lane) and tested one per lane per iteration in a separate, short section, so lanes
+// that found none keep stepping through nodes instead of idling in a per-lane triangle loop.
+// ------------------------------------------------------------------------------------------------------------
 template <bool ANY, bool CNT>
-__device__ __forceinline__ bool trace_iter(const uint4* __restrict__ nodes, const float4* __restrict__ tris, RayState& r, uint2* stack,
-                                           uint32_t& cntNodes, uint32_t& cntTris) {
-  if (r.ng.y & 0xFF000000u) { node_step(nodes, r, stack); if (CNT) ++cntNodes; }
-  else { r.tg = r.ng; r.ng = make_uint2(0u, 0u); }
-  while (r.tg.y) {
-    const int b = __ffs((int)r.tg.y) - 1;
-    r.tg.y &= r.tg.y - 1u;
-    const float4* tp = tris + 3 * (size_t)(r.tg.x + (uint32_t)b);
-    const float4 a = __ldg(tp), bb = __ldg(tp + 1), cc = __ldg(tp + 2);
-    if (CNT) ++cntTris;
-    float t, u, v;
-    if (tri_intersect(mk3(r.ox, r.oy, r.oz), mk3(r.dx, r.dy, r.dz), mk3(a.x, a.y, a.z), mk3(a.w, bb.x, bb.y), mk3(bb.z, bb.w, cc.x),
-                      r.tmin, ANY ? r.tmax : 3.0e38f, t, u, v)) {
-      const uint32_t prim = __float_as_uint(cc.y);
-      if (ANY) { r.prim = prim; return false; }
-      // closest hit: r.tmax is the best t so far (initially the ray's tMax, exclusive); ties -> lowest triangle id
-      if (t < r.tmax || (t == r.tmax && r.prim != DDGI_MISS && prim < r.prim)) { r.tmax = t; r.hu = u; r.hv = v; r.prim = prim; }
-    }
-  }
-  if ((r.ng.y & 0xFF000000u) == 0u) {
-    if (r.sp == 0) return false;
-    r.ng = stack[--r.sp];
-  }
-  return true;
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// k_trace_primary: persistent warps; lanes that finish pick up the next probe rays (rgen:51-106)
-// ------------------------------------------------------------------------------------------------------------
-template <bool CNT>
-__global__ void __launch_bounds__(128) k_trace_primary(const FastCtx c) {
+__global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
   const TraceCtx& t = c.t;
-  const uint32_t lane = threadIdx.x & 31u;
+  __shared__ float4 sRay[4][32][3];
+  __shared__ float4 sLane[4][LS_FIELDS][32];
+  __shared__ uint32_t sPrefix[34];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, ltMask = (1u << lane) - 1u;
+  uint32_t total = c.totalRays;
+  if (ANY) {
+    if (threadIdx.x == 0) { uint32_t s = 0; for (uint32_t q = 0; q < c.numQueues; ++q) { sPrefix[q] = s; s += c.qcount[FAST_QC(q)]; } sPrefix[c.numQueues] = s; }
+    __syncthreads();
+    total = sPrefix[c.numQueues];
+  }
+  uint32_t* cursor = &c.qcount[ANY ? FAST_QC_SHADOW : FAST_QC_PRIMARY];
   const int P = t.nXZ * t.nXZ;
+  const V3 sunL = normalize3(-t.lightDir);
+  const uint32_t triTrigger = c.tune[0];
+  const uint32_t k64 = c.tune[3];          // 0x64646464, opaque to ptxas on purpose (see planes2)
+  float4* myDir = &sLane[warp][LS_DIR][lane];
+  float4* myRes = &sLane[warp][LS_RES][lane];
+  uint4* myPend = reinterpret_cast<uint4*>(&sLane[warp][LS_PEND_A][lane]);      // slot B = myPend + 32
   uint2 stack[DDGI_STACK];
-  RayState r; r.sp = 0; r.prim = DDGI_MISS; r.ng = make_uint2(0, 0); r.tg = make_uint2(0, 0);
-  bool active = false, exhausted = false;
-  uint32_t myIdx = 0, cn = 0, ct = 0, nRays = 0, nHits = 0;
+  RayState r; r.sp = 0; r.npend = 0; r.ng = make_uint2(0, 0); r.tmax = 0.0f; r.octm = 0;
+  r.ox = r.oy = r.oz = 0.0f; r.idx = r.idy = r.idz = 1.0f;
+  bool active = false, exhausted = (total == 0u);
+  uint32_t chunkNext = 0, chunkEnd = 0, staged = 0, stagedPos = 0;      // warp-uniform
+  uint32_t cn = 0, ct = 0, nRays = 0, nHits = 0;
   for (;;) {
-    const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
-    if (idle && !exhausted) {
-      uint32_t base = 0;
-      if (lane == (uint32_t)(__ffs((int)idle) - 1)) base = atomicAdd(&c.qcount[FAST_QC_PRIMARY], (uint32_t)__popc(idle));
-      base = __shfl_sync(0xFFFFFFFFu, base, __ffs((int)idle) - 1);
-      if (base + (uint32_t)__popc(idle) >= c.totalRays) exhausted = true;
-      if (!active) {
-        myIdx = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
-        if (myIdx < c.totalRays) {
-          const uint32_t slot = myIdx % (uint32_t)t.N, probeLin = myIdx / (uint32_t)t.N;
-          const int layerLocal = (int)(probeLin / (uint32_t)P), probe = (int)(probeLin % (uint32_t)P);
-          const uint32_t ray = t.rayOrder ? (uint32_t)t.rayOrder[slot] : slot;
-          const V3 origin = mk3((float)(probe % t.nXZ), (float)(t.layerBegin + layerLocal), (float)(probe / t.nXZ)) * t.step + t.camOff;
-          const float4 d4 = __ldg(&t.dirs[(size_t)layerLocal * t.N + ray]);
-          ray_begin(r, origin, mk3(d4.x, d4.y, d4.z), t.tmin, t.tmax);
-          active = t.numNodes != 0u;
-          if (!active) c.hits[myIdx] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(DDGI_MISS));
-          if (CNT) ++nRays;
+    // ---------------------------------------------------------------- refill idle lanes from the staged batch
+    uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
+    while (idle && !(exhausted && staged == 0u)) {
+      if (staged == 0u) {
+        if (chunkNext == chunkEnd) {
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(cursor, (uint32_t)FAST_CHUNK);
+          base = __shfl_sync(0xFFFFFFFFu, base, 0);
+          if (base >= total) { exhausted = true; break; }
+          chunkNext = base; chunkEnd = min(base + (uint32_t)FAST_CHUNK, total);
         }
+        const uint32_t n = min(32u, chunkEnd - chunkNext);
+        __syncwarp();
+        if (lane < n) {                                             // ray set-up, one ray per lane
+          const uint32_t w = chunkNext + lane;
+          float4* dst = &sRay[warp][lane][0];
+          if (!ANY) {
+            const uint32_t slot = w % (uint32_t)t.N, probeLin = w / (uint32_t)t.N;
+            const int layerLocal = (int)(probeLin / (uint32_t)P), probe = (int)(probeLin % (uint32_t)P);
+            const uint32_t ray = t.rayOrder ? (uint32_t)t.rayOrder[slot] : slot;
+            const V3 origin = mk3((float)(probe % t.nXZ), (float)(t.layerBegin + layerLocal), (float)(probe / t.nXZ)) * t.step + t.camOff;
+            const float4 d4 = __ldg(&t.dirs[(size_t)layerLocal * t.N + ray]);
+            ray_stage(dst, origin, mk3(d4.x, d4.y, d4.z), t.tmax, w, 0u);
+          } else {
+            uint32_t q = 0; while (q + 1 < c.numQueues && sPrefix[q + 1] <= w) ++q;
+            const uint32_t ray = c.queues[(size_t)q * c.totalRays + (w - sPrefix[q])];
+            const float4 s0 = c.surf[3 * (size_t)ray];
+            const V3 pos = mk3(s0.x, s0.y, s0.z);
+            V3 dir = sunL; float tmax = t.tmax;
+            if (q > 0) {
+              const anerend_light_t* lt = &t.lights[q - 1];
+              const V3 lp = mk3(lt->world_pos[0], lt->world_pos[1], lt->world_pos[2]);
+              const V3 dv = lp - pos; tmax = sqrtf(dot3(dv, dv)); dir = normalize3(lp - pos);
+            }
+            ray_stage(dst, pos, dir, tmax, ray, q);
+          }
+        }
+        __syncwarp();
+        chunkNext += n; staged = n; stagedPos = 0;
+      }
+      const uint32_t take = min((uint32_t)__popc(idle), staged), rank = (uint32_t)__popc(idle & ltMask);
+      if (!active && rank < take) {
+        const float4* src = &sRay[warp][stagedPos + rank][0];
+        const float4 a = src[0], b = src[1], cc = src[2];
+        r.ox = a.x; r.oy = a.y; r.oz = a.z; r.tmax = a.w; r.idx = cc.x; r.idy = cc.y; r.idz = cc.z;
+        // sign of the SAFE inverse (d = -0 -> negative); octinv bit k set = direction POSITIVE on axis k
+        const uint32_t octinv = 7u - ((cc.x < 0.0f ? 1u : 0u) | (cc.y < 0.0f ? 2u : 0u) | (cc.z < 0.0f ? 4u : 0u));
+        r.octm = ((octinv & 1u) ? 0x55u : 0u) | ((octinv & 2u) ? 0x3300u : 0u) | ((octinv & 4u) ? 0x0F0000u : 0u) | (octinv << 24);
+        r.ng = make_uint2(0u, 0x80000000u); r.sp = 0; r.npend = 0;
+        *myDir = b;                                                 // (d.xyz, tag)
+        *myRes = make_float4(0.0f, 0.0f, 0.0f, ANY ? cc.w : __uint_as_float(DDGI_MISS));
+        if (CNT) ++nRays;
+        if (!ANY && t.numNodes == 0u) c.hits[__float_as_uint(b.w)] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(DDGI_MISS));
+        else active = true;
+      }
+      stagedPos += take; staged -= take;
+      idle = __ballot_sync(0xFFFFFFFFu, !active);
+    }
+    if (__ballot_sync(0xFFFFFFFFu, active) == 0u) { if (exhausted && staged == 0u) break; else continue; }
+
+    // ---------------------------------------------------------------- node phase: lanes with a free parking slot
+    bool finished = false;
+    if (active && r.npend < 2u) {
+      if ((r.ng.y & 0xFF000000u) == 0u) {
+        if (r.sp > 0) r.ng = stack[--r.sp];
+        else finished = (r.npend == 0u);
+      }
+      if (r.ng.y & 0xFF000000u) {
+        const uint4 tg = node_step(t.nodes, r, stack, t.tmin, k64);
+        if (CNT) ++cn;
+        if (tg.y) { myPend[32u * r.npend] = tg; ++r.npend; }
       }
     }
-    if (__ballot_sync(0xFFFFFFFFu, active) == 0u) break;
-    // traversal until the warp has drained below the refill threshold
-    for (;;) {
-      if (active) {
-        if (!trace_iter<false, CNT>(t.nodes, t.bvhTris, r, stack, cn, ct)) {
-          active = false;
-          c.hits[myIdx] = make_float4(r.prim == DDGI_MISS ? 0.0f : r.tmax, r.hu, r.hv, __uint_as_float(r.prim));
-          if (CNT && r.prim != DDGI_MISS) ++nHits;
+    // ---------------------------------------------------------------- vote: one triangle round?
+    const uint32_t pend = __ballot_sync(0xFFFFFFFFu, active && r.npend != 0u);
+    bool doTri = pend != 0u;
+    if (doTri && triTrigger > 1u && (uint32_t)__popc(pend) < triTrigger)
+      doTri = __ballot_sync(0xFFFFFFFFu, active && r.npend < 2u && ((r.ng.y & 0xFF000000u) != 0u || r.sp > 0)) == 0u;
+    if (doTri) {
+      if (active && r.npend != 0u) {
+        uint4 g = myPend[0];
+        const int b = __ffs((int)g.y) - 1;
+        const float4* tp = t.bvhTris + 3 * (size_t)(g.x + (uint32_t)__popc(g.z & ((1u << b) - 1u)));
+        const float4 a = __ldg(tp), bb = __ldg(tp + 1), cc = __ldg(tp + 2);
+        const float4 d4 = *myDir;
+        g.y &= g.y - 1u;
+        if (g.y != 0u) myPend[0].y = g.y;
+        else { if (r.npend == 2u) myPend[0] = myPend[32]; --r.npend; }
+        if (CNT) ++ct;
+        float tt, u, v;
+        if (tri_intersect(mk3(r.ox, r.oy, r.oz), mk3(d4.x, d4.y, d4.z), mk3(a.x, a.y, a.z), mk3(a.w, bb.x, bb.y), mk3(bb.z, bb.w, cc.x),
+                          t.tmin, ANY ? r.tmax : 3.0e38f, tt, u, v)) {
+          const uint32_t prim = __float_as_uint(cc.y);
+          if (ANY) { myRes->x = 1.0f; finished = true; }
+          else {
+            // closest hit: r.tmax is the best t so far (initially the ray's tMax, exclusive); ties -> lowest triangle id
+            const uint32_t best = __float_as_uint(myRes->w);
+            if (tt < r.tmax || (tt == r.tmax && best != DDGI_MISS && prim < best)) { r.tmax = tt; *myRes = make_float4(tt, u, v, cc.y); }
+          }
         }
+        if (!finished) finished = r.npend == 0u && (r.ng.y & 0xFF000000u) == 0u && r.sp == 0;
       }
-      const uint32_t act = __ballot_sync(0xFFFFFFFFu, active);
-      if (act == 0u || (!exhausted && __popc(act) < FAST_FETCH_THRESHOLD)) break;
+    }
+    // ---------------------------------------------------------------- results
+    if (active && finished) {
+      active = false;
+      const float4 res = *myRes;
+      const uint32_t tag = __float_as_uint(myDir->w);
+      if (!ANY) {
+        c.hits[tag] = res;                                           // (t, u, v, prim); (0,0,0,MISS) for a miss
+        if (CNT && __float_as_uint(res.w) != DDGI_MISS) ++nHits;
+      } else if (res.x == 0.0f) atomicOr(&c.lit[tag], 1u << __float_as_uint(res.w));      // miss shader: shadow = 0 -> lit
     }
   }
   if (CNT && t.stats) {
     for (int o = 16; o; o >>= 1) { cn += __shfl_xor_sync(0xFFFFFFFFu, cn, o); ct += __shfl_xor_sync(0xFFFFFFFFu, ct, o);
                                    nRays += __shfl_xor_sync(0xFFFFFFFFu, nRays, o); nHits += __shfl_xor_sync(0xFFFFFFFFu, nHits, o); }
-    if (lane == 0) { atomicAdd(&t.stats[0], (unsigned long long)nRays); atomicAdd(&t.stats[1], (unsigned long long)nHits);
-                     atomicAdd(&t.stats[3], (unsigned long long)cn); atomicAdd(&t.stats[4], (unsigned long long)ct); }
+    if (lane == 0) {
+      if (!ANY) { atomicAdd(&t.stats[0], (unsigned long long)nRays); atomicAdd(&t.stats[1], (unsigned long long)nHits);
+                  atomicAdd(&t.stats[3], (unsigned long long)cn); atomicAdd(&t.stats[4], (unsigned long long)ct); }
+      else { atomicAdd(&t.stats[2], (unsigned long long)nRays); atomicAdd(&t.stats[5], (unsigned long long)cn); atomicAdd(&t.stats[6], (unsigned long long)ct); }
+    }
   }
 }
 
@@ -269,66 +384,6 @@ __global__ void __launch_bounds__(PREP_BLOCK) k_shade_prep(const FastCtx c) {
       const uint32_t o = sBase[q] + sCnt[q][warp] + (uint32_t)__popc(m & ((1u << lane) - 1u));
       if (q < nq) c.queues[(size_t)q * c.totalRays + o] = idx; else c.hitq[o] = idx;
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// k_trace_shadow: persistent warps over the concatenated per-light queues, any-hit (rchit:48-66)
-// ------------------------------------------------------------------------------------------------------------
-template <bool CNT>
-__global__ void __launch_bounds__(128) k_trace_shadow(const FastCtx c) {
-  const TraceCtx& t = c.t;
-  __shared__ uint32_t sPrefix[34];
-  if (threadIdx.x == 0) { uint32_t s = 0; for (uint32_t q = 0; q < c.numQueues; ++q) { sPrefix[q] = s; s += c.qcount[FAST_QC(q)]; } sPrefix[c.numQueues] = s; }
-  __syncthreads();
-  const uint32_t total = sPrefix[c.numQueues];
-  const uint32_t lane = threadIdx.x & 31u;
-  uint2 stack[DDGI_STACK];
-  RayState r; r.sp = 0; r.prim = DDGI_MISS; r.ng = make_uint2(0, 0); r.tg = make_uint2(0, 0);
-  bool active = false, exhausted = total == 0u;
-  uint32_t myRay = 0, myBit = 0, cn = 0, ct = 0, nRays = 0;
-  const V3 sunL = normalize3(-t.lightDir);
-  for (;;) {
-    const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
-    if (idle && !exhausted) {
-      uint32_t base = 0;
-      if (lane == (uint32_t)(__ffs((int)idle) - 1)) base = atomicAdd(&c.qcount[FAST_QC_SHADOW], (uint32_t)__popc(idle));
-      base = __shfl_sync(0xFFFFFFFFu, base, __ffs((int)idle) - 1);
-      if (base + (uint32_t)__popc(idle) >= total) exhausted = true;
-      if (!active) {
-        const uint32_t w = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
-        if (w < total) {
-          uint32_t q = 0; while (q + 1 < c.numQueues && sPrefix[q + 1] <= w) ++q;
-          myRay = c.queues[(size_t)q * c.totalRays + (w - sPrefix[q])]; myBit = q;
-          const float4 s0 = c.surf[3 * (size_t)myRay];
-          const V3 pos = mk3(s0.x, s0.y, s0.z);
-          V3 dir = sunL; float tmax = t.tmax;
-          if (q > 0) {
-            const anerend_light_t* lt = &t.lights[q - 1];
-            const V3 lp = mk3(lt->world_pos[0], lt->world_pos[1], lt->world_pos[2]);
-            const V3 dv = lp - pos; tmax = sqrtf(dot3(dv, dv)); dir = normalize3(lp - pos);
-          }
-          ray_begin(r, pos, dir, t.tmin, tmax);
-          active = true;
-          if (CNT) ++nRays;
-        }
-      }
-    }
-    if (__ballot_sync(0xFFFFFFFFu, active) == 0u) break;
-    for (;;) {
-      if (active) {
-        if (!trace_iter<true, CNT>(t.nodes, t.bvhTris, r, stack, cn, ct)) {
-          active = false;
-          if (r.prim == DDGI_MISS) atomicOr(&c.lit[myRay], 1u << myBit);      // miss shader: shadow = 0 -> lit
-        }
-      }
-      const uint32_t act = __ballot_sync(0xFFFFFFFFu, active);
-      if (act == 0u || (!exhausted && __popc(act) < FAST_FETCH_THRESHOLD)) break;
-    }
-  }
-  if (CNT && t.stats) {
-    for (int o = 16; o; o >>= 1) { cn += __shfl_xor_sync(0xFFFFFFFFu, cn, o); ct += __shfl_xor_sync(0xFFFFFFFFu, ct, o); nRays += __shfl_xor_sync(0xFFFFFFFFu, nRays, o); }
-    if (lane == 0) { atomicAdd(&t.stats[2], (unsigned long long)nRays); atomicAdd(&t.stats[5], (unsigned long long)cn); atomicAdd(&t.stats[6], (unsigned long long)ct); }
   }
 }
 

@@ -222,8 +222,11 @@ HD void fit_body(uint32_t leaf, const BuildCtx& c) {
 // ----------------------------------------------------------------------------------------------------
 // BVH8: 80-byte compressed wide node (layout after Ylitie, Karras, Laine 2017)
 //   word0: p.x p.y p.z | ex,ey,ez,imask      p = node box min, e* = biased fp32 exponents of the per-axis grid
-//   word1: childBase, triBase, meta[0..3], meta[4..7]
-//          meta: 0 empty | internal: 0b001'11sss (low 5 bits = 24+slot) | leaf: unary count<<5 | first tri offset
+//   word1: childBase, triBase, triMask, 0
+//          imask bit s: slot s is an internal child, stored at childBase + popc(imask below s)
+//          triMask bits 3s..3s+2: slot s is a leaf with 1..3 triangles (unary); triangle (s,j) is stored at
+//          triBase + popc(triMask below bit 3s+j).  A slot with neither is empty (planes lo=255 > hi=0 never pass).
+//          One compare per child then yields both masks: hit ? (7 << 3s | 1 << 24+s) : 0, AND-ed with triMask / imask.
 //   word2: qlo.x[0..7] qlo.y[0..7]   word3: qlo.z[0..7] qhi.x[0..7]   word4: qhi.y[0..7] qhi.z[0..7]
 // Child boxes are quantised outwards to 8 bits on the node's grid, so they stay conservative.
 // ----------------------------------------------------------------------------------------------------
@@ -235,17 +238,18 @@ HD uint32_t grid_exponent(float ext) {
   if (eb > 253u) eb = 253u;
   return eb;
 }
-HD void encode_node(uint4* out, V3 nlo, V3 nhi, const V3* clo, const V3* chi, const uint8_t* meta, uint32_t imask,
+HD void encode_node(uint4* out, V3 nlo, V3 nhi, const V3* clo, const V3* chi, uint32_t imask, uint32_t triMask,
                     uint32_t childBase, uint32_t triBase) {
   V3 ext = nhi - nlo;
   uint32_t ex = grid_exponent(ext.x), ey = grid_exponent(ext.y), ez = grid_exponent(ext.z);
   float ix = u2f((254u - ex) << 23), iy = u2f((254u - ey) << 23), iz = u2f((254u - ez) << 23);
   uint32_t q[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // lox lo/hi, loy lo/hi, loz lo/hi, hix.., hiy.., hiz..
-  uint32_t m[2] = {0, 0};
   for (int s = 0; s < 8; ++s) {
-    if (!meta[s]) continue;
     uint32_t sh = 8u * (uint32_t)(s & 3); int w = s >> 2;
-    m[w] |= (uint32_t)meta[s] << sh;
+    if (!((imask >> s) & 1u) && !((triMask >> (3 * s)) & 7u)) {       // empty slot: lo = 255 > hi = 0
+      q[0 + w] |= 255u << sh; q[2 + w] |= 255u << sh; q[4 + w] |= 255u << sh;
+      continue;
+    }
     uint32_t lx = (uint32_t)clampf(floorf((clo[s].x - nlo.x) * ix - 0.02f), 0.0f, 255.0f);   // 0.02 grid steps of slack:
     uint32_t ly = (uint32_t)clampf(floorf((clo[s].y - nlo.y) * iy - 0.02f), 0.0f, 255.0f);   // the PRMT-based decode of the
     uint32_t lz = (uint32_t)clampf(floorf((clo[s].z - nlo.z) * iz - 0.02f), 0.0f, 255.0f);   // fast kernels is exact to ~1/512 step
@@ -256,7 +260,7 @@ HD void encode_node(uint4* out, V3 nlo, V3 nhi, const V3* clo, const V3* chi, co
     q[6 + w] |= hx << sh; q[8 + w] |= hy << sh; q[10 + w] |= hz << sh;
   }
   out[0] = make_uint4(f2u(nlo.x), f2u(nlo.y), f2u(nlo.z), ex | (ey << 8) | (ez << 16) | (imask << 24));
-  out[1] = make_uint4(childBase, triBase, m[0], m[1]);
+  out[1] = make_uint4(childBase, triBase, triMask, 0u);
   out[2] = make_uint4(q[0], q[1], q[2], q[3]);
   out[3] = make_uint4(q[4], q[5], q[6], q[7]);
   out[4] = make_uint4(q[8], q[9], q[10], q[11]);
@@ -309,22 +313,21 @@ HD void collapse_body(uint32_t i, const BuildCtx& c) {
     if (isInternal(ch[k]) && count(ch[k]) >= 4u) { imask |= 1u << s; ++nInternal; } else nLeafTris += count(ch[k]); }
   uint32_t childBase = nInternal ? atomAdd(&c.counters[0], nInternal) : 0u;
   uint32_t triBase = nLeafTris ? atomAdd(&c.counters[1], nLeafTris) : 0u;
-  V3 clo[8], chi[8]; uint8_t meta[8];
-  uint32_t rank = 0, toff = 0;
+  V3 clo[8], chi[8];
+  uint32_t rank = 0, toff = 0, triMask = 0;
   for (int s = 0; s < 8; ++s) {
-    int k = childAt[s]; meta[s] = 0;
+    int k = childAt[s];
     if (k < 0) continue;
     uint32_t r = ch[k];
     clo[s] = f4v(c.blo[r]); chi[s] = f4v(c.bhi[r]);
     if (imask & (1u << s)) {
-      meta[s] = (uint8_t)(0x20u | (24u + (uint32_t)s));
       uint32_t child = childBase + rank++;
       c.nodeParent[child] = it.node;
       uint32_t qi = atomAdd(&c.counters[2], 1u);
       CItem o; o.ref = r; o.node = child; c.qout[qi] = o;
     } else {
       uint32_t cnt = count(r), first = isInternal(r) ? c.rangeFirst[r] : r - (n - 1);
-      meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | toff);
+      triMask |= ((1u << cnt) - 1u) << (3 * s);
       for (uint32_t j = 0; j < cnt; ++j) {
         uint32_t gid = c.sortedIds[first + j]; size_t slot = (size_t)triBase + toff + j;
         c.bvhTris[3 * slot + 0] = c.wtri[3 * (size_t)gid + 0];
@@ -334,7 +337,7 @@ HD void collapse_body(uint32_t i, const BuildCtx& c) {
       toff += cnt;
     }
   }
-  encode_node(c.nodes + 5 * (size_t)it.node, nlo, nhi, clo, chi, meta, imask, childBase, triBase);
+  encode_node(c.nodes + 5 * (size_t)it.node, nlo, nhi, clo, chi, imask, triMask, childBase, triBase);
   c.nodeLo[it.node] = make_float4(nlo.x, nlo.y, nlo.z, 0.0f);
   c.nodeHi[it.node] = make_float4(nhi.x, nhi.y, nhi.z, 0.0f);
   c.nodePending[it.node] = nInternal;
@@ -361,12 +364,12 @@ HD void refit_node_body(uint32_t node0, const BuildCtx& c) {
 #else
     uint4 w0 = nd[0], w1 = nd[1];
 #endif
-    uint32_t imask = w0.w >> 24, childBase = w1.x, triBase = w1.y;
-    V3 clo[8], chi[8]; uint8_t meta[8];
+    uint32_t imask = w0.w >> 24, childBase = w1.x, triBase = w1.y, triMask = w1.z;
+    V3 clo[8], chi[8];
     V3 nlo = mk3(3.0e38f), nhi = mk3(-3.0e38f);
     for (int s = 0; s < 8; ++s) {
-      uint32_t mt = ((s < 4 ? w1.z : w1.w) >> (8 * (s & 3))) & 0xFFu; meta[s] = (uint8_t)mt;
-      if (!mt) continue;
+      const uint32_t leafBits = (triMask >> (3 * s)) & 7u;
+      if (!leafBits && !(imask & (1u << s))) continue;
       if (imask & (1u << s)) {
         uint32_t child = childBase + (uint32_t)popc32(imask & ((1u << s) - 1u));
 #ifdef __CUDA_ARCH__
@@ -375,7 +378,7 @@ HD void refit_node_body(uint32_t node0, const BuildCtx& c) {
         clo[s] = f4v(c.nodeLo[child]); chi[s] = f4v(c.nodeHi[child]);
 #endif
       } else {
-        uint32_t off = mt & 0x1Fu, cnt = (uint32_t)popc32(mt >> 5);
+        uint32_t off = (uint32_t)popc32(triMask & ((1u << (3 * s)) - 1u)), cnt = (uint32_t)popc32(leafBits);
         V3 lo = mk3(3.0e38f), hi = mk3(-3.0e38f);
         for (uint32_t j = 0; j < cnt; ++j) {
           uint32_t gid = f2u(c.bvhTris[3 * ((size_t)triBase + off + j) + 2].y);
@@ -385,7 +388,7 @@ HD void refit_node_body(uint32_t node0, const BuildCtx& c) {
       }
       nlo = min3(nlo, clo[s]); nhi = max3(nhi, chi[s]);
     }
-    encode_node(nd, nlo, nhi, clo, chi, meta, imask, childBase, triBase);
+    encode_node(nd, nlo, nhi, clo, chi, imask, triMask, childBase, triBase);
     c.nodeLo[node] = make_float4(nlo.x, nlo.y, nlo.z, 0.0f);
     c.nodeHi[node] = make_float4(nhi.x, nhi.y, nhi.z, 0.0f);
     if (node == 0u) return;
@@ -433,9 +436,10 @@ HD bool traverse(const uint4* __restrict__ nodes, const float4* __restrict__ tri
   const uint32_t octinv = 7u - ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
   uint2 stack[DDGI_STACK]; int sp = 0;
   uint2 ng = make_uint2(0u, 0x80000000u);
+  uint32_t tgAll = 0u;
   for (;;) {
     uint2 tg = make_uint2(0u, 0u);
-    if (ng.y & 0xFF000000u) {
+    {                                            // ng always holds at least one unvisited child here
       const int bit = msb32(ng.y);
       ng.y &= ~(1u << bit);
       if (ng.y & 0xFF000000u) { if (sp < DDGI_STACK) stack[sp++] = ng; }
@@ -448,10 +452,11 @@ HD bool traverse(const uint4* __restrict__ nodes, const float4* __restrict__ tri
       const float orgx = (u2f(n0.x) - o.x) * idx, orgy = (u2f(n0.y) - o.y) * idy, orgz = (u2f(n0.z) - o.z) * idz;
       const float tcur = hit.t;
       uint32_t hitmask = 0;
+      const uint32_t imask = n0.w >> 24, triMask = n1.z;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const uint32_t meta = byte_of(n1.z, n1.w, i);
-        if (!meta) continue;
+        const uint32_t leafBits = (triMask >> (3 * i)) & 7u;
+        if (!leafBits && !((imask >> i) & 1u)) continue;
         const float tlx = fmaf((float)byte_of(n2.x, n2.y, i), adjx, orgx), thx = fmaf((float)byte_of(n3.z, n3.w, i), adjx, orgx);
         const float tly = fmaf((float)byte_of(n2.z, n2.w, i), adjy, orgy), thy = fmaf((float)byte_of(n4.x, n4.y, i), adjy, orgy);
         const float tlz = fmaf((float)byte_of(n3.x, n3.y, i), adjz, orgz), thz = fmaf((float)byte_of(n4.z, n4.w, i), adjz, orgz);
@@ -459,17 +464,18 @@ HD bool traverse(const uint4* __restrict__ nodes, const float4* __restrict__ tri
         const float tfb = fminf(fminf(fmaxf(tlx, thx), fmaxf(tly, thy)), fmaxf(tlz, thz)) * 1.0000004f;
         const float tf = fminf(tfb, tcur);
         if (tn <= tf) {
-          if ((meta & 0x1Fu) >= 24u) hitmask |= 1u << (24u + ((meta & 7u) ^ octinv));
-          else hitmask |= (meta >> 5) << (meta & 0x1Fu);
+          if ((imask >> i) & 1u) hitmask |= 1u << (24u + ((uint32_t)i ^ octinv));
+          else hitmask |= leafBits << (3 * i);
         }
       }
       ng = make_uint2(n1.x, (hitmask & 0xFF000000u) | (n0.w >> 24));
       tg = make_uint2(n1.y, hitmask & 0x00FFFFFFu);
-    } else { tg = ng; ng = make_uint2(0u, 0u); }
+      tgAll = triMask;
+    }
     while (tg.y) {
       const int b = msb32(tg.y & (0u - tg.y));   // lowest set bit
       tg.y &= tg.y - 1u;
-      const float4* tp = tris + 3 * (size_t)(tg.x + (uint32_t)b);
+      const float4* tp = tris + 3 * (size_t)(tg.x + (uint32_t)popc32(tgAll & ((1u << b) - 1u)));
       const float4 a = tp[0], bb = tp[1], cc = tp[2];
       if (CNT) ++cntTris;
       float t, u, v;

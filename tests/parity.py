@@ -81,8 +81,7 @@ def decode_bvh8(nodes_u8, tris_u8):
     p = w[:, 0:3].copy().view(np.float32)
     e = np.stack([w[:, 3] & 0xFF, (w[:, 3] >> 8) & 0xFF, (w[:, 3] >> 16) & 0xFF], 1)
     imask = (w[:, 3] >> 24) & 0xFF
-    child_base, tri_base = w[:, 4], w[:, 5]
-    meta = nodes[:, 24:32]
+    child_base, tri_base, tri_mask = w[:, 4], w[:, 5], w[:, 6]
     q = nodes[:, 32:80].reshape(-1, 6, 8)        # lox, loy, loz, hix, hiy, hiz
     scale = (e.astype(np.uint32) << 23).view(np.float32)
     lo = p[:, None, :] + q[:, 0:3, :].transpose(0, 2, 1).astype(np.float32) * scale[:, None, :]
@@ -92,7 +91,7 @@ def decode_bvh8(nodes_u8, tris_u8):
     e1 = t[:, 3:6]
     e2 = t[:, 6:9]
     gid = t[:, 9].copy().view(np.uint32)
-    return dict(p=p, e=e, imask=imask, child_base=child_base, tri_base=tri_base, meta=meta, lo=lo, hi=hi,
+    return dict(p=p, e=e, imask=imask, child_base=child_base, tri_base=tri_base, tri_mask=tri_mask, lo=lo, hi=hi,
                 v0=v0, v1=v0 + e1, v2=v0 + e2, gid=gid)
 
 
@@ -108,13 +107,17 @@ def validate_bvh8(nodes_u8, tris_u8, num_tris):
     true_hi = np.full((nn, 3), -np.inf)
     for n in range(nn - 1, -1, -1):         # children are always allocated after their parent
         rank = 0
+        tm = int(b["tri_mask"][n])
+        assert tm < (1 << 24) and int(nodes_u8.reshape(-1, 80).view(np.uint32)[n, 7]) == 0
         for s in range(8):
-            m = int(b["meta"][n, s])
-            if m == 0:
-                continue
+            leaf_bits = (tm >> (3 * s)) & 7
+            inner = (int(b["imask"][n]) >> s) & 1
             lo, hi = b["lo"][n, s], b["hi"][n, s]
-            if (b["imask"][n] >> s) & 1:
-                assert (m & 0x1F) == 24 + s and (m >> 5) == 1
+            if not leaf_bits and not inner:
+                assert np.any(lo > hi), "empty slot must never pass the box test"
+                continue
+            assert not (leaf_bits and inner) and leaf_bits in (0, 1, 3, 7)
+            if inner:
                 c = int(b["child_base"][n]) + rank
                 rank += 1
                 assert c > n and not seen_nodes[c], "node referenced twice / not after its parent"
@@ -123,8 +126,8 @@ def validate_bvh8(nodes_u8, tris_u8, num_tris):
                 true_lo[n] = np.minimum(true_lo[n], true_lo[c])
                 true_hi[n] = np.maximum(true_hi[n], true_hi[c])
             else:
-                cnt = bin(m >> 5).count("1")
-                off = m & 0x1F
+                cnt = bin(leaf_bits).count("1")
+                off = bin(tm & ((1 << (3 * s)) - 1)).count("1")
                 assert 1 <= cnt <= 3
                 for j in range(cnt):
                     ti = int(b["tri_base"][n]) + off + j
