@@ -349,6 +349,7 @@ __global__ void __launch_bounds__(PREP_BLOCK) k_shade_prep(const FastCtx c) {
   // Which queues does this ray enter?  bit q: shadow ray towards light q (0 = sun, rchit:45-66: every hit; point
   // lights, extension E1: only where the light can contribute); bit 32: the compacted hit list k_shade runs over.
   uint32_t needMask = isHit ? 1u : 0u;
+  if (isHit && (t.flags & ANEREND_DDGI_FLAG_SKIP_DEAD_SHADOW_RAYS) && !(dot3(normal, normalize3(-t.lightDir)) > 0.0f)) needMask = 0u;
   if (isHit && (t.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS)) {
     for (uint32_t li = 0; li < t.numLights; ++li) {
       const anerend_light_t* lt = &t.lights[li];

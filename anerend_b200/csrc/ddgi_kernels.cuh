@@ -680,8 +680,11 @@ HD void trace_ray_body(uint32_t idx, const TraceCtx& c) {
     // sun shadow ray (rchit:45-66): any-hit, origin = hit position without offset
     const V3 sunL = normalize3(-c.lightDir);
     Hit sh;
-    ++nShadow;
-    const bool occluded = traverse<true, CNT>(c.nodes, c.bvhTris, c.numNodes, pos, sunL, c.tmin, c.tmax, sh, cn[1], ct[1]);
+    bool occluded = true;
+    if (!(c.flags & ANEREND_DDGI_FLAG_SKIP_DEAD_SHADOW_RAYS) || dot3(normal, sunL) > 0.0f) {
+      ++nShadow;
+      occluded = traverse<true, CNT>(c.nodes, c.bvhTris, c.numNodes, pos, sunL, c.tmin, c.tmax, sh, cn[1], ct[1]);
+    }
     V3 irradiance = mk3(0.0f);
     if (!occluded) { lit |= 1u; irradiance = calc_light(normal, albedo, metallic, roughness, pos, origin, sunL, c.sunIntensity * mk3(1.0f) * 1.0f); }
     if (c.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) {

@@ -44,8 +44,10 @@ __global__ void __launch_bounds__(128) k_shade(const FastCtx c) {
     V3 irradiance = mk3(0.0f);
     if (lit & 1u) irradiance = calc_light(normal, albedo, metallic, roughness, pos, origin, sunL, t.sunIntensity * mk3(1.0f) * 1.0f);
     if (t.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) {
-      for (uint32_t li = 0; li < t.numLights; ++li) {
-        if (!(lit & (1u << (1u + li)))) continue;
+      // every lane walks ITS OWN unoccluded lights in index order (the oracle's accumulation order); looping over all
+      // lights with a per-lane skip kept a third of the lanes busy
+      for (uint32_t m = lit >> 1; m != 0u; m &= m - 1u) {
+        const uint32_t li = (uint32_t)__ffs((int)m) - 1u;
         const anerend_light_t* lt = &t.lights[li];
         const V3 lp = mk3(lt->world_pos[0], lt->world_pos[1], lt->world_pos[2]);
         const V3 dv = lp - pos; const float dist = sqrtf(dot3(dv, dv)), range = lt->world_pos[3];

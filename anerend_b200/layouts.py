@@ -45,5 +45,6 @@ FLAG_TEXEL_RECORDS = 1 << 2
 FLAG_COUNTERS = 1 << 3
 FLAG_SIMPLE_KERNELS = 1 << 4
 FLAG_FAST_MATH = 1 << 5
+FLAG_SKIP_DEAD_SHADOW_RAYS = 1 << 6
 
 MISS = 0xFFFFFFFF

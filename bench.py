@@ -42,7 +42,7 @@ def workload_desc(name, scene, grid, world):
     nxz, ny, nr = grid
     return {"workload": name, "scene": scene.name, "triangles": int(scene.num_triangles),
             "probes": f"{nxz}x{ny}x{nxz}", "rays_per_probe": nr, "primary_rays_per_update": nxz * nxz * ny * nr,
-            "lights": int(len(scene.lights)), "point_lights_E1": True, "multi_bounce": True,
+            "lights": int(len(scene.lights)), "point_lights_E1": True, "multi_bounce": True, "dead_shadow_rays_skipped": True,
             "mode": "jacobi full-grid update", "parallelism": f"y-slab x{world}" if world > 1 else "single GPU"}
 
 
@@ -156,7 +156,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=[None, "c2", "c3", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fused-gather", action="store_true", help="convolution stores texels into peers' atlases (no NCCL call)")
+    ap.add_argument("--fast-math", action="store_true", help="time the FAST_MATH build as the headline (default: exact build)")
+    ap.add_argument("--no-alt", action="store_true", help="skip the second-build and 1-GPU strong-scaling-base measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -180,72 +181,85 @@ def main():
     scene, grid, seed = build_workload(name)
     nxz, ny, nr = grid
     slab = sharding.slab_for_rank(ny, rank, world)
-    flags = L.FLAG_POINT_LIGHTS
-    h = A.Ddgi(A.make_params(nxz, ny, nr, flags=flags, slab=slab, device=local_rank))
-    h.upload_scene(scene)
-    h.set_scene_ubo(scene.ubo)
-    h.build_accel()
+    # point lights (extension E1) + dead-shadow-ray elimination (radiance bit-identical, tests/test_oracle_kat.py);
+    # the default kernels are the exact build (atlas bit-identical to the oracle); FAST_MATH is timed as a second figure
+    flags = L.FLAG_POINT_LIGHTS | L.FLAG_SKIP_DEAD_SHADOW_RAYS
+    if args.fast_math:
+        flags |= L.FLAG_FAST_MATH
+    dev = torch.device("cuda", local_rank)
+    total_steps = args.warmup + args.steps
+    seq = scenes.rotation_sequence(seed, ny * total_steps)
+    all_rays = nxz * nxz * ny * nr
+
+    def make_handle(hflags, hslab):
+        hh = A.Ddgi(A.make_params(nxz, ny, nr, flags=hflags, slab=hslab, device=local_rank))
+        hh.upload_scene(scene)
+        hh.set_scene_ubo(scene.ubo)
+        hh.build_accel()
+        return hh
+
+    h = make_handle(flags, slab)
     accel_ms = h.timings()["accel_ms"]
     info = h.bvh_info()
-    stream = torch.cuda.ExternalStream(h.stream(), device=torch.device("cuda", local_rank))
-    ptr, nbytes = h.atlas_device_ptr()
-    atlas_t = torch.as_tensor(sharding.DeviceArray(ptr, (h.atlas_height, h.atlas_width, 4)), device=f"cuda:{local_rank}")
-    row_b, row_e = sharding.slab_rows(nxz, slab)
+    rots = h.rotations(seq).reshape(total_steps, ny, 16)
+    my_rays = nxz * nxz * (slab[1] - slab[0]) * nr
+    nbytes = h.atlas_device_ptr()[1]
     host_atlas = torch.empty((h.atlas_height, h.atlas_width, 4), dtype=torch.int16, pin_memory=True)   # pinned result buffer
     host_np = host_atlas.numpy().view(np.uint16)
 
-    total_steps = args.warmup + args.steps
-    seq = scenes.rotation_sequence(seed, ny * total_steps)
-    rots = h.rotations(seq).reshape(total_steps, ny, 16)
-    my_rays = nxz * nxz * (slab[1] - slab[0]) * nr
-    all_rays = nxz * nxz * ny * nr
-
     # working set vs L2 (126 MB): flush between timed iterations when everything would stay cached
-    working_set = info.num_nodes * 80 + info.num_triangles * 48 + scene.vertices.nbytes + scene.indices.nbytes + nbytes + my_rays * 8
+    working_set = info.num_nodes * 80 + info.num_triangles * (48 + 80) + nbytes + my_rays * (8 + 16 + 48 + 4)
     flush = working_set < 256e6
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}") if flush else None
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush else None
 
-    def gather():
-        if world > 1 and not args.fused_gather:
-            with torch.cuda.stream(stream):
-                sharding.all_gather_atlas(atlas_t, nxz, ny, rank, world)
+    def timed(hh, steps, warmup, do_gather, multi):
+        """`steps` full-grid updates of handle hh, CUDA events on the handle's stream; returns device ms and per-pass ms."""
+        stream = torch.cuda.ExternalStream(hh.stream(), device=dev)
+        ptr, _ = hh.atlas_device_ptr()
+        atlas_t = torch.as_tensor(sharding.DeviceArray(ptr, (hh.atlas_height, hh.atlas_width, 4)), device=dev)
 
-    def step(k):
-        h.set_scene_ubo(scene.ubo)
-        h.translate()
-        h.update(-1, rots[k])
-        gather()
+        def step(k):
+            hh.set_scene_ubo(scene.ubo)
+            hh.translate()
+            hh.update(-1, rots[k])
+            if do_gather:
+                with torch.cuda.stream(stream):
+                    sharding.all_gather_atlas(atlas_t, nxz, ny, rank, world)
 
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for k in range(args.warmup):
-        step(k)
-    h.sync()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for k in range(warmup):
+            step(k)
+        hh.sync()
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+        rt, cv, nl = [], [], 0
+        for k in range(steps):
+            if flush:
+                with torch.cuda.stream(stream):
+                    flush_buf.fill_(k & 0xFF)
+            ev[k][0].record(stream)
+            step(warmup + k)
+            ev[k][1].record(stream)
+            t = hh.timings()                     # synchronises the handle's stream
+            rt.append(t["rt_ms"])
+            cv.append(t["convolve_ms"])
+            nl += t["kernel_launches"] + (1 if do_gather else 0)
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        if multi:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms, rt, cv, nl, step
+
+    do_gather = world > 1
     sampler = ClockSampler(local_rank)
     sampler.start()
-    rt_ms, conv_ms, launches = [], [], 0
-    for k in range(args.steps):
-        if flush:
-            with torch.cuda.stream(stream):
-                flush_buf.fill_(k & 0xFF)
-        ev[k][0].record(stream)
-        step(args.warmup + k)
-        ev[k][1].record(stream)
-        t = h.timings()                      # synchronises the handle's stream
-        rt_ms.append(t["rt_ms"])
-        conv_ms.append(t["convolve_ms"])
-        launches += t["kernel_launches"] + (1 if world > 1 and not args.fused_gather else 0)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    dev_ms, rt_ms, conv_ms, launches, step = timed(h, args.steps, args.warmup, do_gather, world > 1)
     clocks = sampler.stop()
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    if world > 1:
-        tt = torch.tensor([dev_ms], device=f"cuda:{local_rank}")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dev_ms = float(tt.item())
     ms_per_step = dev_ms / args.steps
     value = all_rays / (ms_per_step * 1e-3) / 1e6
 
@@ -268,13 +282,32 @@ def main():
     h2d_bytes = (slab[1] - slab[0]) * nr * 16 + 568 + 64 * ny
     d2h_bytes = nbytes
 
+    # ---- second figure: the other arithmetic build (FAST_MATH <-> exact), same workload, fewer steps ----------
+    alt = None
+    if not args.no_alt:
+        ha = make_handle(flags ^ L.FLAG_FAST_MATH, slab)
+        asteps = max(3, min(args.steps, 20))
+        ams, art, acv, _, _ = timed(ha, asteps, 3, do_gather, world > 1)
+        alt = {"build": "exact" if args.fast_math else "fast_math", "ms_per_step": ams / asteps,
+               "value": all_rays / (ams / asteps * 1e-3) / 1e6, "unit": UNIT, "trace_ms": float(np.mean(art)),
+               "convolve_ms": float(np.mean(acv)), "steps": asteps}
+        ha.close()
+
+    # ---- strong-scaling base: the SAME workload on one GPU (rank 0 alone), so the N-GPU figure has its own denominator
+    base1 = None
+    if world > 1 and not args.no_alt:
+        if rank == 0:
+            hb = make_handle(flags, (0, ny))
+            bsteps = 3
+            bms, _, _, _, _ = timed(hb, bsteps, 1, False, False)
+            base1 = {"n_gpus": 1, "ms_per_step": bms / bsteps, "value": all_rays / (bms / bsteps * 1e-3) / 1e6, "unit": UNIT, "steps": bsteps}
+            hb.close()
+        dist.barrier()
+
     line = None
     if rank == 0:
         # ---- roofline of the dominant kernel (k_probe_trace): counted, untimed run of the same update ----------
-        hc = A.Ddgi(A.make_params(nxz, ny, nr, flags=flags | L.FLAG_COUNTERS, slab=slab, device=local_rank))
-        hc.upload_scene(scene)
-        hc.set_scene_ubo(scene.ubo)
-        hc.build_accel()
+        hc = make_handle(flags | L.FLAG_COUNTERS, slab)
         hc.update(-1, rots[args.warmup])
         stats = hc.stats()
         hc.close()
@@ -304,14 +337,16 @@ def main():
         cfg = workload_desc(name, scene, grid, world)
         cfg.update({"l2": "flushed between timed iterations (256 MiB write)" if flush else "working set larger than L2, no flush",
                     "bvh8_nodes": int(info.num_nodes), "accel_build_ms": accel_ms,
-                    "atlas_exchange": ("fused peer stores" if args.fused_gather else "nccl all_gather") if world > 1 else "none"})
+                    "atlas_exchange": "nccl all_gather (in place, on the handle's stream)" if world > 1 else "none"})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "update_ms": {"trace": rt_avg, "convolve": float(np.mean(conv_ms)), "full_grid": ms_per_step}}
+                "update_ms": {"trace": rt_avg, "convolve": float(np.mean(conv_ms)), "full_grid": ms_per_step},
+                "arithmetic": "fast_math (1e-4 relative per update)" if args.fast_math else "exact (atlas bit-identical to the oracle)",
+                "other_build": alt, "strong_scaling_base": base1}
     h.close()
     if world > 1:
         dist.barrier()

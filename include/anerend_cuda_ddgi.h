@@ -40,6 +40,9 @@ extern "C" {
 #define ANEREND_DDGI_FLAG_TEXEL_RECORDS (1u << 2) /* keep the fp32 pre-quantisation value of every convolved texel (parity tests)  */
 #define ANEREND_DDGI_FLAG_COUNTERS      (1u << 3) /* count BVH nodes visited / triangles tested (roofline bytes); slower kernels    */
 #define ANEREND_DDGI_FLAG_SIMPLE_KERNELS (1u << 4) /* one-thread-per-ray reference kernel instead of the wavefront kernels (debug)    */
+#define ANEREND_DDGI_FLAG_SKIP_DEAD_SHADOW_RAYS (1u << 6) /* do not trace the sun shadow ray (rchit:45-66) where dot(N, L) <= 0:
+                                                     calcLight multiplies by max(N.L, 0) = 0 there (pbr_light.glsl:161), so the
+                                                     radiance is unchanged; lit_mask bit 0 reads 0 and shadow_rays counts traced rays */
 #define ANEREND_DDGI_FLAG_FAST_MATH     (1u << 5) /* radiance + convolution with contracted / approximate fp32 (<= 1e-4 relative per
                                                      update instead of bit-identical to the oracle's defined arithmetic); hit ids,
                                                      shadow-ray results and hit positions are unaffected                            */

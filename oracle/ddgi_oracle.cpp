@@ -618,14 +618,20 @@ struct ddgi_oracle {
     // shadow ray to the sun (rchit:45-66): any-hit semantics, same miss shader -> shadow = 0
     V3 lightDir = v3(ubo.light_dir[0], ubo.light_dir[1], ubo.light_dir[2]);
     V3 shadowDir = normalize(-lightDir);
-    cnt[2]++;
-    bool occluded = anyHit(pos, shadowDir, p.t_min, p.t_max, cnt[5], cnt[6]);
     // (uv is interpolated at rchit:70 but only feeds texture taps, which are out of scope)
     V3 normal = normalize(P(vv[0]->normal) * b0 + P(vv[1]->normal) * b1 + P(vv[2]->normal) * b2);
     // normal * gl_WorldToObjectEXT : row-vector times matrix = dot with each column of W2O's 3x3
     normal = normalize(v3(normal.x * in.w2o[0] + normal.y * in.w2o[1] + normal.z * in.w2o[2],
                           normal.x * in.w2o[3] + normal.y * in.w2o[4] + normal.z * in.w2o[5],
                           normal.x * in.w2o[6] + normal.y * in.w2o[7] + normal.z * in.w2o[8]));
+    // The reference traces the sun shadow ray before it knows the normal (rchit:45-66 precede :72-73); its result only
+    // gates calcLight, which multiplies by max(N.L, 0) (pbr_light.glsl:161).  FLAG_SKIP_DEAD_SHADOW_RAYS drops the rays
+    // whose result cannot matter; the radiance is the same (tests/test_oracle_kat.py proves it on the oracle itself).
+    bool occluded = true;
+    if (!(p.flags & ANEREND_DDGI_FLAG_SKIP_DEAD_SHADOW_RAYS) || dot(normal, shadowDir) > 0.0f) {
+      cnt[2]++;
+      occluded = anyHit(pos, shadowDir, p.t_min, p.t_max, cnt[5], cnt[6]);
+    }
     V3 color = P(vv[0]->color) * b0 + P(vv[1]->color) * b1 + P(vv[2]->color) * b2;
     color = toLinear(color);
     // getSurfaceDataFromMat, bindless.glsl:181-237, texture-free branches

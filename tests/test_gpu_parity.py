@@ -41,7 +41,9 @@ def _check_update(o, g, ny, mismatch_frac=0.0):
     return total_mism
 
 
-KERNEL_FLAGS = {"wavefront": 0, "wavefront_fast": L.FLAG_FAST_MATH, "simple": L.FLAG_SIMPLE_KERNELS}
+KERNEL_FLAGS = {"wavefront": 0, "wavefront_fast": L.FLAG_FAST_MATH, "simple": L.FLAG_SIMPLE_KERNELS,
+                "wavefront_skip_dead": L.FLAG_SKIP_DEAD_SHADOW_RAYS,
+                "simple_skip_dead": L.FLAG_SIMPLE_KERNELS | L.FLAG_SKIP_DEAD_SHADOW_RAYS}
 
 
 @pytest.mark.parametrize("kernels", sorted(KERNEL_FLAGS))

@@ -20,10 +20,11 @@ SCENES = {
 }
 
 
+@pytest.mark.parametrize("extra", [0, L.FLAG_SKIP_DEAD_SHADOW_RAYS], ids=["faithful", "skip_dead_shadow_rays"])
 @pytest.mark.parametrize("name", sorted(SCENES))
-def test_full_update_matches_oracle(name, oracle, make_emu):
+def test_full_update_matches_oracle(name, extra, oracle, make_emu):
     scene, (nxz, ny, nr) = SCENES[name]()
-    p = make_params(nxz, ny, nr, flags=ALL)
+    p = make_params(nxz, ny, nr, flags=ALL | extra)
     o, e = oracle.Oracle(p), make_emu(p)
     rots = parity.setup_pair(scene, (o, e), seed=3)
     assert o.bvh_info().num_triangles == e.bvh_info().num_triangles == scene.num_triangles

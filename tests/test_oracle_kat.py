@@ -309,3 +309,31 @@ def test_white_furnace_energy(oracle):
         assert m > prev
         prev = m
     o.close()
+
+
+def test_skipping_dead_shadow_rays_changes_nothing_but_the_ray_count(oracle):
+    """FLAG_SKIP_DEAD_SHADOW_RAYS: the sun shadow ray of rchit:45-66 is not traced where dot(N, L) <= 0.  calcLight
+    multiplies by max(N.L, 0) = 0 there (pbr_light.glsl:161), so radiance and atlas must be bit-identical to the
+    faithful path; only lit_mask bit 0 (forced to 0) and the number of rays traced differ."""
+    for seed in (11, 14):
+        s = scenes.random_soup(seed, ntris=1500)
+        base = L.FLAG_RAY_RECORDS | L.FLAG_POINT_LIGHTS | L.FLAG_COUNTERS
+        a, b = oracle.Oracle(make_params(3, 2, 64, flags=base)), oracle.Oracle(make_params(3, 2, 64, flags=base | L.FLAG_SKIP_DEAD_SHADOW_RAYS))
+        for h in (a, b):
+            h.upload_scene(s)
+            h.set_scene_ubo(s.ubo)
+            h.build_accel()
+        rots = a.rotations(scenes.rotation_sequence(seed, 2))
+        for _ in range(3):
+            for h in (a, b):
+                h.update(-1, rots)
+        for layer in range(2):
+            ra, rb = a.download_ray_records(layer), b.download_ray_records(layer)
+            assert np.array_equal(ra["prim"], rb["prim"]) and np.array_equal(ra["radiance"], rb["radiance"])
+            assert np.array_equal(ra["lit_mask"] >> 1, rb["lit_mask"] >> 1)
+            assert np.all((rb["lit_mask"] & 1) <= (ra["lit_mask"] & 1))
+        assert np.array_equal(a.download_atlas(), b.download_atlas())
+        sa, sb = a.stats(), b.stats()
+        assert sb["shadow_rays"] < sa["shadow_rays"] and sa["primary_hits"] == sb["primary_hits"]
+        a.close()
+        b.close()
