@@ -166,6 +166,14 @@ class DdgiHandle:
             raise ValueError(f"update(layer={layer}) needs {need} floats of rotation, got {rots.size}")
         self._call("update", C.c_int32(layer), _ptr(rots))
 
+    def update_layers(self, layers, rots):
+        """Jacobi update of an arbitrary layer subset; rots = n_y matrices indexed by absolute layer."""
+        layers = _c(layers, np.int32).reshape(-1)
+        rots = _c(rots, np.float32).reshape(-1)
+        if rots.size != 16 * self.n_y:
+            raise ValueError(f"update_layers needs {16 * self.n_y} floats of rotation, got {rots.size}")
+        self._call("update_layers", _ptr(layers), C.c_uint32(layers.size), _ptr(rots))
+
     def frame(self, rot):
         rot = _c(rot, np.float32).reshape(16)
         layer = C.c_int32(-1)

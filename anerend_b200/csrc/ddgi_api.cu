@@ -67,6 +67,8 @@ struct anerend_ddgi {
   uint2* dAtlas = nullptr; uint2* dTemp = nullptr;        // ProbeRaysConvTex, TempProbeTex
   uint2* dRayIrr = nullptr;                                // ProbeRaysIrrTex for all layers, linear [layer][probe][ray]
   float4* dDirs = nullptr; float4* hDirs = nullptr;        // [nY][N] rotated directions (ProbeRaysDirTex is derived from it)
+  int* dLayerMap = nullptr; int* hLayerMap = nullptr;      // [nY] absolute layers of the current launch (pinned staging + device)
+  int numLaunchLayers = 0;
   uint16_t* dRayOrder = nullptr;
   anerend_ddgi_ray_record_t* dRecords = nullptr; float4* dTexelRecords = nullptr; unsigned long long* dStats = nullptr;
   std::vector<float> fib;                                  // N*3
@@ -271,8 +273,7 @@ void rotateDirs(anerend_ddgi* h, int layer, const float* m) {
 int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   Backend& be = h->be;
   const uint32_t nq = 1u + ((h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) ? h->numLights : 0u);
-  const size_t slabRays = (size_t)(h->p.slab_end - h->p.slab_begin) * h->P * h->N;
-  const size_t need = n > slabRays ? n : slabRays;
+  const size_t need = n;                      // grows on demand: a full-grid call after per-layer calls reallocates once
   if (h->fastRays < need || h->fastQueues < nq) {
     BE_CHECK(h, be.sync());
     be.free(h->dHits); be.free(h->dSurf); be.free(h->dLit); be.free(h->dQueues); be.free(h->dQcount); be.free(h->dHitq);
@@ -317,22 +318,30 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
 }
 #endif
 
-int traceLayers(anerend_ddgi* h, int layerBegin, int numLayers, const float* rots /* indexed from layerBegin */) {
+// `layers`: the absolute layers of this launch (any subset of the grid, each at most once); rots + 16*rotStride*i is
+// the randomRot of layers[i] (rotStride 0: one matrix, 1: packed per launched layer; rotsByLayer: indexed by absolute layer)
+int traceLayers(anerend_ddgi* h, const int* layers, int numLayers, const float* rots, bool rotsByLayer) {
   Backend& be = h->be;
   if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "trace before build_accel");
   if (!h->haveUbo) return fail(h, ANEREND_DDGI_E_STATE, "trace before set_scene_ubo");
-  be.waitCopy();            // previous H2D of the staging table must be done before it is rewritten
-  for (int l = 0; l < numLayers; ++l) rotateDirs(h, layerBegin + l, rots + 16 * (size_t)l);
-  BE_CHECK(h, be.h2d(h->dDirs + (size_t)layerBegin * h->N, h->hDirs + (size_t)layerBegin * h->N, (size_t)numLayers * h->N * sizeof(float4)));
+  be.waitCopy();            // previous H2D of the staging tables must be done before they are rewritten
+  for (int l = 0; l < numLayers; ++l) {
+    const int layer = layers[l];
+    rotateDirs(h, layer, rots + 16 * (size_t)(rotsByLayer ? layer : l));
+    h->hLayerMap[l] = layer;
+    BE_CHECK(h, be.h2d(h->dDirs + (size_t)layer * h->N, h->hDirs + (size_t)layer * h->N, (size_t)h->N * sizeof(float4)));
+  }
+  BE_CHECK(h, be.h2d(h->dLayerMap, h->hLayerMap, (size_t)numLayers * sizeof(int)));
+  h->numLaunchLayers = numLayers;
   be.markCopy();
   TraceCtx c{};
   c.nodes = h->dNodes; c.bvhTris = h->dBvhTris; c.numNodes = h->numNodes;
   c.vertices = h->dVertices; c.indices = h->dIndices; c.materials = h->dMaterials;
   c.instances = h->dInstances; c.xforms = h->dXforms; c.triInstance = h->dTriInstance;
   c.lights = h->dLights; c.numLights = h->numLights;
-  c.dirs = h->dDirs + (size_t)layerBegin * h->N; c.rayOrder = h->dRayOrder; c.atlas = h->dAtlas; c.rayIrr = h->dRayIrr;
+  c.dirs = h->dDirs; c.layerMap = h->dLayerMap; c.rayOrder = h->dRayOrder; c.atlas = h->dAtlas; c.rayIrr = h->dRayIrr;
   c.records = h->dRecords; c.stats = h->dStats;
-  c.nXZ = h->nXZ; c.nY = h->nY; c.N = h->N; c.W = h->W; c.H = h->H; c.layerBegin = layerBegin; c.numLayers = numLayers;
+  c.nXZ = h->nXZ; c.nY = h->nY; c.N = h->N; c.W = h->W; c.H = h->H; c.numLayers = numLayers;
   // camOffset (rgen:75-81, pbr_light.glsl:295-301): int() truncates toward zero (quirk Q1)
   const float* step = h->p.probe_step;
   int cix = (int)(h->ubo.camera_pos[0] / step[0]), ciz = (int)(h->ubo.camera_pos[2] / step[2]);
@@ -354,18 +363,27 @@ int traceLayers(anerend_ddgi* h, int layerBegin, int numLayers, const float* rot
     else DDGI_LAUNCH(be, k_probe_trace, trace_ray_body<false>, n, c, 128);
     BE_CHECK(h, be.check());
   }
-  for (int l = 0; l < numLayers; ++l) h->layerTraced[layerBegin + l] = 1;
+  for (int l = 0; l < numLayers; ++l) h->layerTraced[layers[l]] = 1;
   return 0;
 }
 
-int convolveLayers(anerend_ddgi* h, int layerBegin, int numLayers) {
+int convolveLayers(anerend_ddgi* h, const int* layers, int numLayers) {
   Backend& be = h->be;
-  for (int l = 0; l < numLayers; ++l) if (!h->layerTraced[layerBegin + l]) return fail(h, ANEREND_DDGI_E_STATE, "convolve before trace of this layer");
+  for (int l = 0; l < numLayers; ++l) if (!h->layerTraced[layers[l]]) return fail(h, ANEREND_DDGI_E_STATE, "convolve before trace of this layer");
+  bool same = numLayers == h->numLaunchLayers;
+  for (int l = 0; same && l < numLayers; ++l) same = h->hLayerMap[l] == layers[l];
+  if (!same) {              // convolve of a different layer set than the last trace: restage the layer map
+    be.waitCopy();
+    for (int l = 0; l < numLayers; ++l) h->hLayerMap[l] = layers[l];
+    BE_CHECK(h, be.h2d(h->dLayerMap, h->hLayerMap, (size_t)numLayers * sizeof(int)));
+    h->numLaunchLayers = numLayers;
+    be.markCopy();
+  }
   ConvCtx c{};
-  c.rayIrr = h->dRayIrr; c.dirs = h->dDirs + (size_t)layerBegin * h->N; c.atlas = h->dAtlas; c.texelRecords = h->dTexelRecords;
+  c.rayIrr = h->dRayIrr; c.dirs = h->dDirs; c.layerMap = h->dLayerMap; c.atlas = h->dAtlas; c.texelRecords = h->dTexelRecords;
   for (int i = 0; i < h->numPeers; ++i) c.peers[i] = h->peers[i];
   c.numPeers = h->numPeers;
-  c.nXZ = h->nXZ; c.nY = h->nY; c.N = h->N; c.Sx = h->Sx; c.Sy = h->Sy; c.W = h->W; c.H = h->H; c.layerBegin = layerBegin; c.numLayers = numLayers;
+  c.nXZ = h->nXZ; c.nY = h->nY; c.N = h->N; c.Sx = h->Sx; c.Sy = h->Sy; c.W = h->W; c.H = h->H; c.numLayers = numLayers;
   c.hysteresis = h->p.hysteresis;
 #ifndef DDGI_HOST_EMU
   if (!(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS)) {
@@ -404,6 +422,7 @@ void destroyHandle(anerend_ddgi* h) {
   be.sync();
   freeAccel(h); freeScene(h);
   be.free(h->dAtlas); be.free(h->dTemp); be.free(h->dRayIrr); be.free(h->dDirs); be.freeHostPinned(h->hDirs); be.free(h->dRayOrder);
+  be.free(h->dLayerMap); be.freeHostPinned(h->hLayerMap);
   be.free(h->dRecords); be.free(h->dTexelRecords); be.free(h->dStats); be.free(h->dSceneBounds); be.free(h->dCounters);
   be.free(h->dHits); be.free(h->dSurf); be.free(h->dLit); be.free(h->dQueues); be.free(h->dQcount); be.free(h->dHitq); be.free(h->dConvW);
   be.destroy();
@@ -433,7 +452,7 @@ int DDGI_API(create)(const anerend_ddgi_params_t* params, anerend_ddgi_t** out) 
   bool ok = be.alloc(&h->dAtlas, texels) && be.alloc(&h->dTemp, texels) && be.alloc(&h->dRayIrr, rays) &&
             be.alloc(&h->dDirs, (size_t)h->nY * h->N) && be.allocHostPinned(&h->hDirs, (size_t)h->nY * h->N) &&
             be.alloc(&h->dSceneBounds, 6) && be.alloc(&h->dCounters, 4) && be.alloc(&h->dStats, 8) &&
-            be.alloc(&h->dConvW, (size_t)h->nY * h->N * 64);
+            be.alloc(&h->dConvW, (size_t)h->nY * h->N * 64) && be.alloc(&h->dLayerMap, (size_t)h->nY) && be.allocHostPinned(&h->hLayerMap, (size_t)h->nY);
   if (ok && (q.flags & ANEREND_DDGI_FLAG_RAY_RECORDS)) ok = be.alloc(&h->dRecords, rays);
   if (ok && (q.flags & ANEREND_DDGI_FLAG_TEXEL_RECORDS)) ok = be.alloc(&h->dTexelRecords, texels);
   if (ok) ok = be.zero(h->dStats, 8 * sizeof(unsigned long long)) && be.zero(h->dRayIrr, rays * sizeof(uint2));
@@ -567,25 +586,44 @@ int DDGI_API(trace_layer)(anerend_ddgi_t* h, int32_t layer, const float rot[16])
   if (h->haveUbo && !ddgiOn(h)) return 0;
   if (layer < 0 || layer >= h->nY || !rot) return fail(h, ANEREND_DDGI_E_INVALID, "layer out of range");
   beginCall(h); h->be.mark(1);
-  int rc = traceLayers(h, layer, 1, rot); h->be.mark(2); h->timed[1] = true;
+  const int one = layer;
+  int rc = traceLayers(h, &one, 1, rot, false); h->be.mark(2); h->timed[1] = true;
   return rc;
 }
 int DDGI_API(convolve_layer)(anerend_ddgi_t* h, int32_t layer) {
   if (h->haveUbo && !ddgiOn(h)) return 0;
   if (layer < 0 || layer >= h->nY) return fail(h, ANEREND_DDGI_E_INVALID, "layer out of range");
   beginCall(h); h->be.mark(2);
-  int rc = convolveLayers(h, layer, 1); h->be.mark(3); h->timed[2] = true;
+  const int one = layer;
+  int rc = convolveLayers(h, &one, 1); h->be.mark(3); h->timed[2] = true;
   return rc;
 }
 int DDGI_API(update)(anerend_ddgi_t* h, int32_t layer, const float* rots) {
   if (h->haveUbo && !ddgiOn(h)) return 0;
   if (!rots || layer >= h->nY) return fail(h, ANEREND_DDGI_E_INVALID, "bad update arguments");
   beginCall(h); h->be.mark(1);
-  int lb = layer >= 0 ? layer : h->p.slab_begin, nl = layer >= 0 ? 1 : h->p.slab_end - h->p.slab_begin;
-  int rc = traceLayers(h, lb, nl, layer >= 0 ? rots : rots + 16 * (size_t)lb);
+  std::vector<int> layers;
+  if (layer >= 0) layers.push_back(layer); else for (int l = h->p.slab_begin; l < h->p.slab_end; ++l) layers.push_back(l);
+  int rc = traceLayers(h, layers.data(), (int)layers.size(), rots, layer < 0);
   h->be.mark(2); h->timed[1] = true;
   if (rc) return rc;
-  rc = convolveLayers(h, lb, nl);
+  rc = convolveLayers(h, layers.data(), (int)layers.size());
+  h->be.mark(3); h->timed[2] = true;
+  return rc;
+}
+int DDGI_API(update_layers)(anerend_ddgi_t* h, const int32_t* layerList, uint32_t n, const float* rots) {
+  if (h->haveUbo && !ddgiOn(h)) return 0;
+  if (!rots || !layerList || n == 0 || n > (uint32_t)h->nY) return fail(h, ANEREND_DDGI_E_INVALID, "bad update_layers arguments");
+  std::vector<uint8_t> seen(h->nY, 0);
+  for (uint32_t i = 0; i < n; ++i) {
+    if (layerList[i] < 0 || layerList[i] >= h->nY || seen[layerList[i]]) return fail(h, ANEREND_DDGI_E_INVALID, "layer out of range or listed twice");
+    seen[layerList[i]] = 1;
+  }
+  beginCall(h); h->be.mark(1);
+  int rc = traceLayers(h, layerList, (int)n, rots, true);
+  h->be.mark(2); h->timed[1] = true;
+  if (rc) return rc;
+  rc = convolveLayers(h, layerList, (int)n);
   h->be.mark(3); h->timed[2] = true;
   return rc;
 }
@@ -595,11 +633,11 @@ int DDGI_API(frame)(anerend_ddgi_t* h, const float rot[16], int32_t* layerOut) {
   if (rc) return rc;
   if (!ddgiOn(h)) return 0;
   const int layer = h->currentLayer;                                   // IrradianceProbeRayTracingPass.cpp:112
-  rc = traceLayers(h, layer, 1, rot); h->be.mark(2); h->timed[1] = true;
+  rc = traceLayers(h, &layer, 1, rot, false); h->be.mark(2); h->timed[1] = true;
   if (rc) return rc;
   if (layerOut) *layerOut = layer;                                     // blackboard "ProbeLayer" (:158)
   h->currentLayer = (h->currentLayer + 1 >= h->nY) ? 0 : h->currentLayer + 1;   // :160-164
-  rc = convolveLayers(h, layer, 1); h->be.mark(3); h->timed[2] = true;
+  rc = convolveLayers(h, &layer, 1); h->be.mark(3); h->timed[2] = true;
   return rc;
 }
 

@@ -183,8 +183,9 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
             const uint32_t slot = w % (uint32_t)t.N, probeLin = w / (uint32_t)t.N;
             const int layerLocal = (int)(probeLin / (uint32_t)P), probe = (int)(probeLin % (uint32_t)P);
             const uint32_t ray = t.rayOrder ? (uint32_t)t.rayOrder[slot] : slot;
-            const V3 origin = mk3((float)(probe % t.nXZ), (float)(t.layerBegin + layerLocal), (float)(probe / t.nXZ)) * t.step + t.camOff;
-            const float4 d4 = __ldg(&t.dirs[(size_t)layerLocal * t.N + ray]);
+            const int layer = __ldg(&t.layerMap[layerLocal]);
+            const V3 origin = mk3((float)(probe % t.nXZ), (float)layer, (float)(probe / t.nXZ)) * t.step + t.camOff;
+            const float4 d4 = __ldg(&t.dirs[(size_t)layer * t.N + ray]);
             ray_stage(dst, origin, mk3(d4.x, d4.y, d4.z), t.tmax, w, 0u);
           } else {
             uint32_t q = 0; while (q + 1 < c.numQueues && sPrefix[q + 1] <= w) ++q;
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(PREP_BLOCK) k_shade_prep(const FastCtx c) {
       const uint32_t slot = idx % (uint32_t)t.N, probeLin = idx / (uint32_t)t.N;
       const int layerLocal = (int)(probeLin / (uint32_t)P), probe = (int)(probeLin % (uint32_t)P);
       const uint32_t ray = t.rayOrder ? (uint32_t)t.rayOrder[slot] : slot;
-      const size_t o = ((size_t)(t.layerBegin + layerLocal) * P + probe) * t.N + ray;
+      const size_t o = ((size_t)t.layerMap[layerLocal] * P + probe) * t.N + ray;
       t.rayIrr[o] = make_uint2((uint32_t)f2h(t.sky.x) | ((uint32_t)f2h(t.sky.y) << 16), (uint32_t)f2h(t.sky.z) | (0x3C00u << 16));
       if (t.records) { anerend_ddgi_ray_record_t rr; rr.prim = DDGI_MISS; rr.t = 0.0f; rr.u = 0.0f; rr.v = 0.0f;
                        rr.radiance[0] = t.sky.x; rr.radiance[1] = t.sky.y; rr.radiance[2] = t.sky.z; rr.lit_mask = 0u; t.records[o] = rr; }

@@ -501,14 +501,15 @@ struct TraceCtx {
   const anerend_vertex_t* vertices; const uint32_t* indices; const anerend_material_info_t* materials;
   const DInstance* instances; const InstXform* xforms; const uint32_t* triInstance;
   const anerend_light_t* lights; uint32_t numLights;
-  const float4* dirs;          // [numLayers][N]: mat3(randomRot) * fibonacci dir, computed on the host (rgen:87-88)
+  const float4* dirs;          // [nY][N] by absolute layer: mat3(randomRot) * fibonacci dir, computed on the host (rgen:87-88)
+  const int* layerMap;         // [numLayers] absolute layer of each launched layer (a slab, or any subset of the grid)
   const uint16_t* rayOrder;    // [N] slot -> ray index (direction-binned order), or null
   const uint2* atlas;          // ProbeRaysConvTex, RGBA16F texels
   uint2* rayIrr;               // ProbeRaysIrrTex replacement: [nY][P][N] RGBA16F
   anerend_ddgi_ray_record_t* records;   // [nY][P][N] or null
   unsigned long long* stats;   // 7 counters or null
   int nXZ, nY, N, W, H;
-  int layerBegin, numLayers;
+  int numLayers;
   V3 camOff, step, sky, lightDir;
   float tmin, tmax, sunIntensity;
   uint32_t uboFlags, flags;
@@ -643,11 +644,11 @@ HD void trace_ray_body(uint32_t idx, const TraceCtx& c) {
   const int P = c.nXZ * c.nXZ;
   const uint32_t slot = idx % (uint32_t)c.N, probeLin = idx / (uint32_t)c.N;
   const int layerLocal = (int)(probeLin / (uint32_t)P), probe = (int)(probeLin % (uint32_t)P);
-  const int layer = c.layerBegin + layerLocal;
+  const int layer = c.layerMap[layerLocal];
   const uint32_t ray = c.rayOrder ? (uint32_t)c.rayOrder[slot] : slot;
   const int probeX = probe % c.nXZ, probeZ = probe / c.nXZ;
   const V3 origin = mk3((float)probeX, (float)layer, (float)probeZ) * c.step + c.camOff;      // rgen:83
-  const float4 d4 = c.dirs[(size_t)layerLocal * c.N + ray];
+  const float4 d4 = c.dirs[(size_t)layer * c.N + ray];
   const V3 d = mk3(d4.x, d4.y, d4.z);
   uint32_t cn[2] = {0, 0}, ct[2] = {0, 0}, nShadow = 0, lit = 0;
   Hit hit;
@@ -729,22 +730,23 @@ HD void trace_ray_body(uint32_t idx, const TraceCtx& c) {
 // probe_conv.comp main (probe_conv.comp:21-90), live mode.  Thread per interior atlas texel.
 // ----------------------------------------------------------------------------------------------------
 struct ConvCtx {
-  const uint2* rayIrr; const float4* dirs;   // dirs: [numLayers][N] fp32, rounded to fp16 here like the rgba16f store (rgen:108)
+  const uint2* rayIrr; const float4* dirs;   // dirs: [nY][N] fp32 by absolute layer, rounded to fp16 here like the rgba16f store (rgen:108)
+  const int* layerMap;                       // [numLayers] absolute layer of each launched layer
   uint2* atlas; float4* texelRecords;        // atlas written in place (or to every peer's copy, see peers)
   uint2* peers[8]; int numPeers;
-  int nXZ, nY, N, Sx, Sy, W, H, layerBegin, numLayers;
+  int nXZ, nY, N, Sx, Sy, W, H, numLayers;
   float hysteresis;
 };
 HD void conv_texel_body(uint32_t idx, const ConvCtx& c) {
   const int P = c.nXZ * c.nXZ;
   const int texel = (int)(idx & 63u); const uint32_t probeLin = idx >> 6;
-  const int layerLocal = (int)(probeLin / (uint32_t)P), probe = (int)(probeLin % (uint32_t)P), layer = c.layerBegin + layerLocal;
+  const int layerLocal = (int)(probeLin / (uint32_t)P), probe = (int)(probeLin % (uint32_t)P), layer = c.layerMap[layerLocal];
   const int i = texel & 7, j = texel >> 3, probeX = probe % c.nXZ, probeZ = probe / c.nXZ;
   float ux = (2.0f * (float)i + 1.0f) / (2.0f * 8.0f), uy = (2.0f * (float)j + 1.0f) / (2.0f * 8.0f);     // pixelToUv, helpers.glsl:1-4
   ux = ux * 2.0f - 1.0f; uy = uy * 2.0f - 1.0f;
   const V3 octDir = oct_decode(ux, uy);
   const uint2* irr = c.rayIrr + ((size_t)layer * P + probe) * c.N;
-  const float4* dirs = c.dirs + (size_t)layerLocal * c.N;
+  const float4* dirs = c.dirs + (size_t)layer * c.N;
   float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f, r3 = 0.0f;
   for (int x = 0; x < c.Sx; ++x) for (int y = 0; y < c.Sy; ++y) {        // x outer, y inner (probe_conv.comp:49-50)
     const int ray = y * c.Sx + x;

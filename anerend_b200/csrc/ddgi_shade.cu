@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(128) k_shade(const FastCtx c) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nHits; i += gridDim.x * blockDim.x) {
     const uint32_t idx = c.hitq[i];
     const uint32_t slot = idx % (uint32_t)t.N, probeLin = idx / (uint32_t)t.N;
-    const int layerLocal = (int)(probeLin / (uint32_t)P), probe = (int)(probeLin % (uint32_t)P), layer = t.layerBegin + layerLocal;
+    const int layerLocal = (int)(probeLin / (uint32_t)P), probe = (int)(probeLin % (uint32_t)P), layer = t.layerMap[layerLocal];
     const uint32_t ray = t.rayOrder ? (uint32_t)t.rayOrder[slot] : slot;
     const V3 origin = mk3((float)(probe % t.nXZ), (float)layer, (float)(probe / t.nXZ)) * t.step + t.camOff;
     const float4 s0 = c.surf[3 * (size_t)idx], s1 = c.surf[3 * (size_t)idx + 1], s2 = c.surf[3 * (size_t)idx + 2];
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(128) k_conv_weights(const ConvFastCtx f) {
   // position p in the reference's loop order (x outer, y inner; probe_conv.comp:49-50) <-> ray index y*Sx + x
   const uint32_t layerLocal = idx / (uint32_t)c.N, pos = idx % (uint32_t)c.N;
   const uint32_t ray = (pos % (uint32_t)c.Sy) * (uint32_t)c.Sx + pos / (uint32_t)c.Sy;
-  const float4 d4 = c.dirs[layerLocal * (uint32_t)c.N + ray];      // [numLayers][N]
+  const float4 d4 = c.dirs[(uint32_t)c.layerMap[layerLocal] * (uint32_t)c.N + ray];      // [nY][N]
   const V3 d = mk3(h2f(f2h(d4.x)), h2f(f2h(d4.y)), h2f(f2h(d4.z)));  // what the rgba16f ProbeRaysDirTex holds (rgen:108)
   float4* out = (float4*)(f.weights + (size_t)idx * 64);
 #pragma unroll 1
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) k_probe_convolve_fast(const ConvFastCtx f
   const int P = c.nXZ * c.nXZ;
   const int blocksPerLayer = (P + CONV_G - 1) / CONV_G;
   const int layerLocal = (int)blockIdx.x / blocksPerLayer, g0 = ((int)blockIdx.x % blocksPerLayer) * CONV_G;
-  const int layer = c.layerBegin + layerLocal;
+  const int layer = c.layerMap[layerLocal];
   const int texel = (int)threadIdx.x & 63, sub = (int)threadIdx.x >> 6;
   float acc[CONV_PPT][4];
 #pragma unroll

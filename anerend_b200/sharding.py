@@ -19,6 +19,75 @@ def slab_for_rank(num_probes_y, rank, world):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+def layers_for_rank(num_probes_y, rank, world):
+    """Interleaved ("zigzag") layer set of `rank` for a balanced multi-GPU update: layers are dealt to the ranks in
+    boustrophedon order (0..R-1, R-1..0, 0..R-1, ...).  Work per layer falls with height in any scene that has a
+    ground (lower layers hit more geometry and spawn more shadow rays); contiguous slabs gave the bottom rank 1.6x the
+    work of the top one at C5, a zigzag deal cancels a linear trend exactly.  Every rank gets floor or ceil(nY/R) layers."""
+    if world > num_probes_y:
+        raise ValueError(f"{world} ranks cannot share {num_probes_y} probe layers")
+    out = []
+    for y in range(num_probes_y):
+        k, pos = divmod(y, world)
+        owner = pos if k % 2 == 0 else world - 1 - pos
+        if owner == rank:
+            out.append(y)
+    return out
+
+
+def mirrored_slabs_for_rank(num_probes_y, rank, world):
+    """Balanced AND contiguous: rank r owns chunk r of the lower half of the layers and chunk R-1-r of the upper half
+    (k = nY/(2R) layers each).  Like the zigzag deal it cancels a linear work-vs-height trend, but each half is a plain
+    all-gather of contiguous atlas rows (in place for the lower half; into reversed row blocks for the upper half), so
+    the exchange needs no per-texel pack/scatter.  Needs nY divisible by 2R."""
+    if num_probes_y % (2 * world):
+        raise ValueError("mirrored slabs need num_probes_y divisible by twice the world size")
+    k = num_probes_y // (2 * world)
+    half = num_probes_y // 2
+    return list(range(rank * k, (rank + 1) * k)) + list(range(half + (world - 1 - rank) * k, half + (world - rank) * k))
+
+
+def all_gather_atlas_mirrored(atlas, num_probes_xz, num_probes_y, rank, world, group=None):
+    """Exchange for `mirrored_slabs_for_rank`: an in-place all_gather_into_tensor of the lower half of the atlas rows and
+    an all_gather of the upper half whose output blocks are the row ranges in reversed rank order."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return atlas
+    a = atlas.view(torch.int64)                   # one RGBA16F texel per element; bit copy
+    rows = 10 * num_probes_xz
+    k = num_probes_y // (2 * world)
+    half_rows = rows * (num_probes_y // 2)
+    lo, hi = a[:half_rows], a[half_rows:]
+    b = rank * k * rows
+    dist.all_gather_into_tensor(lo.reshape(-1), lo[b:b + k * rows].reshape(-1), group=group)
+    blocks = [hi[(world - 1 - r) * k * rows:(world - r) * k * rows] for r in range(world)]
+    dist.all_gather(blocks, blocks[rank].clone(), group=group)
+    return atlas
+
+
+def all_gather_atlas_layers(atlas, num_probes_xz, num_probes_y, rank, world, group=None):
+    """All-gather for interleaved layer sets (`layers_for_rank`).  `atlas` is a torch tensor [H, W, 4]; a rank's layers
+    are not contiguous rows, so its rows are packed into a send buffer, gathered, and scattered back (two extra
+    device copies of the atlas per update).  Needs nY divisible by R (equal chunks)."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return atlas
+    if num_probes_y % world:
+        raise ValueError("interleaved gather needs num_probes_y divisible by the world size")
+    rows = 10 * num_probes_xz
+    a = atlas.view(torch.int64).view(num_probes_y, rows, atlas.shape[1])              # [nY, rows, W] texels (bit copy)
+    owners = [layers_for_rank(num_probes_y, r, world) for r in range(world)]
+    idx = torch.as_tensor(owners[rank], device=a.device)
+    send = a.index_select(0, idx).contiguous()
+    recv = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=a.device)
+    dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)
+    order = torch.as_tensor([y for o in owners for y in o], device=a.device)
+    a.index_copy_(0, order, recv.view((num_probes_y,) + tuple(send.shape[1:])))
+    return atlas
+
+
 def slab_rows(num_probes_xz, slab):
     """Atlas row range [begin, end) of a layer slab: 10*nXZ rows per layer (IrradianceProbeConvolvePass.cpp:84-99)."""
     return 10 * num_probes_xz * slab[0], 10 * num_probes_xz * slab[1]

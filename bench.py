@@ -4,7 +4,7 @@
 A "step" is one full-grid DDGI probe update (translate if needed -> trace+shade all layers -> convolve) of one
 synthetic workload:
     c3 (default at N=1): Sponza-scale mesh (~262k tris, 64 materials, 8 lights), 24x12x24 probes x 256 rays + shadow rays
-    c5 (default at N>1): large volume (~2M tris), 64x32x64 probes x 256 rays, Y-slab sharded + atlas all-gather
+    c5 (default at N>1): large volume (~2M tris), 64x32x64 probes x 256 rays, probe layers dealt to the ranks + atlas all-gather
     c2                 : Cornell box (~10k tris), 16x8x16 probes x 128 rays
 `value` = primary probe rays of all ranks / device time (CUDA events on the handle's stream, max over ranks), inputs
 resident in HBM.  `e2e` = the same through the public API with host buffers: per step the scene UBO + rotation matrices
@@ -43,7 +43,7 @@ def workload_desc(name, scene, grid, world):
     return {"workload": name, "scene": scene.name, "triangles": int(scene.num_triangles),
             "probes": f"{nxz}x{ny}x{nxz}", "rays_per_probe": nr, "primary_rays_per_update": nxz * nxz * ny * nr,
             "lights": int(len(scene.lights)), "point_lights_E1": True, "multi_bounce": True, "dead_shadow_rays_skipped": True,
-            "mode": "jacobi full-grid update", "parallelism": f"y-slab x{world}" if world > 1 else "single GPU"}
+            "mode": "jacobi full-grid update", "parallelism": f"probe layers dealt to {world} ranks" if world > 1 else "single GPU"}
 
 
 def peaks():
@@ -180,7 +180,12 @@ def main():
     name = args.workload or ("c3" if world == 1 else "c5")
     scene, grid, seed = build_workload(name)
     nxz, ny, nr = grid
-    slab = sharding.slab_for_rank(ny, rank, world)
+    # multi-GPU: interleaved layer sets (balanced) when nY divides evenly, contiguous slabs otherwise
+    mirrored = world > 1 and ny % (2 * world) == 0
+    interleaved = world > 1 and (mirrored or ny % world == 0)
+    slab = (0, ny) if interleaved else sharding.slab_for_rank(ny, rank, world)
+    my_layers = (sharding.mirrored_slabs_for_rank(ny, rank, world) if mirrored else
+                 sharding.layers_for_rank(ny, rank, world) if interleaved else list(range(slab[0], slab[1])))
     # point lights (extension E1) + dead-shadow-ray elimination (radiance bit-identical, tests/test_oracle_kat.py);
     # the default kernels are the exact build (atlas bit-identical to the oracle); FAST_MATH is timed as a second figure
     flags = L.FLAG_POINT_LIGHTS | L.FLAG_SKIP_DEAD_SHADOW_RAYS
@@ -202,7 +207,7 @@ def main():
     accel_ms = h.timings()["accel_ms"]
     info = h.bvh_info()
     rots = h.rotations(seq).reshape(total_steps, ny, 16)
-    my_rays = nxz * nxz * (slab[1] - slab[0]) * nr
+    my_rays = nxz * nxz * len(my_layers) * nr
     nbytes = h.atlas_device_ptr()[1]
     host_atlas = torch.empty((h.atlas_height, h.atlas_width, 4), dtype=torch.int16, pin_memory=True)   # pinned result buffer
     host_np = host_atlas.numpy().view(np.uint16)
@@ -221,10 +226,18 @@ def main():
         def step(k):
             hh.set_scene_ubo(scene.ubo)
             hh.translate()
-            hh.update(-1, rots[k])
-            if do_gather:
+            if do_gather and interleaved:
+                hh.update_layers(my_layers, rots[k])
                 with torch.cuda.stream(stream):
-                    sharding.all_gather_atlas(atlas_t, nxz, ny, rank, world)
+                    if mirrored:
+                        sharding.all_gather_atlas_mirrored(atlas_t, nxz, ny, rank, world)
+                    else:
+                        sharding.all_gather_atlas_layers(atlas_t, nxz, ny, rank, world)
+            else:
+                hh.update(-1, rots[k])
+                if do_gather:
+                    with torch.cuda.stream(stream):
+                        sharding.all_gather_atlas(atlas_t, nxz, ny, rank, world)
 
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         for k in range(warmup):
@@ -244,7 +257,7 @@ def main():
             t = hh.timings()                     # synchronises the handle's stream
             rt.append(t["rt_ms"])
             cv.append(t["convolve_ms"])
-            nl += t["kernel_launches"] + (1 if do_gather else 0)
+            nl += t["kernel_launches"]          # our kernels only (the NCCL collective and torch's pack/unpack copies are not counted)
         torch.cuda.synchronize()
         if multi:
             dist.barrier()
@@ -279,7 +292,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     e2e_value = all_rays * e2e_steps / e2e_s / 1e6
-    h2d_bytes = (slab[1] - slab[0]) * nr * 16 + 568 + 64 * ny
+    h2d_bytes = len(my_layers) * nr * 16 + 568 + 64 * ny
     d2h_bytes = nbytes
 
     # ---- second figure: the other arithmetic build (FAST_MATH <-> exact), same workload, fewer steps ----------
@@ -308,7 +321,10 @@ def main():
     if rank == 0:
         # ---- roofline of the dominant kernel (k_probe_trace): counted, untimed run of the same update ----------
         hc = make_handle(flags | L.FLAG_COUNTERS, slab)
-        hc.update(-1, rots[args.warmup])
+        if interleaved:
+            hc.update_layers(my_layers, rots[args.warmup])
+        else:
+            hc.update(-1, rots[args.warmup])
         stats = hc.stats()
         hc.close()
         peak, peak_src = peaks()
@@ -337,7 +353,9 @@ def main():
         cfg = workload_desc(name, scene, grid, world)
         cfg.update({"l2": "flushed between timed iterations (256 MiB write)" if flush else "working set larger than L2, no flush",
                     "bvh8_nodes": int(info.num_nodes), "accel_build_ms": accel_ms,
-                    "atlas_exchange": "nccl all_gather (in place, on the handle's stream)" if world > 1 else "none"})
+                    "atlas_exchange": ("2 in-place nccl all_gathers of mirrored slabs on the handle's stream" if mirrored else
+                                       "nccl all_gather of interleaved layers (pack, gather, scatter) on the handle's stream" if interleaved
+                                       else "nccl all_gather of contiguous slabs, in place") if world > 1 else "none"})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,

@@ -167,6 +167,10 @@ int anerend_cuda_ddgi_convolve_layer(anerend_ddgi_t* h, int32_t layer);
  *             previous atlas, then all are convolved ("jacobi" mode); rots = num_probes_y matrices,
  *             indexed by absolute layer. */
 int anerend_cuda_ddgi_update(anerend_ddgi_t* h, int32_t layer, const float* rots);
+/* Jacobi update of an arbitrary set of layers (each at most once): the multi-GPU path gives every rank an interleaved
+ * set so the work balances (the reference's own time slicing is one layer per execution,
+ * IrradianceProbeRayTracingPass.cpp:112,160-164).  rots = num_probes_y matrices indexed by absolute layer. */
+int anerend_cuda_ddgi_update_layers(anerend_ddgi_t* h, const int32_t* layers, uint32_t num_layers, const float* rots);
 /* One frame at the reference's cadence: translate, trace+convolve layer `_currentLayer`, advance it
  * (IrradianceProbeRayTracingPass.cpp:112,158-164).  *layer_out receives blackboard "ProbeLayer". */
 int anerend_cuda_ddgi_frame(anerend_ddgi_t* h, const float rot[16], int32_t* layer_out);

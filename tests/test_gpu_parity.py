@@ -244,6 +244,34 @@ def test_config3_sponza_scale_layers_and_properties(oracle, make_gpu):
     g.close()
 
 
+def test_interleaved_layer_sets_assemble_the_full_atlas(make_gpu):
+    """The balanced multi-GPU split (sharding.layers_for_rank + update_layers): handles that each update an interleaved
+    subset of the layers produce, after exchanging their rows, exactly the atlas of one full-grid update."""
+    from anerend_b200 import sharding
+    scene = scenes.cornell_box(grid=(8, 4, 64), wall_res=10, box_res=3)
+    world = 2
+    full = make_gpu(make_params(8, 4, 64, flags=L.FLAG_POINT_LIGHTS))
+    parts = [make_gpu(make_params(8, 4, 64, flags=L.FLAG_POINT_LIGHTS)) for _ in range(world)]
+    rots = parity.setup_pair(scene, [full] + parts, seed=8)
+    sets = [sharding.layers_for_rank(4, r, world) for r in range(world)]
+    assert sets == [[0, 3], [1, 2]]
+    W = 80
+    for it in range(3):
+        full.update(-1, rots)
+        for h, ls in zip(parts, sets):
+            h.update_layers(ls, rots)
+        outs = [h.download_atlas() for h in parts]
+        merged = outs[0].copy()
+        for r in range(1, world):
+            for y in sets[r]:
+                merged[y * W:(y + 1) * W] = outs[r][y * W:(y + 1) * W]
+        for h in parts:
+            h.upload_atlas(merged)
+        assert np.array_equal(merged, full.download_atlas())
+    for h in [full] + parts:
+        h.close()
+
+
 def test_slab_handles_assemble_the_full_atlas(oracle, make_gpu):
     """Multi-GPU sharding on one device: two handles owning disjoint Y-slabs produce, after exchanging slabs, exactly the
     atlas a single full-grid handle produces (jacobi semantics)."""

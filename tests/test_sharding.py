@@ -53,6 +53,75 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
+def _worker_interleaved(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    from anerend_b200 import layouts as L, make_params, scenes
+    from anerend_b200.capi import DdgiHandle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    emu = ctypes.CDLL(g.build_host_emu())
+    nxz, ny, nr = 4, 4, 64
+    scene = scenes.random_soup(52, ntris=400, grid=(nxz, ny, nr))
+    h = DdgiHandle(emu, "anerend_emu_ddgi_", make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS))
+    h.upload_scene(scene)
+    h.set_scene_ubo(scene.ubo)
+    h.build_accel()
+    rots = h.rotations(scenes.rotation_sequence(9, ny))
+    for it in range(4):
+        # alternate the two balanced splits: zigzag deal (packed gather) and mirrored slabs (two in-place gathers)
+        mirrored = it % 2 == 1
+        mine = sharding.mirrored_slabs_for_rank(ny, rank, world) if mirrored else sharding.layers_for_rank(ny, rank, world)
+        h.update_layers(mine, rots)
+        atlas = torch.from_numpy(h.download_atlas().view(np.int16).copy())
+        if mirrored:
+            sharding.all_gather_atlas_mirrored(atlas, nxz, ny, rank, world)
+        else:
+            sharding.all_gather_atlas_layers(atlas, nxz, ny, rank, world)
+        h.upload_atlas(atlas.numpy().view(np.uint16))
+    np.save(os.path.join(out_dir, f"atlas_i{rank}.npy"), h.download_atlas())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_layers_for_rank_is_a_balanced_partition():
+    for ny, world in ((32, 8), (32, 4), (32, 2), (12, 4), (8, 8), (5, 2)):
+        sets = [sharding.layers_for_rank(ny, r, world) for r in range(world)]
+        assert sorted(sum(sets, [])) == list(range(ny))
+        assert max(map(len, sets)) - min(map(len, sets)) <= 1
+        if ny % (2 * world) == 0:                 # a linear work profile is balanced exactly
+            assert len({sum(s) for s in sets}) == 1
+            mir = [sharding.mirrored_slabs_for_rank(ny, r, world) for r in range(world)]
+            assert sorted(sum(mir, [])) == list(range(ny)) and len({sum(s) for s in mir}) == 1
+
+
+def test_two_rank_gloo_interleaved_update_equals_single_rank(tmp_path, make_emu):
+    import torch.multiprocessing as mp
+    from anerend_b200 import layouts as L, make_params, scenes
+    import __graft_entry__ as g
+    g.build_host_emu()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker_interleaved, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    nxz, ny, nr = 4, 4, 64
+    scene = scenes.random_soup(52, ntris=400, grid=(nxz, ny, nr))
+    h = make_emu(make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS))
+    h.upload_scene(scene)
+    h.set_scene_ubo(scene.ubo)
+    h.build_accel()
+    rots = h.rotations(scenes.rotation_sequence(9, ny))
+    for it in range(4):
+        h.update(-1, rots)
+    want = h.download_atlas()
+    a0, a1 = np.load(tmp_path / "atlas_i0.npy"), np.load(tmp_path / "atlas_i1.npy")
+    assert np.array_equal(a0, a1) and np.array_equal(a0, want)
+
+
 def test_two_rank_gloo_slab_update_equals_single_rank(tmp_path, make_emu):
     import torch.multiprocessing as mp
     from anerend_b200 import layouts as L, make_params, scenes
