@@ -77,7 +77,7 @@ struct anerend_ddgi {
   // wavefront (fast) path scratch: hit records, surface records, visibility masks, per-light shadow queues
   float4* dHits = nullptr; float4* dSurf = nullptr; uint32_t* dLit = nullptr; uint32_t* dQueues = nullptr; uint32_t* dQcount = nullptr;
   uint32_t* dHitq = nullptr; float4* dShadeTris = nullptr; float* dConvW = nullptr;
-  size_t fastRays = 0; uint32_t fastQueues = 0; int gridPrimary[2] = {0, 0}, gridShadow[2] = {0, 0}; uint32_t tune[4] = {0, 0, 0, 0}; int sms = 0;
+  size_t fastRays = 0; uint32_t fastQueues = 0; int gridPrimary[2] = {0, 0}, gridShadow[2] = {0, 0}; uint32_t tune[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int sms = 0;
 
   int currentLayer = 0;                                    // IrradianceProbeRayTracingPass::_currentLayer
   int lastProbeIdx[2] = {0, 0};                            // IrradianceProbeTranslationPass::_lastProbeIdx
@@ -290,24 +290,23 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
     BE_CHECK(h, be.ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<false, true>, 128, 0))); h->gridPrimary[1] = sms * (nb > 0 ? nb : 1);
     BE_CHECK(h, be.ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<true, false>, 128, 0))); h->gridShadow[0] = sms * (nb > 0 ? nb : 1);
     BE_CHECK(h, be.ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<true, true>, 128, 0))); h->gridShadow[1] = sms * (nb > 0 ? nb : 1);
-    h->tune[0] = TUNE_TRI_TRIGGER; h->tune[1] = 0; h->tune[2] = 0; h->tune[3] = 0;
+    h->tune[0] = TUNE_NODE_STEPS; h->tune[1] = TUNE_REFILL_MIN; h->tune[2] = TUNE_REFILL_MIN; h->tune[3] = 0;
+    h->tune[4] = TUNE_STEP_MIN; h->tune[5] = TUNE_TRI_MIN; h->tune[6] = 0; h->tune[7] = 0;
     if (const char* e = getenv("DDGI_TUNE")) {          // kernel-tuning sweeps only (tools/); not part of the ABI
-      unsigned v[4] = {h->tune[0], h->tune[1], h->tune[2], h->tune[3]};
-      sscanf(e, "%u,%u,%u,%u", &v[0], &v[1], &v[2], &v[3]);
-      for (int k = 0; k < 4; ++k) h->tune[k] = v[k];
+      unsigned v[8]; for (int k = 0; k < 8; ++k) v[k] = h->tune[k];
+      sscanf(e, "%u,%u,%u,%u,%u,%u,%u,%u", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7]);
+      for (int k = 0; k < 8; ++k) h->tune[k] = v[k];
     }
   }
   FastCtx f{};
   f.t = c; f.shadeTris = h->dShadeTris; f.hits = h->dHits; f.surf = h->dSurf; f.lit = h->dLit; f.queues = h->dQueues; f.hitq = h->dHitq;
   f.qcount = h->dQcount; f.totalRays = n; f.numQueues = nq;
-  for (int k = 0; k < 4; ++k) f.tune[k] = h->tune[k];
+  for (int k = 0; k < 8; ++k) f.tune[k] = h->tune[k];
   f.tune[3] = 0x64646464u;                 // planes2: the PRMT constant travels as a kernel argument so the selector can be the immediate
   BE_CHECK(h, be.zero(h->dQcount, FAST_QC_SIZE * sizeof(uint32_t)));
   const bool cnt = (h->p.flags & ANEREND_DDGI_FLAG_COUNTERS) != 0;
   const uint32_t blocks = (n + PREP_BLOCK - 1u) / PREP_BLOCK;
-  int gp = h->gridPrimary[cnt ? 1 : 0], gs = h->gridShadow[cnt ? 1 : 0];
-  if (h->tune[1]) gp = std::min(gp, h->sms * (int)h->tune[1]);      // blocks per SM caps (tail effect vs latency hiding)
-  if (h->tune[2]) gs = std::min(gs, h->sms * (int)h->tune[2]);
+  const int gp = h->gridPrimary[cnt ? 1 : 0], gs = h->gridShadow[cnt ? 1 : 0];
   if (cnt) k_trace<false, true><<<gp, 128, 0, be.stream>>>(f); else k_trace<false, false><<<gp, 128, 0, be.stream>>>(f);
   k_shade_prep<<<blocks, PREP_BLOCK, 0, be.stream>>>(f);
   if (cnt) k_trace<true, true><<<gs, 128, 0, be.stream>>>(f); else k_trace<true, false><<<gs, 128, 0, be.stream>>>(f);

@@ -19,7 +19,10 @@
 namespace ddgi {
 
 // Tunables of the persistent traversal kernels (FastCtx::tune; DDGI_TUNE="a,b,c" overrides them for sweeps)
-#define TUNE_TRI_TRIGGER 0          // run a triangle round when at least this many lanes hold untested triangles
+#define TUNE_NODE_STEPS 3           // box-test steps per loop iteration before the triangle rounds
+#define TUNE_REFILL_MIN 4           // refill from the staged batch once this many lanes are idle
+#define TUNE_STEP_MIN 16            // (nodeSteps > 1) keep stepping only while this many lanes can
+#define TUNE_TRI_MIN 8              // (nodeSteps > 1) keep running triangle rounds only while this many lanes hold triangles
 #define FAST_CHUNK 64               // ray indices taken per atomic on the global cursor (two staged batches)
 
 // Node-phase state of a ray lives in registers; everything only the triangle rounds touch (direction, parked triangle
@@ -151,7 +154,8 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
   uint32_t* cursor = &c.qcount[ANY ? FAST_QC_SHADOW : FAST_QC_PRIMARY];
   const int P = t.nXZ * t.nXZ;
   const V3 sunL = normalize3(-t.lightDir);
-  const uint32_t triTrigger = c.tune[0];
+  const uint32_t nodeSteps = max(1u, c.tune[0]), refillMin = max(1u, ANY ? c.tune[2] : c.tune[1]);
+  const uint32_t stepMin = max(1u, c.tune[4]), triMin = max(1u, c.tune[5]);
   const uint32_t k64 = c.tune[3];          // 0x64646464, opaque to ptxas on purpose (see planes2)
   float4* myDir = &sLane[warp][LS_DIR][lane];
   float4* myRes = &sLane[warp][LS_RES][lane];
@@ -165,6 +169,7 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
   for (;;) {
     // ---------------------------------------------------------------- refill idle lanes from the staged batch
     uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
+    if ((uint32_t)__popc(idle) < refillMin) idle = 0u;
     while (idle && !(exhausted && staged == 0u)) {
       if (staged == 0u) {
         if (chunkNext == chunkEnd) {
@@ -224,26 +229,26 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
     }
     if (__ballot_sync(0xFFFFFFFFu, active) == 0u) { if (exhausted && staged == 0u) break; else continue; }
 
-    // ---------------------------------------------------------------- node phase: lanes with a free parking slot
+    // ---------------------------------------------------------------- node phase: up to `nodeSteps` box-test steps for
+    // the lanes that have a node to visit and a free parking slot; stops early when too few lanes can still step
     bool finished = false;
-    if (active && r.npend < 2u) {
-      if ((r.ng.y & 0xFF000000u) == 0u) {
-        if (r.sp > 0) r.ng = stack[--r.sp];
-        else finished = (r.npend == 0u);
+    for (uint32_t k = 0;;) {
+      const bool hasNode = (r.ng.y & 0xFF000000u) != 0u || r.sp > 0;
+      if (active && !finished) {
+        if (hasNode && r.npend < 2u) {
+          if ((r.ng.y & 0xFF000000u) == 0u) r.ng = stack[--r.sp];
+          const uint4 tg = node_step(t.nodes, r, stack, t.tmin, k64);
+          if (CNT) ++cn;
+          if (tg.y) { myPend[32u * r.npend] = tg; ++r.npend; }
+        } else if (!hasNode && r.npend == 0u) finished = true;
       }
-      if (r.ng.y & 0xFF000000u) {
-        const uint4 tg = node_step(t.nodes, r, stack, t.tmin, k64);
-        if (CNT) ++cn;
-        if (tg.y) { myPend[32u * r.npend] = tg; ++r.npend; }
-      }
+      if (++k >= nodeSteps) break;
+      const uint32_t can = __ballot_sync(0xFFFFFFFFu, active && !finished && r.npend < 2u && ((r.ng.y & 0xFF000000u) != 0u || r.sp > 0));
+      if ((uint32_t)__popc(can) < stepMin) break;
     }
-    // ---------------------------------------------------------------- vote: one triangle round?
-    const uint32_t pend = __ballot_sync(0xFFFFFFFFu, active && r.npend != 0u);
-    bool doTri = pend != 0u;
-    if (doTri && triTrigger > 1u && (uint32_t)__popc(pend) < triTrigger)
-      doTri = __ballot_sync(0xFFFFFFFFu, active && r.npend < 2u && ((r.ng.y & 0xFF000000u) != 0u || r.sp > 0)) == 0u;
-    if (doTri) {
-      if (active && r.npend != 0u) {
+    // ---------------------------------------------------------------- triangle rounds: one parked triangle per lane and round
+    for (uint32_t pend = __ballot_sync(0xFFFFFFFFu, active && !finished && r.npend != 0u); pend != 0u;) {
+      if (active && !finished && r.npend != 0u) {
         uint4 g = myPend[0];
         const int b = __ffs((int)g.y) - 1;
         const float4* tp = t.bvhTris + 3 * (size_t)(g.x + (uint32_t)__popc(g.z & ((1u << b) - 1u)));
@@ -266,6 +271,10 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
         }
         if (!finished) finished = r.npend == 0u && (r.ng.y & 0xFF000000u) == 0u && r.sp == 0;
       }
+      if (nodeSteps <= 1u) break;
+      pend = __ballot_sync(0xFFFFFFFFu, active && !finished && r.npend != 0u);
+      if ((uint32_t)__popc(pend) < triMin &&
+          __ballot_sync(0xFFFFFFFFu, active && !finished && r.npend < 2u && ((r.ng.y & 0xFF000000u) != 0u || r.sp > 0)) != 0u) break;
     }
     // ---------------------------------------------------------------- results
     if (active && finished) {

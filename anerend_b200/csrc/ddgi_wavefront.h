@@ -44,7 +44,7 @@ struct FastCtx {
   uint32_t* hitq;           // [rays] compacted indices of the rays that hit (k_shade runs over these with full warps)
   uint32_t* qcount;         // FAST_QC_SIZE counters
   uint32_t totalRays, numQueues;
-  uint32_t tune[4];         // [0] triangle-round trigger (lanes holding untested triangles), [3] = 0x64646464 (planes2)
+  uint32_t tune[8];         // loop tunables (ddgi_fast.cuh TUNE_*); [3] = 0x64646464 (planes2)
 };
 
 // W[layer][ray][texel] = max(0, dot(half(dir), octDir(texel))), zero where <= 1e-6 (probe_conv.comp:53-58).  The

@@ -47,6 +47,17 @@ def mirrored_slabs_for_rank(num_probes_y, rank, world):
     return list(range(rank * k, (rank + 1) * k)) + list(range(half + (world - 1 - rank) * k, half + (world - rank) * k))
 
 
+_STAGING = {}
+
+
+def _staging(like, numel):
+    key = (like.device, like.dtype, numel)
+    if key not in _STAGING:
+        import torch
+        _STAGING[key] = torch.empty(numel, dtype=like.dtype, device=like.device)
+    return _STAGING[key]
+
+
 def all_gather_atlas_mirrored(atlas, num_probes_xz, num_probes_y, rank, world, group=None):
     """Exchange for `mirrored_slabs_for_rank`: an in-place all_gather_into_tensor of the lower half of the atlas rows and
     an all_gather of the upper half whose output blocks are the row ranges in reversed rank order."""
@@ -61,8 +72,11 @@ def all_gather_atlas_mirrored(atlas, num_probes_xz, num_probes_y, rank, world, g
     lo, hi = a[:half_rows], a[half_rows:]
     b = rank * k * rows
     dist.all_gather_into_tensor(lo.reshape(-1), lo[b:b + k * rows].reshape(-1), group=group)
-    blocks = [hi[(world - 1 - r) * k * rows:(world - r) * k * rows] for r in range(world)]
-    dist.all_gather(blocks, blocks[rank].clone(), group=group)
+    # upper half: rank r owns block R-1-r; gather into a staging buffer in rank order, then one flipped block copy
+    b = (world - 1 - rank) * k * rows
+    staging = _staging(a, hi.numel())
+    dist.all_gather_into_tensor(staging, hi[b:b + k * rows].reshape(-1), group=group)
+    hi.view(world, -1).copy_(staging.view(world, -1).flip(0))
     return atlas
 
 
