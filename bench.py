@@ -5,6 +5,8 @@ A "step" is one full-grid DDGI probe update (translate if needed -> trace+shade 
 synthetic workload:
     c3 (default at N=1): Sponza-scale mesh (~262k tris, 64 materials, 8 lights), 24x12x24 probes x 256 rays + shadow rays
     c5 (default at N>1): large volume (~2M tris), 64x32x64 probes x 256 rays, probe layers dealt to the ranks + atlas all-gather
+    c4                 : camera-scroll sequence: c3 + 16 moving rigid nodes; every step = new camera UBO (x: -8 -> +8 over 120
+                         steps at 30 Hz sim time), BVH refit of the moved nodes, probe-grid translation, full-grid update
     c2                 : Cornell box (~10k tris), 16x8x16 probes x 128 rays
 `value` = primary probe rays of all ranks / device time (CUDA events on the handle's stream, max over ranks), inputs
 resident in HBM.  `e2e` = the same through the public API with host buffers: per step the scene UBO + rotation matrices
@@ -33,6 +35,8 @@ def build_workload(name):
         return scenes.cornell_box(), (16, 8, 128), 2
     if name == "c3":
         return scenes.sponza_like(), (24, 12, 256), 3
+    if name == "c4":
+        return scenes.sponza_like(seed=4, movers=16), (24, 12, 256), 4
     if name == "c5":
         return scenes.large_volume(), (64, 32, 256), 5
     raise SystemExit(f"unknown workload {name}")
@@ -154,7 +158,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=None, choices=[None, "c2", "c3", "c5"])
+    ap.add_argument("--workload", default=None, choices=[None, "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fast-math", action="store_true", help="time the FAST_MATH build as the headline (default: exact build)")
     ap.add_argument("--no-alt", action="store_true", help="skip the second-build and 1-GPU strong-scaling-base measurements")
@@ -196,6 +200,10 @@ def main():
     seq = scenes.rotation_sequence(seed, ny * total_steps)
     all_rays = nxz * nxz * ny * nr
 
+    if name == "c4":
+        c4_ubos = [scene.with_camera(np.array([-8.0 + 16.0 * k / 120.0, 5.0, 0.0])) for k in range(120)]
+        c4_rend = [scene.animated_renderables(k / 30.0) for k in range(120)]
+
     def make_handle(hflags, hslab):
         hh = A.Ddgi(A.make_params(nxz, ny, nr, flags=hflags, slab=hslab, device=local_rank))
         hh.upload_scene(scene)
@@ -224,7 +232,11 @@ def main():
         atlas_t = torch.as_tensor(sharding.DeviceArray(ptr, (hh.atlas_height, hh.atlas_width, 4)), device=dev)
 
         def step(k):
-            hh.set_scene_ubo(scene.ubo)
+            if name == "c4":                     # camera scroll + moving nodes (host renderable buffer -> refit -> translate)
+                hh.set_scene_ubo(c4_ubos[k % 120])
+                hh.refit_accel(c4_rend[k % 120])
+            else:
+                hh.set_scene_ubo(scene.ubo)
             hh.translate()
             if do_gather and interleaved:
                 hh.update_layers(my_layers, rots[k])
