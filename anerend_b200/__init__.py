@@ -56,5 +56,19 @@ class Ddgi(DdgiHandle):
         arr = (_C.c_void_p * len(ptrs))(*ptrs)
         self._call("set_peer_atlases", arr, _C.c_uint32(len(ptrs)))
 
+    def exchange_export(self):
+        blob = _C.create_string_buffer(128)
+        self._call("exchange_export", blob, _C.c_size_t(128))
+        return blob.raw
+
+    def exchange_connect(self, blobs, world, rank):
+        """`blobs`: the exchange_export() results of all ranks, in rank order."""
+        data = b"".join(blobs)
+        assert len(data) == 128 * world
+        self._call("exchange_connect", _C.c_char_p(data), _C.c_uint32(world), _C.c_uint32(rank))
+
+    def exchange_disconnect(self):
+        self._call("exchange_disconnect")
+
     def refit_accel_device(self, d_ptr, count):
         self._call("refit_accel_device", _C.c_void_p(d_ptr), _C.c_uint32(count))

@@ -74,6 +74,11 @@ struct anerend_ddgi {
   std::vector<float> fib;                                  // N*3
   std::vector<uint8_t> layerTraced;
   uint2* peers[8] = {nullptr}; int numPeers = 0;
+  // fused atlas exchange over NVLink peer memory (exchange_export/connect): arrival flags of the device-side barrier
+  uint32_t* dXflags = nullptr; uint32_t* dXerr = nullptr;   // own flags [8] (written by the peers), sticky time-out flag
+  uint32_t* xflags[8] = {nullptr};                          // flag arrays of all ranks, own included, by rank
+  void* xopened[16] = {nullptr}; int numOpened = 0;         // cudaIpc mappings to close
+  uint32_t xrank = 0, xworld = 0, xepoch = 0;
   // wavefront (fast) path scratch: hit records, surface records, visibility masks, per-light shadow queues
   float4* dHits = nullptr; float4* dSurf = nullptr; uint32_t* dLit = nullptr; uint32_t* dQueues = nullptr; uint32_t* dQcount = nullptr;
   uint32_t* dHitq = nullptr; float4* dShadeTris = nullptr; float* dConvW = nullptr;
@@ -317,6 +322,59 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
 }
 #endif
 
+#ifndef DDGI_HOST_EMU
+// Cross-GPU barrier between the ranks of a connected exchange: thread r announces this rank's arrival in rank r's flag
+// array (a store through the NVLink-mapped pointer), then waits until rank r has announced itself here.  All ranks issue
+// the same sequence of barriers, so `epoch` is the same number everywhere; flags only grow.  A rank that never arrives
+// (a crashed peer) trips the time-out instead of hanging the GPU.
+struct PeerBarrierCtx { uint32_t* flags[8]; uint32_t* err; uint32_t rank, world, epoch; unsigned long long timeoutNs; };
+__global__ void __launch_bounds__(32) k_peer_barrier(const PeerBarrierCtx b) {
+  const uint32_t r = threadIdx.x;
+  if (r < b.world) {
+    __threadfence_system();                                   // this rank's earlier stores (peer atlases) before the flag
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(b.flags[r] + b.rank), "r"(b.epoch) : "memory");
+    const uint32_t* mine = b.flags[b.rank] + r;
+    unsigned long long t0, t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if ((int32_t)(v - b.epoch) >= 0) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > b.timeoutNs) { *b.err = 1u + r; break; }
+      __nanosleep(200);
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+}
+int peerBarrier(anerend_ddgi* h) {
+  if (h->xworld < 2) return 0;
+  PeerBarrierCtx b{};
+  for (uint32_t r = 0; r < h->xworld; ++r) b.flags[r] = h->xflags[r];
+  b.err = h->dXerr; b.rank = h->xrank; b.world = h->xworld; b.epoch = ++h->xepoch; b.timeoutNs = 30ull * 1000000000ull;
+  k_peer_barrier<<<1, 32, 0, h->be.stream>>>(b);
+  ++h->be.launches;
+  BE_CHECK(h, h->be.check());
+  return 0;
+}
+int peerCheck(anerend_ddgi* h) {        // after a stream sync: did a barrier time out?
+  if (h->xworld < 2) return 0;
+  uint32_t e = 0;
+  BE_CHECK(h, h->be.d2h(&e, h->dXerr, sizeof(e)));
+  if (e) return fail(h, ANEREND_DDGI_E_STATE, "exchange barrier timed out waiting for rank " + std::to_string(e - 1));
+  return 0;
+}
+void exchangeDisconnect(anerend_ddgi* h) {
+  h->be.sync();
+  for (int i = 0; i < h->numOpened; ++i) if (h->xopened[i]) cudaIpcCloseMemHandle(h->xopened[i]);
+  h->numOpened = 0; h->numPeers = 0; h->xworld = 0; h->xrank = 0;
+  for (auto& f : h->xflags) f = nullptr;
+}
+#else
+int peerBarrier(anerend_ddgi*) { return 0; }
+int peerCheck(anerend_ddgi*) { return 0; }
+void exchangeDisconnect(anerend_ddgi*) {}
+#endif
+
 // `layers`: the absolute layers of this launch (any subset of the grid, each at most once); rots + 16*rotStride*i is
 // the randomRot of layers[i] (rotStride 0: one matrix, 1: packed per launched layer; rotsByLayer: indexed by absolute layer)
 int traceLayers(anerend_ddgi* h, const int* layers, int numLayers, const float* rots, bool rotsByLayer) {
@@ -419,6 +477,8 @@ void destroyHandle(anerend_ddgi* h) {
   if (!h) return;
   Backend& be = h->be;
   be.sync();
+  exchangeDisconnect(h);
+  be.free(h->dXflags); be.free(h->dXerr);
   freeAccel(h); freeScene(h);
   be.free(h->dAtlas); be.free(h->dTemp); be.free(h->dRayIrr); be.free(h->dDirs); be.freeHostPinned(h->hDirs); be.free(h->dRayOrder);
   be.free(h->dLayerMap); be.freeHostPinned(h->hLayerMap);
@@ -491,7 +551,7 @@ int DDGI_API(reset)(anerend_ddgi_t* h) {
   return clearAtlas(h);
 }
 const char* DDGI_API(last_error)(const anerend_ddgi_t* h) { return h ? h->err.c_str() : "null handle"; }
-int DDGI_API(sync)(anerend_ddgi_t* h) { BE_CHECK(h, h->be.sync()); return 0; }
+int DDGI_API(sync)(anerend_ddgi_t* h) { BE_CHECK(h, h->be.sync()); return peerCheck(h); }
 
 int DDGI_API(upload_scene)(anerend_ddgi_t* h,
     const anerend_vertex_t* vertices, uint32_t nv, const uint32_t* indices, uint32_t ni,
@@ -606,7 +666,9 @@ int DDGI_API(update)(anerend_ddgi_t* h, int32_t layer, const float* rots) {
   int rc = traceLayers(h, layers.data(), (int)layers.size(), rots, layer < 0);
   h->be.mark(2); h->timed[1] = true;
   if (rc) return rc;
+  if ((rc = peerBarrier(h))) return rc;          // connected exchange: every rank has finished reading the previous atlas
   rc = convolveLayers(h, layers.data(), (int)layers.size());
+  if (!rc) rc = peerBarrier(h);                  // ... and every rank's texels have landed in this atlas
   h->be.mark(3); h->timed[2] = true;
   return rc;
 }
@@ -622,7 +684,9 @@ int DDGI_API(update_layers)(anerend_ddgi_t* h, const int32_t* layerList, uint32_
   int rc = traceLayers(h, layerList, (int)n, rots, true);
   h->be.mark(2); h->timed[1] = true;
   if (rc) return rc;
+  if ((rc = peerBarrier(h))) return rc;
   rc = convolveLayers(h, layerList, (int)n);
+  if (!rc) rc = peerBarrier(h);
   h->be.mark(3); h->timed[2] = true;
   return rc;
 }
@@ -655,6 +719,50 @@ int DDGI_API(set_peer_atlases)(anerend_ddgi_t* h, void* const* peers, uint32_t n
   for (uint32_t i = 0; i < n; ++i) h->peers[i] = (uint2*)peers[i];
   h->numPeers = (int)n; return 0;
 }
+int DDGI_API(exchange_export)(anerend_ddgi_t* h, void* blob, size_t bytes) {
+#ifndef DDGI_HOST_EMU
+  if (!blob || bytes != ANEREND_DDGI_EXCHANGE_BLOB_BYTES) return fail(h, ANEREND_DDGI_E_INVALID, "exchange blob size mismatch");
+  static_assert(2 * sizeof(cudaIpcMemHandle_t) == ANEREND_DDGI_EXCHANGE_BLOB_BYTES, "blob = two cudaIpcMemHandle_t");
+  Backend& be = h->be;
+  if (!h->dXflags) {
+    BE_CHECK(h, be.alloc(&h->dXflags, 64)); BE_CHECK(h, be.alloc(&h->dXerr, 1));
+    BE_CHECK(h, be.zero(h->dXflags, 64 * sizeof(uint32_t))); BE_CHECK(h, be.zero(h->dXerr, sizeof(uint32_t))); BE_CHECK(h, be.sync());
+  }
+  cudaIpcMemHandle_t hs[2];
+  BE_CHECK(h, be.ok(cudaIpcGetMemHandle(&hs[0], h->dAtlas))); BE_CHECK(h, be.ok(cudaIpcGetMemHandle(&hs[1], h->dXflags)));
+  memcpy(blob, hs, sizeof(hs));
+  return 0;
+#else
+  (void)blob; (void)bytes; return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "no peer exchange in the host harness");
+#endif
+}
+int DDGI_API(exchange_connect)(anerend_ddgi_t* h, const void* blobs, uint32_t world, uint32_t rank) {
+#ifndef DDGI_HOST_EMU
+  if (!blobs || world < 2 || world > 8 || rank >= world) return fail(h, ANEREND_DDGI_E_INVALID, "exchange_connect: 2..8 ranks");
+  if (!h->dXflags) return fail(h, ANEREND_DDGI_E_STATE, "exchange_connect before exchange_export");
+  exchangeDisconnect(h);
+  Backend& be = h->be;
+  const cudaIpcMemHandle_t* hs = (const cudaIpcMemHandle_t*)blobs;
+  int np = 0;
+  for (uint32_t r = 0; r < world; ++r) {
+    if (r == rank) { h->xflags[r] = h->dXflags; continue; }
+    void *pa = nullptr, *pf = nullptr;
+    cudaIpcMemHandle_t a, f; memcpy(&a, &hs[2 * r], sizeof(a)); memcpy(&f, &hs[2 * r + 1], sizeof(f));
+    if (!be.ok(cudaIpcOpenMemHandle(&pa, a, cudaIpcMemLazyEnablePeerAccess)) || !be.ok(cudaIpcOpenMemHandle(&pf, f, cudaIpcMemLazyEnablePeerAccess))) {
+      if (pa) cudaIpcCloseMemHandle(pa);
+      exchangeDisconnect(h);
+      return fail(h, ANEREND_DDGI_E_CUDA, std::string("cudaIpcOpenMemHandle: ") + be.errStr());
+    }
+    h->xopened[h->numOpened++] = pa; h->xopened[h->numOpened++] = pf;
+    h->peers[np++] = (uint2*)pa; h->xflags[r] = (uint32_t*)pf;
+  }
+  h->numPeers = np; h->xworld = world; h->xrank = rank;
+  return 0;
+#else
+  (void)blobs; (void)world; (void)rank; return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "no peer exchange in the host harness");
+#endif
+}
+int DDGI_API(exchange_disconnect)(anerend_ddgi_t* h) { exchangeDisconnect(h); return 0; }
 int DDGI_API(stream)(anerend_ddgi_t* h, void** s) { *s = (void*)h->be.stream; return 0; }
 
 int DDGI_API(ray_tile)(const anerend_ddgi_t* h, int32_t* sx, int32_t* sy) { *sx = h->Sx; *sy = h->Sy; return 0; }

@@ -162,6 +162,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fast-math", action="store_true", help="time the FAST_MATH build as the headline (default: exact build)")
     ap.add_argument("--no-alt", action="store_true", help="skip the second-build and 1-GPU strong-scaling-base measurements")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N>1: atlas exchange fused into the convolution over NVLink peer memory (default) or NCCL all-gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -204,14 +206,29 @@ def main():
         c4_ubos = [scene.with_camera(np.array([-8.0 + 16.0 * k / 120.0, 5.0, 0.0])) for k in range(120)]
         c4_rend = [scene.animated_renderables(k / 30.0) for k in range(120)]
 
-    def make_handle(hflags, hslab):
+    fused = world > 1 and args.exchange == "fused"
+
+    def make_handle(hflags, hslab, connect=False):
         hh = A.Ddgi(A.make_params(nxz, ny, nr, flags=hflags, slab=hslab, device=local_rank))
         hh.upload_scene(scene)
         hh.set_scene_ubo(scene.ubo)
         hh.build_accel()
+        if connect:                           # fused exchange: map every peer's atlas (cudaIpc over NVLink)
+            blobs = [None] * world
+            dist.all_gather_object(blobs, hh.exchange_export())
+            hh.exchange_connect(blobs, world, rank)
+            dist.barrier()
         return hh
 
-    h = make_handle(flags, slab)
+    def close_handle(hh, connected=False):
+        if connected:
+            hh.sync()
+            dist.barrier()
+            hh.exchange_disconnect()
+            dist.barrier()
+        hh.close()
+
+    h = make_handle(flags, slab, connect=fused)
     accel_ms = h.timings()["accel_ms"]
     info = h.bvh_info()
     rots = h.rotations(seq).reshape(total_steps, ny, 16)
@@ -238,7 +255,9 @@ def main():
             else:
                 hh.set_scene_ubo(scene.ubo)
             hh.translate()
-            if do_gather and interleaved:
+            if do_gather and fused:           # the convolution stores into every peer's atlas; barriers inside the call
+                hh.update_layers(my_layers, rots[k])
+            elif do_gather and interleaved:
                 hh.update_layers(my_layers, rots[k])
                 with torch.cuda.stream(stream):
                     if mirrored:
@@ -310,22 +329,41 @@ def main():
     # ---- second figure: the other arithmetic build (FAST_MATH <-> exact), same workload, fewer steps ----------
     alt = None
     if not args.no_alt:
-        ha = make_handle(flags ^ L.FLAG_FAST_MATH, slab)
+        ha = make_handle(flags ^ L.FLAG_FAST_MATH, slab, connect=fused)
         asteps = max(3, min(args.steps, 20))
         ams, art, acv, _, _ = timed(ha, asteps, 3, do_gather, world > 1)
         alt = {"build": "exact" if args.fast_math else "fast_math", "ms_per_step": ams / asteps,
                "value": all_rays / (ams / asteps * 1e-3) / 1e6, "unit": UNIT, "trace_ms": float(np.mean(art)),
                "convolve_ms": float(np.mean(acv)), "steps": asteps}
-        ha.close()
+        close_handle(ha, fused)
 
     # ---- strong-scaling base: the SAME workload on one GPU (rank 0 alone), so the N-GPU figure has its own denominator
     base1 = None
+    verified = None
     if world > 1 and not args.no_alt:
+        # exchange check: two updates from a cleared atlas on all ranks must give rank 0 the atlas ONE GPU computes
+        # (jacobi updates do not depend on how the layers are dealt; the exact build is bit-reproducible)
+        h.reset()
+        for k in range(2):
+            step(k)
+        h.sync()
+        dist.barrier()
         if rank == 0:
+            multi = np.empty_like(host_np)
+            h.download_atlas(multi)
             hb = make_handle(flags, (0, ny))
             bsteps = 3
             bms, _, _, _, _ = timed(hb, bsteps, 1, False, False)
             base1 = {"n_gpus": 1, "ms_per_step": bms / bsteps, "value": all_rays / (bms / bsteps * 1e-3) / 1e6, "unit": UNIT, "steps": bsteps}
+            if name != "c4":
+                hb.reset()
+                for k in range(2):
+                    hb.set_scene_ubo(scene.ubo)
+                    hb.translate()
+                    hb.update(-1, rots[k])
+                single = np.empty_like(host_np)
+                hb.download_atlas(single)
+                verified = {"updates": 2, "texels": int(single.size // 4), "mismatching_texels": int((multi != single).any(axis=-1).sum())}
             hb.close()
         dist.barrier()
 
@@ -365,7 +403,9 @@ def main():
         cfg = workload_desc(name, scene, grid, world)
         cfg.update({"l2": "flushed between timed iterations (256 MiB write)" if flush else "working set larger than L2, no flush",
                     "bvh8_nodes": int(info.num_nodes), "accel_build_ms": accel_ms,
-                    "atlas_exchange": ("2 in-place nccl all_gathers of mirrored slabs on the handle's stream" if mirrored else
+                    "atlas_exchange": ("fused: convolution stores each texel into all peers' atlases over NVLink (cudaIpc), "
+                                       "device-side barrier before and after; no collective" if fused else
+                                       "2 in-place nccl all_gathers of mirrored slabs on the handle's stream" if mirrored else
                                        "nccl all_gather of interleaved layers (pack, gather, scatter) on the handle's stream" if interleaved
                                        else "nccl all_gather of contiguous slabs, in place") if world > 1 else "none"})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -376,8 +416,8 @@ def main():
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "update_ms": {"trace": rt_avg, "convolve": float(np.mean(conv_ms)), "full_grid": ms_per_step},
                 "arithmetic": "fast_math (1e-4 relative per update)" if args.fast_math else "exact (atlas bit-identical to the oracle)",
-                "other_build": alt, "strong_scaling_base": base1}
-    h.close()
+                "other_build": alt, "strong_scaling_base": base1, "exchange_check_vs_1gpu": verified}
+    close_handle(h, fused)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

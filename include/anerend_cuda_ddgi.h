@@ -188,6 +188,19 @@ int anerend_cuda_ddgi_atlas_device_ptr(anerend_ddgi_t* h, void** d_ptr, size_t* 
 /* Fused atlas all-gather: device pointers to the peers' atlases (cudaIpc-opened or P2P-enabled).  When set,
  * the convolution stores every finished texel into all peers as well, replacing the separate collective. */
 int anerend_cuda_ddgi_set_peer_atlases(anerend_ddgi_t* h, void* const* d_peers, uint32_t num_peers);
+/* Fused atlas exchange between the ranks of one box (one process per GPU), replacing the NCCL all-gather of the
+ * slabs: every rank exports a blob (cudaIpc handles of its atlas and of its barrier flags), the
+ * blobs of all ranks — concatenated in rank order by whatever plumbing the host has (torch.distributed here) — are
+ * handed to _exchange_connect, which maps the peers' atlases over NVLink.  From then on _update/_update_layers run
+ *   trace -> device barrier (all ranks have read the previous atlas) -> convolution storing every finished texel into
+ *   the local atlas AND all peers' -> device barrier (all texels have landed),
+ * so the full atlas is assembled inside the convolution kernel, with no separate collective.  A barrier that waits
+ * longer than 30 s sets a sticky error reported by _sync.  _exchange_disconnect (all ranks, before any _destroy)
+ * unmaps the peers. */
+#define ANEREND_DDGI_EXCHANGE_BLOB_BYTES 128
+int anerend_cuda_ddgi_exchange_export(anerend_ddgi_t* h, void* blob, size_t bytes);
+int anerend_cuda_ddgi_exchange_connect(anerend_ddgi_t* h, const void* blobs, uint32_t world, uint32_t rank);
+int anerend_cuda_ddgi_exchange_disconnect(anerend_ddgi_t* h);
 /* CUDA stream (cudaStream_t) all work of this handle is issued on. */
 int anerend_cuda_ddgi_stream(anerend_ddgi_t* h, void** stream);
 

@@ -4,7 +4,7 @@
 TAG=${1:-sweep}; WL=${2:-c3}; shift; shift
 mkdir -p gpurun_out
 for T in $1; do
-  DDGI_TUNE=$T python bench.py --workload $WL --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/${TAG}_$T.json 2>/dev/null
+  DDGI_TUNE=$T python bench.py --workload $WL --steps 20 --warmup 5 --no-cpu-baseline --no-alt > gpurun_out/${TAG}_$T.json 2>/dev/null
   python - <<PY
 import json
 d=json.load(open("gpurun_out/${TAG}_$T.json"))
