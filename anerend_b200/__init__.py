@@ -40,7 +40,7 @@ class Ddgi(DdgiHandle):
         from .capi import Timings
         t = Timings()
         self._call("get_timings", _C.byref(t))
-        return {k: getattr(t, k) for k, _ in t._fields_}
+        return {k: (list(getattr(t, k)) if k == "rt_kernel_ms" else getattr(t, k)) for k, _ in t._fields_}
 
     def atlas_device_ptr(self):
         p, n = _C.c_void_p(), _C.c_size_t()

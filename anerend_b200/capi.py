@@ -19,7 +19,8 @@ class Params(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [("trans_ms", C.c_float), ("rt_ms", C.c_float), ("convolve_ms", C.c_float),
-                ("accel_ms", C.c_float), ("total_ms", C.c_float), ("kernel_launches", C.c_uint32)]
+                ("accel_ms", C.c_float), ("total_ms", C.c_float), ("kernel_launches", C.c_uint32),
+                ("rt_kernel_ms", C.c_float * 4)]
 
 
 class Stats(C.Structure):

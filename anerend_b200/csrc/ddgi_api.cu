@@ -87,7 +87,7 @@ struct anerend_ddgi {
   int currentLayer = 0;                                    // IrradianceProbeRayTracingPass::_currentLayer
   int lastProbeIdx[2] = {0, 0};                            // IrradianceProbeTranslationPass::_lastProbeIdx
   anerend_ddgi_timings_t timings{};
-  bool timed[4] = {false, false, false, false};
+  bool timed[4] = {false, false, false, false}; bool timedKernels = false;
   float accelMs = 0.0f;
 };
 
@@ -312,10 +312,16 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   const bool cnt = (h->p.flags & ANEREND_DDGI_FLAG_COUNTERS) != 0;
   const uint32_t blocks = (n + PREP_BLOCK - 1u) / PREP_BLOCK;
   const int gp = h->gridPrimary[cnt ? 1 : 0], gs = h->gridShadow[cnt ? 1 : 0];
+  be.mark(6);
   if (cnt) k_trace<false, true><<<gp, 128, 0, be.stream>>>(f); else k_trace<false, false><<<gp, 128, 0, be.stream>>>(f);
+  be.mark(7);
   k_shade_prep<<<blocks, PREP_BLOCK, 0, be.stream>>>(f);
+  be.mark(8);
   if (cnt) k_trace<true, true><<<gs, 128, 0, be.stream>>>(f); else k_trace<true, false><<<gs, 128, 0, be.stream>>>(f);
+  be.mark(9);
   BE_CHECK(h, be.ok((h->p.flags & ANEREND_DDGI_FLAG_FAST_MATH) ? launch_shade_fast(f, be.stream) : launch_shade_exact(f, be.stream)));
+  be.mark(10);
+  h->timedKernels = true;
   be.launches += 5;
   BE_CHECK(h, be.check());
   return 0;
@@ -488,7 +494,7 @@ void destroyHandle(anerend_ddgi* h) {
   delete h;
 }
 
-void beginCall(anerend_ddgi* h) { h->be.launches = 0; h->timed[0] = h->timed[1] = h->timed[2] = false; h->be.mark(0); }
+void beginCall(anerend_ddgi* h) { h->be.launches = 0; h->timed[0] = h->timed[1] = h->timed[2] = false; h->timedKernels = false; h->be.mark(0); }
 
 }  // namespace
 
@@ -800,6 +806,7 @@ int DDGI_API(get_timings)(anerend_ddgi_t* h, anerend_ddgi_timings_t* o) {
   if (h->timed[0]) o->trans_ms = h->be.elapsed(0, 1);
   if (h->timed[1]) o->rt_ms = h->be.elapsed(1, 2);
   if (h->timed[2]) o->convolve_ms = h->be.elapsed(2, 3);
+  if (h->timed[1] && h->timedKernels) for (int k = 0; k < 4; ++k) o->rt_kernel_ms[k] = h->be.elapsed(6 + k, 7 + k);
   if (h->timed[3]) { h->accelMs = h->be.elapsed(4, 5); h->timed[3] = false; }
   o->accel_ms = h->accelMs;
   o->total_ms = o->trans_ms + o->rt_ms + o->convolve_ms;

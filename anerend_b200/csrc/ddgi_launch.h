@@ -22,7 +22,7 @@
 namespace ddgi {
 struct Backend {
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[11] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // 6..10: kernels of the RT pass
   cudaEvent_t evCopy = nullptr; bool copyPending = false;
   uint32_t launches = 0;
   cudaError_t lastErr = cudaSuccess;
@@ -80,7 +80,7 @@ namespace ddgi {
 struct Backend {
   void* stream = nullptr;
   uint32_t launches = 0;
-  std::chrono::steady_clock::time_point tp[6];
+  std::chrono::steady_clock::time_point tp[11];
   const char* errStr() const { return "host emulation"; }
   bool init(int) { return true; }
   void destroy() {}

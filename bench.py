@@ -278,6 +278,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         rt, cv, nl = [], [], 0
+        hh.kernel_ms = []                        # per step: (closest-hit trace, shade_prep, any-hit trace, shade) in ms
         for k in range(steps):
             if flush:
                 with torch.cuda.stream(stream):
@@ -288,6 +289,7 @@ def main():
             t = hh.timings()                     # synchronises the handle's stream
             rt.append(t["rt_ms"])
             cv.append(t["convolve_ms"])
+            hh.kernel_ms.append(t["rt_kernel_ms"])
             nl += t["kernel_launches"]          # our kernels only (the NCCL collective and torch's pack/unpack copies are not counted)
         torch.cuda.synchronize()
         if multi:
@@ -369,7 +371,7 @@ def main():
 
     line = None
     if rank == 0:
-        # ---- roofline of the dominant kernel (k_probe_trace): counted, untimed run of the same update ----------
+        # ---- roofline of the dominant kernel: counted, untimed run of the same update ----------
         hc = make_handle(flags | L.FLAG_COUNTERS, slab)
         if interleaved:
             hc.update_layers(my_layers, rots[args.warmup])
@@ -378,19 +380,40 @@ def main():
         stats = hc.stats()
         hc.close()
         peak, peak_src = peaks()
+        # whole IrradianceProbeRT pass (4 launches): SURVEY.md §8(d) bytes / CUDA-event time of the pass
         abytes = algorithmic_bytes(stats, my_rays)
         rt_avg = float(np.mean(rt_ms))
-        achieved = abytes / (rt_avg * 1e-3) / 1e9
+        kms = np.mean(np.asarray(h.kernel_ms, dtype=np.float64), axis=0)      # live CUDA events around each launch
+        knames = ["k_trace<ANY=0> (closest hit)", "k_shade_prep", "k_trace<ANY=1> (any-hit shadow rays)", "k_shade"]
+        # dominant kernel = the any-hit traversal of the shadow-ray queues: 80 B per BVH8 node fetched + 48 B per
+        # triangle tested + per shadow ray 4 B queue entry, 16 B origin (surface record) and 4 B visibility word
+        kbytes = [80 * stats["primary_nodes_visited"] + 48 * stats["primary_tris_tested"] + my_rays * (16 + 16),
+                  None,
+                  80 * stats["shadow_nodes_visited"] + 48 * stats["shadow_tris_tested"] + stats["shadow_rays"] * 24,
+                  None]
+        dom = int(np.argmax(kms))
+        if kbytes[dom] is None:
+            dom = 2
+        achieved = kbytes[dom] / (kms[dom] * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(name, {}).get("k_probe_trace_dram_bytes_per_launch")
-        roofline = {"bound": "hbm", "kernel": "k_probe_trace", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            traffic = json.load(open(tpath)).get(name, {}).get("k_trace_any_dram_bytes_per_launch" if dom == 2 else
+                                                                "k_trace_closest_dram_bytes_per_launch")
+        roofline = {"bound": "hbm", "kernel": knames[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": abytes, "kernel_ms_avg": rt_avg,
-                    "kernel_share_of_step": rt_avg / ms_per_step,
+                    "algorithmic_bytes_per_launch": kbytes[dom], "kernel_ms_avg": float(kms[dom]),
+                    "kernel_share_of_step": float(kms[dom]) / ms_per_step,
+                    "kernels_ms_avg": {knames[i]: float(kms[i]) for i in range(4)},
+                    "rt_pass": {"launches": 4, "algorithmic_bytes": abytes, "ms_avg": rt_avg,
+                                "achieved": abytes / (rt_avg * 1e-3) / 1e9, "frac": abytes / (rt_avg * 1e-3) / 1e9 / peak,
+                                "share_of_step": rt_avg / ms_per_step},
+                    "note": "the traversal is L2-resident and instruction-issue bound (profiles/): HBM is the bound "
+                            "north_star names, not the limiter ncu shows",
                     "nodes_per_primary_ray": stats["primary_nodes_visited"] / max(1, stats["primary_rays"]),
                     "tris_per_primary_ray": stats["primary_tris_tested"] / max(1, stats["primary_rays"]),
+                    "nodes_per_shadow_ray": stats["shadow_nodes_visited"] / max(1, stats["shadow_rays"]),
+                    "tris_per_shadow_ray": stats["shadow_tris_tested"] / max(1, stats["shadow_rays"]),
                     "shadow_rays_per_primary": stats["shadow_rays"] / max(1, stats["primary_rays"]),
                     "hit_fraction": stats["primary_hits"] / max(1, stats["primary_rays"])}
         cpu_baseline = None

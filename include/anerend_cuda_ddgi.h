@@ -83,6 +83,7 @@ typedef struct anerend_ddgi_timings {
   float accel_ms;             /* last _build_accel/_refit_accel ("TLASUpdate"+"BLASUpdate")   */
   float total_ms;             /* first to last event of the last call                         */
   uint32_t kernel_launches;   /* kernels launched by the last call                            */
+  float rt_kernel_ms[4];      /* inside "IrradianceProbeRT": closest-hit trace, shade_prep, any-hit trace, shade */
 } anerend_ddgi_timings_t;
 
 /* Traversal statistics (ANEREND_DDGI_FLAG_COUNTERS); totals since the last _reset_stats. */
