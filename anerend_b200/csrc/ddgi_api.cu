@@ -27,6 +27,12 @@ DDGI_KERNEL(k_flatten_scene, flatten_tri_body, BuildCtx)
 DDGI_KERNEL(k_morton_codes, morton_body, BuildCtx)
 DDGI_KERNEL(k_lbvh_hierarchy, karras_body, BuildCtx)
 DDGI_KERNEL(k_lbvh_fit, fit_body, BuildCtx)
+DDGI_KERNEL(k_ploc_init, ploc_init_body, BuildCtx)
+DDGI_KERNEL(k_ploc_nn, ploc_nn_body, BuildCtx)
+DDGI_KERNEL(k_ploc_merge, ploc_merge_body, BuildCtx)
+DDGI_KERNEL(k_ploc_compact, ploc_compact_body, BuildCtx)
+DDGI_KERNEL(k_ploc_order, ploc_order_body, BuildCtx)
+DDGI_KERNEL(k_ploc_relabel, ploc_relabel_body, BuildCtx)
 DDGI_KERNEL(k_bvh8_collapse, collapse_body, BuildCtx)
 DDGI_KERNEL(k_refit_tris, refit_tris_body, BuildCtx)
 DDGI_KERNEL(k_refit_nodes, refit_node_body, BuildCtx)
@@ -88,7 +94,7 @@ struct anerend_ddgi {
   int lastProbeIdx[2] = {0, 0};                            // IrradianceProbeTranslationPass::_lastProbeIdx
   anerend_ddgi_timings_t timings{};
   bool timed[4] = {false, false, false, false}; bool timedKernels = false;
-  float accelMs = 0.0f;
+  float accelMs = 0.0f; int plocRounds = 0;
 };
 
 namespace {
@@ -214,9 +220,48 @@ int buildAccel(anerend_ddgi* h) {
   DDGI_LAUNCH(be, k_flatten_scene, flatten_tri_body, n, c, 256);
   DDGI_LAUNCH(be, k_morton_codes, morton_body, n, c, 256);
   if (!be.sortPairs(keys, skeys, ids, sids, n)) { freeScratch(); return fail(h, ANEREND_DDGI_E_CUDA, std::string("radix sort: ") + be.errStr()); }
-  BE_CHECK(h, be.zero(h->dVisit, ((size_t)n + 1) * sizeof(uint32_t)));
-  if (n > 1) DDGI_LAUNCH(be, k_lbvh_hierarchy, karras_body, n - 1, c, 256);
-  DDGI_LAUNCH(be, k_lbvh_fit, fit_body, n, c, 256);
+  uint32_t plocRadius = PLOC_RADIUS;
+  if (const char* e = getenv("DDGI_PLOC_RADIUS")) plocRadius = (uint32_t)atoi(e);     // builder sweeps only (0 = plain LBVH); not part of the ABI
+  if (plocRadius == 0) {
+    BE_CHECK(h, be.zero(h->dVisit, ((size_t)n + 1) * sizeof(uint32_t)));
+    if (n > 1) DDGI_LAUNCH(be, k_lbvh_hierarchy, karras_body, n - 1, c, 256);
+    DDGI_LAUNCH(be, k_lbvh_fit, fit_body, n, c, 256);
+  } else {
+    // PLOC over the Morton order; scratch: two cluster arrays, neighbour / keep / scan words, subtree counts
+    uint32_t *clRef[2] = {nullptr, nullptr}, *nn = nullptr, *keep = nullptr, *pos = nullptr, *sub = nullptr; float4 *clLo[2] = {nullptr, nullptr}, *clHi[2] = {nullptr, nullptr};
+    void* scanTmp = nullptr; const size_t scanBytes = be.scanTempBytes(n);
+    bool okA = be.alloc(&clRef[0], n) && be.alloc(&clRef[1], n) && be.alloc(&clLo[0], n) && be.alloc(&clLo[1], n) && be.alloc(&clHi[0], n) && be.alloc(&clHi[1], n) &&
+               be.alloc(&nn, n) && be.alloc(&keep, n) && be.alloc(&pos, n) && be.alloc(&sub, 2 * (size_t)n) && be.alloc((uint8_t**)&scanTmp, scanBytes);
+    auto freePloc = [&]() { for (int k = 0; k < 2; ++k) { be.free(clRef[k]); be.free(clLo[k]); be.free(clHi[k]); } be.free(nn); be.free(keep); be.free(pos); be.free(sub); be.free(scanTmp); };
+    uint32_t zero = 0;      // parent[] = MISS everywhere: the root (ref 0) keeps it
+    bool okP = okA && be.fill(parent, 0xFF, 2 * (size_t)n * sizeof(uint32_t)) && be.h2d(h->dCounters + 3, &zero, sizeof(uint32_t));
+    c.clNN = nn; c.clKeep = keep; c.clPos = pos; c.subCount = sub; c.plocRadius = plocRadius;
+    c.clRef = clRef[0]; c.clLo = clLo[0]; c.clHi = clHi[0];
+    if (okP) DDGI_LAUNCH(be, k_ploc_init, ploc_init_body, n, c, 256);
+    uint32_t m = n, merged = 0; int cur = 0, rounds = 0;
+    while (okP && m > 1) {
+      c.numClusters = m;
+      c.clRef = clRef[cur]; c.clLo = clLo[cur]; c.clHi = clHi[cur]; c.clRefOut = clRef[cur ^ 1]; c.clLoOut = clLo[cur ^ 1]; c.clHiOut = clHi[cur ^ 1];
+      DDGI_LAUNCH(be, k_ploc_nn, ploc_nn_body, m, c, 128);
+      DDGI_LAUNCH(be, k_ploc_merge, ploc_merge_body, m, c, 128);
+      okP = be.exclusiveSum(scanTmp, scanBytes, keep, pos, m);
+      DDGI_LAUNCH(be, k_ploc_compact, ploc_compact_body, m, c, 256);
+      uint32_t total = 0;
+      okP = okP && be.check() && be.d2h(&total, h->dCounters + 3, sizeof(uint32_t));
+      if (total <= merged) { okP = false; break; }     // no mutual pair: cannot happen with a consistent tie-break
+      m -= total - merged; merged = total; cur ^= 1; ++rounds;
+    }
+    if (okP) {
+      c.leafMap = keys; c.orderedIds = ids;            // the unsorted key/id arrays are free after the sort
+      DDGI_LAUNCH(be, k_ploc_order, ploc_order_body, 2 * n - 1, c, 256);
+      if (n > 1) DDGI_LAUNCH(be, k_ploc_relabel, ploc_relabel_body, n - 1, c, 256);
+      c.sortedIds = ids;
+      okP = be.check() && be.sync();
+    }
+    freePloc();
+    if (!okP) { freeScratch(); return fail(h, ANEREND_DDGI_E_CUDA, std::string("ploc build: ") + be.errStr()); }
+    h->plocRounds = rounds;
+  }
   // collapse, one launch per BVH8 level
   uint32_t counters[3] = {1u, 0u, 0u};
   BE_CHECK(h, be.h2d(h->dCounters, counters, sizeof(counters)));

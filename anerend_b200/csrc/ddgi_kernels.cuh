@@ -41,6 +41,7 @@ HD int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 #define DDGI_PI 3.14159265359f
 #define DDGI_MISS 0xFFFFFFFFu
+#define PLOC_RADIUS 16            // search window of the PLOC builder (positions either side in Morton order)
 
 // ----------------------------------------------------------------------------------------------------
 // device-side scene representation
@@ -70,6 +71,13 @@ struct BuildCtx {
   uint32_t* counters;         // [0] BVH8 nodes allocated, [1] triangle slots allocated, [2] next queue length
   const CItem* qin; CItem* qout;
   float4* shadeTris;          // [numTris][5] object-space shading record (ddgi_wavefront.h ShadeTri) or null
+  // PLOC (parallel locally-ordered clustering) state: clusters in Morton order, double-buffered across the compaction
+  uint32_t* clRef; float4* clLo; float4* clHi;              // current clusters: binary ref + box
+  uint32_t* clRefOut; float4* clLoOut; float4* clHiOut;     // compacted clusters of the next iteration
+  uint32_t* clNN; uint32_t* clKeep; const uint32_t* clPos;  // nearest neighbour, survives-this-round flag, its exclusive scan
+  uint32_t* subCount;         // triangles below each of the 2n-1 binary refs
+  uint32_t* leafMap; uint32_t* orderedIds;                  // Morton position -> depth-first position; triangle ids in that order
+  uint32_t numClusters, plocRadius;
 };
 
 // ----------------------------------------------------------------------------------------------------
@@ -217,6 +225,73 @@ HD void fit_body(uint32_t leaf, const BuildCtx& c) {
     memFence();
     p = c.parent[p];
   }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// PLOC (Meister & Bittner 2018): agglomerative clustering restricted to a window of the Morton order.  Every round each
+// cluster finds the neighbour within `plocRadius` positions whose union has the smallest surface area; mutual pairs
+// merge into a new binary node; survivors are compacted (order kept) for the next round.  Produces the same arrays as
+// the Karras hierarchy (left/right/parent/boxes/ranges) with a markedly lower SAH cost.  Internal refs are handed out
+// downwards from n-2, so the last merge — the root — is ref 0, as the collapse expects.
+// ----------------------------------------------------------------------------------------------------
+HD void ploc_init_body(uint32_t i, const BuildCtx& c) {
+  uint32_t gid = c.sortedIds[i], ref = c.numTris - 1u + i;
+  c.clRef[i] = ref; c.clLo[i] = c.triLo[gid]; c.clHi[i] = c.triHi[gid];
+  c.subCount[ref] = 1u;
+}
+HD float ploc_union_area(float4 alo, float4 ahi, float4 blo, float4 bhi) {
+  float ex = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x), ey = fmaxf(ahi.y, bhi.y) - fminf(alo.y, blo.y), ez = fmaxf(ahi.z, bhi.z) - fminf(alo.z, blo.z);
+  return ex * ey + ey * ez + ez * ex;
+}
+HD void ploc_nn_body(uint32_t i, const BuildCtx& c) {
+  const int m = (int)c.numClusters, r = (int)c.plocRadius, ii = (int)i;
+  const float4 lo = c.clLo[i], hi = c.clHi[i];
+  int b = ii - r < 0 ? 0 : ii - r, e = ii + r > m - 1 ? m - 1 : ii + r;
+  float best = 3.0e38f; int bj = ii;
+  for (int j = b; j <= e; ++j) {             // ascending j + strict '<': ties go to the lower index, which guarantees a mutual pair
+    if (j == ii) continue;
+    float a = ploc_union_area(lo, hi, c.clLo[j], c.clHi[j]);
+    if (a < best) { best = a; bj = j; }
+  }
+  c.clNN[i] = (uint32_t)bj;
+}
+HD void ploc_merge_body(uint32_t i, const BuildCtx& c) {
+  uint32_t j = c.clNN[i];
+  if (j == i || c.clNN[j] != i) { c.clKeep[i] = 1u; return; }
+  if (j < i) { c.clKeep[i] = 0u; return; }   // absorbed by the lower partner
+  uint32_t a = c.clRef[i], b = c.clRef[j];
+  uint32_t id = c.numTris - 2u - atomAdd(&c.counters[3], 1u);
+  float4 alo = c.clLo[i], ahi = c.clHi[i], blo = c.clLo[j], bhi = c.clHi[j];
+  float4 lo = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.0f);
+  float4 hi = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.0f);
+  c.left[id] = a; c.right[id] = b; c.parent[a] = id; c.parent[b] = id;
+  c.blo[id] = lo; c.bhi[id] = hi; c.subCount[id] = c.subCount[a] + c.subCount[b];
+  c.clRef[i] = id; c.clLo[i] = lo; c.clHi[i] = hi; c.clKeep[i] = 1u;
+}
+HD void ploc_compact_body(uint32_t i, const BuildCtx& c) {
+  if (!c.clKeep[i]) return;
+  uint32_t o = c.clPos[i];
+  c.clRefOut[o] = c.clRef[i]; c.clLoOut[o] = c.clLo[i]; c.clHiOut[o] = c.clHi[i];
+}
+// depth-first position of every ref = triangles in the left siblings of its ancestors; leaves are renumbered in that
+// order so that every subtree owns a contiguous triangle range (what the collapse and the leaf copies rely on)
+HD void ploc_order_body(uint32_t ref, const BuildCtx& c) {
+  const uint32_t n = c.numTris;
+  uint32_t off = 0, cur = ref, p = c.parent[cur];
+  while (p != DDGI_MISS) {
+    if (c.right[p] == cur) off += c.subCount[c.left[p]];
+    cur = p; p = c.parent[cur];
+  }
+  if (ref < n - 1u) { c.rangeFirst[ref] = off; c.rangeLast[ref] = off + c.subCount[ref] - 1u; return; }
+  uint32_t s = ref - (n - 1u), gid = c.sortedIds[s];
+  c.leafMap[s] = off; c.orderedIds[off] = gid;
+  c.blo[n - 1u + off] = c.triLo[gid]; c.bhi[n - 1u + off] = c.triHi[gid];
+}
+HD void ploc_relabel_body(uint32_t id, const BuildCtx& c) {
+  const uint32_t n = c.numTris;
+  uint32_t l = c.left[id], r = c.right[id];
+  if (l >= n - 1u) c.left[id] = n - 1u + c.leafMap[l - (n - 1u)];
+  if (r >= n - 1u) c.right[id] = n - 1u + c.leafMap[r - (n - 1u)];
 }
 
 // ----------------------------------------------------------------------------------------------------

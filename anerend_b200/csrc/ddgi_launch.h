@@ -9,6 +9,7 @@
 #ifndef DDGI_HOST_EMU
 // ---------------------------------------------------------------------------------------------- CUDA
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #define DDGI_API(name) anerend_cuda_ddgi_##name
 
 #define DDGI_KERNEL(kname, body, CtxT)                                                   \
@@ -49,6 +50,7 @@ struct Backend {
   }
   bool d2d(void* dst, const void* src, size_t bytes) { return bytes == 0 || ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream)); }
   bool zero(void* p, size_t bytes) { return bytes == 0 || ok(cudaMemsetAsync(p, 0, bytes, stream)); }
+  bool fill(void* p, int byte, size_t bytes) { return bytes == 0 || ok(cudaMemsetAsync(p, byte, bytes, stream)); }
   bool sync() { return ok(cudaStreamSynchronize(stream)); }
   bool check() { return ok(cudaGetLastError()); }
   void mark(int i) { cudaEventRecord(ev[i], stream); }
@@ -62,6 +64,15 @@ struct Backend {
     launches += 4;
     cudaStreamSynchronize(stream); cudaFree(tmp);
     return r;
+  }
+  // exclusive prefix sum (CUB decoupled look-back scan); `tmp` is caller-provided scratch of scanTempBytes(n)
+  size_t scanTempBytes(uint32_t n) {
+    size_t bytes = 0; cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, stream);
+    return bytes ? bytes : 1;
+  }
+  bool exclusiveSum(void* tmp, size_t tmpBytes, const uint32_t* in, uint32_t* out, uint32_t n) {
+    launches += 2;
+    return ok(cub::DeviceScan::ExclusiveSum(tmp, tmpBytes, in, out, (int)n, stream));
   }
 };
 }  // namespace ddgi
@@ -94,6 +105,7 @@ struct Backend {
   bool d2h(void* d, const void* s, size_t b) { if (b) memcpy(d, s, b); return true; }
   bool d2d(void* d, const void* s, size_t b) { if (b) memcpy(d, s, b); return true; }
   bool zero(void* p, size_t b) { if (b) memset(p, 0, b); return true; }
+  bool fill(void* p, int byte, size_t b) { if (b) memset(p, byte, b); return true; }
   bool sync() { return true; }
   bool check() { return true; }
   void mark(int i) { tp[i] = std::chrono::steady_clock::now(); }
@@ -102,6 +114,11 @@ struct Backend {
     std::vector<uint32_t> idx(n); std::iota(idx.begin(), idx.end(), 0u);
     std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return kin[a] < kin[b]; });
     for (uint32_t i = 0; i < n; ++i) { kout[i] = kin[idx[i]]; vout[i] = vin[idx[i]]; }
+    return true;
+  }
+  size_t scanTempBytes(uint32_t) { return 1; }
+  bool exclusiveSum(void*, size_t, const uint32_t* in, uint32_t* out, uint32_t n) {
+    uint32_t acc = 0; for (uint32_t i = 0; i < n; ++i) { uint32_t v = in[i]; out[i] = acc; acc += v; }
     return true;
   }
 };
