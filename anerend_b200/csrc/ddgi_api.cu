@@ -433,12 +433,17 @@ int traceLayers(anerend_ddgi* h, const int* layers, int numLayers, const float* 
   if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "trace before build_accel");
   if (!h->haveUbo) return fail(h, ANEREND_DDGI_E_STATE, "trace before set_scene_ubo");
   be.waitCopy();            // previous H2D of the staging tables must be done before they are rewritten
+  int loLayer = h->nY, hiLayer = -1;
   for (int l = 0; l < numLayers; ++l) {
     const int layer = layers[l];
     rotateDirs(h, layer, rots + 16 * (size_t)(rotsByLayer ? layer : l));
     h->hLayerMap[l] = layer;
-    BE_CHECK(h, be.h2d(h->dDirs + (size_t)layer * h->N, h->hDirs + (size_t)layer * h->N, (size_t)h->N * sizeof(float4)));
+    loLayer = layer < loLayer ? layer : loLayer; hiLayer = layer > hiLayer ? layer : hiLayer;
   }
+  // ONE copy of the table rows [loLayer, hiLayer] (a copy per layer cost ~3 us of stream time each): rows of layers
+  // that are not part of this launch are re-sent with the values the device already holds
+  if (hiLayer >= loLayer)
+    BE_CHECK(h, be.h2d(h->dDirs + (size_t)loLayer * h->N, h->hDirs + (size_t)loLayer * h->N, (size_t)(hiLayer - loLayer + 1) * h->N * sizeof(float4)));
   BE_CHECK(h, be.h2d(h->dLayerMap, h->hLayerMap, (size_t)numLayers * sizeof(int)));
   h->numLaunchLayers = numLayers;
   be.markCopy();
@@ -567,6 +572,7 @@ int DDGI_API(create)(const anerend_ddgi_params_t* params, anerend_ddgi_t** out) 
   if (ok && (q.flags & ANEREND_DDGI_FLAG_TEXEL_RECORDS)) ok = be.alloc(&h->dTexelRecords, texels);
   if (ok) ok = be.zero(h->dStats, 8 * sizeof(unsigned long long)) && be.zero(h->dRayIrr, rays * sizeof(uint2));
   if (!ok) { destroyHandle(h); return ANEREND_DDGI_E_CUDA; }
+  memset(h->hDirs, 0, (size_t)h->nY * h->N * sizeof(float4));      // rows of layers never traced travel with their neighbours
   h->fib.resize((size_t)h->N * 3);
   for (int i = 0; i < h->N; ++i) fibonacciDir((uint32_t)i, (uint32_t)h->N, &h->fib[3 * i]);
   h->layerTraced.assign(h->nY, 0);

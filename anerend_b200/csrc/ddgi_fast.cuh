@@ -365,8 +365,18 @@ __global__ void __launch_bounds__(PREP_BLOCK) k_shade_prep(const FastCtx c) {
       const anerend_light_t* lt = &t.lights[li];
       if (lt->color[3] > 0.5f) {
         const V3 lp = mk3(lt->world_pos[0], lt->world_pos[1], lt->world_pos[2]);
-        const V3 dv = lp - pos; const float dist = sqrtf(dot3(dv, dv));
-        if (dist < lt->world_pos[3]) { const V3 L = normalize3(lp - pos); if (dot3(normal, L) > 0.0f) needMask |= 1u << (1u + li); }
+        const V3 dv = lp - pos; const float d2 = dot3(dv, dv), range = lt->world_pos[3];
+        // the decisions below are the oracle's (dist < range, dot(normal, normalize(dv)) > 0); the two filters only
+        // skip the sqrt / normalise where rounding cannot change the outcome (margins >> the fp32 error of either side)
+        if (d2 > range * range * 1.00001f) continue;
+        const float dist = sqrtf(d2);
+        if (dist < range) {
+          const float sgn = dot3(normal, dv), mag = fabsf(normal.x * dv.x) + fabsf(normal.y * dv.y) + fabsf(normal.z * dv.z);
+          bool facing;
+          if (d2 > 1e-30f && fabsf(sgn) > 1e-5f * mag) facing = sgn > 0.0f;
+          else { const V3 L = normalize3(lp - pos); facing = dot3(normal, L) > 0.0f; }
+          if (facing) needMask |= 1u << (1u + li);
+        }
       }
     }
   }

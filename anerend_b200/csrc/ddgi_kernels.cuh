@@ -646,8 +646,11 @@ HD V3 calc_light(V3 N, V3 albedo, float metallic, float roughness, V3 worldPos, 
 }
 
 // texel fetch + manual bilinear: VK_FILTER_LINEAR with REPEAT addressing (PipelineUtil.h:98-112), fp32 weights
-HD V3 atlas_texel(const TraceCtx& c, int x, int y) {
-  x %= c.W; if (x < 0) x += c.W; y %= c.H; if (y < 0) y += c.H;
+HD int wrap_repeat(int x, int n) {           // REPEAT addressing; taps of the path stay within one period of [0, n)
+  if ((unsigned)x >= (unsigned)n) { x -= n; if ((unsigned)x >= (unsigned)n) { x %= n; if (x < 0) x += n; } }
+  return x;
+}
+HD V3 atlas_texel(const TraceCtx& c, int x, int y) {     // x, y already wrapped
 #ifdef __CUDA_ARCH__
   uint2 t = __ldg(&c.atlas[(size_t)y * c.W + x]);
 #else
@@ -655,24 +658,30 @@ HD V3 atlas_texel(const TraceCtx& c, int x, int y) {
 #endif
   return mk3(h2f((uint16_t)(t.x & 0xFFFFu)), h2f((uint16_t)(t.x >> 16)), h2f((uint16_t)(t.y & 0xFFFFu)));
 }
-HD V3 atlas_bilinear(const TraceCtx& c, float u, float v) {
-  // texel coordinates reach 10*nXZ*nY (2880 at C3): one ulp there is 2.4e-4 texels, so the address math stays exact
-  float x = xsub(xmul(u, (float)c.W), 0.5f), y = xsub(xmul(v, (float)c.H), 0.5f);
-  float fx0 = floorf(x), fy0 = floorf(y);
-  float fx = xsub(x, fx0), fy = xsub(y, fy0); int ix = (int)fx0, iy = (int)fy0;
-  V3 t00 = atlas_texel(c, ix, iy), t10 = atlas_texel(c, ix + 1, iy), t01 = atlas_texel(c, ix, iy + 1), t11 = atlas_texel(c, ix + 1, iy + 1);
+// One axis of sampleSingleProbe (pbr_light.glsl:168-188) + the bilinear footprint along it: `start` = first interior
+// texel of the probe on this axis, `size` = atlas extent, o = octEncode(normal)*0.5+0.5 on this axis.
+// texel coordinates reach 10*nXZ*nY (2880 at C3): one ulp there is 2.4e-4 texels, so the address math stays exact
+struct AxisTap { int i0, i1; float f; };
+HD AxisTap probe_axis_tap(int start, int size, float o) {
+  int end = start + 8 - 1;
+  float ts = xdiv(xadd(xmul(2.0f, (float)start), 1.0f), xmul(2.0f, (float)size));
+  float te = xdiv(xadd(xmul(2.0f, (float)end), 1.0f), xmul(2.0f, (float)size));
+  float uv = xadd(ts, xmul(xsub(te, ts), o));
+  float x = xsub(xmul(uv, (float)size), 0.5f);
+  float f0 = floorf(x);
+  AxisTap t; t.f = xsub(x, f0); int i = (int)f0; t.i0 = wrap_repeat(i, size); t.i1 = wrap_repeat(i + 1, size);
+  return t;
+}
+HD V3 atlas_bilinear(const TraceCtx& c, const AxisTap& ax, const AxisTap& ay) {
+  V3 t00 = atlas_texel(c, ax.i0, ay.i0), t10 = atlas_texel(c, ax.i1, ay.i0), t01 = atlas_texel(c, ax.i0, ay.i1), t11 = atlas_texel(c, ax.i1, ay.i1);
+  float fx = ax.f, fy = ay.f;
   float w00 = (1.0f - fx) * (1.0f - fy), w10 = fx * (1.0f - fy), w01 = (1.0f - fx) * fy, w11 = fx * fy;
   return t00 * w00 + t10 * w10 + t01 * w01 + t11 * w11;
 }
-// pbr_light.glsl:168-188 with octEncode(normalize(normal)) hoisted by the caller (same value for all 8 probes)
-HD V3 sample_single_probe(const TraceCtx& c, int px, int py, int pz, float o0, float o1) {
-  int startX = (8 + 2) * px + 1, startY = (8 + 2) * c.nXZ * py + (8 + 2) * pz + 1;
-  int endX = startX + 8 - 1, endY = startY + 8 - 1;
-  float tsx = xdiv(xadd(xmul(2.0f, (float)startX), 1.0f), xmul(2.0f, (float)c.W)), tsy = xdiv(xadd(xmul(2.0f, (float)startY), 1.0f), xmul(2.0f, (float)c.H));
-  float tex = xdiv(xadd(xmul(2.0f, (float)endX), 1.0f), xmul(2.0f, (float)c.W)), tey = xdiv(xadd(xmul(2.0f, (float)endY), 1.0f), xmul(2.0f, (float)c.H));
-  return atlas_bilinear(c, xadd(tsx, xmul(xsub(tex, tsx), o0)), xadd(tsy, xmul(xsub(tey, tsy), o1)));
-}
-// pbr_light.glsl:240-363 (live-grid branch :294-308) + weightProbe :190-238
+// pbr_light.glsl:240-363 (live-grid branch :294-308) + weightProbe :190-238 + sampleSingleProbe :168-188.
+// octEncode(normalize(normal)) is the same for all 8 probes, and the atlas column of a tap depends only on the corner's
+// x, its row only on (y, z): the per-axis address arithmetic is evaluated once per distinct value (2 + 4 instead of 8 + 8);
+// every value is produced by the same operations as in the shader, so the result is unchanged.
 HD V3 sample_probe(const TraceCtx& c, V3 worldPos, V3 normal) {
   int px = clampi((int)floorf((worldPos.x - c.camOff.x) / c.step.x), 0, c.nXZ - 1);
   int py = clampi((int)floorf(worldPos.y / c.step.y), 0, c.nY - 1);
@@ -681,6 +690,10 @@ HD V3 sample_probe(const TraceCtx& c, V3 worldPos, V3 normal) {
   V3 alpha = clamp3((worldPos - base) / c.step, 0.0f, 1.0f);
   float o0, o1; oct_encode(normalize3x(normal), o0, o1);
   o0 = xmul(xadd(o0, 1.0f), 0.5f); o1 = xmul(xadd(o1, 1.0f), 0.5f);
+  AxisTap tapX[2], tapY[4];
+  for (int ox = 0; ox < 2; ++ox) tapX[ox] = probe_axis_tap((8 + 2) * (px + ox) + 1, c.W, o0);
+  for (int oy = 0; oy < 2; ++oy) for (int oz = 0; oz < 2; ++oz)
+    tapY[oy + 2 * oz] = probe_axis_tap((8 + 2) * c.nXZ * (py + oy) + (8 + 2) * (pz + oz) + 1, c.H, o1);
   float sumW = 0.0f; V3 sum = mk3(0.0f);
   // corner order of the source: 000,111,110,100,011,010,001,101 packed as x | y<<1 | z<<2 per nibble
   const uint32_t order = 0x0u | (0x7u << 4) | (0x3u << 8) | (0x1u << 12) | (0x6u << 16) | (0x2u << 20) | (0x4u << 24) | (0x5u << 28);
@@ -695,7 +708,7 @@ HD V3 sample_probe(const TraceCtx& c, V3 worldPos, V3 normal) {
     weight = fmaxf(0.000001f, weight);
     if (weight < 0.2f) weight *= weight * weight * (1.0f / (0.2f * 0.2f));    // dead code kept verbatim (:221-224)
     weight *= tri.x * tri.y * tri.z;
-    V3 irr = sample_single_probe(c, px + ox, py + oy, pz + oz, o0, o1);
+    V3 irr = atlas_bilinear(c, tapX[ox], tapY[oy + 2 * oz]);
     irr = mk3(sqrtf(irr.x), sqrtf(irr.y), sqrtf(irr.z));
     sum = sum + weight * irr; sumW += weight;
   }

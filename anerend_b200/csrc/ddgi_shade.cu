@@ -20,11 +20,15 @@
 #define SHADE_NS fast
 #endif
 
+#define SHADE_MINB_DEFAULT 6
+#include <cstdlib>
+
 namespace ddgi {
 namespace SHADE_NS {
 
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_shade(const FastCtx c) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_shade(const FastCtx c) {
   const TraceCtx& t = c.t;
   const uint32_t nHits = c.qcount[FAST_QC_HITS];
   const int P = t.nXZ * t.nXZ;
@@ -71,26 +75,39 @@ __global__ void __launch_bounds__(128) k_shade(const FastCtx c) {
   }
 }
 
-static cudaError_t launch_shade_impl(const FastCtx& f, cudaStream_t s) {
+template <int MINB>
+static cudaError_t launch_shade_minb(const FastCtx& f, cudaStream_t s) {
   static int maxBlocks = 0;
   if (!maxBlocks) {
     int dev = 0, sms = 0, nb = 0;
     cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade<MINB>, 128, 0);
     maxBlocks = sms * (nb > 0 ? nb : 1);
   }
   // the hit count lives on the device: size the grid for the worst case (every ray hits), capped at one resident wave
   uint32_t blocks = (f.totalRays + 127u) / 128u;
   if (blocks > (uint32_t)maxBlocks) blocks = (uint32_t)maxBlocks;
   if (blocks == 0) return cudaSuccess;
-  k_shade<<<blocks, 128, 0, s>>>(f);
+  k_shade<MINB><<<blocks, 128, 0, s>>>(f);
   return cudaGetLastError();
+}
+static cudaError_t launch_shade_impl(const FastCtx& f, cudaStream_t s) {
+  static int minb = 0;            // register budget of k_shade: resident blocks per SM the compiler must allow
+  if (!minb) { const char* e = getenv("DDGI_SHADE_MINB"); minb = e ? atoi(e) : SHADE_MINB_DEFAULT; }   // sweeps only
+  switch (minb) {
+    case 4: return launch_shade_minb<4>(f, s);
+    case 5: return launch_shade_minb<5>(f, s);
+    case 7: return launch_shade_minb<7>(f, s);
+    case 8: return launch_shade_minb<8>(f, s);
+    default: return launch_shade_minb<6>(f, s);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_conv_weights(const ConvFastCtx f) {
   const ConvCtx& c = f.c;
-  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  // one thread per (layer, ray, texel row j): 8 weights each, so even a single layer fills a few SMs
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, idx = tid >> 3, j = tid & 7u;
   if (idx >= (uint32_t)c.numLayers * (uint32_t)c.N) return;
   // position p in the reference's loop order (x outer, y inner; probe_conv.comp:49-50) <-> ray index y*Sx + x
   const uint32_t layerLocal = idx / (uint32_t)c.N, pos = idx % (uint32_t)c.N;
@@ -98,20 +115,17 @@ __global__ void __launch_bounds__(128) k_conv_weights(const ConvFastCtx f) {
   const float4 d4 = c.dirs[(uint32_t)c.layerMap[layerLocal] * (uint32_t)c.N + ray];      // [nY][N]
   const V3 d = mk3(h2f(f2h(d4.x)), h2f(f2h(d4.y)), h2f(f2h(d4.z)));  // what the rgba16f ProbeRaysDirTex holds (rgen:108)
   float4* out = (float4*)(f.weights + (size_t)idx * 64);
-#pragma unroll 1
-  for (int j = 0; j < 8; ++j) {
-    float w[8];
+  float w[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float ux = (2.0f * (float)i + 1.0f) / (2.0f * 8.0f), uy = (2.0f * (float)j + 1.0f) / (2.0f * 8.0f);   // pixelToUv
-      ux = ux * 2.0f - 1.0f; uy = uy * 2.0f - 1.0f;
-      const V3 octDir = oct_decode(ux, uy);
-      const float ww = fmaxf(0.0f, dot3(d, octDir));
-      w[i] = ww > 1e-6f ? ww : 0.0f;                                // probe_conv.comp:55
-    }
-    out[2 * j] = make_float4(w[0], w[1], w[2], w[3]);
-    out[2 * j + 1] = make_float4(w[4], w[5], w[6], w[7]);
+  for (int i = 0; i < 8; ++i) {
+    float ux = (2.0f * (float)i + 1.0f) / (2.0f * 8.0f), uy = (2.0f * (float)j + 1.0f) / (2.0f * 8.0f);   // pixelToUv
+    ux = ux * 2.0f - 1.0f; uy = uy * 2.0f - 1.0f;
+    const V3 octDir = oct_decode(ux, uy);
+    const float ww = fmaxf(0.0f, dot3(d, octDir));
+    w[i] = ww > 1e-6f ? ww : 0.0f;                                // probe_conv.comp:55
   }
+  out[2 * j] = make_float4(w[0], w[1], w[2], w[3]);
+  out[2 * j + 1] = make_float4(w[4], w[5], w[6], w[7]);
 }
 
 #define CONV_PPT 4                    // probes per thread
@@ -126,9 +140,9 @@ __global__ void __launch_bounds__(256) k_probe_convolve_fast(const ConvFastCtx f
   const int layerLocal = (int)blockIdx.x / blocksPerLayer, g0 = ((int)blockIdx.x % blocksPerLayer) * CONV_G;
   const int layer = c.layerMap[layerLocal];
   const int texel = (int)threadIdx.x & 63, sub = (int)threadIdx.x >> 6;
-  float acc[CONV_PPT][4];
+  float acc[CONV_PPT][3], accW = 0.0f;          // sum of the weights: the same for every probe of the layer
 #pragma unroll
-  for (int k = 0; k < CONV_PPT; ++k) { acc[k][0] = 0.0f; acc[k][1] = 0.0f; acc[k][2] = 0.0f; acc[k][3] = 0.0f; }
+  for (int k = 0; k < CONV_PPT; ++k) { acc[k][0] = 0.0f; acc[k][1] = 0.0f; acc[k][2] = 0.0f; }
   const float* W = f.weights + (size_t)layerLocal * c.N * 64 + texel;
   for (int r0 = 0; r0 < c.N; r0 += CONV_CHUNK) {
     const int nr = min(CONV_CHUNK, c.N - r0);
@@ -148,15 +162,16 @@ __global__ void __launch_bounds__(256) k_probe_convolve_fast(const ConvFastCtx f
 #pragma unroll 4
     for (int r = 0; r < nr; ++r) {
       const float w = __ldg(W + (size_t)(r0 + r) * 64);
+      accW += w;
 #pragma unroll
       for (int k = 0; k < CONV_PPT; ++k) {
         const float4 v = myRad[k * CONV_CHUNK + r];
 #ifdef DDGI_SHADE_EXACT
         // the oracle's sequence: result += (w*rad, w) in loop order; w == 0 where the shader skips (adds +0)
-        acc[k][0] = acc[k][0] + w * v.x; acc[k][1] = acc[k][1] + w * v.y; acc[k][2] = acc[k][2] + w * v.z; acc[k][3] += w;
+        acc[k][0] = acc[k][0] + w * v.x; acc[k][1] = acc[k][1] + w * v.y; acc[k][2] = acc[k][2] + w * v.z;
 #else
         acc[k][0] = fmaf(w, v.x, acc[k][0]); acc[k][1] = fmaf(w, v.y, acc[k][1]);
-        acc[k][2] = fmaf(w, v.z, acc[k][2]); acc[k][3] += w;
+        acc[k][2] = fmaf(w, v.z, acc[k][2]);
 #endif
       }
     }
@@ -173,7 +188,7 @@ __global__ void __launch_bounds__(256) k_probe_convolve_fast(const ConvFastCtx f
     const uint2 ot = c.atlas[ti];
     const float o0 = h2f((uint16_t)(ot.x & 0xFFFFu)), o1 = h2f((uint16_t)(ot.x >> 16)), o2 = h2f((uint16_t)(ot.y & 0xFFFFu)), o3 = h2f((uint16_t)(ot.y >> 16));
     float r0 = acc[k][0], r1 = acc[k][1], r2 = acc[k][2];
-    const float r3 = acc[k][3];
+    const float r3 = accW;
 #ifdef DDGI_SHADE_EXACT
     if (r3 > 1e-6f) { r0 /= r3; r1 /= r3; r2 /= r3; }
 #else
@@ -191,7 +206,7 @@ static cudaError_t launch_convolve_impl(const ConvFastCtx& f, cudaStream_t s) {
   const ConvCtx& c = f.c;
   const uint32_t nw = (uint32_t)c.numLayers * (uint32_t)c.N;
   if (nw == 0) return cudaSuccess;
-  k_conv_weights<<<(nw + 127u) / 128u, 128, 0, s>>>(f);
+  k_conv_weights<<<(8u * nw + 127u) / 128u, 128, 0, s>>>(f);
   const int P = c.nXZ * c.nXZ;
   const uint32_t blocks = (uint32_t)c.numLayers * (uint32_t)((P + CONV_G - 1) / CONV_G);
   k_probe_convolve_fast<<<blocks, 256, 0, s>>>(f);
