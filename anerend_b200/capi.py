@@ -186,6 +186,14 @@ class DdgiHandle:
             self._call("sync")
 
     # ---- results ---------------------------------------------------------------------------------
+    def download_atlas_layers(self, layers, out=None):
+        """Atlas rows of the given Y-layers, packed: uint16 [len(layers), 10*nXZ, W, 4]."""
+        layers = _c(layers, np.int32).reshape(-1)
+        if out is None:
+            out = np.empty((layers.size, self.atlas_width, self.atlas_width, 4), np.uint16)
+        self._call("download_atlas_layers", _ptr(layers), C.c_uint32(layers.size), _ptr(out), C.c_size_t(out.nbytes))
+        return out
+
     def download_atlas(self, out=None):
         """ProbeRaysConvTex as uint16 [H, W, 4] (RGBA16F bit patterns)."""
         if out is None:

@@ -397,6 +397,29 @@ __global__ void __launch_bounds__(32) k_peer_barrier(const PeerBarrierCtx b) {
   __syncwarp();
   __threadfence_system();
 }
+// Push of this rank's freshly convolved layers into every peer's atlas over NVLink: whole layer blocks (10*nXZ atlas rows,
+// contiguous) as 16-byte loads and stores, one load feeding all peers.  The per-texel stores of the convolution reach
+// the link as 64-byte runs (8 interior texels of a probe row); full lines move ~2x the bytes per unit time.
+struct PushCtx { const uint4* src; uint4* peers[8]; const int* layerMap; uint32_t numPeers, chunksPerLayer; };
+__global__ void __launch_bounds__(256) k_atlas_push(const PushCtx c) {
+  const size_t base = (size_t)c.layerMap[blockIdx.y] * c.chunksPerLayer;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < c.chunksPerLayer; i += gridDim.x * blockDim.x) {
+    const uint4 v = __ldcg(c.src + base + i);
+    for (uint32_t p = 0; p < c.numPeers; ++p) __stcg(c.peers[p] + base + i, v);
+  }
+}
+int pushLayers(anerend_ddgi* h, int numLayers) {
+  if (h->numPeers == 0 || numLayers == 0) return 0;
+  PushCtx c{};
+  c.src = (const uint4*)h->dAtlas; c.layerMap = h->dLayerMap; c.numPeers = (uint32_t)h->numPeers;
+  for (int p = 0; p < h->numPeers; ++p) c.peers[p] = (uint4*)h->peers[p];
+  c.chunksPerLayer = (uint32_t)((size_t)h->W * h->W * sizeof(uint2) / sizeof(uint4));      // W = 10*nXZ is even
+  const uint32_t bx = std::min<uint32_t>((c.chunksPerLayer + 255u) / 256u, (uint32_t)std::max(1, 4 * h->sms / numLayers));
+  k_atlas_push<<<dim3(bx, (uint32_t)numLayers), 256, 0, h->be.stream>>>(c);
+  ++h->be.launches;
+  BE_CHECK(h, h->be.check());
+  return 0;
+}
 int peerBarrier(anerend_ddgi* h) {
   if (h->xworld < 2) return 0;
   PeerBarrierCtx b{};
@@ -422,6 +445,7 @@ void exchangeDisconnect(anerend_ddgi* h) {
 }
 #else
 int peerBarrier(anerend_ddgi*) { return 0; }
+int pushLayers(anerend_ddgi*, int) { return 0; }
 int peerCheck(anerend_ddgi*) { return 0; }
 void exchangeDisconnect(anerend_ddgi*) {}
 #endif
@@ -494,8 +518,11 @@ int convolveLayers(anerend_ddgi* h, const int* layers, int numLayers) {
   }
   ConvCtx c{};
   c.rayIrr = h->dRayIrr; c.dirs = h->dDirs; c.layerMap = h->dLayerMap; c.atlas = h->dAtlas; c.texelRecords = h->dTexelRecords;
+  // peers: whole layer blocks are pushed after the convolution (pushLayers); DDGI_EXCHANGE_TEXEL=1 keeps the first
+  // version, per-texel peer stores from inside the convolution, for A/B measurements
+  static const bool texelStores = getenv("DDGI_EXCHANGE_TEXEL") != nullptr;
   for (int i = 0; i < h->numPeers; ++i) c.peers[i] = h->peers[i];
-  c.numPeers = h->numPeers;
+  c.numPeers = texelStores ? h->numPeers : 0;
   c.nXZ = h->nXZ; c.nY = h->nY; c.N = h->N; c.Sx = h->Sx; c.Sy = h->Sy; c.W = h->W; c.H = h->H; c.numLayers = numLayers;
   c.hysteresis = h->p.hysteresis;
 #ifndef DDGI_HOST_EMU
@@ -507,6 +534,7 @@ int convolveLayers(anerend_ddgi* h, const int* layers, int numLayers) {
 #endif
   DDGI_LAUNCH(be, k_probe_convolve, conv_texel_body, (uint32_t)numLayers * (uint32_t)h->P * 64u, c, 128);
   BE_CHECK(h, be.check());
+  if (!texelStores) return pushLayers(h, numLayers);
   return 0;
 }
 
@@ -765,6 +793,15 @@ int DDGI_API(atlas_dims)(const anerend_ddgi_t* h, int32_t* w, int32_t* hh) { *w 
 int DDGI_API(download_atlas)(anerend_ddgi_t* h, void* out, size_t bytes) {
   if (bytes != (size_t)h->W * h->H * 8) return fail(h, ANEREND_DDGI_E_INVALID, "atlas size mismatch");
   BE_CHECK(h, h->be.d2h(out, h->dAtlas, bytes)); return 0;
+}
+int DDGI_API(download_atlas_layers)(anerend_ddgi_t* h, const int32_t* layers, uint32_t n, void* out, size_t bytes) {
+  const size_t layerBytes = (size_t)h->W * h->W * 8;       // 10*nXZ rows of 10*nXZ RGBA16F texels
+  if (!layers || bytes != layerBytes * n) return fail(h, ANEREND_DDGI_E_INVALID, "layer block size mismatch");
+  for (uint32_t i = 0; i < n; ++i) if (layers[i] < 0 || layers[i] >= h->nY) return fail(h, ANEREND_DDGI_E_INVALID, "layer out of range");
+  for (uint32_t i = 0; i < n; ++i)
+    if (!h->be.d2hAsync((char*)out + layerBytes * i, (const char*)h->dAtlas + layerBytes * (size_t)layers[i], layerBytes))
+      return fail(h, ANEREND_DDGI_E_CUDA, std::string("download_atlas_layers: ") + h->be.errStr());
+  BE_CHECK(h, h->be.sync()); return 0;
 }
 int DDGI_API(upload_atlas)(anerend_ddgi_t* h, const void* in, size_t bytes) {
   if (bytes != (size_t)h->W * h->H * 8) return fail(h, ANEREND_DDGI_E_INVALID, "atlas size mismatch");

@@ -48,6 +48,7 @@ struct Backend {
   bool d2h(void* dst, const void* src, size_t bytes) {
     return bytes == 0 || (ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream)) && ok(cudaStreamSynchronize(stream)));
   }
+  bool d2hAsync(void* dst, const void* src, size_t bytes) { return bytes == 0 || ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream)); }
   bool d2d(void* dst, const void* src, size_t bytes) { return bytes == 0 || ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream)); }
   bool zero(void* p, size_t bytes) { return bytes == 0 || ok(cudaMemsetAsync(p, 0, bytes, stream)); }
   bool fill(void* p, int byte, size_t bytes) { return bytes == 0 || ok(cudaMemsetAsync(p, byte, bytes, stream)); }
@@ -103,6 +104,7 @@ struct Backend {
   void freeHostPinned(void* p) { ::free(p); }
   bool h2d(void* d, const void* s, size_t b) { if (b) memcpy(d, s, b); return true; }
   bool d2h(void* d, const void* s, size_t b) { if (b) memcpy(d, s, b); return true; }
+  bool d2hAsync(void* d, const void* s, size_t b) { if (b) memcpy(d, s, b); return true; }
   bool d2d(void* d, const void* s, size_t b) { if (b) memcpy(d, s, b); return true; }
   bool zero(void* p, size_t b) { if (b) memset(p, 0, b); return true; }
   bool fill(void* p, int byte, size_t b) { if (b) memset(p, byte, b); return true; }

@@ -20,7 +20,7 @@
 #define SHADE_NS fast
 #endif
 
-#define SHADE_MINB_DEFAULT 6
+#define SHADE_MINB_DEFAULT 8         // 64 registers: occupancy beats the few spills (gpu sweep: 4/5/6/7/8 -> 218/192/185/179/175 us at C3)
 #include <cstdlib>
 
 namespace ddgi {
@@ -98,8 +98,10 @@ static cudaError_t launch_shade_impl(const FastCtx& f, cudaStream_t s) {
     case 4: return launch_shade_minb<4>(f, s);
     case 5: return launch_shade_minb<5>(f, s);
     case 7: return launch_shade_minb<7>(f, s);
-    case 8: return launch_shade_minb<8>(f, s);
-    default: return launch_shade_minb<6>(f, s);
+    case 6: return launch_shade_minb<6>(f, s);
+    case 10: return launch_shade_minb<10>(f, s);
+    case 12: return launch_shade_minb<12>(f, s);
+    default: return launch_shade_minb<8>(f, s);
   }
 }
 

@@ -47,6 +47,42 @@ def mirrored_slabs_for_rank(num_probes_y, rank, world):
     return list(range(rank * k, (rank + 1) * k)) + list(range(half + (world - 1 - rank) * k, half + (world - rank) * k))
 
 
+def balanced_layers(costs, world):
+    """Measured-cost deal of the layers (longest-processing-time-first): `costs[y]` is the time (any unit) one update of
+    layer y takes; layers are handed out in order of falling cost, each to the rank with the least work so far (ties ->
+    lowest rank, so every rank derives the same deal from the same costs).  Returns one sorted layer list per rank; every
+    rank gets at least one layer.  Jacobi updates do not depend on how the layers are dealt, so the deal can be
+    re-measured at any time; it needs an exchange that takes arbitrary layer sets (the fused peer-store exchange)."""
+    n = len(costs)
+    if world > n:
+        raise ValueError(f"{world} ranks cannot share {n} probe layers")
+    order = sorted(range(n), key=lambda y: (-float(costs[y]), y))
+    load, out = [0.0] * world, [[] for _ in range(world)]
+    for i, y in enumerate(order):
+        remaining = n - i
+        empty = [r for r in range(world) if not out[r]]
+        # never leave a rank without a layer: once the layers left only just cover the empty ranks, serve those
+        cand = empty if empty and remaining <= len(empty) else range(world)
+        r = min(cand, key=lambda k: (load[k], k))
+        out[r].append(y)
+        load[r] += float(costs[y])
+    return [sorted(o) for o in out]
+
+
+def measure_layer_costs(handle, rots, repeats=2):
+    """Per-layer update time in ms (trace + convolve, CUDA events of the handle), best of `repeats`: one single-layer
+    update_layers call per layer.  Run it on an UNCONNECTED handle (no peer stores); it advances the atlas like any
+    update, so callers reset() afterwards if they need the cleared state."""
+    ny = handle.n_y
+    costs = [float("inf")] * ny
+    for _ in range(repeats):
+        for y in range(ny):
+            handle.update_layers([y], rots)
+            t = handle.timings()
+            costs[y] = min(costs[y], t["rt_ms"] + t["convolve_ms"])
+    return costs
+
+
 _STAGING = {}
 
 

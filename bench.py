@@ -162,6 +162,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fast-math", action="store_true", help="time the FAST_MATH build as the headline (default: exact build)")
     ap.add_argument("--no-alt", action="store_true", help="skip the second-build and 1-GPU strong-scaling-base measurements")
+    ap.add_argument("--deal", default="measured", choices=["measured", "static"],
+                    help="N>1, fused exchange: deal the probe layers by measured per-layer cost (default) or by the static mirrored/zigzag rule")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N>1: atlas exchange fused into the convolution over NVLink peer memory (default) or NCCL all-gather")
     args = ap.parse_args()
@@ -189,7 +191,8 @@ def main():
     # multi-GPU: interleaved layer sets (balanced) when nY divides evenly, contiguous slabs otherwise
     mirrored = world > 1 and ny % (2 * world) == 0
     interleaved = world > 1 and (mirrored or ny % world == 0)
-    slab = (0, ny) if interleaved else sharding.slab_for_rank(ny, rank, world)
+    measured_deal = world > 1 and args.exchange == "fused" and args.deal == "measured"
+    slab = (0, ny) if (interleaved or measured_deal) else sharding.slab_for_rank(ny, rank, world)
     my_layers = (sharding.mirrored_slabs_for_rank(ny, rank, world) if mirrored else
                  sharding.layers_for_rank(ny, rank, world) if interleaved else list(range(slab[0], slab[1])))
     # point lights (extension E1) + dead-shadow-ray elimination (radiance bit-identical, tests/test_oracle_kat.py);
@@ -213,11 +216,8 @@ def main():
         hh.upload_scene(scene)
         hh.set_scene_ubo(scene.ubo)
         hh.build_accel()
-        if connect:                           # fused exchange: map every peer's atlas (cudaIpc over NVLink)
-            blobs = [None] * world
-            dist.all_gather_object(blobs, hh.exchange_export())
-            hh.exchange_connect(blobs, world, rank)
-            dist.barrier()
+        if connect:
+            connect_handle(hh)
         return hh
 
     def close_handle(hh, connected=False):
@@ -228,10 +228,31 @@ def main():
             dist.barrier()
         hh.close()
 
-    h = make_handle(flags, slab, connect=fused)
+    def connect_handle(hh):                   # fused exchange: map every peer's atlas (cudaIpc over NVLink)
+        blobs = [None] * world
+        dist.all_gather_object(blobs, hh.exchange_export())
+        hh.exchange_connect(blobs, world, rank)
+        dist.barrier()
+
+    h = make_handle(flags, slab, connect=False)
     accel_ms = h.timings()["accel_ms"]
     info = h.bvh_info()
     rots = h.rotations(seq).reshape(total_steps, ny, 16)
+    balanced = None
+    if measured_deal:
+        # measured-cost deal of the layers (sharding.balanced_layers): every rank times one update of each layer alone on
+        # its own GPU (replicated scene: same numbers everywhere), rank 0's figures are broadcast so all ranks derive
+        # the same deal.  The peer-store exchange takes arbitrary layer sets; the NCCL gathers keep the static deals.
+        costs = [sharding.measure_layer_costs(h, rots[0])]
+        dist.broadcast_object_list(costs, src=0)
+        deal = sharding.balanced_layers(costs[0], world)
+        my_layers = deal[rank]
+        loads = [sum(costs[0][y] for y in d) for d in deal]
+        balanced = {"layer_cost_ms_min": min(costs[0]), "layer_cost_ms_max": max(costs[0]), "rank_load_ms_min": min(loads),
+                    "rank_load_ms_max": max(loads), "layers_per_rank": [len(d) for d in deal]}
+        h.reset()
+    if fused:
+        connect_handle(h)
     my_rays = nxz * nxz * len(my_layers) * nr
     nbytes = h.atlas_device_ptr()[1]
     host_atlas = torch.empty((h.atlas_height, h.atlas_width, 4), dtype=torch.int16, pin_memory=True)   # pinned result buffer
@@ -315,9 +336,15 @@ def main():
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
+    # result read-back: the whole atlas on one GPU; at N>1 every rank reads back the layers it computed (together the
+    # ranks return the whole atlas once per step)
+    own_np = host_np.reshape(-1)[:len(my_layers) * h.atlas_width * h.atlas_width * 4].reshape(len(my_layers), h.atlas_width, h.atlas_width, 4)
     for k in range(e2e_steps):
         step(args.warmup + (k % args.steps))
-        h.download_atlas(host_np)            # D2H of the result (synchronous)
+        if world > 1:
+            h.download_atlas_layers(my_layers, own_np)
+        else:
+            h.download_atlas(host_np)            # D2H of the result (synchronous)
     h.sync()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -326,7 +353,7 @@ def main():
         e2e_s = float(tt.item())
     e2e_value = all_rays * e2e_steps / e2e_s / 1e6
     h2d_bytes = len(my_layers) * nr * 16 + 568 + 64 * ny
-    d2h_bytes = nbytes
+    d2h_bytes = nbytes if world == 1 else int(own_np.nbytes)
 
     # ---- second figure: the other arithmetic build (FAST_MATH <-> exact), same workload, fewer steps ----------
     alt = None
@@ -373,7 +400,7 @@ def main():
     if rank == 0:
         # ---- roofline of the dominant kernel: counted, untimed run of the same update ----------
         hc = make_handle(flags | L.FLAG_COUNTERS, slab)
-        if interleaved:
+        if interleaved or measured_deal:
             hc.update_layers(my_layers, rots[args.warmup])
         else:
             hc.update(-1, rots[args.warmup])
@@ -424,6 +451,8 @@ def main():
                             "sample": f"{len(layers)} of {ny} Y-layers of {name} ({rays} primary rays + shadow rays), "
                                       f"{secs:.2f} s, multithreaded C++ oracle (shader transliteration)"}
         cfg = workload_desc(name, scene, grid, world)
+        if balanced is not None:
+            cfg["parallelism"] = f"probe layers dealt to {world} ranks by measured per-layer cost (LPT)"
         cfg.update({"l2": "flushed between timed iterations (256 MiB write)" if flush else "working set larger than L2, no flush",
                     "bvh8_nodes": int(info.num_nodes), "accel_build_ms": accel_ms,
                     "atlas_exchange": ("fused: convolution stores each texel into all peers' atlases over NVLink (cudaIpc), "
@@ -439,7 +468,7 @@ def main():
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "update_ms": {"trace": rt_avg, "convolve": float(np.mean(conv_ms)), "full_grid": ms_per_step},
                 "arithmetic": "fast_math (1e-4 relative per update)" if args.fast_math else "exact (atlas bit-identical to the oracle)",
-                "other_build": alt, "strong_scaling_base": base1, "exchange_check_vs_1gpu": verified}
+                "other_build": alt, "strong_scaling_base": base1, "exchange_check_vs_1gpu": verified, "layer_deal": balanced}
     close_handle(h, fused)
     if world > 1:
         dist.barrier()

@@ -182,6 +182,9 @@ int anerend_cuda_ddgi_atlas_dims(const anerend_ddgi_t* h, int32_t* width, int32_
 /* "ProbeRaysConvTex" as row-major RGBA16F, width*height*8 bytes (mirrors downloadDDGIAtlas,
  * VulkanRenderer.cpp:2706-2771). */
 int anerend_cuda_ddgi_download_atlas(anerend_ddgi_t* h, void* rgba16f, size_t bytes);
+/* The atlas rows of `num_layers` Y-layers (10*nXZ rows each), packed in the order given: what one rank of a sharded
+ * update reads back (its own layers); bytes = num_layers * (10*nXZ)^2 * 8. */
+int anerend_cuda_ddgi_download_atlas_layers(anerend_ddgi_t* h, const int32_t* layers, uint32_t num_layers, void* rgba16f, size_t bytes);
 int anerend_cuda_ddgi_upload_atlas(anerend_ddgi_t* h, const void* rgba16f, size_t bytes);
 /* Device pointer of the atlas for consumers on the same device (deferred lighting, NCCL all-gather of slabs).
  * Rows [10*nXZ*slab_begin, 10*nXZ*slab_end) are the rows this handle writes. */

@@ -145,3 +145,37 @@ def test_two_rank_gloo_slab_update_equals_single_rank(tmp_path, make_emu):
     assert np.array_equal(a0, a1) and np.array_equal(a0, want)
     merged = sharding.merge_slabs_numpy([a0, a1], nxz, ny)
     assert np.array_equal(merged, want)
+
+
+def test_balanced_layers_is_a_partition_and_beats_the_static_deals():
+    rng = np.random.default_rng(5)
+    for ny, world in ((32, 8), (32, 4), (12, 2), (12, 5), (8, 8)):
+        # cost falls with height, plus a bump (a dense layer of props) and noise: what C5 looks like
+        costs = [3.0 * np.exp(-y / (0.3 * ny)) + (1.5 if y == ny // 3 else 0.0) + 0.2 * rng.random() + 0.3 for y in range(ny)]
+        deal = sharding.balanced_layers(costs, world)
+        assert sorted(y for d in deal for y in d) == list(range(ny)) and all(d for d in deal)
+        load = [sum(costs[y] for y in d) for d in deal]
+        zig = [sum(costs[y] for y in sharding.layers_for_rank(ny, r, world)) for r in range(world)]
+        assert max(load) <= max(zig) + 1e-9
+        # LPT bound: the busiest rank carries at most the mean plus one layer
+        assert max(load) <= sum(costs) / world + max(costs) + 1e-9
+    assert sharding.balanced_layers([1.0, 1.0, 1.0], 3) == [[0], [1], [2]]
+    with pytest.raises(ValueError):
+        sharding.balanced_layers([1.0, 2.0], 3)
+
+
+def test_download_atlas_layers_returns_the_layer_rows(make_emu):
+    from anerend_b200 import layouts as L, make_params, scenes
+    from tests import parity
+    scene = scenes.random_soup(31, ntris=300)
+    e = make_emu(make_params(4, 3, 64, flags=L.FLAG_POINT_LIGHTS))
+    rots = parity.setup_pair(scene, (e,), seed=9)
+    e.update(-1, rots)
+    full = e.download_atlas()
+    rows = 10 * 4
+    got = e.download_atlas_layers([2, 0])
+    assert got.shape == (2, rows, rows, 4)
+    assert np.array_equal(got[0], full[2 * rows:3 * rows]) and np.array_equal(got[1], full[0:rows])
+    with pytest.raises(Exception):
+        e.download_atlas_layers([3])
+    e.close()
