@@ -186,6 +186,20 @@ class DdgiHandle:
             self._call("sync")
 
     # ---- results ---------------------------------------------------------------------------------
+    def set_row_stripe(self, offset, stride):
+        """This handle updates only the probe rows z = offset + k*stride of every layer (multi-GPU sharding inside the layers)."""
+        self._call("set_row_stripe", C.c_int32(offset), C.c_int32(stride))
+        self.stripe = (int(offset), int(stride))
+
+    def download_atlas_stripe(self, out=None):
+        """Atlas rows of this handle's stripe in all layers: uint16 [n_y, rows, 10, W, 4]."""
+        off, stride = getattr(self, "stripe", (0, 1))
+        rows = (self.n_xz - off + stride - 1) // stride
+        if out is None:
+            out = np.empty((self.n_y, rows, 10, self.atlas_width, 4), np.uint16)
+        self._call("download_atlas_stripe", _ptr(out), C.c_size_t(out.nbytes))
+        return out
+
     def download_atlas_layers(self, layers, out=None):
         """Atlas rows of the given Y-layers, packed: uint16 [len(layers), 10*nXZ, W, 4]."""
         layers = _c(layers, np.int32).reshape(-1)

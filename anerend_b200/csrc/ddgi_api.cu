@@ -90,6 +90,7 @@ struct anerend_ddgi {
   uint32_t* dHitq = nullptr; float4* dShadeTris = nullptr; float* dConvW = nullptr;
   size_t fastRays = 0; uint32_t fastQueues = 0; int gridPrimary[2] = {0, 0}, gridShadow[2] = {0, 0}; uint32_t tune[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int sms = 0;
 
+  int rowOffset = 0, rowStride = 1, Pl = 0;                // row stripe (set_row_stripe): probes launched per layer = Pl
   int currentLayer = 0;                                    // IrradianceProbeRayTracingPass::_currentLayer
   int lastProbeIdx[2] = {0, 0};                            // IrradianceProbeTranslationPass::_lastProbeIdx
   anerend_ddgi_timings_t timings{};
@@ -400,12 +401,16 @@ __global__ void __launch_bounds__(32) k_peer_barrier(const PeerBarrierCtx b) {
 // Push of this rank's freshly convolved layers into every peer's atlas over NVLink: whole layer blocks (10*nXZ atlas rows,
 // contiguous) as 16-byte loads and stores, one load feeding all peers.  The per-texel stores of the convolution reach
 // the link as 64-byte runs (8 interior texels of a probe row); full lines move ~2x the bytes per unit time.
-struct PushCtx { const uint4* src; uint4* peers[8]; const int* layerMap; uint32_t numPeers, chunksPerLayer; };
+struct PushCtx { const uint4* src; uint4* peers[8]; const int* layerMap; uint32_t numPeers, chunksPerRow, rows, rowOffset, rowStride, nXZ; };
 __global__ void __launch_bounds__(256) k_atlas_push(const PushCtx c) {
-  const size_t base = (size_t)c.layerMap[blockIdx.y] * c.chunksPerLayer;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < c.chunksPerLayer; i += gridDim.x * blockDim.x) {
-    const uint4 v = __ldcg(c.src + base + i);
-    for (uint32_t p = 0; p < c.numPeers; ++p) __stcg(c.peers[p] + base + i, v);
+  // a probe row z of a layer = 10 atlas rows = chunksPerRow 16-byte chunks, contiguous; this handle owns `rows` of them
+  const size_t layerBase = (size_t)c.layerMap[blockIdx.y] * c.nXZ * c.chunksPerRow;
+  const uint32_t total = c.rows * c.chunksPerRow;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t zr = i / c.chunksPerRow, w = i % c.chunksPerRow;
+    const size_t o = layerBase + (size_t)(c.rowOffset + zr * c.rowStride) * c.chunksPerRow + w;
+    const uint4 v = __ldcg(c.src + o);
+    for (uint32_t p = 0; p < c.numPeers; ++p) __stcg(c.peers[p] + o, v);
   }
 }
 int pushLayers(anerend_ddgi* h, int numLayers) {
@@ -413,8 +418,9 @@ int pushLayers(anerend_ddgi* h, int numLayers) {
   PushCtx c{};
   c.src = (const uint4*)h->dAtlas; c.layerMap = h->dLayerMap; c.numPeers = (uint32_t)h->numPeers;
   for (int p = 0; p < h->numPeers; ++p) c.peers[p] = (uint4*)h->peers[p];
-  c.chunksPerLayer = (uint32_t)((size_t)h->W * h->W * sizeof(uint2) / sizeof(uint4));      // W = 10*nXZ is even
-  const uint32_t bx = std::min<uint32_t>((c.chunksPerLayer + 255u) / 256u, (uint32_t)std::max(1, 4 * h->sms / numLayers));
+  c.chunksPerRow = (uint32_t)((size_t)10 * h->W * sizeof(uint2) / sizeof(uint4));          // W = 10*nXZ is even
+  c.rows = (uint32_t)(h->Pl / h->nXZ); c.rowOffset = (uint32_t)h->rowOffset; c.rowStride = (uint32_t)h->rowStride; c.nXZ = (uint32_t)h->nXZ;
+  const uint32_t bx = std::min<uint32_t>((c.rows * c.chunksPerRow + 255u) / 256u, (uint32_t)std::max(1, 4 * h->sms / numLayers));
   k_atlas_push<<<dim3(bx, (uint32_t)numLayers), 256, 0, h->be.stream>>>(c);
   ++h->be.launches;
   BE_CHECK(h, h->be.check());
@@ -479,6 +485,7 @@ int traceLayers(anerend_ddgi* h, const int* layers, int numLayers, const float* 
   c.dirs = h->dDirs; c.layerMap = h->dLayerMap; c.rayOrder = h->dRayOrder; c.atlas = h->dAtlas; c.rayIrr = h->dRayIrr;
   c.records = h->dRecords; c.stats = h->dStats;
   c.nXZ = h->nXZ; c.nY = h->nY; c.N = h->N; c.W = h->W; c.H = h->H; c.numLayers = numLayers;
+  c.Pl = h->Pl; c.rowOffset = h->rowOffset; c.rowStride = h->rowStride;
   // camOffset (rgen:75-81, pbr_light.glsl:295-301): int() truncates toward zero (quirk Q1)
   const float* step = h->p.probe_step;
   int cix = (int)(h->ubo.camera_pos[0] / step[0]), ciz = (int)(h->ubo.camera_pos[2] / step[2]);
@@ -491,7 +498,7 @@ int traceLayers(anerend_ddgi* h, const int* layers, int numLayers, const float* 
   c.lightDir = mk3(h->ubo.light_dir[0], h->ubo.light_dir[1], h->ubo.light_dir[2]);
   c.tmin = h->p.t_min; c.tmax = h->p.t_max; c.sunIntensity = h->ubo.sun_intensity;
   c.uboFlags = h->ubo.flags; c.flags = h->p.flags;
-  const uint32_t n = (uint32_t)numLayers * (uint32_t)h->P * (uint32_t)h->N;
+  const uint32_t n = (uint32_t)numLayers * (uint32_t)h->Pl * (uint32_t)h->N;
 #ifndef DDGI_HOST_EMU
   if (!(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS)) { int rc = traceFast(h, c, n); if (rc) return rc; } else
 #endif
@@ -524,6 +531,7 @@ int convolveLayers(anerend_ddgi* h, const int* layers, int numLayers) {
   for (int i = 0; i < h->numPeers; ++i) c.peers[i] = h->peers[i];
   c.numPeers = texelStores ? h->numPeers : 0;
   c.nXZ = h->nXZ; c.nY = h->nY; c.N = h->N; c.Sx = h->Sx; c.Sy = h->Sy; c.W = h->W; c.H = h->H; c.numLayers = numLayers;
+  c.Pl = h->Pl; c.rowOffset = h->rowOffset; c.rowStride = h->rowStride;
   c.hysteresis = h->p.hysteresis;
 #ifndef DDGI_HOST_EMU
   if (!(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS)) {
@@ -532,7 +540,7 @@ int convolveLayers(anerend_ddgi* h, const int* layers, int numLayers) {
     be.launches += 2;
   } else
 #endif
-  DDGI_LAUNCH(be, k_probe_convolve, conv_texel_body, (uint32_t)numLayers * (uint32_t)h->P * 64u, c, 128);
+  DDGI_LAUNCH(be, k_probe_convolve, conv_texel_body, (uint32_t)numLayers * (uint32_t)h->Pl * 64u, c, 128);
   BE_CHECK(h, be.check());
   if (!texelStores) return pushLayers(h, numLayers);
   return 0;
@@ -588,7 +596,7 @@ int DDGI_API(create)(const anerend_ddgi_params_t* params, anerend_ddgi_t** out) 
   if (!(q.probe_step[0] > 0.0f && q.probe_step[1] > 0.0f && q.probe_step[2] > 0.0f)) return ANEREND_DDGI_E_INVALID;
   anerend_ddgi* h = new anerend_ddgi();
   h->p = q; h->nXZ = q.num_probes_xz; h->nY = q.num_probes_y; h->N = q.rays_per_probe; h->Sx = sx; h->Sy = sy;
-  h->W = 10 * h->nXZ; h->H = 10 * h->nXZ * h->nY; h->P = h->nXZ * h->nXZ;
+  h->W = 10 * h->nXZ; h->H = 10 * h->nXZ * h->nY; h->P = h->nXZ * h->nXZ; h->Pl = h->P;
   Backend& be = h->be;
   if (!be.init(q.device)) { delete h; return ANEREND_DDGI_E_CUDA; }   // no CUDA device: there is no CPU fallback
   const size_t texels = (size_t)h->W * h->H, rays = (size_t)h->nY * h->P * h->N;
@@ -793,6 +801,24 @@ int DDGI_API(atlas_dims)(const anerend_ddgi_t* h, int32_t* w, int32_t* hh) { *w 
 int DDGI_API(download_atlas)(anerend_ddgi_t* h, void* out, size_t bytes) {
   if (bytes != (size_t)h->W * h->H * 8) return fail(h, ANEREND_DDGI_E_INVALID, "atlas size mismatch");
   BE_CHECK(h, h->be.d2h(out, h->dAtlas, bytes)); return 0;
+}
+// Row stripe: this handle updates only the probe rows z = offset + k*stride of every layer it launches (sharding inside
+// the layers: with R ranks, rank r takes (r, R) and every rank carries the same share of every layer's work).
+int DDGI_API(set_row_stripe)(anerend_ddgi_t* h, int32_t offset, int32_t stride) {
+  if (stride < 1 || offset < 0 || offset >= stride || offset >= h->nXZ) return fail(h, ANEREND_DDGI_E_INVALID, "row stripe out of range");
+  h->rowOffset = offset; h->rowStride = stride;
+  h->Pl = ((h->nXZ - offset + stride - 1) / stride) * h->nXZ;
+  return 0;
+}
+// The atlas rows of this handle's stripe in all layers, packed in (layer, row) order: rows * nY blocks of 10 atlas rows.
+int DDGI_API(download_atlas_stripe)(anerend_ddgi_t* h, void* out, size_t bytes) {
+  const size_t rowBytes = (size_t)10 * h->W * 8, rows = (size_t)(h->Pl / h->nXZ);
+  if (bytes != rowBytes * rows * h->nY) return fail(h, ANEREND_DDGI_E_INVALID, "stripe size mismatch");
+  for (int y = 0; y < h->nY; ++y)
+    if (!h->be.d2hStrided((char*)out + rowBytes * rows * y, rowBytes, (const char*)h->dAtlas + rowBytes * ((size_t)y * h->nXZ + h->rowOffset),
+                          rowBytes * h->rowStride, rowBytes, rows))
+      return fail(h, ANEREND_DDGI_E_CUDA, std::string("download_atlas_stripe: ") + h->be.errStr());
+  BE_CHECK(h, h->be.sync()); return 0;
 }
 int DDGI_API(download_atlas_layers)(anerend_ddgi_t* h, const int32_t* layers, uint32_t n, void* out, size_t bytes) {
   const size_t layerBytes = (size_t)h->W * h->W * 8;       // 10*nXZ rows of 10*nXZ RGBA16F texels

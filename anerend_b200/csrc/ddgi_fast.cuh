@@ -152,7 +152,6 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
     total = sPrefix[c.numQueues];
   }
   uint32_t* cursor = &c.qcount[ANY ? FAST_QC_SHADOW : FAST_QC_PRIMARY];
-  const int P = t.nXZ * t.nXZ;
   const V3 sunL = normalize3(-t.lightDir);
   const uint32_t nodeSteps = max(1u, c.tune[0]), refillMin = max(1u, ANY ? c.tune[2] : c.tune[1]);
   const uint32_t stepMin = max(1u, c.tune[4]), triMin = max(1u, c.tune[5]);
@@ -186,7 +185,7 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
           float4* dst = &sRay[warp][lane][0];
           if (!ANY) {
             const uint32_t slot = w % (uint32_t)t.N, probeLin = w / (uint32_t)t.N;
-            const int layerLocal = (int)(probeLin / (uint32_t)P), probe = (int)(probeLin % (uint32_t)P);
+            const int layerLocal = (int)(probeLin / (uint32_t)t.Pl), probe = stripe_probe((int)(probeLin % (uint32_t)t.Pl), t.nXZ, t.rowOffset, t.rowStride);
             const uint32_t ray = t.rayOrder ? (uint32_t)t.rayOrder[slot] : slot;
             const int layer = __ldg(&t.layerMap[layerLocal]);
             const V3 origin = mk3((float)(probe % t.nXZ), (float)layer, (float)(probe / t.nXZ)) * t.step + t.camOff;
@@ -348,7 +347,7 @@ __global__ void __launch_bounds__(PREP_BLOCK) k_shade_prep(const FastCtx c) {
     } else {
       // rmiss:20 + rgen:109
       const uint32_t slot = idx % (uint32_t)t.N, probeLin = idx / (uint32_t)t.N;
-      const int layerLocal = (int)(probeLin / (uint32_t)P), probe = (int)(probeLin % (uint32_t)P);
+      const int layerLocal = (int)(probeLin / (uint32_t)t.Pl), probe = stripe_probe((int)(probeLin % (uint32_t)t.Pl), t.nXZ, t.rowOffset, t.rowStride);
       const uint32_t ray = t.rayOrder ? (uint32_t)t.rayOrder[slot] : slot;
       const size_t o = ((size_t)t.layerMap[layerLocal] * P + probe) * t.N + ray;
       t.rayIrr[o] = make_uint2((uint32_t)f2h(t.sky.x) | ((uint32_t)f2h(t.sky.y) << 16), (uint32_t)f2h(t.sky.z) | (0x3C00u << 16));

@@ -585,10 +585,15 @@ struct TraceCtx {
   unsigned long long* stats;   // 7 counters or null
   int nXZ, nY, N, W, H;
   int numLayers;
+  int Pl, rowOffset, rowStride;   // probes launched per layer: the z-rows rowOffset, rowOffset+rowStride, ... (stripe_probe)
   V3 camOff, step, sky, lightDir;
   float tmin, tmax, sunIntensity;
   uint32_t uboFlags, flags;
 };
+
+// Row stripe (multi-GPU sharding inside the layers): launched probe `pl` of a layer -> probe index in the layer.  A handle
+// updates the probe rows z = rowOffset + k*rowStride of every layer it launches; (0, 1) = all rows.
+HD int stripe_probe(int pl, int nXZ, int rowOffset, int rowStride) { return ((pl / nXZ) * rowStride + rowOffset) * nXZ + pl % nXZ; }
 
 HD float sign_not_zero(float k) { return (k >= 0.0f) ? 1.0f : -1.0f; }            // octahedron_helpers.glsl:1-3
 HD void oct_encode(V3 v, float& ox, float& oy) {                                    // octahedron_helpers.glsl:10-20
@@ -731,7 +736,7 @@ template <bool CNT>
 HD void trace_ray_body(uint32_t idx, const TraceCtx& c) {
   const int P = c.nXZ * c.nXZ;
   const uint32_t slot = idx % (uint32_t)c.N, probeLin = idx / (uint32_t)c.N;
-  const int layerLocal = (int)(probeLin / (uint32_t)P), probe = (int)(probeLin % (uint32_t)P);
+  const int layerLocal = (int)(probeLin / (uint32_t)c.Pl), probe = stripe_probe((int)(probeLin % (uint32_t)c.Pl), c.nXZ, c.rowOffset, c.rowStride);
   const int layer = c.layerMap[layerLocal];
   const uint32_t ray = c.rayOrder ? (uint32_t)c.rayOrder[slot] : slot;
   const int probeX = probe % c.nXZ, probeZ = probe / c.nXZ;
@@ -823,12 +828,13 @@ struct ConvCtx {
   uint2* atlas; float4* texelRecords;        // atlas written in place (or to every peer's copy, see peers)
   uint2* peers[8]; int numPeers;
   int nXZ, nY, N, Sx, Sy, W, H, numLayers;
+  int Pl, rowOffset, rowStride;              // row stripe, as in TraceCtx
   float hysteresis;
 };
 HD void conv_texel_body(uint32_t idx, const ConvCtx& c) {
   const int P = c.nXZ * c.nXZ;
   const int texel = (int)(idx & 63u); const uint32_t probeLin = idx >> 6;
-  const int layerLocal = (int)(probeLin / (uint32_t)P), probe = (int)(probeLin % (uint32_t)P), layer = c.layerMap[layerLocal];
+  const int layerLocal = (int)(probeLin / (uint32_t)c.Pl), probe = stripe_probe((int)(probeLin % (uint32_t)c.Pl), c.nXZ, c.rowOffset, c.rowStride), layer = c.layerMap[layerLocal];
   const int i = texel & 7, j = texel >> 3, probeX = probe % c.nXZ, probeZ = probe / c.nXZ;
   float ux = (2.0f * (float)i + 1.0f) / (2.0f * 8.0f), uy = (2.0f * (float)j + 1.0f) / (2.0f * 8.0f);     // pixelToUv, helpers.glsl:1-4
   ux = ux * 2.0f - 1.0f; uy = uy * 2.0f - 1.0f;

@@ -49,6 +49,9 @@ struct Backend {
     return bytes == 0 || (ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream)) && ok(cudaStreamSynchronize(stream)));
   }
   bool d2hAsync(void* dst, const void* src, size_t bytes) { return bytes == 0 || ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream)); }
+  bool d2hStrided(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows) {
+    return rows == 0 || ok(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToHost, stream));
+  }
   bool d2d(void* dst, const void* src, size_t bytes) { return bytes == 0 || ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream)); }
   bool zero(void* p, size_t bytes) { return bytes == 0 || ok(cudaMemsetAsync(p, 0, bytes, stream)); }
   bool fill(void* p, int byte, size_t bytes) { return bytes == 0 || ok(cudaMemsetAsync(p, byte, bytes, stream)); }
@@ -105,6 +108,10 @@ struct Backend {
   bool h2d(void* d, const void* s, size_t b) { if (b) memcpy(d, s, b); return true; }
   bool d2h(void* d, const void* s, size_t b) { if (b) memcpy(d, s, b); return true; }
   bool d2hAsync(void* d, const void* s, size_t b) { if (b) memcpy(d, s, b); return true; }
+  bool d2hStrided(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t rows) {
+    for (size_t r = 0; r < rows; ++r) memcpy((char*)d + dp * r, (const char*)s + sp * r, w);
+    return true;
+  }
   bool d2d(void* d, const void* s, size_t b) { if (b) memcpy(d, s, b); return true; }
   bool zero(void* p, size_t b) { if (b) memset(p, 0, b); return true; }
   bool fill(void* p, int byte, size_t b) { if (b) memset(p, byte, b); return true; }

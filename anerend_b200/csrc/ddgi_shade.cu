@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const FastCtx c) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nHits; i += gridDim.x * blockDim.x) {
     const uint32_t idx = c.hitq[i];
     const uint32_t slot = idx % (uint32_t)t.N, probeLin = idx / (uint32_t)t.N;
-    const int layerLocal = (int)(probeLin / (uint32_t)P), probe = (int)(probeLin % (uint32_t)P), layer = t.layerMap[layerLocal];
+    const int layerLocal = (int)(probeLin / (uint32_t)t.Pl), probe = stripe_probe((int)(probeLin % (uint32_t)t.Pl), t.nXZ, t.rowOffset, t.rowStride), layer = t.layerMap[layerLocal];
     const uint32_t ray = t.rayOrder ? (uint32_t)t.rayOrder[slot] : slot;
     const V3 origin = mk3((float)(probe % t.nXZ), (float)layer, (float)(probe / t.nXZ)) * t.step + t.camOff;
     const float4 s0 = c.surf[3 * (size_t)idx], s1 = c.surf[3 * (size_t)idx + 1], s2 = c.surf[3 * (size_t)idx + 2];
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) k_probe_convolve_fast(const ConvFastCtx f
   const ConvCtx& c = f.c;
   __shared__ float4 sRad[CONV_G * CONV_CHUNK];                      // 32 KB
   const int P = c.nXZ * c.nXZ;
-  const int blocksPerLayer = (P + CONV_G - 1) / CONV_G;
+  const int blocksPerLayer = (c.Pl + CONV_G - 1) / CONV_G;
   const int layerLocal = (int)blockIdx.x / blocksPerLayer, g0 = ((int)blockIdx.x % blocksPerLayer) * CONV_G;
   const int layer = c.layerMap[layerLocal];
   const int texel = (int)threadIdx.x & 63, sub = (int)threadIdx.x >> 6;
@@ -152,9 +152,9 @@ __global__ void __launch_bounds__(256) k_probe_convolve_fast(const ConvFastCtx f
     for (int e = (int)threadIdx.x; e < CONV_G * CONV_CHUNK; e += 256) {
       const int g = e / CONV_CHUNK, r = e % CONV_CHUNK;
       float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      if (g0 + g < P && r < nr) {
+      if (g0 + g < c.Pl && r < nr) {
         const int pos = r0 + r, ray = (pos % c.Sy) * c.Sx + pos / c.Sy;      // reference loop order
-        const uint2 rr = __ldg(&c.rayIrr[((size_t)layer * P + g0 + g) * c.N + ray]);
+        const uint2 rr = __ldg(&c.rayIrr[((size_t)layer * P + stripe_probe(g0 + g, c.nXZ, c.rowOffset, c.rowStride)) * c.N + ray]);
         v = make_float4(h2f((uint16_t)(rr.x & 0xFFFFu)), h2f((uint16_t)(rr.x >> 16)), h2f((uint16_t)(rr.y & 0xFFFFu)), 1.0f);
       }
       sRad[e] = v;
@@ -182,8 +182,8 @@ __global__ void __launch_bounds__(256) k_probe_convolve_fast(const ConvFastCtx f
   const float hy = c.hysteresis;
 #pragma unroll
   for (int k = 0; k < CONV_PPT; ++k) {
-    const int probe = g0 + sub * CONV_PPT + k;
-    if (probe >= P) continue;
+    if (g0 + sub * CONV_PPT + k >= c.Pl) continue;
+    const int probe = stripe_probe(g0 + sub * CONV_PPT + k, c.nXZ, c.rowOffset, c.rowStride);
     const int probeX = probe % c.nXZ, probeZ = probe / c.nXZ;
     const int ax = 10 * probeX + 1 + i, ay = 10 * c.nXZ * layer + 10 * probeZ + 1 + j;       // pixOffset + pixel (:42,:64)
     const size_t ti = (size_t)ay * c.W + ax;
@@ -209,8 +209,7 @@ static cudaError_t launch_convolve_impl(const ConvFastCtx& f, cudaStream_t s) {
   const uint32_t nw = (uint32_t)c.numLayers * (uint32_t)c.N;
   if (nw == 0) return cudaSuccess;
   k_conv_weights<<<(8u * nw + 127u) / 128u, 128, 0, s>>>(f);
-  const int P = c.nXZ * c.nXZ;
-  const uint32_t blocks = (uint32_t)c.numLayers * (uint32_t)((P + CONV_G - 1) / CONV_G);
+  const uint32_t blocks = (uint32_t)c.numLayers * (uint32_t)((c.Pl + CONV_G - 1) / CONV_G);
   k_probe_convolve_fast<<<blocks, 256, 0, s>>>(f);
   return cudaGetLastError();
 }

@@ -162,8 +162,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fast-math", action="store_true", help="time the FAST_MATH build as the headline (default: exact build)")
     ap.add_argument("--no-alt", action="store_true", help="skip the second-build and 1-GPU strong-scaling-base measurements")
-    ap.add_argument("--deal", default="measured", choices=["measured", "static"],
-                    help="N>1, fused exchange: deal the probe layers by measured per-layer cost (default) or by the static mirrored/zigzag rule")
+    ap.add_argument("--deal", default="stripes", choices=["stripes", "measured", "static"],
+                    help="N>1, fused exchange: every rank takes the probe rows z = rank mod N of every layer (default; needs nXZ "
+                         "divisible by N), or whole layers dealt by measured per-layer cost, or by the static mirrored/zigzag rule")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="N>1: atlas exchange fused into the convolution over NVLink peer memory (default) or NCCL all-gather")
     args = ap.parse_args()
@@ -191,9 +192,10 @@ def main():
     # multi-GPU: interleaved layer sets (balanced) when nY divides evenly, contiguous slabs otherwise
     mirrored = world > 1 and ny % (2 * world) == 0
     interleaved = world > 1 and (mirrored or ny % world == 0)
-    measured_deal = world > 1 and args.exchange == "fused" and args.deal == "measured"
-    slab = (0, ny) if (interleaved or measured_deal) else sharding.slab_for_rank(ny, rank, world)
-    my_layers = (sharding.mirrored_slabs_for_rank(ny, rank, world) if mirrored else
+    stripes = world > 1 and args.exchange == "fused" and args.deal == "stripes" and nxz % world == 0
+    measured_deal = world > 1 and args.exchange == "fused" and (args.deal == "measured" or (args.deal == "stripes" and not stripes))
+    slab = (0, ny) if (interleaved or measured_deal or stripes) else sharding.slab_for_rank(ny, rank, world)
+    my_layers = (list(range(ny)) if stripes else sharding.mirrored_slabs_for_rank(ny, rank, world) if mirrored else
                  sharding.layers_for_rank(ny, rank, world) if interleaved else list(range(slab[0], slab[1])))
     # point lights (extension E1) + dead-shadow-ray elimination (radiance bit-identical, tests/test_oracle_kat.py);
     # the default kernels are the exact build (atlas bit-identical to the oracle); FAST_MATH is timed as a second figure
@@ -211,8 +213,10 @@ def main():
 
     fused = world > 1 and args.exchange == "fused"
 
-    def make_handle(hflags, hslab, connect=False):
+    def make_handle(hflags, hslab, connect=False, striped=True):
         hh = A.Ddgi(A.make_params(nxz, ny, nr, flags=hflags, slab=hslab, device=local_rank))
+        if stripes and striped:
+            hh.set_row_stripe(rank, world)
         hh.upload_scene(scene)
         hh.set_scene_ubo(scene.ubo)
         hh.build_accel()
@@ -253,7 +257,7 @@ def main():
         h.reset()
     if fused:
         connect_handle(h)
-    my_rays = nxz * nxz * len(my_layers) * nr
+    my_rays = nxz * nxz * len(my_layers) * nr // (world if stripes else 1)
     nbytes = h.atlas_device_ptr()[1]
     host_atlas = torch.empty((h.atlas_height, h.atlas_width, 4), dtype=torch.int16, pin_memory=True)   # pinned result buffer
     host_np = host_atlas.numpy().view(np.uint16)
@@ -327,6 +331,12 @@ def main():
     sampler.start()
     dev_ms, rt_ms, conv_ms, launches, step = timed(h, args.steps, args.warmup, do_gather, world > 1)
     clocks = sampler.stop()
+    per_rank = None
+    if world > 1:                                  # own trace / convolve(+exchange) ms of every rank: shows the load balance
+        mine = torch.tensor([float(np.mean(rt_ms)), float(np.mean(conv_ms))], device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"trace_ms": [round(float(t[0]), 4) for t in allr], "convolve_exchange_ms": [round(float(t[1]), 4) for t in allr]}
     ms_per_step = dev_ms / args.steps
     value = all_rays / (ms_per_step * 1e-3) / 1e6
 
@@ -338,10 +348,15 @@ def main():
     t0 = time.perf_counter()
     # result read-back: the whole atlas on one GPU; at N>1 every rank reads back the layers it computed (together the
     # ranks return the whole atlas once per step)
-    own_np = host_np.reshape(-1)[:len(my_layers) * h.atlas_width * h.atlas_width * 4].reshape(len(my_layers), h.atlas_width, h.atlas_width, 4)
+    if stripes:
+        own_np = host_np.reshape(-1)[:host_np.size // world].reshape(ny, nxz // world, 10, h.atlas_width, 4)
+    else:
+        own_np = host_np.reshape(-1)[:len(my_layers) * h.atlas_width * h.atlas_width * 4].reshape(len(my_layers), h.atlas_width, h.atlas_width, 4)
     for k in range(e2e_steps):
         step(args.warmup + (k % args.steps))
-        if world > 1:
+        if stripes:
+            h.download_atlas_stripe(own_np)
+        elif world > 1:
             h.download_atlas_layers(my_layers, own_np)
         else:
             h.download_atlas(host_np)            # D2H of the result (synchronous)
@@ -352,7 +367,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     e2e_value = all_rays * e2e_steps / e2e_s / 1e6
-    h2d_bytes = len(my_layers) * nr * 16 + 568 + 64 * ny
+    h2d_bytes = ny * nr * 16 + 568 + 64 * ny           # direction table rows of all layers + scene UBO + rotations
     d2h_bytes = nbytes if world == 1 else int(own_np.nbytes)
 
     # ---- second figure: the other arithmetic build (FAST_MATH <-> exact), same workload, fewer steps ----------
@@ -380,7 +395,7 @@ def main():
         if rank == 0:
             multi = np.empty_like(host_np)
             h.download_atlas(multi)
-            hb = make_handle(flags, (0, ny))
+            hb = make_handle(flags, (0, ny), striped=False)
             bsteps = 3
             bms, _, _, _, _ = timed(hb, bsteps, 1, False, False)
             base1 = {"n_gpus": 1, "ms_per_step": bms / bsteps, "value": all_rays / (bms / bsteps * 1e-3) / 1e6, "unit": UNIT, "steps": bsteps}
@@ -400,7 +415,7 @@ def main():
     if rank == 0:
         # ---- roofline of the dominant kernel: counted, untimed run of the same update ----------
         hc = make_handle(flags | L.FLAG_COUNTERS, slab)
-        if interleaved or measured_deal:
+        if interleaved or measured_deal or stripes:
             hc.update_layers(my_layers, rots[args.warmup])
         else:
             hc.update(-1, rots[args.warmup])
@@ -453,10 +468,12 @@ def main():
         cfg = workload_desc(name, scene, grid, world)
         if balanced is not None:
             cfg["parallelism"] = f"probe layers dealt to {world} ranks by measured per-layer cost (LPT)"
+        if stripes:
+            cfg["parallelism"] = f"row stripes: rank r updates the probe rows z = r mod {world} of every layer"
         cfg.update({"l2": "flushed between timed iterations (256 MiB write)" if flush else "working set larger than L2, no flush",
                     "bvh8_nodes": int(info.num_nodes), "accel_build_ms": accel_ms,
-                    "atlas_exchange": ("fused: convolution stores each texel into all peers' atlases over NVLink (cudaIpc), "
-                                       "device-side barrier before and after; no collective" if fused else
+                    "atlas_exchange": ("peer push: after the convolution a copy kernel stores this rank's atlas rows into all peers' atlases "
+                                       "over NVLink (cudaIpc-mapped), device-side barrier before and after; no collective" if fused else
                                        "2 in-place nccl all_gathers of mirrored slabs on the handle's stream" if mirrored else
                                        "nccl all_gather of interleaved layers (pack, gather, scatter) on the handle's stream" if interleaved
                                        else "nccl all_gather of contiguous slabs, in place") if world > 1 else "none"})
@@ -468,7 +485,7 @@ def main():
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "update_ms": {"trace": rt_avg, "convolve": float(np.mean(conv_ms)), "full_grid": ms_per_step},
                 "arithmetic": "fast_math (1e-4 relative per update)" if args.fast_math else "exact (atlas bit-identical to the oracle)",
-                "other_build": alt, "strong_scaling_base": base1, "exchange_check_vs_1gpu": verified, "layer_deal": balanced}
+                "other_build": alt, "strong_scaling_base": base1, "exchange_check_vs_1gpu": verified, "layer_deal": balanced, "per_rank_ms": per_rank}
     close_handle(h, fused)
     if world > 1:
         dist.barrier()

@@ -182,6 +182,12 @@ int anerend_cuda_ddgi_atlas_dims(const anerend_ddgi_t* h, int32_t* width, int32_
 /* "ProbeRaysConvTex" as row-major RGBA16F, width*height*8 bytes (mirrors downloadDDGIAtlas,
  * VulkanRenderer.cpp:2706-2771). */
 int anerend_cuda_ddgi_download_atlas(anerend_ddgi_t* h, void* rgba16f, size_t bytes);
+/* Row stripe (sharding inside the layers): the handle updates only the probe rows z = offset + k*stride of
+ * every layer it launches; (0, 1) = all rows (default).  With R ranks, rank r takes (r, R): every rank carries the same
+ * share of every layer, so the ranks finish together whatever the scene looks like.  _download_atlas_stripe returns
+ * this handle's rows of all layers, packed (layer, row): num_probes_y * rows * 10 * width * 8 bytes. */
+int anerend_cuda_ddgi_set_row_stripe(anerend_ddgi_t* h, int32_t offset, int32_t stride);
+int anerend_cuda_ddgi_download_atlas_stripe(anerend_ddgi_t* h, void* rgba16f, size_t bytes);
 /* The atlas rows of `num_layers` Y-layers (10*nXZ rows each), packed in the order given: what one rank of a sharded
  * update reads back (its own layers); bytes = num_layers * (10*nXZ)^2 * 8. */
 int anerend_cuda_ddgi_download_atlas_layers(anerend_ddgi_t* h, const int32_t* layers, uint32_t num_layers, void* rgba16f, size_t bytes);

@@ -342,3 +342,33 @@ def test_slab_handles_assemble_the_full_atlas(oracle, make_gpu):
         assert np.array_equal(merged, full.download_atlas())
     for h in [full] + parts:
         h.close()
+
+
+@pytest.mark.gpu
+def test_row_stripe_handles_assemble_the_full_atlas(make_gpu):
+    """Sharding inside the layers on one device: handle r updates the probe rows z = r mod R of every layer with the
+    production kernels; the merged rows equal the single-handle atlas bit for bit, update after update."""
+    nxz, ny, nr, world = 8, 4, 64, 4
+    scene = scenes.cornell_box(grid=(nxz, ny, nr), wall_res=10, box_res=3)
+    p = make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS | L.FLAG_SKIP_DEAD_SHADOW_RAYS)
+    full, parts = make_gpu(p), [make_gpu(p) for _ in range(world)]
+    rots = parity.setup_pair(scene, [full] + parts, seed=8)
+    for r, h in enumerate(parts):
+        h.set_row_stripe(r, world)
+    for it in range(3):
+        full.update(-1, rots)
+        for h in parts:
+            h.update(-1, rots)
+        slabs = [h.download_atlas() for h in parts]
+        merged = slabs[0].copy()
+        for y in range(ny):
+            for z in range(nxz):
+                r0 = 10 * nxz * y + 10 * z
+                merged[r0:r0 + 10] = slabs[z % world][r0:r0 + 10]
+        own = parts[1].download_atlas_stripe()
+        assert np.array_equal(own[2, 1], merged[10 * nxz * 2 + 10 * 5:10 * nxz * 2 + 10 * 5 + 10])     # layer 2, row z = 1 + 1*4
+        for h in parts:
+            h.upload_atlas(merged)
+        assert np.array_equal(merged, full.download_atlas())
+    for h in [full] + parts:
+        h.close()

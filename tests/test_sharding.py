@@ -179,3 +179,47 @@ def test_download_atlas_layers_returns_the_layer_rows(make_emu):
     with pytest.raises(Exception):
         e.download_atlas_layers([3])
     e.close()
+
+
+def _stripe_merge(handles, nxz, ny, world):
+    """What the peer push / an all-gather does for row stripes: probe row z of every layer comes from handle z % world."""
+    parts = [h.download_atlas() for h in handles]
+    merged = parts[0].copy()
+    for y in range(ny):
+        for z in range(nxz):
+            r0 = 10 * nxz * y + 10 * z
+            merged[r0:r0 + 10] = parts[z % world][r0:r0 + 10]
+    return merged
+
+
+def test_row_stripes_assemble_the_full_atlas(make_emu):
+    """Sharding inside the layers: handle r updates the probe rows z = r mod R of every layer; after exchanging rows
+    the atlas equals the one a single handle computes (jacobi updates), also when nXZ is not a multiple of R."""
+    from anerend_b200 import layouts as L, make_params, scenes
+    from tests import parity
+    nxz, ny, nr, world = 5, 2, 64, 3
+    scene = scenes.random_soup(41, ntris=400, grid=(nxz, ny, nr))
+    p = make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS)
+    full, parts = make_emu(p), [make_emu(p) for _ in range(world)]
+    rots = parity.setup_pair(scene, [full] + parts, seed=12)
+    for r, h in enumerate(parts):
+        h.set_row_stripe(r, world)
+    for it in range(2):
+        full.update(-1, rots)
+        for h in parts:
+            h.update(-1, rots)
+        merged = _stripe_merge(parts, nxz, ny, world)
+        for r, h in enumerate(parts):
+            own = h.download_atlas_stripe()
+            rows = list(range(r, nxz, world))
+            assert own.shape == (ny, len(rows), 10, 10 * nxz, 4)
+            for y in range(ny):
+                for k, z in enumerate(rows):
+                    r0 = 10 * nxz * y + 10 * z
+                    assert np.array_equal(own[y, k], merged[r0:r0 + 10])
+            h.upload_atlas(merged)
+        assert np.array_equal(merged, full.download_atlas())
+    with pytest.raises(Exception):
+        parts[0].set_row_stripe(3, 3)
+    for h in [full] + parts:
+        h.close()
