@@ -186,6 +186,15 @@ class DdgiHandle:
             self._call("sync")
 
     # ---- results ---------------------------------------------------------------------------------
+    def indirect_diffuse(self, points, view_pos, clamp_to_edge=False):
+        """Atlas consumer: calcIndirectDiffuseLight for surface points [n, 12] float32 (pos, normal, albedo, metallic,
+        roughness, unused) -> [n, 4] float32 (rgb, 0).  clamp_to_edge: the deferred pass's sampler; False: REPEAT."""
+        points = _c(points, np.float32).reshape(-1, 12)
+        out = np.empty((points.shape[0], 4), np.float32)
+        vp = (C.c_float * 3)(*[float(x) for x in view_pos])
+        self._call("indirect_diffuse", _ptr(points), C.c_uint32(points.shape[0]), vp, C.c_int32(1 if clamp_to_edge else 0), _ptr(out))
+        return out
+
     def set_row_stripe(self, offset, stride):
         """This handle updates only the probe rows z = offset + k*stride of every layer (multi-GPU sharding inside the layers)."""
         self._call("set_row_stripe", C.c_int32(offset), C.c_int32(stride))

@@ -40,6 +40,7 @@ DDGI_KERNEL(k_probe_trace, trace_ray_body<false>, TraceCtx)
 DDGI_KERNEL(k_probe_trace_counted, trace_ray_body<true>, TraceCtx)
 DDGI_KERNEL(k_probe_convolve, conv_texel_body, ConvCtx)
 DDGI_KERNEL(k_probe_translate, translate_body, TransCtx)
+DDGI_KERNEL(k_indirect_diffuse, indirect_diffuse_body, ConsumerCtx)
 DDGI_KERNEL(k_atlas_clear, clear_body, ClearCtx)
 
 // ------------------------------------------------------------------------------------------------ handle
@@ -794,6 +795,39 @@ int DDGI_API(frame)(anerend_ddgi_t* h, const float rot[16], int32_t* layerOut) {
   if (layerOut) *layerOut = layer;                                     // blackboard "ProbeLayer" (:158)
   h->currentLayer = (h->currentLayer + 1 >= h->nY) ? 0 : h->currentLayer + 1;   // :160-164
   rc = convolveLayers(h, &layer, 1); h->be.mark(3); h->timed[2] = true;
+  return rc;
+}
+
+// ---- atlas consumer ------------------------------------------------------------------------
+namespace {
+int indirectDiffuse(anerend_ddgi* h, const float4* dPoints, uint32_t count, const float viewPos[3], int clampSampler, float4* dOut) {
+  if (!h->haveUbo) return fail(h, ANEREND_DDGI_E_STATE, "indirect_diffuse before set_scene_ubo");
+  ConsumerCtx c{};
+  c.t.atlas = h->dAtlas; c.t.nXZ = h->nXZ; c.t.nY = h->nY; c.t.N = h->N; c.t.W = h->W; c.t.H = h->H; c.t.clampSampler = clampSampler ? 1 : 0;
+  const float* step = h->p.probe_step;       // camOffset as in sampleProbe (pbr_light.glsl:295-301), from the CURRENT camera
+  int cix = (int)(h->ubo.camera_pos[0] / step[0]), ciz = (int)(h->ubo.camera_pos[2] / step[2]);
+  c.t.camOff = mk3(float(cix) * step[0] - step[0] * float(h->nXZ) / 2.0f, 0.0f, float(ciz) * step[2] - step[2] * float(h->nXZ) / 2.0f);
+  c.t.step = mk3(step[0], step[1], step[2]);
+  c.points = dPoints; c.out = dOut; c.viewPos = mk3(viewPos[0], viewPos[1], viewPos[2]);
+  DDGI_LAUNCH(h->be, k_indirect_diffuse, indirect_diffuse_body, count, c, 128);
+  BE_CHECK(h, h->be.check());
+  return 0;
+}
+}  // namespace
+int DDGI_API(indirect_diffuse_device)(anerend_ddgi_t* h, const void* dPoints, uint32_t count, const float viewPos[3], int32_t clampToEdge, void* dOut) {
+  if (!dPoints || !dOut || !viewPos) return fail(h, ANEREND_DDGI_E_INVALID, "null argument");
+  return indirectDiffuse(h, (const float4*)dPoints, count, viewPos, clampToEdge, (float4*)dOut);
+}
+int DDGI_API(indirect_diffuse)(anerend_ddgi_t* h, const float* points, uint32_t count, const float viewPos[3], int32_t clampToEdge, float* outRgba) {
+  if (!points || !outRgba || !viewPos) return fail(h, ANEREND_DDGI_E_INVALID, "null argument");
+  if (count == 0) return 0;
+  Backend& be = h->be;
+  float4 *dP = nullptr, *dO = nullptr;
+  if (!be.alloc(&dP, 3 * (size_t)count) || !be.alloc(&dO, count)) { be.free(dP); be.free(dO); return fail(h, ANEREND_DDGI_E_CUDA, std::string("indirect_diffuse: ") + be.errStr()); }
+  int rc = be.h2d(dP, points, (size_t)count * 48) ? 0 : fail(h, ANEREND_DDGI_E_CUDA, std::string("indirect_diffuse: ") + be.errStr());
+  if (!rc) rc = indirectDiffuse(h, dP, count, viewPos, clampToEdge, dO);
+  if (!rc && !be.d2h(outRgba, dO, (size_t)count * 16)) rc = fail(h, ANEREND_DDGI_E_CUDA, std::string("indirect_diffuse: ") + be.errStr());
+  be.sync(); be.free(dP); be.free(dO);
   return rc;
 }
 

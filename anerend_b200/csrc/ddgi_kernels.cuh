@@ -586,6 +586,7 @@ struct TraceCtx {
   int nXZ, nY, N, W, H;
   int numLayers;
   int Pl, rowOffset, rowStride;   // probes launched per layer: the z-rows rowOffset, rowOffset+rowStride, ... (stripe_probe)
+  int clampSampler;               // atlas sampler addressing: 0 = REPEAT (probe RT pass, SpecularGIRT), 1 = CLAMP_TO_EDGE (deferred lighting)
   V3 camOff, step, sky, lightDir;
   float tmin, tmax, sunIntensity;
   uint32_t uboFlags, flags;
@@ -667,14 +668,16 @@ HD V3 atlas_texel(const TraceCtx& c, int x, int y) {     // x, y already wrapped
 // texel of the probe on this axis, `size` = atlas extent, o = octEncode(normal)*0.5+0.5 on this axis.
 // texel coordinates reach 10*nXZ*nY (2880 at C3): one ulp there is 2.4e-4 texels, so the address math stays exact
 struct AxisTap { int i0, i1; float f; };
-HD AxisTap probe_axis_tap(int start, int size, float o) {
+HD AxisTap probe_axis_tap(int start, int size, float o, int clampSampler = 0) {
   int end = start + 8 - 1;
   float ts = xdiv(xadd(xmul(2.0f, (float)start), 1.0f), xmul(2.0f, (float)size));
   float te = xdiv(xadd(xmul(2.0f, (float)end), 1.0f), xmul(2.0f, (float)size));
   float uv = xadd(ts, xmul(xsub(te, ts), o));
   float x = xsub(xmul(uv, (float)size), 0.5f);
   float f0 = floorf(x);
-  AxisTap t; t.f = xsub(x, f0); int i = (int)f0; t.i0 = wrap_repeat(i, size); t.i1 = wrap_repeat(i + 1, size);
+  AxisTap t; t.f = xsub(x, f0); int i = (int)f0;
+  if (clampSampler) { t.i0 = clampi(i, 0, size - 1); t.i1 = clampi(i + 1, 0, size - 1); }      // VK_SAMPLER_ADDRESS_MODE_CLAMP_TO_EDGE
+  else { t.i0 = wrap_repeat(i, size); t.i1 = wrap_repeat(i + 1, size); }
   return t;
 }
 HD V3 atlas_bilinear(const TraceCtx& c, const AxisTap& ax, const AxisTap& ay) {
@@ -696,9 +699,9 @@ HD V3 sample_probe(const TraceCtx& c, V3 worldPos, V3 normal) {
   float o0, o1; oct_encode(normalize3x(normal), o0, o1);
   o0 = xmul(xadd(o0, 1.0f), 0.5f); o1 = xmul(xadd(o1, 1.0f), 0.5f);
   AxisTap tapX[2], tapY[4];
-  for (int ox = 0; ox < 2; ++ox) tapX[ox] = probe_axis_tap((8 + 2) * (px + ox) + 1, c.W, o0);
+  for (int ox = 0; ox < 2; ++ox) tapX[ox] = probe_axis_tap((8 + 2) * (px + ox) + 1, c.W, o0, c.clampSampler);
   for (int oy = 0; oy < 2; ++oy) for (int oz = 0; oz < 2; ++oz)
-    tapY[oy + 2 * oz] = probe_axis_tap((8 + 2) * c.nXZ * (py + oy) + (8 + 2) * (pz + oz) + 1, c.H, o1);
+    tapY[oy + 2 * oz] = probe_axis_tap((8 + 2) * c.nXZ * (py + oy) + (8 + 2) * (pz + oz) + 1, c.H, o1, c.clampSampler);
   float sumW = 0.0f; V3 sum = mk3(0.0f);
   // corner order of the source: 000,111,110,100,011,010,001,101 packed as x | y<<1 | z<<2 per nibble
   const uint32_t order = 0x0u | (0x7u << 4) | (0x3u << 8) | (0x1u << 12) | (0x6u << 16) | (0x2u << 20) | (0x4u << 24) | (0x5u << 28);
@@ -729,6 +732,16 @@ HD V3 calc_indirect(const TraceCtx& c, V3 normal, V3 albedo, float metallic, flo
   V3 kD = mk3(1.0f) - kS; kD = kD * (1.0f - metallic);
   V3 irradiance = sample_probe(c, worldPos, normal);
   return kD * (irradiance * albedo);
+}
+
+// Atlas consumer: calcIndirectDiffuseLight for a batch of surface points, what deferred_tiled.comp:264-296
+// (CLAMP_TO_EDGE sampler, DeferredLightingRenderPass.cpp:192-200) and mirror_reflections.rchit:92-118 (REPEAT) evaluate per
+// pixel / per hit against "ProbeRaysConvTex".  Point record: 3 x float4 = (pos.xyz, n.x) (n.yz, albedo.xy) (albedo.z, metallic, roughness, -).
+struct ConsumerCtx { TraceCtx t; const float4* points; float4* out; V3 viewPos; };
+HD void indirect_diffuse_body(uint32_t i, const ConsumerCtx& c) {
+  const float4 a = c.points[3 * (size_t)i], b = c.points[3 * (size_t)i + 1], d = c.points[3 * (size_t)i + 2];
+  const V3 r = calc_indirect(c.t, mk3(a.w, b.x, b.y), mk3(b.z, b.w, d.x), d.y, d.z, mk3(a.x, a.y, a.z), c.viewPos);
+  c.out[i] = make_float4(r.x, r.y, r.z, 0.0f);
 }
 
 // rgen main + rchit main + rmiss main for one probe ray (rgen:48-111, rchit:24-111, rmiss:17-21)

@@ -182,6 +182,18 @@ int anerend_cuda_ddgi_atlas_dims(const anerend_ddgi_t* h, int32_t* width, int32_
 /* "ProbeRaysConvTex" as row-major RGBA16F, width*height*8 bytes (mirrors downloadDDGIAtlas,
  * VulkanRenderer.cpp:2706-2771). */
 int anerend_cuda_ddgi_download_atlas(anerend_ddgi_t* h, void* rgba16f, size_t bytes);
+/* ---- atlas consumer ---------------------------------------------------------
+ * calcIndirectDiffuseLight (pbr_light.glsl:365-388) for `count` surface points against the current atlas: what
+ * deferred_tiled.comp:264-296 evaluates per G-buffer pixel (CLAMP_TO_EDGE sampler, DeferredLightingRenderPass.cpp:192-200;
+ * clamp_to_edge = 1) and mirror_reflections.rchit:92-118 per reflection hit (default REPEAT sampler, SpecularGIRTPass.cpp:66;
+ * clamp_to_edge = 0).  The probe grid is centred on the camera of the last _set_scene_ubo, like the shader's.
+ * points: 12 floats each = pos.xyz, normal.xyz, albedo.rgb, metallic, roughness, unused.  out: 4 floats each (rgb, 0).
+ * The _device variant takes device pointers (16-byte aligned) and runs asynchronously on the handle's stream. */
+int anerend_cuda_ddgi_indirect_diffuse(anerend_ddgi_t* h, const float* points, uint32_t count, const float view_pos[3],
+                                       int32_t clamp_to_edge, float* out_rgba);
+int anerend_cuda_ddgi_indirect_diffuse_device(anerend_ddgi_t* h, const void* d_points, uint32_t count, const float view_pos[3],
+                                              int32_t clamp_to_edge, void* d_out_rgba);
+
 /* Row stripe (sharding inside the layers): the handle updates only the probe rows z = offset + k*stride of
  * every layer it launches; (0, 1) = all rows (default).  With R ranks, rank r takes (r, R): every rank carries the same
  * share of every layer, so the ranks finish together whatever the scene looks like.  _download_atlas_stripe returns

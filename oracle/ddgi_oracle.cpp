@@ -532,7 +532,9 @@ struct ddgi_oracle {
   // ---- atlas sampling: sampler2D probeTex with VK_FILTER_LINEAR, REPEAT (PipelineUtil.h:98-112) --------
   // Defined arithmetic: unnormalised coord = uv*size - 0.5, weights = fract, texel fetch with REPEAT wrap,
   // (1-fx)(1-fy)t00 + fx(1-fy)t10 + (1-fx)fy t01 + fx fy t11 in fp32 (Vulkan spec §16.8 formula).
+  bool clampSampler = false;     // consumers only: VK_SAMPLER_ADDRESS_MODE_CLAMP_TO_EDGE (DeferredLightingRenderPass.cpp:192-200)
   V3 texel(int x, int y) const {
+    if (clampSampler) { x = std::min(std::max(x, 0), W - 1); y = std::min(std::max(y, 0), H - 1); }
     x %= W; if (x < 0) x += W; y %= H; if (y < 0) y += H;
     const uint16_t* t = &atlas[4 * ((size_t)y * W + x)];
     return v3(h2f(t[0]), h2f(t[1]), h2f(t[2]));
@@ -949,6 +951,17 @@ int ddgi_oracle_calc_indirect(ddgi_oracle_t* h, const float n[3], const float a[
                               const float wp[3], const float vp[3], float out[3]) {
   V3 r = h->calcIndirectDiffuseLight(v3(n[0], n[1], n[2]), v3(a[0], a[1], a[2]), metallic, roughness, v3(wp[0], wp[1], wp[2]), v3(vp[0], vp[1], vp[2]));
   out[0] = r.x; out[1] = r.y; out[2] = r.z; return 0;
+}
+// deferred_tiled.comp:264-296 / mirror_reflections.rchit:92-118: calcIndirectDiffuseLight per surface point (12 floats each)
+int ddgi_oracle_indirect_diffuse(ddgi_oracle_t* h, const float* pts, uint32_t count, const float vp[3], int32_t clampToEdge, float* out) {
+  h->clampSampler = clampToEdge != 0;
+  for (uint32_t i = 0; i < count; ++i) {
+    const float* q = pts + 12 * (size_t)i;
+    V3 r = h->calcIndirectDiffuseLight(v3(q[3], q[4], q[5]), v3(q[6], q[7], q[8]), q[9], q[10], v3(q[0], q[1], q[2]), v3(vp[0], vp[1], vp[2]));
+    out[4 * (size_t)i] = r.x; out[4 * (size_t)i + 1] = r.y; out[4 * (size_t)i + 2] = r.z; out[4 * (size_t)i + 3] = 0.0f;
+  }
+  h->clampSampler = false;
+  return 0;
 }
 int ddgi_oracle_intersect(const float o[3], const float d[3], const float a[3], const float b[3], const float c[3],
                           float tmin, float tmax, float* t, float* u, float* v) {

@@ -81,6 +81,7 @@ void ddgi_oracle_calc_light(const float normal[3], const float albedo[3], float 
                             const float world_pos[3], const float view_pos[3], const anerend_light_t* light,
                             int32_t directional, const float light_dir[3], float sun_intensity, float out[3]);
 /* calcIndirectDiffuseLight against the handle's current atlas/UBO (pbr_light.glsl:365-388). */
+int  ddgi_oracle_indirect_diffuse(ddgi_oracle_t* h, const float* points, uint32_t count, const float view_pos[3], int32_t clamp_to_edge, float* out_rgba);
 int  ddgi_oracle_calc_indirect(ddgi_oracle_t* h, const float normal[3], const float albedo[3], float metallic,
                                float roughness, const float world_pos[3], const float view_pos[3], float out[3]);
 /* Möller–Trumbore exactly as DESIGN.md specifies; returns 1 on hit with t in (tmin,tmax). */

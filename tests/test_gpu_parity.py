@@ -372,3 +372,33 @@ def test_row_stripe_handles_assemble_the_full_atlas(make_gpu):
         assert np.array_equal(merged, full.download_atlas())
     for h in [full] + parts:
         h.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("clamp", [False, True], ids=["repeat", "clamp_to_edge"])
+def test_atlas_consumer_matches_oracle_bit_for_bit(clamp, oracle, make_gpu):
+    """SURVEY §8f N1 through the C ABI: calcIndirectDiffuseLight for a synthetic G-buffer against the atlas the CUDA update
+    produced (host-pointer entry point and device-pointer entry point)."""
+    import torch
+    from tests.consumer_points import surface_points
+    nxz, ny, nr = 8, 4, 64
+    scene = scenes.cornell_box(grid=(nxz, ny, nr), wall_res=10, box_res=3)
+    p = make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS)
+    o, g = oracle.Oracle(p), make_gpu(p)
+    rots = parity.setup_pair(scene, (o, g), seed=5)
+    for h in (o, g):
+        for _ in range(2):
+            h.update(-1, rots)
+    assert np.array_equal(o.download_atlas(), g.download_atlas())
+    pts = surface_points(20000, nxz, ny, seed=23)
+    view = (0.0, 1.0, 0.0)
+    ro, rg = o.indirect_diffuse(pts, view, clamp), g.indirect_diffuse(pts, view, clamp)
+    assert np.array_equal(ro.view(np.uint32), rg.view(np.uint32))
+    dp = torch.from_numpy(pts).cuda()
+    dout = torch.empty((pts.shape[0], 4), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    g.indirect_diffuse_device(dp.data_ptr(), pts.shape[0], view, clamp, dout.data_ptr())
+    g.sync()
+    assert np.array_equal(dout.cpu().numpy().view(np.uint32), ro.view(np.uint32))
+    o.close()
+    g.close()

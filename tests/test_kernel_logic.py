@@ -158,3 +158,27 @@ def test_error_behaviour(make_emu):
     e.close()
     with pytest.raises(Exception):
         make_emu(make_params(4, 2, 48))                   # rays per probe must tile
+
+
+@pytest.mark.parametrize("clamp", [False, True], ids=["repeat", "clamp_to_edge"])
+def test_atlas_consumer_matches_oracle(clamp, oracle, make_emu):
+    """calcIndirectDiffuseLight per surface point (deferred_tiled.comp:264-296 with the CLAMP_TO_EDGE sampler,
+    mirror_reflections.rchit:92-118 with REPEAT) against the atlas the update produced."""
+    from tests.consumer_points import surface_points
+    scene, (nxz, ny, nr) = SCENES["cornell"]()
+    p = make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS)
+    o, e = oracle.Oracle(p), make_emu(p)
+    rots = parity.setup_pair(scene, (o, e), seed=5)
+    for h in (o, e):
+        for _ in range(2):
+            h.update(-1, rots)
+    assert np.array_equal(o.download_atlas(), e.download_atlas())
+    pts = surface_points(3000, nxz, ny, seed=17)
+    view = scene.ubo["camera_pos"][0][:3] if hasattr(scene.ubo, "dtype") else (0.0, 1.0, 0.0)
+    ro, re = o.indirect_diffuse(pts, view, clamp), e.indirect_diffuse(pts, view, clamp)
+    assert np.isfinite(ro).all() and (ro[:, :3] >= 0).all() and ro[:, :3].max() > 0
+    assert np.array_equal(ro.view(np.uint32), re.view(np.uint32))
+    other = o.indirect_diffuse(pts, view, not clamp)
+    assert not np.array_equal(other, ro)            # the sampler mode matters at the edge of the grid
+    o.close()
+    e.close()

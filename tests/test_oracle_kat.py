@@ -337,3 +337,34 @@ def test_skipping_dead_shadow_rays_changes_nothing_but_the_ray_count(oracle):
         assert sb["shadow_rays"] < sa["shadow_rays"] and sa["primary_hits"] == sb["primary_hits"]
         a.close()
         b.close()
+
+
+def test_atlas_consumer_uniform_atlas_known_answer(oracle):
+    """KAT for the consumer: with every atlas texel = L, every probe tap returns L, so the sqrt-space blend
+    gives irradiance = L * 0.5 * 3.1415926 whatever the weights, and calcIndirectDiffuseLight = kD * irradiance * albedo
+    with kD = (1 - kS)(1 - metallic), kS = F0 + (max(1 - r^4... see fresnelSchlickRoughness(cos, F0, roughness^2)."""
+    n_xz, n_y = 4, 2
+    o = oracle.Oracle(make_params(n_xz, n_y, 64))
+    s = scenes.empty_scene(grid=(n_xz, n_y, 64))
+    o.set_scene_ubo(s.ubo)
+    W, H = 10 * n_xz, 10 * n_xz * n_y
+    Lrgb = np.array([0.25, 1.0, 4.0], np.float32)             # exact in fp16, exact square roots
+    a = np.zeros((H, W, 4), np.float16); a[..., :3] = Lrgb; a[..., 3] = 1.0
+    o.upload_atlas(a.view(np.uint16))
+    pts = np.zeros((3, 12), np.float32)
+    pts[:, 0:3] = [(0.3, 1.1, -0.4), (-1.2, 0.5, 1.7), (0.9, 2.5, 0.1)]        # inside the grid: taps never leave it
+    pts[:, 3:6] = [(0, 1, 0), (0.6, 0.0, 0.8), (-1, 0, 0)]
+    pts[:, 6:9] = [(0.8, 0.5, 0.2), (1, 1, 1), (0.3, 0.3, 0.3)]
+    pts[:, 9] = [0.0, 0.0, 0.5]; pts[:, 10] = [1.0, 0.5, 0.3]
+    view = np.array([0.0, 5.0, 0.0], np.float32)
+    for clamp in (False, True):
+        got = o.indirect_diffuse(pts, view, clamp)[:, :3]
+        for i in range(3):
+            pos, n, alb, met, rough = pts[i, 0:3], pts[i, 3:6], pts[i, 6:9], pts[i, 9], pts[i, 10]
+            V = (view - pos) / np.linalg.norm(view - pos)
+            F0 = 0.04 * (1 - met) + alb * met
+            cos = max(float(np.dot(n, V)), 0.0)
+            kS = F0 + (np.maximum(1.0 - rough * rough, F0) - F0) * (1.0 - cos) ** 5
+            want = (1 - kS) * (1 - met) * (Lrgb * 0.5 * 3.1415926) * alb
+            assert np.allclose(got[i], want, rtol=2e-5, atol=1e-7), (i, got[i], want)
+    o.close()
