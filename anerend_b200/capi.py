@@ -38,6 +38,10 @@ class BvhInfo(C.Structure):
                 ("bounds_min", C.c_float * 3), ("bounds_max", C.c_float * 3)]
 
 
+class TextureDesc(C.Structure):        # anerend_texture_desc_t
+    _fields_ = [("pixels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_uint32), ("clamp_to_edge", C.c_uint32)]
+
+
 class DdgiError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"[{code}] {msg}")
@@ -115,9 +119,22 @@ class DdgiHandle:
         self.close()
 
     # ---- scene ---------------------------------------------------------------------------------
+    def upload_textures(self, textures):
+        """`textures`: list of (pixels uint8 [h, w, c], ANEREND_TEX_* format, clamp_to_edge); index = bindless index."""
+        n = len(textures)
+        arr = (TextureDesc * max(n, 1))()
+        keep = []
+        for i, (px, fmt, clamp) in enumerate(textures):
+            px = np.ascontiguousarray(px, np.uint8)
+            keep.append(px)
+            arr[i].pixels = px.ctypes.data_as(C.c_void_p)
+            arr[i].width, arr[i].height, arr[i].format, arr[i].clamp_to_edge = px.shape[1], px.shape[0], int(fmt), 1 if clamp else 0
+        self._call("upload_textures", arr, C.c_uint32(n))
+
     def upload_scene(self, scene):
         s = scene
         self._keep = s
+        self.upload_textures(getattr(s, "textures", []))
         self._call("upload_scene",
                    _ptr(s.vertices), C.c_uint32(len(s.vertices)), _ptr(s.indices), C.c_uint32(len(s.indices)),
                    _ptr(s.meshes), _ptr(s.mesh_num_indices), C.c_uint32(len(s.meshes)),

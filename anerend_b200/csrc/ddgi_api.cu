@@ -89,6 +89,11 @@ struct anerend_ddgi {
   // wavefront (fast) path scratch: hit records, surface records, visibility masks, per-light shadow queues
   float4* dHits = nullptr; float4* dSurf = nullptr; uint32_t* dLit = nullptr; uint32_t* dQueues = nullptr; uint32_t* dQcount = nullptr;
   uint32_t* dHitq = nullptr; float4* dShadeTris = nullptr; float* dConvW = nullptr;
+  // bindless textures: descriptor table, texel pool, decode table (sRGB EOTF + UNORM); per-triangle uv records and per-ray
+  // emissive exist only while some material is textured
+  DTexture* dTextures = nullptr; uint8_t* dTexPool = nullptr; float* dSrgbLut = nullptr; uint32_t numTextures = 0;
+  std::vector<DTexture> textures; bool texturedScene = false, emissiveTextures = false;
+  float4* dShadeUV = nullptr; float4* dEmisTex = nullptr;
   size_t fastRays = 0; uint32_t fastQueues = 0; int gridPrimary[2] = {0, 0}, gridShadow[2] = {0, 0}; uint32_t tune[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int sms = 0;
 
   int rowOffset = 0, rowStride = 1, Pl = 0;                // row stripe (set_row_stripe): probes launched per layer = Pl
@@ -157,7 +162,7 @@ BuildCtx buildCtx(anerend_ddgi* h) {
   c.wtri = h->dWtri; c.triLo = h->dTriLo; c.triHi = h->dTriHi; c.sceneBounds = h->dSceneBounds;
   c.nodes = h->dNodes; c.bvhTris = h->dBvhTris; c.nodeParent = h->dNodeParent; c.nodeLo = h->dNodeLo; c.nodeHi = h->dNodeHi;
   c.nodePending = h->dNodePending; c.visit = h->dVisit; c.counters = h->dCounters;
-  c.shadeTris = nullptr;
+  c.shadeTris = nullptr; c.shadeUV = nullptr;
   return c;
 }
 
@@ -165,7 +170,7 @@ void freeAccel(anerend_ddgi* h) {
   Backend& be = h->be;
   be.free(h->dInstances); be.free(h->dXforms); be.free(h->dTriInstance); be.free(h->dWtri); be.free(h->dTriLo); be.free(h->dTriHi);
   be.free(h->dNodes); be.free(h->dBvhTris); be.free(h->dNodeParent); be.free(h->dNodeLo); be.free(h->dNodeHi); be.free(h->dNodePending); be.free(h->dVisit);
-  be.free(h->dShadeTris); h->dShadeTris = nullptr;
+  be.free(h->dShadeTris); h->dShadeTris = nullptr; be.free(h->dShadeUV); h->dShadeUV = nullptr;
   h->dInstances = nullptr; h->dXforms = nullptr; h->dTriInstance = nullptr; h->dWtri = nullptr; h->dTriLo = nullptr; h->dTriHi = nullptr;
   h->dNodes = nullptr; h->dBvhTris = nullptr; h->dNodeParent = nullptr; h->dNodeLo = nullptr; h->dNodeHi = nullptr; h->dNodePending = nullptr; h->dVisit = nullptr;
   h->haveAccel = false; h->numTris = 0; h->numNodes = 0;
@@ -204,6 +209,7 @@ int buildAccel(anerend_ddgi* h) {
   BE_CHECK(h, be.alloc(&h->dNodeParent, nodeCap)); BE_CHECK(h, be.alloc(&h->dNodeLo, nodeCap)); BE_CHECK(h, be.alloc(&h->dNodeHi, nodeCap));
   BE_CHECK(h, be.alloc(&h->dNodePending, nodeCap)); BE_CHECK(h, be.alloc(&h->dVisit, (size_t)n + 1));
   BE_CHECK(h, be.alloc(&h->dShadeTris, 5 * (size_t)n));
+  if (h->texturedScene) BE_CHECK(h, be.alloc(&h->dShadeUV, 2 * (size_t)n));
   // build-only scratch
   uint32_t *keys = nullptr, *ids = nullptr, *skeys = nullptr, *sids = nullptr, *left = nullptr, *right = nullptr, *parent = nullptr, *rf = nullptr, *rl = nullptr;
   float4 *blo = nullptr, *bhi = nullptr; CItem *qa = nullptr, *qb = nullptr;
@@ -216,7 +222,7 @@ int buildAccel(anerend_ddgi* h) {
   BE_CHECK(h, be.h2d(h->dSceneBounds, initBounds, sizeof(initBounds)));
   BuildCtx c = buildCtx(h);
   c.mortonKeys = keys; c.triIds = ids; c.sortedKeys = skeys; c.sortedIds = sids; c.left = left; c.right = right; c.parent = parent;
-  c.rangeFirst = rf; c.rangeLast = rl; c.blo = blo; c.bhi = bhi; c.shadeTris = h->dShadeTris;
+  c.rangeFirst = rf; c.rangeLast = rl; c.blo = blo; c.bhi = bhi; c.shadeTris = h->dShadeTris; c.shadeUV = h->dShadeUV;
   be.mark(4);
   DDGI_LAUNCH(be, k_inst_xform, inst_xform_body, ni, c, 128);
   DDGI_LAUNCH(be, k_flatten_scene, flatten_tri_body, n, c, 256);
@@ -333,7 +339,9 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
     BE_CHECK(h, be.alloc(&h->dHits, need)); BE_CHECK(h, be.alloc(&h->dSurf, 3 * need)); BE_CHECK(h, be.alloc(&h->dLit, need));
     BE_CHECK(h, be.alloc(&h->dQueues, (size_t)nq * need)); BE_CHECK(h, be.alloc(&h->dQcount, FAST_QC_SIZE)); BE_CHECK(h, be.alloc(&h->dHitq, need));
     h->fastRays = need; h->fastQueues = nq;
+    be.free(h->dEmisTex); h->dEmisTex = nullptr;
   }
+  if (h->emissiveTextures && !h->dEmisTex) BE_CHECK(h, be.alloc(&h->dEmisTex, h->fastRays));     // per-ray emissive of textured materials
   if (h->gridPrimary[0] == 0) {
     int dev = 0, sms = 0, nb = 0;
     BE_CHECK(h, be.ok(cudaGetDevice(&dev))); BE_CHECK(h, be.ok(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)));
@@ -351,7 +359,7 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
     }
   }
   FastCtx f{};
-  f.t = c; f.shadeTris = h->dShadeTris; f.hits = h->dHits; f.surf = h->dSurf; f.lit = h->dLit; f.queues = h->dQueues; f.hitq = h->dHitq;
+  f.t = c; f.shadeTris = h->dShadeTris; f.shadeUV = h->dShadeUV; f.emisTex = h->dEmisTex; f.hits = h->dHits; f.surf = h->dSurf; f.lit = h->dLit; f.queues = h->dQueues; f.hitq = h->dHitq;
   f.qcount = h->dQcount; f.totalRays = n; f.numQueues = nq;
   for (int k = 0; k < 8; ++k) f.tune[k] = h->tune[k];
   f.tune[3] = 0x64646464u;                 // planes2: the PRMT constant travels as a kernel argument so the selector can be the immediate
@@ -481,6 +489,7 @@ int traceLayers(anerend_ddgi* h, const int* layers, int numLayers, const float* 
   TraceCtx c{};
   c.nodes = h->dNodes; c.bvhTris = h->dBvhTris; c.numNodes = h->numNodes;
   c.vertices = h->dVertices; c.indices = h->dIndices; c.materials = h->dMaterials;
+  c.textures = h->dTextures; c.texPool = h->dTexPool; c.srgbLut = h->dSrgbLut; c.numTextures = h->numTextures;
   c.instances = h->dInstances; c.xforms = h->dXforms; c.triInstance = h->dTriInstance;
   c.lights = h->dLights; c.numLights = h->numLights;
   c.dirs = h->dDirs; c.layerMap = h->dLayerMap; c.rayOrder = h->dRayOrder; c.atlas = h->dAtlas; c.rayIrr = h->dRayIrr;
@@ -575,6 +584,7 @@ void destroyHandle(anerend_ddgi* h) {
   freeAccel(h); freeScene(h);
   be.free(h->dAtlas); be.free(h->dTemp); be.free(h->dRayIrr); be.free(h->dDirs); be.freeHostPinned(h->hDirs); be.free(h->dRayOrder);
   be.free(h->dLayerMap); be.freeHostPinned(h->hLayerMap);
+  be.free(h->dTextures); be.free(h->dTexPool); be.free(h->dSrgbLut); be.free(h->dEmisTex);
   be.free(h->dRecords); be.free(h->dTexelRecords); be.free(h->dStats); be.free(h->dSceneBounds); be.free(h->dCounters);
   be.free(h->dHits); be.free(h->dSurf); be.free(h->dLit); be.free(h->dQueues); be.free(h->dQcount); be.free(h->dHitq); be.free(h->dConvW);
   be.destroy();
@@ -647,6 +657,43 @@ int DDGI_API(reset)(anerend_ddgi_t* h) {
 const char* DDGI_API(last_error)(const anerend_ddgi_t* h) { return h ? h->err.c_str() : "null handle"; }
 int DDGI_API(sync)(anerend_ddgi_t* h) { BE_CHECK(h, h->be.sync()); return peerCheck(h); }
 
+int DDGI_API(upload_textures)(anerend_ddgi_t* h, const anerend_texture_desc_t* tex, uint32_t count) {
+  Backend& be = h->be;
+  if (count && !tex) return fail(h, ANEREND_DDGI_E_INVALID, "null texture array");
+  std::vector<DTexture> table(count);
+  size_t total = 0;
+  for (uint32_t i = 0; i < count; ++i) {
+    if (!tex[i].pixels || tex[i].width == 0 || tex[i].height == 0 || tex[i].width > 16384u || tex[i].height > 16384u || tex[i].format > ANEREND_TEX_R8_UNORM)
+      return fail(h, ANEREND_DDGI_E_INVALID, "bad texture descriptor (BC-compressed assets are handed over decoded)");
+    const size_t bpp = tex[i].format <= ANEREND_TEX_RGBA8_SRGB ? 4 : (tex[i].format == ANEREND_TEX_RG8_UNORM ? 2 : 1);
+    total = (total + 15) & ~(size_t)15;
+    if (total > 0xFFFFFFFFull - (size_t)tex[i].width * tex[i].height * bpp) return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "texture pool larger than 4 GiB");
+    table[i].offset = (uint32_t)total; table[i].width = tex[i].width; table[i].height = tex[i].height;
+    table[i].formatClamp = tex[i].format | (tex[i].clamp_to_edge ? 1u << 8 : 0u);
+    total += (size_t)tex[i].width * tex[i].height * bpp;
+  }
+  BE_CHECK(h, be.sync());
+  be.free(h->dTextures); be.free(h->dTexPool); h->dTextures = nullptr; h->dTexPool = nullptr; h->numTextures = 0; h->textures.clear();
+  if (count == 0) return 0;
+  if (!h->dSrgbLut) {          // texel decode table, made once on the host in fp32 (the oracle makes the same one)
+    float lut[512];
+    for (int c = 0; c < 256; ++c) {
+      const float v = (float)c / 255.0f;
+      const float higher = powf((v + 0.055f) / 1.055f, 2.4f), lower = v / 12.92f;     // sRGB EOTF, as toLinear (bindless.glsl:240-247)
+      lut[c] = (v < 0.04045f) ? lower : higher; lut[256 + c] = v;
+    }
+    BE_CHECK(h, be.alloc(&h->dSrgbLut, 512)); BE_CHECK(h, be.h2d(h->dSrgbLut, lut, sizeof(lut))); BE_CHECK(h, be.sync());
+  }
+  BE_CHECK(h, be.alloc(&h->dTextures, count)); BE_CHECK(h, be.alloc(&h->dTexPool, total));
+  for (uint32_t i = 0; i < count; ++i) {
+    const size_t bpp = tex[i].format <= ANEREND_TEX_RGBA8_SRGB ? 4 : (tex[i].format == ANEREND_TEX_RG8_UNORM ? 2 : 1);
+    BE_CHECK(h, be.h2d(h->dTexPool + table[i].offset, tex[i].pixels, (size_t)tex[i].width * tex[i].height * bpp));
+  }
+  BE_CHECK(h, be.h2d(h->dTextures, table.data(), count * sizeof(DTexture))); BE_CHECK(h, be.sync());
+  h->numTextures = count; h->textures = table;
+  return 0;
+}
+
 int DDGI_API(upload_scene)(anerend_ddgi_t* h,
     const anerend_vertex_t* vertices, uint32_t nv, const uint32_t* indices, uint32_t ni,
     const anerend_mesh_info_t* meshes, const uint32_t* meshNumIndices, uint32_t nm,
@@ -655,8 +702,14 @@ int DDGI_API(upload_scene)(anerend_ddgi_t* h,
     const uint32_t* modelIdx, uint32_t nmi, const uint32_t* matIdx, uint32_t nmti,
     const anerend_light_t* lights, uint32_t nl) {
   Backend& be = h->be;
-  for (uint32_t i = 0; i < nmat; ++i) for (int k = 0; k < 4; ++k)
-    if (materials[i].bindless_indices[k] != -1) return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "textured materials are outside the path's scope");
+  bool textured = false, emisTex = false;
+  for (uint32_t i = 0; i < nmat; ++i) for (int k = 0; k < 4; ++k) {
+    const int32_t ti = materials[i].bindless_indices[k];
+    if (k == 2 || ti == -1) continue;          // [2] = normal map: never sampled on this path (rchit:77 passes a zero tangent)
+    if (ti < 0 || (uint32_t)ti >= h->numTextures) return fail(h, ANEREND_DDGI_E_INVALID, "material refers to a texture that was not uploaded (upload_textures first)");
+    textured = true; emisTex = emisTex || k == 3;
+  }
+  h->texturedScene = textured; h->emissiveTextures = emisTex;
   if ((h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) && nl > 31) return fail(h, ANEREND_DDGI_E_INVALID, "at most 31 point lights with FLAG_POINT_LIGHTS");
   for (uint32_t i = 0; i < nm; ++i) {
     if ((uint64_t)meshes[i].index_offset + meshNumIndices[i] > ni) return fail(h, ANEREND_DDGI_E_INVALID, "mesh index range exceeds the index buffer");

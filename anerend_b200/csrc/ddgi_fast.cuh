@@ -328,7 +328,9 @@ __global__ void __launch_bounds__(PREP_BLOCK) k_shade_prep(const FastCtx c) {
                               normal.x * xf.w2o[6] + normal.y * xf.w2o[7] + normal.z * xf.w2o[8]));
       const anerend_material_info_t* m = &t.materials[material];
       V3 albedo;
-      if (m->base_col_fac[0] + m->base_col_fac[1] + m->base_col_fac[2] > 0.1f) albedo = mk3(m->base_col_fac[0], m->base_col_fac[1], m->base_col_fac[2]);
+      float metallic = m->met_rough[0], roughness = m->met_rough[1];
+      const bool textured = c.shadeUV != nullptr && material_textured(m);
+      if (!textured && m->base_col_fac[0] + m->base_col_fac[1] + m->base_col_fac[2] > 0.1f) albedo = mk3(m->base_col_fac[0], m->base_col_fac[1], m->base_col_fac[2]);
       else {
         // vertex colour decides (rchit:71,75; bindless.glsl:187-194): rare, so the colours stay in the vertex buffer
         const DInstance in = t.instances[ii];
@@ -339,10 +341,17 @@ __global__ void __launch_bounds__(PREP_BLOCK) k_shade_prep(const FastCtx c) {
         const V3 color = mk3(v0->color[0], v0->color[1], v0->color[2]) * b0 + mk3(v1->color[0], v1->color[1], v1->color[2]) * b1 +
                          mk3(v2->color[0], v2->color[1], v2->color[2]) * b2;
         albedo = mk3(to_linear1(color.x), to_linear1(color.y), to_linear1(color.z));
+        if (textured) {        // getSurfaceDataFromMat with texture taps (bindless.glsl:196-233), uv as rchit:70
+          const float4 ua = __ldg(c.shadeUV + 2 * (size_t)hp), ub = __ldg(c.shadeUV + 2 * (size_t)hp + 1);
+          const float tu = ua.x * b0 + ua.z * b1 + ub.x * b2, tv = ua.y * b0 + ua.w * b1 + ub.y * b2;
+          const Surface sf = surface_from_material(t, m, tu, tv, albedo);
+          albedo = sf.albedo; metallic = sf.metallic; roughness = sf.roughness;
+          if (c.emisTex && m->bindless_indices[3] != -1) c.emisTex[idx] = make_float4(sf.emissive.x, sf.emissive.y, sf.emissive.z, 0.0f);
+        }
       }
       c.surf[3 * (size_t)idx + 0] = make_float4(pos.x, pos.y, pos.z, normal.x);
       c.surf[3 * (size_t)idx + 1] = make_float4(normal.y, normal.z, albedo.x, albedo.y);
-      c.surf[3 * (size_t)idx + 2] = make_float4(albedo.z, __uint_as_float(material), 0.0f, 0.0f);
+      c.surf[3 * (size_t)idx + 2] = make_float4(albedo.z, __uint_as_float(material), metallic, roughness);
       c.lit[idx] = 0u;
     } else {
       // rmiss:20 + rgen:109

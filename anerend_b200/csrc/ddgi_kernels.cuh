@@ -71,6 +71,7 @@ struct BuildCtx {
   uint32_t* counters;         // [0] BVH8 nodes allocated, [1] triangle slots allocated, [2] next queue length
   const CItem* qin; CItem* qout;
   float4* shadeTris;          // [numTris][5] object-space shading record (ddgi_wavefront.h ShadeTri) or null
+  float4* shadeUV;            // [numTris][2] (uv0, uv1) (uv2, -, -): only when some material is textured
   // PLOC (parallel locally-ordered clustering) state: clusters in Morton order, double-buffered across the compaction
   uint32_t* clRef; float4* clLo; float4* clHi;              // current clusters: binary ref + box
   uint32_t* clRefOut; float4* clLoOut; float4* clHiOut;     // compacted clusters of the next iteration
@@ -131,6 +132,12 @@ HD void flatten_tri_body(uint32_t t, const BuildCtx& c) {
     o[0] = make_float4(sr[0], sr[1], sr[2], sr[3]); o[1] = make_float4(sr[4], sr[5], sr[6], sr[7]);
     o[2] = make_float4(sr[8], sr[9], sr[10], sr[11]); o[3] = make_float4(sr[12], sr[13], sr[14], sr[15]);
     o[4] = make_float4(sr[16], sr[17], u2f(ii), u2f(in.material));
+  }
+  if (c.shadeUV) {
+    float uv[6];
+    for (int k = 0; k < 3; ++k) { const float* q = c.vertices[in.vertexOffset + c.indices[in.indexOffset + 3 * prim + k]].uv; uv[2 * k] = q[0]; uv[2 * k + 1] = q[1]; }
+    c.shadeUV[2 * (size_t)t] = make_float4(uv[0], uv[1], uv[2], uv[3]);
+    c.shadeUV[2 * (size_t)t + 1] = make_float4(uv[4], uv[5], 0.0f, 0.0f);
   }
   V3 e1 = w[1] - w[0], e2 = w[2] - w[0];
   c.wtri[3 * (size_t)t + 0] = make_float4(w[0].x, w[0].y, w[0].z, e1.x);
@@ -571,6 +578,10 @@ HD bool traverse(const uint4* __restrict__ nodes, const float4* __restrict__ tri
 // ----------------------------------------------------------------------------------------------------
 // shading: irradiance_probe_update.rchit + pbr_light.glsl + bindless.glsl + octahedron_helpers.glsl
 // ----------------------------------------------------------------------------------------------------
+// One bindless texture (bindless.glsl:179 `textures[]`): mip 0 in the byte pool, sampled like the reference's default sampler
+// (VK_FILTER_LINEAR, REPEAT or CLAMP_TO_EDGE per texture, PipelineUtil.h:98-112) at LOD 0 — ray-tracing stages have no derivatives.
+struct DTexture { uint32_t offset, width, height, formatClamp; };       // formatClamp: ANEREND_TEX_* | clamp_to_edge << 8
+
 struct TraceCtx {
   const uint4* nodes; const float4* bvhTris; uint32_t numNodes;
   const anerend_vertex_t* vertices; const uint32_t* indices; const anerend_material_info_t* materials;
@@ -586,6 +597,7 @@ struct TraceCtx {
   int nXZ, nY, N, W, H;
   int numLayers;
   int Pl, rowOffset, rowStride;   // probes launched per layer: the z-rows rowOffset, rowOffset+rowStride, ... (stripe_probe)
+  const DTexture* textures; const uint8_t* texPool; const float* srgbLut; uint32_t numTextures;   // bindless textures (set 0 binding 16)
   int clampSampler;               // atlas sampler addressing: 0 = REPEAT (probe RT pass, SpecularGIRT), 1 = CLAMP_TO_EDGE (deferred lighting)
   V3 camOff, step, sky, lightDir;
   float tmin, tmax, sunIntensity;
@@ -614,6 +626,58 @@ HD V3 oct_decode(float ox, float oy) {                                          
 HD float to_linear1(float c) {                                                      // bindless.glsl:240-247
   float higher = powf((c + 0.055f) / 1.055f, 2.4f), lower = c / 12.92f;
   return (c < 0.04045f) ? lower : higher;
+}
+
+// texture(textures[idx], uv) at LOD 0.  Defined arithmetic (the reference leaves it to the sampler hardware): unnormalised
+// coordinate uv*size - 0.5, floor / fract weights in fp32, texel decode UNORM8 -> c/255, sRGB8 -> linear (both through a host-made
+// table; alpha stays linear), missing components (0, 0, 1), blend w00*t00 + w10*t10 + w01*t01 + w11*t11 like the atlas taps.
+HD int tex_wrap(int i, int n, bool clampEdge) {
+  if (clampEdge) return clampi(i, 0, n - 1);
+  i %= n; return i < 0 ? i + n : i;
+}
+HD void tex_fetch(const TraceCtx& c, const DTexture& t, int x, int y, float out[4]) {
+  const uint32_t fmt = t.formatClamp & 0xFFu;
+  const uint32_t bpp = fmt <= ANEREND_TEX_RGBA8_SRGB ? 4u : (fmt == ANEREND_TEX_RG8_UNORM ? 2u : 1u);
+  const uint8_t* p = c.texPool + t.offset + ((size_t)y * t.width + (size_t)x) * bpp;
+  out[0] = 0.0f; out[1] = 0.0f; out[2] = 0.0f; out[3] = 1.0f;
+  // srgbLut[0..255] = sRGB EOTF of c/255, srgbLut[256..511] = c/255 (both made on the host, one table for oracle and device)
+  if (fmt == ANEREND_TEX_RGBA8_SRGB) { out[0] = c.srgbLut[p[0]]; out[1] = c.srgbLut[p[1]]; out[2] = c.srgbLut[p[2]]; out[3] = c.srgbLut[256 + p[3]]; }
+  else for (uint32_t k = 0; k < bpp; ++k) out[k] = c.srgbLut[256 + p[k]];
+}
+HD void sample_texture(const TraceCtx& c, int idx, float u, float v, float out[4]) {
+  const DTexture t = c.textures[idx];
+  const bool clampEdge = (t.formatClamp >> 8) != 0u;
+  const float x = xsub(xmul(u, (float)t.width), 0.5f), y = xsub(xmul(v, (float)t.height), 0.5f);
+  const float fx0 = floorf(x), fy0 = floorf(y);
+  const float fx = xsub(x, fx0), fy = xsub(y, fy0);
+  const int ix = (int)fx0, iy = (int)fy0;
+  const int x0 = tex_wrap(ix, (int)t.width, clampEdge), x1 = tex_wrap(ix + 1, (int)t.width, clampEdge);
+  const int y0 = tex_wrap(iy, (int)t.height, clampEdge), y1 = tex_wrap(iy + 1, (int)t.height, clampEdge);
+  float t00[4], t10[4], t01[4], t11[4];
+  tex_fetch(c, t, x0, y0, t00); tex_fetch(c, t, x1, y0, t10); tex_fetch(c, t, x0, y1, t01); tex_fetch(c, t, x1, y1, t11);
+  const float w00 = xmul(xsub(1.0f, fx), xsub(1.0f, fy)), w10 = xmul(fx, xsub(1.0f, fy)), w01 = xmul(xsub(1.0f, fx), fy), w11 = xmul(fx, fy);
+  for (int k = 0; k < 4; ++k) out[k] = xadd(xadd(xadd(xmul(t00[k], w00), xmul(t10[k], w10)), xmul(t01[k], w01)), xmul(t11[k], w11));
+}
+// getSurfaceDataFromMat (bindless.glsl:181-237) as the probe rchit calls it (rchit:77: TBN and tangent are zero, so the
+// normal-map branch never runs; discardPixel is ignored).  `color` = linearised vertex colour.
+struct Surface { V3 albedo; float metallic, roughness; V3 emissive; };
+HD bool material_textured(const anerend_material_info_t* m) { return m->bindless_indices[0] != -1 || m->bindless_indices[1] != -1 || m->bindless_indices[3] != -1; }
+HD Surface surface_from_material(const TraceCtx& c, const anerend_material_info_t* m, float u, float v, V3 color) {
+  Surface s;
+  s.albedo = color;
+  const int metRoughIdx = m->bindless_indices[0], albedoIdx = m->bindless_indices[1], emissiveIdx = m->bindless_indices[3];
+  float t[4];
+  if (albedoIdx != -1) {
+    sample_texture(c, albedoIdx, u, v, t);
+    s.albedo = mk3(xmul(m->base_col_fac[0], t[0]), xmul(m->base_col_fac[1], t[1]), xmul(m->base_col_fac[2], t[2]));
+  } else if (m->base_col_fac[0] + m->base_col_fac[1] + m->base_col_fac[2] > 0.1f) s.albedo = mk3(m->base_col_fac[0], m->base_col_fac[1], m->base_col_fac[2]);
+  if (metRoughIdx != -1) { sample_texture(c, metRoughIdx, u, v, t); s.metallic = t[1]; s.roughness = t[0]; }
+  else { s.metallic = m->met_rough[0]; s.roughness = m->met_rough[1]; }
+  if (emissiveIdx != -1) {
+    sample_texture(c, emissiveIdx, u, v, t);
+    s.emissive = mk3(xmul(xmul(t[0], m->emissive[0]), m->emissive[3]), xmul(xmul(t[1], m->emissive[1]), m->emissive[3]), xmul(xmul(t[2], m->emissive[2]), m->emissive[3]));
+  } else s.emissive = mk3(m->emissive[0], m->emissive[1], m->emissive[2]) * m->emissive[3];
+  return s;
 }
 
 // pbr_light.glsl:10-43
@@ -778,12 +842,12 @@ HD void trace_ray_body(uint32_t idx, const TraceCtx& c) {
     V3 color = mk3(v0->color[0], v0->color[1], v0->color[2]) * b0 + mk3(v1->color[0], v1->color[1], v1->color[2]) * b1 +
                mk3(v2->color[0], v2->color[1], v2->color[2]) * b2;
     color = mk3(to_linear1(color.x), to_linear1(color.y), to_linear1(color.z));              // rchit:75
-    // getSurfaceDataFromMat, texture-free branches (bindless.glsl:181-237)
+    // getSurfaceDataFromMat (bindless.glsl:181-237); uv as rchit:70
     const anerend_material_info_t* m = &c.materials[in.material];
-    V3 albedo = color;
-    if (m->base_col_fac[0] + m->base_col_fac[1] + m->base_col_fac[2] > 0.1f) albedo = mk3(m->base_col_fac[0], m->base_col_fac[1], m->base_col_fac[2]);
-    const float metallic = m->met_rough[0], roughness = m->met_rough[1];
-    const V3 emissive = mk3(m->emissive[0], m->emissive[1], m->emissive[2]) * m->emissive[3];
+    const float tu = v0->uv[0] * b0 + v1->uv[0] * b1 + v2->uv[0] * b2, tv = v0->uv[1] * b0 + v1->uv[1] * b1 + v2->uv[1] * b2;
+    const Surface sf = surface_from_material(c, m, tu, tv, color);
+    const V3 albedo = sf.albedo, emissive = sf.emissive;
+    const float metallic = sf.metallic, roughness = sf.roughness;
     // sun shadow ray (rchit:45-66): any-hit, origin = hit position without offset
     const V3 sunL = normalize3(-c.lightDir);
     Hit sh;

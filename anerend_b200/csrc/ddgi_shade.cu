@@ -42,8 +42,9 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const FastCtx c) {
     const float4 s0 = c.surf[3 * (size_t)idx], s1 = c.surf[3 * (size_t)idx + 1], s2 = c.surf[3 * (size_t)idx + 2];
     const V3 pos = mk3(s0.x, s0.y, s0.z), normal = mk3(s0.w, s1.x, s1.y), albedo = mk3(s1.z, s1.w, s2.x);
     const anerend_material_info_t* m = &t.materials[__float_as_uint(s2.y)];
-    const float metallic = m->met_rough[0], roughness = m->met_rough[1];
-    const V3 emissive = mk3(m->emissive[0], m->emissive[1], m->emissive[2]) * m->emissive[3];
+    const float metallic = s2.z, roughness = s2.w;                 // material factors or texture taps (k_shade_prep)
+    V3 emissive = mk3(m->emissive[0], m->emissive[1], m->emissive[2]) * m->emissive[3];
+    if (c.emisTex && m->bindless_indices[3] != -1) { const float4 e = c.emisTex[idx]; emissive = mk3(e.x, e.y, e.z); }
     const uint32_t lit = c.lit[idx];
     V3 irradiance = mk3(0.0f);
     if (lit & 1u) irradiance = calc_light(normal, albedo, metallic, roughness, pos, origin, sunL, t.sunIntensity * mk3(1.0f) * 1.0f);

@@ -37,8 +37,10 @@ static_assert(sizeof(ShadeTri) == 80, "ShadeTri is five float4");
 struct FastCtx {
   TraceCtx t;
   const float4* shadeTris;  // [numTris] ShadeTri
+  const float4* shadeUV;    // [numTris][2] texture coordinates of the three vertices, or null (no textured material)
+  float4* emisTex;          // [rays] emissive of hits on emissive-textured materials, or null
   float4* hits;             // [rays] t,u,v,prim   (launch order: idx = (layerLocal*P + probe)*N + slot)
-  float4* surf;             // [rays][3] pos.xyz,n.x | n.yz,albedo.xy | albedo.z,material,-,-
+  float4* surf;             // [rays][3] pos.xyz,n.x | n.yz,albedo.xy | albedo.z,material,metallic,roughness
   uint32_t* lit;            // [rays] visibility bits written by k_trace_shadow
   uint32_t* queues;         // [numQueues][rays] ray indices needing a shadow ray towards light q (0 = sun)
   uint32_t* hitq;           // [rays] compacted indices of the rays that hit (k_shade runs over these with full warps)

@@ -48,3 +48,6 @@ FLAG_FAST_MATH = 1 << 5
 FLAG_SKIP_DEAD_SHADOW_RAYS = 1 << 6
 
 MISS = 0xFFFFFFFF
+
+# anerend_texture_desc_t.format (include/anerend_ddgi_layouts.h)
+TEX_RGBA8_UNORM, TEX_RGBA8_SRGB, TEX_RG8_UNORM, TEX_R8_UNORM = 0, 1, 2, 3

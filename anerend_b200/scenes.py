@@ -136,6 +136,7 @@ class Scene:
     grid: tuple = (16, 8, 16)         # nXZ, nY (as (nXZ, nY, rays))
     movers: list = field(default_factory=list)   # [(renderable index, base 4x4, centre, amplitude, omega, phase)]
     seed: int = 0
+    textures: list = field(default_factory=list)   # [(pixels uint8 [h, w, c], TEX_* format, clamp_to_edge)], index = bindless index
 
     @property
     def num_triangles(self):
@@ -170,10 +171,17 @@ class SceneBuilder:
         self.v, self.i, self.meshes, self.mni = [], [], [], []
         self.nv = self.ni = 0
         self.mats, self.rends, self.model_idx, self.mat_idx, self.lights, self.movers = [], [], [], [], [], []
+        self.textures = []
 
-    def add_mesh(self, pos, nrm, idx, color=(1.0, 1.0, 1.0)):
+    def add_texture(self, pixels, fmt, clamp_to_edge=False):
+        self.textures.append((np.ascontiguousarray(pixels, np.uint8), fmt, clamp_to_edge))
+        return len(self.textures) - 1
+
+    def add_mesh(self, pos, nrm, idx, color=(1.0, 1.0, 1.0), uv=None):
         v = np.zeros(len(pos), L.VERTEX)
         v["pos"], v["normal"], v["color"] = pos, nrm, color     # GLTFLoader.cpp:343-366 default colour = 1,1,1
+        if uv is not None:
+            v["uv"] = uv
         m = np.zeros(1, L.MESH_INFO)
         m["min_pos"][0, :3], m["max_pos"][0, :3] = pos.min(0), pos.max(0)
         m["vertex_offset"], m["index_offset"] = self.nv, self.ni
@@ -185,11 +193,12 @@ class SceneBuilder:
         self.ni += len(idx)
         return len(self.meshes) - 1
 
-    def add_material(self, base_col, metallic=0.0, roughness=1.0, emissive=(0, 0, 0, 0)):
+    def add_material(self, base_col, metallic=0.0, roughness=1.0, emissive=(0, 0, 0, 0), tex=(-1, -1, -1, -1)):
+        """tex = bindless indices (metallicRoughness, albedo, normal, emissive), -1 = none (GpuBuffers.h:29-36)."""
         m = np.zeros(1, L.MATERIAL)
         m["base_col_fac"][0] = (*base_col, 1.0)
         m["emissive"][0] = emissive
-        m["bindless_indices"][0] = -1
+        m["bindless_indices"][0] = tex
         m["met_rough"][0, :2] = (metallic, roughness)
         self.mats.append(m)
         return len(self.mats) - 1
@@ -226,7 +235,7 @@ class SceneBuilder:
         return Scene(self.name, cat(self.v, L.VERTEX), cat(self.i, np.uint32), cat(self.meshes, L.MESH_INFO),
                      np.asarray(self.mni, np.uint32), cat(self.mats, L.MATERIAL), cat(self.rends, L.RENDERABLE),
                      np.asarray(self.model_idx, np.uint32), np.asarray(self.mat_idx, np.uint32),
-                     cat(self.lights, L.LIGHT), ubo, grid, self.movers, self.seed)
+                     cat(self.lights, L.LIGHT), ubo, grid, self.movers, self.seed, list(self.textures))
 
 
 def make_ubo(camera, multi_bounce=True, sun_intensity=5.0, sky_intensity=1.0, sky_color=(0.2, 0.5, 0.7),
@@ -439,4 +448,55 @@ def random_soup(seed, ntris=2000, extent=6.0, grid=(4, 3, 64), camera=(0.3, 2.0,
             b.add_renderable(M, meshes[k % 4], mats[k % nmat], visible=(3 if k == 5 else 1))   # k==5: cull bit set
     for k in range(nlights):
         b.add_light(rng.uniform(-2, 2, 3) + (0, 2, 0), rng.uniform(4, 9), tuple(rng.uniform(1, 5, 3)), enabled=(k != 1 or nlights < 3))
+    return b.finish(camera, grid)
+
+
+def _procedural_texture(rng, w, h, channels):
+    """Smooth noise + checker + a few hard edges, as uint8 [h, w, channels]."""
+    y, x = np.mgrid[0:h, 0:w]
+    t = np.zeros((h, w, channels))
+    for c in range(channels):
+        fx, fy, ph = rng.uniform(0.5, 4.0), rng.uniform(0.5, 4.0), rng.uniform(0, 6.28)
+        t[..., c] = 0.5 + 0.35 * np.sin(2 * np.pi * (fx * x / w + fy * y / h) + ph) + 0.15 * (((x // 4) + (y // 4)) % 2)
+    t += rng.uniform(-0.08, 0.08, t.shape)
+    return np.clip(t * 255.0, 0, 255).astype(np.uint8)
+
+
+def textured_soup(seed, ntris=1200, grid=(4, 3, 64), camera=(0.3, 2.0, -0.2)):
+    """Triangle soup whose materials sample bindless textures (bindless.glsl:196-233): albedo (sRGB and UNORM, REPEAT and
+    CLAMP_TO_EDGE, uvs well outside [0,1]), metallic-roughness (RGBA8 and RG8), emissive, a 1x1 texture, a material whose only
+    texture is the (never sampled) normal map, plus factor-only and vertex-colour materials."""
+    b = SceneBuilder("texsoup%d" % seed, seed)
+    rng = b.rng
+    t_alb_srgb = b.add_texture(_procedural_texture(rng, 32, 16, 4), L.TEX_RGBA8_SRGB)
+    t_alb_unorm = b.add_texture(_procedural_texture(rng, 8, 8, 4), L.TEX_RGBA8_UNORM, clamp_to_edge=True)
+    t_mr = b.add_texture(_procedural_texture(rng, 16, 16, 4), L.TEX_RGBA8_UNORM)
+    t_mr_rg = b.add_texture(_procedural_texture(rng, 5, 7, 2), L.TEX_RG8_UNORM)
+    t_emis = b.add_texture(_procedural_texture(rng, 16, 4, 4), L.TEX_RGBA8_SRGB)
+    t_one = b.add_texture(np.array([[[200, 100, 50, 255]]], np.uint8), L.TEX_RGBA8_SRGB)
+    t_r8 = b.add_texture(_procedural_texture(rng, 4, 4, 1), L.TEX_R8_UNORM)
+    mats = [
+        b.add_material((1.0, 1.0, 1.0), 0.0, 1.0, tex=(-1, t_alb_srgb, -1, -1)),
+        b.add_material((0.8, 0.6, 0.9), 0.3, 0.5, tex=(t_mr, t_alb_unorm, -1, -1)),
+        b.add_material((0.5, 0.5, 0.5), 0.0, 0.7, (1.0, 0.8, 0.5, 2.0), tex=(t_mr_rg, -1, -1, t_emis)),
+        b.add_material((0.9, 0.9, 0.9), 0.1, 0.9, tex=(-1, t_one, 5, -1)),            # normal-map index is ignored on this path
+        b.add_material((0.01, 0.02, 0.03), 0.0, 0.6, (0.2, 0.3, 0.1, 1.5), tex=(-1, -1, -1, t_r8)),   # vertex colour + R8 emissive
+        b.add_material((0.7, 0.2, 0.2), 0.0, 0.8),                                     # factor only
+    ]
+    meshes = []
+    per = max(1, ntris // 4)
+    for m in range(4):
+        c = rng.uniform(-0.5, 0.5, (per, 1, 3))
+        tri = c + rng.uniform(-0.15, 0.15, (per, 3, 3))
+        n = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+        n /= np.maximum(np.linalg.norm(n, axis=1, keepdims=True), 1e-12)
+        nrm = np.repeat(n, 3, 0) + rng.uniform(-0.2, 0.2, (per * 3, 3))
+        col = rng.uniform(0.2, 1.0, (per * 3, 3)) if m % 2 else (1.0, 1.0, 1.0)
+        uv = rng.uniform(-1.5, 2.5, (per * 3, 2)).astype(np.float32)
+        meshes.append(b.add_mesh(tri.reshape(-1, 3).astype(np.float32), nrm.astype(np.float32),
+                                 np.arange(per * 3, dtype=np.uint32), col, uv))
+    for k in range(6):
+        M = translate(rng.uniform(-2, 2, 3) + (0, 2, 0)) @ rotate(k % 3, rng.uniform(0, 360)) @ scale(rng.uniform(2.0, 6.0, 3))
+        b.add_renderable(M, meshes[k % 4], mats[k % len(mats)])
+    b.add_light((0.5, 3.0, 0.2), 8.0, (3.0, 2.0, 4.0))
     return b.finish(camera, grid)

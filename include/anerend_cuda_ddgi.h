@@ -137,6 +137,12 @@ int anerend_cuda_ddgi_upload_scene(anerend_ddgi_t* h,
     const uint32_t* material_indices, uint32_t num_material_indices,/* binding 7: rendMatIndexBuffer */
     const anerend_light_t* lights, uint32_t num_lights);
 
+/* Bindless textures (set 0 binding 16): the whole array, index = bindless index.  Call before _upload_scene; materials may
+ * then reference them through bindless_indices {metallicRoughness, albedo, normal, emissive} (the normal map is never sampled
+ * on this path: rchit:77 passes a zero tangent).  Sampling: LOD 0, bilinear, REPEAT / CLAMP_TO_EDGE per texture.
+ * count = 0 removes all textures. */
+int anerend_cuda_ddgi_upload_textures(anerend_ddgi_t* h, const anerend_texture_desc_t* textures, uint32_t count);
+
 /* Binding 0 (scene_ubo.glsl:14-37).  Fields read: cameraPos, lightDir, skyColor, sunIntensity,
  * skyIntensity, flags (DDGI, DDGI_MULTI, RT_ON, BAKE_MODE_ON). */
 int anerend_cuda_ddgi_set_scene_ubo(anerend_ddgi_t* h, const anerend_scene_ubo_t* ubo);

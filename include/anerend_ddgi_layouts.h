@@ -65,6 +65,20 @@ typedef struct anerend_material_info {
 } anerend_material_info_t;
 ANEREND_STATIC_ASSERT(sizeof(anerend_material_info_t) == 64, "GPUMaterialInfo must be 64 bytes");
 
+/* One entry of the bindless texture array `textures[]` (bindless.glsl:179, VulkanRenderer::addTextureToBindless,
+ * VulkanRenderer.cpp:4916-4946): mip 0 of an asset::Texture (asset/Texture.h:10-40), uncompressed.  The array index is
+ * the bindless index the materials refer to.  BC-compressed assets are handed over decoded (RGBA8). */
+#define ANEREND_TEX_RGBA8_UNORM 0u   /* asset::Texture::Format::RGBA8_UNORM */
+#define ANEREND_TEX_RGBA8_SRGB  1u   /* RGBA8_SRGB: rgb decoded to linear before filtering, alpha linear */
+#define ANEREND_TEX_RG8_UNORM   2u   /* RG8_UNORM: (r, g, 0, 1) */
+#define ANEREND_TEX_R8_UNORM    3u   /* R8_UNORM: (r, 0, 0, 1) */
+typedef struct anerend_texture_desc {
+  const void* pixels;            /* width*height texels, rows top to bottom, tightly packed */
+  uint32_t width, height;
+  uint32_t format;               /* ANEREND_TEX_* */
+  uint32_t clamp_to_edge;        /* asset::Texture::_clampToEdge; 0 = REPEAT (PipelineUtil.h:102) */
+} anerend_texture_desc_t;
+
 /* GpuBuffers.h:38-44 */
 typedef struct anerend_mesh_info {
   float min_pos[4];

@@ -58,6 +58,11 @@ class Oracle(DdgiHandle):
         self._call("download_world_triangles", out.ctypes.data_as(C.c_void_p), C.c_size_t(n))
         return out
 
+    def sample_texture(self, index, u, v):
+        out = (C.c_float * 4)()
+        self._call("sample_texture", C.c_int32(index), C.c_float(u), C.c_float(v), out)
+        return np.array(out[:], np.float32)
+
     def calc_indirect(self, normal, albedo, metallic, roughness, world_pos, view_pos):
         f3 = lambda v: (C.c_float * 3)(*[float(x) for x in v])
         out = (C.c_float * 3)()

@@ -529,6 +529,40 @@ struct ddgi_oracle {
     return Lo;
   }
 
+  // ---- bindless textures: texture(textures[idx], uv) in a ray-tracing stage = LOD 0 (no derivatives), VK_FILTER_LINEAR,
+  // REPEAT or CLAMP_TO_EDGE per texture (asset/Texture.h:39, PipelineUtil.h:98-112).  Defined arithmetic: unnormalised
+  // coordinate uv*size - 0.5, fract weights in fp32, UNORM8 -> c/255, sRGB8 rgb -> linear before filtering (alpha linear),
+  // missing components (0, 0, 1), blend w00*t00 + w10*t10 + w01*t01 + w11*t11.
+  struct Tex { std::vector<uint8_t> px; uint32_t w = 0, h = 0, fmt = 0; bool clampEdge = false; };
+  std::vector<Tex> textures;
+  float texLut[512];
+  void makeTexLut() {
+    for (int c = 0; c < 256; ++c) { float v = (float)c / 255.0f; texLut[c] = toLinear1(v); texLut[256 + c] = v; }
+  }
+  void texFetch(const Tex& t, int x, int y, float out[4]) const {
+    const uint32_t bpp = t.fmt <= ANEREND_TEX_RGBA8_SRGB ? 4u : (t.fmt == ANEREND_TEX_RG8_UNORM ? 2u : 1u);
+    const uint8_t* q = &t.px[((size_t)y * t.w + (size_t)x) * bpp];
+    out[0] = 0.0f; out[1] = 0.0f; out[2] = 0.0f; out[3] = 1.0f;
+    if (t.fmt == ANEREND_TEX_RGBA8_SRGB) { out[0] = texLut[q[0]]; out[1] = texLut[q[1]]; out[2] = texLut[q[2]]; out[3] = texLut[256 + q[3]]; }
+    else for (uint32_t k = 0; k < bpp; ++k) out[k] = texLut[256 + q[k]];
+  }
+  static int texWrap(int i, int n, bool clampEdge) {
+    if (clampEdge) return std::min(std::max(i, 0), n - 1);
+    i %= n; return i < 0 ? i + n : i;
+  }
+  void sampleTexture(int idx, float u, float v, float out[4]) const {
+    const Tex& t = textures[(size_t)idx];
+    float x = u * float(t.w) - 0.5f, y = v * float(t.h) - 0.5f;
+    float fx0 = std::floor(x), fy0 = std::floor(y);
+    float fx = x - fx0, fy = y - fy0; int ix = (int)fx0, iy = (int)fy0;
+    int x0 = texWrap(ix, (int)t.w, t.clampEdge), x1 = texWrap(ix + 1, (int)t.w, t.clampEdge);
+    int y0 = texWrap(iy, (int)t.h, t.clampEdge), y1 = texWrap(iy + 1, (int)t.h, t.clampEdge);
+    float t00[4], t10[4], t01[4], t11[4];
+    texFetch(t, x0, y0, t00); texFetch(t, x1, y0, t10); texFetch(t, x0, y1, t01); texFetch(t, x1, y1, t11);
+    float w00 = (1.0f - fx) * (1.0f - fy), w10 = fx * (1.0f - fy), w01 = (1.0f - fx) * fy, w11 = fx * fy;
+    for (int k = 0; k < 4; ++k) out[k] = t00[k] * w00 + t10[k] * w10 + t01[k] * w01 + t11[k] * w11;
+  }
+
   // ---- atlas sampling: sampler2D probeTex with VK_FILTER_LINEAR, REPEAT (PipelineUtil.h:98-112) --------
   // Defined arithmetic: unnormalised coord = uv*size - 0.5, weights = fract, texel fetch with REPEAT wrap,
   // (1-fx)(1-fy)t00 + fx(1-fy)t10 + (1-fx)fy t01 + fx fy t11 in fp32 (Vulkan spec §16.8 formula).
@@ -620,7 +654,7 @@ struct ddgi_oracle {
     // shadow ray to the sun (rchit:45-66): any-hit semantics, same miss shader -> shadow = 0
     V3 lightDir = v3(ubo.light_dir[0], ubo.light_dir[1], ubo.light_dir[2]);
     V3 shadowDir = normalize(-lightDir);
-    // (uv is interpolated at rchit:70 but only feeds texture taps, which are out of scope)
+    float uvx = vv[0]->uv[0] * b0 + vv[1]->uv[0] * b1 + vv[2]->uv[0] * b2, uvy = vv[0]->uv[1] * b0 + vv[1]->uv[1] * b1 + vv[2]->uv[1] * b2;   // rchit:70
     V3 normal = normalize(P(vv[0]->normal) * b0 + P(vv[1]->normal) * b1 + P(vv[2]->normal) * b2);
     // normal * gl_WorldToObjectEXT : row-vector times matrix = dot with each column of W2O's 3x3
     normal = normalize(v3(normal.x * in.w2o[0] + normal.y * in.w2o[1] + normal.z * in.w2o[2],
@@ -636,12 +670,21 @@ struct ddgi_oracle {
     }
     V3 color = P(vv[0]->color) * b0 + P(vv[1]->color) * b1 + P(vv[2]->color) * b2;
     color = toLinear(color);
-    // getSurfaceDataFromMat, bindless.glsl:181-237, texture-free branches
+    // getSurfaceDataFromMat, bindless.glsl:181-237 (normal map never sampled: rchit:77 passes tangent = 0; discardPixel unused)
     const anerend_material_info_t& m = materials[in.material];
     V3 sColor = color;
-    if (m.base_col_fac[0] + m.base_col_fac[1] + m.base_col_fac[2] > 0.1f) sColor = v3(m.base_col_fac[0], m.base_col_fac[1], m.base_col_fac[2]);
+    float tx[4];
+    if (m.bindless_indices[1] != -1) {
+      sampleTexture(m.bindless_indices[1], uvx, uvy, tx);
+      sColor = v3(m.base_col_fac[0] * tx[0], m.base_col_fac[1] * tx[1], m.base_col_fac[2] * tx[2]);
+    } else if (m.base_col_fac[0] + m.base_col_fac[1] + m.base_col_fac[2] > 0.1f) sColor = v3(m.base_col_fac[0], m.base_col_fac[1], m.base_col_fac[2]);
     float metallic = m.met_rough[0], roughness = m.met_rough[1];
+    if (m.bindless_indices[0] != -1) { sampleTexture(m.bindless_indices[0], uvx, uvy, tx); metallic = tx[1]; roughness = tx[0]; }
     V3 emissive = v3(m.emissive[0], m.emissive[1], m.emissive[2]) * m.emissive[3];
+    if (m.bindless_indices[3] != -1) {
+      sampleTexture(m.bindless_indices[3], uvx, uvy, tx);
+      emissive = v3(tx[0] * m.emissive[0] * m.emissive[3], tx[1] * m.emissive[1] * m.emissive[3], tx[2] * m.emissive[2] * m.emissive[3]);
+    }
 
     V3 irradiance = v3(0.0f);
     litMask = 0;
@@ -813,7 +856,8 @@ int ddgi_oracle_upload_scene(ddgi_oracle_t* h,
     const uint32_t* modelIdx, uint32_t nmi, const uint32_t* matIdx, uint32_t nmti,
     const anerend_light_t* lights, uint32_t nl) {
   for (uint32_t i = 0; i < nmat; ++i) for (int k = 0; k < 4; ++k)
-    if (materials[i].bindless_indices[k] != -1) { h->err = "textured materials are outside the path's scope"; return ANEREND_DDGI_E_UNSUPPORTED; }
+    if (k != 2 && materials[i].bindless_indices[k] != -1 && (materials[i].bindless_indices[k] < 0 || (size_t)materials[i].bindless_indices[k] >= h->textures.size())) {
+      h->err = "material refers to a texture that was not uploaded (upload_textures first)"; return ANEREND_DDGI_E_INVALID; }
   if ((h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) && nl > 31) { h->err = "at most 31 point lights with FLAG_POINT_LIGHTS"; return ANEREND_DDGI_E_INVALID; }
   h->vertices.assign(vertices, vertices + nv); h->indices.assign(indices, indices + ni);
   h->meshes.assign(meshes, meshes + nm); h->meshNumIndices.assign(meshNumIndices, meshNumIndices + nm);
@@ -821,6 +865,22 @@ int ddgi_oracle_upload_scene(ddgi_oracle_t* h,
   h->modelIdx.assign(modelIdx, modelIdx + nmi); h->matIdx.assign(matIdx, matIdx + nmti);
   h->lights.assign(lights, lights + nl);
   h->haveScene = true; h->haveAccel = false; return 0;
+}
+int ddgi_oracle_upload_textures(ddgi_oracle_t* h, const anerend_texture_desc_t* tex, uint32_t count) {
+  std::vector<ddgi_oracle::Tex> out(count);
+  for (uint32_t i = 0; i < count; ++i) {
+    if (!tex[i].pixels || !tex[i].width || !tex[i].height || tex[i].format > ANEREND_TEX_R8_UNORM) { h->err = "bad texture descriptor"; return ANEREND_DDGI_E_INVALID; }
+    size_t bpp = tex[i].format <= ANEREND_TEX_RGBA8_SRGB ? 4 : (tex[i].format == ANEREND_TEX_RG8_UNORM ? 2 : 1);
+    out[i].w = tex[i].width; out[i].h = tex[i].height; out[i].fmt = tex[i].format; out[i].clampEdge = tex[i].clamp_to_edge != 0;
+    const uint8_t* p = (const uint8_t*)tex[i].pixels;
+    out[i].px.assign(p, p + (size_t)tex[i].width * tex[i].height * bpp);
+  }
+  h->textures.swap(out); h->makeTexLut();
+  return 0;
+}
+int ddgi_oracle_sample_texture(ddgi_oracle_t* h, int32_t idx, float u, float v, float out[4]) {
+  if (idx < 0 || (size_t)idx >= h->textures.size()) return ANEREND_DDGI_E_INVALID;
+  h->sampleTexture(idx, u, v, out); return 0;
 }
 int ddgi_oracle_set_scene_ubo(ddgi_oracle_t* h, const anerend_scene_ubo_t* ubo) { h->ubo = *ubo; h->haveUbo = true; return 0; }
 int ddgi_oracle_build_accel(ddgi_oracle_t* h) {

@@ -16,6 +16,8 @@ SCENES = {
     "soup12_128rays": lambda: (scenes.random_soup(12, ntris=900, grid=(3, 2, 128)), (3, 2, 128)),
     "soup13_256rays": lambda: (scenes.random_soup(13, ntris=5000, grid=(5, 2, 256)), (5, 2, 256)),
     "quad": lambda: (scenes.quad_scene(second_quad=True), (4, 2, 64)),
+    "textured": lambda: (scenes.textured_soup(51), (4, 3, 64)),          # bindless texture taps (bindless.glsl:196-233)
+    "textured_256rays": lambda: (scenes.textured_soup(52, ntris=4000, grid=(5, 2, 256)), (5, 2, 256)),
     "empty": lambda: (scenes.empty_scene(grid=(4, 2, 64)), (4, 2, 64)),
 }
 

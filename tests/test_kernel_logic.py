@@ -16,6 +16,7 @@ SCENES = {
     "soup11": lambda: (scenes.random_soup(11), (4, 3, 64)),
     "soup12_128rays": lambda: (scenes.random_soup(12, ntris=900, grid=(3, 2, 128)), (3, 2, 128)),
     "quad": lambda: (scenes.quad_scene(second_quad=True), (4, 2, 64)),
+    "textured": lambda: (scenes.textured_soup(51), (4, 3, 64)),
     "empty": lambda: (scenes.empty_scene(grid=(4, 2, 64)), (4, 2, 64)),
 }
 
@@ -182,3 +183,30 @@ def test_atlas_consumer_matches_oracle(clamp, oracle, make_emu):
     assert not np.array_equal(other, ro)            # the sampler mode matters at the edge of the grid
     o.close()
     e.close()
+
+
+def test_textures_change_the_result_and_are_validated(oracle, make_emu):
+    """The textured scene really samples its textures (stripping them changes the atlas), materials that point at a missing
+    texture are rejected, and the (never sampled) normal-map index is not."""
+    scene, (nxz, ny, nr) = SCENES["textured"]()
+    p = make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS)
+    e = make_emu(p)
+    rots = parity.setup_pair(scene, (e,), seed=3)
+    e.update(-1, rots)
+    with_tex = e.download_atlas()
+    import copy
+    plain = copy.copy(scene)
+    plain.materials = scene.materials.copy()
+    plain.materials["bindless_indices"][:] = -1
+    plain.textures = []
+    e2 = make_emu(p)
+    parity.setup_pair(plain, (e2,), seed=3)
+    e2.update(-1, rots)
+    assert not np.array_equal(with_tex, e2.download_atlas())
+    bad = copy.copy(scene)
+    bad.textures = scene.textures[:2]
+    e3 = make_emu(p)
+    with pytest.raises(Exception):
+        e3.upload_scene(bad)
+    for h in (e, e2, e3):
+        h.close()

@@ -368,3 +368,68 @@ def test_atlas_consumer_uniform_atlas_known_answer(oracle):
             want = (1 - kS) * (1 - met) * (Lrgb * 0.5 * 3.1415926) * alb
             assert np.allclose(got[i], want, rtol=2e-5, atol=1e-7), (i, got[i], want)
     o.close()
+
+
+def _srgb_to_linear(c):
+    v = np.float32(c) / np.float32(255.0)
+    return v / np.float32(12.92) if v < np.float32(0.04045) else np.float32(((np.float64(v) + 0.055) / 1.055) ** 2.4)
+
+
+def test_texture_sampling_known_answers(oracle):
+    """KATs for texture(textures[idx], uv) as defined in DESIGN.md: LOD 0, bilinear with texel centres at (i + 0.5) / size,
+    REPEAT vs CLAMP_TO_EDGE, UNORM8 = c/255, sRGB8 decoded before filtering, alpha linear, RG8 -> (r, g, 0, 1)."""
+    o = oracle.Oracle(make_params(4, 2, 64))
+    px = np.zeros((2, 4, 4), np.uint8)
+    px[0, :, 0] = (0, 51, 102, 255); px[1, :, 0] = (255, 204, 153, 0); px[..., 1] = 128; px[..., 3] = (64, 255, 0, 128)
+    rg = np.array([[[10, 20], [30, 40]]], np.uint8)
+    o.upload_textures([(px, L.TEX_RGBA8_UNORM, False), (px, L.TEX_RGBA8_UNORM, True), (px, L.TEX_RGBA8_SRGB, False), (rg, L.TEX_RG8_UNORM, False)])
+    # texel centres return the texel
+    for (i, j) in ((0, 0), (2, 1), (3, 0)):
+        got = o.sample_texture(0, (i + 0.5) / 4, (j + 0.5) / 2)
+        assert np.allclose(got, px[j, i] / 255.0, atol=1e-7)
+    # halfway between texel (1,0) and (2,0): the mean
+    got = o.sample_texture(0, 2.0 / 4, 0.5 / 2)
+    assert np.allclose(got[0], (51 + 102) / 2 / 255.0, atol=1e-6)
+    # left of the first texel centre: REPEAT blends with the last column, CLAMP_TO_EDGE returns the first
+    rep, clp = o.sample_texture(0, 0.0, 0.25), o.sample_texture(1, 0.0, 0.25)
+    assert np.allclose(rep[0], (0 + 255) / 2 / 255.0, atol=1e-6) and np.allclose(clp[0], 0.0, atol=1e-7)
+    assert np.allclose(o.sample_texture(0, 1.625, 0.25), o.sample_texture(0, 0.625, 0.25), atol=1e-6)     # period 1
+    assert np.allclose(o.sample_texture(0, -0.375, 0.25), o.sample_texture(0, 0.625, 0.25), atol=1e-6)
+    # sRGB: decode, then filter; alpha is not decoded
+    got = o.sample_texture(2, 1.5 / 4, 0.5 / 2)
+    assert np.allclose(got[0], _srgb_to_linear(51), rtol=1e-6) and np.allclose(got[1], _srgb_to_linear(128), rtol=1e-6) and np.allclose(got[3], 1.0)
+    mid = o.sample_texture(2, 2.0 / 4, 0.5 / 2)
+    assert np.allclose(mid[0], (_srgb_to_linear(51) + _srgb_to_linear(102)) / 2, rtol=1e-6)
+    assert np.allclose(o.sample_texture(3, 0.25, 0.5), (10 / 255.0, 20 / 255.0, 0.0, 1.0), atol=1e-7)
+    o.close()
+
+
+def test_constant_texture_equals_the_factor_material(oracle):
+    """A 1x1 sRGB albedo texture with unit base colour factor shades exactly like the factor-only material holding the
+    decoded colour; a constant metallic-roughness texture like the factors it holds."""
+    def build(textured):
+        b = scenes.SceneBuilder("kat_tex", 3)
+        pos, nrm, idx = scenes.box(3)
+        if textured:
+            ta = b.add_texture(np.array([[[200, 100, 50, 255]]], np.uint8), L.TEX_RGBA8_SRGB)
+            tm = b.add_texture(np.array([[[102, 51, 0, 255]]], np.uint8), L.TEX_RGBA8_UNORM)
+            mat = b.add_material((1.0, 1.0, 1.0), 0.9, 0.1, tex=(tm, ta, -1, -1))
+        else:
+            mat = b.add_material(tuple(float(_srgb_to_linear(c)) for c in (200, 100, 50)), 51 / 255.0, 102 / 255.0)
+        mesh = b.add_mesh(pos, nrm, idx, uv=np.random.RandomState(1).uniform(-3, 3, (len(pos), 2)).astype(np.float32))
+        b.add_renderable(scenes.translate((0.2, 2.0, 0.1)) @ scenes.scale(5.0), mesh, mat)
+        b.add_light((0.0, 2.0, 0.0), 6.0, (3.0, 3.0, 3.0))
+        return b.finish((0.3, 2.0, -0.2), (4, 3, 64))
+    atl = []
+    for textured in (True, False):
+        s = build(textured)
+        o = oracle.Oracle(make_params(4, 3, 64, flags=L.FLAG_POINT_LIGHTS))
+        o.upload_scene(s); o.set_scene_ubo(s.ubo); o.build_accel()
+        rots = o.rotations(scenes.rotation_sequence(3, 3))
+        for _ in range(2):
+            o.update(-1, rots)
+        atl.append(o.download_atlas().view(np.float16).astype(np.float32))
+        o.close()
+    assert atl[0][..., :3].max() > 0.01
+    # the factor material stores the decoded colour rounded to fp32 once more than the texture path: allow a few fp16 ulps
+    assert np.allclose(atl[0], atl[1], rtol=4e-3, atol=1e-5)
