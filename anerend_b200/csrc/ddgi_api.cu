@@ -489,7 +489,7 @@ int traceLayers(anerend_ddgi* h, const int* layers, int numLayers, const float* 
   TraceCtx c{};
   c.nodes = h->dNodes; c.bvhTris = h->dBvhTris; c.numNodes = h->numNodes;
   c.vertices = h->dVertices; c.indices = h->dIndices; c.materials = h->dMaterials;
-  c.textures = h->dTextures; c.texPool = h->dTexPool; c.srgbLut = h->dSrgbLut; c.numTextures = h->numTextures;
+  c.tex.textures = h->dTextures; c.tex.texPool = h->dTexPool; c.tex.srgbLut = h->dSrgbLut; c.tex.numTextures = h->numTextures;
   c.instances = h->dInstances; c.xforms = h->dXforms; c.triInstance = h->dTriInstance;
   c.lights = h->dLights; c.numLights = h->numLights;
   c.dirs = h->dDirs; c.layerMap = h->dLayerMap; c.rayOrder = h->dRayOrder; c.atlas = h->dAtlas; c.rayIrr = h->dRayIrr;

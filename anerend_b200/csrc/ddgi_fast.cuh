@@ -302,7 +302,20 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
 // ------------------------------------------------------------------------------------------------------------
 #define PREP_BLOCK 256
 #define PREP_WARPS (PREP_BLOCK / 32)
-__global__ void __launch_bounds__(PREP_BLOCK) k_shade_prep(const FastCtx c) {
+// getSurfaceDataFromMat with texture taps (bindless.glsl:196-233), uv as rchit:70.  Out of line: factor-only scenes (all
+// BASELINE configs) must not pay registers for the sampling code (32 registers = 8 blocks per SM).
+// Returns (albedo.rgb, metallic) and writes roughness through the side buffer slot: everything travels in registers.
+__device__ __noinline__ float4 prep_textured_surface(const TexCtx tex, const float4* shadeUV, float4* emisTex, const anerend_material_info_t* m,
+                                                     uint32_t hp, uint32_t idx, float b1, float b2, float3 color, float* roughnessOut) {
+  const float b0 = 1.0f - b1 - b2;
+  const float4 ua = __ldg(shadeUV + 2 * (size_t)hp), ub = __ldg(shadeUV + 2 * (size_t)hp + 1);
+  const float tu = ua.x * b0 + ua.z * b1 + ub.x * b2, tv = ua.y * b0 + ua.w * b1 + ub.y * b2;
+  const Surface sf = surface_from_material(tex, m, tu, tv, mk3(color.x, color.y, color.z));
+  if (emisTex && m->bindless_indices[3] != -1) emisTex[idx] = make_float4(sf.emissive.x, sf.emissive.y, sf.emissive.z, 0.0f);
+  *roughnessOut = sf.roughness;
+  return make_float4(sf.albedo.x, sf.albedo.y, sf.albedo.z, sf.metallic);
+}
+__global__ void __launch_bounds__(PREP_BLOCK, 8) k_shade_prep(const FastCtx c) {
   const TraceCtx& t = c.t;
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
   const bool inRange = idx < c.totalRays;
@@ -329,6 +342,7 @@ __global__ void __launch_bounds__(PREP_BLOCK) k_shade_prep(const FastCtx c) {
       const anerend_material_info_t* m = &t.materials[material];
       V3 albedo;
       float metallic = m->met_rough[0], roughness = m->met_rough[1];
+      bool textureRough = false;
       const bool textured = c.shadeUV != nullptr && material_textured(m);
       if (!textured && m->base_col_fac[0] + m->base_col_fac[1] + m->base_col_fac[2] > 0.1f) albedo = mk3(m->base_col_fac[0], m->base_col_fac[1], m->base_col_fac[2]);
       else {
@@ -341,16 +355,15 @@ __global__ void __launch_bounds__(PREP_BLOCK) k_shade_prep(const FastCtx c) {
         const V3 color = mk3(v0->color[0], v0->color[1], v0->color[2]) * b0 + mk3(v1->color[0], v1->color[1], v1->color[2]) * b1 +
                          mk3(v2->color[0], v2->color[1], v2->color[2]) * b2;
         albedo = mk3(to_linear1(color.x), to_linear1(color.y), to_linear1(color.z));
-        if (textured) {        // getSurfaceDataFromMat with texture taps (bindless.glsl:196-233), uv as rchit:70
-          const float4 ua = __ldg(c.shadeUV + 2 * (size_t)hp), ub = __ldg(c.shadeUV + 2 * (size_t)hp + 1);
-          const float tu = ua.x * b0 + ua.z * b1 + ub.x * b2, tv = ua.y * b0 + ua.w * b1 + ub.y * b2;
-          const Surface sf = surface_from_material(t, m, tu, tv, albedo);
-          albedo = sf.albedo; metallic = sf.metallic; roughness = sf.roughness;
-          if (c.emisTex && m->bindless_indices[3] != -1) c.emisTex[idx] = make_float4(sf.emissive.x, sf.emissive.y, sf.emissive.z, 0.0f);
+        if (textured) {
+          const float4 r = prep_textured_surface(t.tex, c.shadeUV, c.emisTex, m, hp, idx, h.y, h.z, make_float3(albedo.x, albedo.y, albedo.z),
+                                                 reinterpret_cast<float*>(&c.surf[3 * (size_t)idx + 2]) + 3);
+          albedo = mk3(r.x, r.y, r.z); metallic = r.w; textureRough = true;
         }
       }
       c.surf[3 * (size_t)idx + 0] = make_float4(pos.x, pos.y, pos.z, normal.x);
       c.surf[3 * (size_t)idx + 1] = make_float4(normal.y, normal.z, albedo.x, albedo.y);
+      if (textureRough) roughness = c.surf[3 * (size_t)idx + 2].w;       // written by prep_textured_surface
       c.surf[3 * (size_t)idx + 2] = make_float4(albedo.z, __uint_as_float(material), metallic, roughness);
       c.lit[idx] = 0u;
     } else {

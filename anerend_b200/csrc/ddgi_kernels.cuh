@@ -581,6 +581,7 @@ HD bool traverse(const uint4* __restrict__ nodes, const float4* __restrict__ tri
 // One bindless texture (bindless.glsl:179 `textures[]`): mip 0 in the byte pool, sampled like the reference's default sampler
 // (VK_FILTER_LINEAR, REPEAT or CLAMP_TO_EDGE per texture, PipelineUtil.h:98-112) at LOD 0 — ray-tracing stages have no derivatives.
 struct DTexture { uint32_t offset, width, height, formatClamp; };       // formatClamp: ANEREND_TEX_* | clamp_to_edge << 8
+struct TexCtx { const DTexture* textures; const uint8_t* texPool; const float* srgbLut; uint32_t numTextures; };
 
 struct TraceCtx {
   const uint4* nodes; const float4* bvhTris; uint32_t numNodes;
@@ -597,7 +598,7 @@ struct TraceCtx {
   int nXZ, nY, N, W, H;
   int numLayers;
   int Pl, rowOffset, rowStride;   // probes launched per layer: the z-rows rowOffset, rowOffset+rowStride, ... (stripe_probe)
-  const DTexture* textures; const uint8_t* texPool; const float* srgbLut; uint32_t numTextures;   // bindless textures (set 0 binding 16)
+  TexCtx tex;                     // bindless textures (set 0 binding 16)
   int clampSampler;               // atlas sampler addressing: 0 = REPEAT (probe RT pass, SpecularGIRT), 1 = CLAMP_TO_EDGE (deferred lighting)
   V3 camOff, step, sky, lightDir;
   float tmin, tmax, sunIntensity;
@@ -635,7 +636,7 @@ HD int tex_wrap(int i, int n, bool clampEdge) {
   if (clampEdge) return clampi(i, 0, n - 1);
   i %= n; return i < 0 ? i + n : i;
 }
-HD void tex_fetch(const TraceCtx& c, const DTexture& t, int x, int y, float out[4]) {
+HD void tex_fetch(const TexCtx& c, const DTexture& t, int x, int y, float out[4]) {
   const uint32_t fmt = t.formatClamp & 0xFFu;
   const uint32_t bpp = fmt <= ANEREND_TEX_RGBA8_SRGB ? 4u : (fmt == ANEREND_TEX_RG8_UNORM ? 2u : 1u);
   const uint8_t* p = c.texPool + t.offset + ((size_t)y * t.width + (size_t)x) * bpp;
@@ -644,7 +645,7 @@ HD void tex_fetch(const TraceCtx& c, const DTexture& t, int x, int y, float out[
   if (fmt == ANEREND_TEX_RGBA8_SRGB) { out[0] = c.srgbLut[p[0]]; out[1] = c.srgbLut[p[1]]; out[2] = c.srgbLut[p[2]]; out[3] = c.srgbLut[256 + p[3]]; }
   else for (uint32_t k = 0; k < bpp; ++k) out[k] = c.srgbLut[256 + p[k]];
 }
-HD void sample_texture(const TraceCtx& c, int idx, float u, float v, float out[4]) {
+HD void sample_texture(const TexCtx& c, int idx, float u, float v, float out[4]) {
   const DTexture t = c.textures[idx];
   const bool clampEdge = (t.formatClamp >> 8) != 0u;
   const float x = xsub(xmul(u, (float)t.width), 0.5f), y = xsub(xmul(v, (float)t.height), 0.5f);
@@ -662,7 +663,7 @@ HD void sample_texture(const TraceCtx& c, int idx, float u, float v, float out[4
 // normal-map branch never runs; discardPixel is ignored).  `color` = linearised vertex colour.
 struct Surface { V3 albedo; float metallic, roughness; V3 emissive; };
 HD bool material_textured(const anerend_material_info_t* m) { return m->bindless_indices[0] != -1 || m->bindless_indices[1] != -1 || m->bindless_indices[3] != -1; }
-HD Surface surface_from_material(const TraceCtx& c, const anerend_material_info_t* m, float u, float v, V3 color) {
+HD Surface surface_from_material(const TexCtx& c, const anerend_material_info_t* m, float u, float v, V3 color) {
   Surface s;
   s.albedo = color;
   const int metRoughIdx = m->bindless_indices[0], albedoIdx = m->bindless_indices[1], emissiveIdx = m->bindless_indices[3];
@@ -845,7 +846,7 @@ HD void trace_ray_body(uint32_t idx, const TraceCtx& c) {
     // getSurfaceDataFromMat (bindless.glsl:181-237); uv as rchit:70
     const anerend_material_info_t* m = &c.materials[in.material];
     const float tu = v0->uv[0] * b0 + v1->uv[0] * b1 + v2->uv[0] * b2, tv = v0->uv[1] * b0 + v1->uv[1] * b1 + v2->uv[1] * b2;
-    const Surface sf = surface_from_material(c, m, tu, tv, color);
+    const Surface sf = surface_from_material(c.tex, m, tu, tv, color);
     const V3 albedo = sf.albedo, emissive = sf.emissive;
     const float metallic = sf.metallic, roughness = sf.roughness;
     // sun shadow ray (rchit:45-66): any-hit, origin = hit position without offset
