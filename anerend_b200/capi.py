@@ -234,6 +234,13 @@ class DdgiHandle:
         self._call("download_atlas_layers", _ptr(layers), C.c_uint32(layers.size), _ptr(out), C.c_size_t(out.nbytes))
         return out
 
+    def download_atlas_async(self, out):
+        """Background read-back into `out` (uint16 [H, W, 4], ideally pinned); download_wait() before reading it."""
+        self._call("download_atlas_async", _ptr(out), C.c_size_t(out.nbytes))
+
+    def download_wait(self):
+        self._call("download_wait")
+
     def download_atlas(self, out=None):
         """ProbeRaysConvTex as uint16 [H, W, 4] (RGBA16F bit patterns)."""
         if out is None:

@@ -183,6 +183,7 @@ void freeScene(anerend_ddgi* h) {
 }
 
 int clearAtlas(anerend_ddgi* h) {
+  BE_CHECK(h, h->be.fenceDownload());
   ClearCtx c{h->dAtlas, h->dTemp};
   DDGI_LAUNCH(h->be, k_atlas_clear, clear_body, (uint32_t)(h->W * h->H), c, 256);
   if (h->dTexelRecords) BE_CHECK(h, h->be.zero(h->dTexelRecords, (size_t)h->W * h->H * sizeof(float4)));
@@ -523,6 +524,7 @@ int traceLayers(anerend_ddgi* h, const int* layers, int numLayers, const float* 
 
 int convolveLayers(anerend_ddgi* h, const int* layers, int numLayers) {
   Backend& be = h->be;
+  BE_CHECK(h, be.fenceDownload());          // a background read-back of the previous atlas must finish before it is overwritten
   for (int l = 0; l < numLayers; ++l) if (!h->layerTraced[layers[l]]) return fail(h, ANEREND_DDGI_E_STATE, "convolve before trace of this layer");
   bool same = numLayers == h->numLaunchLayers;
   for (int l = 0; same && l < numLayers; ++l) same = h->hLayerMap[l] == layers[l];
@@ -565,6 +567,7 @@ int translate(anerend_ddgi* h) {
   int dx = ix - h->lastProbeIdx[0], dz = iz - h->lastProbeIdx[1];
   if (dx == 0 && dz == 0) return 0;
   h->lastProbeIdx[0] = ix; h->lastProbeIdx[1] = iz;
+  BE_CHECK(h, be.fenceDownload());
   BE_CHECK(h, be.d2d(h->dTemp, h->dAtlas, (size_t)h->W * h->H * sizeof(uint2)));   // first vkCmdCopyImage (:92-99)
   ++be.launches;
   TransCtx c{};
@@ -578,6 +581,7 @@ int translate(anerend_ddgi* h) {
 void destroyHandle(anerend_ddgi* h) {
   if (!h) return;
   Backend& be = h->be;
+  be.waitDownload();
   be.sync();
   exchangeDisconnect(h);
   be.free(h->dXflags); be.free(h->dXerr);
@@ -916,9 +920,18 @@ int DDGI_API(download_atlas_layers)(anerend_ddgi_t* h, const int32_t* layers, ui
       return fail(h, ANEREND_DDGI_E_CUDA, std::string("download_atlas_layers: ") + h->be.errStr());
   BE_CHECK(h, h->be.sync()); return 0;
 }
+// Asynchronous read-back: the copy starts when the work queued so far has finished and runs on its own stream, so the next
+// update's tracing overlaps it; the next writer of the atlas (convolution, translation, reset) waits for it on the device.
+// `rgba16f` should be page-locked for the overlap to happen.  _download_wait blocks the host until the bytes have landed.
+int DDGI_API(download_atlas_async)(anerend_ddgi_t* h, void* out, size_t bytes) {
+  if (!out || bytes != (size_t)h->W * h->H * 8) return fail(h, ANEREND_DDGI_E_INVALID, "atlas size mismatch");
+  if (h->xworld > 1) return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "asynchronous read-back with a connected exchange (peers write this atlas)");
+  BE_CHECK(h, h->be.d2hBackground(out, h->dAtlas, bytes)); return 0;
+}
+int DDGI_API(download_wait)(anerend_ddgi_t* h) { BE_CHECK(h, h->be.waitDownload()); return 0; }
 int DDGI_API(upload_atlas)(anerend_ddgi_t* h, const void* in, size_t bytes) {
   if (bytes != (size_t)h->W * h->H * 8) return fail(h, ANEREND_DDGI_E_INVALID, "atlas size mismatch");
-  BE_CHECK(h, h->be.sync()); BE_CHECK(h, h->be.h2d(h->dAtlas, in, bytes)); BE_CHECK(h, h->be.sync()); return 0;
+  BE_CHECK(h, h->be.waitDownload()); BE_CHECK(h, h->be.sync()); BE_CHECK(h, h->be.h2d(h->dAtlas, in, bytes)); BE_CHECK(h, h->be.sync()); return 0;
 }
 int DDGI_API(atlas_device_ptr)(anerend_ddgi_t* h, void** p, size_t* bytes) { *p = h->dAtlas; *bytes = (size_t)h->W * h->H * 8; return 0; }
 int DDGI_API(set_peer_atlases)(anerend_ddgi_t* h, void* const* peers, uint32_t n) {

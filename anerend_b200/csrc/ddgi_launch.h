@@ -25,6 +25,9 @@ struct Backend {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[11] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // 6..10: kernels of the RT pass
   cudaEvent_t evCopy = nullptr; bool copyPending = false;
+  // asynchronous result read-back: a second stream copies the atlas to the host while the next update traces;
+  // whatever writes the atlas next waits for it (fenceDownload)
+  cudaStream_t dlStream = nullptr; cudaEvent_t evResult = nullptr, evDownload = nullptr; bool downloadPending = false;
   uint32_t launches = 0;
   cudaError_t lastErr = cudaSuccess;
   bool ok(cudaError_t e) { if (e != cudaSuccess) { lastErr = e; return false; } return true; }
@@ -35,9 +38,23 @@ struct Backend {
     if (device >= 0 && !ok(cudaSetDevice(device))) return false;
     if (!ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking))) return false;
     for (auto& e : ev) if (!ok(cudaEventCreate(&e))) return false;
+    if (!ok(cudaStreamCreateWithFlags(&dlStream, cudaStreamNonBlocking))) return false;
+    if (!ok(cudaEventCreateWithFlags(&evResult, cudaEventDisableTiming)) || !ok(cudaEventCreateWithFlags(&evDownload, cudaEventDisableTiming))) return false;
     return ok(cudaEventCreateWithFlags(&evCopy, cudaEventDisableTiming));
   }
-  void destroy() { for (auto& e : ev) if (e) cudaEventDestroy(e); if (evCopy) cudaEventDestroy(evCopy); if (stream) cudaStreamDestroy(stream); }
+  bool d2hBackground(void* dst, const void* src, size_t bytes) {      // ordered after everything queued on `stream` so far
+    if (!ok(cudaEventRecord(evResult, stream)) || !ok(cudaStreamWaitEvent(dlStream, evResult, 0))) return false;
+    if (!ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, dlStream))) return false;
+    downloadPending = true;
+    return ok(cudaEventRecord(evDownload, dlStream));
+  }
+  bool fenceDownload() { return !downloadPending || ok(cudaStreamWaitEvent(stream, evDownload, 0)); }   // device-side: stream waits, host does not
+  bool waitDownload() { if (!downloadPending) return true; downloadPending = false; return ok(cudaEventSynchronize(evDownload)); }
+  void destroy() {
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (evCopy) cudaEventDestroy(evCopy); if (evResult) cudaEventDestroy(evResult); if (evDownload) cudaEventDestroy(evDownload);
+    if (dlStream) cudaStreamDestroy(dlStream); if (stream) cudaStreamDestroy(stream);
+  }
   void waitCopy() { if (copyPending) { cudaEventSynchronize(evCopy); copyPending = false; } }
   void markCopy() { cudaEventRecord(evCopy, stream); copyPending = true; }
   template <class T> bool alloc(T** p, size_t count) { *p = nullptr; return ok(cudaMalloc((void**)p, (count ? count : 1) * sizeof(T))); }
@@ -101,6 +118,9 @@ struct Backend {
   void destroy() {}
   void waitCopy() {}
   void markCopy() {}
+  bool d2hBackground(void* d, const void* s, size_t b) { if (b) memcpy(d, s, b); return true; }
+  bool fenceDownload() { return true; }
+  bool waitDownload() { return true; }
   template <class T> bool alloc(T** p, size_t count) { *p = (T*)calloc(count ? count : 1, sizeof(T)); return *p != nullptr; }
   void free(void* p) { ::free(p); }
   template <class T> bool allocHostPinned(T** p, size_t count) { return alloc(p, count); }

@@ -209,6 +209,11 @@ int anerend_cuda_ddgi_download_atlas_stripe(anerend_ddgi_t* h, void* rgba16f, si
 /* The atlas rows of `num_layers` Y-layers (10*nXZ rows each), packed in the order given: what one rank of a sharded
  * update reads back (its own layers); bytes = num_layers * (10*nXZ)^2 * 8. */
 int anerend_cuda_ddgi_download_atlas_layers(anerend_ddgi_t* h, const int32_t* layers, uint32_t num_layers, void* rgba16f, size_t bytes);
+/* Asynchronous read-back: returns at once; the copy starts when the work queued so far is done and overlaps the next update's
+ * tracing (the next writer of the atlas waits for it on the device).  `rgba16f` should be page-locked.  _download_wait blocks
+ * until the bytes have landed.  Not available while a peer exchange is connected. */
+int anerend_cuda_ddgi_download_atlas_async(anerend_ddgi_t* h, void* rgba16f, size_t bytes);
+int anerend_cuda_ddgi_download_wait(anerend_ddgi_t* h);
 int anerend_cuda_ddgi_upload_atlas(anerend_ddgi_t* h, const void* rgba16f, size_t bytes);
 /* Device pointer of the atlas for consumers on the same device (deferred lighting, NCCL all-gather of slabs).
  * Rows [10*nXZ*slab_begin, 10*nXZ*slab_end) are the rows this handle writes. */

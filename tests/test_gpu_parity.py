@@ -404,3 +404,30 @@ def test_atlas_consumer_matches_oracle_bit_for_bit(clamp, oracle, make_gpu):
     assert np.array_equal(dout.cpu().numpy().view(np.uint32), ro.view(np.uint32))
     o.close()
     g.close()
+
+
+@pytest.mark.gpu
+def test_async_download_returns_the_atlas_of_its_update(make_gpu):
+    """download_atlas_async overlaps the next update: the bytes that land are the atlas as it was when the call was made,
+    even though the next update (which overwrites the atlas) is queued right behind it."""
+    import torch
+    nxz, ny, nr = 8, 4, 64
+    scene = scenes.cornell_box(grid=(nxz, ny, nr), wall_res=10, box_res=3)
+    p = make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS)
+    g = make_gpu(p)
+    rots = parity.setup_pair(scene, (g,), seed=4)
+    g.update(-1, rots)
+    first = g.download_atlas().copy()
+    g.update(-1, rots)
+    second = g.download_atlas().copy()
+    assert not np.array_equal(first, second)
+    g.reset()
+    bufs = [torch.empty((g.atlas_height, g.atlas_width, 4), dtype=torch.int16, pin_memory=True).numpy().view(np.uint16) for _ in range(2)]
+    g.update(-1, rots)
+    g.download_atlas_async(bufs[0])
+    g.update(-1, rots)
+    g.download_atlas_async(bufs[1])
+    g.translate()                                  # no-op here, but every atlas writer must respect the pending copy
+    g.download_wait()
+    assert np.array_equal(bufs[0], first) and np.array_equal(bufs[1], second)
+    g.close()

@@ -210,3 +210,15 @@ def test_textures_change_the_result_and_are_validated(oracle, make_emu):
         e3.upload_scene(bad)
     for h in (e, e2, e3):
         h.close()
+
+
+def test_async_download_entry_points_in_the_host_harness(make_emu):
+    scene, (nxz, ny, nr) = SCENES["quad"]()
+    e = make_emu(make_params(nxz, ny, nr))
+    rots = parity.setup_pair(scene, (e,), seed=2)
+    e.update(-1, rots)
+    buf = np.empty((e.atlas_height, e.atlas_width, 4), np.uint16)
+    e.download_atlas_async(buf)
+    e.download_wait()
+    assert np.array_equal(buf, e.download_atlas())
+    e.close()
