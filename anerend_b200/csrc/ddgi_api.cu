@@ -73,6 +73,7 @@ struct anerend_ddgi {
   // pass resources
   uint2* dAtlas = nullptr; uint2* dTemp = nullptr;        // ProbeRaysConvTex, TempProbeTex
   uint2* dRayIrr = nullptr;                                // ProbeRaysIrrTex for all layers, linear [layer][probe][ray]
+  float* dFib = nullptr;                                   // [N][3] unrotated Fibonacci directions
   float4* dDirs = nullptr; float4* hDirs = nullptr;        // [nY][N] rotated directions (ProbeRaysDirTex is derived from it)
   int* dLayerMap = nullptr; int* hLayerMap = nullptr;      // [nY] absolute layers of the current launch (pinned staging + device)
   int numLaunchLayers = 0;
@@ -318,6 +319,7 @@ int refitAccel(anerend_ddgi* h) {
   return 0;
 }
 
+#ifdef DDGI_HOST_EMU
 // mat3(randomRot) * dir for every ray of `layer` into the pinned staging table (rgen:87-88)
 void rotateDirs(anerend_ddgi* h, int layer, const float* m) {
   float4* out = h->hDirs + (size_t)layer * h->N;
@@ -326,8 +328,13 @@ void rotateDirs(anerend_ddgi* h, int layer, const float* m) {
     out[i] = make_float4(m[0] * x + m[4] * y + m[8] * z, m[1] * x + m[5] * y + m[9] * z, m[2] * x + m[6] * y + m[10] * z, 1.0f);
   }
 }
+#endif
 
 #ifndef DDGI_HOST_EMU
+__global__ void __launch_bounds__(256) k_zero_words(uint32_t* p, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0u;
+}
 // Wavefront path: k_trace_primary -> k_shade_prep -> k_trace_shadow -> k_shade (ddgi_fast.cuh)
 int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   Backend& be = h->be;
@@ -364,7 +371,10 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   f.qcount = h->dQcount; f.totalRays = n; f.numQueues = nq;
   for (int k = 0; k < 8; ++k) f.tune[k] = h->tune[k];
   f.tune[3] = 0x64646464u;                 // planes2: the PRMT constant travels as a kernel argument so the selector can be the immediate
-  BE_CHECK(h, be.zero(h->dQcount, FAST_QC_SIZE * sizeof(uint32_t)));
+  // queue counters and cursors: cleared by a kernel, not cudaMemsetAsync (a memset may be scheduled on a copy engine, where
+  // it waits behind a background read-back of the atlas)
+  k_zero_words<<<(FAST_QC_SIZE + 255u) / 256u, 256, 0, be.stream>>>(h->dQcount, (uint32_t)FAST_QC_SIZE);
+  ++be.launches;
   const bool cnt = (h->p.flags & ANEREND_DDGI_FLAG_COUNTERS) != 0;
   const uint32_t blocks = (n + PREP_BLOCK - 1u) / PREP_BLOCK;
   const int gp = h->gridPrimary[cnt ? 1 : 0], gs = h->gridShadow[cnt ? 1 : 0];
@@ -466,27 +476,60 @@ int peerCheck(anerend_ddgi*) { return 0; }
 void exchangeDisconnect(anerend_ddgi*) {}
 #endif
 
+#ifndef DDGI_HOST_EMU
+#define DIRS_BATCH 32
+struct DirsCtx { float m[DIRS_BATCH][9]; int layer[DIRS_BATCH]; const float* fib; float4* dDirs; int* dLayerMap; uint32_t N, first, count; };
+// mat3(randomRot) * worldDirFromFibonacciIndex(i) (rgen:87-88) for the layers of one launch + their entries of the layer map
+__global__ void __launch_bounds__(128) k_make_dirs(const DirsCtx c) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+  if (i >= c.N) return;
+  const float* m = c.m[k];
+  const float x = c.fib[3 * i], y = c.fib[3 * i + 1], z = c.fib[3 * i + 2];
+  c.dDirs[(size_t)c.layer[k] * c.N + i] = make_float4(m[0] * x + m[3] * y + m[6] * z, m[1] * x + m[4] * y + m[7] * z, m[2] * x + m[5] * y + m[8] * z, 1.0f);
+  if (i == 0) c.dLayerMap[c.first + k] = c.layer[k];
+}
+#endif
+
 // `layers`: the absolute layers of this launch (any subset of the grid, each at most once); rots + 16*rotStride*i is
 // the randomRot of layers[i] (rotStride 0: one matrix, 1: packed per launched layer; rotsByLayer: indexed by absolute layer)
 int traceLayers(anerend_ddgi* h, const int* layers, int numLayers, const float* rots, bool rotsByLayer) {
   Backend& be = h->be;
   if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "trace before build_accel");
   if (!h->haveUbo) return fail(h, ANEREND_DDGI_E_STATE, "trace before set_scene_ubo");
-  be.waitCopy();            // previous H2D of the staging tables must be done before they are rewritten
+  be.waitCopy();            // a pending H2D of the layer map (convolveLayers) must be done before the staging array is rewritten
+  for (int l = 0; l < numLayers; ++l) h->hLayerMap[l] = layers[l];
+#ifdef DDGI_HOST_EMU
   int loLayer = h->nY, hiLayer = -1;
   for (int l = 0; l < numLayers; ++l) {
     const int layer = layers[l];
     rotateDirs(h, layer, rots + 16 * (size_t)(rotsByLayer ? layer : l));
-    h->hLayerMap[l] = layer;
     loLayer = layer < loLayer ? layer : loLayer; hiLayer = layer > hiLayer ? layer : hiLayer;
   }
-  // ONE copy of the table rows [loLayer, hiLayer] (a copy per layer cost ~3 us of stream time each): rows of layers
-  // that are not part of this launch are re-sent with the values the device already holds
+#endif
+#ifndef DDGI_HOST_EMU
+  // Direction table and layer map are made ON the device from the rotation matrices, which travel as kernel arguments:
+  // no host memory is read at the start of an update.  (A host->device copy, or a kernel reading page-locked memory,
+  // queues up behind a background read-back of the atlas — PCIe reads may not pass the posted writes of that copy — and
+  // held the whole update back by the length of the copy, 85 us at C3.)  Same fp32 operations as rotateDirs, no contraction.
+  for (int l0 = 0; l0 < numLayers; l0 += DIRS_BATCH) {
+    DirsCtx dc{};
+    dc.fib = h->dFib; dc.dDirs = h->dDirs; dc.dLayerMap = h->dLayerMap; dc.N = (uint32_t)h->N; dc.first = (uint32_t)l0;
+    dc.count = (uint32_t)std::min(DIRS_BATCH, numLayers - l0);
+    for (uint32_t k = 0; k < dc.count; ++k) {
+      const int layer = layers[l0 + (int)k];
+      const float* m = rots + 16 * (size_t)(rotsByLayer ? layer : l0 + (int)k);
+      dc.layer[k] = layer;
+      for (int c3 = 0; c3 < 3; ++c3) for (int r3 = 0; r3 < 3; ++r3) dc.m[k][c3 * 3 + r3] = m[c3 * 4 + r3];
+    }
+    k_make_dirs<<<dim3(((uint32_t)h->N + 127u) / 128u, dc.count), 128, 0, be.stream>>>(dc);
+    ++be.launches;
+  }
+#else
   if (hiLayer >= loLayer)
     BE_CHECK(h, be.h2d(h->dDirs + (size_t)loLayer * h->N, h->hDirs + (size_t)loLayer * h->N, (size_t)(hiLayer - loLayer + 1) * h->N * sizeof(float4)));
   BE_CHECK(h, be.h2d(h->dLayerMap, h->hLayerMap, (size_t)numLayers * sizeof(int)));
+#endif
   h->numLaunchLayers = numLayers;
-  be.markCopy();
   TraceCtx c{};
   c.nodes = h->dNodes; c.bvhTris = h->dBvhTris; c.numNodes = h->numNodes;
   c.vertices = h->dVertices; c.indices = h->dIndices; c.materials = h->dMaterials;
@@ -586,7 +629,7 @@ void destroyHandle(anerend_ddgi* h) {
   exchangeDisconnect(h);
   be.free(h->dXflags); be.free(h->dXerr);
   freeAccel(h); freeScene(h);
-  be.free(h->dAtlas); be.free(h->dTemp); be.free(h->dRayIrr); be.free(h->dDirs); be.freeHostPinned(h->hDirs); be.free(h->dRayOrder);
+  be.free(h->dAtlas); be.free(h->dTemp); be.free(h->dRayIrr); be.free(h->dDirs); be.free(h->dFib); be.freeHostPinned(h->hDirs); be.free(h->dRayOrder);
   be.free(h->dLayerMap); be.freeHostPinned(h->hLayerMap);
   be.free(h->dTextures); be.free(h->dTexPool); be.free(h->dSrgbLut); be.free(h->dEmisTex);
   be.free(h->dRecords); be.free(h->dTexelRecords); be.free(h->dStats); be.free(h->dSceneBounds); be.free(h->dCounters);
@@ -627,6 +670,7 @@ int DDGI_API(create)(const anerend_ddgi_params_t* params, anerend_ddgi_t** out) 
   h->fib.resize((size_t)h->N * 3);
   for (int i = 0; i < h->N; ++i) fibonacciDir((uint32_t)i, (uint32_t)h->N, &h->fib[3 * i]);
   h->layerTraced.assign(h->nY, 0);
+  if (!be.alloc(&h->dFib, (size_t)h->N * 3) || !be.h2d(h->dFib, h->fib.data(), (size_t)h->N * 3 * sizeof(float)) || !be.sync()) { destroyHandle(h); return ANEREND_DDGI_E_CUDA; }
   { // ray binning: slot -> ray index, sorted by the Morton code of the octahedral mapping of the (unrotated) direction;
     // a rotation is rigid, so 32 consecutive slots (one warp) stay a compact cone of directions
     std::vector<std::pair<uint32_t, uint16_t>> keyed(h->N);
