@@ -70,6 +70,9 @@ class Ddgi(DdgiHandle):
     def exchange_disconnect(self):
         self._call("exchange_disconnect")
 
+    def shadow_rt_device(self, d_depth, width, height, d_out):
+        self._call("shadow_rt_device", _C.c_void_p(d_depth), _C.c_uint32(width), _C.c_uint32(height), _C.c_void_p(d_out))
+
     def indirect_diffuse_device(self, d_points, count, view_pos, clamp_to_edge, d_out):
         vp = (_C.c_float * 3)(*[float(x) for x in view_pos])
         self._call("indirect_diffuse_device", _C.c_void_p(d_points), _C.c_uint32(count), vp, _C.c_int32(1 if clamp_to_edge else 0), _C.c_void_p(d_out))

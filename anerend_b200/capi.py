@@ -203,6 +203,13 @@ class DdgiHandle:
             self._call("sync")
 
     # ---- results ---------------------------------------------------------------------------------
+    def shadow_rt(self, depth):
+        """Frame-graph pass "ShadowRT": depth float32 [height, width] -> r32f [height, width] (1 lit / sky, 0 shadowed)."""
+        depth = _c(depth, np.float32)
+        out = np.full(depth.shape, -1.0, np.float32)          # untouched when UBO_RT_SHADOWS_FLAG is off
+        self._call("shadow_rt", _ptr(depth), C.c_uint32(depth.shape[1]), C.c_uint32(depth.shape[0]), _ptr(out))
+        return out
+
     def indirect_diffuse(self, points, view_pos, clamp_to_edge=False):
         """Atlas consumer: calcIndirectDiffuseLight for surface points [n, 12] float32 (pos, normal, albedo, metallic,
         roughness, unused) -> [n, 4] float32 (rgb, 0).  clamp_to_edge: the deferred pass's sampler; False: REPEAT."""

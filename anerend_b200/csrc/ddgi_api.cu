@@ -41,6 +41,7 @@ DDGI_KERNEL(k_probe_trace_counted, trace_ray_body<true>, TraceCtx)
 DDGI_KERNEL(k_probe_convolve, conv_texel_body, ConvCtx)
 DDGI_KERNEL(k_probe_translate, translate_body, TransCtx)
 DDGI_KERNEL(k_indirect_diffuse, indirect_diffuse_body, ConsumerCtx)
+DDGI_KERNEL(k_shadow_rt, shadow_rt_body, ShadowRtCtx)
 DDGI_KERNEL(k_atlas_clear, clear_body, ClearCtx)
 
 // ------------------------------------------------------------------------------------------------ handle
@@ -95,6 +96,8 @@ struct anerend_ddgi {
   DTexture* dTextures = nullptr; uint8_t* dTexPool = nullptr; float* dSrgbLut = nullptr; uint32_t numTextures = 0;
   std::vector<DTexture> textures; bool texturedScene = false, emissiveTextures = false;
   float4* dShadeUV = nullptr; float4* dEmisTex = nullptr;
+  // ShadowRT scratch (pixels): staged positions, visibility words, ray queue, counters
+  float4* dSrtPos = nullptr; uint32_t* dSrtLit = nullptr; uint32_t* dSrtQueue = nullptr; uint32_t* dSrtQcount = nullptr; uint32_t srtPixels = 0; int srtGrid = 0;
   size_t fastRays = 0; uint32_t fastQueues = 0; int gridPrimary[2] = {0, 0}, gridShadow[2] = {0, 0}; uint32_t tune[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int sms = 0;
 
   int rowOffset = 0, rowStride = 1, Pl = 0;                // row stripe (set_row_stripe): probes launched per layer = Pl
@@ -369,6 +372,7 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   FastCtx f{};
   f.t = c; f.shadeTris = h->dShadeTris; f.shadeUV = h->dShadeUV; f.emisTex = h->dEmisTex; f.hits = h->dHits; f.surf = h->dSurf; f.lit = h->dLit; f.queues = h->dQueues; f.hitq = h->dHitq;
   f.qcount = h->dQcount; f.totalRays = n; f.numQueues = nq;
+  f.surfStride = 3u; f.rawSunDir = 0u;
   for (int k = 0; k < 8; ++k) f.tune[k] = h->tune[k];
   f.tune[3] = 0x64646464u;                 // planes2: the PRMT constant travels as a kernel argument so the selector can be the immediate
   // queue counters and cursors: cleared by a kernel, not cudaMemsetAsync (a memset may be scheduled on a copy engine, where
@@ -632,6 +636,7 @@ void destroyHandle(anerend_ddgi* h) {
   be.free(h->dAtlas); be.free(h->dTemp); be.free(h->dRayIrr); be.free(h->dDirs); be.free(h->dFib); be.freeHostPinned(h->hDirs); be.free(h->dRayOrder);
   be.free(h->dLayerMap); be.freeHostPinned(h->hLayerMap);
   be.free(h->dTextures); be.free(h->dTexPool); be.free(h->dSrgbLut); be.free(h->dEmisTex);
+  be.free(h->dSrtPos); be.free(h->dSrtLit); be.free(h->dSrtQueue); be.free(h->dSrtQcount);
   be.free(h->dRecords); be.free(h->dTexelRecords); be.free(h->dStats); be.free(h->dSceneBounds); be.free(h->dCounters);
   be.free(h->dHits); be.free(h->dSurf); be.free(h->dLit); be.free(h->dQueues); be.free(h->dQcount); be.free(h->dHitq); be.free(h->dConvW);
   be.destroy();
@@ -896,6 +901,74 @@ int DDGI_API(frame)(anerend_ddgi_t* h, const float rot[16], int32_t* layerOut) {
   if (layerOut) *layerOut = layer;                                     // blackboard "ProbeLayer" (:158)
   h->currentLayer = (h->currentLayer + 1 >= h->nY) ? 0 : h->currentLayer + 1;   // :160-164
   rc = convolveLayers(h, &layer, 1); h->be.mark(3); h->timed[2] = true;
+  return rc;
+}
+
+// ---- ShadowRT on the same BVH ------------------------------------------------------------------
+namespace {
+int shadowRt(anerend_ddgi* h, const float* dDepth, uint32_t width, uint32_t height, float* dOut) {
+  Backend& be = h->be;
+  if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "shadow_rt before build_accel");
+  if (!h->haveUbo) return fail(h, ANEREND_DDGI_E_STATE, "shadow_rt before set_scene_ubo");
+  if (!(h->ubo.flags & ANEREND_UBO_RT_SHADOWS_FLAG)) return 0;          // shadow.rgen:32-34: the pass writes nothing
+  const uint32_t n = width * height;
+  if (n == 0) return 0;
+  ShadowRtCtx c{};
+  c.nodes = h->dNodes; c.bvhTris = h->dBvhTris; c.numNodes = h->numNodes; c.depth = dDepth; c.out = dOut; c.width = (int)width; c.height = (int)height;
+  for (int k = 0; k < 16; ++k) c.invViewProj[k] = h->ubo.inv_view_proj[k];
+  c.lightDir = mk3(h->ubo.light_dir[0], h->ubo.light_dir[1], h->ubo.light_dir[2]);
+  c.tmin = 0.1f; c.tmax = 50.0f;                                        // literals of shadow.rgen:64-65
+  c.screenW = (float)h->ubo.screen_width; c.screenH = (float)h->ubo.screen_height;
+#ifndef DDGI_HOST_EMU
+  if (!(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS) && h->numNodes > 0) {
+    // the persistent any-hit kernel over one queue of pixels; scratch of its own (a frame buffer is not a probe layer)
+    if (h->srtPixels < n) {
+      BE_CHECK(h, be.sync());
+      be.free(h->dSrtPos); be.free(h->dSrtLit); be.free(h->dSrtQueue); h->dSrtPos = nullptr; h->dSrtLit = nullptr; h->dSrtQueue = nullptr; h->srtPixels = 0;
+      BE_CHECK(h, be.alloc(&h->dSrtPos, n)); BE_CHECK(h, be.alloc(&h->dSrtLit, n)); BE_CHECK(h, be.alloc(&h->dSrtQueue, n));
+      if (!h->dSrtQcount) BE_CHECK(h, be.alloc(&h->dSrtQcount, FAST_QC_SIZE));
+      h->srtPixels = n;
+    }
+    if (h->gridShadow[0] == 0) {
+      int dev = 0, sms = 0, nb = 0;
+      BE_CHECK(h, be.ok(cudaGetDevice(&dev))); BE_CHECK(h, be.ok(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)));
+      BE_CHECK(h, be.ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<true, false>, 128, 0)));
+      h->srtGrid = sms * (nb > 0 ? nb : 1);
+    } else h->srtGrid = h->gridShadow[0];
+    k_zero_words<<<(FAST_QC_SIZE + 255u) / 256u, 256, 0, be.stream>>>(h->dSrtQcount, (uint32_t)FAST_QC_SIZE);
+    k_shadowrt_stage<<<(n + 255u) / 256u, 256, 0, be.stream>>>(c, h->dSrtPos, h->dSrtLit, h->dSrtQueue, h->dSrtQcount + FAST_QC(0));
+    FastCtx f{};
+    f.t.nodes = h->dNodes; f.t.bvhTris = h->dBvhTris; f.t.numNodes = h->numNodes; f.t.lightDir = c.lightDir; f.t.tmin = c.tmin; f.t.tmax = c.tmax;
+    f.surf = h->dSrtPos; f.lit = h->dSrtLit; f.queues = h->dSrtQueue; f.qcount = h->dSrtQcount; f.totalRays = n; f.numQueues = 1u;
+    f.surfStride = 1u; f.rawSunDir = 1u;
+    f.tune[0] = TUNE_NODE_STEPS; f.tune[1] = f.tune[2] = TUNE_REFILL_MIN; f.tune[3] = 0x64646464u; f.tune[4] = TUNE_STEP_MIN; f.tune[5] = TUNE_TRI_MIN;
+    k_trace<true, false><<<h->srtGrid, 128, 0, be.stream>>>(f);
+    k_shadowrt_resolve<<<(n + 255u) / 256u, 256, 0, be.stream>>>(dDepth, h->dSrtLit, dOut, n);
+    be.launches += 4;
+    BE_CHECK(h, be.check());
+    return 0;
+  }
+#endif
+  DDGI_LAUNCH(be, k_shadow_rt, shadow_rt_body, n, c, 128);
+  BE_CHECK(h, be.check());
+  return 0;
+}
+}  // namespace
+int DDGI_API(shadow_rt_device)(anerend_ddgi_t* h, const void* dDepth, uint32_t width, uint32_t height, void* dOut) {
+  if (!dDepth || !dOut) return fail(h, ANEREND_DDGI_E_INVALID, "null argument");
+  return shadowRt(h, (const float*)dDepth, width, height, (float*)dOut);
+}
+int DDGI_API(shadow_rt)(anerend_ddgi_t* h, const float* depth, uint32_t width, uint32_t height, float* out) {
+  if (!depth || !out) return fail(h, ANEREND_DDGI_E_INVALID, "null argument");
+  const size_t n = (size_t)width * height;
+  if (n == 0 || !h->haveUbo || !(h->ubo.flags & ANEREND_UBO_RT_SHADOWS_FLAG)) return h->haveUbo ? 0 : fail(h, ANEREND_DDGI_E_STATE, "shadow_rt before set_scene_ubo");
+  Backend& be = h->be;
+  float *dD = nullptr, *dO = nullptr;
+  if (!be.alloc(&dD, n) || !be.alloc(&dO, n)) { be.free(dD); be.free(dO); return fail(h, ANEREND_DDGI_E_CUDA, std::string("shadow_rt: ") + be.errStr()); }
+  int rc = be.h2d(dD, depth, n * sizeof(float)) ? 0 : fail(h, ANEREND_DDGI_E_CUDA, std::string("shadow_rt: ") + be.errStr());
+  if (!rc) rc = shadowRt(h, dD, width, height, dO);
+  if (!rc && !be.d2h(out, dO, n * sizeof(float))) rc = fail(h, ANEREND_DDGI_E_CUDA, std::string("shadow_rt: ") + be.errStr());
+  be.sync(); be.free(dD); be.free(dO);
   return rc;
 }
 

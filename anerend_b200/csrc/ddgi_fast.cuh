@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
     total = sPrefix[c.numQueues];
   }
   uint32_t* cursor = &c.qcount[ANY ? FAST_QC_SHADOW : FAST_QC_PRIMARY];
-  const V3 sunL = normalize3(-t.lightDir);
+  const V3 sunL = c.rawSunDir ? -t.lightDir : normalize3(-t.lightDir);
   const uint32_t nodeSteps = max(1u, c.tune[0]), refillMin = max(1u, ANY ? c.tune[2] : c.tune[1]);
   const uint32_t stepMin = max(1u, c.tune[4]), triMin = max(1u, c.tune[5]);
   const uint32_t k64 = c.tune[3];          // 0x64646464, opaque to ptxas on purpose (see planes2)
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
           } else {
             uint32_t q = 0; while (q + 1 < c.numQueues && sPrefix[q + 1] <= w) ++q;
             const uint32_t ray = c.queues[(size_t)q * c.totalRays + (w - sPrefix[q])];
-            const float4 s0 = c.surf[3 * (size_t)ray];
+            const float4 s0 = c.surf[(size_t)c.surfStride * ray];
             const V3 pos = mk3(s0.x, s0.y, s0.z);
             V3 dir = sunL; float tmax = t.tmax;
             if (q > 0) {
@@ -427,6 +427,35 @@ __global__ void __launch_bounds__(PREP_BLOCK, 8) k_shade_prep(const FastCtx c) {
       if (q < nq) c.queues[(size_t)q * c.totalRays + o] = idx; else c.hitq[o] = idx;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// ShadowRT on the wavefront kernels: k_shadowrt_stage (world positions + the ray queue, pixel order) -> k_trace<true> ->
+// k_shadowrt_resolve
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_shadowrt_stage(const ShadowRtCtx c, float4* pos, uint32_t* lit, uint32_t* queue, uint32_t* qcount) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, n = (uint32_t)c.width * (uint32_t)c.height, lane = threadIdx.x & 31u;
+  bool need = false;
+  if (i < n) {
+    const float depthSamp = c.depth[i];
+    lit[i] = 0u;
+    if (depthSamp != 1.0f) {
+      const V3 p = shadow_rt_world_pos(c, (int)(i % (uint32_t)c.width), (int)(i / (uint32_t)c.width), depthSamp);
+      pos[i] = make_float4(p.x, p.y, p.z, 0.0f);
+      need = true;
+    }
+  }
+  __shared__ uint32_t sCnt[8], sBase;
+  const uint32_t m = __ballot_sync(0xFFFFFFFFu, need), warp = threadIdx.x >> 5;
+  if (lane == 0) sCnt[warp] = (uint32_t)__popc(m);
+  __syncthreads();
+  if (threadIdx.x == 0) { uint32_t sum = 0; for (int w = 0; w < 8; ++w) { const uint32_t v = sCnt[w]; sCnt[w] = sum; sum += v; } sBase = sum ? atomicAdd(qcount, sum) : 0u; }
+  __syncthreads();
+  if (need) queue[sBase + sCnt[warp] + (uint32_t)__popc(m & ((1u << lane) - 1u))] = i;
+}
+__global__ void __launch_bounds__(256) k_shadowrt_resolve(const float* depth, const uint32_t* lit, float* out, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (depth[i] == 1.0f || (lit[i] & 1u)) ? 1.0f : 0.0f;
 }
 
 }  // namespace ddgi

@@ -809,6 +809,32 @@ HD void indirect_diffuse_body(uint32_t i, const ConsumerCtx& c) {
   c.out[i] = make_float4(r.x, r.y, r.z, 0.0f);
 }
 
+// ShadowRT: shadow.rgen:30-82 + shadow.rmiss for one pixel — world position from the depth buffer, one
+// any-hit ray towards -lightDir (NOT normalised, as in the shader), r32f result: 1 = lit or sky, 0 = shadowed.
+struct ShadowRtCtx {
+  const uint4* nodes; const float4* bvhTris; uint32_t numNodes;
+  const float* depth; float* out; int width, height;
+  float invViewProj[16]; V3 lightDir; float tmin, tmax; float screenW, screenH;
+};
+// shadow.rgen:20-28 calcWorldPos with pixelToUv (helpers.glsl:1-4); mat4 * vec4 evaluated c0*x + c1*y + c2*z + c3*w
+HD V3 shadow_rt_world_pos(const ShadowRtCtx& c, int px, int py, float depthSamp) {
+  const float u = (2.0f * (float)px + 1.0f) / (2.0f * c.screenW), v = (2.0f * (float)py + 1.0f) / (2.0f * c.screenH);
+  const float cx = u * 2.0f - 1.0f, cy = v * 2.0f - 1.0f, cz = depthSamp;
+  const float* m = c.invViewProj;
+  const float X = m[0] * cx + m[4] * cy + m[8] * cz + m[12] * 1.0f, Y = m[1] * cx + m[5] * cy + m[9] * cz + m[13] * 1.0f;
+  const float Z = m[2] * cx + m[6] * cy + m[10] * cz + m[14] * 1.0f, W = m[3] * cx + m[7] * cy + m[11] * cz + m[15] * 1.0f;
+  return mk3(X / W, Y / W, Z / W);
+}
+HD void shadow_rt_body(uint32_t i, const ShadowRtCtx& c) {
+  const int px = (int)(i % (uint32_t)c.width), py = (int)(i / (uint32_t)c.width);
+  const float depthSamp = c.depth[i];                      // texel centre of a depth image of the launch size
+  if (depthSamp == 1.0f) { c.out[i] = 1.0f; return; }      // sky (shadow.rgen:45-48)
+  const V3 origin = shadow_rt_world_pos(c, px, py, depthSamp);
+  Hit sh; uint32_t cn = 0, ct = 0;
+  const bool occluded = traverse<true, false>(c.nodes, c.bvhTris, c.numNodes, origin, -c.lightDir, c.tmin, c.tmax, sh, cn, ct);
+  c.out[i] = occluded ? 0.0f : 1.0f;                       // payload starts at 0, shadow.rmiss sets 1
+}
+
 // rgen main + rchit main + rmiss main for one probe ray (rgen:48-111, rchit:24-111, rmiss:17-21)
 template <bool CNT>
 HD void trace_ray_body(uint32_t idx, const TraceCtx& c) {

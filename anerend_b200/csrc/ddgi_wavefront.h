@@ -46,6 +46,8 @@ struct FastCtx {
   uint32_t* hitq;           // [rays] compacted indices of the rays that hit (k_shade runs over these with full warps)
   uint32_t* qcount;         // FAST_QC_SIZE counters
   uint32_t totalRays, numQueues;
+  uint32_t surfStride;      // float4s per surface record (3; ShadowRT stages positions only: 1)
+  uint32_t rawSunDir;       // queue 0 rays run along -lightDir as given (ShadowRT) instead of normalize(-lightDir) (probe rchit)
   uint32_t tune[8];         // loop tunables (ddgi_fast.cuh TUNE_*); [3] = 0x64646464 (planes2)
 };
 

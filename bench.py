@@ -444,6 +444,34 @@ def main():
         consumer = {"points": npts, "sampler": "clamp_to_edge (deferred lighting)", "ms": cms, "mpoints_per_s": npts / cms / 1e3,
                     "algorithmic_bytes": cbytes, "achieved_gbs": cbytes / (cms * 1e-3) / 1e9, "finite": bool(torch.isfinite(outc).all().item())}
 
+    # ---- ShadowRT on the same BVH: one any-hit ray per pixel of a 1920x1080 depth buffer (top-down view)
+    shadow_rt = None
+    if world == 1:
+        from anerend_b200 import layouts as _L
+        sw, sh = 1920, 1080
+        u = scene.ubo.copy()
+        m = np.zeros((4, 4)); m[0, 0], m[2, 1], m[1, 2], m[3, 3] = 0.5 * nxz, 0.5 * nxz, 2.0 * ny, 1.0     # clip -> world, w = 1
+        m[0, 3], m[2, 3] = float(u["camera_pos"][0][0]), float(u["camera_pos"][0][2])
+        u["inv_view_proj"][0] = m.T.astype(np.float32).ravel()
+        u["screen_width"], u["screen_height"] = sw, sh
+        u["flags"] |= _L.UBO_RT_SHADOWS_FLAG
+        h.set_scene_ubo(u)
+        gen = torch.Generator(device=dev); gen.manual_seed(12)
+        ddepth = torch.rand((sh, sw), generator=gen, device=dev) * 0.96 + 0.02
+        dvis = torch.empty((sh, sw), dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()
+        sstream = torch.cuda.ExternalStream(h.stream(), device=dev)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(13):
+            if it == 3:
+                s0.record(sstream)
+            h.shadow_rt_device(ddepth.data_ptr(), sw, sh, dvis.data_ptr())
+        s1.record(sstream)
+        h.sync()
+        sms = s0.elapsed_time(s1) / 10.0
+        shadow_rt = {"pixels": sw * sh, "ms": sms, "mrays_per_s": sw * sh / sms / 1e3, "lit_fraction": float(dvis.mean().item())}
+        h.set_scene_ubo(scene.ubo)
+
     line = None
     if rank == 0:
         # ---- roofline of the dominant kernel: counted, untimed run of the same update ----------
@@ -518,7 +546,7 @@ def main():
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "update_ms": {"trace": rt_avg, "convolve": float(np.mean(conv_ms)), "full_grid": ms_per_step},
                 "arithmetic": "fast_math (1e-4 relative per update)" if args.fast_math else "exact (atlas bit-identical to the oracle)",
-                "other_build": alt, "strong_scaling_base": base1, "exchange_check_vs_1gpu": verified, "layer_deal": balanced, "per_rank_ms": per_rank, "atlas_consumer": consumer}
+                "other_build": alt, "strong_scaling_base": base1, "exchange_check_vs_1gpu": verified, "layer_deal": balanced, "per_rank_ms": per_rank, "atlas_consumer": consumer, "shadow_rt": shadow_rt}
     close_handle(h, fused)
     if world > 1:
         dist.barrier()

@@ -200,6 +200,15 @@ int anerend_cuda_ddgi_indirect_diffuse(anerend_ddgi_t* h, const float* points, u
 int anerend_cuda_ddgi_indirect_diffuse_device(anerend_ddgi_t* h, const void* d_points, uint32_t count, const float view_pos[3],
                                               int32_t clamp_to_edge, void* d_out_rgba);
 
+/* ---- ShadowRT on the same acceleration structure ---------------------------
+ * The frame-graph pass "ShadowRT" (ShadowRayTracingPass.cpp:73-81, shadow.rgen:30-82, shadow.rmiss): for every pixel of a
+ * width x height depth buffer (float, row-major, the launch size), world position = invViewProj * (uv*2-1, depth, 1) with
+ * uv = pixelToUv(pixel, (screenWidth, screenHeight)), one any-hit ray along -lightDir (not normalised), t in (0.1, 50).
+ * out: r32f image, 1 = lit (or sky: depth == 1), 0 = shadowed.  Nothing is written unless UBO_RT_SHADOWS_FLAG is set.
+ * Reads invViewProj, lightDir, screenWidth/Height and flags from the last _set_scene_ubo. */
+int anerend_cuda_ddgi_shadow_rt(anerend_ddgi_t* h, const float* depth, uint32_t width, uint32_t height, float* out_r32f);
+int anerend_cuda_ddgi_shadow_rt_device(anerend_ddgi_t* h, const void* d_depth, uint32_t width, uint32_t height, void* d_out_r32f);
+
 /* Row stripe (sharding inside the layers): the handle updates only the probe rows z = offset + k*stride of
  * every layer it launches; (0, 1) = all rows (default).  With R ranks, rank r takes (r, R): every rank carries the same
  * share of every layer, so the ranks finish together whatever the scene looks like.  _download_atlas_stripe returns

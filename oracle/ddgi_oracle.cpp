@@ -1012,6 +1012,31 @@ int ddgi_oracle_calc_indirect(ddgi_oracle_t* h, const float n[3], const float a[
   V3 r = h->calcIndirectDiffuseLight(v3(n[0], n[1], n[2]), v3(a[0], a[1], a[2]), metallic, roughness, v3(wp[0], wp[1], wp[2]), v3(vp[0], vp[1], vp[2]));
   out[0] = r.x; out[1] = r.y; out[2] = r.z; return 0;
 }
+// shadow.rgen:30-82 + shadow.rmiss (frame-graph pass "ShadowRT", ShadowRayTracingPass.cpp:73-81) for a width x height depth buffer
+int ddgi_oracle_shadow_rt(ddgi_oracle_t* h, const float* depth, uint32_t width, uint32_t height, float* out) {
+  if (!h->haveAccel) { h->err = "shadow_rt before build_accel"; return ANEREND_DDGI_E_STATE; }
+  if (!h->haveUbo) { h->err = "shadow_rt before set_scene_ubo"; return ANEREND_DDGI_E_STATE; }
+  if (!(h->ubo.flags & ANEREND_UBO_RT_SHADOWS_FLAG)) return 0;                       // shadow.rgen:32-34
+  const float* m = h->ubo.inv_view_proj;
+  const float sw = (float)h->ubo.screen_width, sh = (float)h->ubo.screen_height;
+  const V3 dir = -v3(h->ubo.light_dir[0], h->ubo.light_dir[1], h->ubo.light_dir[2]);  // shadow.rgen:58, not normalised
+  h->parallelFor((int)height, [&](int py) {
+    uint64_t cn = 0, ct = 0;
+    for (uint32_t px = 0; px < width; ++px) {
+      const size_t i = (size_t)py * width + px;
+      const float depthSamp = depth[i];                                               // texel centre (pixelToUv, helpers.glsl:1-4)
+      if (depthSamp == 1.0f) { out[i] = 1.0f; continue; }                             // sky, shadow.rgen:45-48
+      const float u = (2.0f * (float)px + 1.0f) / (2.0f * sw), v = (2.0f * (float)py + 1.0f) / (2.0f * sh);
+      const float cx = u * 2.0f - 1.0f, cy = v * 2.0f - 1.0f, cz = depthSamp;
+      // calcWorldPos, shadow.rgen:20-28: mat4 * vec4 = c0*x + c1*y + c2*z + c3*w, then the perspective divide
+      const float X = m[0] * cx + m[4] * cy + m[8] * cz + m[12] * 1.0f, Y = m[1] * cx + m[5] * cy + m[9] * cz + m[13] * 1.0f;
+      const float Z = m[2] * cx + m[6] * cy + m[10] * cz + m[14] * 1.0f, W = m[3] * cx + m[7] * cy + m[11] * cz + m[15] * 1.0f;
+      const V3 origin = v3(X / W, Y / W, Z / W);
+      out[i] = h->anyHit(origin, dir, 0.1f, 50.0f, cn, ct) ? 0.0f : 1.0f;           // payload 0, shadow.rmiss sets 1
+    }
+  });
+  return 0;
+}
 // deferred_tiled.comp:264-296 / mirror_reflections.rchit:92-118: calcIndirectDiffuseLight per surface point (12 floats each)
 int ddgi_oracle_indirect_diffuse(ddgi_oracle_t* h, const float* pts, uint32_t count, const float vp[3], int32_t clampToEdge, float* out) {
   h->clampSampler = clampToEdge != 0;

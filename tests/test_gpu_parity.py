@@ -431,3 +431,34 @@ def test_async_download_returns_the_atlas_of_its_update(make_gpu):
     g.download_wait()
     assert np.array_equal(bufs[0], first) and np.array_equal(bufs[1], second)
     g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernels", ["wavefront", "simple"])
+def test_shadow_rt_matches_oracle_bit_for_bit(kernels, oracle, make_gpu):
+    """SURVEY §8f N2 through the C ABI: the "ShadowRT" pass on the path's BVH with the persistent any-hit kernel (and with
+    the one-thread-per-ray kernel), host-pointer and device-pointer entry points."""
+    import torch
+    from tests import shadow_inputs as SI
+    nxz, ny, nr = 8, 4, 64
+    scene = scenes.cornell_box(grid=(nxz, ny, nr), wall_res=10, box_res=3)
+    p = make_params(nxz, ny, nr, flags=KERNEL_FLAGS[kernels])
+    o, g = oracle.Oracle(p), make_gpu(p)
+    parity.setup_pair(scene, (o, g), seed=5)
+    W, H = 200, 120
+    depth = SI.depth_buffer(W, H, seed=4)
+    for ivp in (SI.ortho_inv_view_proj(7.0, 7.0, 14.0), SI.perspective_inv_view_proj(3)):
+        ubo = SI.with_shadow_camera(scene.ubo, ivp, W, H)
+        for h in (o, g):
+            h.set_scene_ubo(ubo)
+        ro, rg = o.shadow_rt(depth), g.shadow_rt(depth)
+        assert np.array_equal(ro, rg), f"{(ro != rg).sum()} pixels differ"
+        assert 0.02 < (ro == 0.0).mean() < 0.98
+    dd = torch.from_numpy(depth).cuda()
+    dout = torch.full((H, W), -1.0, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    g.shadow_rt_device(dd.data_ptr(), W, H, dout.data_ptr())
+    g.sync()
+    assert np.array_equal(dout.cpu().numpy(), ro)
+    o.close()
+    g.close()

@@ -222,3 +222,28 @@ def test_async_download_entry_points_in_the_host_harness(make_emu):
     e.download_wait()
     assert np.array_equal(buf, e.download_atlas())
     e.close()
+
+
+def test_shadow_rt_matches_oracle(oracle, make_emu):
+    """the "ShadowRT" pass (shadow.rgen / shadow.rmiss) on the path's BVH; bit-exact visibility image."""
+    from tests import shadow_inputs as SI
+    scene, (nxz, ny, nr) = SCENES["cornell"]()
+    p = make_params(nxz, ny, nr)
+    o, e = oracle.Oracle(p), make_emu(p)
+    parity.setup_pair(scene, (o, e), seed=5)
+    W, H = 48, 32
+    depth = SI.depth_buffer(W, H, seed=3)
+    for ivp in (SI.ortho_inv_view_proj(7.0, 7.0, 14.0), SI.perspective_inv_view_proj(2)):
+        ubo = SI.with_shadow_camera(scene.ubo, ivp, W, H)
+        for h in (o, e):
+            h.set_scene_ubo(ubo)
+        ro, re = o.shadow_rt(depth), e.shadow_rt(depth)
+        assert np.array_equal(ro, re)
+        assert set(np.unique(ro)) <= {0.0, 1.0} and (ro[depth == 1.0] == 1.0).all()
+    assert 0.05 < (ro == 0.0).mean() < 0.95                        # both outcomes occur
+    off = SI.with_shadow_camera(scene.ubo, ivp, W, H, rt_shadows=False)
+    for h in (o, e):
+        h.set_scene_ubo(off)
+        assert (h.shadow_rt(depth) == -1.0).all()                   # shadow.rgen:32-34: nothing written
+    o.close()
+    e.close()

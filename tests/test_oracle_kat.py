@@ -433,3 +433,32 @@ def test_constant_texture_equals_the_factor_material(oracle):
     assert atl[0][..., :3].max() > 0.01
     # the factor material stores the decoded colour rounded to fp32 once more than the texture path: allow a few fp16 ulps
     assert np.allclose(atl[0], atl[1], rtol=4e-3, atol=1e-5)
+
+
+def test_shadow_rt_known_answer(oracle):
+    """KAT for ShadowRT: a horizontal quad at y = 2 over x, z in [-1, 1], light straight down.  Seen through a top-down
+    orthographic inverse view-projection, pixels whose world position lies under the quad (y < 2 - tMin) are shadowed, pixels
+    above it or outside its footprint are lit, sky pixels (depth == 1) are lit without a ray."""
+    from tests import shadow_inputs as SI
+    b = scenes.SceneBuilder("kat_shadow", 1)
+    pos = np.array([(-1, 2, -1), (1, 2, -1), (1, 2, 1), (-1, 2, 1)], np.float32)
+    mesh = b.add_mesh(pos, np.tile(np.array([0, 1, 0], np.float32), (4, 1)), np.array([0, 1, 2, 0, 2, 3], np.uint32))
+    b.add_renderable(np.eye(4), mesh, b.add_material((0.5, 0.5, 0.5)))
+    s = b.finish((0.0, 1.0, 0.0), (4, 2, 64))
+    o = oracle.Oracle(make_params(4, 2, 64))
+    o.upload_scene(s); o.build_accel()
+    W, H = 16, 16
+    ubo = SI.with_shadow_camera(s.ubo, SI.ortho_inv_view_proj(4.0, 4.0, 4.0), W, H)
+    ubo["light_dir"][0] = (0.0, -1.0, 0.0, 0.0)
+    o.set_scene_ubo(ubo)
+    depth = np.full((H, W), 0.25, np.float32)          # world y = 1
+    depth[0, :] = 0.75                                  # world y = 3: above the quad
+    depth[1, 0] = 1.0                                   # sky
+    got = o.shadow_rt(depth)
+    xs = 4.0 * ((2 * np.arange(W) + 1) / (2 * W) * 2 - 1)
+    inside = np.abs(xs) < 1.0
+    want = np.ones((H, W), np.float32)
+    want[np.ix_(inside, inside)] = 0.0                  # rows = z, columns = x
+    want[0, :] = 1.0
+    assert np.array_equal(got, want)
+    o.close()
