@@ -129,6 +129,23 @@ bool ddgiOn(const anerend_ddgi* h) {   // IrradianceProbeRayTracingPass.cpp:97-9
   return (h->ubo.flags & ANEREND_UBO_RT_ON_FLAG) && (h->ubo.flags & ANEREND_UBO_DDGI_FLAG);
 }
 
+// Origin and spacing of the probe grid: live mode follows the camera (rgen:75-83, pbr_light.glsl:295-301; int() truncates toward
+// zero, quirk Q1); bake mode (UBO_BAKE_MODE_ON_FLAG, rgen:61-73, pbr_light.glsl:274-291) covers the tile bakeTileInfo.xy of
+// size bakeTileInfo.z with step (tSize / nXZ, 1.0, tSize / nXZ) — the y step is 1, not PROBE_STEP.y.
+bool bakeMode(const anerend_ddgi* h) { return (h->ubo.flags & ANEREND_UBO_BAKE_MODE_ON_FLAG) == ANEREND_UBO_BAKE_MODE_ON_FLAG; }
+void gridFrame(const anerend_ddgi* h, V3& camOff, V3& stepOut) {
+  if (bakeMode(h)) {
+    const float ts = float(h->ubo.bake_tile_info[2]), s = ts / float(h->nXZ);
+    stepOut = mk3(s, 1.0f, s);
+    camOff = mk3(float(h->ubo.bake_tile_info[0]) * ts, 0.0f, float(h->ubo.bake_tile_info[1]) * ts);
+    return;
+  }
+  const float* step = h->p.probe_step;
+  int cix = (int)(h->ubo.camera_pos[0] / step[0]), ciz = (int)(h->ubo.camera_pos[2] / step[2]);
+  camOff = mk3(float(cix) * step[0] - step[0] * float(h->nXZ) / 2.0f, 0.0f, float(ciz) * step[2] - step[2] * float(h->nXZ) / 2.0f);
+  stepOut = mk3(step[0], step[1], step[2]);
+}
+
 // tlas_update.comp:37-99: which (renderable, mesh) pairs enter the acceleration structure, in renderable order
 int selectInstances(anerend_ddgi* h, std::vector<DInstance>& out, uint32_t& numTris) {
   out.clear(); numTris = 0;
@@ -544,11 +561,7 @@ int traceLayers(anerend_ddgi* h, const int* layers, int numLayers, const float* 
   c.records = h->dRecords; c.stats = h->dStats;
   c.nXZ = h->nXZ; c.nY = h->nY; c.N = h->N; c.W = h->W; c.H = h->H; c.numLayers = numLayers;
   c.Pl = h->Pl; c.rowOffset = h->rowOffset; c.rowStride = h->rowStride;
-  // camOffset (rgen:75-81, pbr_light.glsl:295-301): int() truncates toward zero (quirk Q1)
-  const float* step = h->p.probe_step;
-  int cix = (int)(h->ubo.camera_pos[0] / step[0]), ciz = (int)(h->ubo.camera_pos[2] / step[2]);
-  c.camOff = mk3(float(cix) * step[0] - step[0] * float(h->nXZ) / 2.0f, 0.0f, float(ciz) * step[2] - step[2] * float(h->nXZ) / 2.0f);
-  c.step = mk3(step[0], step[1], step[2]);
+  gridFrame(h, c.camOff, c.step);
   // rmiss:20 toLinear(skyIntensity * skyColor), constant per frame
   { float s[3]; for (int k = 0; k < 3; ++k) { float v = h->ubo.sky_intensity * h->ubo.sky_color[k];
       float higher = powf((v + 0.055f) / 1.055f, 2.4f), lower = v / 12.92f; s[k] = (v < 0.04045f) ? lower : higher; }
@@ -591,7 +604,7 @@ int convolveLayers(anerend_ddgi* h, const int* layers, int numLayers) {
   c.numPeers = texelStores ? h->numPeers : 0;
   c.nXZ = h->nXZ; c.nY = h->nY; c.N = h->N; c.Sx = h->Sx; c.Sy = h->Sy; c.W = h->W; c.H = h->H; c.numLayers = numLayers;
   c.Pl = h->Pl; c.rowOffset = h->rowOffset; c.rowStride = h->rowStride;
-  c.hysteresis = h->p.hysteresis;
+  c.hysteresis = h->p.hysteresis; c.bakeMode = bakeMode(h) ? 1 : 0;
 #ifndef DDGI_HOST_EMU
   if (!(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS)) {
     ConvFastCtx f{}; f.c = c; f.weights = h->dConvW;
@@ -978,10 +991,7 @@ int indirectDiffuse(anerend_ddgi* h, const float4* dPoints, uint32_t count, cons
   if (!h->haveUbo) return fail(h, ANEREND_DDGI_E_STATE, "indirect_diffuse before set_scene_ubo");
   ConsumerCtx c{};
   c.t.atlas = h->dAtlas; c.t.nXZ = h->nXZ; c.t.nY = h->nY; c.t.N = h->N; c.t.W = h->W; c.t.H = h->H; c.t.clampSampler = clampSampler ? 1 : 0;
-  const float* step = h->p.probe_step;       // camOffset as in sampleProbe (pbr_light.glsl:295-301), from the CURRENT camera
-  int cix = (int)(h->ubo.camera_pos[0] / step[0]), ciz = (int)(h->ubo.camera_pos[2] / step[2]);
-  c.t.camOff = mk3(float(cix) * step[0] - step[0] * float(h->nXZ) / 2.0f, 0.0f, float(ciz) * step[2] - step[2] * float(h->nXZ) / 2.0f);
-  c.t.step = mk3(step[0], step[1], step[2]);
+  gridFrame(h, c.t.camOff, c.t.step);        // as sampleProbe places the grid (pbr_light.glsl:274-301), from the CURRENT scene UBO
   c.points = dPoints; c.out = dOut; c.viewPos = mk3(viewPos[0], viewPos[1], viewPos[2]);
   DDGI_LAUNCH(h->be, k_indirect_diffuse, indirect_diffuse_body, count, c, 128);
   BE_CHECK(h, h->be.check());

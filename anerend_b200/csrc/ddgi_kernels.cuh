@@ -933,6 +933,7 @@ struct ConvCtx {
   uint2* peers[8]; int numPeers;
   int nXZ, nY, N, Sx, Sy, W, H, numLayers;
   int Pl, rowOffset, rowStride;              // row stripe, as in TraceCtx
+  int bakeMode;                              // UBO_BAKE_MODE_ON_FLAG: running weighted mean instead of the hysteresis blend (probe_conv.comp:67-79)
   float hysteresis;
 };
 HD void conv_texel_body(uint32_t idx, const ConvCtx& c) {
@@ -958,9 +959,17 @@ HD void conv_texel_body(uint32_t idx, const ConvCtx& c) {
   const size_t ti = (size_t)ay * c.W + ax;
   const uint2 ot = c.atlas[ti];
   const float o0 = h2f((uint16_t)(ot.x & 0xFFFFu)), o1 = h2f((uint16_t)(ot.x >> 16)), o2 = h2f((uint16_t)(ot.y & 0xFFFFu)), o3 = h2f((uint16_t)(ot.y >> 16));
-  if (r3 > 1e-6f) { r0 /= r3; r1 /= r3; r2 /= r3; }
-  const float hy = c.hysteresis;
-  const float n0 = r0 * (1.0f - hy) + o0 * hy, n1 = r1 * (1.0f - hy) + o1 * hy, n2 = r2 * (1.0f - hy) + o2 * hy, n3 = r3 * (1.0f - hy) + o3 * hy;
+  float n0, n1, n2, n3;
+  if (c.bakeMode) {
+    const float totalWeight = o3 + r3;
+    float t0 = r0 + o0 * o3, t1 = r1 + o1 * o3, t2 = r2 + o2 * o3;
+    if (totalWeight > 1e-6f) { t0 /= totalWeight; t1 /= totalWeight; t2 /= totalWeight; }
+    n0 = t0; n1 = t1; n2 = t2; n3 = totalWeight;
+  } else {
+    if (r3 > 1e-6f) { r0 /= r3; r1 /= r3; r2 /= r3; }
+    const float hy = c.hysteresis;
+    n0 = r0 * (1.0f - hy) + o0 * hy; n1 = r1 * (1.0f - hy) + o1 * hy; n2 = r2 * (1.0f - hy) + o2 * hy; n3 = r3 * (1.0f - hy) + o3 * hy;
+  }
   const uint2 nt = make_uint2((uint32_t)f2h(n0) | ((uint32_t)f2h(n1) << 16), (uint32_t)f2h(n2) | ((uint32_t)f2h(n3) << 16));
   c.atlas[ti] = nt;
   for (int p = 0; p < c.numPeers; ++p) c.peers[p][ti] = nt;               // fused all-gather: store into every peer's atlas

@@ -192,12 +192,20 @@ __global__ void __launch_bounds__(256) k_probe_convolve_fast(const ConvFastCtx f
     const float o0 = h2f((uint16_t)(ot.x & 0xFFFFu)), o1 = h2f((uint16_t)(ot.x >> 16)), o2 = h2f((uint16_t)(ot.y & 0xFFFFu)), o3 = h2f((uint16_t)(ot.y >> 16));
     float r0 = acc[k][0], r1 = acc[k][1], r2 = acc[k][2];
     const float r3 = accW;
+    float n0, n1, n2, n3;
+    if (c.bakeMode) {                       // probe_conv.comp:67-79: running weighted mean, weight sum in alpha
+      const float totalWeight = o3 + r3;
+      float t0 = r0 + o0 * o3, t1 = r1 + o1 * o3, t2 = r2 + o2 * o3;
+      if (totalWeight > 1e-6f) { t0 /= totalWeight; t1 /= totalWeight; t2 /= totalWeight; }
+      n0 = t0; n1 = t1; n2 = t2; n3 = totalWeight;
+    } else {
 #ifdef DDGI_SHADE_EXACT
-    if (r3 > 1e-6f) { r0 /= r3; r1 /= r3; r2 /= r3; }
+      if (r3 > 1e-6f) { r0 /= r3; r1 /= r3; r2 /= r3; }
 #else
-    if (r3 > 1e-6f) { const float inv = 1.0f / r3; r0 *= inv; r1 *= inv; r2 *= inv; }
+      if (r3 > 1e-6f) { const float inv = 1.0f / r3; r0 *= inv; r1 *= inv; r2 *= inv; }
 #endif
-    const float n0 = r0 * (1.0f - hy) + o0 * hy, n1 = r1 * (1.0f - hy) + o1 * hy, n2 = r2 * (1.0f - hy) + o2 * hy, n3 = r3 * (1.0f - hy) + o3 * hy;
+      n0 = r0 * (1.0f - hy) + o0 * hy; n1 = r1 * (1.0f - hy) + o1 * hy; n2 = r2 * (1.0f - hy) + o2 * hy; n3 = r3 * (1.0f - hy) + o3 * hy;
+    }
     const uint2 nt = make_uint2((uint32_t)f2h(n0) | ((uint32_t)f2h(n1) << 16), (uint32_t)f2h(n2) | ((uint32_t)f2h(n3) << 16));
     c.atlas[ti] = nt;
     for (int p = 0; p < c.numPeers; ++p) c.peers[p][ti] = nt;               // fused all-gather: store into every peer's atlas

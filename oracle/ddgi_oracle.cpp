@@ -468,7 +468,15 @@ struct ddgi_oracle {
   }
 
   // ---- probe-grid addressing shared by rgen:75-83 and pbr_light.glsl:294-301 -------------------------
+  // Bake mode (UBO_BAKE_MODE_ON_FLAG; rgen:61-73, pbr_light.glsl:274-291): the grid covers the tile bakeTileInfo.xy of size
+  // bakeTileInfo.z: origin = tile corner, step = (tSize / nXZ, 1.0, tSize / nXZ) — the y step is 1, not PROBE_STEP.y.
+  bool bakeMode() const { return (ubo.flags & ANEREND_UBO_BAKE_MODE_ON_FLAG) == ANEREND_UBO_BAKE_MODE_ON_FLAG; }
+  V3 gridStep() const {
+    if (bakeMode()) { float s = float(ubo.bake_tile_info[2]) / float(nXZ); return v3(s, 1.0f, s); }
+    return v3(p.probe_step[0], p.probe_step[1], p.probe_step[2]);
+  }
   V3 camOffset() const {
+    if (bakeMode()) return v3(float(ubo.bake_tile_info[0]) * float(ubo.bake_tile_info[2]), 0.0f, float(ubo.bake_tile_info[1]) * float(ubo.bake_tile_info[2]));
     int cix = (int)(ubo.camera_pos[0] / p.probe_step[0]);   // C truncation, quirk Q1
     int ciz = (int)(ubo.camera_pos[2] / p.probe_step[2]);
     return v3(float(cix) * p.probe_step[0] - p.probe_step[0] * float(nXZ) / 2.0f, 0.0f,
@@ -609,7 +617,7 @@ struct ddgi_oracle {
   }
   // pbr_light.glsl:240-363, live-grid branch (:294-308); no baked tiles (quirk Q5), bake mode out of scope
   V3 sampleProbe(V3 worldPos, V3 normal) const {
-    V3 step = v3(p.probe_step[0], p.probe_step[1], p.probe_step[2]);
+    V3 step = gridStep();
     V3 co = camOffset();
     int px = std::min(std::max((int)std::floor((worldPos.x - co.x) / step.x), 0), nXZ - 1);
     int py = std::min(std::max((int)std::floor(worldPos.y / step.y), 0), nY - 1);
@@ -729,7 +737,7 @@ struct ddgi_oracle {
     // rmiss:17-21
     V3 sky = toLinear(v3(ubo.sky_intensity * ubo.sky_color[0], ubo.sky_intensity * ubo.sky_color[1], ubo.sky_intensity * ubo.sky_color[2]));
     V3 co = camOffset();
-    V3 step = v3(p.probe_step[0], p.probe_step[1], p.probe_step[2]);
+    V3 step = gridStep();
     parallelFor(P, [&](int probe) {
       int probeX = probe % nXZ, probeZ = probe / nXZ;
       V3 origin = v3(float(probeX), float(layer), float(probeZ)) * step + co;
@@ -778,9 +786,15 @@ struct ddgi_oracle {
         int ax = 10 * probeX + 1 + i, ay = 10 * nXZ * layer + 10 * probeZ + 1 + j;   // pixOffset + pixel (probe_conv.comp:42,64)
         uint16_t* t = &atlas[4 * ((size_t)ay * W + ax)];
         float old[4] = {h2f(t[0]), h2f(t[1]), h2f(t[2]), h2f(t[3])};
-        if (r4[3] > 1e-6f) { r4[0] /= r4[3]; r4[1] /= r4[3]; r4[2] /= r4[3]; }
+        float baked[4];
+        if (bakeMode()) {                      // probe_conv.comp:67-79: running weighted mean, weight sum in alpha
+          float totalWeight = old[3] + r4[3];
+          float tr[3] = {r4[0] + old[0] * old[3], r4[1] + old[1] * old[3], r4[2] + old[2] * old[3]};
+          if (totalWeight > 1e-6f) { tr[0] /= totalWeight; tr[1] /= totalWeight; tr[2] /= totalWeight; }
+          baked[0] = tr[0]; baked[1] = tr[1]; baked[2] = tr[2]; baked[3] = totalWeight;
+        } else if (r4[3] > 1e-6f) { r4[0] /= r4[3]; r4[1] /= r4[3]; r4[2] /= r4[3]; }
         for (int c = 0; c < 4; ++c) {
-          float o = r4[c] * (1.0f - hysteresis) + old[c] * hysteresis;
+          float o = bakeMode() ? baked[c] : r4[c] * (1.0f - hysteresis) + old[c] * hysteresis;
           t[c] = f2h(o);
           if (trec) texelRecords[4 * ((size_t)ay * W + ax) + c] = o;
         }

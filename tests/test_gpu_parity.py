@@ -462,3 +462,27 @@ def test_shadow_rt_matches_oracle_bit_for_bit(kernels, oracle, make_gpu):
     assert np.array_equal(dout.cpu().numpy(), ro)
     o.close()
     g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernels", ["wavefront", "simple"])
+def test_bake_mode_matches_oracle_bit_for_bit(kernels, oracle, make_gpu):
+    """SURVEY §8f N4 through the C ABI: bake mode (tile-placed grid, running-mean convolution) with the production kernels."""
+    nxz, ny, nr = 8, 4, 64
+    scene = scenes.cornell_box(grid=(nxz, ny, nr), wall_res=10, box_res=3)
+    p = make_params(nxz, ny, nr, flags=ALL | KERNEL_FLAGS[kernels])
+    o, g = oracle.Oracle(p), make_gpu(p)
+    rots = parity.setup_pair(scene, (o, g), seed=6)
+    ubo = scene.ubo.copy()
+    ubo["flags"] |= L.UBO_BAKE_MODE_ON_FLAG
+    ubo["bake_tile_info"][0] = (-1, 0, 6, 0)
+    for h in (o, g):
+        h.set_scene_ubo(ubo)
+    for it in range(3):
+        for h in (o, g):
+            h.translate()
+            h.update(-1, rots)
+        _check_update(o, g, ny)
+        assert np.array_equal(o.download_atlas(), g.download_atlas()), "atlas is not bit-identical"
+    o.close()
+    g.close()

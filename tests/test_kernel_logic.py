@@ -247,3 +247,28 @@ def test_shadow_rt_matches_oracle(oracle, make_emu):
         assert (h.shadow_rt(depth) == -1.0).all()                   # shadow.rgen:32-34: nothing written
     o.close()
     e.close()
+
+
+def test_bake_mode_matches_oracle(oracle, make_emu):
+    """UBO_BAKE_MODE_ON_FLAG — tile-placed grid (rgen:61-73, pbr_light.glsl:274-291), running-mean convolution
+    (probe_conv.comp:67-79), translation disabled; three accumulating updates, atlas bit-identical."""
+    scene, (nxz, ny, nr) = SCENES["cornell"]()
+    p = make_params(nxz, ny, nr, flags=ALL)
+    o, e = oracle.Oracle(p), make_emu(p)
+    rots = parity.setup_pair(scene, (o, e), seed=6)
+    ubo = scene.ubo.copy()
+    ubo["flags"] |= L.UBO_BAKE_MODE_ON_FLAG
+    ubo["bake_tile_info"][0] = (-1, 0, 6, 0)
+    for h in (o, e):
+        h.set_scene_ubo(ubo)
+    for it in range(3):
+        for h in (o, e):
+            h.translate()
+            h.update(-1, rots)
+        for layer in range(ny):
+            parity.compare_records(o.download_ray_records(layer), e.download_ray_records(layer))
+        assert np.array_equal(o.download_atlas(), e.download_atlas())
+    a = o.download_atlas().view(np.float16).astype(np.float32)
+    assert a[..., 3].max() > 100.0                                   # alpha carries the accumulated weight
+    o.close()
+    e.close()

@@ -462,3 +462,52 @@ def test_shadow_rt_known_answer(oracle):
     want[0, :] = 1.0
     assert np.array_equal(got, want)
     o.close()
+
+
+def test_bake_mode_running_mean_and_tile_grid(oracle):
+    """KATs for bake mode.  (a) probe_conv.comp:67-79: with uniform radiance L on all rays, k convolutions from
+    the cleared atlas (0,0,0,1) give alpha = 1 + k*S and rgb = L * k*S / (1 + k*S), S = sum of the texel's weights (the cleared
+    texel counts as one black sample of weight 1).  (b) rgen:61-73: the grid covers tile bakeTileInfo.xy of size bakeTileInfo.z
+    with step (tSize/nXZ, 1, tSize/nXZ): in an empty scene nothing depends on it, with one quad it decides which probes see it."""
+    o, dir_img, _ = _conv_setup(oracle, 4, 2, 256, seed=1)
+    ubo = scenes.empty_scene(grid=(4, 2, 256)).ubo.copy()
+    ubo["flags"] |= L.UBO_BAKE_MODE_ON_FLAG
+    ubo["bake_tile_info"][0] = (0, 0, 8, 0)
+    o.set_scene_ubo(ubo)
+    L0 = np.array([0.75, 1.5, 0.25], np.float16)
+    irr = np.zeros_like(dir_img); irr[..., :3] = L0; irr[..., 3] = 1.0
+    for layer in range(2):
+        o.set_rays(layer, irr.view(np.uint16), dir_img.view(np.uint16))
+    from tests import parity as _p
+    mask = _p.interior_mask(4, 2)
+    S = None
+    for k in range(1, 5):
+        for layer in range(2):
+            o.convolve_layer(layer)
+        rec = o.download_texel_records()
+        alpha = rec[..., 3][mask]
+        if S is None:
+            S = alpha - 1.0
+            assert np.all((S > 55) & (S < 75))                    # ~N/4 = 64
+        np.testing.assert_allclose(alpha, 1.0 + k * S, rtol=3e-3)  # alpha is re-rounded to fp16 every update
+        rgb = rec[..., :3][mask]
+        want = L0.astype(np.float64)[None, :] * (k * S / (1.0 + k * S))[:, None]
+        np.testing.assert_allclose(rgb, want, rtol=3e-3)
+    o.close()
+    # (b) probe origins: quad straight above tile (1, 0) of size 4 -> only probes of a handle baking that tile see it overhead
+    b = scenes.SceneBuilder("kat_bake", 1)
+    pos = np.array([(4, 9, 0), (8, 9, 0), (8, 9, 4), (4, 9, 4)], np.float32)
+    mesh = b.add_mesh(pos, np.tile(np.array([0, -1, 0], np.float32), (4, 1)), np.array([0, 1, 2, 0, 2, 3], np.uint32))
+    b.add_renderable(np.eye(4), mesh, b.add_material((0.5, 0.5, 0.5), emissive=(1.0, 1.0, 1.0, 3.0)))
+    s = b.finish((100.0, 1.0, 100.0), (4, 2, 64))                  # the camera is far away: bake mode must not use it
+    hits = {}
+    for tile in ((1, 0), (5, 5)):
+        oo = oracle.Oracle(make_params(4, 2, 64, flags=L.FLAG_RAY_RECORDS))
+        oo.upload_scene(s); oo.build_accel()
+        u = s.ubo.copy(); u["flags"] |= L.UBO_BAKE_MODE_ON_FLAG; u["bake_tile_info"][0] = (tile[0], tile[1], 4, 0)
+        oo.set_scene_ubo(u)
+        oo.translate()                                              # no-op in bake mode (IrradianceProbeTranslationPass.cpp:58-59)
+        oo.update(-1, oo.rotations(scenes.rotation_sequence(1, 2)))
+        hits[tile] = sum(int((oo.download_ray_records(l)["prim"] != 0xFFFFFFFF).sum()) for l in range(2))
+        oo.close()
+    assert hits[(1, 0)] > 10 and hits[(5, 5)] == 0        # ~1.6 % of 2048 rays point at the quad from 8-9 m below
