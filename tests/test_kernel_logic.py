@@ -269,6 +269,6 @@ def test_bake_mode_matches_oracle(oracle, make_emu):
             parity.compare_records(o.download_ray_records(layer), e.download_ray_records(layer))
         assert np.array_equal(o.download_atlas(), e.download_atlas())
     a = o.download_atlas().view(np.float16).astype(np.float32)
-    assert a[..., 3].max() > 100.0                                   # alpha carries the accumulated weight
+    assert a[..., 3].max() > 40.0                                    # alpha carries the accumulated weight (3 x ~16 at 64 rays)
     o.close()
     e.close()
