@@ -105,7 +105,7 @@ def run_oracle_sample(scene, grid, layers, threads=0, point_lights=True):
     from anerend_b200 import layouts as L, make_params, scenes
     from oracle import binding as ob
     nxz, ny, nr = grid
-    o = ob.Oracle(make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS if point_lights else 0))
+    o = ob.Oracle(make_params(nxz, ny, nr, flags=(L.FLAG_POINT_LIGHTS | L.FLAG_SKIP_DEAD_SHADOW_RAYS) if point_lights else L.FLAG_SKIP_DEAD_SHADOW_RAYS))
     nthreads = o.set_threads(threads)
     o.upload_scene(scene)
     o.set_scene_ubo(scene.ubo)
@@ -129,7 +129,7 @@ def reference_arm(args, rank, world):
     from anerend_b200 import layouts as L, make_params, scenes
     from oracle import binding as ob
     nxz, ny, nr = grid
-    o = ob.Oracle(make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS))
+    o = ob.Oracle(make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS | L.FLAG_SKIP_DEAD_SHADOW_RAYS))     # the same work as the CUDA arm
     threads = o.set_threads(0)
     o.upload_scene(scene)
     o.set_scene_ubo(scene.ubo)
