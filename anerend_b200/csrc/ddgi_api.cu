@@ -397,12 +397,14 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   k_zero_words<<<(FAST_QC_SIZE + 255u) / 256u, 256, 0, be.stream>>>(h->dQcount, (uint32_t)FAST_QC_SIZE);
   ++be.launches;
   const bool cnt = (h->p.flags & ANEREND_DDGI_FLAG_COUNTERS) != 0;
-  const uint32_t blocks = (n + PREP_BLOCK - 1u) / PREP_BLOCK;
+  static const int prepBlock = getenv("DDGI_PREP_BLOCK") ? atoi(getenv("DDGI_PREP_BLOCK")) : PREP_BLOCK_DEFAULT;     // sweeps only
   const int gp = h->gridPrimary[cnt ? 1 : 0], gs = h->gridShadow[cnt ? 1 : 0];
   be.mark(6);
   if (cnt) k_trace<false, true><<<gp, 128, 0, be.stream>>>(f); else k_trace<false, false><<<gp, 128, 0, be.stream>>>(f);
   be.mark(7);
-  k_shade_prep<<<blocks, PREP_BLOCK, 0, be.stream>>>(f);
+  if (prepBlock == 128) k_shade_prep<128><<<(n + 127u) / 128u, 128, 0, be.stream>>>(f);
+  else if (prepBlock == 512) k_shade_prep<512><<<(n + 511u) / 512u, 512, 0, be.stream>>>(f);
+  else k_shade_prep<256><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
   be.mark(8);
   if (cnt) k_trace<true, true><<<gs, 128, 0, be.stream>>>(f); else k_trace<true, false><<<gs, 128, 0, be.stream>>>(f);
   be.mark(9);

@@ -300,8 +300,7 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
 // ------------------------------------------------------------------------------------------------------------
 // k_shade_prep: rchit:27-42,70-77 (hit attributes + surface) and the decision which shadow rays exist
 // ------------------------------------------------------------------------------------------------------------
-#define PREP_BLOCK 256
-#define PREP_WARPS (PREP_BLOCK / 32)
+#define PREP_BLOCK_DEFAULT 256
 // getSurfaceDataFromMat with texture taps (bindless.glsl:196-233), uv as rchit:70.  Out of line: factor-only scenes (all
 // BASELINE configs) must not pay registers for the sampling code (32 registers = 8 blocks per SM).
 // Returns (albedo.rgb, metallic) and writes roughness through the side buffer slot: everything travels in registers.
@@ -315,7 +314,9 @@ __device__ __noinline__ float4 prep_textured_surface(const TexCtx tex, const flo
   *roughnessOut = sf.roughness;
   return make_float4(sf.albedo.x, sf.albedo.y, sf.albedo.z, sf.metallic);
 }
-__global__ void __launch_bounds__(PREP_BLOCK, 8) k_shade_prep(const FastCtx c) {
+template <int PREP_BLOCK>
+__global__ void __launch_bounds__(PREP_BLOCK, 2048 / PREP_BLOCK) k_shade_prep(const FastCtx c) {
+  constexpr int PREP_WARPS = PREP_BLOCK / 32;
   const TraceCtx& t = c.t;
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
   const bool inRange = idx < c.totalRays;
