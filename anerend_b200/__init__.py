@@ -70,6 +70,9 @@ class Ddgi(DdgiHandle):
     def exchange_disconnect(self):
         self._call("exchange_disconnect")
 
+    def specular_gi_device(self, d_depth, d_geom0, width, height, d_out):
+        self._call("specular_gi_device", _C.c_void_p(d_depth), _C.c_void_p(d_geom0), _C.c_uint32(width), _C.c_uint32(height), _C.c_void_p(d_out))
+
     def shadow_rt_device(self, d_depth, width, height, d_out):
         self._call("shadow_rt_device", _C.c_void_p(d_depth), _C.c_uint32(width), _C.c_uint32(height), _C.c_void_p(d_out))
 

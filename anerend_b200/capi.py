@@ -203,6 +203,15 @@ class DdgiHandle:
             self._call("sync")
 
     # ---- results ---------------------------------------------------------------------------------
+    def specular_gi(self, depth, geom0):
+        """Frame-graph pass "SpecularGIRT": depth float32 [h, w], geom0 float32 [h, w, 4] (normal in rgb) -> uint16 [h, w, 4]
+        (RGBA16F bit patterns: irradiance, hit distance)."""
+        depth = _c(depth, np.float32)
+        geom0 = _c(geom0, np.float32)
+        out = np.full(depth.shape + (4,), 0xFFFF, np.uint16)          # untouched when the pass is disabled
+        self._call("specular_gi", _ptr(depth), _ptr(geom0), C.c_uint32(depth.shape[1]), C.c_uint32(depth.shape[0]), _ptr(out))
+        return out
+
     def shadow_rt(self, depth):
         """Frame-graph pass "ShadowRT": depth float32 [height, width] -> r32f [height, width] (1 lit / sky, 0 shadowed)."""
         depth = _c(depth, np.float32)

@@ -42,6 +42,7 @@ DDGI_KERNEL(k_probe_convolve, conv_texel_body, ConvCtx)
 DDGI_KERNEL(k_probe_translate, translate_body, TransCtx)
 DDGI_KERNEL(k_indirect_diffuse, indirect_diffuse_body, ConsumerCtx)
 DDGI_KERNEL(k_shadow_rt, shadow_rt_body, ShadowRtCtx)
+DDGI_KERNEL(k_specular_gi, specular_gi_body, SpecularCtx)
 DDGI_KERNEL(k_atlas_clear, clear_body, ClearCtx)
 
 // ------------------------------------------------------------------------------------------------ handle
@@ -499,6 +500,29 @@ int peerCheck(anerend_ddgi*) { return 0; }
 void exchangeDisconnect(anerend_ddgi*) {}
 #endif
 
+// Everything of a TraceCtx that does not depend on which layers are launched
+TraceCtx sceneTraceCtx(anerend_ddgi* h) {
+  TraceCtx c{};
+  c.nodes = h->dNodes; c.bvhTris = h->dBvhTris; c.numNodes = h->numNodes;
+  c.vertices = h->dVertices; c.indices = h->dIndices; c.materials = h->dMaterials;
+  c.tex.textures = h->dTextures; c.tex.texPool = h->dTexPool; c.tex.srgbLut = h->dSrgbLut; c.tex.numTextures = h->numTextures;
+  c.instances = h->dInstances; c.xforms = h->dXforms; c.triInstance = h->dTriInstance;
+  c.lights = h->dLights; c.numLights = h->numLights;
+  c.dirs = h->dDirs; c.layerMap = h->dLayerMap; c.rayOrder = h->dRayOrder; c.atlas = h->dAtlas; c.rayIrr = h->dRayIrr;
+  c.records = h->dRecords; c.stats = h->dStats;
+  c.nXZ = h->nXZ; c.nY = h->nY; c.N = h->N; c.W = h->W; c.H = h->H; c.numLayers = 0;
+  c.Pl = h->Pl; c.rowOffset = h->rowOffset; c.rowStride = h->rowStride;
+  gridFrame(h, c.camOff, c.step);
+  // rmiss:20 toLinear(skyIntensity * skyColor), constant per frame
+  { float s[3]; for (int k = 0; k < 3; ++k) { float v = h->ubo.sky_intensity * h->ubo.sky_color[k];
+      float higher = powf((v + 0.055f) / 1.055f, 2.4f), lower = v / 12.92f; s[k] = (v < 0.04045f) ? lower : higher; }
+    c.sky = mk3(s[0], s[1], s[2]); }
+  c.lightDir = mk3(h->ubo.light_dir[0], h->ubo.light_dir[1], h->ubo.light_dir[2]);
+  c.tmin = h->p.t_min; c.tmax = h->p.t_max; c.sunIntensity = h->ubo.sun_intensity;
+  c.uboFlags = h->ubo.flags; c.flags = h->p.flags;
+  return c;
+}
+
 #ifndef DDGI_HOST_EMU
 #define DIRS_BATCH 32
 struct DirsCtx { float m[DIRS_BATCH][9]; int layer[DIRS_BATCH]; const float* fib; float4* dDirs; int* dLayerMap; uint32_t N, first, count; };
@@ -553,24 +577,7 @@ int traceLayers(anerend_ddgi* h, const int* layers, int numLayers, const float* 
   BE_CHECK(h, be.h2d(h->dLayerMap, h->hLayerMap, (size_t)numLayers * sizeof(int)));
 #endif
   h->numLaunchLayers = numLayers;
-  TraceCtx c{};
-  c.nodes = h->dNodes; c.bvhTris = h->dBvhTris; c.numNodes = h->numNodes;
-  c.vertices = h->dVertices; c.indices = h->dIndices; c.materials = h->dMaterials;
-  c.tex.textures = h->dTextures; c.tex.texPool = h->dTexPool; c.tex.srgbLut = h->dSrgbLut; c.tex.numTextures = h->numTextures;
-  c.instances = h->dInstances; c.xforms = h->dXforms; c.triInstance = h->dTriInstance;
-  c.lights = h->dLights; c.numLights = h->numLights;
-  c.dirs = h->dDirs; c.layerMap = h->dLayerMap; c.rayOrder = h->dRayOrder; c.atlas = h->dAtlas; c.rayIrr = h->dRayIrr;
-  c.records = h->dRecords; c.stats = h->dStats;
-  c.nXZ = h->nXZ; c.nY = h->nY; c.N = h->N; c.W = h->W; c.H = h->H; c.numLayers = numLayers;
-  c.Pl = h->Pl; c.rowOffset = h->rowOffset; c.rowStride = h->rowStride;
-  gridFrame(h, c.camOff, c.step);
-  // rmiss:20 toLinear(skyIntensity * skyColor), constant per frame
-  { float s[3]; for (int k = 0; k < 3; ++k) { float v = h->ubo.sky_intensity * h->ubo.sky_color[k];
-      float higher = powf((v + 0.055f) / 1.055f, 2.4f), lower = v / 12.92f; s[k] = (v < 0.04045f) ? lower : higher; }
-    c.sky = mk3(s[0], s[1], s[2]); }
-  c.lightDir = mk3(h->ubo.light_dir[0], h->ubo.light_dir[1], h->ubo.light_dir[2]);
-  c.tmin = h->p.t_min; c.tmax = h->p.t_max; c.sunIntensity = h->ubo.sun_intensity;
-  c.uboFlags = h->ubo.flags; c.flags = h->p.flags;
+  TraceCtx c = sceneTraceCtx(h); c.numLayers = numLayers;
   const uint32_t n = (uint32_t)numLayers * (uint32_t)h->Pl * (uint32_t)h->N;
 #ifndef DDGI_HOST_EMU
   if (!(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS)) { int rc = traceFast(h, c, n); if (rc) return rc; } else
@@ -984,6 +991,45 @@ int DDGI_API(shadow_rt)(anerend_ddgi_t* h, const float* depth, uint32_t width, u
   if (!rc) rc = shadowRt(h, dD, width, height, dO);
   if (!rc && !be.d2h(out, dO, n * sizeof(float))) rc = fail(h, ANEREND_DDGI_E_CUDA, std::string("shadow_rt: ") + be.errStr());
   be.sync(); be.free(dD); be.free(dO);
+  return rc;
+}
+
+// ---- SpecularGIRT on the same BVH and atlas -----------------------------------------------------
+namespace {
+int specularGi(anerend_ddgi* h, const float* dDepth, const float4* dGeom0, uint32_t width, uint32_t height, uint2* dOut) {
+  if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "specular_gi before build_accel");
+  if (!h->haveUbo) return fail(h, ANEREND_DDGI_E_STATE, "specular_gi before set_scene_ubo");
+  if (!(h->ubo.flags & ANEREND_UBO_RT_ON_FLAG) || !(h->ubo.flags & ANEREND_UBO_SPECULAR_GI_FLAG)) return 0;    // SpecularGIRTPass.cpp:102-103
+  const uint32_t n = width * height;
+  if (n == 0) return 0;
+  SpecularCtx c{};
+  c.t = sceneTraceCtx(h);
+  c.t.tmin = 0.1f; c.t.tmax = 50.0f; c.t.records = nullptr; c.t.stats = nullptr;      // literals of mirror_reflections.rgen:57-58 / .rchit:49-50
+  c.depth = dDepth; c.geom0 = dGeom0; c.out = dOut; c.width = (int)width; c.height = (int)height;
+  for (int k = 0; k < 16; ++k) c.invViewProj[k] = h->ubo.inv_view_proj[k];
+  c.cameraPos = mk3(h->ubo.camera_pos[0], h->ubo.camera_pos[1], h->ubo.camera_pos[2]);
+  c.screenW = (float)h->ubo.screen_width; c.screenH = (float)h->ubo.screen_height;
+  DDGI_LAUNCH(h->be, k_specular_gi, specular_gi_body, n, c, 128);
+  BE_CHECK(h, h->be.check());
+  return 0;
+}
+}  // namespace
+int DDGI_API(specular_gi_device)(anerend_ddgi_t* h, const void* dDepth, const void* dGeom0, uint32_t width, uint32_t height, void* dOut) {
+  if (!dDepth || !dGeom0 || !dOut) return fail(h, ANEREND_DDGI_E_INVALID, "null argument");
+  return specularGi(h, (const float*)dDepth, (const float4*)dGeom0, width, height, (uint2*)dOut);
+}
+int DDGI_API(specular_gi)(anerend_ddgi_t* h, const float* depth, const float* geom0, uint32_t width, uint32_t height, void* outRgba16f) {
+  if (!depth || !geom0 || !outRgba16f) return fail(h, ANEREND_DDGI_E_INVALID, "null argument");
+  if (!h->haveUbo) return fail(h, ANEREND_DDGI_E_STATE, "specular_gi before set_scene_ubo");
+  const size_t n = (size_t)width * height;
+  if (n == 0 || !(h->ubo.flags & ANEREND_UBO_RT_ON_FLAG) || !(h->ubo.flags & ANEREND_UBO_SPECULAR_GI_FLAG)) return 0;
+  Backend& be = h->be;
+  float* dD = nullptr; float4* dG = nullptr; uint2* dO = nullptr;
+  if (!be.alloc(&dD, n) || !be.alloc(&dG, n) || !be.alloc(&dO, n)) { be.free(dD); be.free(dG); be.free(dO); return fail(h, ANEREND_DDGI_E_CUDA, std::string("specular_gi: ") + be.errStr()); }
+  int rc = (be.h2d(dD, depth, n * sizeof(float)) && be.h2d(dG, geom0, n * sizeof(float4))) ? 0 : fail(h, ANEREND_DDGI_E_CUDA, std::string("specular_gi: ") + be.errStr());
+  if (!rc) rc = specularGi(h, dD, dG, width, height, dO);
+  if (!rc && !be.d2h(outRgba16f, dO, n * sizeof(uint2))) rc = fail(h, ANEREND_DDGI_E_CUDA, std::string("specular_gi: ") + be.errStr());
+  be.sync(); be.free(dD); be.free(dG); be.free(dO);
   return rc;
 }
 

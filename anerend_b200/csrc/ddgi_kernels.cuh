@@ -835,6 +835,105 @@ HD void shadow_rt_body(uint32_t i, const ShadowRtCtx& c) {
   c.out[i] = occluded ? 0.0f : 1.0f;                       // payload starts at 0, shadow.rmiss sets 1
 }
 
+// rchit main for one hit (irradiance_probe_update.rchit:24-111; SPECULAR: mirror_reflections.rchit:24-118, which differs in the
+// normal transform and in the flag that gates the indirect term).  origin = gl_WorldRayOriginEXT.
+template <bool CNT, bool SPECULAR>
+HD V3 shade_hit_simple(const TraceCtx& c, const Hit& hit, V3 origin, uint32_t& lit, uint32_t& nShadow, uint32_t* cn, uint32_t* ct, V3& hitPos) {
+  const uint32_t ii = c.triInstance[hit.prim];
+  const DInstance in = c.instances[ii];
+  const InstXform& xf = c.xforms[ii];
+  const uint32_t prim = hit.prim - in.firstTri;                                            // gl_PrimitiveID
+  const anerend_vertex_t* v0 = &c.vertices[in.vertexOffset + c.indices[in.indexOffset + 3 * prim + 0]];
+  const anerend_vertex_t* v1 = &c.vertices[in.vertexOffset + c.indices[in.indexOffset + 3 * prim + 1]];
+  const anerend_vertex_t* v2 = &c.vertices[in.vertexOffset + c.indices[in.indexOffset + 3 * prim + 2]];
+  const float b0 = 1.0f - hit.u - hit.v, b1 = hit.u, b2 = hit.v;
+  V3 pos = mk3(v0->pos[0], v0->pos[1], v0->pos[2]) * b0 + mk3(v1->pos[0], v1->pos[1], v1->pos[2]) * b1 + mk3(v2->pos[0], v2->pos[1], v2->pos[2]) * b2;
+  pos = xform_point(xf.o2w, pos);                                                          // rchit:42
+  V3 normal = normalize3(mk3(v0->normal[0], v0->normal[1], v0->normal[2]) * b0 + mk3(v1->normal[0], v1->normal[1], v1->normal[2]) * b1 +
+                         mk3(v2->normal[0], v2->normal[1], v2->normal[2]) * b2);
+  if (!SPECULAR)
+    normal = normalize3(mk3(normal.x * xf.w2o[0] + normal.y * xf.w2o[1] + normal.z * xf.w2o[2],
+                            normal.x * xf.w2o[3] + normal.y * xf.w2o[4] + normal.z * xf.w2o[5],
+                            normal.x * xf.w2o[6] + normal.y * xf.w2o[7] + normal.z * xf.w2o[8]));   // rchit:73: normal * gl_WorldToObjectEXT
+  else                                                                                           // mirror_reflections.rchit:74: mat3(gl_ObjectToWorldEXT) * normal
+    normal = normalize3(mk3(xf.o2w[0] * normal.x + xf.o2w[3] * normal.y + xf.o2w[6] * normal.z,
+                            xf.o2w[1] * normal.x + xf.o2w[4] * normal.y + xf.o2w[7] * normal.z,
+                            xf.o2w[2] * normal.x + xf.o2w[5] * normal.y + xf.o2w[8] * normal.z));
+  V3 color = mk3(v0->color[0], v0->color[1], v0->color[2]) * b0 + mk3(v1->color[0], v1->color[1], v1->color[2]) * b1 +
+             mk3(v2->color[0], v2->color[1], v2->color[2]) * b2;
+  color = mk3(to_linear1(color.x), to_linear1(color.y), to_linear1(color.z));              // rchit:75
+  // getSurfaceDataFromMat (bindless.glsl:181-237); uv as rchit:70
+  const anerend_material_info_t* m = &c.materials[in.material];
+  const float tu = v0->uv[0] * b0 + v1->uv[0] * b1 + v2->uv[0] * b2, tv = v0->uv[1] * b0 + v1->uv[1] * b1 + v2->uv[1] * b2;
+  const Surface sf = surface_from_material(c.tex, m, tu, tv, color);
+  const V3 albedo = sf.albedo, emissive = sf.emissive;
+  const float metallic = sf.metallic, roughness = sf.roughness;
+  // sun shadow ray (rchit:45-66): any-hit, origin = hit position without offset
+  const V3 sunL = normalize3(-c.lightDir);
+  Hit sh;
+  bool occluded = true;
+  if (!(c.flags & ANEREND_DDGI_FLAG_SKIP_DEAD_SHADOW_RAYS) || dot3(normal, sunL) > 0.0f) {
+    ++nShadow;
+    occluded = traverse<true, CNT>(c.nodes, c.bvhTris, c.numNodes, pos, sunL, c.tmin, c.tmax, sh, cn[1], ct[1]);
+  }
+  V3 irradiance = mk3(0.0f);
+  if (!occluded) { lit |= 1u; irradiance = calc_light(normal, albedo, metallic, roughness, pos, origin, sunL, c.sunIntensity * mk3(1.0f) * 1.0f); }
+  if (c.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) {
+    // extension E1: enabled point lights, calcLight(directional = 0) gated by an any-hit ray pos -> light
+    for (uint32_t li = 0; li < c.numLights; ++li) {
+      const anerend_light_t* lt = &c.lights[li];
+      if (!(lt->color[3] > 0.5f)) continue;
+      const V3 lp = mk3(lt->world_pos[0], lt->world_pos[1], lt->world_pos[2]);
+      const V3 dv = lp - pos; const float dist = sqrtf(dot3(dv, dv)), range = lt->world_pos[3];
+      if (!(dist < range)) continue;
+      const V3 L = normalize3(lp - pos);
+      if (!(dot3(normal, L) > 0.0f)) continue;
+      ++nShadow;
+      if (traverse<true, CNT>(c.nodes, c.bvhTris, c.numNodes, pos, L, c.tmin, dist, sh, cn[1], ct[1])) continue;
+      lit |= 1u << (1u + li);
+      const float dd = fminf(dist, range);
+      const float att = (1.0f - dd / range) * (1.0f - dd / range) * 1.0f;
+      irradiance = irradiance + calc_light(normal, albedo, metallic, roughness, pos, origin, L, mk3(lt->color[0], lt->color[1], lt->color[2]) * att);
+    }
+  }
+  const uint32_t gate = SPECULAR ? ANEREND_UBO_DDGI_FLAG : ANEREND_UBO_DDGI_MULTI_FLAG;      // mirror_reflections.rchit:105 / rchit:98
+  if ((c.uboFlags & gate) == gate)
+    irradiance = irradiance + calc_indirect(c, normal, albedo, metallic, roughness, pos, origin);   // rchit:98-107
+  hitPos = pos;
+  return irradiance + emissive;                                                                      // rchit:109
+}
+
+// SpecularGIRT: mirror_reflections.rgen:30-81 + .rchit + .rmiss for one pixel — reflect the view vector about
+// the G-buffer normal, closest hit on the path's BVH, shade the hit like the probe rchit (sun shadow ray, calcLight, indirect
+// diffuse from the atlas, emissive); rgba16f result (irradiance, hit distance), (sky, 1e6) on a miss, 0 for sky pixels.
+struct SpecularCtx {
+  TraceCtx t;                         // scene, BVH, atlas, lights, flags; camOff/step as sampleProbe places the grid
+  const float* depth; const float4* geom0; uint2* out; int width, height;
+  float invViewProj[16]; V3 cameraPos; float screenW, screenH;
+};
+HD void specular_gi_body(uint32_t i, const SpecularCtx& c) {
+  const int px = (int)(i % (uint32_t)c.width), py = (int)(i / (uint32_t)c.width);
+  const float depthSamp = c.depth[i];
+  if (depthSamp == 1.0f) { c.out[i] = make_uint2(0u, 0u); return; }                              // rgen:41-44
+  ShadowRtCtx w{};                                                                               // calcWorldPos is the same function (rgen:22-30)
+  for (int k = 0; k < 16; ++k) w.invViewProj[k] = c.invViewProj[k];
+  w.screenW = c.screenW; w.screenH = c.screenH;
+  const V3 pos = shadow_rt_world_pos(w, px, py, depthSamp);
+  const float4 g0 = c.geom0[i];
+  const V3 normal = normalize3(mk3(g0.x, g0.y, g0.z));                                           // rgen:46
+  const V3 vv = normalize3(pos - c.cameraPos);
+  const float dn = dot3(normal, vv);
+  const V3 dir = vv - (2.0f * dn) * normal;                                                      // reflect(v, normal)
+  Hit hit; uint32_t cn[2] = {0, 0}, ct[2] = {0, 0}, lit = 0, nShadow = 0;
+  V3 rad; float dist;
+  if (traverse<false, false>(c.t.nodes, c.t.bvhTris, c.t.numNodes, pos, dir, 0.1f, 50.0f, hit, cn[0], ct[0])) {
+    V3 hp;
+    rad = shade_hit_simple<false, true>(c.t, hit, pos, lit, nShadow, cn, ct, hp);
+    const V3 dd = hp - pos; dist = sqrtf(dot3(dd, dd));                                          // distance(pos, gl_WorldRayOriginEXT)
+  } else { rad = c.t.sky; dist = 1e6f; }                                                         // mirror_reflections.rmiss
+  c.out[i] = make_uint2((uint32_t)f2h(rad.x) | ((uint32_t)f2h(rad.y) << 16), (uint32_t)f2h(rad.z) | ((uint32_t)f2h(dist) << 16));
+}
+
 // rgen main + rchit main + rmiss main for one probe ray (rgen:48-111, rchit:24-111, rmiss:17-21)
 template <bool CNT>
 HD void trace_ray_body(uint32_t idx, const TraceCtx& c) {
@@ -851,61 +950,8 @@ HD void trace_ray_body(uint32_t idx, const TraceCtx& c) {
   Hit hit;
   V3 rad;
   if (traverse<false, CNT>(c.nodes, c.bvhTris, c.numNodes, origin, d, c.tmin, c.tmax, hit, cn[0], ct[0])) {
-    const uint32_t ii = c.triInstance[hit.prim];
-    const DInstance in = c.instances[ii];
-    const InstXform& xf = c.xforms[ii];
-    const uint32_t prim = hit.prim - in.firstTri;                                            // gl_PrimitiveID
-    const anerend_vertex_t* v0 = &c.vertices[in.vertexOffset + c.indices[in.indexOffset + 3 * prim + 0]];
-    const anerend_vertex_t* v1 = &c.vertices[in.vertexOffset + c.indices[in.indexOffset + 3 * prim + 1]];
-    const anerend_vertex_t* v2 = &c.vertices[in.vertexOffset + c.indices[in.indexOffset + 3 * prim + 2]];
-    const float b0 = 1.0f - hit.u - hit.v, b1 = hit.u, b2 = hit.v;
-    V3 pos = mk3(v0->pos[0], v0->pos[1], v0->pos[2]) * b0 + mk3(v1->pos[0], v1->pos[1], v1->pos[2]) * b1 + mk3(v2->pos[0], v2->pos[1], v2->pos[2]) * b2;
-    pos = xform_point(xf.o2w, pos);                                                          // rchit:42
-    V3 normal = normalize3(mk3(v0->normal[0], v0->normal[1], v0->normal[2]) * b0 + mk3(v1->normal[0], v1->normal[1], v1->normal[2]) * b1 +
-                           mk3(v2->normal[0], v2->normal[1], v2->normal[2]) * b2);
-    normal = normalize3(mk3(normal.x * xf.w2o[0] + normal.y * xf.w2o[1] + normal.z * xf.w2o[2],
-                            normal.x * xf.w2o[3] + normal.y * xf.w2o[4] + normal.z * xf.w2o[5],
-                            normal.x * xf.w2o[6] + normal.y * xf.w2o[7] + normal.z * xf.w2o[8]));   // rchit:73
-    V3 color = mk3(v0->color[0], v0->color[1], v0->color[2]) * b0 + mk3(v1->color[0], v1->color[1], v1->color[2]) * b1 +
-               mk3(v2->color[0], v2->color[1], v2->color[2]) * b2;
-    color = mk3(to_linear1(color.x), to_linear1(color.y), to_linear1(color.z));              // rchit:75
-    // getSurfaceDataFromMat (bindless.glsl:181-237); uv as rchit:70
-    const anerend_material_info_t* m = &c.materials[in.material];
-    const float tu = v0->uv[0] * b0 + v1->uv[0] * b1 + v2->uv[0] * b2, tv = v0->uv[1] * b0 + v1->uv[1] * b1 + v2->uv[1] * b2;
-    const Surface sf = surface_from_material(c.tex, m, tu, tv, color);
-    const V3 albedo = sf.albedo, emissive = sf.emissive;
-    const float metallic = sf.metallic, roughness = sf.roughness;
-    // sun shadow ray (rchit:45-66): any-hit, origin = hit position without offset
-    const V3 sunL = normalize3(-c.lightDir);
-    Hit sh;
-    bool occluded = true;
-    if (!(c.flags & ANEREND_DDGI_FLAG_SKIP_DEAD_SHADOW_RAYS) || dot3(normal, sunL) > 0.0f) {
-      ++nShadow;
-      occluded = traverse<true, CNT>(c.nodes, c.bvhTris, c.numNodes, pos, sunL, c.tmin, c.tmax, sh, cn[1], ct[1]);
-    }
-    V3 irradiance = mk3(0.0f);
-    if (!occluded) { lit |= 1u; irradiance = calc_light(normal, albedo, metallic, roughness, pos, origin, sunL, c.sunIntensity * mk3(1.0f) * 1.0f); }
-    if (c.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) {
-      // extension E1: enabled point lights, calcLight(directional = 0) gated by an any-hit ray pos -> light
-      for (uint32_t li = 0; li < c.numLights; ++li) {
-        const anerend_light_t* lt = &c.lights[li];
-        if (!(lt->color[3] > 0.5f)) continue;
-        const V3 lp = mk3(lt->world_pos[0], lt->world_pos[1], lt->world_pos[2]);
-        const V3 dv = lp - pos; const float dist = sqrtf(dot3(dv, dv)), range = lt->world_pos[3];
-        if (!(dist < range)) continue;
-        const V3 L = normalize3(lp - pos);
-        if (!(dot3(normal, L) > 0.0f)) continue;
-        ++nShadow;
-        if (traverse<true, CNT>(c.nodes, c.bvhTris, c.numNodes, pos, L, c.tmin, dist, sh, cn[1], ct[1])) continue;
-        lit |= 1u << (1u + li);
-        const float dd = fminf(dist, range);
-        const float att = (1.0f - dd / range) * (1.0f - dd / range) * 1.0f;
-        irradiance = irradiance + calc_light(normal, albedo, metallic, roughness, pos, origin, L, mk3(lt->color[0], lt->color[1], lt->color[2]) * att);
-      }
-    }
-    if ((c.uboFlags & ANEREND_UBO_DDGI_MULTI_FLAG) == ANEREND_UBO_DDGI_MULTI_FLAG)
-      irradiance = irradiance + calc_indirect(c, normal, albedo, metallic, roughness, pos, origin);   // rchit:98-107
-    rad = irradiance + emissive;                                                                      // rchit:109
+    V3 hitPos;
+    rad = shade_hit_simple<CNT, false>(c, hit, origin, lit, nShadow, cn, ct, hitPos);
   } else {
     rad = c.sky;                                                                                      // rmiss:20
   }

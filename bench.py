@@ -470,6 +470,19 @@ def main():
         h.sync()
         sms = s0.elapsed_time(s1) / 10.0
         shadow_rt = {"pixels": sw * sh, "ms": sms, "mrays_per_s": sw * sh / sms / 1e3, "lit_fraction": float(dvis.mean().item())}
+        # SpecularGIRT: same camera and depth, random G-buffer normals; one-thread-per-pixel kernel (not yet on the wavefront kernels)
+        u["flags"] |= _L.UBO_SPECULAR_GI_FLAG
+        h.set_scene_ubo(u)
+        dgeom = torch.randn((sh, sw, 4), generator=gen, device=dev)
+        dspec = torch.empty((sh, sw, 4), dtype=torch.int16, device=dev)
+        torch.cuda.synchronize()
+        for it in range(5):
+            if it == 2:
+                s0.record(sstream)
+            h.specular_gi_device(ddepth.data_ptr(), dgeom.data_ptr(), sw, sh, dspec.data_ptr())
+        s1.record(sstream)
+        h.sync()
+        shadow_rt["specular_gi_ms"] = s0.elapsed_time(s1) / 3.0
         h.set_scene_ubo(scene.ubo)
 
     line = None

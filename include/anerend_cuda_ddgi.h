@@ -209,6 +209,17 @@ int anerend_cuda_ddgi_indirect_diffuse_device(anerend_ddgi_t* h, const void* d_p
 int anerend_cuda_ddgi_shadow_rt(anerend_ddgi_t* h, const float* depth, uint32_t width, uint32_t height, float* out_r32f);
 int anerend_cuda_ddgi_shadow_rt_device(anerend_ddgi_t* h, const void* d_depth, uint32_t width, uint32_t height, void* d_out_r32f);
 
+/* The frame-graph pass "SpecularGIRT" (SpecularGIRTPass.cpp:100-127, mirror_reflections.rgen/.rchit/.rmiss): per pixel, the view
+ * vector reflected about the G-buffer normal (geom0: rgba32f, normal in rgb), closest hit on the path's BVH, the hit shaded like
+ * the probe hit shader (sun shadow ray, calcLight, calcIndirectDiffuseLight from the current atlas when UBO_DDGI_FLAG is set,
+ * emissive).  out: rgba16f (irradiance.rgb, hit distance); (sky, 1e6) on a miss; 0 for sky pixels (depth == 1).  Nothing is
+ * written unless UBO_RT_ON_FLAG and UBO_SPECULAR_GI_FLAG are set.  Reads invViewProj, cameraPos, screenWidth/Height, lightDir,
+ * sun/sky and flags from the last _set_scene_ubo. */
+int anerend_cuda_ddgi_specular_gi(anerend_ddgi_t* h, const float* depth, const float* geom0_rgba32f, uint32_t width, uint32_t height,
+                                  void* out_rgba16f);
+int anerend_cuda_ddgi_specular_gi_device(anerend_ddgi_t* h, const void* d_depth, const void* d_geom0_rgba32f, uint32_t width,
+                                         uint32_t height, void* d_out_rgba16f);
+
 /* Row stripe (sharding inside the layers): the handle updates only the probe rows z = offset + k*stride of
  * every layer it launches; (0, 1) = all rows (default).  With R ranks, rank r takes (r, R): every rank carries the same
  * share of every layer, so the ranks finish together whatever the scene looks like.  _download_atlas_stripe returns

@@ -649,7 +649,9 @@ struct ddgi_oracle {
   }
 
   // ---- rchit main (irradiance_probe_update.rchit:24-111) -----------------------------------------------
-  V3 shadeHit(const Hit& hit, V3 rayOrigin, uint32_t& litMask, uint64_t* cnt) const {
+  // specular = mirror_reflections.rchit:24-118: the same shader except for the normal transform (:74) and the flag gating the
+  // indirect term (:105)
+  V3 shadeHit(const Hit& hit, V3 rayOrigin, uint32_t& litMask, uint64_t* cnt, bool specular = false, V3* hitPos = nullptr) const {
     const Instance& in = instances[triInstance[hit.prim]];
     const anerend_mesh_info_t& mi = meshes[in.mesh];
     uint32_t prim = hit.prim - in.firstTri;                         // gl_PrimitiveID
@@ -665,9 +667,15 @@ struct ddgi_oracle {
     float uvx = vv[0]->uv[0] * b0 + vv[1]->uv[0] * b1 + vv[2]->uv[0] * b2, uvy = vv[0]->uv[1] * b0 + vv[1]->uv[1] * b1 + vv[2]->uv[1] * b2;   // rchit:70
     V3 normal = normalize(P(vv[0]->normal) * b0 + P(vv[1]->normal) * b1 + P(vv[2]->normal) * b2);
     // normal * gl_WorldToObjectEXT : row-vector times matrix = dot with each column of W2O's 3x3
-    normal = normalize(v3(normal.x * in.w2o[0] + normal.y * in.w2o[1] + normal.z * in.w2o[2],
-                          normal.x * in.w2o[3] + normal.y * in.w2o[4] + normal.z * in.w2o[5],
-                          normal.x * in.w2o[6] + normal.y * in.w2o[7] + normal.z * in.w2o[8]));
+    if (!specular)
+      normal = normalize(v3(normal.x * in.w2o[0] + normal.y * in.w2o[1] + normal.z * in.w2o[2],
+                            normal.x * in.w2o[3] + normal.y * in.w2o[4] + normal.z * in.w2o[5],
+                            normal.x * in.w2o[6] + normal.y * in.w2o[7] + normal.z * in.w2o[8]));
+    else      // mat3(gl_ObjectToWorldEXT) * normal: c0*n.x + c1*n.y + c2*n.z (o2w is the column-major mat4: column c at o2w[4c])
+      normal = normalize(v3(in.o2w[0] * normal.x + in.o2w[4] * normal.y + in.o2w[8] * normal.z,
+                            in.o2w[1] * normal.x + in.o2w[5] * normal.y + in.o2w[9] * normal.z,
+                            in.o2w[2] * normal.x + in.o2w[6] * normal.y + in.o2w[10] * normal.z));
+    if (hitPos) *hitPos = pos;
     // The reference traces the sun shadow ray before it knows the normal (rchit:45-66 precede :72-73); its result only
     // gates calcLight, which multiplies by max(N.L, 0) (pbr_light.glsl:161).  FLAG_SKIP_DEAD_SHADOW_RAYS drops the rays
     // whose result cannot matter; the radiance is the same (tests/test_oracle_kat.py proves it on the oracle itself).
@@ -717,7 +725,8 @@ struct ddgi_oracle {
         irradiance = irradiance + calcLight(normal, sColor, metallic, roughness, pos, rayOrigin, &lt, 0, lightDir, ubo.sun_intensity);
       }
     }
-    if ((ubo.flags & ANEREND_UBO_DDGI_MULTI_FLAG) == ANEREND_UBO_DDGI_MULTI_FLAG)
+    const uint32_t gate = specular ? ANEREND_UBO_DDGI_FLAG : ANEREND_UBO_DDGI_MULTI_FLAG;
+    if ((ubo.flags & gate) == gate)
       irradiance = irradiance + calcIndirectDiffuseLight(normal, sColor, metallic, roughness, pos, rayOrigin);
     irradiance = irradiance + emissive;
     return irradiance;
@@ -1025,6 +1034,43 @@ int ddgi_oracle_calc_indirect(ddgi_oracle_t* h, const float n[3], const float a[
                               const float wp[3], const float vp[3], float out[3]) {
   V3 r = h->calcIndirectDiffuseLight(v3(n[0], n[1], n[2]), v3(a[0], a[1], a[2]), metallic, roughness, v3(wp[0], wp[1], wp[2]), v3(vp[0], vp[1], vp[2]));
   out[0] = r.x; out[1] = r.y; out[2] = r.z; return 0;
+}
+// mirror_reflections.rgen:30-81 + .rchit + .rmiss (frame-graph pass "SpecularGIRT", SpecularGIRTPass.cpp:100-127): per pixel, reflect
+// the view vector about the G-buffer normal, closest hit, shade like the probe rchit; out = rgba16f (irradiance, hit distance).
+int ddgi_oracle_specular_gi(ddgi_oracle_t* h, const float* depth, const float* geom0, uint32_t width, uint32_t height, uint16_t* out) {
+  if (!h->haveAccel) { h->err = "specular_gi before build_accel"; return ANEREND_DDGI_E_STATE; }
+  if (!h->haveUbo) { h->err = "specular_gi before set_scene_ubo"; return ANEREND_DDGI_E_STATE; }
+  if (!(h->ubo.flags & ANEREND_UBO_RT_ON_FLAG) || !(h->ubo.flags & ANEREND_UBO_SPECULAR_GI_FLAG)) return 0;   // SpecularGIRTPass.cpp:102-103
+  const float* m = h->ubo.inv_view_proj;
+  const float sw = (float)h->ubo.screen_width, sh = (float)h->ubo.screen_height;
+  const V3 cam = v3(h->ubo.camera_pos[0], h->ubo.camera_pos[1], h->ubo.camera_pos[2]);
+  const V3 sky = toLinear(v3(h->ubo.sky_intensity * h->ubo.sky_color[0], h->ubo.sky_intensity * h->ubo.sky_color[1], h->ubo.sky_intensity * h->ubo.sky_color[2]));
+  h->parallelFor((int)height, [&](int py) {
+    uint64_t cnt[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t px = 0; px < width; ++px) {
+      const size_t i = (size_t)py * width + px;
+      uint16_t* o = out + 4 * i;
+      const float depthSamp = depth[i];
+      if (depthSamp == 1.0f) { o[0] = o[1] = o[2] = o[3] = 0; continue; }                        // rgen:41-44
+      const float u = (2.0f * (float)px + 1.0f) / (2.0f * sw), v = (2.0f * (float)py + 1.0f) / (2.0f * sh);
+      const float cx = u * 2.0f - 1.0f, cy = v * 2.0f - 1.0f, cz = depthSamp;
+      const float X = m[0] * cx + m[4] * cy + m[8] * cz + m[12] * 1.0f, Y = m[1] * cx + m[5] * cy + m[9] * cz + m[13] * 1.0f;
+      const float Z = m[2] * cx + m[6] * cy + m[10] * cz + m[14] * 1.0f, W = m[3] * cx + m[7] * cy + m[11] * cz + m[15] * 1.0f;
+      const V3 pos = v3(X / W, Y / W, Z / W);
+      const V3 normal = normalize(v3(geom0[4 * i], geom0[4 * i + 1], geom0[4 * i + 2]));          // rgen:46
+      const V3 vv = normalize(pos - cam);
+      const float dn = dot(normal, vv);
+      const V3 dir = vv - (2.0f * dn) * normal;                                                 // reflect(v, normal) = I - 2 dot(N, I) N
+      Hit hit; uint32_t lit = 0; V3 rad; float dist;
+      if (h->closestHit(pos, dir, 0.1f, 50.0f, hit, cnt[3], cnt[4])) {
+        V3 hp;
+        rad = h->shadeHit(hit, pos, lit, cnt, true, &hp);
+        const V3 dd = hp - pos; dist = std::sqrt(dot(dd, dd));                                   // distance(pos, gl_WorldRayOriginEXT)
+      } else { rad = sky; dist = 1e6f; }                                                         // mirror_reflections.rmiss
+      o[0] = f2h(rad.x); o[1] = f2h(rad.y); o[2] = f2h(rad.z); o[3] = f2h(dist);
+    }
+  });
+  return 0;
 }
 // shadow.rgen:30-82 + shadow.rmiss (frame-graph pass "ShadowRT", ShadowRayTracingPass.cpp:73-81) for a width x height depth buffer
 int ddgi_oracle_shadow_rt(ddgi_oracle_t* h, const float* depth, uint32_t width, uint32_t height, float* out) {

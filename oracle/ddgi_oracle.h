@@ -83,6 +83,7 @@ void ddgi_oracle_calc_light(const float normal[3], const float albedo[3], float 
                             const float world_pos[3], const float view_pos[3], const anerend_light_t* light,
                             int32_t directional, const float light_dir[3], float sun_intensity, float out[3]);
 /* calcIndirectDiffuseLight against the handle's current atlas/UBO (pbr_light.glsl:365-388). */
+int  ddgi_oracle_specular_gi(ddgi_oracle_t* h, const float* depth, const float* geom0_rgba32f, uint32_t width, uint32_t height, uint16_t* out_rgba16f);
 int  ddgi_oracle_shadow_rt(ddgi_oracle_t* h, const float* depth, uint32_t width, uint32_t height, float* out_r32f);
 int  ddgi_oracle_indirect_diffuse(ddgi_oracle_t* h, const float* points, uint32_t count, const float view_pos[3], int32_t clamp_to_edge, float* out_rgba);
 int  ddgi_oracle_calc_indirect(ddgi_oracle_t* h, const float normal[3], const float albedo[3], float metallic,

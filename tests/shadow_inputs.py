@@ -37,3 +37,22 @@ def depth_buffer(width, height, seed, sky_fraction=0.1):
     d = rng.uniform(0.02, 0.98, (height, width)).astype(np.float32)
     d[rng.rand(height, width) < sky_fraction] = 1.0
     return d
+
+
+def gbuffer_normals(width, height, seed):
+    """geom0 (rgba32f): un-normalised normals in rgb (the shader normalises), albedo.r in a."""
+    rng = np.random.RandomState(seed)
+    g = np.zeros((height, width, 4), np.float32)
+    n = rng.normal(size=(height, width, 3))
+    g[..., :3] = n * rng.uniform(0.5, 2.0, (height, width, 1))
+    g[..., 3] = rng.uniform(0, 1, (height, width))
+    return g
+
+
+def with_specular_camera(ubo, inv_view_proj, width, height, enabled=True):
+    u = with_shadow_camera(ubo, inv_view_proj, width, height, rt_shadows=False)
+    if enabled:
+        u["flags"] |= L.UBO_SPECULAR_GI_FLAG
+    else:
+        u["flags"] &= ~np.uint32(L.UBO_SPECULAR_GI_FLAG)
+    return u

@@ -486,3 +486,34 @@ def test_bake_mode_matches_oracle_bit_for_bit(kernels, oracle, make_gpu):
         assert np.array_equal(o.download_atlas(), g.download_atlas()), "atlas is not bit-identical"
     o.close()
     g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cornell_small", "textured"])
+def test_specular_gi_matches_oracle_bit_for_bit(name, oracle, make_gpu):
+    """SURVEY §8f N2 through the C ABI: the "SpecularGIRT" pass on the path's BVH and atlas (host- and device-pointer entry points)."""
+    import torch
+    from tests import shadow_inputs as SI
+    scene, (nxz, ny, nr) = SCENES[name]()
+    p = make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS)
+    o, g = oracle.Oracle(p), make_gpu(p)
+    rots = parity.setup_pair(scene, (o, g), seed=5)
+    for h in (o, g):
+        h.update(-1, rots)
+    assert np.array_equal(o.download_atlas(), g.download_atlas())
+    W, H = 160, 90
+    depth, geom0 = SI.depth_buffer(W, H, seed=3), SI.gbuffer_normals(W, H, seed=4)
+    for ivp in (SI.ortho_inv_view_proj(5.0, 5.0, 8.0), SI.perspective_inv_view_proj(2)):
+        ubo = SI.with_specular_camera(scene.ubo, ivp, W, H)
+        for h in (o, g):
+            h.set_scene_ubo(ubo)
+        ro, rg = o.specular_gi(depth, geom0), g.specular_gi(depth, geom0)
+        assert np.array_equal(ro, rg), f"{(ro != rg).any(axis=-1).sum()} pixels differ"
+    dd, dg = torch.from_numpy(depth).cuda(), torch.from_numpy(geom0).cuda()
+    dout = torch.zeros((H, W, 4), dtype=torch.int16, device="cuda")
+    torch.cuda.synchronize()
+    g.specular_gi_device(dd.data_ptr(), dg.data_ptr(), W, H, dout.data_ptr())
+    g.sync()
+    assert np.array_equal(dout.cpu().numpy().view(np.uint16), ro)
+    o.close()
+    g.close()

@@ -272,3 +272,34 @@ def test_bake_mode_matches_oracle(oracle, make_emu):
     assert a[..., 3].max() > 40.0                                    # alpha carries the accumulated weight (3 x ~16 at 64 rays)
     o.close()
     e.close()
+
+
+@pytest.mark.parametrize("name", ["cornell", "textured"])
+def test_specular_gi_matches_oracle(name, oracle, make_emu):
+    """the "SpecularGIRT" pass (mirror_reflections.rgen/.rchit/.rmiss) on the path's BVH and atlas; the rgba16f
+    image is bit-identical."""
+    from tests import shadow_inputs as SI
+    scene, (nxz, ny, nr) = SCENES[name]()
+    p = make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS)
+    o, e = oracle.Oracle(p), make_emu(p)
+    rots = parity.setup_pair(scene, (o, e), seed=5)
+    for h in (o, e):
+        h.update(-1, rots)                       # a non-trivial atlas for the indirect term
+    W, H = 40, 24
+    depth, geom0 = SI.depth_buffer(W, H, seed=3), SI.gbuffer_normals(W, H, seed=4)
+    for ivp in (SI.ortho_inv_view_proj(5.0, 5.0, 8.0), SI.perspective_inv_view_proj(2)):
+        ubo = SI.with_specular_camera(scene.ubo, ivp, W, H)
+        for h in (o, e):
+            h.set_scene_ubo(ubo)
+        ro, re = o.specular_gi(depth, geom0), e.specular_gi(depth, geom0)
+        assert np.array_equal(ro, re)
+        assert (ro[depth == 1.0] == 0).all()
+    f = ro.view(np.float16).astype(np.float32)
+    hit = np.isfinite(f[..., 3]) & (f[..., 3] > 0)
+    assert hit.any() and (~hit & (depth != 1.0)).any()                 # hits (finite distance) and misses (1e6 -> inf in fp16)
+    off = SI.with_specular_camera(scene.ubo, ivp, W, H, enabled=False)
+    for h in (o, e):
+        h.set_scene_ubo(off)
+        assert (h.specular_gi(depth, geom0) == 0xFFFF).all()          # SpecularGIRTPass.cpp:102-103: nothing written
+    o.close()
+    e.close()

@@ -511,3 +511,36 @@ def test_bake_mode_running_mean_and_tile_grid(oracle):
         hits[tile] = sum(int((oo.download_ray_records(l)["prim"] != 0xFFFFFFFF).sum()) for l in range(2))
         oo.close()
     assert hits[(1, 0)] > 10 and hits[(5, 5)] == 0        # ~1.6 % of 2048 rays point at the quad from 8-9 m below
+
+
+def test_specular_gi_known_answer(oracle):
+    """KAT for SpecularGIRT: a mirror-like floor point at the origin seen from a camera at (0, 3, -3) reflects towards (0, 3, 3)
+    (angle of incidence = angle of reflection).  An emissive quad placed there, facing the floor, with the sun and DDGI off,
+    gives irradiance = emissive and distance = |(0,3,3)| = 4.2426; a pixel whose reflection leaves the scene gives (sky, inf)."""
+    from tests import shadow_inputs as SI
+    b = scenes.SceneBuilder("kat_spec", 1)
+    c = np.array([0.0, 3.0, 3.0]); n = -c / np.linalg.norm(c)
+    t1 = np.cross(n, [1.0, 0.0, 0.0]); t1 /= np.linalg.norm(t1); t2 = np.cross(n, t1)
+    pos = np.array([c - t1 - t2, c + t1 - t2, c + t1 + t2, c - t1 + t2], np.float32)
+    mesh = b.add_mesh(pos, np.tile(n.astype(np.float32), (4, 1)), np.array([0, 1, 2, 0, 2, 3], np.uint32))
+    b.add_renderable(np.eye(4), mesh, b.add_material((0.5, 0.5, 0.5), emissive=(0.5, 1.0, 2.0, 1.5)))
+    s = b.finish((0.0, 3.0, -3.0), (4, 2, 64))
+    o = oracle.Oracle(make_params(4, 2, 64))
+    o.upload_scene(s); o.build_accel()
+    W = H = 2
+    ivp = np.zeros((4, 4)); ivp[0, 0], ivp[2, 1], ivp[1, 2], ivp[3, 3] = 1e-3, 1e-3, 1.0, 1.0      # every pixel ~ world (0, depth, 0)
+    u = SI.with_specular_camera(s.ubo, ivp.T.astype(np.float32).ravel(), W, H)
+    u["flags"] &= ~np.uint32(L.UBO_DDGI_FLAG | L.UBO_DDGI_MULTI_FLAG)
+    u["sun_intensity"] = 0.0
+    o.set_scene_ubo(u)
+    depth = np.zeros((H, W), np.float32)                     # world y = 0: the floor point
+    geom0 = np.zeros((H, W, 4), np.float32); geom0[..., 1] = 2.0          # normal (0, 1, 0), un-normalised
+    geom0[1, 1, :3] = (0.0, 0.0, -1.0)                       # this pixel's reflection goes up and back: leaves the scene
+    depth[0, 1] = 1.0                                        # sky pixel
+    got = o.specular_gi(depth, geom0).view(np.float16).astype(np.float32)
+    want_e = np.array([0.5, 1.0, 2.0]) * 1.5
+    for (y, x) in ((0, 0), (1, 0)):
+        assert np.allclose(got[y, x, :3], want_e, rtol=2e-3) and abs(got[y, x, 3] - np.sqrt(18.0)) < 0.01
+    assert (got[0, 1] == 0).all()
+    assert np.isinf(got[1, 1, 3]) and np.allclose(got[1, 1, :3], (0.033105, 0.214041, 0.447988), rtol=2e-3)
+    o.close()
