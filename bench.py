@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=[None, "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fast-math", action="store_true", help="time the FAST_MATH build as the headline (default: exact build)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the atlas-consumer / ShadowRT / SpecularGIRT figures and the C5 1-GPU base")
     ap.add_argument("--no-alt", action="store_true", help="skip the second-build and 1-GPU strong-scaling-base measurements")
     ap.add_argument("--deal", default="stripes", choices=["stripes", "measured", "static"],
                     help="N>1, fused exchange: every rank takes the probe rows z = rank mod N of every layer (default; needs nXZ "
@@ -417,7 +418,7 @@ def main():
 
     # ---- atlas consumer: calcIndirectDiffuseLight for a 1920x1080 synthetic G-buffer against the atlas
     consumer = None
-    if world == 1:
+    if world == 1 and not args.no_extras:
         npts = 1920 * 1080
         gen = torch.Generator(device=dev); gen.manual_seed(11)
         pts = torch.zeros((npts, 12), dtype=torch.float32, device=dev)
@@ -446,7 +447,7 @@ def main():
 
     # ---- ShadowRT on the same BVH: one any-hit ray per pixel of a 1920x1080 depth buffer (top-down view)
     shadow_rt = None
-    if world == 1:
+    if world == 1 and not args.no_extras:
         from anerend_b200 import layouts as _L
         sw, sh = 1920, 1080
         u = scene.ubo.copy()
@@ -484,6 +485,20 @@ def main():
         h.sync()
         shadow_rt["specular_gi_ms"] = s0.elapsed_time(s1) / 3.0
         h.set_scene_ubo(scene.ubo)
+
+    # ---- base of the multi-GPU series: the N>1 runs of this script time C5 (the configuration BASELINE.json shards over 2/4/8
+    # GPUs), so the default N=1 run also reports C5 on one GPU — the denominator of that series — next to its own C3 headline
+    series_base = None
+    if world == 1 and args.workload is None and not args.no_extras:
+        import subprocess
+        try:
+            outp = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", "c5", "--steps", "5", "--warmup", "3", "--no-alt",
+                                   "--no-cpu-baseline", "--no-extras"], capture_output=True, text=True, timeout=600)
+            d5 = json.loads([ln for ln in outp.stdout.splitlines() if ln.startswith("{")][-1])
+            series_base = {"workload": "c5", "n_gpus": 1, "value": d5["value"], "unit": UNIT, "ms_per_step": d5["ms_per_step"], "steps": d5["steps"],
+                           "probes": d5["config"]["probes"], "triangles": d5["config"]["triangles"]}
+        except Exception as e:      # the headline line must not depend on this extra
+            series_base = {"workload": "c5", "error": f"{type(e).__name__}: {e}"[:200]}
 
     line = None
     if rank == 0:
@@ -559,7 +574,7 @@ def main():
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "update_ms": {"trace": rt_avg, "convolve": float(np.mean(conv_ms)), "full_grid": ms_per_step},
                 "arithmetic": "fast_math (1e-4 relative per update)" if args.fast_math else "exact (atlas bit-identical to the oracle)",
-                "other_build": alt, "strong_scaling_base": base1, "exchange_check_vs_1gpu": verified, "layer_deal": balanced, "per_rank_ms": per_rank, "atlas_consumer": consumer, "shadow_rt": shadow_rt}
+                "other_build": alt, "strong_scaling_base": base1, "exchange_check_vs_1gpu": verified, "layer_deal": balanced, "per_rank_ms": per_rank, "atlas_consumer": consumer, "shadow_rt": shadow_rt, "multi_gpu_series_base": series_base}
     close_handle(h, fused)
     if world > 1:
         dist.barrier()
