@@ -372,7 +372,8 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     e2e_value = all_rays * e2e_steps / e2e_s / 1e6
-    h2d_bytes = ny * nr * 16 + 568 + 64 * ny           # direction table rows of all layers + scene UBO + rotations
+    h2d_bytes = 568 + 64 * ny                          # scene UBO + one rotation matrix per layer (they travel as kernel arguments; the
+                                                       # direction table is made on the device from them)
     d2h_bytes = nbytes if world == 1 else int(own_np.nbytes)
 
     # ---- second figure: the other arithmetic build (FAST_MATH <-> exact), same workload, fewer steps ----------
