@@ -98,6 +98,7 @@ struct anerend_ddgi {
   std::vector<DTexture> textures; bool texturedScene = false, emissiveTextures = false;
   float4* dShadeUV = nullptr; float4* dEmisTex = nullptr;
   // ShadowRT scratch (pixels): staged positions, visibility words, ray queue, counters
+  float4* dExtRays = nullptr; float* dExtDist = nullptr; uint32_t extPixels = 0;      // SpecularGIRT: staged rays, hit distances
   float4* dSrtPos = nullptr; uint32_t* dSrtLit = nullptr; uint32_t* dSrtQueue = nullptr; uint32_t* dSrtQcount = nullptr; uint32_t srtPixels = 0; int srtGrid = 0;
   size_t fastRays = 0; uint32_t fastQueues = 0; int gridPrimary[2] = {0, 0}, gridShadow[2] = {0, 0}; uint32_t tune[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int sms = 0;
 
@@ -356,11 +357,9 @@ __global__ void __launch_bounds__(256) k_zero_words(uint32_t* p, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 0u;
 }
-// Wavefront path: k_trace_primary -> k_shade_prep -> k_trace_shadow -> k_shade (ddgi_fast.cuh)
-int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
+// scratch of the wavefront kernels (hit records, surface records, visibility words, per-light queues, hit list); grows on demand
+int ensureFastScratch(anerend_ddgi* h, size_t need, uint32_t nq) {
   Backend& be = h->be;
-  const uint32_t nq = 1u + ((h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) ? h->numLights : 0u);
-  const size_t need = n;                      // grows on demand: a full-grid call after per-layer calls reallocates once
   if (h->fastRays < need || h->fastQueues < nq) {
     BE_CHECK(h, be.sync());
     be.free(h->dHits); be.free(h->dSurf); be.free(h->dLit); be.free(h->dQueues); be.free(h->dQcount); be.free(h->dHitq);
@@ -371,6 +370,10 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
     be.free(h->dEmisTex); h->dEmisTex = nullptr;
   }
   if (h->emissiveTextures && !h->dEmisTex) BE_CHECK(h, be.alloc(&h->dEmisTex, h->fastRays));     // per-ray emissive of textured materials
+  return 0;
+}
+int ensureFastGrids(anerend_ddgi* h) {
+  Backend& be = h->be;
   if (h->gridPrimary[0] == 0) {
     int dev = 0, sms = 0, nb = 0;
     BE_CHECK(h, be.ok(cudaGetDevice(&dev))); BE_CHECK(h, be.ok(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)));
@@ -387,6 +390,14 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
       for (int k = 0; k < 8; ++k) h->tune[k] = v[k];
     }
   }
+  return 0;
+}
+// Wavefront path: k_trace_primary -> k_shade_prep -> k_trace_shadow -> k_shade (ddgi_fast.cuh)
+int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
+  Backend& be = h->be;
+  const uint32_t nq = 1u + ((h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) ? h->numLights : 0u);
+  { int rcs = ensureFastScratch(h, n, nq); if (rcs) return rcs; }
+  { int rcg = ensureFastGrids(h); if (rcg) return rcg; }
   FastCtx f{};
   f.t = c; f.shadeTris = h->dShadeTris; f.shadeUV = h->dShadeUV; f.emisTex = h->dEmisTex; f.hits = h->dHits; f.surf = h->dSurf; f.lit = h->dLit; f.queues = h->dQueues; f.hitq = h->dHitq;
   f.qcount = h->dQcount; f.totalRays = n; f.numQueues = nq;
@@ -658,6 +669,7 @@ void destroyHandle(anerend_ddgi* h) {
   be.free(h->dAtlas); be.free(h->dTemp); be.free(h->dRayIrr); be.free(h->dDirs); be.free(h->dFib); be.freeHostPinned(h->hDirs); be.free(h->dRayOrder);
   be.free(h->dLayerMap); be.freeHostPinned(h->hLayerMap);
   be.free(h->dTextures); be.free(h->dTexPool); be.free(h->dSrgbLut); be.free(h->dEmisTex);
+  be.free(h->dExtRays); be.free(h->dExtDist);
   be.free(h->dSrtPos); be.free(h->dSrtLit); be.free(h->dSrtQueue); be.free(h->dSrtQcount);
   be.free(h->dRecords); be.free(h->dTexelRecords); be.free(h->dStats); be.free(h->dSceneBounds); be.free(h->dCounters);
   be.free(h->dHits); be.free(h->dSurf); be.free(h->dLit); be.free(h->dQueues); be.free(h->dQcount); be.free(h->dHitq); be.free(h->dConvW);
@@ -1009,6 +1021,38 @@ int specularGi(anerend_ddgi* h, const float* dDepth, const float4* dGeom0, uint3
   for (int k = 0; k < 16; ++k) c.invViewProj[k] = h->ubo.inv_view_proj[k];
   c.cameraPos = mk3(h->ubo.camera_pos[0], h->ubo.camera_pos[1], h->ubo.camera_pos[2]);
   c.screenW = (float)h->ubo.screen_width; c.screenH = (float)h->ubo.screen_height;
+#ifndef DDGI_HOST_EMU
+  if (!(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS) && h->numNodes > 0) {
+    // the wavefront kernels in external-ray mode: one reflected ray per pixel instead of the probe rays
+    Backend& be = h->be;
+    const uint32_t nq = 1u + ((h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) ? h->numLights : 0u);
+    { int rcs = ensureFastScratch(h, n, nq); if (rcs) return rcs; }
+    { int rcg = ensureFastGrids(h); if (rcg) return rcg; }
+    if (h->extPixels < n) {
+      BE_CHECK(h, be.sync());
+      be.free(h->dExtRays); be.free(h->dExtDist); h->dExtRays = nullptr; h->dExtDist = nullptr; h->extPixels = 0;
+      BE_CHECK(h, be.alloc(&h->dExtRays, 2 * (size_t)n)); BE_CHECK(h, be.alloc(&h->dExtDist, n));
+      h->extPixels = n;
+    }
+    FastCtx f{};
+    f.t = c.t; f.t.rayIrr = dOut; f.t.layerMap = nullptr; f.t.rayOrder = nullptr;
+    f.shadeTris = h->dShadeTris; f.shadeUV = h->dShadeUV; f.emisTex = h->dEmisTex; f.hits = h->dHits; f.surf = h->dSurf; f.lit = h->dLit;
+    f.queues = h->dQueues; f.hitq = h->dHitq; f.qcount = h->dQcount; f.totalRays = n; f.numQueues = nq;
+    f.surfStride = 3u; f.rawSunDir = 0u; f.extRays = h->dExtRays; f.extDist = h->dExtDist;
+    for (int k = 0; k < 8; ++k) f.tune[k] = h->tune[k];
+    f.tune[3] = 0x64646464u;
+    k_zero_words<<<(FAST_QC_SIZE + 255u) / 256u, 256, 0, be.stream>>>(h->dQcount, (uint32_t)FAST_QC_SIZE);
+    k_specular_stage<<<(n + 255u) / 256u, 256, 0, be.stream>>>(c, h->dExtRays);
+    k_trace<false, false, true><<<h->gridPrimary[0], 128, 0, be.stream>>>(f);
+    k_shade_prep<256, true><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
+    k_trace<true, false><<<h->gridShadow[0], 128, 0, be.stream>>>(f);
+    BE_CHECK(h, be.ok((h->p.flags & ANEREND_DDGI_FLAG_FAST_MATH) ? launch_shade_ext_fast(f, be.stream) : launch_shade_ext_exact(f, be.stream)));
+    k_specular_resolve<<<(n + 255u) / 256u, 256, 0, be.stream>>>(dDepth, dOut, n);
+    be.launches += 7;
+    BE_CHECK(h, be.check());
+    return 0;
+  }
+#endif
   DDGI_LAUNCH(h->be, k_specular_gi, specular_gi_body, n, c, 128);
   BE_CHECK(h, h->be.check());
   return 0;

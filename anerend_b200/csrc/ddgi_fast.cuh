@@ -138,7 +138,7 @@ __device__ __forceinline__ uint4 node_step(const uint4* __restrict__ nodes, RayS
 // shared memory (two groups per lane) and tested one per lane per iteration in a separate, short section, so lanes
 // that found none keep stepping through nodes instead of idling in a per-lane triangle loop.
 // ------------------------------------------------------------------------------------------------------------
-template <bool ANY, bool CNT>
+template <bool ANY, bool CNT, bool EXT = false>
 __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
   const TraceCtx& t = c.t;
   __shared__ float4 sRay[4][32][3];
@@ -183,7 +183,10 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
         if (lane < n) {                                             // ray set-up, one ray per lane
           const uint32_t w = chunkNext + lane;
           float4* dst = &sRay[warp][lane][0];
-          if (!ANY) {
+          if (!ANY && EXT) {                                        // one ray per pixel, staged by the caller (SpecularGIRT)
+            const float4 ea = __ldg(&c.extRays[2 * (size_t)w]), eb = __ldg(&c.extRays[2 * (size_t)w + 1]);
+            ray_stage(dst, mk3(ea.x, ea.y, ea.z), mk3(eb.x, eb.y, eb.z), ea.w, w, 0u);
+          } else if (!ANY) {
             const uint32_t slot = w % (uint32_t)t.N, probeLin = w / (uint32_t)t.N;
             const int layerLocal = (int)(probeLin / (uint32_t)t.Pl), probe = stripe_probe((int)(probeLin % (uint32_t)t.Pl), t.nXZ, t.rowOffset, t.rowStride);
             const uint32_t ray = t.rayOrder ? (uint32_t)t.rayOrder[slot] : slot;
@@ -314,7 +317,7 @@ __device__ __noinline__ float4 prep_textured_surface(const TexCtx tex, const flo
   *roughnessOut = sf.roughness;
   return make_float4(sf.albedo.x, sf.albedo.y, sf.albedo.z, sf.metallic);
 }
-template <int PREP_BLOCK>
+template <int PREP_BLOCK, bool EXT = false>
 __global__ void __launch_bounds__(PREP_BLOCK, 2048 / PREP_BLOCK) k_shade_prep(const FastCtx c) {
   constexpr int PREP_WARPS = PREP_BLOCK / 32;
   const TraceCtx& t = c.t;
@@ -337,9 +340,18 @@ __global__ void __launch_bounds__(PREP_BLOCK, 2048 / PREP_BLOCK) k_shade_prep(co
       pos = mk3(s0.x, s0.y, s0.z) * b0 + mk3(s0.w, s1.x, s1.y) * b1 + mk3(s1.z, s1.w, s2.x) * b2;
       pos = xform_point(xf.o2w, pos);
       normal = normalize3(mk3(s2.y, s2.z, s2.w) * b0 + mk3(s3.x, s3.y, s3.z) * b1 + mk3(s3.w, s4.x, s4.y) * b2);
-      normal = normalize3(mk3(normal.x * xf.w2o[0] + normal.y * xf.w2o[1] + normal.z * xf.w2o[2],
-                              normal.x * xf.w2o[3] + normal.y * xf.w2o[4] + normal.z * xf.w2o[5],
-                              normal.x * xf.w2o[6] + normal.y * xf.w2o[7] + normal.z * xf.w2o[8]));
+      if (!EXT)
+        normal = normalize3(mk3(normal.x * xf.w2o[0] + normal.y * xf.w2o[1] + normal.z * xf.w2o[2],
+                                normal.x * xf.w2o[3] + normal.y * xf.w2o[4] + normal.z * xf.w2o[5],
+                                normal.x * xf.w2o[6] + normal.y * xf.w2o[7] + normal.z * xf.w2o[8]));
+      else {                                                          // mirror_reflections.rchit:74 + :86
+        normal = normalize3(mk3(xf.o2w[0] * normal.x + xf.o2w[3] * normal.y + xf.o2w[6] * normal.z,
+                                xf.o2w[1] * normal.x + xf.o2w[4] * normal.y + xf.o2w[7] * normal.z,
+                                xf.o2w[2] * normal.x + xf.o2w[5] * normal.y + xf.o2w[8] * normal.z));
+        const float4 ea = __ldg(&c.extRays[2 * (size_t)idx]);
+        const V3 dd = pos - mk3(ea.x, ea.y, ea.z);
+        c.extDist[idx] = sqrtf(dot3(dd, dd));
+      }
       const anerend_material_info_t* m = &t.materials[material];
       V3 albedo;
       float metallic = m->met_rough[0], roughness = m->met_rough[1];
@@ -367,6 +379,9 @@ __global__ void __launch_bounds__(PREP_BLOCK, 2048 / PREP_BLOCK) k_shade_prep(co
       if (textureRough) roughness = c.surf[3 * (size_t)idx + 2].w;       // written by prep_textured_surface
       c.surf[3 * (size_t)idx + 2] = make_float4(albedo.z, __uint_as_float(material), metallic, roughness);
       c.lit[idx] = 0u;
+    } else if (EXT) {
+      // mirror_reflections.rmiss: (sky, 1e6); pixels without a ray are overwritten by the resolve kernel
+      t.rayIrr[idx] = make_uint2((uint32_t)f2h(t.sky.x) | ((uint32_t)f2h(t.sky.y) << 16), (uint32_t)f2h(t.sky.z) | ((uint32_t)f2h(1e6f) << 16));
     } else {
       // rmiss:20 + rgen:109
       const uint32_t slot = idx % (uint32_t)t.N, probeLin = idx / (uint32_t)t.N;
@@ -457,6 +472,30 @@ __global__ void __launch_bounds__(256) k_shadowrt_stage(const ShadowRtCtx c, flo
 __global__ void __launch_bounds__(256) k_shadowrt_resolve(const float* depth, const uint32_t* lit, float* out, uint32_t n) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (depth[i] == 1.0f || (lit[i] & 1u)) ? 1.0f : 0.0f;
+}
+
+// SpecularGIRT on the wavefront kernels: k_specular_stage (one reflected ray per pixel) -> k_trace<false, false, true> ->
+// k_shade_prep<., true> -> k_trace<true> -> k_shade<., true> -> k_specular_resolve (pixels of the sky)
+__global__ void __launch_bounds__(256) k_specular_stage(const SpecularCtx c, float4* extRays) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, n = (uint32_t)c.width * (uint32_t)c.height;
+  if (i >= n) return;
+  const float depthSamp = c.depth[i];
+  if (depthSamp == 1.0f) { extRays[2 * (size_t)i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); extRays[2 * (size_t)i + 1] = make_float4(0.0f, 0.0f, 1.0f, 0.0f); return; }
+  ShadowRtCtx w{};
+  for (int k = 0; k < 16; ++k) w.invViewProj[k] = c.invViewProj[k];
+  w.screenW = c.screenW; w.screenH = c.screenH;
+  const V3 pos = shadow_rt_world_pos(w, (int)(i % (uint32_t)c.width), (int)(i / (uint32_t)c.width), depthSamp);
+  const float4 g0 = c.geom0[i];
+  const V3 normal = normalize3(mk3(g0.x, g0.y, g0.z));
+  const V3 vv = normalize3(pos - c.cameraPos);
+  const float dn = dot3(normal, vv);
+  const V3 dir = vv - (2.0f * dn) * normal;
+  extRays[2 * (size_t)i] = make_float4(pos.x, pos.y, pos.z, 50.0f);
+  extRays[2 * (size_t)i + 1] = make_float4(dir.x, dir.y, dir.z, 0.0f);
+}
+__global__ void __launch_bounds__(256) k_specular_resolve(const float* depth, uint2* out, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && depth[i] == 1.0f) out[i] = make_uint2(0u, 0u);
 }
 
 }  // namespace ddgi

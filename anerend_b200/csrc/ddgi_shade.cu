@@ -27,7 +27,7 @@ namespace ddgi {
 namespace SHADE_NS {
 
 // ------------------------------------------------------------------------------------------------------------
-template <int MINB>
+template <int MINB, bool EXT = false>
 __global__ void __launch_bounds__(128, MINB) k_shade(const FastCtx c) {
   const TraceCtx& t = c.t;
   const uint32_t nHits = c.qcount[FAST_QC_HITS];
@@ -35,10 +35,14 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const FastCtx c) {
   const V3 sunL = normalize3x(-t.lightDir);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nHits; i += gridDim.x * blockDim.x) {
     const uint32_t idx = c.hitq[i];
-    const uint32_t slot = idx % (uint32_t)t.N, probeLin = idx / (uint32_t)t.N;
-    const int layerLocal = (int)(probeLin / (uint32_t)t.Pl), probe = stripe_probe((int)(probeLin % (uint32_t)t.Pl), t.nXZ, t.rowOffset, t.rowStride), layer = t.layerMap[layerLocal];
-    const uint32_t ray = t.rayOrder ? (uint32_t)t.rayOrder[slot] : slot;
-    const V3 origin = mk3((float)(probe % t.nXZ), (float)layer, (float)(probe / t.nXZ)) * t.step + t.camOff;
+    int layer = 0, probe = 0; uint32_t ray = 0; V3 origin;
+    if (!EXT) {
+      const uint32_t slot = idx % (uint32_t)t.N, probeLin = idx / (uint32_t)t.N;
+      const int layerLocal = (int)(probeLin / (uint32_t)t.Pl);
+      probe = stripe_probe((int)(probeLin % (uint32_t)t.Pl), t.nXZ, t.rowOffset, t.rowStride); layer = t.layerMap[layerLocal];
+      ray = t.rayOrder ? (uint32_t)t.rayOrder[slot] : slot;
+      origin = mk3((float)(probe % t.nXZ), (float)layer, (float)(probe / t.nXZ)) * t.step + t.camOff;
+    } else { const float4 ea = c.extRays[2 * (size_t)idx]; origin = mk3(ea.x, ea.y, ea.z); }      // gl_WorldRayOriginEXT
     const float4 s0 = c.surf[3 * (size_t)idx], s1 = c.surf[3 * (size_t)idx + 1], s2 = c.surf[3 * (size_t)idx + 2];
     const V3 pos = mk3(s0.x, s0.y, s0.z), normal = mk3(s0.w, s1.x, s1.y), albedo = mk3(s1.z, s1.w, s2.x);
     const anerend_material_info_t* m = &t.materials[__float_as_uint(s2.y)];
@@ -62,11 +66,13 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const FastCtx c) {
         irradiance = irradiance + calc_light(normal, albedo, metallic, roughness, pos, origin, L, mk3(lt->color[0], lt->color[1], lt->color[2]) * att);
       }
     }
-    if ((t.uboFlags & ANEREND_UBO_DDGI_MULTI_FLAG) == ANEREND_UBO_DDGI_MULTI_FLAG)
+    const uint32_t gate = EXT ? ANEREND_UBO_DDGI_FLAG : ANEREND_UBO_DDGI_MULTI_FLAG;      // mirror_reflections.rchit:105 / rchit:98
+    if ((t.uboFlags & gate) == gate)
       irradiance = irradiance + calc_indirect(t, normal, albedo, metallic, roughness, pos, origin);
     const V3 rad = irradiance + emissive;
-    const size_t o = ((size_t)layer * P + probe) * t.N + ray;
-    t.rayIrr[o] = make_uint2((uint32_t)f2h(rad.x) | ((uint32_t)f2h(rad.y) << 16), (uint32_t)f2h(rad.z) | (0x3C00u << 16));
+    const size_t o = EXT ? (size_t)idx : ((size_t)layer * P + probe) * t.N + ray;
+    const uint32_t alpha = EXT ? (uint32_t)f2h(c.extDist[idx]) : 0x3C00u;                 // SpecularGIRT stores the hit distance (rgen:79)
+    t.rayIrr[o] = make_uint2((uint32_t)f2h(rad.x) | ((uint32_t)f2h(rad.y) << 16), (uint32_t)f2h(rad.z) | (alpha << 16));
     if (t.records) {
       const float4 h = c.hits[idx];
       anerend_ddgi_ray_record_t rr;
@@ -76,6 +82,20 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const FastCtx c) {
   }
 }
 
+static cudaError_t launch_shade_ext_impl(const FastCtx& f, cudaStream_t s) {
+  static int maxBlocks = 0;
+  if (!maxBlocks) {
+    int dev = 0, sms = 0, nb = 0;
+    cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade<8, true>, 128, 0);
+    maxBlocks = sms * (nb > 0 ? nb : 1);
+  }
+  uint32_t blocks = (f.totalRays + 127u) / 128u;
+  if (blocks > (uint32_t)maxBlocks) blocks = (uint32_t)maxBlocks;
+  if (blocks == 0) return cudaSuccess;
+  k_shade<8, true><<<blocks, 128, 0, s>>>(f);
+  return cudaGetLastError();
+}
 template <int MINB>
 static cudaError_t launch_shade_minb(const FastCtx& f, cudaStream_t s) {
   static int maxBlocks = 0;
@@ -227,9 +247,11 @@ static cudaError_t launch_convolve_impl(const ConvFastCtx& f, cudaStream_t s) {
 
 #ifdef DDGI_SHADE_EXACT
 cudaError_t launch_shade_exact(const FastCtx& f, cudaStream_t s) { return exact::launch_shade_impl(f, s); }
+cudaError_t launch_shade_ext_exact(const FastCtx& f, cudaStream_t s) { return exact::launch_shade_ext_impl(f, s); }
 cudaError_t launch_convolve_exact(const ConvFastCtx& f, cudaStream_t s) { return exact::launch_convolve_impl(f, s); }
 #else
 cudaError_t launch_shade_fast(const FastCtx& f, cudaStream_t s) { return fast::launch_shade_impl(f, s); }
+cudaError_t launch_shade_ext_fast(const FastCtx& f, cudaStream_t s) { return fast::launch_shade_ext_impl(f, s); }
 cudaError_t launch_convolve_fast(const ConvFastCtx& f, cudaStream_t s) { return fast::launch_convolve_impl(f, s); }
 #endif
 

@@ -46,6 +46,9 @@ struct FastCtx {
   uint32_t* hitq;           // [rays] compacted indices of the rays that hit (k_shade runs over these with full warps)
   uint32_t* qcount;         // FAST_QC_SIZE counters
   uint32_t totalRays, numQueues;
+  // external-ray mode (SpecularGIRT: one ray per pixel instead of the probe rays; kernels instantiated with EXT = true)
+  const float4* extRays;    // [rays][2] (origin.xyz, tMax; 0 = no ray) (dir.xyz, -)
+  float* extDist;           // [rays] distance(hit position, ray origin) of the hits (mirror_reflections.rchit:86)
   uint32_t surfStride;      // float4s per surface record (3; ShadowRT stages positions only: 1)
   uint32_t rawSunDir;       // queue 0 rays run along -lightDir as given (ShadowRT) instead of normalize(-lightDir) (probe rchit)
   uint32_t tune[8];         // loop tunables (ddgi_fast.cuh TUNE_*); [3] = 0x64646464 (planes2)
@@ -61,6 +64,8 @@ struct ConvFastCtx {
 
 // launchers implemented in ddgi_shade.cu (one pair per build of that file)
 cudaError_t launch_shade_exact(const FastCtx& f, cudaStream_t s);
+cudaError_t launch_shade_ext_exact(const FastCtx& f, cudaStream_t s);      // EXT = true (SpecularGIRT)
+cudaError_t launch_shade_ext_fast(const FastCtx& f, cudaStream_t s);
 cudaError_t launch_convolve_exact(const ConvFastCtx& f, cudaStream_t s);
 cudaError_t launch_shade_fast(const FastCtx& f, cudaStream_t s);
 cudaError_t launch_convolve_fast(const ConvFastCtx& f, cudaStream_t s);

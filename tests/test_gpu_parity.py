@@ -489,13 +489,14 @@ def test_bake_mode_matches_oracle_bit_for_bit(kernels, oracle, make_gpu):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kernels", ["wavefront", "simple"])
 @pytest.mark.parametrize("name", ["cornell_small", "textured"])
-def test_specular_gi_matches_oracle_bit_for_bit(name, oracle, make_gpu):
+def test_specular_gi_matches_oracle_bit_for_bit(name, kernels, oracle, make_gpu):
     """SURVEY §8f N2 through the C ABI: the "SpecularGIRT" pass on the path's BVH and atlas (host- and device-pointer entry points)."""
     import torch
     from tests import shadow_inputs as SI
     scene, (nxz, ny, nr) = SCENES[name]()
-    p = make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS)
+    p = make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS | KERNEL_FLAGS[kernels])
     o, g = oracle.Oracle(p), make_gpu(p)
     rots = parity.setup_pair(scene, (o, g), seed=5)
     for h in (o, g):
@@ -515,5 +516,9 @@ def test_specular_gi_matches_oracle_bit_for_bit(name, oracle, make_gpu):
     g.specular_gi_device(dd.data_ptr(), dg.data_ptr(), W, H, dout.data_ptr())
     g.sync()
     assert np.array_equal(dout.cpu().numpy().view(np.uint16), ro)
+    for h in (o, g):                              # the pass shares the wavefront scratch with the probe update: still intact
+        h.set_scene_ubo(scene.ubo)
+        h.update(-1, rots)
+    assert np.array_equal(o.download_atlas(), g.download_atlas())
     o.close()
     g.close()
