@@ -1022,7 +1022,8 @@ int specularGi(anerend_ddgi* h, const float* dDepth, const float4* dGeom0, uint3
   c.cameraPos = mk3(h->ubo.camera_pos[0], h->ubo.camera_pos[1], h->ubo.camera_pos[2]);
   c.screenW = (float)h->ubo.screen_width; c.screenH = (float)h->ubo.screen_height;
 #ifndef DDGI_HOST_EMU
-  if (!(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS) && h->numNodes > 0) {
+  static const bool specWavefront = getenv("DDGI_SPECULAR_SIMPLE") == nullptr && getenv("DDGI_SPECULAR_WAVEFRONT") != nullptr;   // opt-in until validated on the GPU
+  if (specWavefront && !(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS) && h->numNodes > 0) {
     // the wavefront kernels in external-ray mode: one reflected ray per pixel instead of the probe rays
     Backend& be = h->be;
     const uint32_t nq = 1u + ((h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) ? h->numLights : 0u);
