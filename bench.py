@@ -472,7 +472,7 @@ def main():
         h.sync()
         sms = s0.elapsed_time(s1) / 10.0
         shadow_rt = {"pixels": sw * sh, "ms": sms, "mrays_per_s": sw * sh / sms / 1e3, "lit_fraction": float(dvis.mean().item())}
-        # SpecularGIRT: same camera and depth, random G-buffer normals; one-thread-per-pixel kernel (not yet on the wavefront kernels)
+        # SpecularGIRT: same camera and depth, random G-buffer normals (incoherent reflections); wavefront kernels in external-ray mode
         u["flags"] |= _L.UBO_SPECULAR_GI_FLAG
         h.set_scene_ubo(u)
         dgeom = torch.randn((sh, sw, 4), generator=gen, device=dev)
