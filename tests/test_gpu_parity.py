@@ -522,3 +522,27 @@ def test_specular_gi_matches_oracle_bit_for_bit(name, kernels, oracle, make_gpu)
     assert np.array_equal(o.download_atlas(), g.download_atlas())
     o.close()
     g.close()
+
+
+@pytest.mark.gpu
+def test_reference_default_grid_matches_oracle(oracle, make_gpu):
+    """The reference's own compile-time configuration (probe_helpers.glsl:1-7: 64 probes per plane side, 8 planes, 256 rays,
+    16x16 ray tiles, atlas 640 x 5120): two full-grid updates of 8.4 M probe rays each, atlas bit-identical to the oracle."""
+    nxz, ny, nr = 64, 8, 256
+    scene = scenes.cornell_box(grid=(nxz, ny, nr), wall_res=24, box_res=6)
+    p = make_params(nxz, ny, nr, flags=L.FLAG_SKIP_DEAD_SHADOW_RAYS)          # the faithful subset: sun only
+    o, g = oracle.Oracle(p), make_gpu(p)
+    o.set_threads(0)
+    rots = parity.setup_pair(scene, (o, g), seed=9)
+    assert (g.atlas_width, g.atlas_height) == (640, 5120) and g.ray_tile == (16, 16)
+    for it in range(2):
+        for h in (o, g):
+            h.translate()
+            h.update(-1, rots)
+        assert np.array_equal(o.download_atlas(), g.download_atlas()), "atlas is not bit-identical"
+    io, do = o.download_rays(3)
+    ig, dg = g.download_rays(3)
+    assert io.shape == (1024, 1024, 4) and np.array_equal(do, dg) and np.array_equal(io, ig)      # ProbeRaysIrrTex / DirTex of one layer
+    so, sg = o.stats(), g.stats()
+    o.close()
+    g.close()
