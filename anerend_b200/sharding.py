@@ -138,6 +138,25 @@ def all_gather_atlas_layers(atlas, num_probes_xz, num_probes_y, rank, world, gro
     return atlas
 
 
+def all_gather_atlas_stripes(atlas, num_probes_xz, num_probes_y, rank, world, group=None):
+    """All-gather for row stripes (`_set_row_stripe(rank, world)`): rank r owns the probe rows z = r mod R of every layer, i.e.
+    the 10-row blocks r, r+R, ... of the atlas.  Packed send buffer, one all_gather_into_tensor, one strided scatter back.
+    `atlas` is a torch tensor [H, W, 4]; needs nXZ divisible by R (equal stripes)."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return atlas
+    if num_probes_xz % world:
+        raise ValueError("stripe gather needs num_probes_xz divisible by the world size")
+    per = num_probes_xz // world
+    a = atlas.view(torch.int64).view(num_probes_y, per, world, 10, atlas.shape[1])        # [layer][row k][owner][10 atlas rows][W] texels
+    send = a[:, :, rank].contiguous()
+    recv = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=a.device)
+    dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)
+    a.copy_(recv.permute(1, 2, 0, 3, 4))
+    return atlas
+
+
 def slab_rows(num_probes_xz, slab):
     """Atlas row range [begin, end) of a layer slab: 10*nXZ rows per layer (IrradianceProbeConvolvePass.cpp:84-99)."""
     return 10 * num_probes_xz * slab[0], 10 * num_probes_xz * slab[1]

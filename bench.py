@@ -163,7 +163,7 @@ def main():
     ap.add_argument("--fast-math", action="store_true", help="time the FAST_MATH build as the headline (default: exact build)")
     ap.add_argument("--no-extras", action="store_true", help="skip the atlas-consumer / ShadowRT / SpecularGIRT figures and the C5 1-GPU base")
     ap.add_argument("--no-alt", action="store_true", help="skip the second-build and 1-GPU strong-scaling-base measurements")
-    ap.add_argument("--deal", default="stripes", choices=["stripes", "measured", "static"],
+    ap.add_argument("--deal", default=None, choices=["stripes", "measured", "static"],
                     help="N>1, fused exchange: every rank takes the probe rows z = rank mod N of every layer (default; needs nXZ "
                          "divisible by N), or whole layers dealt by measured per-layer cost, or by the static mirrored/zigzag rule")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
@@ -193,7 +193,9 @@ def main():
     # multi-GPU: interleaved layer sets (balanced) when nY divides evenly, contiguous slabs otherwise
     mirrored = world > 1 and ny % (2 * world) == 0
     interleaved = world > 1 and (mirrored or ny % world == 0)
-    stripes = world > 1 and args.exchange == "fused" and args.deal == "stripes" and nxz % world == 0
+    if args.deal is None:                      # peer push: row stripes; NCCL: the static mirrored slabs (the measured collective baseline)
+        args.deal = "stripes" if args.exchange == "fused" else "static"
+    stripes = world > 1 and args.deal == "stripes" and nxz % world == 0
     measured_deal = world > 1 and args.exchange == "fused" and (args.deal == "measured" or (args.deal == "stripes" and not stripes))
     slab = (0, ny) if (interleaved or measured_deal or stripes) else sharding.slab_for_rank(ny, rank, world)
     my_layers = (list(range(ny)) if stripes else sharding.mirrored_slabs_for_rank(ny, rank, world) if mirrored else
@@ -283,6 +285,10 @@ def main():
             hh.translate()
             if do_gather and fused:           # the convolution stores into every peer's atlas; barriers inside the call
                 hh.update_layers(my_layers, rots[k])
+            elif do_gather and stripes:       # row stripes + one NCCL all-gather of the packed stripe rows
+                hh.update_layers(my_layers, rots[k])
+                with torch.cuda.stream(stream):
+                    sharding.all_gather_atlas_stripes(atlas_t, nxz, ny, rank, world)
             elif do_gather and interleaved:
                 hh.update_layers(my_layers, rots[k])
                 with torch.cuda.stream(stream):
@@ -564,6 +570,7 @@ def main():
                     "bvh8_nodes": int(info.num_nodes), "accel_build_ms": accel_ms,
                     "atlas_exchange": ("peer push: after the convolution a copy kernel stores this rank's atlas rows into all peers' atlases "
                                        "over NVLink (cudaIpc-mapped), device-side barrier before and after; no collective" if fused else
+                                       "nccl all_gather of the packed stripe rows on the handle's stream" if stripes else
                                        "2 in-place nccl all_gathers of mirrored slabs on the handle's stream" if mirrored else
                                        "nccl all_gather of interleaved layers (pack, gather, scatter) on the handle's stream" if interleaved
                                        else "nccl all_gather of contiguous slabs, in place") if world > 1 else "none"})

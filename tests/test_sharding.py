@@ -223,3 +223,58 @@ def test_row_stripes_assemble_the_full_atlas(make_emu):
         parts[0].set_row_stripe(3, 3)
     for h in [full] + parts:
         h.close()
+
+
+def _worker_stripes(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    from anerend_b200 import layouts as L, make_params, scenes
+    from anerend_b200.capi import DdgiHandle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    emu = ctypes.CDLL(g.build_host_emu())
+    nxz, ny, nr = 4, 3, 64
+    scene = scenes.random_soup(53, ntris=400, grid=(nxz, ny, nr))
+    h = DdgiHandle(emu, "anerend_emu_ddgi_", make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS))
+    h.upload_scene(scene)
+    h.set_scene_ubo(scene.ubo)
+    h.build_accel()
+    h.set_row_stripe(rank, world)
+    rots = h.rotations(scenes.rotation_sequence(9, ny))
+    for it in range(3):
+        h.update(-1, rots)
+        atlas = torch.from_numpy(h.download_atlas().view(np.int16).copy())
+        sharding.all_gather_atlas_stripes(atlas, nxz, ny, rank, world)
+        h.upload_atlas(atlas.numpy().view(np.uint16))
+    np.save(os.path.join(out_dir, f"atlas_s{rank}.npy"), h.download_atlas())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_row_stripes_equal_single_rank(tmp_path, make_emu):
+    """The default multi-GPU partition (row stripes) with a collective exchange, world size 2 over gloo."""
+    import torch.multiprocessing as mp
+    from anerend_b200 import layouts as L, make_params, scenes
+    import __graft_entry__ as g
+    g.build_host_emu()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker_stripes, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    nxz, ny, nr = 4, 3, 64
+    scene = scenes.random_soup(53, ntris=400, grid=(nxz, ny, nr))
+    h = make_emu(make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS))
+    h.upload_scene(scene)
+    h.set_scene_ubo(scene.ubo)
+    h.build_accel()
+    rots = h.rotations(scenes.rotation_sequence(9, ny))
+    for it in range(3):
+        h.update(-1, rots)
+    single = h.download_atlas()
+    h.close()
+    for r in range(2):
+        assert np.array_equal(np.load(os.path.join(str(tmp_path), f"atlas_s{r}.npy")), single)
