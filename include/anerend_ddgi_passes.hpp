@@ -1,4 +1,4 @@
-// anerend_ddgi_passes.hpp — header-only adapter: the three DDGI passes as AneRend `RenderPass` subclasses that call
+// anerend_ddgi_passes.hpp — header-only adapter: the three DDGI passes (and ShadowRT / SpecularGIRT) as AneRend `RenderPass` subclasses that call
 // the C ABI (anerend_cuda_ddgi.h) instead of recording Vulkan ray-tracing/compute/transfer commands.
 //
 // Mirrors, name for name:
@@ -124,6 +124,66 @@ public:
       if (!exeParams.rc->getRenderOptions().ddgiEnabled) return;         // :112
       uint32_t probeLayer = (uint32_t)exeParams.rc->blackboardValueInt(ANEREND_BLACKBOARD_LAYER);   // :126
       if (anerend_cuda_ddgi_convolve_layer(_vol->handle, (int32_t)probeLayer) != 0) std::printf("%s\n", anerend_cuda_ddgi_last_error(_vol->handle));
+    });
+  }
+private:
+  std::shared_ptr<Volume> _vol;
+};
+
+// ---- the other ray passes on the same acceleration structure ---------------------------------------
+// They read and write frame-graph images.  The engine hands those over as CUDA device pointers through ONE more accessor,
+//   void* rc->cudaResource(const char* resourceName)   (the image's memory, imported once via VK_KHR_external_memory)
+// for the resource names the reference passes declare (ShadowRayTracingPass.cpp:18-36, SpecularGIRTPass.cpp:19-88); a null
+// pointer turns the pass into a no-op.  Formats: GeometryDepthImage r32f, RTShadowImage r32f, Geometry0Image rgba32f (normal in
+// rgb), ReflectTex rgba16f; all of the swap-chain extent (rc->screenWidth() x rc->screenHeight()).
+
+template <class Engine>
+class ShadowRayTracingPass : public Engine::RenderPass {          // src/anerend/render/passes/ShadowRayTracingPass.{h,cpp}, "ShadowRT"
+public:
+  explicit ShadowRayTracingPass(std::shared_ptr<Volume> v) : _vol(std::move(v)) {}
+  void registerToGraph(typename Engine::FrameGraphBuilder& fgb, typename Engine::RenderContext*) override final {
+    typename Engine::RenderPassRegisterInfo info{};
+    info._name = "ShadowRT";
+    { typename Engine::ResourceUsage u{}; u._resourceName = "GeometryDepthImage"; info._resourceUsages.emplace_back(std::move(u)); }   // :22
+    { typename Engine::ResourceUsage u{}; u._resourceName = "RTShadowImage"; info._resourceUsages.emplace_back(std::move(u)); }        // :30
+    fgb.registerRenderPass(std::move(info));
+    fgb.registerRenderPassExe("ShadowRT", [this](typename Engine::RenderExeParams exeParams) {
+      if (!_vol->handle) return;
+      void* depth = exeParams.rc->cudaResource("GeometryDepthImage");
+      void* out = exeParams.rc->cudaResource("RTShadowImage");
+      if (!depth || !out) return;
+      anerend_cuda_ddgi_set_scene_ubo(_vol->handle, exeParams.rc->sceneUbo());      // UBO_RT_SHADOWS_FLAG gates the pass (shadow.rgen:32-34)
+      if (anerend_cuda_ddgi_shadow_rt_device(_vol->handle, depth, exeParams.rc->screenWidth(), exeParams.rc->screenHeight(), out) != 0)
+        std::printf("%s\n", anerend_cuda_ddgi_last_error(_vol->handle));
+    });
+  }
+private:
+  std::shared_ptr<Volume> _vol;
+};
+
+template <class Engine>
+class SpecularGIRTPass : public Engine::RenderPass {              // src/anerend/render/passes/SpecularGIRTPass.{h,cpp}, "SpecularGIRT"
+public:
+  explicit SpecularGIRTPass(std::shared_ptr<Volume> v) : _vol(std::move(v)) {}
+  void registerToGraph(typename Engine::FrameGraphBuilder& fgb, typename Engine::RenderContext*) override final {
+    typename Engine::RenderPassRegisterInfo info{};
+    info._name = "SpecularGIRT";
+    info._group = "SpecularGI";
+    for (const char* n : {"ReflectTex", "GeometryDepthImage", "Geometry0Image", ANEREND_RES_CONV, "Geometry1Image", "SpecularBRDFLutTex"}) {   // :30-82
+      typename Engine::ResourceUsage u{}; u._resourceName = n; info._resourceUsages.emplace_back(std::move(u));
+    }
+    fgb.registerRenderPass(std::move(info));
+    fgb.registerRenderPassExe("SpecularGIRT", [this](typename Engine::RenderExeParams exeParams) {
+      if (!_vol->handle) return;
+      if (!exeParams.rc->getRenderOptions().raytracingEnabled) return;   // SpecularGIRTPass.cpp:102
+      if (!exeParams.rc->getRenderOptions().specularGiEnabled) return;   // :103
+      void* depth = exeParams.rc->cudaResource("GeometryDepthImage");
+      void* geom0 = exeParams.rc->cudaResource("Geometry0Image");
+      void* out = exeParams.rc->cudaResource("ReflectTex");
+      if (!depth || !geom0 || !out) return;
+      anerend_cuda_ddgi_set_scene_ubo(_vol->handle, exeParams.rc->sceneUbo());
+      if (anerend_cuda_ddgi_specular_gi_device(_vol->handle, depth, geom0, exeParams.rc->screenWidth(), exeParams.rc->screenHeight(), out) != 0)
+        std::printf("%s\n", anerend_cuda_ddgi_last_error(_vol->handle));
     });
   }
 private:

@@ -14,7 +14,7 @@
 #include "../../include/anerend_ddgi_passes.hpp"
 
 namespace stub {
-struct RenderOptions { bool raytracingEnabled = true; bool ddgiEnabled = true; bool multiBounceDdgiEnabled = true; };
+struct RenderOptions { bool raytracingEnabled = true; bool ddgiEnabled = true; bool multiBounceDdgiEnabled = true; bool specularGiEnabled = true; };
 struct RenderContext {
   RenderOptions opts; anerend_scene_ubo_t ubo{}; std::map<std::string, int> blackboard; bool baking = false;
   size_t nXZ = 8, nY = 4;
@@ -25,6 +25,10 @@ struct RenderContext {
   int blackboardValueInt(const std::string& k) { return blackboard[k]; }
   void setBlackboardValueInt(const std::string& k, int v) { blackboard[k] = v; }
   const anerend_scene_ubo_t* sceneUbo() { return &ubo; }
+  std::map<std::string, void*> cuda;            // device pointers of frame-graph images (none in this stub: the passes no-op)
+  void* cudaResource(const char* name) { auto it = cuda.find(name); return it == cuda.end() ? nullptr : it->second; }
+  uint32_t screenWidth() { return ubo.screen_width; }
+  uint32_t screenHeight() { return ubo.screen_height; }
 };
 struct RenderExeParams { RenderContext* rc; };
 struct ResourceUsage { std::string _resourceName; };
@@ -59,6 +63,17 @@ int main(int argc, char** argv) {
   IrradianceProbeTranslationPass<stub::Engine> trans(vol);
   IrradianceProbeRayTracingPass<stub::Engine> rt(vol);
   IrradianceProbeConvolvePass<stub::Engine> conv(vol);
+  ShadowRayTracingPass<stub::Engine> shadowRt(vol);
+  SpecularGIRTPass<stub::Engine> specRt(vol);
+  {  // the other ray passes: names, group and resource usages as the reference declares them; without images they no-op
+    stub::FrameGraphBuilder g2;
+    shadowRt.registerToGraph(g2, &rc); specRt.registerToGraph(g2, &rc);
+    if (g2.passes.size() != 2 || g2.passes[0]._name != "ShadowRT" || g2.passes[0]._resourceUsages.size() != 2 ||
+        g2.passes[0]._resourceUsages[1]._resourceName != "RTShadowImage" || g2.passes[1]._name != "SpecularGIRT" ||
+        g2.passes[1]._group != "SpecularGI" || g2.passes[1]._resourceUsages.size() != 6 ||
+        g2.passes[1]._resourceUsages[3]._resourceName != "ProbeRaysConvTex") { printf("FAIL ray pass names\n"); return 1; }
+    g2.executeGraph(&rc);
+  }
   std::vector<stub::RenderPass*> passes = {&trans, &rt, &conv};              // VulkanRenderer.cpp:4473-4475
   for (auto* p : passes) p->registerToGraph(fgb, &rc);
   if (fgb.passes.size() != 3 || fgb.passes[0]._name != "IrradianceProbeTrans" || fgb.passes[1]._name != "IrradianceProbeRT" ||
