@@ -544,3 +544,119 @@ def test_specular_gi_known_answer(oracle):
     assert (got[0, 1] == 0).all()
     assert np.isinf(got[1, 1, 3]) and np.allclose(got[1, 1, :3], (0.033105, 0.214041, 0.447988), rtol=2e-3)
     o.close()
+
+
+def _cook_torrance_f64(N, albedo, metallic, roughness, pos, view, L, radiance):
+    """pbr_light.glsl:98-166 restated in float64 from SURVEY.md Appendix A.7 (independent of the oracle's code)."""
+    N, albedo, pos, view, L, radiance = (np.asarray(v, np.float64) for v in (N, albedo, pos, view, L, radiance))
+    V = (view - pos) / np.linalg.norm(view - pos)
+    F0 = 0.04 * (1 - metallic) + albedo * metallic
+    H = (V + L) / np.linalg.norm(V + L)
+    a2 = (roughness * roughness) ** 2
+    NdotH = max(N @ H, 0.0)
+    NDF = (a2 + 0.001) / (3.14159265359 * (NdotH * NdotH * (a2 - 1) + 1) ** 2)
+    k = (roughness + 1) ** 2 / 8
+    NdotV, NdotL = max(N @ V, 0.0), max(N @ L, 0.0)
+    G = (NdotL / (NdotL * (1 - k) + k)) * (NdotV / (NdotV * (1 - k) + k))
+    F = F0 + (1 - F0) * np.clip(1 - max(H @ V, 0.0), 0, 1) ** 5
+    kD = (1 - F) * (1 - metallic)
+    spec = np.clip(NDF * G * F / (4 * NdotV * NdotL + 1e-4), 0, 1)
+    return (kD * albedo / 3.14159265359 + spec) * radiance * NdotL
+
+
+def test_calc_light_known_answers(oracle):
+    """KATs for calcLight (pbr_light.glsl:98-166): the sun (radiance = sunIntensity) and a point light with the (1 - d/range)^2
+    falloff (:132-138), against a float64 restatement of the formulas; plus the closed form at normal incidence."""
+    rng = np.random.RandomState(3)
+    for it in range(40):
+        N = rng.normal(size=3); N /= np.linalg.norm(N)
+        pos, view = rng.uniform(-3, 3, 3), rng.uniform(-3, 3, 3)
+        albedo, metallic, rough = rng.uniform(0.05, 0.95, 3), float(rng.rand() < 0.3), rng.uniform(0.15, 1.0)
+        ld = rng.normal(size=3); ld /= np.linalg.norm(ld)
+        got = oracle.calc_light(N, albedo, metallic, rough, pos, view, ld, 5.0)
+        want = _cook_torrance_f64(N, albedo, metallic, rough, pos, view, -ld, np.full(3, 5.0))
+        assert np.allclose(got, want, rtol=3e-4, atol=2e-6), (it, got, want)
+        light = np.zeros(1, L.LIGHT); lp = pos + rng.uniform(-4, 4, 3); rng_m = 9.0
+        light["world_pos"][0] = (*lp, rng_m); light["color"][0] = (2.0, 3.0, 4.0, 1.0)
+        d = min(np.linalg.norm(lp - pos), rng_m)
+        got = oracle.calc_light(N, albedo, metallic, rough, pos, view, ld, 5.0, light=light)
+        want = _cook_torrance_f64(N, albedo, metallic, rough, pos, view, (lp - pos) / np.linalg.norm(lp - pos), np.array([2.0, 3.0, 4.0]) * (1 - d / rng_m) ** 2)
+        assert np.allclose(got, want, rtol=3e-4, atol=2e-6), (it, got, want)
+    # normal incidence, dielectric, roughness 1: N = V = L -> NdotH = 1, NDF = 1.001/pi, G = 1, F = F0 = 0.04
+    got = oracle.calc_light((0, 1, 0), (0.5, 0.5, 0.5), 0.0, 1.0, (0, 0, 0), (0, 2, 0), (0, -1, 0), 3.0)
+    spec = min(1.001 / 3.14159265359 * 0.04 / (4 + 1e-4), 1.0)
+    assert np.allclose(got, ((1 - 0.04) * 0.5 / 3.14159265359 + spec) * 3.0, rtol=1e-5)
+    # light below the horizon: NdotL = 0 -> exactly zero
+    assert (oracle.calc_light((0, 1, 0), (0.5, 0.5, 0.5), 0.0, 0.5, (0, 0, 0), (1, 2, 0), (0, 1, 0), 3.0) == 0).all()
+
+
+def _indirect_f64(atlas, nxz, ny, cam, pos, n, albedo, metallic, rough, view, clamp):
+    """calcIndirectDiffuseLight restated in float64 from SURVEY.md Appendix A.8 (sampleProbe, weightProbe, sampleSingleProbe,
+    octEncode, fresnelSchlickRoughness), independent of the oracle's code."""
+    H, W = atlas.shape[:2]
+    step = np.array([1.0, 2.0, 1.0])
+    camoff = np.array([int(cam[0] / 1.0) * 1.0 - nxz / 2.0, 0.0, int(cam[2] / 1.0) * 1.0 - nxz / 2.0])
+    pos, n, albedo, view = (np.asarray(v, np.float64) for v in (pos, n, albedo, view))
+    V = (view - pos) / np.linalg.norm(view - pos)
+    F0 = 0.04 * (1 - metallic) + albedo * metallic
+    r2 = rough * rough
+    kS = F0 + (np.maximum(1 - r2, F0) - F0) * np.clip(1 - max(n @ V, 0.0), 0, 1) ** 5
+    kD = (1 - kS) * (1 - metallic)
+    p = np.array([np.clip(np.floor((pos[0] - camoff[0]) / 1.0), 0, nxz - 1), np.clip(np.floor(pos[1] / 2.0), 0, ny - 1),
+                  np.clip(np.floor((pos[2] - camoff[2]) / 1.0), 0, nxz - 1)])
+    base = p * step + camoff
+    alpha = np.clip((pos - base) / step, 0, 1)
+    nn = n / np.linalg.norm(n)
+    v = np.array([nn[0], nn[2], nn[1]])                                  # octEncode swaps y and z first
+    v = v / np.abs(v).sum()
+    o = v[:2].copy()
+    if v[2] < 0:
+        sgn = np.where(o >= 0, 1.0, -1.0)
+        o = (1 - np.abs(o[::-1])) * sgn
+    o = o * 0.5 + 0.5
+
+    def texel(x, y):
+        if clamp:
+            x, y = min(max(x, 0), W - 1), min(max(y, 0), H - 1)
+        return atlas[y % H, x % W, :3].astype(np.float64)
+
+    sw, sm = 0.0, np.zeros(3)
+    for off in ((0, 0, 0), (1, 1, 1), (1, 1, 0), (1, 0, 0), (0, 1, 1), (0, 1, 0), (0, 0, 1), (1, 0, 1)):
+        off = np.array(off)
+        tri = np.where(off == 1, alpha, 1 - alpha)
+        dirp = base + off * step - pos
+        dirp = dirp / np.linalg.norm(dirp)
+        w = max(1e-6, max(1e-4, (dirp @ n + 1) / 2) ** 2 + 0.2) * tri.prod()
+        q = (p + off).astype(int)
+        sx, sy = 10 * q[0] + 1, 10 * nxz * q[1] + 10 * q[2] + 1
+        tsx, tex = (2 * sx + 1) / (2 * W), (2 * (sx + 7) + 1) / (2 * W)
+        tsy, tey = (2 * sy + 1) / (2 * H), (2 * (sy + 7) + 1) / (2 * H)
+        x, y = (tsx + (tex - tsx) * o[0]) * W - 0.5, (tsy + (tey - tsy) * o[1]) * H - 0.5
+        ix, iy = int(np.floor(x)), int(np.floor(y)); fx, fy = x - ix, y - iy
+        c = (texel(ix, iy) * (1 - fx) * (1 - fy) + texel(ix + 1, iy) * fx * (1 - fy) + texel(ix, iy + 1) * (1 - fx) * fy + texel(ix + 1, iy + 1) * fx * fy)
+        sm += w * np.sqrt(c); sw += w
+    irr = (sm / sw) ** 2 * 0.5 * 3.1415926
+    return kD * irr * albedo
+
+
+def test_indirect_diffuse_against_a_float64_restatement(oracle):
+    """Pins sampleProbe / weightProbe / sampleSingleProbe / octEncode (pbr_light.glsl:168-388) on a random atlas: the oracle
+    against an independent float64 restatement, REPEAT and CLAMP_TO_EDGE samplers, points inside and outside the grid."""
+    from tests.consumer_points import surface_points
+    nxz, ny = 4, 2
+    o = oracle.Oracle(make_params(nxz, ny, 64))
+    s = scenes.empty_scene(grid=(nxz, ny, 64))
+    cam = (0.3, 1.0, -0.6)
+    o.set_scene_ubo(s.with_camera(cam))
+    rng = np.random.RandomState(8)
+    a = np.zeros((10 * nxz * ny, 10 * nxz, 4), np.float16)
+    a[..., :3] = rng.uniform(0.0, 2.0, a.shape[:2] + (3,)); a[..., 3] = 1.0
+    o.upload_atlas(a.view(np.uint16))
+    pts = surface_points(120, nxz, ny, seed=5, camera=cam)
+    view = np.array([0.2, 3.0, 0.1])
+    for clamp in (False, True):
+        got = o.indirect_diffuse(pts, view, clamp)[:, :3]
+        want = np.array([_indirect_f64(a.astype(np.float32), nxz, ny, cam, q[0:3], q[3:6], q[6:9], q[9], q[10], view, clamp) for q in pts])
+        close = np.isclose(got, want, rtol=2e-3, atol=1e-5).all(axis=1)
+        assert close.mean() >= 0.97, (clamp, close.mean(), got[~close][:2], want[~close][:2])    # a texel-boundary tap may land one texel off in float64
+    o.close()
