@@ -96,6 +96,7 @@ struct anerend_ddgi {
   // emissive exist only while some material is textured
   DTexture* dTextures = nullptr; uint8_t* dTexPool = nullptr; float* dSrgbLut = nullptr; uint32_t numTextures = 0;
   std::vector<DTexture> textures; bool texturedScene = false, emissiveTextures = false;
+  bool texturesStale = false;      // the texture array was replaced after the scene that refers to it was validated
   float4* dShadeUV = nullptr; float4* dEmisTex = nullptr;
   // ShadowRT scratch (pixels): staged positions, visibility words, ray queue, counters
   float4* dExtRays = nullptr; float* dExtDist = nullptr; uint32_t extPixels = 0;      // SpecularGIRT: staged rays, hit distances
@@ -512,6 +513,10 @@ void exchangeDisconnect(anerend_ddgi*) {}
 #endif
 
 // Everything of a TraceCtx that does not depend on which layers are launched
+int texturesUsable(anerend_ddgi* h) {
+  if (h->texturesStale) return fail(h, ANEREND_DDGI_E_STATE, "upload_textures was called after upload_scene: upload the scene again so its texture indices are re-checked");
+  return 0;
+}
 TraceCtx sceneTraceCtx(anerend_ddgi* h) {
   TraceCtx c{};
   c.nodes = h->dNodes; c.bvhTris = h->dBvhTris; c.numNodes = h->numNodes;
@@ -554,6 +559,7 @@ int traceLayers(anerend_ddgi* h, const int* layers, int numLayers, const float* 
   Backend& be = h->be;
   if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "trace before build_accel");
   if (!h->haveUbo) return fail(h, ANEREND_DDGI_E_STATE, "trace before set_scene_ubo");
+  { int rct = texturesUsable(h); if (rct) return rct; }
   be.waitCopy();            // a pending H2D of the layer map (convolveLayers) must be done before the staging array is rewritten
   for (int l = 0; l < numLayers; ++l) h->hLayerMap[l] = layers[l];
 #ifdef DDGI_HOST_EMU
@@ -761,6 +767,7 @@ int DDGI_API(upload_textures)(anerend_ddgi_t* h, const anerend_texture_desc_t* t
   }
   BE_CHECK(h, be.sync());
   be.free(h->dTextures); be.free(h->dTexPool); h->dTextures = nullptr; h->dTexPool = nullptr; h->numTextures = 0; h->textures.clear();
+  h->texturesStale = h->haveScene && h->texturedScene;
   if (count == 0) return 0;
   if (!h->dSrgbLut) {          // texel decode table, made once on the host in fp32 (the oracle makes the same one)
     float lut[512];
@@ -778,6 +785,7 @@ int DDGI_API(upload_textures)(anerend_ddgi_t* h, const anerend_texture_desc_t* t
   }
   BE_CHECK(h, be.h2d(h->dTextures, table.data(), count * sizeof(DTexture))); BE_CHECK(h, be.sync());
   h->numTextures = count; h->textures = table;
+  h->texturesStale = h->haveScene && h->texturedScene;       // material indices were checked against the previous array
   return 0;
 }
 
@@ -796,7 +804,7 @@ int DDGI_API(upload_scene)(anerend_ddgi_t* h,
     if (ti < 0 || (uint32_t)ti >= h->numTextures) return fail(h, ANEREND_DDGI_E_INVALID, "material refers to a texture that was not uploaded (upload_textures first)");
     textured = true; emisTex = emisTex || k == 3;
   }
-  h->texturedScene = textured; h->emissiveTextures = emisTex;
+  h->texturedScene = textured; h->emissiveTextures = emisTex; h->texturesStale = false;
   if ((h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) && nl > 31) return fail(h, ANEREND_DDGI_E_INVALID, "at most 31 point lights with FLAG_POINT_LIGHTS");
   for (uint32_t i = 0; i < nm; ++i) {
     if ((uint64_t)meshes[i].index_offset + meshNumIndices[i] > ni) return fail(h, ANEREND_DDGI_E_INVALID, "mesh index range exceeds the index buffer");
@@ -1012,6 +1020,7 @@ int specularGi(anerend_ddgi* h, const float* dDepth, const float4* dGeom0, uint3
   if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "specular_gi before build_accel");
   if (!h->haveUbo) return fail(h, ANEREND_DDGI_E_STATE, "specular_gi before set_scene_ubo");
   if (!(h->ubo.flags & ANEREND_UBO_RT_ON_FLAG) || !(h->ubo.flags & ANEREND_UBO_SPECULAR_GI_FLAG)) return 0;    // SpecularGIRTPass.cpp:102-103
+  { int rct = texturesUsable(h); if (rct) return rct; }
   const uint32_t n = width * height;
   if (n == 0) return 0;
   SpecularCtx c{};

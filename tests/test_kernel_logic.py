@@ -303,3 +303,17 @@ def test_specular_gi_matches_oracle(name, oracle, make_emu):
         assert (h.specular_gi(depth, geom0) == 0xFFFF).all()          # SpecularGIRTPass.cpp:102-103: nothing written
     o.close()
     e.close()
+
+
+def test_replacing_textures_after_the_scene_is_refused(make_emu):
+    scene, (nxz, ny, nr) = SCENES["textured"]()
+    e = make_emu(make_params(nxz, ny, nr))
+    rots = parity.setup_pair(scene, (e,), seed=3)
+    e.update(-1, rots)
+    e.upload_textures(scene.textures[:1])            # material indices now dangle
+    with pytest.raises(Exception):
+        e.update(-1, rots)
+    e.upload_scene(scene)                            # re-uploads the full array, then the scene: valid again
+    e.build_accel()
+    e.update(-1, rots)
+    e.close()
