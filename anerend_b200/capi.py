@@ -131,6 +131,11 @@ class DdgiHandle:
             arr[i].width, arr[i].height, arr[i].format, arr[i].clamp_to_edge = px.shape[1], px.shape[0], int(fmt), 1 if clamp else 0
         self._call("upload_textures", arr, C.c_uint32(n))
 
+    def upload_tile_infos(self, atlas_indices):
+        """tileInfoBuffer: bindless index of each paged tile's baked atlas (-1 = none), 21 x 21 entries around the camera."""
+        arr = _c(atlas_indices, np.int32).reshape(-1)
+        self._call("upload_tile_infos", _ptr(arr) if arr.size else None, C.c_uint32(arr.size))
+
     def upload_scene(self, scene):
         s = scene
         self._keep = s

@@ -94,6 +94,7 @@ struct anerend_ddgi {
   uint32_t* dHitq = nullptr; float4* dShadeTris = nullptr; float* dConvW = nullptr;
   // bindless textures: descriptor table, texel pool, decode table (sRGB EOTF + UNORM); per-triangle uv records and per-ray
   // emissive exist only while some material is textured
+  int32_t* dTileInfos = nullptr; uint32_t numTiles = 0;     // tileInfoBuffer (baked atlases of the paged tiles)
   DTexture* dTextures = nullptr; uint8_t* dTexPool = nullptr; float* dSrgbLut = nullptr; uint32_t numTextures = 0;
   std::vector<DTexture> textures; bool texturedScene = false, emissiveTextures = false;
   bool texturesStale = false;      // the texture array was replaced after the scene that refers to it was validated
@@ -522,6 +523,8 @@ TraceCtx sceneTraceCtx(anerend_ddgi* h) {
   c.nodes = h->dNodes; c.bvhTris = h->dBvhTris; c.numNodes = h->numNodes;
   c.vertices = h->dVertices; c.indices = h->dIndices; c.materials = h->dMaterials;
   c.tex.textures = h->dTextures; c.tex.texPool = h->dTexPool; c.tex.srgbLut = h->dSrgbLut; c.tex.numTextures = h->numTextures;
+  c.tex.tileInfos = h->dTileInfos; c.tex.numTiles = h->numTiles;
+  c.cameraPos = mk3(h->ubo.camera_pos[0], h->ubo.camera_pos[1], h->ubo.camera_pos[2]);
   c.instances = h->dInstances; c.xforms = h->dXforms; c.triInstance = h->dTriInstance;
   c.lights = h->dLights; c.numLights = h->numLights;
   c.dirs = h->dDirs; c.layerMap = h->dLayerMap; c.rayOrder = h->dRayOrder; c.atlas = h->dAtlas; c.rayIrr = h->dRayIrr;
@@ -674,7 +677,7 @@ void destroyHandle(anerend_ddgi* h) {
   freeAccel(h); freeScene(h);
   be.free(h->dAtlas); be.free(h->dTemp); be.free(h->dRayIrr); be.free(h->dDirs); be.free(h->dFib); be.freeHostPinned(h->hDirs); be.free(h->dRayOrder);
   be.free(h->dLayerMap); be.freeHostPinned(h->hLayerMap);
-  be.free(h->dTextures); be.free(h->dTexPool); be.free(h->dSrgbLut); be.free(h->dEmisTex);
+  be.free(h->dTextures); be.free(h->dTexPool); be.free(h->dSrgbLut); be.free(h->dEmisTex); be.free(h->dTileInfos);
   be.free(h->dExtRays); be.free(h->dExtDist);
   be.free(h->dSrtPos); be.free(h->dSrtLit); be.free(h->dSrtQueue); be.free(h->dSrtQcount);
   be.free(h->dRecords); be.free(h->dTexelRecords); be.free(h->dStats); be.free(h->dSceneBounds); be.free(h->dCounters);
@@ -750,16 +753,29 @@ int DDGI_API(reset)(anerend_ddgi_t* h) {
 const char* DDGI_API(last_error)(const anerend_ddgi_t* h) { return h ? h->err.c_str() : "null handle"; }
 int DDGI_API(sync)(anerend_ddgi_t* h) { BE_CHECK(h, h->be.sync()); return peerCheck(h); }
 
+static size_t texelBytes(uint32_t format) { return format == ANEREND_TEX_RGBA16F ? 8 : format <= ANEREND_TEX_RGBA8_SRGB ? 4 : (format == ANEREND_TEX_RG8_UNORM ? 2 : 1); }
+// tileInfoBuffer (bindless.glsl binding 14, GPUTileInfo): one entry per tile of the (2*10+1)^2 page around the camera; ddgiAtlasTex
+// = bindless index of the tile's baked atlas (an ANEREND_TEX_RGBA16F texture of the atlas size) or -1.  count = 0 removes it.
+int DDGI_API(upload_tile_infos)(anerend_ddgi_t* h, const anerend_tile_info_t* tiles, uint32_t count) {
+  Backend& be = h->be;
+  if (count && !tiles) return fail(h, ANEREND_DDGI_E_INVALID, "null tile array");
+  BE_CHECK(h, be.sync());
+  be.free(h->dTileInfos); h->dTileInfos = nullptr; h->numTiles = 0;
+  if (count == 0) return 0;
+  BE_CHECK(h, be.alloc(&h->dTileInfos, count)); BE_CHECK(h, be.h2d(h->dTileInfos, tiles, count * sizeof(int32_t))); BE_CHECK(h, be.sync());
+  h->numTiles = count;
+  return 0;
+}
 int DDGI_API(upload_textures)(anerend_ddgi_t* h, const anerend_texture_desc_t* tex, uint32_t count) {
   Backend& be = h->be;
   if (count && !tex) return fail(h, ANEREND_DDGI_E_INVALID, "null texture array");
   std::vector<DTexture> table(count);
   size_t total = 0;
   for (uint32_t i = 0; i < count; ++i) {
-    if (!tex[i].pixels || tex[i].width == 0 || tex[i].height == 0 || tex[i].width > 16384u || tex[i].height > 16384u || tex[i].format > ANEREND_TEX_R8_UNORM)
+    if (!tex[i].pixels || tex[i].width == 0 || tex[i].height == 0 || tex[i].width > 16384u || tex[i].height > 16384u || tex[i].format > ANEREND_TEX_RGBA16F)
       return fail(h, ANEREND_DDGI_E_INVALID, "bad texture descriptor (BC-compressed assets are handed over decoded)");
-    const size_t bpp = tex[i].format <= ANEREND_TEX_RGBA8_SRGB ? 4 : (tex[i].format == ANEREND_TEX_RG8_UNORM ? 2 : 1);
-    total = (total + 15) & ~(size_t)15;
+    const size_t bpp = texelBytes(tex[i].format);
+    total = (total + 15) & ~(size_t)15;      // 16-byte aligned images (RGBA16F texels are read as 8-byte words)
     if (total > 0xFFFFFFFFull - (size_t)tex[i].width * tex[i].height * bpp) return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "texture pool larger than 4 GiB");
     table[i].offset = (uint32_t)total; table[i].width = tex[i].width; table[i].height = tex[i].height;
     table[i].formatClamp = tex[i].format | (tex[i].clamp_to_edge ? 1u << 8 : 0u);
@@ -780,7 +796,7 @@ int DDGI_API(upload_textures)(anerend_ddgi_t* h, const anerend_texture_desc_t* t
   }
   BE_CHECK(h, be.alloc(&h->dTextures, count)); BE_CHECK(h, be.alloc(&h->dTexPool, total));
   for (uint32_t i = 0; i < count; ++i) {
-    const size_t bpp = tex[i].format <= ANEREND_TEX_RGBA8_SRGB ? 4 : (tex[i].format == ANEREND_TEX_RG8_UNORM ? 2 : 1);
+    const size_t bpp = texelBytes(tex[i].format);
     BE_CHECK(h, be.h2d(h->dTexPool + table[i].offset, tex[i].pixels, (size_t)tex[i].width * tex[i].height * bpp));
   }
   BE_CHECK(h, be.h2d(h->dTextures, table.data(), count * sizeof(DTexture))); BE_CHECK(h, be.sync());
@@ -1091,8 +1107,9 @@ int DDGI_API(specular_gi)(anerend_ddgi_t* h, const float* depth, const float* ge
 namespace {
 int indirectDiffuse(anerend_ddgi* h, const float4* dPoints, uint32_t count, const float viewPos[3], int clampSampler, float4* dOut) {
   if (!h->haveUbo) return fail(h, ANEREND_DDGI_E_STATE, "indirect_diffuse before set_scene_ubo");
+  { int rct = texturesUsable(h); if (rct) return rct; }
   ConsumerCtx c{};
-  c.t.atlas = h->dAtlas; c.t.nXZ = h->nXZ; c.t.nY = h->nY; c.t.N = h->N; c.t.W = h->W; c.t.H = h->H; c.t.clampSampler = clampSampler ? 1 : 0;
+  c.t = sceneTraceCtx(h); c.t.clampSampler = clampSampler ? 1 : 0;
   gridFrame(h, c.t.camOff, c.t.step);        // as sampleProbe places the grid (pbr_light.glsl:274-301), from the CURRENT scene UBO
   c.points = dPoints; c.out = dOut; c.viewPos = mk3(viewPos[0], viewPos[1], viewPos[2]);
   DDGI_LAUNCH(h->be, k_indirect_diffuse, indirect_diffuse_body, count, c, 128);

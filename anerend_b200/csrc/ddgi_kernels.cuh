@@ -581,7 +581,8 @@ HD bool traverse(const uint4* __restrict__ nodes, const float4* __restrict__ tri
 // One bindless texture (bindless.glsl:179 `textures[]`): mip 0 in the byte pool, sampled like the reference's default sampler
 // (VK_FILTER_LINEAR, REPEAT or CLAMP_TO_EDGE per texture, PipelineUtil.h:98-112) at LOD 0 — ray-tracing stages have no derivatives.
 struct DTexture { uint32_t offset, width, height, formatClamp; };       // formatClamp: ANEREND_TEX_* | clamp_to_edge << 8
-struct TexCtx { const DTexture* textures; const uint8_t* texPool; const float* srgbLut; uint32_t numTextures; };
+struct TexCtx { const DTexture* textures; const uint8_t* texPool; const float* srgbLut; uint32_t numTextures;
+                const int32_t* tileInfos; uint32_t numTiles; };      // tileInfoBuffer (bindless.glsl binding 14): ddgiAtlasTex per paged tile, or null
 
 struct TraceCtx {
   const uint4* nodes; const float4* bvhTris; uint32_t numNodes;
@@ -599,6 +600,7 @@ struct TraceCtx {
   int numLayers;
   int Pl, rowOffset, rowStride;   // probes launched per layer: the z-rows rowOffset, rowOffset+rowStride, ... (stripe_probe)
   TexCtx tex;                     // bindless textures (set 0 binding 16)
+  V3 cameraPos;                   // ubo.cameraPos.xyz: centre of the tile page (worldPosToTileInfo, bindless.glsl:291-308)
   int clampSampler;               // atlas sampler addressing: 0 = REPEAT (probe RT pass, SpecularGIRT), 1 = CLAMP_TO_EDGE (deferred lighting)
   V3 camOff, step, sky, lightDir;
   float tmin, tmax, sunIntensity;
@@ -638,9 +640,14 @@ HD int tex_wrap(int i, int n, bool clampEdge) {
 }
 HD void tex_fetch(const TexCtx& c, const DTexture& t, int x, int y, float out[4]) {
   const uint32_t fmt = t.formatClamp & 0xFFu;
-  const uint32_t bpp = fmt <= ANEREND_TEX_RGBA8_SRGB ? 4u : (fmt == ANEREND_TEX_RG8_UNORM ? 2u : 1u);
+  const uint32_t bpp = fmt == ANEREND_TEX_RGBA16F ? 8u : fmt <= ANEREND_TEX_RGBA8_SRGB ? 4u : (fmt == ANEREND_TEX_RG8_UNORM ? 2u : 1u);
   const uint8_t* p = c.texPool + t.offset + ((size_t)y * t.width + (size_t)x) * bpp;
   out[0] = 0.0f; out[1] = 0.0f; out[2] = 0.0f; out[3] = 1.0f;
+  if (fmt == ANEREND_TEX_RGBA16F) {          // baked DDGI atlases (VulkanRenderer.cpp:2759); texels are 8-byte aligned in the pool
+    const uint2 h = *reinterpret_cast<const uint2*>(p);
+    out[0] = h2f((uint16_t)(h.x & 0xFFFFu)); out[1] = h2f((uint16_t)(h.x >> 16)); out[2] = h2f((uint16_t)(h.y & 0xFFFFu)); out[3] = h2f((uint16_t)(h.y >> 16));
+    return;
+  }
   // srgbLut[0..255] = sRGB EOTF of c/255, srgbLut[256..511] = c/255 (both made on the host, one table for oracle and device)
   if (fmt == ANEREND_TEX_RGBA8_SRGB) { out[0] = c.srgbLut[p[0]]; out[1] = c.srgbLut[p[1]]; out[2] = c.srgbLut[p[2]]; out[3] = c.srgbLut[256 + p[3]]; }
   else for (uint32_t k = 0; k < bpp; ++k) out[k] = c.srgbLut[256 + p[k]];
@@ -751,28 +758,68 @@ HD V3 atlas_bilinear(const TraceCtx& c, const AxisTap& ax, const AxisTap& ay) {
   float w00 = (1.0f - fx) * (1.0f - fy), w10 = fx * (1.0f - fy), w01 = (1.0f - fx) * fy, w11 = fx * fy;
   return t00 * w00 + t10 * w10 + t01 * w01 + t11 * w11;
 }
+// the same footprint on a bindless texture (a baked tile atlas)
+HD V3 texture_bilinear_taps(const TexCtx& c, int idx, const AxisTap& ax, const AxisTap& ay) {
+  const DTexture t = c.textures[idx];
+  float t00[4], t10[4], t01[4], t11[4];
+  tex_fetch(c, t, ax.i0, ay.i0, t00); tex_fetch(c, t, ax.i1, ay.i0, t10); tex_fetch(c, t, ax.i0, ay.i1, t01); tex_fetch(c, t, ax.i1, ay.i1, t11);
+  const float fx = ax.f, fy = ay.f;
+  const float w00 = (1.0f - fx) * (1.0f - fy), w10 = fx * (1.0f - fy), w01 = (1.0f - fx) * fy, w11 = fx * fy;
+  return mk3(t00[0], t00[1], t00[2]) * w00 + mk3(t10[0], t10[1], t10[2]) * w10 + mk3(t01[0], t01[1], t01[2]) * w01 + mk3(t11[0], t11[1], t11[2]) * w11;
+}
 // pbr_light.glsl:240-363 (live-grid branch :294-308) + weightProbe :190-238 + sampleSingleProbe :168-188.
 // octEncode(normalize(normal)) is the same for all 8 probes, and the atlas column of a tap depends only on the corner's
 // x, its row only on (y, z): the per-axis address arithmetic is evaluated once per distinct value (2 + 4 instead of 8 + 8);
 // every value is produced by the same operations as in the shader, so the result is unchanged.
-HD V3 sample_probe(const TraceCtx& c, V3 worldPos, V3 normal) {
-  int px = clampi((int)floorf((worldPos.x - c.camOff.x) / c.step.x), 0, c.nXZ - 1);
-  int py = clampi((int)floorf(worldPos.y / c.step.y), 0, c.nY - 1);
-  int pz = clampi((int)floorf((worldPos.z - c.camOff.z) / c.step.z), 0, c.nXZ - 1);
-  V3 base = mk3((float)px, (float)py, (float)pz) * c.step + c.camOff;
-  V3 alpha = clamp3((worldPos - base) / c.step, 0.0f, 1.0f);
+//
+// TILES (a tileInfoBuffer was uploaded): worldPosToTileInfo (bindless.glsl:291-308, only the upper bounds of the page are
+// checked, as in the shader) finds the paged tile of worldPos; if it carries a baked atlas (ddgiAtlasTex >= 0) the grid is
+// placed on that 32 m tile with step (32/nXZ, 1, 32/nXZ) (pbr_light.glsl:251-273).  WHICH texture is sampled is the caller's
+// choice, as in the shaders: the probe and reflection hit shaders always pass the live atlas (srcTex < 0), the deferred pass
+// passes the tile's baked atlas (deferred_tiled.comp:264-296).
+#define ANEREND_TILE_PAGE_RADIUS 10
+#define ANEREND_TILE_SIZE 32
+HD int world_pos_to_tile_atlas(const TraceCtx& c, V3 worldPos, int& tx, int& tz) {
+  const int w = ANEREND_TILE_PAGE_RADIUS * 2 + 1;
+  tx = (int)floorf(worldPos.x / (float)ANEREND_TILE_SIZE); tz = (int)floorf(worldPos.z / (float)ANEREND_TILE_SIZE);
+  const int cx = (int)floorf(c.cameraPos.x / (float)ANEREND_TILE_SIZE), cz = (int)floorf(c.cameraPos.z / (float)ANEREND_TILE_SIZE);
+  if (tx - cx > ANEREND_TILE_PAGE_RADIUS || tz - cz > ANEREND_TILE_PAGE_RADIUS) return -1;
+  const int idx = (tz - cz + ANEREND_TILE_PAGE_RADIUS) * w + (tx - cx + ANEREND_TILE_PAGE_RADIUS);
+  if (idx < 0 || (uint32_t)idx >= c.tex.numTiles) return -1;            // the shader would read out of bounds here: treated as "no tile"
+  const int atlasIdx = c.tex.tileInfos[idx];
+  return (atlasIdx >= 0 && (uint32_t)atlasIdx < c.tex.numTextures) ? atlasIdx : -1;
+}
+template <bool TILES = false>
+HD V3 sample_probe(const TraceCtx& c, V3 worldPos, V3 normal, int srcTex = -1) {
+  V3 step = c.step, camOff = c.camOff;
+  if (TILES) {
+    int tx, tz;
+    if (world_pos_to_tile_atlas(c, worldPos, tx, tz) >= 0) {
+      const float s = (float)ANEREND_TILE_SIZE / (float)c.nXZ;
+      step = mk3(s, 1.0f, s);
+      camOff = mk3((float)tx * (float)ANEREND_TILE_SIZE, 0.0f, (float)tz * (float)ANEREND_TILE_SIZE);
+    }
+  }
+  int px = clampi((int)floorf((worldPos.x - camOff.x) / step.x), 0, c.nXZ - 1);
+  int py = clampi((int)floorf(worldPos.y / step.y), 0, c.nY - 1);
+  int pz = clampi((int)floorf((worldPos.z - camOff.z) / step.z), 0, c.nXZ - 1);
+  V3 base = mk3((float)px, (float)py, (float)pz) * step + camOff;
+  V3 alpha = clamp3((worldPos - base) / step, 0.0f, 1.0f);
   float o0, o1; oct_encode(normalize3x(normal), o0, o1);
   o0 = xmul(xadd(o0, 1.0f), 0.5f); o1 = xmul(xadd(o1, 1.0f), 0.5f);
+  // texel footprint of the taps: in the size of the texture that is sampled (textureSize(probeTex, 0), pbr_light.glsl:170)
+  int srcW = c.W, srcH = c.H, srcClamp = c.clampSampler;
+  if (TILES && srcTex >= 0) { const DTexture st = c.tex.textures[srcTex]; srcW = (int)st.width; srcH = (int)st.height; srcClamp = (int)(st.formatClamp >> 8); }
   AxisTap tapX[2], tapY[4];
-  for (int ox = 0; ox < 2; ++ox) tapX[ox] = probe_axis_tap((8 + 2) * (px + ox) + 1, c.W, o0, c.clampSampler);
+  for (int ox = 0; ox < 2; ++ox) tapX[ox] = probe_axis_tap((8 + 2) * (px + ox) + 1, srcW, o0, srcClamp);
   for (int oy = 0; oy < 2; ++oy) for (int oz = 0; oz < 2; ++oz)
-    tapY[oy + 2 * oz] = probe_axis_tap((8 + 2) * c.nXZ * (py + oy) + (8 + 2) * (pz + oz) + 1, c.H, o1, c.clampSampler);
+    tapY[oy + 2 * oz] = probe_axis_tap((8 + 2) * c.nXZ * (py + oy) + (8 + 2) * (pz + oz) + 1, srcH, o1, srcClamp);
   float sumW = 0.0f; V3 sum = mk3(0.0f);
   // corner order of the source: 000,111,110,100,011,010,001,101 packed as x | y<<1 | z<<2 per nibble
   const uint32_t order = 0x0u | (0x7u << 4) | (0x3u << 8) | (0x1u << 12) | (0x6u << 16) | (0x2u << 20) | (0x4u << 24) | (0x5u << 28);
   for (int k = 0; k < 8; ++k) {
     uint32_t o = (order >> (4 * k)) & 7u; int ox = (int)(o & 1u), oy = (int)((o >> 1) & 1u), oz = (int)((o >> 2) & 1u);
-    V3 probePos = (k == 0) ? base : base + mk3((float)ox, (float)oy, (float)oz) * c.step;
+    V3 probePos = (k == 0) ? base : base + mk3((float)ox, (float)oy, (float)oz) * step;
     V3 tri = mk3(mixf(1.0f - alpha.x, alpha.x, (float)ox), mixf(1.0f - alpha.y, alpha.y, (float)oy), mixf(1.0f - alpha.z, alpha.z, (float)oz));
     float weight = 1.0f;
     V3 toProbe = normalize3(probePos - worldPos);
@@ -781,7 +828,7 @@ HD V3 sample_probe(const TraceCtx& c, V3 worldPos, V3 normal) {
     weight = fmaxf(0.000001f, weight);
     if (weight < 0.2f) weight *= weight * weight * (1.0f / (0.2f * 0.2f));    // dead code kept verbatim (:221-224)
     weight *= tri.x * tri.y * tri.z;
-    V3 irr = atlas_bilinear(c, tapX[ox], tapY[oy + 2 * oz]);
+    V3 irr = (TILES && srcTex >= 0) ? texture_bilinear_taps(c.tex, srcTex, tapX[ox], tapY[oy + 2 * oz]) : atlas_bilinear(c, tapX[ox], tapY[oy + 2 * oz]);
     irr = mk3(sqrtf(irr.x), sqrtf(irr.y), sqrtf(irr.z));
     sum = sum + weight * irr; sumW += weight;
   }
@@ -789,13 +836,14 @@ HD V3 sample_probe(const TraceCtx& c, V3 worldPos, V3 normal) {
   net = net * net;
   return net * .5f * 3.1415926f;
 }
-HD V3 calc_indirect(const TraceCtx& c, V3 normal, V3 albedo, float metallic, float roughness, V3 worldPos, V3 viewPos) {   // :365-388
+template <bool TILES = false>
+HD V3 calc_indirect(const TraceCtx& c, V3 normal, V3 albedo, float metallic, float roughness, V3 worldPos, V3 viewPos, int srcTex = -1) {   // :365-388
   V3 V = normalize3(viewPos - worldPos);
   V3 F0 = mix3(mk3(0.04f), albedo, metallic);
   float rr = roughness * roughness;
   V3 kS = F0 + (max3(mk3(1.0f - rr), F0) - F0) * pow5(clampf(1.0f - fmaxf(dot3(normal, V), 0.0f), 0.0f, 1.0f));   // fresnelSchlickRoughness :93-96
   V3 kD = mk3(1.0f) - kS; kD = kD * (1.0f - metallic);
-  V3 irradiance = sample_probe(c, worldPos, normal);
+  V3 irradiance = sample_probe<TILES>(c, worldPos, normal, srcTex);
   return kD * (irradiance * albedo);
 }
 
@@ -805,7 +853,15 @@ HD V3 calc_indirect(const TraceCtx& c, V3 normal, V3 albedo, float metallic, flo
 struct ConsumerCtx { TraceCtx t; const float4* points; float4* out; V3 viewPos; };
 HD void indirect_diffuse_body(uint32_t i, const ConsumerCtx& c) {
   const float4 a = c.points[3 * (size_t)i], b = c.points[3 * (size_t)i + 1], d = c.points[3 * (size_t)i + 2];
-  const V3 r = calc_indirect(c.t, mk3(a.w, b.x, b.y), mk3(b.z, b.w, d.x), d.y, d.z, mk3(a.x, a.y, a.z), c.viewPos);
+  const V3 wp = mk3(a.x, a.y, a.z);
+  V3 r;
+  if (c.t.tex.tileInfos) {
+    // deferred_tiled.comp:264-296 samples the tile's baked atlas where there is one (the pass with the CLAMP_TO_EDGE probeTex);
+    // mirror_reflections.rchit:105-114 always samples the live atlas
+    int tx, tz;
+    const int src = c.t.clampSampler ? world_pos_to_tile_atlas(c.t, wp, tx, tz) : -1;
+    r = calc_indirect<true>(c.t, mk3(a.w, b.x, b.y), mk3(b.z, b.w, d.x), d.y, d.z, wp, c.viewPos, src);
+  } else r = calc_indirect<false>(c.t, mk3(a.w, b.x, b.y), mk3(b.z, b.w, d.x), d.y, d.z, wp, c.viewPos);
   c.out[i] = make_float4(r.x, r.y, r.z, 0.0f);
 }
 
@@ -898,7 +954,8 @@ HD V3 shade_hit_simple(const TraceCtx& c, const Hit& hit, V3 origin, uint32_t& l
   }
   const uint32_t gate = SPECULAR ? ANEREND_UBO_DDGI_FLAG : ANEREND_UBO_DDGI_MULTI_FLAG;      // mirror_reflections.rchit:105 / rchit:98
   if ((c.uboFlags & gate) == gate)
-    irradiance = irradiance + calc_indirect(c, normal, albedo, metallic, roughness, pos, origin);   // rchit:98-107
+    irradiance = irradiance + (c.tex.tileInfos ? calc_indirect<true>(c, normal, albedo, metallic, roughness, pos, origin)
+                                               : calc_indirect<false>(c, normal, albedo, metallic, roughness, pos, origin));   // rchit:98-107
   hitPos = pos;
   return irradiance + emissive;                                                                      // rchit:109
 }

@@ -27,7 +27,7 @@ namespace ddgi {
 namespace SHADE_NS {
 
 // ------------------------------------------------------------------------------------------------------------
-template <int MINB, bool EXT = false>
+template <int MINB, bool EXT = false, bool TILES = false>
 __global__ void __launch_bounds__(128, MINB) k_shade(const FastCtx c) {
   const TraceCtx& t = c.t;
   const uint32_t nHits = c.qcount[FAST_QC_HITS];
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const FastCtx c) {
     }
     const uint32_t gate = EXT ? ANEREND_UBO_DDGI_FLAG : ANEREND_UBO_DDGI_MULTI_FLAG;      // mirror_reflections.rchit:105 / rchit:98
     if ((t.uboFlags & gate) == gate)
-      irradiance = irradiance + calc_indirect(t, normal, albedo, metallic, roughness, pos, origin);
+      irradiance = irradiance + calc_indirect<TILES>(t, normal, albedo, metallic, roughness, pos, origin);      // live atlas (probeTex), tile placement if TILES
     const V3 rad = irradiance + emissive;
     const size_t o = EXT ? (size_t)idx : ((size_t)layer * P + probe) * t.N + ray;
     const uint32_t alpha = EXT ? (uint32_t)f2h(c.extDist[idx]) : 0x3C00u;                 // SpecularGIRT stores the hit distance (rgen:79)
@@ -82,19 +82,24 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const FastCtx c) {
   }
 }
 
-static cudaError_t launch_shade_ext_impl(const FastCtx& f, cudaStream_t s) {
+// the less common instantiations (SpecularGIRT's external rays, scenes with baked tile atlases): one resident wave of blocks
+template <bool EXT, bool TILES>
+static cudaError_t launch_shade_variant(const FastCtx& f, cudaStream_t s) {
   static int maxBlocks = 0;
   if (!maxBlocks) {
     int dev = 0, sms = 0, nb = 0;
     cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade<8, true>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade<8, EXT, TILES>, 128, 0);
     maxBlocks = sms * (nb > 0 ? nb : 1);
   }
   uint32_t blocks = (f.totalRays + 127u) / 128u;
   if (blocks > (uint32_t)maxBlocks) blocks = (uint32_t)maxBlocks;
   if (blocks == 0) return cudaSuccess;
-  k_shade<8, true><<<blocks, 128, 0, s>>>(f);
+  k_shade<8, EXT, TILES><<<blocks, 128, 0, s>>>(f);
   return cudaGetLastError();
+}
+static cudaError_t launch_shade_ext_impl(const FastCtx& f, cudaStream_t s) {
+  return f.t.tex.tileInfos ? launch_shade_variant<true, true>(f, s) : launch_shade_variant<true, false>(f, s);
 }
 template <int MINB>
 static cudaError_t launch_shade_minb(const FastCtx& f, cudaStream_t s) {
@@ -113,6 +118,7 @@ static cudaError_t launch_shade_minb(const FastCtx& f, cudaStream_t s) {
   return cudaGetLastError();
 }
 static cudaError_t launch_shade_impl(const FastCtx& f, cudaStream_t s) {
+  if (f.t.tex.tileInfos) return launch_shade_variant<false, true>(f, s);
   static int minb = 0;            // register budget of k_shade: resident blocks per SM the compiler must allow
   if (!minb) { const char* e = getenv("DDGI_SHADE_MINB"); minb = e ? atoi(e) : SHADE_MINB_DEFAULT; }   // sweeps only
   switch (minb) {

@@ -53,3 +53,4 @@ MISS = 0xFFFFFFFF
 TEX_RGBA8_UNORM, TEX_RGBA8_SRGB, TEX_RG8_UNORM, TEX_R8_UNORM = 0, 1, 2, 3
 UBO_RT_SHADOWS_FLAG = 1 << 3
 UBO_SPECULAR_GI_FLAG = 1 << 6
+TEX_RGBA16F = 4

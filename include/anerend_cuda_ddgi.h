@@ -142,6 +142,12 @@ int anerend_cuda_ddgi_upload_scene(anerend_ddgi_t* h,
  * on this path: rchit:77 passes a zero tangent).  Sampling: LOD 0, bilinear, REPEAT / CLAMP_TO_EDGE per texture.
  * count = 0 removes all textures. */
 int anerend_cuda_ddgi_upload_textures(anerend_ddgi_t* h, const anerend_texture_desc_t* textures, uint32_t count);
+/* tileInfoBuffer (set 0 binding 14, GPUTileInfo, GpuBuffers.h:74-76): one entry per tile of the 21 x 21 page around the camera
+ * (bindless.glsl:4-5, 291-308); ddgi_atlas_tex = bindless index of the tile's baked atlas (ANEREND_TEX_RGBA16F, what
+ * _download_atlas returned after baking that tile) or -1.  With it, sampleProbe places the grid on the baked tile where there
+ * is one (pbr_light.glsl:251-273) and _indirect_diffuse(clamp_to_edge = 1) samples the baked atlas like the deferred pass
+ * (deferred_tiled.comp:264-296).  count = 0 removes it. */
+int anerend_cuda_ddgi_upload_tile_infos(anerend_ddgi_t* h, const anerend_tile_info_t* tiles, uint32_t count);
 
 /* Binding 0 (scene_ubo.glsl:14-37).  Fields read: cameraPos, lightDir, skyColor, sunIntensity,
  * skyIntensity, flags (DDGI, DDGI_MULTI, RT_ON, BAKE_MODE_ON). */

@@ -72,6 +72,7 @@ ANEREND_STATIC_ASSERT(sizeof(anerend_material_info_t) == 64, "GPUMaterialInfo mu
 #define ANEREND_TEX_RGBA8_SRGB  1u   /* RGBA8_SRGB: rgb decoded to linear before filtering, alpha linear */
 #define ANEREND_TEX_RG8_UNORM   2u   /* RG8_UNORM: (r, g, 0, 1) */
 #define ANEREND_TEX_R8_UNORM    3u   /* R8_UNORM: (r, 0, 0, 1) */
+#define ANEREND_TEX_RGBA16F     4u   /* RGBA16F_SFLOAT: baked DDGI atlases (VulkanRenderer::downloadDDGIAtlas, VulkanRenderer.cpp:2706-2771) */
 typedef struct anerend_texture_desc {
   const void* pixels;            /* width*height texels, rows top to bottom, tightly packed */
   uint32_t width, height;

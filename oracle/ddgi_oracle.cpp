@@ -548,9 +548,10 @@ struct ddgi_oracle {
     for (int c = 0; c < 256; ++c) { float v = (float)c / 255.0f; texLut[c] = toLinear1(v); texLut[256 + c] = v; }
   }
   void texFetch(const Tex& t, int x, int y, float out[4]) const {
-    const uint32_t bpp = t.fmt <= ANEREND_TEX_RGBA8_SRGB ? 4u : (t.fmt == ANEREND_TEX_RG8_UNORM ? 2u : 1u);
+    const uint32_t bpp = t.fmt == ANEREND_TEX_RGBA16F ? 8u : t.fmt <= ANEREND_TEX_RGBA8_SRGB ? 4u : (t.fmt == ANEREND_TEX_RG8_UNORM ? 2u : 1u);
     const uint8_t* q = &t.px[((size_t)y * t.w + (size_t)x) * bpp];
     out[0] = 0.0f; out[1] = 0.0f; out[2] = 0.0f; out[3] = 1.0f;
+    if (t.fmt == ANEREND_TEX_RGBA16F) { uint16_t hh[4]; memcpy(hh, q, 8); for (int k = 0; k < 4; ++k) out[k] = h2f(hh[k]); return; }
     if (t.fmt == ANEREND_TEX_RGBA8_SRGB) { out[0] = texLut[q[0]]; out[1] = texLut[q[1]]; out[2] = texLut[q[2]]; out[3] = texLut[256 + q[3]]; }
     else for (uint32_t k = 0; k < bpp; ++k) out[k] = texLut[256 + q[k]];
   }
@@ -590,14 +591,18 @@ struct ddgi_oracle {
     return t00 * w00 + t10 * w10 + t01 * w01 + t11 * w11;
   }
   // pbr_light.glsl:168-188
+  // probeTex: the live atlas (srcTex < 0) or a bindless texture (a tile's baked atlas, passed by the deferred pass)
+  int srcTex = -1;
   V3 sampleSingleProbe(int pxI, int pyI, int pzI, V3 normal) const {
     int startX = (8 + 2) * pxI + 1, startY = (8 + 2) * nXZ * pyI + (8 + 2) * pzI + 1;
     int endX = startX + 8 - 1, endY = startY + 8 - 1;
-    float tsx = (2.0f * float(startX) + 1.0f) / (2.0f * float(W)), tsy = (2.0f * float(startY) + 1.0f) / (2.0f * float(H));   // pixelToUv, helpers.glsl:1-4
-    float tex = (2.0f * float(endX) + 1.0f) / (2.0f * float(W)), tey = (2.0f * float(endY) + 1.0f) / (2.0f * float(H));
+    const float tw = srcTex >= 0 ? float(textures[(size_t)srcTex].w) : float(W), th = srcTex >= 0 ? float(textures[(size_t)srcTex].h) : float(H);   // textureSize(probeTex, 0)
+    float tsx = (2.0f * float(startX) + 1.0f) / (2.0f * tw), tsy = (2.0f * float(startY) + 1.0f) / (2.0f * th);   // pixelToUv, helpers.glsl:1-4
+    float tex = (2.0f * float(endX) + 1.0f) / (2.0f * tw), tey = (2.0f * float(endY) + 1.0f) / (2.0f * th);
     float oct[2]; octEncode(normalize(normal), oct);
     oct[0] = (oct[0] + 1.0f) * 0.5f; oct[1] = (oct[1] + 1.0f) * 0.5f;
     float cu = tsx + (tex - tsx) * oct[0], cv = tsy + (tey - tsy) * oct[1];
+    if (srcTex >= 0) { float t4[4]; sampleTexture(srcTex, cu, cv, t4); return v3(t4[0], t4[1], t4[2]); }
     return textureBilinear(cu, cv);
   }
   // pbr_light.glsl:190-238
@@ -616,9 +621,25 @@ struct ddgi_oracle {
     return V4{irr.x, irr.y, irr.z, weight};
   }
   // pbr_light.glsl:240-363, live-grid branch (:294-308); no baked tiles (quirk Q5), bake mode out of scope
+  // tileInfoBuffer (bindless.glsl binding 14) + worldPosToTileInfo (bindless.glsl:291-308; only the upper page bounds are checked,
+  // as in the shader; an index outside the uploaded buffer is "no tile"): bindless index of the tile's baked atlas, or -1
+  std::vector<int32_t> tileInfos;
+  int worldPosToTileAtlas(V3 worldPos, int& tx, int& tz) const {
+    if (tileInfos.empty()) return -1;
+    const int R = 10, TS = 32, w = R * 2 + 1;
+    tx = (int)std::floor(worldPos.x / float(TS)); tz = (int)std::floor(worldPos.z / float(TS));
+    int cx = (int)std::floor(ubo.camera_pos[0] / float(TS)), cz = (int)std::floor(ubo.camera_pos[2] / float(TS));
+    if (tx - cx > R || tz - cz > R) return -1;
+    int idx = (tz - cz + R) * w + (tx - cx + R);
+    if (idx < 0 || (size_t)idx >= tileInfos.size()) return -1;
+    int a = tileInfos[(size_t)idx];
+    return (a >= 0 && (size_t)a < textures.size()) ? a : -1;
+  }
   V3 sampleProbe(V3 worldPos, V3 normal) const {
     V3 step = gridStep();
     V3 co = camOffset();
+    { int tx, tz;                                      // pbr_light.glsl:251-273: a baked tile places the grid on the tile
+      if (worldPosToTileAtlas(worldPos, tx, tz) >= 0) { float s = 32.0f / float(nXZ); step = v3(s, 1.0f, s); co = v3(float(tx) * 32.0f, 0.0f, float(tz) * 32.0f); } }
     int px = std::min(std::max((int)std::floor((worldPos.x - co.x) / step.x), 0), nXZ - 1);
     int py = std::min(std::max((int)std::floor(worldPos.y / step.y), 0), nY - 1);
     int pz = std::min(std::max((int)std::floor((worldPos.z - co.z) / step.z), 0), nXZ - 1);
@@ -892,8 +913,8 @@ int ddgi_oracle_upload_scene(ddgi_oracle_t* h,
 int ddgi_oracle_upload_textures(ddgi_oracle_t* h, const anerend_texture_desc_t* tex, uint32_t count) {
   std::vector<ddgi_oracle::Tex> out(count);
   for (uint32_t i = 0; i < count; ++i) {
-    if (!tex[i].pixels || !tex[i].width || !tex[i].height || tex[i].format > ANEREND_TEX_R8_UNORM) { h->err = "bad texture descriptor"; return ANEREND_DDGI_E_INVALID; }
-    size_t bpp = tex[i].format <= ANEREND_TEX_RGBA8_SRGB ? 4 : (tex[i].format == ANEREND_TEX_RG8_UNORM ? 2 : 1);
+    if (!tex[i].pixels || !tex[i].width || !tex[i].height || tex[i].format > ANEREND_TEX_RGBA16F) { h->err = "bad texture descriptor"; return ANEREND_DDGI_E_INVALID; }
+    size_t bpp = tex[i].format == ANEREND_TEX_RGBA16F ? 8 : tex[i].format <= ANEREND_TEX_RGBA8_SRGB ? 4 : (tex[i].format == ANEREND_TEX_RG8_UNORM ? 2 : 1);
     out[i].w = tex[i].width; out[i].h = tex[i].height; out[i].fmt = tex[i].format; out[i].clampEdge = tex[i].clamp_to_edge != 0;
     const uint8_t* p = (const uint8_t*)tex[i].pixels;
     out[i].px.assign(p, p + (size_t)tex[i].width * tex[i].height * bpp);
@@ -1102,10 +1123,17 @@ int ddgi_oracle_indirect_diffuse(ddgi_oracle_t* h, const float* pts, uint32_t co
   h->clampSampler = clampToEdge != 0;
   for (uint32_t i = 0; i < count; ++i) {
     const float* q = pts + 12 * (size_t)i;
+    // deferred_tiled.comp:264-296 passes the tile's baked atlas as probeTex where there is one; mirror_reflections.rchit the live atlas
+    { int tx, tz; h->srcTex = clampToEdge ? h->worldPosToTileAtlas(v3(q[0], q[1], q[2]), tx, tz) : -1; }
     V3 r = h->calcIndirectDiffuseLight(v3(q[3], q[4], q[5]), v3(q[6], q[7], q[8]), q[9], q[10], v3(q[0], q[1], q[2]), v3(vp[0], vp[1], vp[2]));
     out[4 * (size_t)i] = r.x; out[4 * (size_t)i + 1] = r.y; out[4 * (size_t)i + 2] = r.z; out[4 * (size_t)i + 3] = 0.0f;
   }
-  h->clampSampler = false;
+  h->clampSampler = false; h->srcTex = -1;
+  return 0;
+}
+int ddgi_oracle_upload_tile_infos(ddgi_oracle_t* h, const anerend_tile_info_t* tiles, uint32_t count) {
+  h->tileInfos.resize(count);
+  for (uint32_t i = 0; i < count; ++i) h->tileInfos[i] = tiles[i].ddgi_atlas_tex;
   return 0;
 }
 int ddgi_oracle_intersect(const float o[3], const float d[3], const float a[3], const float b[3], const float c[3],

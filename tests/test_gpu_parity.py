@@ -546,3 +546,54 @@ def test_reference_default_grid_matches_oracle(oracle, make_gpu):
     so, sg = o.stats(), g.stats()
     o.close()
     g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernels", ["wavefront", "simple"])
+def test_baked_tile_atlases_match_oracle_bit_for_bit(kernels, oracle, make_gpu):
+    """SURVEY §8f N4 / quirk Q5 through the C ABI: tileInfoBuffer + a baked RGBA16F atlas; probe update (tile placement, live
+    atlas), SpecularGIRT, and the deferred-pass consumer (baked atlas) against the oracle."""
+    import copy
+    from tests.consumer_points import surface_points
+    from tests import shadow_inputs as SI
+    nxz, ny, nr = 8, 4, 64
+    scene = scenes.cornell_box(grid=(nxz, ny, nr), wall_res=10, box_res=3)
+    flags = L.FLAG_POINT_LIGHTS | KERNEL_FLAGS[kernels]
+
+    def bake(make):
+        h = make(make_params(nxz, ny, nr, flags=flags))
+        rots = parity.setup_pair(scene, (h,), seed=11)
+        u = scene.ubo.copy(); u["flags"] |= L.UBO_BAKE_MODE_ON_FLAG; u["bake_tile_info"][0] = (0, 0, 32, 0)
+        h.set_scene_ubo(u)
+        for _ in range(3):
+            h.update(-1, rots)
+        a = h.download_atlas().copy()
+        h.close()
+        return a
+    baked = bake(oracle.Oracle)
+    assert np.array_equal(baked, bake(make_gpu))
+    tiled = copy.copy(scene)
+    tiled.textures = [(baked.view(np.uint8).reshape(baked.shape[0], baked.shape[1], 8), L.TEX_RGBA16F, False)]
+    tiles = np.full(21 * 21, -1, np.int32); tiles[10 * 21 + 10] = 0
+    p = make_params(nxz, ny, nr, flags=ALL | KERNEL_FLAGS[kernels])
+    o, g = oracle.Oracle(p), make_gpu(p)
+    rots = parity.setup_pair(tiled, (o, g), seed=3)
+    for h in (o, g):
+        h.upload_tile_infos(tiles)
+    for it in range(2):
+        for h in (o, g):
+            h.update(-1, rots)
+        _check_update(o, g, ny)
+        assert np.array_equal(o.download_atlas(), g.download_atlas()), "atlas is not bit-identical"
+    pts = surface_points(5000, nxz, ny, seed=21); pts[:, 0] = np.abs(pts[:, 0]); pts[:2000, 2] = np.abs(pts[:2000, 2])
+    for clamp in (True, False):
+        ro, rg = o.indirect_diffuse(pts, (0.0, 1.0, 0.0), clamp), g.indirect_diffuse(pts, (0.0, 1.0, 0.0), clamp)
+        assert np.array_equal(ro.view(np.uint32), rg.view(np.uint32))
+    W, H = 96, 64
+    depth, geom0 = SI.depth_buffer(W, H, seed=3), SI.gbuffer_normals(W, H, seed=4)
+    ubo = SI.with_specular_camera(scene.ubo, SI.ortho_inv_view_proj(5.0, 5.0, 8.0), W, H)
+    for h in (o, g):
+        h.set_scene_ubo(ubo)
+    assert np.array_equal(o.specular_gi(depth, geom0), g.specular_gi(depth, geom0))
+    o.close()
+    g.close()

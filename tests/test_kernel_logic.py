@@ -317,3 +317,60 @@ def test_replacing_textures_after_the_scene_is_refused(make_emu):
     e.build_accel()
     e.update(-1, rots)
     e.close()
+
+
+def _bake_tile_atlas(make_handle, scene, grid, tile, updates=3):
+    """Bakes tile `tile` (x, z) of size 32 with a handle in bake mode; returns the atlas as an RGBA16F texture."""
+    nxz, ny, nr = grid
+    h = make_handle(make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS))
+    rots = parity.setup_pair(scene, (h,), seed=11)
+    u = scene.ubo.copy()
+    u["flags"] |= L.UBO_BAKE_MODE_ON_FLAG
+    u["bake_tile_info"][0] = (tile[0], tile[1], 32, 0)
+    h.set_scene_ubo(u)
+    for _ in range(updates):
+        h.update(-1, rots)
+    atlas = h.download_atlas().copy()
+    h.close()
+    return atlas
+
+
+def test_baked_tile_atlases_match_oracle(oracle, make_emu):
+    """a tileInfoBuffer with a baked atlas.  sampleProbe places the grid on the baked tile
+    (pbr_light.glsl:251-273) for the probe hit shader (which still samples the live atlas), and the deferred-pass consumer
+    samples the tile's baked atlas (deferred_tiled.comp:264-296); hit shading, atlas and consumer output bit-identical."""
+    import copy
+    from tests.consumer_points import surface_points
+    scene, grid = SCENES["cornell"]()
+    nxz, ny, nr = grid
+    baked = _bake_tile_atlas(oracle.Oracle, scene, grid, (0, 0))
+    assert np.array_equal(baked, _bake_tile_atlas(make_emu, scene, grid, (0, 0)))
+    tiled = copy.copy(scene)
+    tiled.textures = list(scene.textures) + [(baked.view(np.uint8).reshape(baked.shape[0], baked.shape[1], 8), L.TEX_RGBA16F, False)]
+    tiles = np.full(21 * 21, -1, np.int32)
+    tiles[10 * 21 + 10] = len(tiled.textures) - 1             # the camera's own tile (0, 0): x, z in [0, 32)
+    p = make_params(nxz, ny, nr, flags=ALL)
+    o, e, plain = oracle.Oracle(p), make_emu(p), make_emu(p)
+    rots = parity.setup_pair(tiled, (o, e), seed=3)
+    parity.setup_pair(scene, (plain,), seed=3)
+    for h in (o, e):
+        h.upload_tile_infos(tiles)
+    for it in range(2):
+        for h in (o, e, plain):
+            h.update(-1, rots)
+        for layer in range(ny):
+            parity.compare_records(o.download_ray_records(layer), e.download_ray_records(layer))
+        assert np.array_equal(o.download_atlas(), e.download_atlas())
+    assert not np.array_equal(e.download_atlas(), plain.download_atlas())          # the tile placement changes the multi-bounce term
+    pts = surface_points(2000, nxz, ny, seed=21)
+    pts[:, 0] = np.abs(pts[:, 0]); pts[:500, 2] = np.abs(pts[:500, 2])              # many points inside the baked tile
+    view = (0.0, 1.0, 0.0)
+    for clamp in (True, False):
+        ro, re = o.indirect_diffuse(pts, view, clamp), e.indirect_diffuse(pts, view, clamp)
+        assert np.array_equal(ro.view(np.uint32), re.view(np.uint32))
+        assert not np.array_equal(re, plain.indirect_diffuse(pts, view, clamp))
+    for h in (o, e):
+        h.upload_tile_infos([])                                                       # removing the buffer restores the live placement
+    assert np.array_equal(e.indirect_diffuse(pts, view, False)[:, :3] >= 0, np.ones((2000, 3), bool))
+    for h in (o, e, plain):
+        h.close()

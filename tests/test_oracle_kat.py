@@ -660,3 +660,36 @@ def test_indirect_diffuse_against_a_float64_restatement(oracle):
         close = np.isclose(got, want, rtol=2e-3, atol=1e-5).all(axis=1)
         assert close.mean() >= 0.97, (clamp, close.mean(), got[~close][:2], want[~close][:2])    # a texel-boundary tap may land one texel off in float64
     o.close()
+
+
+def test_tile_lookup_and_baked_atlas_known_answers(oracle):
+    """KATs for the tile page (bindless.glsl:4-5, 291-308) and the baked-atlas branch of sampleProbe (pbr_light.glsl:251-273):
+    a uniform baked atlas B on one tile and a uniform live atlas A.  The deferred-pass consumer returns kD*albedo*B*pi/2 for
+    points on that tile and kD*albedo*A*pi/2 elsewhere; the REPEAT-sampler consumer (SpecularGIRT) always reads the live atlas."""
+    n_xz, n_y = 4, 2
+    o = oracle.Oracle(make_params(n_xz, n_y, 64))
+    s = scenes.empty_scene(grid=(n_xz, n_y, 64))
+    W, H = 10 * n_xz, 10 * n_xz * n_y
+    def uniform(v):
+        a = np.zeros((H, W, 4), np.float16); a[..., :3] = v; a[..., 3] = 1.0
+        return a
+    A, B = 0.25, 4.0
+    o.upload_textures([(uniform(B).view(np.uint8).reshape(H, W, 8), L.TEX_RGBA16F, False)])
+    o.set_scene_ubo(s.with_camera((40.0, 1.0, 10.0)))                # camera tile (1, 0)
+    o.upload_atlas(uniform(A).view(np.uint16))
+    tiles = np.full(21 * 21, -1, np.int32)
+    tiles[(0 - 0 + 10) * 21 + (2 - 1 + 10)] = 0                       # world tile (2, 0): x in [64, 96), z in [0, 32)
+    o.upload_tile_infos(tiles)
+    pts = np.zeros((3, 12), np.float32)
+    pts[:, 0:3] = [(70.0, 1.0, 5.0), (40.5, 1.0, 10.5), (64.0 - 1e-3, 1.0, 5.0)]       # on the baked tile, on the camera's tile, just outside
+    pts[:, 3:6] = (0, 1, 0); pts[:, 6:9] = 0.5; pts[:, 10] = 1.0
+    view = np.array([40.0, 6.0, 10.0], np.float32)
+    def want(i, Lv):
+        V = (view - pts[i, 0:3]) / np.linalg.norm(view - pts[i, 0:3])
+        kS = 0.04 + (max(1.0 - 1.0, 0.04) - 0.04) * (1.0 - max(float(V[1]), 0.0)) ** 5
+        return (1 - kS) * Lv * 0.5 * 3.1415926 * 0.5
+    got = o.indirect_diffuse(pts, view, True)[:, 0]
+    assert np.allclose(got, [want(0, B), want(1, A), want(2, A)], rtol=2e-3)
+    got = o.indirect_diffuse(pts, view, False)[:, 0]
+    assert np.allclose(got, [want(0, A), want(1, A), want(2, A)], rtol=2e-3)
+    o.close()
