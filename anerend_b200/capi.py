@@ -131,6 +131,11 @@ class DdgiHandle:
             arr[i].width, arr[i].height, arr[i].format, arr[i].clamp_to_edge = px.shape[1], px.shape[0], int(fmt), 1 if clamp else 0
         self._call("upload_textures", arr, C.c_uint32(n))
 
+    def update_vertices(self, vertices, first=0):
+        """Overwrites a range of the giga vertex buffer (deforming / skinned meshes); follow with refit_accel()."""
+        v = _c(vertices, L.VERTEX)
+        self._call("update_vertices", _ptr(v), C.c_uint32(first), C.c_uint32(len(v)))
+
     def upload_tile_infos(self, atlas_indices):
         """tileInfoBuffer: bindless index of each paged tile's baked atlas (-1 = none), 21 x 21 entries around the camera."""
         arr = _c(atlas_indices, np.int32).reshape(-1)

@@ -97,6 +97,7 @@ struct anerend_ddgi {
   int32_t* dTileInfos = nullptr; uint32_t numTiles = 0;     // tileInfoBuffer (baked atlases of the paged tiles)
   DTexture* dTextures = nullptr; uint8_t* dTexPool = nullptr; float* dSrgbLut = nullptr; uint32_t numTextures = 0;
   std::vector<DTexture> textures; bool texturedScene = false, emissiveTextures = false;
+  bool verticesDirty = false;      // update_vertices since the last build / refit
   bool texturesStale = false;      // the texture array was replaced after the scene that refers to it was validated
   float4* dShadeUV = nullptr; float4* dEmisTex = nullptr;
   // ShadowRT scratch (pixels): staged positions, visibility words, ray queue, counters
@@ -322,7 +323,7 @@ int buildAccel(anerend_ddgi* h) {
   if (counters[1] != n) return fail(h, ANEREND_DDGI_E_CUDA, "bvh8 collapse lost triangles");
   if (depth > DDGI_STACK) return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "BVH8 deeper than the traversal stack");
   h->accelMs = be.elapsed(4, 5);
-  h->haveAccel = true;
+  h->haveAccel = true; h->verticesDirty = false;
   return 0;
 }
 
@@ -331,6 +332,7 @@ int refitAccel(anerend_ddgi* h) {
   if (h->numTris == 0) return 0;
   BuildCtx c = buildCtx(h);
   c.sceneBounds = nullptr;
+  if (h->verticesDirty) { c.shadeTris = h->dShadeTris; c.shadeUV = h->dShadeUV; h->verticesDirty = false; }   // deformed meshes: refresh the shading records too
   be.mark(4);
   DDGI_LAUNCH(be, k_inst_xform, inst_xform_body, (uint32_t)h->instances.size(), c, 128);
   DDGI_LAUNCH(be, k_flatten_scene, flatten_tri_body, h->numTris, c, 256);
@@ -861,6 +863,24 @@ static int refitCommon(anerend_ddgi_t* h) {
   for (size_t i = 0; same && i < inst.size(); ++i) same = inst[i].renderable == h->instances[i].renderable && inst[i].mesh == h->instances[i].mesh && inst[i].material == h->instances[i].material;
   if (!same) { h->haveAccel = false; return fail(h, ANEREND_DDGI_E_STATE, "visibility changed: rebuild required"); }
   return refitAccel(h);
+}
+// Deforming geometry (skinned meshes: the reference re-skins into the giga vertex buffer every frame and refits the BLAS,
+// UpdateBlasPass.cpp:60-175, VulkanRenderer.cpp:967-1143): refresh a vertex range, then _refit_accel — the topology of the
+// hierarchy is kept, triangles, boxes and the per-triangle shading records are recomputed from the new vertices.
+int DDGI_API(update_vertices)(anerend_ddgi_t* h, const anerend_vertex_t* vertices, uint32_t first, uint32_t count) {
+  if (!h->haveScene) return fail(h, ANEREND_DDGI_E_STATE, "update_vertices before upload_scene");
+  if (!vertices || (uint64_t)first + count > h->numVertices) return fail(h, ANEREND_DDGI_E_INVALID, "vertex range out of bounds");
+  BE_CHECK(h, h->be.sync());
+  BE_CHECK(h, h->be.h2d(h->dVertices + first, vertices, (size_t)count * sizeof(anerend_vertex_t)));
+  h->verticesDirty = true;
+  return 0;
+}
+int DDGI_API(update_vertices_device)(anerend_ddgi_t* h, const void* dVertices, uint32_t first, uint32_t count) {
+  if (!h->haveScene) return fail(h, ANEREND_DDGI_E_STATE, "update_vertices before upload_scene");
+  if (!dVertices || (uint64_t)first + count > h->numVertices) return fail(h, ANEREND_DDGI_E_INVALID, "vertex range out of bounds");
+  BE_CHECK(h, h->be.d2d(h->dVertices + first, dVertices, (size_t)count * sizeof(anerend_vertex_t)));
+  h->verticesDirty = true;
+  return 0;
 }
 int DDGI_API(refit_accel)(anerend_ddgi_t* h, const anerend_renderable_t* renderables, uint32_t nr) {
   if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "refit before build_accel");

@@ -156,6 +156,11 @@ int anerend_cuda_ddgi_set_scene_ubo(anerend_ddgi_t* h, const anerend_scene_ubo_t
 /* Replaces tlas_update.comp + the TLAS/BLAS builds (UpdateTLASPass.cpp:128-248, VulkanRenderer.cpp:1267-1417):
  * instance selection (visible bit set, cull bit clear), flatten to world-space triangles, LBVH, BVH8. */
 int anerend_cuda_ddgi_build_accel(anerend_ddgi_t* h);
+/* Deforming geometry (skinned meshes; UpdateBlasPass.cpp:60-175, VulkanRenderer.cpp:967-1143): overwrite `count` vertices of
+ * the giga vertex buffer starting at `first` (host pointer, or a device pointer for a buffer the skinning pass wrote), then call
+ * _refit_accel: the hierarchy's topology is kept, triangles, boxes and shading records follow the new vertices. */
+int anerend_cuda_ddgi_update_vertices(anerend_ddgi_t* h, const anerend_vertex_t* vertices, uint32_t first, uint32_t count);
+int anerend_cuda_ddgi_update_vertices_device(anerend_ddgi_t* h, const void* d_vertices, uint32_t first, uint32_t count);
 /* Moving nodes: new renderable buffer (same count, same visibility) -> re-flatten + bottom-up refit.
  * renderables may be NULL to refit with the current buffer.  `_device` takes a device pointer (the
  * reference's RenderableBuffer is GPU-written earlier in the frame, cull.comp:303). */

@@ -932,6 +932,11 @@ int ddgi_oracle_build_accel(ddgi_oracle_t* h) {
   int rc = h->buildInstances(); if (rc) return rc;
   h->bvh.build(h->tris); h->haveAccel = true; return 0;
 }
+int ddgi_oracle_update_vertices(ddgi_oracle_t* h, const anerend_vertex_t* v, uint32_t first, uint32_t count) {
+  if (!v || (size_t)first + count > h->vertices.size()) { h->err = "vertex range out of bounds"; return ANEREND_DDGI_E_INVALID; }
+  std::copy(v, v + count, h->vertices.begin() + first);
+  return 0;
+}
 int ddgi_oracle_refit_accel(ddgi_oracle_t* h, const anerend_renderable_t* r, uint32_t n) {
   if (!h->haveAccel) { h->err = "refit before build_accel"; return ANEREND_DDGI_E_STATE; }
   if (r) { if (n != h->renderables.size()) { h->err = "renderable count changed"; return ANEREND_DDGI_E_INVALID; } h->renderables.assign(r, r + n); }

@@ -41,6 +41,7 @@ int ddgi_oracle_upload_scene(ddgi_oracle_t* h,
     const uint32_t* model_indices, uint32_t num_model_indices,
     const uint32_t* material_indices, uint32_t num_material_indices,
     const anerend_light_t* lights, uint32_t num_lights);
+int ddgi_oracle_update_vertices(ddgi_oracle_t* h, const anerend_vertex_t* vertices, uint32_t first, uint32_t count);
 int ddgi_oracle_upload_tile_infos(ddgi_oracle_t* h, const anerend_tile_info_t* tiles, uint32_t count);
 int ddgi_oracle_sample_texture(ddgi_oracle_t* h, int32_t index, float u, float v, float out_rgba[4]);
 int ddgi_oracle_upload_textures(ddgi_oracle_t* h, const anerend_texture_desc_t* textures, uint32_t count);

@@ -597,3 +597,30 @@ def test_baked_tile_atlases_match_oracle_bit_for_bit(kernels, oracle, make_gpu):
     assert np.array_equal(o.specular_gi(depth, geom0), g.specular_gi(depth, geom0))
     o.close()
     g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernels", ["wavefront", "simple"])
+def test_deforming_mesh_update_vertices_and_refit(kernels, oracle, make_gpu):
+    """Skinned / deforming meshes through the C ABI: update_vertices + refit_accel; the wavefront path's per-triangle shading
+    and uv records are refreshed by the refit."""
+    scene, (nxz, ny, nr) = SCENES["textured"]()
+    p = make_params(nxz, ny, nr, flags=ALL | KERNEL_FLAGS[kernels])
+    o, g = oracle.Oracle(p), make_gpu(p)
+    rots = parity.setup_pair(scene, (o, g), seed=3)
+    rng = np.random.RandomState(4)
+    nv = len(scene.vertices)
+    first, count = nv // 4, nv // 2
+    for it in range(3):
+        v = scene.vertices[first:first + count].copy()
+        v["pos"] += rng.uniform(-0.03, 0.03, v["pos"].shape).astype(np.float32) * (it + 1)
+        v["normal"] += rng.uniform(-0.2, 0.2, v["normal"].shape).astype(np.float32)
+        v["uv"] += np.float32(0.1 * (it + 1))
+        for h in (o, g):
+            h.update_vertices(v, first)
+            h.refit_accel()
+            h.update(-1, rots)
+        _check_update(o, g, ny)
+        assert np.array_equal(o.download_atlas(), g.download_atlas()), "atlas is not bit-identical"
+    o.close()
+    g.close()

@@ -374,3 +374,31 @@ def test_baked_tile_atlases_match_oracle(oracle, make_emu):
     assert np.array_equal(e.indirect_diffuse(pts, view, False)[:, :3] >= 0, np.ones((2000, 3), bool))
     for h in (o, e, plain):
         h.close()
+
+
+def test_deforming_mesh_update_vertices_and_refit(oracle, make_emu):
+    """Skinned / deforming meshes (the refit half): new vertex positions, normals and uvs into the giga vertex
+    buffer, then refit — triangles, boxes AND shading records follow; three deformation steps bit-identical to the oracle."""
+    scene, (nxz, ny, nr) = SCENES["textured"]()
+    p = make_params(nxz, ny, nr, flags=ALL)
+    o, e = oracle.Oracle(p), make_emu(p)
+    rots = parity.setup_pair(scene, (o, e), seed=3)
+    rng = np.random.RandomState(4)
+    nv = len(scene.vertices)
+    first, count = nv // 4, nv // 2
+    for it in range(3):
+        v = scene.vertices[first:first + count].copy()
+        v["pos"] += rng.uniform(-0.03, 0.03, v["pos"].shape).astype(np.float32) * (it + 1)
+        v["normal"] += rng.uniform(-0.2, 0.2, v["normal"].shape).astype(np.float32)
+        v["uv"] += np.float32(0.1 * (it + 1))
+        for h in (o, e):
+            h.update_vertices(v, first)
+            h.refit_accel()
+            h.update(-1, rots)
+        for layer in range(ny):
+            parity.compare_records(o.download_ray_records(layer), e.download_ray_records(layer))
+        assert np.array_equal(o.download_atlas(), e.download_atlas())
+    with pytest.raises(Exception):
+        e.update_vertices(scene.vertices, 1)                      # range runs past the buffer
+    o.close()
+    e.close()
