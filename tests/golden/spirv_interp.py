@@ -58,7 +58,7 @@ class Module:
         w = struct.unpack("<%dI" % (len(data) // 4), data)
         assert w[0] == 0x07230203
         self.types, self.consts, self.names, self.member_names, self.decor = {}, {}, {}, {}, {}
-        self.globals, self.functions, self.entry = {}, {}, None
+        self.globals, self.functions, self.entry, self.global_init = {}, {}, None, {}
         i, cur = 5, None
         while i < len(w):
             op, wc = w[i] & 0xFFFF, w[i] >> 16
@@ -85,6 +85,14 @@ class Module:
                 self.types[a[0]] = ("mat", a[1], a[2])
             elif op == 25:
                 self.types[a[0]] = ("image",)
+            elif op == 26:
+                self.types[a[0]] = ("sampler",)
+            elif op == 27:
+                self.types[a[0]] = ("image",)                      # sampled image: bound as one sampler object
+            elif op == 29:
+                self.types[a[0]] = ("rtarray", a[1])
+            elif op == 5341:
+                self.types[a[0]] = ("accel",)
             elif op == 28:
                 self.types[a[0]] = ("array", a[1], a[2])
             elif op == 30:
@@ -106,6 +114,8 @@ class Module:
                 self.consts[a[1]] = self.zero(a[0])
             elif op == 59 and cur is None:
                 self.globals[a[1]] = (a[0], a[2])                  # result type (pointer), storage class
+                if len(a) > 3:
+                    self.global_init[a[1]] = a[3]
             elif op == 54:
                 cur = {"id": a[1], "params": [], "blocks": {}, "order": [], "type": a[0]}
                 self.functions[a[1]] = cur
@@ -143,6 +153,10 @@ class Module:
             return [self.zero(t[1]) for _ in range(self.consts[t[2]])]
         if t[0] == "struct":
             return [self.zero(m) for m in t[1]]
+        if t[0] == "rtarray":
+            return []
+        if t[0] in ("image", "sampler", "accel"):
+            return None
         raise NotImplementedError(t)
 
     def struct_member(self, struct_type_id, name):
@@ -160,6 +174,7 @@ class Invocation:
     def __init__(self, module, bind):
         self.m = module
         self.g = {}
+        self.trace = bind.get("traceRay")                                # callable(origin, direction, tmin, tmax, payload Ptr)
         for gid, (pty, storage) in module.globals.items():
             name = module.names.get(gid, "")
             pointee = module.types[pty][2]
@@ -167,8 +182,11 @@ class Invocation:
                 val = bind[name]
             elif any(d[0] == 11 and d[1] == 28 for d in module.decor.get(gid, [])):      # BuiltIn GlobalInvocationId
                 val = bind["gl_GlobalInvocationID"]
-            elif module.types[pointee][0] == "image":
-                raise KeyError(f"image {name} not bound")
+            elif pointee in module.types and module.types[pointee][0] == "struct" and len(module.types[pointee][1]) == 1 and \
+                    module.types[module.types[pointee][1][0]][0] == "rtarray":
+                val = [[]]                                               # an unbound storage buffer: never indexed
+            elif gid in module.global_init:
+                val = _copy(module.consts[module.global_init[gid]])
             else:
                 val = module.zero(pointee)
             self.g[gid] = Ptr([val], (0,))
@@ -271,6 +289,34 @@ class Invocation:
                             acc = f32(acc + f32(x[k] * x[k]))
                         inv = f32(f32(1.0) / f32(np.sqrt(acc)))
                         v[a[1]] = [f32(c * inv) for c in x]
+                    elif inst == 8:
+                        v[a[1]] = _map(lambda x: f32(np.floor(x)), ops[0])
+                    elif inst == 26:
+                        v[a[1]] = _map(lambda x, y: f32(np.power(f32(x), f32(y))), ops[0], ops[1])
+                    elif inst == 31:
+                        v[a[1]] = _map(lambda x: f32(np.sqrt(f32(x))), ops[0])
+                    elif inst == 37:
+                        v[a[1]] = _map(lambda x, y: f32(min(x, y)), ops[0], ops[1])
+                    elif inst == 43:                                # FClamp = min(max(x, lo), hi)
+                        v[a[1]] = _map(lambda x, lo, hi: f32(min(max(x, lo), hi)), ops[0], ops[1], ops[2])
+                    elif inst == 45:                                # SClamp
+                        v[a[1]] = _map(lambda x, lo, hi: _s32(min(max(_s32(x), _s32(lo)), _s32(hi))), ops[0], ops[1], ops[2])
+                    elif inst == 46:                                # FMix = x * (1 - a) + y * a
+                        v[a[1]] = _map(lambda x, y, t: f32(f32(x * f32(f32(1.0) - t)) + f32(y * t)), ops[0], ops[1], ops[2])
+                    elif inst == 67:                                # Distance
+                        d = [f32(p - q) for p, q in zip(ops[0], ops[1])]
+                        v[a[1]] = f32(np.sqrt(_dot(d, d)))
+                    elif inst == 66:
+                        v[a[1]] = f32(np.sqrt(_dot(ops[0], ops[0])))
+                    elif inst == 71:                                # Reflect = I - 2 dot(N, I) N
+                        dn = f32(f32(2.0) * _dot(ops[1], ops[0]))
+                        v[a[1]] = [f32(i - f32(dn * n)) for i, n in zip(ops[0], ops[1])]
+                    elif inst == 13:
+                        v[a[1]] = _map(lambda x: f32(np.sin(f32(x))), ops[0])
+                    elif inst == 14:
+                        v[a[1]] = _map(lambda x: f32(np.cos(f32(x))), ops[0])
+                    elif inst == 17:
+                        v[a[1]] = _map(lambda x: f32(np.arccos(f32(x))), ops[0])
                     else:
                         raise NotImplementedError(f"GLSL.std.450 {inst}")
                 elif op == 172:
@@ -296,6 +342,48 @@ class Invocation:
                     v[a[1]] = [xx if cc else yy for cc, xx, yy in zip(c, x, y)] if isinstance(c, list) else (x if c else y)
                 elif op == 199:
                     v[a[1]] = _map(lambda x, y: _u32(x) & _u32(y), val(a[2]), val(a[3]))
+                elif op in (83, 400):                               # OpCopyObject / OpCopyLogical
+                    v[a[1]] = _copy(val(a[2]))
+                elif op == 88:                                      # OpImageSampleExplicitLod (Lod operand)
+                    assert a[4] == 2, "only the Lod image operand is supported"
+                    v[a[1]] = [f32(c) for c in val(a[2]).sample_lod([f32(c) for c in val(a[3])], f32(val(a[5])))]
+                elif op == 100:                                     # OpImage
+                    v[a[1]] = val(a[2])
+                elif op == 103:                                     # OpImageQuerySizeLod
+                    v[a[1]] = [int(c) for c in val(a[2]).size(int(val(a[3])))]
+                elif op == 110:
+                    v[a[1]] = _map(lambda x: _s32(int(np.trunc(x))), val(a[2]))
+                elif op == 144:                                     # OpVectorTimesMatrix: result[c] = dot(v, column c)
+                    vec, mat = val(a[2]), val(a[3])
+                    v[a[1]] = [_dot(vec, col) for col in mat]
+                elif op == 145:                                     # OpMatrixTimesVector: sum_c column c * v[c], left to right
+                    mat, vec = val(a[2]), val(a[3])
+                    out = [f32(mat[0][r] * vec[0]) for r in range(len(mat[0]))]
+                    for c2 in range(1, len(mat)):
+                        out = [f32(out[r] + f32(mat[c2][r] * vec[c2])) for r in range(len(out))]
+                    v[a[1]] = out
+                elif op == 154:
+                    v[a[1]] = any(val(a[2]))
+                elif op == 171:
+                    v[a[1]] = _map(lambda x, y: _u32(x) != _u32(y), val(a[2]), val(a[3]))
+                elif op == 173:
+                    v[a[1]] = _map(lambda x, y: _s32(x) > _s32(y), val(a[2]), val(a[3]))
+                elif op == 175:
+                    v[a[1]] = _map(lambda x, y: _s32(x) >= _s32(y), val(a[2]), val(a[3]))
+                elif op in (182, 183):
+                    v[a[1]] = _map(lambda x, y: bool(x != y), val(a[2]), val(a[3]))
+                elif op == 180:
+                    v[a[1]] = _map(lambda x, y: bool(x == y), val(a[2]), val(a[3]))
+                elif op == 188:
+                    v[a[1]] = _map(lambda x, y: bool(x <= y), val(a[2]), val(a[3]))
+                elif op in (202, 203):                              # OpBitFieldSExtract / UExtract
+                    base, off, cnt = _u32(val(a[2])), int(val(a[3])), int(val(a[4]))
+                    bits = (base >> off) & ((1 << cnt) - 1) if cnt else 0
+                    if op == 202 and cnt and bits & (1 << (cnt - 1)):
+                        bits -= 1 << cnt
+                    v[a[1]] = _s32(bits) if op == 202 else _u32(bits)
+                elif op == 4445:                                    # OpTraceRayKHR
+                    self.trace([f32(c) for c in val(a[6])], [f32(c) for c in val(a[8])], f32(val(a[7])), f32(val(a[9])), val(a[10]))
                 elif op == 98:                                      # OpImageRead
                     v[a[1]] = [f32(c) for c in val(a[2]).read([_s32(c) for c in val(a[3])])]
                 elif op == 99:                                      # OpImageWrite
@@ -307,6 +395,13 @@ class Invocation:
             if nxt is None:
                 raise RuntimeError("block fell through")
             prev, label = label, nxt
+
+
+def _dot(x, y):
+    acc = f32(x[0] * y[0])
+    for k in range(1, len(x)):
+        acc = f32(acc + f32(x[k] * y[k]))
+    return acc
 
 
 def _is_signed(m, ty):

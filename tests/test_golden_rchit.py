@@ -1,0 +1,43 @@
+"""The oracle's hit shading against the REFERENCE'S OWN COMPILED HIT SHADER.
+
+tests/golden/rchit_golden.npz holds, for 96 hits of a textured test scene on the reference's native 64 x 8 x 64 probe grid, the
+payload that assets/irradiance_probe_update_rchit.spv (the binary the renderer loads) produces when it is executed with the small
+SPIR-V interpreter tests/golden/spirv_interp.py (generator: tests/golden/make_rchit_golden.py, run in the build container where
+the reference is mounted).  The compiled code covers the vertex fetch and interpolation, the normal transform, toLinear,
+getSurfaceDataFromMat with its texture taps, calcLight, calcIndirectDiffuseLight / sampleProbe / weightProbe / sampleSingleProbe /
+octEncode against the previous atlas, and the emissive term; the interpreter is handed what the driver would provide (the hit,
+the shadow-ray result, bilinear sampling as DESIGN.md defines it).  Multi-bounce is on, so the previous atlas matters.
+The CUDA kernels are held to the oracle bit for bit by the -m gpu tests."""
+import os
+
+import numpy as np
+
+from anerend_b200 import layouts as L, make_params, scenes
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rchit_golden.npz"))
+
+
+def test_oracle_hit_shading_equals_the_compiled_reference_shader(oracle):
+    nxz, ny, nr = (int(v) for v in G["grid"])
+    scene = scenes.textured_soup(51, grid=(nxz, ny, nr))
+    o = oracle.Oracle(make_params(nxz, ny, nr, flags=L.FLAG_RAY_RECORDS))      # the faithful subset: sun only, every sun shadow ray traced
+    o.set_threads(0)
+    o.upload_scene(scene); o.set_scene_ubo(scene.ubo); o.build_accel()
+    rots = o.rotations(scenes.rotation_sequence(3, ny))
+    o.update(-1, rots)
+    o.update(-1, rots)                          # these hits are shaded against the atlas of the first update
+    recs = {}
+    got = np.zeros_like(G["irradiance"])
+    for k, (layer, probe, ray) in enumerate(G["rays"]):
+        if layer not in recs:
+            recs[int(layer)] = o.download_ray_records(int(layer))
+        r = recs[int(layer)][probe, ray]
+        assert (int(r["prim"]), float(r["u"]), float(r["v"])) == tuple(G["prim_uv"][k]) and (int(r["lit_mask"]) & 1) == G["lit"][k]
+        got[k] = r["radiance"]
+    o.close()
+    want = G["irradiance"]
+    assert want.max() > 1.0 and (want > 0).all(axis=1).mean() > 0.9 and len(set(G["lit"])) == 2       # a non-trivial sample: lit and shadowed hits
+    rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-6)
+    # the only operations not reproduced bit for bit are pow() calls (numpy's powf in the interpreter, libm in the oracle)
+    assert rel.max() <= 2e-6, f"max relative difference {rel.max():.3e}"
+    assert (got.view(np.uint32) == want.view(np.uint32)).mean() > 0.9
