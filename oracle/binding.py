@@ -70,6 +70,12 @@ class Oracle(DdgiHandle):
                    f3(view_pos), out)
         return np.array(out[:], np.float32)
 
+    def probe_ray(self, layer, probe, ray, rot):
+        """(origin, direction, miss radiance) of one launch pixel, from the functions trace_layer uses (rgen:51-87, rmiss:17-21)."""
+        o, d, m = (C.c_float * 3)(), (C.c_float * 3)(), (C.c_float * 3)()
+        r = np.ascontiguousarray(rot, np.float32).reshape(16)
+        self._call("probe_ray", C.c_int32(layer), C.c_int32(probe), C.c_int32(ray), r.ctypes.data_as(C.c_void_p), o, d, m)
+        return np.array(o[:], np.float32), np.array(d[:], np.float32), np.array(m[:], np.float32)
 
 # ---- single shader functions (KATs) ----------------------------------------------------------------
 def _f(n, v):

@@ -753,6 +753,16 @@ struct ddgi_oracle {
     return irradiance;
   }
 
+  // rgen:51-83: probe (probeX, layer, probeZ) of the launch pixel -> ray origin
+  V3 probeOrigin(int layer, int probe) const {
+    int probeX = probe % nXZ, probeZ = probe / nXZ;
+    return v3(float(probeX), float(layer), float(probeZ)) * gridStep() + camOffset();
+  }
+  // rgen:86-87: mat3(pc.randomRot) * worldDirFromFibonacciIndex(rayIndex), the Fibonacci direction from the host table
+  V3 probeRayDir(const float* rot, int ray) const { return mulMat3(rot, v3(fibDirs[3 * ray], fibDirs[3 * ray + 1], fibDirs[3 * ray + 2])); }
+  // rmiss:17-21
+  V3 missRadiance() const { return toLinear(v3(ubo.sky_intensity * ubo.sky_color[0], ubo.sky_intensity * ubo.sky_color[1], ubo.sky_intensity * ubo.sky_color[2])); }
+
   // ---- rgen main for every ray of one layer (irradiance_probe_update.rgen:48-111) -------------------------
   int traceLayer(int layer, const float* rot) {
     if (!haveAccel) { err = "trace before build_accel"; return ANEREND_DDGI_E_STATE; }
@@ -763,14 +773,10 @@ struct ddgi_oracle {
     bool rec = (p.flags & ANEREND_DDGI_FLAG_RAY_RECORDS) != 0;
     if (rec) records[layer].assign((size_t)P * N, anerend_ddgi_ray_record_t{});
     std::vector<V3> dirs(N);
-    for (int i = 0; i < N; ++i) dirs[i] = mulMat3(rot, v3(fibDirs[3 * i], fibDirs[3 * i + 1], fibDirs[3 * i + 2]));
-    // rmiss:17-21
-    V3 sky = toLinear(v3(ubo.sky_intensity * ubo.sky_color[0], ubo.sky_intensity * ubo.sky_color[1], ubo.sky_intensity * ubo.sky_color[2]));
-    V3 co = camOffset();
-    V3 step = gridStep();
+    for (int i = 0; i < N; ++i) dirs[i] = probeRayDir(rot, i);
+    V3 sky = missRadiance();
     parallelFor(P, [&](int probe) {
-      int probeX = probe % nXZ, probeZ = probe / nXZ;
-      V3 origin = v3(float(probeX), float(layer), float(probeZ)) * step + co;
+      V3 origin = probeOrigin(layer, probe);
       uint64_t cnt[7] = {0, 0, 0, 0, 0, 0, 0};
       for (int ray = 0; ray < N; ++ray) {
         V3 d = dirs[ray]; Hit hit; uint32_t lit = 0; V3 rad;
@@ -1041,6 +1047,12 @@ int ddgi_oracle_get_stats(ddgi_oracle_t* h, anerend_ddgi_stats_t* o) {
 int ddgi_oracle_reset_stats(ddgi_oracle_t* h) { for (auto& s : h->st) s = 0; return 0; }
 
 int ddgi_oracle_make_rotation(int32_t axis, float deg, float out[16]) { if (axis < 0 || axis > 2) return ANEREND_DDGI_E_INVALID; makeRotation(axis, deg, out); return 0; }
+int ddgi_oracle_probe_ray(ddgi_oracle_t* h, int32_t layer, int32_t probe, int32_t ray, const float rot[16], float origin[3], float dir[3], float miss[3]) {
+  if (!h || !h->haveUbo || layer < 0 || layer >= h->nY || probe < 0 || probe >= h->nXZ * h->nXZ || ray < 0 || ray >= h->N) return ANEREND_DDGI_E_INVALID;
+  V3 o = h->probeOrigin(layer, probe), d = h->probeRayDir(rot, ray), m = h->missRadiance();
+  origin[0] = o.x; origin[1] = o.y; origin[2] = o.z; dir[0] = d.x; dir[1] = d.y; dir[2] = d.z; miss[0] = m.x; miss[1] = m.y; miss[2] = m.z;
+  return 0;
+}
 int ddgi_oracle_fibonacci_dirs(int32_t n, float* out) {
   if (n < 1) return ANEREND_DDGI_E_INVALID;
   for (int i = 0; i < n; ++i) { V3 d = fibonacciDir(i, n); out[3 * i] = d.x; out[3 * i + 1] = d.y; out[3 * i + 2] = d.z; } return 0;

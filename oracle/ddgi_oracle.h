@@ -73,6 +73,9 @@ int ddgi_oracle_reset_stats(ddgi_oracle_t* h);
 int ddgi_oracle_set_rays(ddgi_oracle_t* h, int32_t layer, const void* irr_rgba16f, const void* dir_rgba16f, size_t bytes_each);
 
 /* ---- single shader functions, exported for the known-answer tests ------------------------ */
+/* What rgen hands to traceRayEXT for launch pixel (probe, ray) of `layer` (origin rgen:51-83, direction rgen:86-87), and what rmiss
+ * would return for it (rmiss:17-21): the functions trace_layer itself uses. */
+int  ddgi_oracle_probe_ray(ddgi_oracle_t* h, int32_t layer, int32_t probe, int32_t ray, const float rot[16], float origin[3], float dir[3], float miss[3]);
 int  ddgi_oracle_make_rotation(int32_t axis, float angle_deg, float out[16]);          /* glm::rotate */
 int  ddgi_oracle_fibonacci_dirs(int32_t n, float* out);                                /* rgen:35-46 */
 void ddgi_oracle_oct_encode(const float v[3], float out[2]);                           /* octahedron_helpers.glsl:10-20 */
