@@ -296,6 +296,12 @@ class DdgiHandle:
         self._call("download_texel_records", _ptr(out), C.c_size_t(out.nbytes))
         return out
 
+    def download_instances(self):
+        """uint32 [num_instances, 4]: renderable, custom index (material | mesh << 10), first triangle, triangle count."""
+        out = np.empty((self.bvh_info().num_instances, 4), np.uint32)
+        self._call("download_instances", _ptr(out), C.c_size_t(len(out)))
+        return out
+
     def download_bvh(self):
         """(nodes uint8[num_nodes*80], tris uint8[num_triangles*48]) — the BVH8 exactly as the traversal kernel reads it."""
         info = self.bvh_info()

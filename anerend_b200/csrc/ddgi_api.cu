@@ -907,6 +907,13 @@ int DDGI_API(get_bvh_info)(anerend_ddgi_t* h, anerend_ddgi_bvh_info_t* o) {
   for (int k = 0; k < 3; ++k) { o->bounds_min[k] = h->boundsMin[k]; o->bounds_max[k] = h->boundsMax[k]; }
   return 0;
 }
+int DDGI_API(download_instances)(anerend_ddgi_t* h, anerend_ddgi_instance_t* out, size_t count) {
+  if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "no acceleration structure");
+  if (!out || count != h->instances.size()) return fail(h, ANEREND_DDGI_E_INVALID, "instance count mismatch");
+  for (size_t i = 0; i < count; ++i) { const DInstance& in = h->instances[i];
+    out[i].renderable = in.renderable; out[i].custom_index = in.material | (in.mesh << 10); out[i].first_triangle = in.firstTri; out[i].num_triangles = in.numTris; }
+  return 0;
+}
 int DDGI_API(download_bvh)(anerend_ddgi_t* h, void* nodes, size_t nb, void* tris, size_t tb) {
   if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "no acceleration structure");
   if (nb != (size_t)h->numNodes * 80 || tb != (size_t)h->numTris * 48) return fail(h, ANEREND_DDGI_E_INVALID, "size mismatch");

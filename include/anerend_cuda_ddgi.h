@@ -167,6 +167,16 @@ int anerend_cuda_ddgi_update_vertices_device(anerend_ddgi_t* h, const void* d_ve
 int anerend_cuda_ddgi_refit_accel(anerend_ddgi_t* h, const anerend_renderable_t* renderables, uint32_t num_renderables);
 int anerend_cuda_ddgi_refit_accel_device(anerend_ddgi_t* h, const void* d_renderables, uint32_t num_renderables);
 int anerend_cuda_ddgi_get_bvh_info(anerend_ddgi_t* h, anerend_ddgi_bvh_info_t* out);
+/* The instances _build_accel selected, in the order they were emitted: what tlas_update.comp:54-98 writes to its InstanceBuffer
+ * when its invocations run in renderable order (custom index = material | mesh << 10, tlas_update.comp:88-91), plus the range of
+ * flattened triangle ids the instance owns.  count must equal bvh_info.num_instances.  Inspection only (tests/test_golden_tlas.py). */
+typedef struct anerend_ddgi_instance {
+  uint32_t renderable;        /* index into the renderable buffer                            */
+  uint32_t custom_index;      /* 24-bit instanceCustomIndex: material (10 bits) | mesh << 10 */
+  uint32_t first_triangle;    /* first flattened world triangle id                           */
+  uint32_t num_triangles;
+} anerend_ddgi_instance_t;
+int anerend_cuda_ddgi_download_instances(anerend_ddgi_t* h, anerend_ddgi_instance_t* out, size_t count);
 /* Debug/validation: copies the BVH8 nodes (num_nodes*80 B) and traversal triangles (num_triangles*48 B). */
 int anerend_cuda_ddgi_download_bvh(anerend_ddgi_t* h, void* nodes, size_t nodes_bytes, void* tris, size_t tris_bytes);
 

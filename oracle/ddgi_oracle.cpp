@@ -959,6 +959,12 @@ int ddgi_oracle_get_bvh_info(ddgi_oracle_t* h, anerend_ddgi_bvh_info_t* o) {
   if (!h->bvh.nodes.empty()) for (int k = 0; k < 3; ++k) { o->bounds_min[k] = h->bvh.nodes[0].lo[k]; o->bounds_max[k] = h->bvh.nodes[0].hi[k]; }
   return 0;
 }
+int ddgi_oracle_download_instances(ddgi_oracle_t* h, anerend_ddgi_instance_t* out, size_t count) {
+  if (!out || count != h->instances.size()) { h->err = "instance count mismatch"; return ANEREND_DDGI_E_INVALID; }
+  for (size_t i = 0; i < count; ++i) { const Instance& in = h->instances[i];
+    out[i].renderable = in.renderable; out[i].custom_index = in.material | (in.mesh << 10); out[i].first_triangle = in.firstTri; out[i].num_triangles = in.numTris; }
+  return 0;
+}
 int ddgi_oracle_download_world_triangles(ddgi_oracle_t* h, float* out, size_t count) {
   if (count != h->tris.size()) { h->err = "triangle count mismatch"; return ANEREND_DDGI_E_INVALID; }
   for (size_t i = 0; i < count; ++i) { const WTri& t = h->tris[i]; V3 a = t.v0, b = t.v0 + t.e1, c = t.v0 + t.e2;

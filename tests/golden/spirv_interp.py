@@ -321,6 +321,20 @@ class Invocation:
                         raise NotImplementedError(f"GLSL.std.450 {inst}")
                 elif op == 172:
                     v[a[1]] = _map(lambda x, y: _u32(x) > _u32(y), val(a[2]), val(a[3]))
+                elif op == 174:
+                    v[a[1]] = _map(lambda x, y: _u32(x) >= _u32(y), val(a[2]), val(a[3]))
+                elif op == 176:
+                    v[a[1]] = _map(lambda x, y: _u32(x) < _u32(y), val(a[2]), val(a[3]))
+                elif op == 201:                                     # OpBitFieldInsert
+                    base, ins, off, cnt = _u32(val(a[2])), _u32(val(a[3])), int(val(a[4])), int(val(a[5]))
+                    mask = (((1 << cnt) - 1) << off) & 0xFFFFFFFF
+                    r = (base & ~mask) | ((ins << off) & mask)
+                    v[a[1]] = _s32(r) if _is_signed(m, a[0]) else _u32(r)
+                elif op == 234:                                     # OpAtomicIAdd: invocations run one after another
+                    ptr = val(a[2])
+                    old_v = ptr.load()
+                    ptr.store(_u32(int(old_v) + int(val(a[5]))))
+                    v[a[1]] = old_v
                 elif op == 177:
                     v[a[1]] = _map(lambda x, y: _s32(x) < _s32(y), val(a[2]), val(a[3]))
                 elif op == 170:
