@@ -1,7 +1,9 @@
 // ddgi_oracle.cpp — CPU oracle for AneRend's DDGI irradiance-probe update.
 //
-// TEST INFRASTRUCTURE ONLY (see ddgi_oracle.h).  PARITY UNPINNED: the reference has no golden vectors, tests
-// or CPU path for this chain; the oracle is pinned by KATs derived from the shader formulas.
+// TEST INFRASTRUCTURE ONLY (see ddgi_oracle.h).  The reference has no golden vectors, tests or CPU path for this chain;
+// the oracle is held to the reference's COMPILED shaders (assets/*.spv executed by tests/golden/spirv_interp.py, vectors in
+// tests/golden/) for everything those binaries compute.  PARITY UNPINNED for what they leave to the Vulkan driver — the
+// ray/triangle intersection and traversal — which is pinned by KATs (tests/test_oracle_kat.py) only.
 //
 // Every function below restates one reference function and cites it (paths relative to the AneRend repo;
 // shaders live in assets/shaders/).  Arithmetic is IEEE fp32 evaluated strictly left to right, compiled with

@@ -5,9 +5,11 @@
  * shaders and pass code; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load it.  The product (anerend_b200/) never links, imports or calls anything in oracle/.
  *
- * PARITY UNPINNED: the reference holds no golden vectors, tests or CPU path for this chain,
- * and its ray/triangle intersection lives in the Vulkan driver.  The oracle is pinned instead by known-answer
- * tests derived from the shader formulas (tests/test_oracle_kat.py).
+ * PINNING: the reference holds no golden vectors, tests or CPU path for this chain and cannot be built here.
+ * The oracle is held to the reference's own COMPILED shaders instead: assets/probe_conv_comp.spv, irradiance_probe_update_rgen /
+ * _rchit / _rmiss.spv and tlas_update_comp.spv executed by tests/golden/spirv_interp.py (vectors + generators in tests/golden/,
+ * tests/test_golden_*.py).  PARITY UNPINNED for what those binaries leave to the Vulkan driver: the ray/triangle intersection and
+ * traversal (defined in DESIGN.md, checked by known-answer tests in tests/test_oracle_kat.py), filtering weights, fp16 rounding.
  *
  * The API mirrors include/anerend_cuda_ddgi.h one to one (same parameter struct, same buffer formats), so a
  * parity test drives both sides with identical calls.
