@@ -70,6 +70,13 @@ class Oracle(DdgiHandle):
                    f3(view_pos), out)
         return np.array(out[:], np.float32)
 
+    def screen_ray(self, specular, px, py, depth, normal=(0.0, 1.0, 0.0)):
+        """(origin, direction) shadow.rgen / mirror_reflections.rgen trace for a screen pixel."""
+        o, d = (C.c_float * 3)(), (C.c_float * 3)()
+        self._call("screen_ray", C.c_int32(1 if specular else 0), C.c_uint32(px), C.c_uint32(py), C.c_float(depth),
+                   (C.c_float * 3)(*[float(x) for x in normal]), o, d)
+        return np.array(o[:], np.float32), np.array(d[:], np.float32)
+
     def probe_ray(self, layer, probe, ray, rot):
         """(origin, direction, miss radiance) of one launch pixel, from the functions trace_layer uses (rgen:51-87, rmiss:17-21)."""
         o, d, m = (C.c_float * 3)(), (C.c_float * 3)(), (C.c_float * 3)()

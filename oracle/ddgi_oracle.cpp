@@ -755,6 +755,24 @@ struct ddgi_oracle {
     return irradiance;
   }
 
+  // calcWorldPos(pixelToUv(pixel, screen), depth) — shadow.rgen:20-28,38 and mirror_reflections.rgen:38-46,51:
+  // mat4 * vec4 = c0*x + c1*y + c2*z + c3*w, then the perspective divide
+  V3 screenWorldPos(uint32_t px, uint32_t py, float depthSamp) const {
+    const float* m = ubo.inv_view_proj;
+    const float sw = (float)ubo.screen_width, sh = (float)ubo.screen_height;
+    const float u = (2.0f * (float)px + 1.0f) / (2.0f * sw), v = (2.0f * (float)py + 1.0f) / (2.0f * sh);   // pixelToUv, helpers.glsl:1-4
+    const float cx = u * 2.0f - 1.0f, cy = v * 2.0f - 1.0f, cz = depthSamp;
+    const float X = m[0] * cx + m[4] * cy + m[8] * cz + m[12] * 1.0f, Y = m[1] * cx + m[5] * cy + m[9] * cz + m[13] * 1.0f;
+    const float Z = m[2] * cx + m[6] * cy + m[10] * cz + m[14] * 1.0f, W = m[3] * cx + m[7] * cy + m[11] * cz + m[15] * 1.0f;
+    return v3(X / W, Y / W, Z / W);
+  }
+  // mirror_reflections.rgen:64-70: reflect(normalize(pos - cameraPos), normalize(geom0.rgb)); reflect(I, N) = I - 2 dot(N, I) N
+  V3 reflectionDir(V3 pos, V3 geomNormal) const {
+    const V3 normal = normalize(geomNormal);
+    const V3 vv = normalize(pos - v3(ubo.camera_pos[0], ubo.camera_pos[1], ubo.camera_pos[2]));
+    const float dn = dot(normal, vv);
+    return vv - (2.0f * dn) * normal;
+  }
   // rgen:51-83: probe (probeX, layer, probeZ) of the launch pixel -> ray origin
   V3 probeOrigin(int layer, int probe) const {
     int probeX = probe % nXZ, probeZ = probe / nXZ;
@@ -1055,6 +1073,13 @@ int ddgi_oracle_get_stats(ddgi_oracle_t* h, anerend_ddgi_stats_t* o) {
 int ddgi_oracle_reset_stats(ddgi_oracle_t* h) { for (auto& s : h->st) s = 0; return 0; }
 
 int ddgi_oracle_make_rotation(int32_t axis, float deg, float out[16]) { if (axis < 0 || axis > 2) return ANEREND_DDGI_E_INVALID; makeRotation(axis, deg, out); return 0; }
+int ddgi_oracle_screen_ray(ddgi_oracle_t* h, int32_t specular, uint32_t px, uint32_t py, float depth, const float geom_normal[3], float origin[3], float dir[3]) {
+  if (!h || !h->haveUbo) return ANEREND_DDGI_E_INVALID;
+  V3 o = h->screenWorldPos(px, py, depth);
+  V3 d = specular ? h->reflectionDir(o, v3(geom_normal[0], geom_normal[1], geom_normal[2])) : -v3(h->ubo.light_dir[0], h->ubo.light_dir[1], h->ubo.light_dir[2]);
+  origin[0] = o.x; origin[1] = o.y; origin[2] = o.z; dir[0] = d.x; dir[1] = d.y; dir[2] = d.z;
+  return 0;
+}
 int ddgi_oracle_probe_ray(ddgi_oracle_t* h, int32_t layer, int32_t probe, int32_t ray, const float rot[16], float origin[3], float dir[3], float miss[3]) {
   if (!h || !h->haveUbo || layer < 0 || layer >= h->nY || probe < 0 || probe >= h->nXZ * h->nXZ || ray < 0 || ray >= h->N) return ANEREND_DDGI_E_INVALID;
   V3 o = h->probeOrigin(layer, probe), d = h->probeRayDir(rot, ray), m = h->missRadiance();
@@ -1087,9 +1112,6 @@ int ddgi_oracle_specular_gi(ddgi_oracle_t* h, const float* depth, const float* g
   if (!h->haveAccel) { h->err = "specular_gi before build_accel"; return ANEREND_DDGI_E_STATE; }
   if (!h->haveUbo) { h->err = "specular_gi before set_scene_ubo"; return ANEREND_DDGI_E_STATE; }
   if (!(h->ubo.flags & ANEREND_UBO_RT_ON_FLAG) || !(h->ubo.flags & ANEREND_UBO_SPECULAR_GI_FLAG)) return 0;   // SpecularGIRTPass.cpp:102-103
-  const float* m = h->ubo.inv_view_proj;
-  const float sw = (float)h->ubo.screen_width, sh = (float)h->ubo.screen_height;
-  const V3 cam = v3(h->ubo.camera_pos[0], h->ubo.camera_pos[1], h->ubo.camera_pos[2]);
   const V3 sky = toLinear(v3(h->ubo.sky_intensity * h->ubo.sky_color[0], h->ubo.sky_intensity * h->ubo.sky_color[1], h->ubo.sky_intensity * h->ubo.sky_color[2]));
   h->parallelFor((int)height, [&](int py) {
     uint64_t cnt[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -1098,15 +1120,8 @@ int ddgi_oracle_specular_gi(ddgi_oracle_t* h, const float* depth, const float* g
       uint16_t* o = out + 4 * i;
       const float depthSamp = depth[i];
       if (depthSamp == 1.0f) { o[0] = o[1] = o[2] = o[3] = 0; continue; }                        // rgen:41-44
-      const float u = (2.0f * (float)px + 1.0f) / (2.0f * sw), v = (2.0f * (float)py + 1.0f) / (2.0f * sh);
-      const float cx = u * 2.0f - 1.0f, cy = v * 2.0f - 1.0f, cz = depthSamp;
-      const float X = m[0] * cx + m[4] * cy + m[8] * cz + m[12] * 1.0f, Y = m[1] * cx + m[5] * cy + m[9] * cz + m[13] * 1.0f;
-      const float Z = m[2] * cx + m[6] * cy + m[10] * cz + m[14] * 1.0f, W = m[3] * cx + m[7] * cy + m[11] * cz + m[15] * 1.0f;
-      const V3 pos = v3(X / W, Y / W, Z / W);
-      const V3 normal = normalize(v3(geom0[4 * i], geom0[4 * i + 1], geom0[4 * i + 2]));          // rgen:46
-      const V3 vv = normalize(pos - cam);
-      const float dn = dot(normal, vv);
-      const V3 dir = vv - (2.0f * dn) * normal;                                                 // reflect(v, normal) = I - 2 dot(N, I) N
+      const V3 pos = h->screenWorldPos(px, py, depthSamp);
+      const V3 dir = h->reflectionDir(pos, v3(geom0[4 * i], geom0[4 * i + 1], geom0[4 * i + 2]));
       Hit hit; uint32_t lit = 0; V3 rad; float dist;
       if (h->closestHit(pos, dir, 0.1f, 50.0f, hit, cnt[3], cnt[4])) {
         V3 hp;
@@ -1123,8 +1138,6 @@ int ddgi_oracle_shadow_rt(ddgi_oracle_t* h, const float* depth, uint32_t width, 
   if (!h->haveAccel) { h->err = "shadow_rt before build_accel"; return ANEREND_DDGI_E_STATE; }
   if (!h->haveUbo) { h->err = "shadow_rt before set_scene_ubo"; return ANEREND_DDGI_E_STATE; }
   if (!(h->ubo.flags & ANEREND_UBO_RT_SHADOWS_FLAG)) return 0;                       // shadow.rgen:32-34
-  const float* m = h->ubo.inv_view_proj;
-  const float sw = (float)h->ubo.screen_width, sh = (float)h->ubo.screen_height;
   const V3 dir = -v3(h->ubo.light_dir[0], h->ubo.light_dir[1], h->ubo.light_dir[2]);  // shadow.rgen:58, not normalised
   h->parallelFor((int)height, [&](int py) {
     uint64_t cn = 0, ct = 0;
@@ -1132,12 +1145,7 @@ int ddgi_oracle_shadow_rt(ddgi_oracle_t* h, const float* depth, uint32_t width, 
       const size_t i = (size_t)py * width + px;
       const float depthSamp = depth[i];                                               // texel centre (pixelToUv, helpers.glsl:1-4)
       if (depthSamp == 1.0f) { out[i] = 1.0f; continue; }                             // sky, shadow.rgen:45-48
-      const float u = (2.0f * (float)px + 1.0f) / (2.0f * sw), v = (2.0f * (float)py + 1.0f) / (2.0f * sh);
-      const float cx = u * 2.0f - 1.0f, cy = v * 2.0f - 1.0f, cz = depthSamp;
-      // calcWorldPos, shadow.rgen:20-28: mat4 * vec4 = c0*x + c1*y + c2*z + c3*w, then the perspective divide
-      const float X = m[0] * cx + m[4] * cy + m[8] * cz + m[12] * 1.0f, Y = m[1] * cx + m[5] * cy + m[9] * cz + m[13] * 1.0f;
-      const float Z = m[2] * cx + m[6] * cy + m[10] * cz + m[14] * 1.0f, W = m[3] * cx + m[7] * cy + m[11] * cz + m[15] * 1.0f;
-      const V3 origin = v3(X / W, Y / W, Z / W);
+      const V3 origin = h->screenWorldPos(px, py, depthSamp);                        // calcWorldPos, shadow.rgen:20-28
       out[i] = h->anyHit(origin, dir, 0.1f, 50.0f, cn, ct) ? 0.0f : 1.0f;           // payload 0, shadow.rmiss sets 1
     }
   });

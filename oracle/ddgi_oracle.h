@@ -76,6 +76,9 @@ int ddgi_oracle_reset_stats(ddgi_oracle_t* h);
 int ddgi_oracle_set_rays(ddgi_oracle_t* h, int32_t layer, const void* irr_rgba16f, const void* dir_rgba16f, size_t bytes_each);
 
 /* ---- single shader functions, exported for the known-answer tests ------------------------ */
+/* The ray shadow.rgen (specular = 0) or mirror_reflections.rgen (specular = 1) traces for screen pixel (px, py) with depth sample
+ * `depth` (and G-buffer normal geom_normal): the functions the two passes themselves use. */
+int  ddgi_oracle_screen_ray(ddgi_oracle_t* h, int32_t specular, uint32_t px, uint32_t py, float depth, const float geom_normal[3], float origin[3], float dir[3]);
 /* What rgen hands to traceRayEXT for launch pixel (probe, ray) of `layer` (origin rgen:51-83, direction rgen:86-87), and what rmiss
  * would return for it (rmiss:17-21): the functions trace_layer itself uses. */
 int  ddgi_oracle_probe_ray(ddgi_oracle_t* h, int32_t layer, int32_t probe, int32_t ray, const float rot[16], float origin[3], float dir[3], float miss[3]);
