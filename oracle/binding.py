@@ -70,6 +70,13 @@ class Oracle(DdgiHandle):
                    f3(view_pos), out)
         return np.array(out[:], np.float32)
 
+    def shade_hit(self, prim, u, v, origin, specular=False):
+        """(irradiance [3], distance, lit mask) of the probe / mirror-reflection hit shader for one hit."""
+        out, lit = (C.c_float * 4)(), C.c_uint32(0)
+        self._call("shade_hit", C.c_uint32(prim), C.c_float(u), C.c_float(v), (C.c_float * 3)(*[float(x) for x in origin]),
+                   C.c_int32(1 if specular else 0), out, C.byref(lit))
+        return np.array(out[:3], np.float32), np.float32(out[3]), int(lit.value)
+
     def screen_ray(self, specular, px, py, depth, normal=(0.0, 1.0, 0.0)):
         """(origin, direction) shadow.rgen / mirror_reflections.rgen trace for a screen pixel."""
         o, d = (C.c_float * 3)(), (C.c_float * 3)()

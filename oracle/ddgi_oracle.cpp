@@ -1073,6 +1073,16 @@ int ddgi_oracle_get_stats(ddgi_oracle_t* h, anerend_ddgi_stats_t* o) {
 int ddgi_oracle_reset_stats(ddgi_oracle_t* h) { for (auto& s : h->st) s = 0; return 0; }
 
 int ddgi_oracle_make_rotation(int32_t axis, float deg, float out[16]) { if (axis < 0 || axis > 2) return ANEREND_DDGI_E_INVALID; makeRotation(axis, deg, out); return 0; }
+int ddgi_oracle_shade_hit(ddgi_oracle_t* h, uint32_t prim, float u, float v, const float origin[3], int32_t specular, float out[4], uint32_t* lit_mask) {
+  if (!h || !h->haveAccel || !h->haveUbo || prim >= h->tris.size()) return ANEREND_DDGI_E_INVALID;
+  Hit hit{prim, 0.0f, u, v}; uint32_t lit = 0; uint64_t cnt[7] = {0, 0, 0, 0, 0, 0, 0}; V3 hp;
+  const V3 o = v3(origin[0], origin[1], origin[2]);
+  V3 rad = h->shadeHit(hit, o, lit, cnt, specular != 0, &hp);
+  const V3 dd = hp - o;
+  out[0] = rad.x; out[1] = rad.y; out[2] = rad.z; out[3] = std::sqrt(dot(dd, dd));       // distance(pos, gl_WorldRayOriginEXT), mirror_reflections.rchit:90
+  if (lit_mask) *lit_mask = lit;
+  return 0;
+}
 int ddgi_oracle_screen_ray(ddgi_oracle_t* h, int32_t specular, uint32_t px, uint32_t py, float depth, const float geom_normal[3], float origin[3], float dir[3]) {
   if (!h || !h->haveUbo) return ANEREND_DDGI_E_INVALID;
   V3 o = h->screenWorldPos(px, py, depth);

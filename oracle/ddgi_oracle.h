@@ -76,6 +76,10 @@ int ddgi_oracle_reset_stats(ddgi_oracle_t* h);
 int ddgi_oracle_set_rays(ddgi_oracle_t* h, int32_t layer, const void* irr_rgba16f, const void* dir_rgba16f, size_t bytes_each);
 
 /* ---- single shader functions, exported for the known-answer tests ------------------------ */
+/* The hit shader for one hit (flattened triangle id, barycentrics) of a ray from `origin`: irradiance_probe_update.rchit
+ * (specular = 0) or mirror_reflections.rchit (specular = 1) against the handle's current atlas; out = (irradiance, distance from
+ * the origin).  The function trace_layer / specular_gi themselves call. */
+int  ddgi_oracle_shade_hit(ddgi_oracle_t* h, uint32_t prim, float u, float v, const float origin[3], int32_t specular, float out[4], uint32_t* lit_mask);
 /* The ray shadow.rgen (specular = 0) or mirror_reflections.rgen (specular = 1) traces for screen pixel (px, py) with depth sample
  * `depth` (and G-buffer normal geom_normal): the functions the two passes themselves use. */
 int  ddgi_oracle_screen_ray(ddgi_oracle_t* h, int32_t specular, uint32_t px, uint32_t py, float depth, const float geom_normal[3], float origin[3], float dir[3]);

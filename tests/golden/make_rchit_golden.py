@@ -2,7 +2,8 @@
 """Golden vectors for the probe hit shader from the reference's OWN compiled shader: executes
 assets/irradiance_probe_update_rchit.spv (main + getSurfaceDataFromMat + calcLight + calcIndirectDiffuseLight + sampleProbe + ...)
 with tests/golden/spirv_interp.py for a sample of the hits of a textured test scene, and writes the hits and the payload the binary
-produces to tests/golden/rchit_golden.npz.  What the driver / hardware would supply is supplied here from the oracle's run of the
+produces to tests/golden/rchit_golden.npz.  The same hits are also run through assets/mirror_reflections_rchit.spv (the "SpecularGIRT"
+hit shader: mat3(gl_ObjectToWorldEXT) normal transform, distance payload, UBO_DDGI_FLAG gate) against the atlas after the second update.  What the driver / hardware would supply is supplied here from the oracle's run of the
 same scene: the hit (instance custom index, primitive id, barycentrics, object<->world matrices, ray origin), the result of the shadow
 ray (OpTraceRayKHR callback), and texture / atlas sampling (bilinear at LOD 0 as DESIGN.md defines it).  Everything else — vertex
 fetch and interpolation, normal transform, toLinear, surface data from the material and its textures, Cook-Torrance, the probe-grid
@@ -88,6 +89,13 @@ def main():
     prev = o.download_atlas().view(np.float16).astype(np.float32)             # the atlas the second update's hit shader samples
     o.update(-1, rots)
     recs = [o.download_ray_records(l) for l in range(ny)]
+    atlas2 = o.download_atlas().view(np.float16).astype(np.float32)           # the atlas mirror_reflections.rchit samples below
+    mm = Module(os.path.join(os.path.dirname(path), "mirror_reflections_rchit.spv"))
+    mubo_gid = next(g for g, n in mm.names.items() if n == "ubo" and g in mm.globals)
+    mubo_t = mm.types[mm.globals[mubo_gid][0]][2]
+    msp_gid = next(g for g, n in mm.names.items() if n == "shadowPayload" and g in mm.globals)
+    mshadow_member = mm.struct_member(mm.types[mm.globals[msp_gid][0]][2], "shadow")
+    mpay_gid = next(g for g, n in mm.names.items() if n == "payload" and g in mm.globals)
     # instances in the order tlas_update.comp emits them (visible, not culled), with their triangle ranges
     inst, first = [], 0
     for r in scene.renderables:
@@ -109,12 +117,13 @@ def main():
             for mt in scene.materials]
     ubo_gid = next(g for g, n in m.names.items() if n == "ubo" and g in m.globals)
     ubo_t = m.types[m.globals[ubo_gid][0]][2]
-    ubo = m.zero(ubo_t)
+    ubo, mubo = m.zero(ubo_t), mm.zero(mubo_t)
     u = scene.ubo[0]
     for name, val in (("cameraPos", [f32(x) for x in u["camera_pos"]]), ("lightDir", [f32(x) for x in u["light_dir"]]),
                       ("skyColor", [f32(x) for x in u["sky_color"]]), ("bakeTileInfo", [int(x) for x in u["bake_tile_info"]]),
                       ("sunIntensity", f32(u["sun_intensity"])), ("skyIntensity", f32(u["sky_intensity"])), ("flags", int(u["flags"]))):
         ubo[m.struct_member(ubo_t, name)] = val
+        mubo[mm.struct_member(mubo_t, name)] = val
     step, cam = (1.0, 2.0, 1.0), u["camera_pos"]
     camoff = (f32(int(cam[0] / 1.0)) * f32(1.0) - f32(1.0) * f32(nxz) / f32(2.0), f32(0.0), f32(int(cam[2] / 1.0)) * f32(1.0) - f32(1.0) * f32(nxz) / f32(2.0))
     sp_gid = next(g for g, n in m.names.items() if n == "shadowPayload" and g in m.globals)
@@ -122,6 +131,7 @@ def main():
     rng = np.random.RandomState(1)
     hits = [(l, p, r) for l in range(ny) for p in range(nxz * nxz) for r in range(nr) if recs[l][p, r]["prim"] != 0xFFFFFFFF]
     pick = [hits[k] for k in rng.choice(len(hits), SAMPLES, replace=False)]
+    mirror = np.zeros((SAMPLES, 4), np.float32); origins = np.zeros((SAMPLES, 3), np.float32)
     out = np.zeros((SAMPLES, 3), np.float32); meta = np.zeros((SAMPLES, 3), np.int64); prim_uv = np.zeros((SAMPLES, 3), np.float64); lit = np.zeros(SAMPLES, np.int64)
     for k, (layer, probe, ray) in enumerate(pick):
         rec = recs[layer][probe, ray]
@@ -153,11 +163,29 @@ def main():
         res = inv.g[pay_gid].load()
         out[k] = res[0]
         assert len(shadow_calls) == 1 and float(shadow_calls[0][2]) == np.float32(0.1) and float(shadow_calls[0][3]) == 50.0
+        # the same hit through mirror_reflections.rchit ("SpecularGIRT"): payload (irradiance, dist, shadow), the live atlas of now
+        mcalls = []
+
+        def mtrace(org, d, tmin, tmax, payload, _rec=rec, _calls=mcalls):
+            _calls.append((org, d, tmin, tmax))
+            sp = payload.load()
+            sp[mshadow_member] = f32(0.0) if (int(_rec["lit_mask"]) & 1) else f32(1.0)
+            payload.store(sp)
+
+        mbind = dict(bind)
+        mbind.update({"ubo": mubo, "probeTex": Sampler(atlas2), "payload": [[f32(0)] * 3, f32(0), f32(0)], "shadowPayload": [[f32(0)] * 3, f32(0), f32(0)],
+                      "traceRay": mtrace})
+        minv = Invocation(mm, mbind)
+        minv.run()
+        mres = minv.g[mpay_gid].load()
+        mirror[k] = [*mres[0], mres[1]]; origins[k] = origin
+        assert len(mcalls) == 1 and [float(c) for c in mcalls[0][0]] == [float(c) for c in shadow_calls[0][0]]      # same shadow ray as the probe shader
         meta[k] = (layer, probe, ray); prim_uv[k] = (prim, rec["u"], rec["v"]); lit[k] = int(rec["lit_mask"]) & 1
         if k % 16 == 0 or os.environ.get("RCHIT_VERBOSE"):
             print(k, "binary:", out[k], "oracle:", rec["radiance"], "lit", lit[k], "material", mat)
+            print("   mirror binary:", mirror[k], "oracle:", o.shade_hit(prim, rec["u"], rec["v"], origin, specular=True)[:2])
     dst = os.path.join(HERE, "rchit_golden.npz")
-    np.savez_compressed(dst, rays=meta, prim_uv=prim_uv, lit=lit, irradiance=out, grid=np.array(GRID))
+    np.savez_compressed(dst, rays=meta, prim_uv=prim_uv, lit=lit, irradiance=out, grid=np.array(GRID), origins=origins, mirror=mirror)
     print("wrote", dst)
 
 

@@ -5,7 +5,8 @@ payload that assets/irradiance_probe_update_rchit.spv (the binary the renderer l
 SPIR-V interpreter tests/golden/spirv_interp.py (generator: tests/golden/make_rchit_golden.py, run in the build container where
 the reference is mounted).  The compiled code covers the vertex fetch and interpolation, the normal transform, toLinear,
 getSurfaceDataFromMat with its texture taps, calcLight, calcIndirectDiffuseLight / sampleProbe / weightProbe / sampleSingleProbe /
-octEncode against the previous atlas, and the emissive term; the interpreter is handed what the driver would provide (the hit,
+octEncode against the previous atlas, and the emissive term (and, for the same hits, assets/mirror_reflections_rchit.spv — the
+"SpecularGIRT" hit shader — with its other normal transform, distance payload and UBO_DDGI_FLAG gate); the interpreter is handed what the driver would provide (the hit,
 the shadow-ray result, bilinear sampling as DESIGN.md defines it).  Multi-bounce is on, so the previous atlas matters.
 The CUDA kernels are held to the oracle bit for bit by the -m gpu tests."""
 import os
@@ -34,7 +35,20 @@ def test_oracle_hit_shading_equals_the_compiled_reference_shader(oracle):
         r = recs[int(layer)][probe, ray]
         assert (int(r["prim"]), float(r["u"]), float(r["v"])) == tuple(G["prim_uv"][k]) and (int(r["lit_mask"]) & 1) == G["lit"][k]
         got[k] = r["radiance"]
+    # the same hits through mirror_reflections.rchit (SpecularGIRT), against the atlas as it is now
+    mgot = np.zeros_like(G["mirror"])
+    for k in range(len(G["rays"])):
+        prim, u, v = G["prim_uv"][k]
+        rad, dist, lit = o.shade_hit(int(prim), u, v, G["origins"][k], specular=True)
+        mgot[k] = (*rad, dist)
+        assert (lit & 1) == G["lit"][k]
     o.close()
+    mwant = G["mirror"]
+    assert np.array_equal(mgot[:, 3], mwant[:, 3])                              # distance(pos, gl_WorldRayOriginEXT): bit-exact
+    mrel = np.abs(mgot[:, :3] - mwant[:, :3]) / np.maximum(np.abs(mwant[:, :3]), 1e-6)
+    assert mrel.max() <= 2e-6, f"mirror shader: max relative difference {mrel.max():.3e}"
+    assert (mgot.view(np.uint32) == mwant.view(np.uint32)).mean() > 0.9
+    assert np.abs(mwant[:, :3] - G["irradiance"]).max() > 0.05                  # and it is a different shader: other normal transform, gate and atlas
     want = G["irradiance"]
     assert want.max() > 1.0 and (want > 0).all(axis=1).mean() > 0.9 and len(set(G["lit"])) == 2       # a non-trivial sample: lit and shadowed hits
     rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-6)
