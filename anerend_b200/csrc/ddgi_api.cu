@@ -748,17 +748,19 @@ int DDGI_API(destroy)(anerend_ddgi_t* h) {
 }
 
 int DDGI_API(reset)(anerend_ddgi_t* h) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   h->currentLayer = 0; h->lastProbeIdx[0] = h->lastProbeIdx[1] = 0;
   std::fill(h->layerTraced.begin(), h->layerTraced.end(), 0);
   return clearAtlas(h);
 }
 const char* DDGI_API(last_error)(const anerend_ddgi_t* h) { return h ? h->err.c_str() : "null handle"; }
-int DDGI_API(sync)(anerend_ddgi_t* h) { BE_CHECK(h, h->be.sync()); return peerCheck(h); }
+int DDGI_API(sync)(anerend_ddgi_t* h) { if (!h) return ANEREND_DDGI_E_INVALID; BE_CHECK(h, h->be.sync()); return peerCheck(h); }
 
 static size_t texelBytes(uint32_t format) { return format == ANEREND_TEX_RGBA16F ? 8 : format <= ANEREND_TEX_RGBA8_SRGB ? 4 : (format == ANEREND_TEX_RG8_UNORM ? 2 : 1); }
 // tileInfoBuffer (bindless.glsl binding 14, GPUTileInfo): one entry per tile of the (2*10+1)^2 page around the camera; ddgiAtlasTex
 // = bindless index of the tile's baked atlas (an ANEREND_TEX_RGBA16F texture of the atlas size) or -1.  count = 0 removes it.
 int DDGI_API(upload_tile_infos)(anerend_ddgi_t* h, const anerend_tile_info_t* tiles, uint32_t count) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   Backend& be = h->be;
   if (count && !tiles) return fail(h, ANEREND_DDGI_E_INVALID, "null tile array");
   BE_CHECK(h, be.sync());
@@ -769,6 +771,7 @@ int DDGI_API(upload_tile_infos)(anerend_ddgi_t* h, const anerend_tile_info_t* ti
   return 0;
 }
 int DDGI_API(upload_textures)(anerend_ddgi_t* h, const anerend_texture_desc_t* tex, uint32_t count) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   Backend& be = h->be;
   if (count && !tex) return fail(h, ANEREND_DDGI_E_INVALID, "null texture array");
   std::vector<DTexture> table(count);
@@ -814,6 +817,7 @@ int DDGI_API(upload_scene)(anerend_ddgi_t* h,
     const anerend_renderable_t* renderables, uint32_t nr,
     const uint32_t* modelIdx, uint32_t nmi, const uint32_t* matIdx, uint32_t nmti,
     const anerend_light_t* lights, uint32_t nl) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   Backend& be = h->be;
   bool textured = false, emisTex = false;
   for (uint32_t i = 0; i < nmat; ++i) for (int k = 0; k < 4; ++k) {
@@ -846,11 +850,13 @@ int DDGI_API(upload_scene)(anerend_ddgi_t* h,
 }
 
 int DDGI_API(set_scene_ubo)(anerend_ddgi_t* h, const anerend_scene_ubo_t* ubo) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (!ubo) return fail(h, ANEREND_DDGI_E_INVALID, "null ubo");
   h->ubo = *ubo; h->haveUbo = true; return 0;
 }
 
 int DDGI_API(build_accel)(anerend_ddgi_t* h) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (!h->haveScene) return fail(h, ANEREND_DDGI_E_STATE, "build_accel before upload_scene");
   return buildAccel(h);
 }
@@ -868,6 +874,7 @@ static int refitCommon(anerend_ddgi_t* h) {
 // UpdateBlasPass.cpp:60-175, VulkanRenderer.cpp:967-1143): refresh a vertex range, then _refit_accel — the topology of the
 // hierarchy is kept, triangles, boxes and the per-triangle shading records are recomputed from the new vertices.
 int DDGI_API(update_vertices)(anerend_ddgi_t* h, const anerend_vertex_t* vertices, uint32_t first, uint32_t count) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (!h->haveScene) return fail(h, ANEREND_DDGI_E_STATE, "update_vertices before upload_scene");
   if (!vertices || (uint64_t)first + count > h->numVertices) return fail(h, ANEREND_DDGI_E_INVALID, "vertex range out of bounds");
   BE_CHECK(h, h->be.sync());
@@ -876,6 +883,7 @@ int DDGI_API(update_vertices)(anerend_ddgi_t* h, const anerend_vertex_t* vertice
   return 0;
 }
 int DDGI_API(update_vertices_device)(anerend_ddgi_t* h, const void* dVertices, uint32_t first, uint32_t count) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (!h->haveScene) return fail(h, ANEREND_DDGI_E_STATE, "update_vertices before upload_scene");
   if (!dVertices || (uint64_t)first + count > h->numVertices) return fail(h, ANEREND_DDGI_E_INVALID, "vertex range out of bounds");
   BE_CHECK(h, h->be.d2d(h->dVertices + first, dVertices, (size_t)count * sizeof(anerend_vertex_t)));
@@ -883,6 +891,7 @@ int DDGI_API(update_vertices_device)(anerend_ddgi_t* h, const void* dVertices, u
   return 0;
 }
 int DDGI_API(refit_accel)(anerend_ddgi_t* h, const anerend_renderable_t* renderables, uint32_t nr) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "refit before build_accel");
   if (renderables) {
     if (nr != h->renderables.size()) return fail(h, ANEREND_DDGI_E_INVALID, "renderable count changed");
@@ -893,6 +902,7 @@ int DDGI_API(refit_accel)(anerend_ddgi_t* h, const anerend_renderable_t* rendera
   return refitCommon(h);
 }
 int DDGI_API(refit_accel_device)(anerend_ddgi_t* h, const void* dRenderables, uint32_t nr) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "refit before build_accel");
   if (!dRenderables || nr != h->renderables.size()) return fail(h, ANEREND_DDGI_E_INVALID, "renderable count changed");
   // device-written RenderableBuffer (cull.comp:303, particle_update.comp:84-85): transforms are taken as they are,
@@ -902,12 +912,14 @@ int DDGI_API(refit_accel_device)(anerend_ddgi_t* h, const void* dRenderables, ui
 }
 
 int DDGI_API(get_bvh_info)(anerend_ddgi_t* h, anerend_ddgi_bvh_info_t* o) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   memset(o, 0, sizeof(*o));
   o->num_triangles = h->numTris; o->num_nodes = h->numNodes; o->node_bytes = 80; o->tri_bytes = 48; o->num_instances = (uint32_t)h->instances.size();
   for (int k = 0; k < 3; ++k) { o->bounds_min[k] = h->boundsMin[k]; o->bounds_max[k] = h->boundsMax[k]; }
   return 0;
 }
 int DDGI_API(download_instances)(anerend_ddgi_t* h, anerend_ddgi_instance_t* out, size_t count) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "no acceleration structure");
   if (!out || count != h->instances.size()) return fail(h, ANEREND_DDGI_E_INVALID, "instance count mismatch");
   for (size_t i = 0; i < count; ++i) { const DInstance& in = h->instances[i];
@@ -915,6 +927,7 @@ int DDGI_API(download_instances)(anerend_ddgi_t* h, anerend_ddgi_instance_t* out
   return 0;
 }
 int DDGI_API(download_bvh)(anerend_ddgi_t* h, void* nodes, size_t nb, void* tris, size_t tb) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "no acceleration structure");
   if (nb != (size_t)h->numNodes * 80 || tb != (size_t)h->numTris * 48) return fail(h, ANEREND_DDGI_E_INVALID, "size mismatch");
   BE_CHECK(h, h->be.d2h(nodes, h->dNodes, nb)); BE_CHECK(h, h->be.d2h(tris, h->dBvhTris, tb));
@@ -922,11 +935,13 @@ int DDGI_API(download_bvh)(anerend_ddgi_t* h, void* nodes, size_t nb, void* tris
 }
 
 int DDGI_API(translate)(anerend_ddgi_t* h) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   beginCall(h);
   int rc = translate(h); h->be.mark(1); h->timed[0] = true;
   return rc;
 }
 int DDGI_API(trace_layer)(anerend_ddgi_t* h, int32_t layer, const float rot[16]) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (h->haveUbo && !ddgiOn(h)) return 0;
   if (layer < 0 || layer >= h->nY || !rot) return fail(h, ANEREND_DDGI_E_INVALID, "layer out of range");
   beginCall(h); h->be.mark(1);
@@ -935,6 +950,7 @@ int DDGI_API(trace_layer)(anerend_ddgi_t* h, int32_t layer, const float rot[16])
   return rc;
 }
 int DDGI_API(convolve_layer)(anerend_ddgi_t* h, int32_t layer) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (h->haveUbo && !ddgiOn(h)) return 0;
   if (layer < 0 || layer >= h->nY) return fail(h, ANEREND_DDGI_E_INVALID, "layer out of range");
   beginCall(h); h->be.mark(2);
@@ -943,6 +959,7 @@ int DDGI_API(convolve_layer)(anerend_ddgi_t* h, int32_t layer) {
   return rc;
 }
 int DDGI_API(update)(anerend_ddgi_t* h, int32_t layer, const float* rots) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (h->haveUbo && !ddgiOn(h)) return 0;
   if (!rots || layer >= h->nY) return fail(h, ANEREND_DDGI_E_INVALID, "bad update arguments");
   beginCall(h); h->be.mark(1);
@@ -958,6 +975,7 @@ int DDGI_API(update)(anerend_ddgi_t* h, int32_t layer, const float* rots) {
   return rc;
 }
 int DDGI_API(update_layers)(anerend_ddgi_t* h, const int32_t* layerList, uint32_t n, const float* rots) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (h->haveUbo && !ddgiOn(h)) return 0;
   if (!rots || !layerList || n == 0 || n > (uint32_t)h->nY) return fail(h, ANEREND_DDGI_E_INVALID, "bad update_layers arguments");
   std::vector<uint8_t> seen(h->nY, 0);
@@ -976,6 +994,7 @@ int DDGI_API(update_layers)(anerend_ddgi_t* h, const int32_t* layerList, uint32_
   return rc;
 }
 int DDGI_API(frame)(anerend_ddgi_t* h, const float rot[16], int32_t* layerOut) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   beginCall(h);
   int rc = translate(h); h->be.mark(1); h->timed[0] = true;
   if (rc) return rc;
@@ -1040,10 +1059,12 @@ int shadowRt(anerend_ddgi* h, const float* dDepth, uint32_t width, uint32_t heig
 }
 }  // namespace
 int DDGI_API(shadow_rt_device)(anerend_ddgi_t* h, const void* dDepth, uint32_t width, uint32_t height, void* dOut) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (!dDepth || !dOut) return fail(h, ANEREND_DDGI_E_INVALID, "null argument");
   return shadowRt(h, (const float*)dDepth, width, height, (float*)dOut);
 }
 int DDGI_API(shadow_rt)(anerend_ddgi_t* h, const float* depth, uint32_t width, uint32_t height, float* out) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (!depth || !out) return fail(h, ANEREND_DDGI_E_INVALID, "null argument");
   const size_t n = (size_t)width * height;
   if (n == 0 || !h->haveUbo || !(h->ubo.flags & ANEREND_UBO_RT_SHADOWS_FLAG)) return h->haveUbo ? 0 : fail(h, ANEREND_DDGI_E_STATE, "shadow_rt before set_scene_ubo");
@@ -1112,10 +1133,12 @@ int specularGi(anerend_ddgi* h, const float* dDepth, const float4* dGeom0, uint3
 }
 }  // namespace
 int DDGI_API(specular_gi_device)(anerend_ddgi_t* h, const void* dDepth, const void* dGeom0, uint32_t width, uint32_t height, void* dOut) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (!dDepth || !dGeom0 || !dOut) return fail(h, ANEREND_DDGI_E_INVALID, "null argument");
   return specularGi(h, (const float*)dDepth, (const float4*)dGeom0, width, height, (uint2*)dOut);
 }
 int DDGI_API(specular_gi)(anerend_ddgi_t* h, const float* depth, const float* geom0, uint32_t width, uint32_t height, void* outRgba16f) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (!depth || !geom0 || !outRgba16f) return fail(h, ANEREND_DDGI_E_INVALID, "null argument");
   if (!h->haveUbo) return fail(h, ANEREND_DDGI_E_STATE, "specular_gi before set_scene_ubo");
   const size_t n = (size_t)width * height;
@@ -1145,10 +1168,12 @@ int indirectDiffuse(anerend_ddgi* h, const float4* dPoints, uint32_t count, cons
 }
 }  // namespace
 int DDGI_API(indirect_diffuse_device)(anerend_ddgi_t* h, const void* dPoints, uint32_t count, const float viewPos[3], int32_t clampToEdge, void* dOut) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (!dPoints || !dOut || !viewPos) return fail(h, ANEREND_DDGI_E_INVALID, "null argument");
   return indirectDiffuse(h, (const float4*)dPoints, count, viewPos, clampToEdge, (float4*)dOut);
 }
 int DDGI_API(indirect_diffuse)(anerend_ddgi_t* h, const float* points, uint32_t count, const float viewPos[3], int32_t clampToEdge, float* outRgba) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (!points || !outRgba || !viewPos) return fail(h, ANEREND_DDGI_E_INVALID, "null argument");
   if (count == 0) return 0;
   Backend& be = h->be;
@@ -1161,14 +1186,16 @@ int DDGI_API(indirect_diffuse)(anerend_ddgi_t* h, const float* points, uint32_t 
   return rc;
 }
 
-int DDGI_API(atlas_dims)(const anerend_ddgi_t* h, int32_t* w, int32_t* hh) { *w = h->W; *hh = h->H; return 0; }
+int DDGI_API(atlas_dims)(const anerend_ddgi_t* h, int32_t* w, int32_t* hh) { if (!h) return ANEREND_DDGI_E_INVALID; *w = h->W; *hh = h->H; return 0; }
 int DDGI_API(download_atlas)(anerend_ddgi_t* h, void* out, size_t bytes) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (bytes != (size_t)h->W * h->H * 8) return fail(h, ANEREND_DDGI_E_INVALID, "atlas size mismatch");
   BE_CHECK(h, h->be.d2h(out, h->dAtlas, bytes)); return 0;
 }
 // Row stripe: this handle updates only the probe rows z = offset + k*stride of every layer it launches (sharding inside
 // the layers: with R ranks, rank r takes (r, R) and every rank carries the same share of every layer's work).
 int DDGI_API(set_row_stripe)(anerend_ddgi_t* h, int32_t offset, int32_t stride) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (stride < 1 || offset < 0 || offset >= stride || offset >= h->nXZ) return fail(h, ANEREND_DDGI_E_INVALID, "row stripe out of range");
   h->rowOffset = offset; h->rowStride = stride;
   h->Pl = ((h->nXZ - offset + stride - 1) / stride) * h->nXZ;
@@ -1176,6 +1203,7 @@ int DDGI_API(set_row_stripe)(anerend_ddgi_t* h, int32_t offset, int32_t stride) 
 }
 // The atlas rows of this handle's stripe in all layers, packed in (layer, row) order: rows * nY blocks of 10 atlas rows.
 int DDGI_API(download_atlas_stripe)(anerend_ddgi_t* h, void* out, size_t bytes) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   const size_t rowBytes = (size_t)10 * h->W * 8, rows = (size_t)(h->Pl / h->nXZ);
   if (bytes != rowBytes * rows * h->nY) return fail(h, ANEREND_DDGI_E_INVALID, "stripe size mismatch");
   for (int y = 0; y < h->nY; ++y)
@@ -1185,6 +1213,7 @@ int DDGI_API(download_atlas_stripe)(anerend_ddgi_t* h, void* out, size_t bytes) 
   BE_CHECK(h, h->be.sync()); return 0;
 }
 int DDGI_API(download_atlas_layers)(anerend_ddgi_t* h, const int32_t* layers, uint32_t n, void* out, size_t bytes) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   const size_t layerBytes = (size_t)h->W * h->W * 8;       // 10*nXZ rows of 10*nXZ RGBA16F texels
   if (!layers || bytes != layerBytes * n) return fail(h, ANEREND_DDGI_E_INVALID, "layer block size mismatch");
   for (uint32_t i = 0; i < n; ++i) if (layers[i] < 0 || layers[i] >= h->nY) return fail(h, ANEREND_DDGI_E_INVALID, "layer out of range");
@@ -1197,22 +1226,26 @@ int DDGI_API(download_atlas_layers)(anerend_ddgi_t* h, const int32_t* layers, ui
 // update's tracing overlaps it; the next writer of the atlas (convolution, translation, reset) waits for it on the device.
 // `rgba16f` should be page-locked for the overlap to happen.  _download_wait blocks the host until the bytes have landed.
 int DDGI_API(download_atlas_async)(anerend_ddgi_t* h, void* out, size_t bytes) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (!out || bytes != (size_t)h->W * h->H * 8) return fail(h, ANEREND_DDGI_E_INVALID, "atlas size mismatch");
   if (h->xworld > 1) return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "asynchronous read-back with a connected exchange (peers write this atlas)");
   BE_CHECK(h, h->be.d2hBackground(out, h->dAtlas, bytes)); return 0;
 }
-int DDGI_API(download_wait)(anerend_ddgi_t* h) { BE_CHECK(h, h->be.waitDownload()); return 0; }
+int DDGI_API(download_wait)(anerend_ddgi_t* h) { if (!h) return ANEREND_DDGI_E_INVALID; BE_CHECK(h, h->be.waitDownload()); return 0; }
 int DDGI_API(upload_atlas)(anerend_ddgi_t* h, const void* in, size_t bytes) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (bytes != (size_t)h->W * h->H * 8) return fail(h, ANEREND_DDGI_E_INVALID, "atlas size mismatch");
   BE_CHECK(h, h->be.waitDownload()); BE_CHECK(h, h->be.sync()); BE_CHECK(h, h->be.h2d(h->dAtlas, in, bytes)); BE_CHECK(h, h->be.sync()); return 0;
 }
-int DDGI_API(atlas_device_ptr)(anerend_ddgi_t* h, void** p, size_t* bytes) { *p = h->dAtlas; *bytes = (size_t)h->W * h->H * 8; return 0; }
+int DDGI_API(atlas_device_ptr)(anerend_ddgi_t* h, void** p, size_t* bytes) { if (!h) return ANEREND_DDGI_E_INVALID; *p = h->dAtlas; *bytes = (size_t)h->W * h->H * 8; return 0; }
 int DDGI_API(set_peer_atlases)(anerend_ddgi_t* h, void* const* peers, uint32_t n) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (n > 8) return fail(h, ANEREND_DDGI_E_INVALID, "at most 8 peers");
   for (uint32_t i = 0; i < n; ++i) h->peers[i] = (uint2*)peers[i];
   h->numPeers = (int)n; return 0;
 }
 int DDGI_API(exchange_export)(anerend_ddgi_t* h, void* blob, size_t bytes) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
 #ifndef DDGI_HOST_EMU
   if (!blob || bytes != ANEREND_DDGI_EXCHANGE_BLOB_BYTES) return fail(h, ANEREND_DDGI_E_INVALID, "exchange blob size mismatch");
   static_assert(2 * sizeof(cudaIpcMemHandle_t) == ANEREND_DDGI_EXCHANGE_BLOB_BYTES, "blob = two cudaIpcMemHandle_t");
@@ -1230,6 +1263,7 @@ int DDGI_API(exchange_export)(anerend_ddgi_t* h, void* blob, size_t bytes) {
 #endif
 }
 int DDGI_API(exchange_connect)(anerend_ddgi_t* h, const void* blobs, uint32_t world, uint32_t rank) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
 #ifndef DDGI_HOST_EMU
   if (!blobs || world < 2 || world > 8 || rank >= world) return fail(h, ANEREND_DDGI_E_INVALID, "exchange_connect: 2..8 ranks");
   if (!h->dXflags) return fail(h, ANEREND_DDGI_E_STATE, "exchange_connect before exchange_export");
@@ -1255,11 +1289,12 @@ int DDGI_API(exchange_connect)(anerend_ddgi_t* h, const void* blobs, uint32_t wo
   (void)blobs; (void)world; (void)rank; return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "no peer exchange in the host harness");
 #endif
 }
-int DDGI_API(exchange_disconnect)(anerend_ddgi_t* h) { exchangeDisconnect(h); return 0; }
-int DDGI_API(stream)(anerend_ddgi_t* h, void** s) { *s = (void*)h->be.stream; return 0; }
+int DDGI_API(exchange_disconnect)(anerend_ddgi_t* h) { if (!h) return ANEREND_DDGI_E_INVALID; exchangeDisconnect(h); return 0; }
+int DDGI_API(stream)(anerend_ddgi_t* h, void** s) { if (!h) return ANEREND_DDGI_E_INVALID; *s = (void*)h->be.stream; return 0; }
 
-int DDGI_API(ray_tile)(const anerend_ddgi_t* h, int32_t* sx, int32_t* sy) { *sx = h->Sx; *sy = h->Sy; return 0; }
+int DDGI_API(ray_tile)(const anerend_ddgi_t* h, int32_t* sx, int32_t* sy) { if (!h) return ANEREND_DDGI_E_INVALID; *sx = h->Sx; *sy = h->Sy; return 0; }
 int DDGI_API(download_rays)(anerend_ddgi_t* h, int32_t layer, void* irrOut, void* dirOut, size_t bytesEach) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (layer < 0 || layer >= h->nY || !h->layerTraced[layer]) return fail(h, ANEREND_DDGI_E_STATE, "no rays for this layer");
   const size_t n = (size_t)h->P * h->N;
   if (bytesEach != n * 8) return fail(h, ANEREND_DDGI_E_INVALID, "ray image size mismatch");
@@ -1277,17 +1312,20 @@ int DDGI_API(download_rays)(anerend_ddgi_t* h, int32_t layer, void* irrOut, void
   return 0;
 }
 int DDGI_API(download_ray_records)(anerend_ddgi_t* h, int32_t layer, anerend_ddgi_ray_record_t* out, size_t count) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (!h->dRecords) return fail(h, ANEREND_DDGI_E_STATE, "FLAG_RAY_RECORDS not set");
   if (layer < 0 || layer >= h->nY || count != (size_t)h->P * h->N || !h->layerTraced[layer]) return fail(h, ANEREND_DDGI_E_INVALID, "no records for this layer / count mismatch");
   BE_CHECK(h, h->be.d2h(out, h->dRecords + (size_t)layer * count, count * sizeof(*out))); return 0;
 }
 int DDGI_API(download_texel_records)(anerend_ddgi_t* h, float* out, size_t bytes) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   if (!h->dTexelRecords) return fail(h, ANEREND_DDGI_E_STATE, "FLAG_TEXEL_RECORDS not set");
   if (bytes != (size_t)h->W * h->H * 16) return fail(h, ANEREND_DDGI_E_INVALID, "size mismatch");
   BE_CHECK(h, h->be.d2h(out, h->dTexelRecords, bytes)); return 0;
 }
 
 int DDGI_API(get_timings)(anerend_ddgi_t* h, anerend_ddgi_timings_t* o) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   BE_CHECK(h, h->be.sync());
   memset(o, 0, sizeof(*o));
   if (h->timed[0]) o->trans_ms = h->be.elapsed(0, 1);
@@ -1301,13 +1339,14 @@ int DDGI_API(get_timings)(anerend_ddgi_t* h, anerend_ddgi_timings_t* o) {
   return 0;
 }
 int DDGI_API(get_stats)(anerend_ddgi_t* h, anerend_ddgi_stats_t* o) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
   unsigned long long s[8];
   BE_CHECK(h, h->be.d2h(s, h->dStats, sizeof(s)));
   o->primary_rays = s[0]; o->primary_hits = s[1]; o->shadow_rays = s[2]; o->primary_nodes_visited = s[3]; o->primary_tris_tested = s[4];
   o->shadow_nodes_visited = s[5]; o->shadow_tris_tested = s[6];
   return 0;
 }
-int DDGI_API(reset_stats)(anerend_ddgi_t* h) { BE_CHECK(h, h->be.zero(h->dStats, 8 * sizeof(unsigned long long))); return 0; }
+int DDGI_API(reset_stats)(anerend_ddgi_t* h) { if (!h) return ANEREND_DDGI_E_INVALID; BE_CHECK(h, h->be.zero(h->dStats, 8 * sizeof(unsigned long long))); return 0; }
 
 // glm::rotate(mat4(1), radians(deg), axis) (IrradianceProbeRayTracingPass.cpp:133; glm/ext/matrix_transform.inl:18-46)
 int DDGI_API(make_rotation)(int32_t axisIdx, float deg, float out[16]) {

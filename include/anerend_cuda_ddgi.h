@@ -11,7 +11,9 @@
  * Conventions: every function returns 0 on success or a negative ANEREND_DDGI_E_*
  * code (never throws, no global state besides the opaque handle);
  * anerend_cuda_ddgi_last_error(h) returns a human-readable message for the last
- * failure on that handle.  A handle is not thread-safe; all device work of a
+ * failure on that handle.  A NULL handle is ANEREND_DDGI_E_INVALID for every entry
+ * point (_destroy(NULL) is a no-op returning 0, _last_error(NULL) returns "null
+ * handle").  A handle is not thread-safe; all device work of a
  * handle is issued on one CUDA stream in call order and is asynchronous with
  * respect to the host until _sync or a _download_* call.  Host pointers passed in
  * are only read during the call.  There is NO CPU fallback: every entry point that

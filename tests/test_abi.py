@@ -29,6 +29,25 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in lib.anerend_cuda_ddgi_version()
 
 
+def test_null_handle_is_an_error_not_a_crash():
+    """Header conventions: every entry point taking the handle first returns ANEREND_DDGI_E_INVALID (-1) for NULL (no device needed)."""
+    import __graft_entry__ as g
+    lib = ctypes.CDLL(g.build_cuda())
+    src = open(os.path.join(ROOT, "include", "anerend_cuda_ddgi.h")).read()
+    decls = re.findall(r"\bint\s+(anerend_cuda_ddgi_[a-z_0-9]+)\s*\(\s*(?:const\s+)?anerend_ddgi_t\s*\*\s*h\b([^;]*)\)\s*;", src)
+    assert len(decls) >= 45
+    for name, rest in decls:
+        fn = getattr(lib, name)
+        nargs = 1 + (rest.count(",") if rest.strip() else 0)
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.c_void_p] * nargs         # pointers and small integers all travel as 8-byte zeros here
+        rc = fn(*([None] * nargs))
+        assert rc == (0 if name.endswith("_destroy") else -1), name
+    lib.anerend_cuda_ddgi_last_error.restype = ctypes.c_char_p
+    lib.anerend_cuda_ddgi_last_error.argtypes = [ctypes.c_void_p]
+    assert lib.anerend_cuda_ddgi_last_error(None) == b"null handle"
+
+
 def test_oracle_mirrors_the_abi():
     src = open(os.path.join(ROOT, "oracle", "ddgi_oracle.h")).read()
     oracle_names = set(re.findall(r"\bddgi_oracle_([a-z_0-9]+)\s*\(", src))
