@@ -132,6 +132,11 @@ def main():
     hits = [(l, p, r) for l in range(ny) for p in range(nxz * nxz) for r in range(nr) if recs[l][p, r]["prim"] != 0xFFFFFFFF]
     pick = [hits[k] for k in rng.choice(len(hits), SAMPLES, replace=False)]
     mirror = np.zeros((SAMPLES, 4), np.float32); origins = np.zeros((SAMPLES, 3), np.float32)
+    # baked tiles (quirk Q5 / SURVEY 8f N4): a checkerboard of the 21 x 21 paged tiles has a baked atlas (bindless index 0), so hits on those
+    # tiles place the probe grid on the 32 m tile (pbr_light.glsl:251-273) while the hit shader keeps sampling the live atlas
+    tile_pattern = np.array([0 if (i % 21 + i // 21) % 2 == 0 else -1 for i in range(441)], np.int32)
+    o.upload_tile_infos(tile_pattern)
+    tiled = np.zeros((SAMPLES, 3), np.float32)
     out = np.zeros((SAMPLES, 3), np.float32); meta = np.zeros((SAMPLES, 3), np.int64); prim_uv = np.zeros((SAMPLES, 3), np.float64); lit = np.zeros(SAMPLES, np.int64)
     for k, (layer, probe, ray) in enumerate(pick):
         rec = recs[layer][probe, ray]
@@ -179,13 +184,22 @@ def main():
         minv.run()
         mres = minv.g[mpay_gid].load()
         mirror[k] = [*mres[0], mres[1]]; origins[k] = origin
+        # the probe hit shader again, with the tile-info buffer filled
+        tbind = dict(bind)
+        tbind.update({"tileInfoBuffer": [[[int(t)] for t in tile_pattern]], "probeTex": Sampler(atlas2), "payload": [[f32(0)] * 3, [f32(0)] * 3, f32(0)],
+                      "shadowPayload": [[f32(0)] * 3, [f32(0)] * 3, f32(0)], "traceRay": trace})
+        tinv = Invocation(m, tbind)
+        tinv.run()
+        tiled[k] = tinv.g[pay_gid].load()[0]
         assert len(mcalls) == 1 and [float(c) for c in mcalls[0][0]] == [float(c) for c in shadow_calls[0][0]]      # same shadow ray as the probe shader
         meta[k] = (layer, probe, ray); prim_uv[k] = (prim, rec["u"], rec["v"]); lit[k] = int(rec["lit_mask"]) & 1
         if k % 16 == 0 or os.environ.get("RCHIT_VERBOSE"):
             print(k, "binary:", out[k], "oracle:", rec["radiance"], "lit", lit[k], "material", mat)
-            print("   mirror binary:", mirror[k], "oracle:", o.shade_hit(prim, rec["u"], rec["v"], origin, specular=True)[:2])
+            print("   tiled binary:", tiled[k], "oracle:", o.shade_hit(prim, rec["u"], rec["v"], origin)[0])
+            print("   mirror binary:", mirror[k])
     dst = os.path.join(HERE, "rchit_golden.npz")
-    np.savez_compressed(dst, rays=meta, prim_uv=prim_uv, lit=lit, irradiance=out, grid=np.array(GRID), origins=origins, mirror=mirror)
+    np.savez_compressed(dst, rays=meta, prim_uv=prim_uv, lit=lit, irradiance=out, grid=np.array(GRID), origins=origins, mirror=mirror, tiled=tiled,
+                        tile_pattern=tile_pattern)
     print("wrote", dst)
 
 

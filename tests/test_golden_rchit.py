@@ -42,7 +42,18 @@ def test_oracle_hit_shading_equals_the_compiled_reference_shader(oracle):
         rad, dist, lit = o.shade_hit(int(prim), u, v, G["origins"][k], specular=True)
         mgot[k] = (*rad, dist)
         assert (lit & 1) == G["lit"][k]
+    # and through the probe hit shader with baked tiles paged in (quirk Q5 / SURVEY 8f N4): hits on those tiles place the grid on the tile
+    shade = lambda k: o.shade_hit(int(G["prim_uv"][k][0]), G["prim_uv"][k][1], G["prim_uv"][k][2], G["origins"][k])[0]
+    plain = np.stack([shade(k) for k in range(len(G["rays"]))])
+    o.upload_tile_infos(G["tile_pattern"])
+    tgot = np.stack([shade(k) for k in range(len(G["rays"]))])
     o.close()
+    twant = G["tiled"]
+    trel = np.abs(tgot - twant) / np.maximum(np.abs(twant), 1e-6)
+    assert trel.max() <= 2e-6, f"tiled: max relative difference {trel.max():.3e}"
+    assert (tgot.view(np.uint32) == twant.view(np.uint32)).mean() > 0.9
+    moved = (np.abs(tgot - plain).max(axis=1) > 0).mean()
+    assert 0.2 < moved < 0.8, moved                                             # the checkerboard: some hits are on baked tiles, some are not
     mwant = G["mirror"]
     assert np.array_equal(mgot[:, 3], mwant[:, 3])                              # distance(pos, gl_WorldRayOriginEXT): bit-exact
     mrel = np.abs(mgot[:, :3] - mwant[:, :3]) / np.maximum(np.abs(mwant[:, :3]), 1e-6)
