@@ -61,6 +61,10 @@ class Sampler:
         return [f32(f32(f32(f32(t00[k] * w00) + f32(t10[k] * w10)) + f32(t01[k] * w01)) + f32(t11[k] * w11)) for k in range(4)]
 
 
+def _copy_nested(x):
+    return [_copy_nested(c) for c in x] if isinstance(x, list) else x
+
+
 def decode_texture(px, fmt, lut):
     from anerend_b200 import layouts as L
     h, w = px.shape[:2]
@@ -137,6 +141,12 @@ def main():
     tile_pattern = np.array([0 if (i % 21 + i // 21) % 2 == 0 else -1 for i in range(441)], np.int32)
     o.upload_tile_infos(tile_pattern)
     tiled = np.zeros((SAMPLES, 3), np.float32)
+    # bake mode: UBO_BAKE_MODE_ON_FLAG places the grid on tile bakeTileInfo.xy of size bakeTileInfo.z (pbr_light.glsl:274-291)
+    bake_tile = (-1, -1, 48, 0)
+    baked = np.zeros((SAMPLES, 3), np.float32)
+    bubo = _copy_nested(ubo)
+    bubo[m.struct_member(ubo_t, "flags")] = int(u["flags"]) | (1 << 11)
+    bubo[m.struct_member(ubo_t, "bakeTileInfo")] = [int(x) for x in bake_tile]
     out = np.zeros((SAMPLES, 3), np.float32); meta = np.zeros((SAMPLES, 3), np.int64); prim_uv = np.zeros((SAMPLES, 3), np.float64); lit = np.zeros(SAMPLES, np.int64)
     for k, (layer, probe, ray) in enumerate(pick):
         rec = recs[layer][probe, ray]
@@ -191,6 +201,12 @@ def main():
         tinv = Invocation(m, tbind)
         tinv.run()
         tiled[k] = tinv.g[pay_gid].load()[0]
+        bbind = dict(bind)
+        bbind.update({"ubo": bubo, "probeTex": Sampler(atlas2), "payload": [[f32(0)] * 3, [f32(0)] * 3, f32(0)],
+                      "shadowPayload": [[f32(0)] * 3, [f32(0)] * 3, f32(0)], "traceRay": trace})
+        binv = Invocation(m, bbind)
+        binv.run()
+        baked[k] = binv.g[pay_gid].load()[0]
         assert len(mcalls) == 1 and [float(c) for c in mcalls[0][0]] == [float(c) for c in shadow_calls[0][0]]      # same shadow ray as the probe shader
         meta[k] = (layer, probe, ray); prim_uv[k] = (prim, rec["u"], rec["v"]); lit[k] = int(rec["lit_mask"]) & 1
         if k % 16 == 0 or os.environ.get("RCHIT_VERBOSE"):
@@ -199,7 +215,7 @@ def main():
             print("   mirror binary:", mirror[k])
     dst = os.path.join(HERE, "rchit_golden.npz")
     np.savez_compressed(dst, rays=meta, prim_uv=prim_uv, lit=lit, irradiance=out, grid=np.array(GRID), origins=origins, mirror=mirror, tiled=tiled,
-                        tile_pattern=tile_pattern)
+                        tile_pattern=tile_pattern, baked=baked, bake_tile=np.array(bake_tile))
     print("wrote", dst)
 
 

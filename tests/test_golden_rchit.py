@@ -45,6 +45,16 @@ def test_oracle_hit_shading_equals_the_compiled_reference_shader(oracle):
     # and through the probe hit shader with baked tiles paged in (quirk Q5 / SURVEY 8f N4): hits on those tiles place the grid on the tile
     shade = lambda k: o.shade_hit(int(G["prim_uv"][k][0]), G["prim_uv"][k][1], G["prim_uv"][k][2], G["origins"][k])[0]
     plain = np.stack([shade(k) for k in range(len(G["rays"]))])
+    # bake mode: the grid is placed on tile bakeTileInfo.xy of size bakeTileInfo.z (pbr_light.glsl:274-291)
+    bake_ubo = scene.ubo.copy()
+    bake_ubo["flags"] |= L.UBO_BAKE_MODE_ON_FLAG
+    bake_ubo["bake_tile_info"][0] = G["bake_tile"]
+    o.set_scene_ubo(bake_ubo)
+    bgot = np.stack([shade(k) for k in range(len(G["rays"]))])
+    o.set_scene_ubo(scene.ubo)
+    brel = np.abs(bgot - G["baked"]) / np.maximum(np.abs(G["baked"]), 1e-6)
+    assert brel.max() <= 2e-6, f"bake mode: max relative difference {brel.max():.3e}"
+    assert (np.abs(bgot - plain).max(axis=1) > 0).mean() > 0.9
     o.upload_tile_infos(G["tile_pattern"])
     tgot = np.stack([shade(k) for k in range(len(G["rays"]))])
     o.close()
