@@ -31,4 +31,4 @@ def test_oracle_calc_light_equals_the_compiled_reference_function(oracle):
         assert (want[sel].max(axis=1) > 0).sum() >= 30              # both branches are exercised
     rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-12)
     assert rel.max() <= 4e-6, f"max relative difference {rel.max():.3e}"
-    assert (got.view(np.uint32) == want.view(np.uint32)).mean() > 0.6
+    assert (got.view(np.uint32) == want.view(np.uint32)).mean() > 0.95          # in fact every value is bit-identical here
