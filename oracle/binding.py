@@ -36,6 +36,57 @@ def lib():
     return _LIB
 
 
+REF_ROOT = os.environ.get("ANEREND_REFERENCE", "/root/reference")
+_REF = None
+
+
+def build_ref(force=False):
+    """oracle/_ref/libanerend_ref_host.so: the reference's own struct headers and glm compiled from /root/reference (oracle/Makefile).
+    Returns the path, or None when neither the reference nor a previously built library is there (the GPU box gets the built file)."""
+    so = os.path.join(_HERE, "_ref", "libanerend_ref_host.so")
+    if os.path.isdir(os.path.join(REF_ROOT, "contrib", "glm", "include")):
+        src = os.path.join(_HERE, "ref_host_shim.cpp")
+        if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "REF=" + REF_ROOT, "_ref/libanerend_ref_host.so"], stdout=subprocess.DEVNULL)
+    return so if os.path.exists(so) else None
+
+
+def ref_lib():
+    global _REF
+    if _REF is None:
+        so = build_ref()
+        if so is None:
+            return None
+        _REF = C.CDLL(so)
+        _REF.ref_host_layout.restype = C.c_size_t
+        _REF.ref_host_layout.argtypes = [C.c_char_p, C.c_size_t]
+    return _REF
+
+
+def ref_layout():
+    """({'Struct.field': (offset, size), 'Struct': (0, sizeof)}, {'FLAG': value}) from the reference's compiled headers, or None."""
+    lib_ = ref_lib()
+    if lib_ is None:
+        return None
+    n = lib_.ref_host_layout(None, 0)
+    buf = C.create_string_buffer(n + 1)
+    lib_.ref_host_layout(buf, n + 1)
+    fields, flags = {}, {}
+    for line in buf.value.decode().splitlines():
+        a = line.split()
+        if a[0] == "flag":
+            flags[a[1]] = int(a[2])
+        else:
+            fields[a[0]] = (int(a[1]), int(a[2]))
+    return fields, flags
+
+
+def ref_make_rotation(axis, deg):
+    out = np.empty(16, np.float32)
+    ref_lib().ref_host_make_rotation(C.c_int(axis), C.c_float(deg), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 class Oracle(DdgiHandle):
     def __init__(self, params):
         super().__init__(lib(), "ddgi_oracle_", params)
