@@ -81,6 +81,12 @@ def ref_layout():
     return fields, flags
 
 
+def ref_render_option_defaults():
+    out = np.empty(13, np.float32)
+    ref_lib().ref_host_render_option_defaults(out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 def ref_make_rotation(axis, deg):
     out = np.empty(16, np.float32)
     ref_lib().ref_host_make_rotation(C.c_int(axis), C.c_float(deg), out.ctypes.data_as(C.c_void_p))

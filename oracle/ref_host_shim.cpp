@@ -1,6 +1,7 @@
 // ref_host_shim.cpp — oracle/_ref: the parts of the REFERENCE'S OWN HOST CODE on the DDGI path that compile in this image, built from
 // the sources where they lie under /root/reference (oracle/Makefile, target _ref/libanerend_ref_host.so; never copied into this repo):
 //   * src/anerend/render/GpuBuffers.h and Vertex.h — the structs behind the bindless buffers and the scene UBO;
+//   * src/anerend/render/RenderOptions.h — the defaults the synthetic scenes' UBO starts from;
 //   * contrib/glm — glm::rotate / glm::radians exactly as IrradianceProbeRayTracingPass.cpp:115-133 calls them (A3).
 // TEST INFRASTRUCTURE ONLY: loaded by tests/ and tests/golden/make_ref_host_golden.py; nothing under anerend_b200/ uses it.
 // The GLSL stages and the Vulkan host code cannot be built here; their compiled SPIR-V is executed instead.
@@ -12,6 +13,7 @@
 #include <glm/gtc/matrix_transform.hpp>
 
 #include "GpuBuffers.h"
+#include "RenderOptions.h"
 #include "Vertex.h"
 
 namespace {
@@ -48,6 +50,14 @@ size_t ref_host_layout(char* buf, size_t cap) {
   for (const Field& f : kFields) n += (size_t)snprintf(buf ? buf + n : nullptr, buf && cap > n ? cap - n : 0, "%s %zu %zu\n", f.name, f.offset, f.size);
   for (const Flag& f : kFlags) n += (size_t)snprintf(buf ? buf + n : nullptr, buf && cap > n ? cap - n : 0, "flag %s %u\n", f.name, f.value);
   return n;
+}
+// RenderOptions{} as the renderer starts with: sunIntensity, skyIntensity, exposure, skyColor.rgb, bloomThresh, bloomKnee, then the
+// switches raytracingEnabled, ddgiEnabled, multiBounceDdgiEnabled, specularGiEnabled, raytracedShadows as 0/1
+void ref_host_render_option_defaults(float out[13]) {
+  render::RenderOptions o;
+  const float v[13] = {o.sunIntensity, o.skyIntensity, o.exposure, o.skyColor.x, o.skyColor.y, o.skyColor.z, o.bloomThresh, o.bloomKnee,
+                       (float)o.raytracingEnabled, (float)o.ddgiEnabled, (float)o.multiBounceDdgiEnabled, (float)o.specularGiEnabled, (float)o.raytracedShadows};
+  std::memcpy(out, v, sizeof(v));
 }
 // IrradianceProbeRayTracingPass.cpp:120-133: rotAx from the axis index, glm::rotate(glm::mat4(1.0f), glm::radians(float(angle)), rotAx)
 void ref_host_make_rotation(int axis, float angle_deg, float out[16]) {

@@ -37,6 +37,7 @@ def test_golden_is_what_the_compiled_reference_headers_report(oracle):
     assert {k: list(v) for k, v in fields.items()} == G["layout"] and flags == G["flags"]
     for r in G["rotations"][::7]:
         assert [int(x) for x in oracle.ref_make_rotation(r["axis"], r["angle_deg"]).view(np.uint32)] == r["bits"]
+    assert [float(x) for x in oracle.ref_render_option_defaults()] == G["render_option_defaults"]
 
 
 def test_c_header_layouts_equal_the_reference_structs(tmp_path):
@@ -80,3 +81,14 @@ def test_rotation_matrices_equal_glm_rotate_bit_for_bit(oracle):
         assert lib.anerend_cuda_ddgi_make_rotation(ctypes.c_int32(r["axis"]), ctypes.c_float(r["angle_deg"]), out.ctypes.data_as(ctypes.c_void_p)) == 0
         assert np.array_equal(out.view(np.uint32), want), ("product", r["axis"], r["angle_deg"])
         assert np.array_equal(oracle.make_rotation(r["axis"], r["angle_deg"]).view(np.uint32), want), ("oracle", r["axis"], r["angle_deg"])
+
+
+def test_synthetic_scene_ubo_starts_from_the_reference_render_option_defaults():
+    from anerend_b200 import scenes
+    d = G["render_option_defaults"]            # RenderOptions.h:7-28, compiled
+    u = scenes.make_ubo((0.0, 0.0, 0.0))[0]
+    assert [float(u["sun_intensity"]), float(u["sky_intensity"]), float(u["exposure"])] == d[0:3]
+    assert [float(np.float32(c)) for c in u["sky_color"][:3]] == d[3:6] and [float(u["bloom_thresh"]), float(u["bloom_knee"])] == d[6:8]
+    # raytracingEnabled, ddgiEnabled, multiBounceDdgiEnabled are on by default (VulkanRenderer.cpp:1222-1232 turns them into flags)
+    assert d[8:11] == [1.0, 1.0, 1.0]
+    assert int(u["flags"]) & (L.UBO_RT_ON_FLAG | L.UBO_DDGI_FLAG | L.UBO_DDGI_MULTI_FLAG) == L.UBO_RT_ON_FLAG | L.UBO_DDGI_FLAG | L.UBO_DDGI_MULTI_FLAG
