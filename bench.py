@@ -120,8 +120,9 @@ def run_oracle_sample(scene, grid, layers, threads=0, point_lights=True):
 
 
 def reference_arm(args, rank, world):
-    """The reference's CPU implementation of the path = the oracle (there is no oracle/_ref: GLSL + Vulkan RT cannot
-    be built here).  Rank 0 alone runs; each step is a bounded sample (one Y-layer) of the workload."""
+    """The reference's CPU implementation of the path = the oracle (the path itself — GLSL + Vulkan RT — cannot be built here;
+    oracle/_ref only holds the reference's struct headers and glm::rotate).  Rank 0 alone runs; each step is a bounded sample
+    (one Y-layer) of the workload."""
     if rank != 0:
         return
     name = args.workload or ("c3" if world == 1 else "c5")
@@ -145,7 +146,7 @@ def reference_arm(args, rank, world):
     value = per_step * args.steps / dt / 1e6
     sample = f"{args.steps} steps x 1 Y-layer ({per_step} primary rays + their shadow rays) of {name}"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_desc(name, scene, grid, 1),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
