@@ -1,4 +1,5 @@
-// anerend_ddgi_passes.hpp — header-only adapter: the three DDGI passes (and ShadowRT / SpecularGIRT) as AneRend `RenderPass` subclasses that call
+// anerend_ddgi_passes.hpp — header-only adapter: the three DDGI passes (plus TLASUpdate / BLASUpdate in front of them and ShadowRT /
+// SpecularGIRT on the same acceleration structure) as AneRend `RenderPass` subclasses that call
 // the C ABI (anerend_cuda_ddgi.h) instead of recording Vulkan ray-tracing/compute/transfer commands.
 //
 // Mirrors, name for name:
@@ -31,6 +32,7 @@ struct Volume {
   anerend_ddgi_t* handle = nullptr;
   anerend_ddgi_params_t params{};
   std::string error;
+  bool topologyDirty = true;      // set by the engine when instances appear / disappear / flip visibility: TLASUpdate rebuilds instead of refitting
   ~Volume() { if (handle) anerend_cuda_ddgi_destroy(handle); }
   // Called from registerToGraph: the reference re-registers the same pass objects on swap-chain recreation
   // (VulkanRenderer.cpp:1962-2000), re-creating and re-clearing the atlas and resetting _currentLayer.
@@ -183,6 +185,71 @@ public:
       if (!depth || !geom0 || !out) return;
       anerend_cuda_ddgi_set_scene_ubo(_vol->handle, exeParams.rc->sceneUbo());
       if (anerend_cuda_ddgi_specular_gi_device(_vol->handle, depth, geom0, exeParams.rc->screenWidth(), exeParams.rc->screenHeight(), out) != 0)
+        std::printf("%s\n", anerend_cuda_ddgi_last_error(_vol->handle));
+    });
+  }
+private:
+  std::shared_ptr<Volume> _vol;
+};
+
+// -----------------------------------------------------------------------------------------------------------------
+// The acceleration-structure passes in front of the chain.  The reference fills the TLAS instance buffer with
+// tlas_update.comp and rebuilds the TLAS every frame ("TLASUpdate", UpdateTLASPass.cpp:77-248), and refits the BLASes of skinned
+// meshes from the giga vertex buffer ("BLASUpdate", UpdateBlasPass.cpp:14-207).  Here both become calls on the volume's handle:
+// the device RenderableBuffer is re-flattened and the hierarchy refitted; deforming vertices are copied first.  The engine
+// tells the adapter when the set of instances changed (an asset upload, a visibility flip) through Volume::topologyDirty —
+// then the next TLASUpdate rebuilds (anerend_cuda_ddgi_build_accel) instead of refitting.  Two additions to RenderContext next
+// to cudaResource(name): getCurrentNumRenderables() (already there, RenderContext.h:135) and dynamicVertexRange(first, count),
+// the range of GigaVtxBuffer the skinning pass wrote this frame (false: nothing moved).
+
+template <class Engine>
+class UpdateTLASPass : public Engine::RenderPass {                // src/anerend/render/passes/UpdateTLASPass.{h,cpp}, "TLASUpdate"
+public:
+  explicit UpdateTLASPass(std::shared_ptr<Volume> v) : _vol(std::move(v)) {}
+  void registerToGraph(typename Engine::FrameGraphBuilder& fgb, typename Engine::RenderContext*) override final {
+    typename Engine::RenderPassRegisterInfo info{};
+    info._name = "TLASUpdate";
+    for (const char* n : {"TLASInstanceBuf", "TLASCounterBuf", "RenderableBuffer"}) {        // UpdateTLASPass.cpp:80-117
+      typename Engine::ResourceUsage u{}; u._resourceName = n; info._resourceUsages.emplace_back(std::move(u));
+    }
+    fgb.registerRenderPass(std::move(info));
+    fgb.registerRenderPassExe("TLASUpdate", [this](typename Engine::RenderExeParams exeParams) {
+      if (!_vol->handle) return;
+      if (!exeParams.rc->getRenderOptions().raytracingEnabled) return;                       // UpdateTLASPass.cpp:130
+      int rc = 0;
+      if (_vol->topologyDirty) {                                                              // instances changed: select + flatten + build
+        rc = anerend_cuda_ddgi_build_accel(_vol->handle);
+        if (rc == 0) _vol->topologyDirty = false;
+      } else {
+        void* rend = exeParams.rc->cudaResource("RenderableBuffer");                         // GPU-written earlier in the frame (cull.comp:303)
+        if (!rend) return;
+        rc = anerend_cuda_ddgi_refit_accel_device(_vol->handle, rend, (uint32_t)exeParams.rc->getCurrentNumRenderables());
+      }
+      if (rc != 0) std::printf("%s\n", anerend_cuda_ddgi_last_error(_vol->handle));
+    });
+  }
+private:
+  std::shared_ptr<Volume> _vol;
+};
+
+template <class Engine>
+class UpdateBlasPass : public Engine::RenderPass {                // src/anerend/render/passes/UpdateBlasPass.{h,cpp}, "BLASUpdate"
+public:
+  explicit UpdateBlasPass(std::shared_ptr<Volume> v) : _vol(std::move(v)) {}
+  void registerToGraph(typename Engine::FrameGraphBuilder& fgb, typename Engine::RenderContext*) override final {
+    typename Engine::RenderPassRegisterInfo info{};
+    info._name = "BLASUpdate";
+    { typename Engine::ResourceUsage u{}; u._resourceName = "GigaVtxBuffer"; info._resourceUsages.emplace_back(std::move(u)); }   // UpdateBlasPass.cpp:24-32
+    fgb.registerRenderPass(std::move(info));
+    fgb.registerRenderPassExe("BLASUpdate", [this](typename Engine::RenderExeParams exeParams) {
+      if (!_vol->handle) return;
+      if (!exeParams.rc->getRenderOptions().raytracingEnabled) return;                       // UpdateBlasPass.cpp:37
+      uint32_t first = 0, count = 0;
+      if (!exeParams.rc->dynamicVertexRange(&first, &count) || count == 0) return;           // no dynamic BLAS this frame (:41)
+      const char* vtx = static_cast<const char*>(exeParams.rc->cudaResource("GigaVtxBuffer"));
+      if (!vtx) return;
+      // the following TLASUpdate refits triangles, boxes and shading records from the new vertices
+      if (anerend_cuda_ddgi_update_vertices_device(_vol->handle, vtx + (size_t)first * sizeof(anerend_vertex_t), first, count) != 0)
         std::printf("%s\n", anerend_cuda_ddgi_last_error(_vol->handle));
     });
   }

@@ -27,6 +27,9 @@ struct RenderContext {
   const anerend_scene_ubo_t* sceneUbo() { return &ubo; }
   std::map<std::string, void*> cuda;            // device pointers of frame-graph images (none in this stub: the passes no-op)
   void* cudaResource(const char* name) { auto it = cuda.find(name); return it == cuda.end() ? nullptr : it->second; }
+  size_t numRenderables = 0; uint32_t dynFirst = 0, dynCount = 0;
+  size_t getCurrentNumRenderables() { return numRenderables; }
+  bool dynamicVertexRange(uint32_t* first, uint32_t* count) { *first = dynFirst; *count = dynCount; return dynCount != 0; }
   uint32_t screenWidth() { return ubo.screen_width; }
   uint32_t screenHeight() { return ubo.screen_height; }
 };
@@ -74,6 +77,18 @@ int main(int argc, char** argv) {
         g2.passes[1]._resourceUsages[3]._resourceName != "ProbeRaysConvTex") { printf("FAIL ray pass names\n"); return 1; }
     g2.executeGraph(&rc);
   }
+  UpdateBlasPass<stub::Engine> blas(vol);
+  UpdateTLASPass<stub::Engine> tlas(vol);
+  {  // the acceleration-structure passes: names and resource usages as the reference declares them
+    stub::FrameGraphBuilder g3;
+    blas.registerToGraph(g3, &rc); tlas.registerToGraph(g3, &rc);
+    if (g3.passes.size() != 2 || g3.passes[0]._name != "BLASUpdate" || g3.passes[0]._resourceUsages.size() != 1 ||
+        g3.passes[0]._resourceUsages[0]._resourceName != "GigaVtxBuffer" || g3.passes[1]._name != "TLASUpdate" ||
+        g3.passes[1]._resourceUsages.size() != 3 || g3.passes[1]._resourceUsages[0]._resourceName != "TLASInstanceBuf" ||
+        g3.passes[1]._resourceUsages[2]._resourceName != "RenderableBuffer") { printf("FAIL accel pass names\n"); return 1; }
+    rc.opts.raytracingEnabled = false; g3.executeGraph(&rc); rc.opts.raytracingEnabled = true;       // gated off: no call, no error
+    if (!vol->topologyDirty) { printf("FAIL accel gating\n"); return 1; }
+  }
   std::vector<stub::RenderPass*> passes = {&trans, &rt, &conv};              // VulkanRenderer.cpp:4473-4475
   for (auto* p : passes) p->registerToGraph(fgb, &rc);
   if (fgb.passes.size() != 3 || fgb.passes[0]._name != "IrradianceProbeTrans" || fgb.passes[1]._name != "IrradianceProbeRT" ||
@@ -89,8 +104,14 @@ int main(int argc, char** argv) {
     int r = anerend_cuda_ddgi_upload_scene(vol->handle, vtx.data(), (uint32_t)vtx.size(), idx.data(), (uint32_t)idx.size(), meshes.data(), mni.data(),
                                            (uint32_t)meshes.size(), mats.data(), (uint32_t)mats.size(), rends.data(), (uint32_t)rends.size(), mi.data(),
                                            (uint32_t)mi.size(), mti.data(), (uint32_t)mti.size(), lights.data(), (uint32_t)lights.size());
-    if (r == 0) r = anerend_cuda_ddgi_build_accel(vol->handle);
     if (r != 0) { printf("FAIL scene: %s\n", anerend_cuda_ddgi_last_error(vol->handle)); return 1; }
+    // the acceleration structure is built by the TLASUpdate pass (topologyDirty), as the frame graph would run it
+    rc.numRenderables = rends.size();
+    stub::FrameGraphBuilder g4; blas.registerToGraph(g4, &rc); tlas.registerToGraph(g4, &rc);
+    g4.executeGraph(&rc);
+    anerend_ddgi_bvh_info_t bi{};
+    if (vol->topologyDirty || anerend_cuda_ddgi_get_bvh_info(vol->handle, &bi) != 0 || bi.num_triangles == 0) { printf("FAIL TLASUpdate build\n"); return 1; }
+    g4.executeGraph(&rc);                                                      // no device RenderableBuffer in the stub: the refit no-ops
   }
   rt.seed(seed);
   for (int fr = 0; fr < frames; ++fr) {
