@@ -61,11 +61,8 @@ void ref_host_render_option_defaults(float out[13]) {
 }
 // IrradianceProbeRayTracingPass.cpp:120-133: rotAx from the axis index, glm::rotate(glm::mat4(1.0f), glm::radians(float(angle)), rotAx)
 void ref_host_make_rotation(int axis, float angle_deg, float out[16]) {
-  glm::vec3 rotAx{0.0f};
-  if (axis == 0) rotAx = glm::vec3(1.0f, 0.0f, 0.0f);
-  else if (axis == 1) rotAx = glm::vec3(0.0f, 1.0f, 0.0f);
-  else rotAx = glm::vec3(0.0f, 0.0f, 1.0f);
-  glm::mat4 randomRot = glm::rotate(glm::mat4(1.0f), glm::radians(angle_deg), rotAx);
+  const glm::vec3 axes[3] = {glm::vec3(1.0f, 0.0f, 0.0f), glm::vec3(0.0f, 1.0f, 0.0f), glm::vec3(0.0f, 0.0f, 1.0f)};
+  const glm::mat4 randomRot = glm::rotate(glm::mat4(1.0f), glm::radians(angle_deg), axes[axis < 0 ? 0 : axis > 2 ? 2 : axis]);
   std::memcpy(out, &randomRot[0][0], 64);
 }
 }
