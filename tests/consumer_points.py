@@ -16,3 +16,11 @@ def surface_points(n, nxz, ny, seed, camera=(0.0, 0.0, 0.0), step=(1.0, 2.0, 1.0
     pts[:, 9] = (rng.rand(n) < 0.2).astype(np.float32)
     pts[:, 10] = rng.uniform(0.1, 1.0, n)
     return pts
+
+
+def synthetic_baked_atlas(width, height, seed):
+    """A deterministic stand-in for a baked tile atlas: RGBA16F bit patterns [height, width, 4] (uint16), radiance in [0, 2), alpha = weight sum."""
+    rng = np.random.RandomState(seed)
+    a = rng.uniform(0.0, 2.0, (height, width, 4)).astype(np.float16)
+    a[..., 3] = np.float16(64.0)
+    return a.view(np.uint16)

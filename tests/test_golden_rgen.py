@@ -10,6 +10,7 @@ are held to a few ulp.  The CUDA kernels are held to the oracle bit for bit by t
 import os
 
 import numpy as np
+import pytest
 
 from anerend_b200 import layouts as L, make_params, scenes
 
@@ -87,6 +88,15 @@ def test_oracle_miss_radiance_equals_the_compiled_miss_shader(oracle):
 
 def test_product_kernel_logic_ray_images_match_the_compiled_shader(make_emu):
     # the same check on the PRODUCT's kernel bodies (k_make_dirs, ray set-up, miss path) run by the host harness
+    _ray_images_against_the_binary(make_emu)
+
+
+@pytest.mark.gpu
+def test_cuda_ray_images_match_the_compiled_shader(make_gpu):
+    _ray_images_against_the_binary(make_gpu)
+
+
+def _ray_images_against_the_binary(make_emu):
     ci = 1
     s = scenes.empty_scene(grid=(NXZ, NY, NR), camera=tuple(float(c) for c in G["case_camera"][ci]))
     s.ubo["sky_color"][0] = (*G["sky"][0][:3], 1.0)
