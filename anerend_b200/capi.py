@@ -286,6 +286,13 @@ class DdgiHandle:
         self._call("download_rays", C.c_int32(layer), _ptr(irr), _ptr(dr), C.c_size_t(irr.nbytes))
         return irr, dr
 
+    def upload_ray_radiance(self, layer, irr, rot):
+        """Convolution alone (BASELINE config 1): ProbeRaysIrrTex of `layer` as uint16 [S_y*nXZ, S_x*nXZ, 4]; directions from `rot`."""
+        irr = np.ascontiguousarray(irr)
+        irr = irr.view(np.uint16) if irr.dtype == np.float16 else _c(irr, np.uint16)
+        rot = _c(rot, np.float32).reshape(16)
+        self._call("upload_ray_radiance", C.c_int32(layer), _ptr(irr), C.c_size_t(irr.nbytes), _ptr(rot))
+
     def download_ray_records(self, layer):
         out = np.empty(self.n_xz * self.n_xz * self.n_rays, L.RAY_RECORD)
         self._call("download_ray_records", C.c_int32(layer), _ptr(out), C.c_size_t(len(out)))

@@ -1311,6 +1311,40 @@ int DDGI_API(download_rays)(anerend_ddgi_t* h, int32_t layer, void* irrOut, void
   }
   return 0;
 }
+// IrradianceProbeConvolve on its own (BASELINE config 1): the caller supplies ProbeRaysIrrTex of `layer`; ProbeRaysDirTex is what
+// IrradianceProbeRT would have written for randomRot = rot (rgen:87-88,108), made by the same code as in traceLayers.
+int DDGI_API(upload_ray_radiance)(anerend_ddgi_t* h, int32_t layer, const void* irr, size_t bytes, const float rot[16]) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
+  if (layer < 0 || layer >= h->nY || !irr || !rot) return fail(h, ANEREND_DDGI_E_INVALID, "layer out of range");
+  if (h->rowStride != 1) return fail(h, ANEREND_DDGI_E_STATE, "upload_ray_radiance with a row stripe set");
+  const size_t n = (size_t)h->P * h->N;
+  if (bytes != n * 8) return fail(h, ANEREND_DDGI_E_INVALID, "ray image size mismatch");
+  std::vector<uint2> lin(n);
+  const int IW = h->Sx * h->nXZ;
+  for (int probe = 0; probe < h->P; ++probe) for (int ray = 0; ray < h->N; ++ray) {
+    int px = ray % h->Sx, py = ray / h->Sx, X = (probe % h->nXZ) * h->Sx + px, Y = (probe / h->nXZ) * h->Sy + py;   // rgen:51-58
+    lin[(size_t)probe * h->N + ray] = ((const uint2*)irr)[(size_t)Y * IW + X];
+  }
+  Backend& be = h->be;
+  BE_CHECK(h, be.sync());
+  BE_CHECK(h, be.h2d(h->dRayIrr + (size_t)layer * n, lin.data(), n * 8));
+  be.waitCopy();
+  h->hLayerMap[0] = layer; h->numLaunchLayers = 1;
+#ifdef DDGI_HOST_EMU
+  rotateDirs(h, layer, rot);
+  BE_CHECK(h, be.h2d(h->dDirs + (size_t)layer * h->N, h->hDirs + (size_t)layer * h->N, (size_t)h->N * sizeof(float4)));
+  BE_CHECK(h, be.h2d(h->dLayerMap, h->hLayerMap, sizeof(int)));
+#else
+  DirsCtx dc{};
+  dc.fib = h->dFib; dc.dDirs = h->dDirs; dc.dLayerMap = h->dLayerMap; dc.N = (uint32_t)h->N; dc.first = 0; dc.count = 1; dc.layer[0] = layer;
+  for (int c3 = 0; c3 < 3; ++c3) for (int r3 = 0; r3 < 3; ++r3) dc.m[0][c3 * 3 + r3] = rot[c3 * 4 + r3];
+  k_make_dirs<<<dim3(((uint32_t)h->N + 127u) / 128u, 1), 128, 0, be.stream>>>(dc);
+  ++be.launches;
+#endif
+  BE_CHECK(h, be.sync());            // `lin` is pageable: the copy is complete before it goes away
+  h->layerTraced[layer] = 1;
+  return 0;
+}
 int DDGI_API(download_ray_records)(anerend_ddgi_t* h, int32_t layer, anerend_ddgi_ray_record_t* out, size_t count) {
   if (!h) return ANEREND_DDGI_E_INVALID;
   if (!h->dRecords) return fail(h, ANEREND_DDGI_E_STATE, "FLAG_RAY_RECORDS not set");

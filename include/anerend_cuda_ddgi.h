@@ -284,6 +284,10 @@ int anerend_cuda_ddgi_stream(anerend_ddgi_t* h, void** stream);
  * (S_x*nXZ) x (S_y*nXZ) RGBA16F, pixel (probeX*S_x+px, probeZ*S_y+py), rayIndex = py*S_x+px  (rgen:51-58). */
 int anerend_cuda_ddgi_ray_tile(const anerend_ddgi_t* h, int32_t* sx, int32_t* sy);
 int anerend_cuda_ddgi_download_rays(anerend_ddgi_t* h, int32_t layer, void* irr_rgba16f, void* dir_rgba16f, size_t bytes_each);
+/* "IrradianceProbeConvolve" on its own (BASELINE config 1, probe_conv.comp over caller-supplied radiance): ProbeRaysIrrTex of
+ * `layer` in the image layout above (host pointer); ProbeRaysDirTex becomes what "IrradianceProbeRT" writes for randomRot = rot
+ * (mat3(rot) * Fibonacci direction, rgen:87-88,108).  Follow with _convolve_layer(h, layer).  Not available with a row stripe. */
+int anerend_cuda_ddgi_upload_ray_radiance(anerend_ddgi_t* h, int32_t layer, const void* irr_rgba16f, size_t bytes, const float rot[16]);
 /* nXZ*nXZ*rays records, index (probeZ*nXZ+probeX)*rays + rayIndex.  Needs FLAG_RAY_RECORDS. */
 int anerend_cuda_ddgi_download_ray_records(anerend_ddgi_t* h, int32_t layer, anerend_ddgi_ray_record_t* out, size_t count);
 /* fp32 RGBA per atlas texel (same addressing as the atlas) of the last convolution.  Needs FLAG_TEXEL_RECORDS. */

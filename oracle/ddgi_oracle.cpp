@@ -1056,6 +1056,21 @@ int ddgi_oracle_set_rays(ddgi_oracle_t* h, int32_t layer, const void* irr, const
   }
   return 0;
 }
+// the product's _upload_ray_radiance: radiance image from the caller, direction image as trace_layer writes it for `rot`
+int ddgi_oracle_upload_ray_radiance(ddgi_oracle_t* h, int32_t layer, const void* irr, size_t bytes, const float rot[16]) {
+  size_t n = (size_t)h->nXZ * h->nXZ * h->N * 4;
+  if (layer < 0 || layer >= h->nY || bytes != n * 2 || !irr || !rot) { h->err = "bad upload_ray_radiance arguments"; return ANEREND_DDGI_E_INVALID; }
+  h->rayIrr[layer].resize(n); h->rayDir[layer].resize(n);
+  int IW = h->Sx * h->nXZ; const uint16_t* ii = (const uint16_t*)irr;
+  for (int probe = 0; probe < h->nXZ * h->nXZ; ++probe) for (int ray = 0; ray < h->N; ++ray) {
+    int px = ray % h->Sx, py = ray / h->Sx, X = (probe % h->nXZ) * h->Sx + px, Y = (probe / h->nXZ) * h->Sy + py;
+    size_t o = 4 * ((size_t)probe * h->N + ray);
+    std::memcpy(&h->rayIrr[layer][o], &ii[4 * ((size_t)Y * IW + X)], 8);
+    V3 d = h->probeRayDir(rot, ray);
+    h->rayDir[layer][o] = f2h(d.x); h->rayDir[layer][o + 1] = f2h(d.y); h->rayDir[layer][o + 2] = f2h(d.z); h->rayDir[layer][o + 3] = 0x3C00;
+  }
+  return 0;
+}
 int ddgi_oracle_download_ray_records(ddgi_oracle_t* h, int32_t layer, anerend_ddgi_ray_record_t* out, size_t count) {
   if (!(h->p.flags & ANEREND_DDGI_FLAG_RAY_RECORDS)) { h->err = "FLAG_RAY_RECORDS not set"; return ANEREND_DDGI_E_STATE; }
   if (layer < 0 || layer >= h->nY || h->records[layer].size() != count) { h->err = "no records for this layer / count mismatch"; return ANEREND_DDGI_E_INVALID; }

@@ -75,6 +75,8 @@ int ddgi_oracle_reset_stats(ddgi_oracle_t* h);
  * image layout (RGBA16F, (S_x*nXZ) x (S_y*nXZ)), then probe_conv.comp over `layer`. */
 int ddgi_oracle_set_rays(ddgi_oracle_t* h, int32_t layer, const void* irr_rgba16f, const void* dir_rgba16f, size_t bytes_each);
 
+int ddgi_oracle_upload_ray_radiance(ddgi_oracle_t* h, int32_t layer, const void* irr_rgba16f, size_t bytes, const float rot[16]);
+
 /* ---- single shader functions, exported for the known-answer tests ------------------------ */
 /* The hit shader for one hit (flattened triangle id, barycentrics) of a ray from `origin`: irradiance_probe_update.rchit
  * (specular = 0) or mirror_reflections.rchit (specular = 1) against the handle's current atlas; out = (irradiance, distance from

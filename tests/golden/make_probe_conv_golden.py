@@ -49,11 +49,24 @@ def main():
         for j in range(8):
             for i in range(8):                                      # atlas texel (10 px + 1 + i, 10*64*layer + 10 pz + 1 + j)
                 old[(10 * px + 1 + i, 10 * NXZ * LAYER + 10 * pz + 1 + j)] = [float(c) for c in old_in[k, j, i]]
+    # a second direction image, the one the ray-generation shader writes: mat3(randomRot) * Fibonacci direction, the same 256
+    # directions for every probe (rgen:87-88,108) — the case the product's _upload_ray_radiance + _convolve_layer can be fed with
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import binding as ob
+    shared_rot = ob.make_rotation(1, 211.25)
+    fib = ob.fibonacci_dirs(S * S)
+    R = shared_rot.reshape(4, 4)[:3, :3].T
+    rdirs = np.stack([[np.float32(np.float32(np.float32(R[r, 0] * d[0]) + np.float32(R[r, 1] * d[1])) + np.float32(R[r, 2] * d[2])) for r in range(3)] for d in fib]).astype(np.float16)
+    dirs_shared = {}
+    for (px, pz) in PROBES:
+        for y in range(S):
+            for x in range(S):
+                dirs_shared[(px * S + x, pz * S + y)] = [float(c) for c in rdirs[y * S + x]] + [1.0]
     ubo_gid = next(g for g, n in m.names.items() if n == "ubo" and g in m.globals)
     ubo_struct = m.types[m.globals[ubo_gid][0]][2]
     flags_member = m.struct_member(ubo_struct, "flags")
     out = {}
-    for mode, flags in (("live", 0), ("bake", 1 << 11)):
+    for mode, flags, dirs in (("live", 0, dirs), ("bake", 1 << 11, dirs), ("live_shared", 0, dirs_shared), ("bake_shared", 1 << 11, dirs_shared)):
         ubo = m.zero(ubo_struct); ubo[flags_member] = flags
         res = np.zeros((len(PROBES), 8, 8, 4), np.float32)
         for k, (px, pz) in enumerate(PROBES):
@@ -70,7 +83,8 @@ def main():
         print(mode, "done", res[0, 0, 0], res[-1, 7, 7])
     dst = os.path.join(HERE, "probe_conv_golden.npz")
     np.savez_compressed(dst, probes=np.array(PROBES), layer=LAYER, irr=irr_in.view(np.uint16), dir=dir_in.view(np.uint16), old=old_in.view(np.uint16),
-                        out_live=out["live"], out_bake=out["bake"])
+                        out_live=out["live"], out_bake=out["bake"], shared_rot=shared_rot, shared_dir=rdirs.view(np.uint16),
+                        out_live_shared=out["live_shared"], out_bake_shared=out["bake_shared"])
     print("wrote", dst)
 
 

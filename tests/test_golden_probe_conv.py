@@ -52,3 +52,52 @@ def test_oracle_convolution_equals_the_compiled_reference_shader(mode, oracle):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"max rel diff {np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-6)):.3e}"
     # and the stored RGBA16F texels are the round-to-nearest-even halves of those values
     assert np.array_equal(half.view(np.float16), want.astype(np.float16))
+
+
+# ---- the same binary with the direction image the ray-generation pass writes (one rotation, shared by all probes): this case can be
+# ---- fed to the PRODUCT through _upload_ray_radiance + _convolve_layer, so its convolution is held to the compiled shader directly
+def _run_shared(make, bake):
+    h = make(make_params(NXZ, NY, N, flags=L.FLAG_TEXEL_RECORDS))
+    ubo = scenes.empty_scene(grid=(NXZ, NY, N)).ubo.copy()
+    if bake:
+        ubo["flags"] |= L.UBO_BAKE_MODE_ON_FLAG
+    h.set_scene_ubo(ubo)
+    layer = int(G["layer"])
+    irr = np.zeros((S * NXZ, S * NXZ, 4), np.uint16)
+    atlas = h.download_atlas()
+    for k, (px, pz) in enumerate(G["probes"]):
+        irr[pz * S:(pz + 1) * S, px * S:(px + 1) * S] = G["irr"][k]
+        y0, x0 = 10 * NXZ * layer + 10 * pz + 1, 10 * px + 1
+        atlas[y0:y0 + 8, x0:x0 + 8] = G["old"][k]
+    h.upload_atlas(atlas)
+    h.upload_ray_radiance(layer, irr, G["shared_rot"])
+    _, dirs = h.download_rays(layer)
+    for (px, pz) in G["probes"]:                                    # ProbeRaysDirTex is the golden's direction image, bit for bit
+        assert np.array_equal(dirs[pz * S:(pz + 1) * S, px * S:(px + 1) * S, :3].reshape(N, 3), G["shared_dir"])
+    h.convolve_layer(layer)
+    rec = h.download_texel_records()
+    h.close()
+    return np.stack([rec[10 * NXZ * layer + 10 * pz + 1:10 * NXZ * layer + 10 * pz + 9, 10 * px + 1:10 * px + 9] for (px, pz) in G["probes"]])
+
+
+def _check_shared(make, mode):
+    want = G["out_" + mode + "_shared"]
+    got = _run_shared(make, mode == "bake")
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"max rel diff {np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-6)):.3e}"
+
+
+@pytest.mark.parametrize("mode", ["live", "bake"])
+@pytest.mark.parametrize("side", ["oracle", "product_harness"])
+def test_convolution_with_rgen_directions_equals_the_compiled_reference_shader(side, mode, oracle, make_emu):
+    _check_shared(oracle.Oracle if side == "oracle" else make_emu, mode)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["live", "bake"])
+@pytest.mark.parametrize("kernels", ["wavefront", "simple"])
+def test_cuda_convolution_equals_the_compiled_reference_shader(kernels, mode, make_gpu):
+    def make(p):
+        if kernels == "simple":
+            p.flags |= L.FLAG_SIMPLE_KERNELS
+        return make_gpu(p)
+    _check_shared(make, mode)
