@@ -93,3 +93,55 @@ def test_product_kernel_logic_matches_oracle_on_adversarial_geometry(oracle, mak
             parity.compare_records(o.download_ray_records(layer), e.download_ray_records(layer))
         assert np.array_equal(o.download_atlas(), e.download_atlas())
     o.close(); e.close()
+
+
+def test_empty_and_ragged_inputs(oracle, make_emu):
+    """Nothing visible (an acceleration structure of zero triangles), a mesh whose index count is not a multiple of three (the last
+    partial triangle is dropped, as primitiveCount = numIndices / 3 does in the reference's BLAS build, VulkanRenderer.cpp:1313),
+    indices pointing past the vertex buffer (refused), a grid of one probe."""
+    import pytest
+    p = make_params(2, 1, 64, flags=ALL)
+    # (a) every renderable hidden: zero triangles, every ray is the sky, both sides agree
+    scene = scenes.quad_scene(grid=(2, 1, 64))
+    scene.renderables["visible"][:] = 0
+    o, e = oracle.Oracle(p), make_emu(p)
+    rots = parity.setup_pair(scene, (o, e), seed=1)
+    assert o.bvh_info().num_triangles == e.bvh_info().num_triangles == 0 and e.bvh_info().num_instances == 0
+    for h in (o, e):
+        h.update(-1, rots)
+    assert np.all(e.download_ray_records(0)["prim"] == L.MISS)
+    assert np.array_equal(o.download_atlas(), e.download_atlas())
+    # (b) ragged index count: 7 indices = 2 triangles + 1 dangling index
+    ragged = scenes.quad_scene(grid=(2, 1, 64))
+    ragged.indices = np.concatenate([ragged.indices[:6], ragged.indices[:1]]).astype(np.uint32)
+    ragged.mesh_num_indices = np.array([7], np.uint32)
+    for h in (o, e):
+        h.upload_scene(ragged); h.set_scene_ubo(ragged.ubo); h.build_accel()
+        assert h.bvh_info().num_triangles == 2
+        h.update(-1, rots)
+    parity.compare_records(o.download_ray_records(0), e.download_ray_records(0))
+    assert np.array_equal(o.download_atlas(), e.download_atlas())
+    # (c) an index past the end of the vertex buffer, a mesh reaching past the end of the index buffer: refused by both, handle stays usable
+    bad = scenes.quad_scene(grid=(2, 1, 64))
+    bad.indices = bad.indices.copy(); bad.indices[4] = len(bad.vertices) + 5
+    for h in (o, e):
+        with pytest.raises(Exception):
+            h.upload_scene(bad); h.build_accel()
+    bad2 = scenes.quad_scene(grid=(2, 1, 64))
+    bad2.mesh_num_indices = np.array([600], np.uint32)
+    for h in (o, e):
+        with pytest.raises(Exception):
+            h.upload_scene(bad2); h.build_accel()
+        h.upload_scene(ragged); h.set_scene_ubo(ragged.ubo); h.build_accel()
+        assert h.bvh_info().num_triangles == 2
+    o.close(); e.close()
+    # (d) the smallest grid there is
+    p1 = make_params(1, 1, 32, flags=ALL)
+    one = scenes.quad_scene(grid=(1, 1, 32))
+    o, e = oracle.Oracle(p1), make_emu(p1)
+    rots = parity.setup_pair(one, (o, e), seed=2)
+    for h in (o, e):
+        h.update(-1, rots)
+    parity.compare_records(o.download_ray_records(0), e.download_ray_records(0))
+    assert np.array_equal(o.download_atlas(), e.download_atlas()) and o.download_atlas().shape == (10, 10, 4)
+    o.close(); e.close()
