@@ -119,6 +119,57 @@ def run_oracle_sample(scene, grid, layers, threads=0, point_lights=True):
     return len(layers) * nxz * nxz * nr, dt, nthreads
 
 
+def run_config1(dev, cpu_baseline=True):
+    """BASELINE config 1 — probe_conv.comp alone: 8 x 8 x 8 probes x 64 rays on synthetic radiance U[0, 4)^3.  The CUDA convolution runs
+    through _upload_ray_radiance + _convolve_layer (radiance resident, one launch set per layer, all 8 layers = one pass); next to it the
+    single-thread CPU transliteration the config names (the oracle; cpu_baseline leg).  Parity of the two: tests/test_config1.py."""
+    import torch
+    import anerend_b200 as A
+    from anerend_b200 import make_params, scenes
+    nxz, ny, nr = 8, 8, 64
+    ubo = scenes.empty_scene(grid=(nxz, ny, nr)).ubo
+    rng = np.random.RandomState(1)
+    irr = np.ones((ny, 8 * nxz, 8 * nxz, 4), np.float16)
+    irr[..., :3] = rng.uniform(0, 4, irr[..., :3].shape)
+    hc = A.Ddgi(make_params(nxz, ny, nr))
+    out = {"workload": "c1", "probes": "8x8x8", "rays_per_probe": nr, "texels": nxz * nxz * ny * 64}
+    try:
+        hc.set_scene_ubo(ubo)
+        rot = hc.make_rotation(*scenes.rotation_sequence(1, 1)[0])
+        for layer in range(ny):
+            hc.upload_ray_radiance(layer, irr[layer], rot)
+        stream = torch.cuda.ExternalStream(hc.stream(), device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(23):
+            if it == 3:
+                e0.record(stream)
+            for layer in range(ny):
+                hc.convolve_layer(layer)
+        e1.record(stream)
+        hc.sync()
+        ms = e0.elapsed_time(e1) / 20.0
+        out["gpu"] = {"ms_per_pass": ms, "mprobes_per_s": nxz * nxz * ny / ms / 1e3, "launches_per_pass": 2 * ny,
+                      "note": "8 per-layer calls of a 64-probe layer each: launch-latency bound at this size"}
+    finally:
+        hc.close()
+    if cpu_baseline:
+        from oracle import binding as ob
+        o = ob.Oracle(make_params(nxz, ny, nr))
+        o.set_threads(1)
+        o.set_scene_ubo(ubo)
+        for layer in range(ny):
+            o.upload_ray_radiance(layer, irr[layer], rot)
+        best = float("inf")
+        for it in range(5):
+            t0 = time.perf_counter()
+            for layer in range(ny):
+                o.convolve_layer(layer)
+            best = min(best, time.perf_counter() - t0)
+        o.close()
+        out["cpu_single_thread"] = {"ms_per_pass": best * 1e3, "ns_per_texel": best * 1e9 / (nxz * nxz * ny * 64), "kind": "port", "cores": 1}
+    return out
+
+
 def reference_arm(args, rank, world):
     """The reference's CPU implementation of the path = the oracle (the path itself — GLSL + Vulkan RT — cannot be built here;
     oracle/_ref only holds the reference's struct headers and glm::rotate).  Rank 0 alone runs; each step is a bounded sample
@@ -494,6 +545,14 @@ def main():
         shadow_rt["specular_gi_ms"] = s0.elapsed_time(s1) / 3.0
         h.set_scene_ubo(scene.ubo)
 
+    # ---- BASELINE config 1 (the reference's CPU-runnable case): an extra figure, never allowed to take the headline line down with it
+    config1 = None
+    if world == 1 and args.workload is None and not args.no_extras:
+        try:
+            config1 = run_config1(dev, cpu_baseline=not args.no_cpu_baseline)
+        except Exception as ex:                                     # noqa: BLE001
+            config1 = {"workload": "c1", "error": str(ex)[:200]}
+
     # ---- base of the multi-GPU series: the N>1 runs of this script time C5 (the configuration BASELINE.json shards over 2/4/8
     # GPUs), so the default N=1 run also reports C5 on one GPU — the denominator of that series — next to its own C3 headline
     series_base = None
@@ -583,7 +642,8 @@ def main():
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "update_ms": {"trace": rt_avg, "convolve": float(np.mean(conv_ms)), "full_grid": ms_per_step},
                 "arithmetic": "fast_math (1e-4 relative per update)" if args.fast_math else "exact (atlas bit-identical to the oracle)",
-                "other_build": alt, "strong_scaling_base": base1, "exchange_check_vs_1gpu": verified, "layer_deal": balanced, "per_rank_ms": per_rank, "atlas_consumer": consumer, "shadow_rt": shadow_rt, "multi_gpu_series_base": series_base}
+                "other_build": alt, "strong_scaling_base": base1, "exchange_check_vs_1gpu": verified, "layer_deal": balanced, "per_rank_ms": per_rank, "atlas_consumer": consumer, "shadow_rt": shadow_rt, "multi_gpu_series_base": series_base,
+                "config1_conv_only": config1}
     close_handle(h, fused)
     if world > 1:
         dist.barrier()
