@@ -9,7 +9,7 @@ shadow rays?  CPU only, uses the oracle (test infrastructure) on a BASELINE scen
     the exact Moeller-Trumbore tests a grid walk would still have to do (no early out counted) — to be read next to what the
     product's BVH8 walk does today (bench line: roofline.nodes_per_shadow_ray, tris_per_shadow_ray).
 
-    python tools/lightspace_probe.py [c2|c3] [grid=1024]
+    python tests/lightspace_probe.py [c2|c3] [grid=1024]
 """
 import os
 import sys
