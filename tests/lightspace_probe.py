@@ -86,6 +86,38 @@ def main():
     for nm, v in (("triangles in the ray's cell", in_cell), ("of those on the sun side within (tMin, tMax): exact tests left", ahead)):
         print(f"  {nm}: mean {v.mean():.1f}, median {np.median(v):.0f}, p90 {np.percentile(v, 90):.0f}, max {v.max()}")
 
+    # ---- point lights (extension E1): rays share their END point, so the analogue is a direction-space structure around each light
+    # (e.g. a cube map of triangle lists).  Estimated per query with angular bounding cones instead of building the cube map: a triangle is a
+    # candidate when the ray's direction from the light falls inside the triangle's cone widened by one cell (face resolution G), and its
+    # distance interval from the light reaches in front of the hit point.
+    lights = [l for l in scene.lights if l["color"][3] > 0.5]
+    cell_angle = (np.pi / 2) / G
+    tot, left = [], []
+    for l in lights:
+        lp, rng_m = l["world_pos"][:3].astype(np.float64), float(l["world_pos"][3])
+        rel = tris - lp                                                  # [n, 3, 3]
+        dist_v = np.linalg.norm(rel, axis=2)
+        cdir = rel.mean(1); cdir /= np.linalg.norm(cdir, axis=1, keepdims=True)
+        cosv = np.clip(np.einsum("nvk,nk->nv", rel / np.maximum(dist_v[..., None], 1e-12), cdir), -1, 1)
+        rho = np.arccos(cosv.min(1)) + cell_angle
+        dmin, dmax = dist_v.min(1), dist_v.max(1)
+        d = pos - lp
+        dd = np.linalg.norm(d, axis=1)
+        sel = np.nonzero(dd < rng_m)[0]
+        if sel.size == 0:
+            continue
+        for i in rng.choice(sel, min(sel.size, 400), replace=False):
+            qd = d[i] / dd[i]
+            ang = np.arccos(np.clip(cdir @ qd, -1, 1))
+            cand = ang <= rho
+            tot.append(int(cand.sum()))
+            left.append(int((cand & (dmin < dd[i] - tmin)).sum()))
+    if tot:
+        tot, left = np.array(tot), np.array(left)
+        print(f"point lights ({len(lights)} enabled, cube map of {G} x {G} per face, estimated with bounding cones):")
+        for nm, v in (("triangles in the ray's direction cell", tot), ("of those nearer to the light than the hit point: exact tests left", left)):
+            print(f"  {nm}: mean {v.mean():.1f}, median {np.median(v):.0f}, p90 {np.percentile(v, 90):.0f}, max {v.max()}")
+
 
 if __name__ == "__main__":
     main()
