@@ -119,6 +119,22 @@ def run_oracle_sample(scene, grid, layers, threads=0, point_lights=True):
     return len(layers) * nxz * nxz * nr, dt, nthreads
 
 
+def vulkan_reference_status():
+    """north_star: 'the reference Vulkan path, reported additionally if the host driver exposes ray-tracing pipelines'.  It never can be
+    run from this repo (the reference's host code is Win32-only and its shaders need VK_KHR_ray_tracing_pipeline); this records why."""
+    try:
+        import ctypes.util
+        import shutil
+        loader = ctypes.util.find_library("vulkan")
+        info = shutil.which("vulkaninfo")
+        if not loader and not info:
+            return "n/a: no Vulkan loader (libvulkan) and no vulkaninfo on this box; B200 exposes no VK_KHR_ray_tracing_pipeline"
+        return ("n/a: a Vulkan loader is present (%s) but the reference's host code is Win32-only and B200 exposes no "
+                "VK_KHR_ray_tracing_pipeline" % (loader or info))
+    except Exception as ex:                                         # noqa: BLE001
+        return "n/a: probe failed (%s)" % str(ex)[:80]
+
+
 def run_config1(dev, cpu_baseline=True):
     """BASELINE config 1 — probe_conv.comp alone: 8 x 8 x 8 probes x 64 rays on synthetic radiance U[0, 4)^3.  The CUDA convolution runs
     through _upload_ray_radiance + _convolve_layer (radiance resident, one launch set per layer, all 8 layers = one pass); next to it the
@@ -643,7 +659,7 @@ def main():
                 "update_ms": {"trace": rt_avg, "convolve": float(np.mean(conv_ms)), "full_grid": ms_per_step},
                 "arithmetic": "fast_math (1e-4 relative per update)" if args.fast_math else "exact (atlas bit-identical to the oracle)",
                 "other_build": alt, "strong_scaling_base": base1, "exchange_check_vs_1gpu": verified, "layer_deal": balanced, "per_rank_ms": per_rank, "atlas_consumer": consumer, "shadow_rt": shadow_rt, "multi_gpu_series_base": series_base,
-                "config1_conv_only": config1}
+                "config1_conv_only": config1, "vulkan_reference": vulkan_reference_status()}
     close_handle(h, fused)
     if world > 1:
         dist.barrier()
