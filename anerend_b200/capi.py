@@ -168,6 +168,12 @@ class DdgiHandle:
             r = _c(renderables, L.RENDERABLE)
             self._call("refit_accel", _ptr(r), C.c_uint32(len(r)))
 
+    def apply_camera_cull(self, range_m=50.0):
+        """The cull bit of cull.comp:296-303 for the current scene UBO; returns how many renderables flipped (then build_accel again)."""
+        n = C.c_uint32(0)
+        self._call("apply_camera_cull", C.c_float(range_m), C.byref(n))
+        return int(n.value)
+
     def bvh_info(self):
         b = BvhInfo()
         self._call("get_bvh_info", C.byref(b))

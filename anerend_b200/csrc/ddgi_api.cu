@@ -911,6 +911,35 @@ int DDGI_API(refit_accel_device)(anerend_ddgi_t* h, const void* dRenderables, ui
   return refitAccel(h);
 }
 
+// cull.comp:241-244,296-303: the renderable culling pass marks every VISIBLE renderable whose bounding-sphere centre — bounds.xyz moved
+// by the translation of its transform only (buildTranslation, cull.comp:229-239) — lies farther than `range` (reference: 50 m) from the
+// camera; tlas_update.comp then leaves it out of the TLAS.  For hosts that do not run the Vulkan cull pass in front of the chain.
+// A changed bit invalidates the acceleration structure (the instance set differs): _build_accel must follow.
+int DDGI_API(apply_camera_cull)(anerend_ddgi_t* h, float range, uint32_t* changedOut) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
+  if (!h->haveScene) return fail(h, ANEREND_DDGI_E_STATE, "apply_camera_cull before upload_scene");
+  if (!h->haveUbo) return fail(h, ANEREND_DDGI_E_STATE, "apply_camera_cull before set_scene_ubo");
+  uint32_t changed = 0;
+  for (anerend_renderable_t& r : h->renderables) {
+    if (!(r.visible & 1u)) continue;                                   // cull.comp:289-292: hidden renderables are not looked at
+    // trans * vec4(bounds.xyz, 1) with trans = identity + translation column: c0*x + c1*y + c2*z + c3*1
+    const float cx = ((1.0f * r.bounds[0] + 0.0f * r.bounds[1]) + 0.0f * r.bounds[2]) + r.transform[12] * 1.0f;
+    const float cy = ((0.0f * r.bounds[0] + 1.0f * r.bounds[1]) + 0.0f * r.bounds[2]) + r.transform[13] * 1.0f;
+    const float cz = ((0.0f * r.bounds[0] + 0.0f * r.bounds[1]) + 1.0f * r.bounds[2]) + r.transform[14] * 1.0f;
+    const float dx = h->ubo.camera_pos[0] - cx, dy = h->ubo.camera_pos[1] - cy, dz = h->ubo.camera_pos[2] - cz;
+    const bool within = sqrtf((dx * dx + dy * dy) + dz * dz) <= range;                        // distance(cameraPos, centre) <= range
+    const uint32_t v = (r.visible & ~2u) | (within ? 0u : 2u);                                // setCullBit(rend, !withinRange), bindless.glsl:254-258
+    if (v != r.visible) { r.visible = v; ++changed; }
+  }
+  if (changed) {
+    BE_CHECK(h, h->be.sync());
+    BE_CHECK(h, h->be.h2d(h->dRenderables, h->renderables.data(), h->renderables.size() * sizeof(anerend_renderable_t)));
+    BE_CHECK(h, h->be.sync());
+    h->haveAccel = false;                                              // trace / refit now fail loudly until _build_accel
+  }
+  if (changedOut) *changedOut = changed;
+  return 0;
+}
 int DDGI_API(get_bvh_info)(anerend_ddgi_t* h, anerend_ddgi_bvh_info_t* o) {
   if (!h) return ANEREND_DDGI_E_INVALID;
   memset(o, 0, sizeof(*o));

@@ -168,6 +168,12 @@ int anerend_cuda_ddgi_update_vertices_device(anerend_ddgi_t* h, const void* d_ve
  * reference's RenderableBuffer is GPU-written earlier in the frame, cull.comp:303). */
 int anerend_cuda_ddgi_refit_accel(anerend_ddgi_t* h, const anerend_renderable_t* renderables, uint32_t num_renderables);
 int anerend_cuda_ddgi_refit_accel_device(anerend_ddgi_t* h, const void* d_renderables, uint32_t num_renderables);
+/* The cull bit the reference's culling pass sets in front of the chain (cull.comp:241-244,296-303): every visible renderable whose
+ * bounding-sphere centre (bounds.xyz + the transform's translation) is farther than `range` metres from ubo.cameraPos gets bit 1 of
+ * `visible` set, the others get it cleared; tlas_update.comp (and _build_accel) leave culled renderables out.  For hosts that do not
+ * run the Vulkan cull pass; the reference uses range = 50.  *changed = number of renderables whose bit flipped; if it is not 0 the
+ * acceleration structure is invalid until the next _build_accel. */
+int anerend_cuda_ddgi_apply_camera_cull(anerend_ddgi_t* h, float range, uint32_t* changed);
 int anerend_cuda_ddgi_get_bvh_info(anerend_ddgi_t* h, anerend_ddgi_bvh_info_t* out);
 /* The instances _build_accel selected, in the order they were emitted: what tlas_update.comp:54-98 writes to its InstanceBuffer
  * when its invocations run in renderable order (custom index = material | mesh << 10, tlas_update.comp:88-91), plus the range of

@@ -972,6 +972,23 @@ int ddgi_oracle_refit_accel(ddgi_oracle_t* h, const anerend_renderable_t* r, uin
   h->bvh.build(h->tris);   // the oracle simply rebuilds; closest hit does not depend on the tree
   return 0;
 }
+// cull.comp:241-244,296-303 (withinRangeOfCamera + setCullBit), centre = buildTranslation(model) * vec4(bounds.xyz, 1) (cull.comp:229-239,297)
+int ddgi_oracle_apply_camera_cull(ddgi_oracle_t* h, float range, uint32_t* changedOut) {
+  if (!h->haveUbo) { h->err = "apply_camera_cull before set_scene_ubo"; return ANEREND_DDGI_E_STATE; }
+  uint32_t changed = 0;
+  for (anerend_renderable_t& r : h->renderables) {
+    if (!(r.visible & 1u)) continue;
+    const float trans[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, r.transform[12], r.transform[13], r.transform[14], 1};
+    const V3 centre = xformPoint(trans, v3(r.bounds[0], r.bounds[1], r.bounds[2]));
+    const V3 d = v3(h->ubo.camera_pos[0], h->ubo.camera_pos[1], h->ubo.camera_pos[2]) - centre;
+    const bool within = std::sqrt(dot(d, d)) <= range;
+    const uint32_t v = (r.visible & ~2u) | (within ? 0u : 2u);
+    if (v != r.visible) { r.visible = v; ++changed; }
+  }
+  if (changed) h->haveAccel = false;
+  if (changedOut) *changedOut = changed;
+  return 0;
+}
 int ddgi_oracle_get_bvh_info(ddgi_oracle_t* h, anerend_ddgi_bvh_info_t* o) {
   std::memset(o, 0, sizeof(*o));
   o->num_triangles = (uint32_t)h->tris.size(); o->num_nodes = (uint32_t)h->bvh.nodes.size(); o->node_bytes = sizeof(BNode); o->tri_bytes = sizeof(WTri);

@@ -50,6 +50,7 @@ int ddgi_oracle_upload_textures(ddgi_oracle_t* h, const anerend_texture_desc_t* 
 int ddgi_oracle_set_scene_ubo(ddgi_oracle_t* h, const anerend_scene_ubo_t* ubo);
 int ddgi_oracle_build_accel(ddgi_oracle_t* h);
 int ddgi_oracle_refit_accel(ddgi_oracle_t* h, const anerend_renderable_t* renderables, uint32_t num_renderables);
+int ddgi_oracle_apply_camera_cull(ddgi_oracle_t* h, float range, uint32_t* changed);
 int ddgi_oracle_get_bvh_info(ddgi_oracle_t* h, anerend_ddgi_bvh_info_t* out);
 int ddgi_oracle_download_instances(ddgi_oracle_t* h, anerend_ddgi_instance_t* out, size_t count);
 /* World-space flattened triangles, 9 floats each (v0, v1, v2), in global triangle-id order. */

@@ -376,6 +376,15 @@ class Invocation:
                     for c2 in range(1, len(mat)):
                         out = [f32(out[r] + f32(mat[c2][r] * vec[c2])) for r in range(len(out))]
                     v[a[1]] = out
+                elif op == 146:                                     # OpMatrixTimesMatrix: column c of the result = left * (column c of right)
+                    left, right = val(a[2]), val(a[3])
+                    res = []
+                    for col in right:
+                        out = [f32(left[0][r] * col[0]) for r in range(len(left[0]))]
+                        for k2 in range(1, len(left)):
+                            out = [f32(out[r] + f32(left[k2][r] * col[k2])) for r in range(len(out))]
+                        res.append(out)
+                    v[a[1]] = res
                 elif op == 154:
                     v[a[1]] = any(val(a[2]))
                 elif op == 171:
