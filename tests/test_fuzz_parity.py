@@ -66,3 +66,34 @@ def test_random_consumer_points_and_camera_walks_bit_exact(oracle, make_emu):
                 h.set_scene_ubo(u); h.translate()
             assert np.array_equal(o.download_atlas(), e.download_atlas()), (seed, step)
         o.close(); e.close()
+
+
+def test_random_refits_and_vertex_updates_bit_exact(oracle, make_emu):
+    """Moving nodes (random rigid steps, now and then mirrored) and deforming vertex ranges, refit after each step."""
+    for seed in range(3000, 3016):
+        rng = np.random.RandomState(seed)
+        nxz, ny, nr = int(rng.choice([2, 3])), int(rng.choice([1, 2])), 64
+        s = scenes.random_soup(seed, ntris=int(rng.choice([100, 600])), grid=(nxz, ny, nr))
+        p = make_params(nxz, ny, nr, flags=ALL)
+        o, e = oracle.Oracle(p), make_emu(p)
+        rots = parity.setup_pair(s, (o, e), seed=seed)
+        verts = s.vertices.copy()
+        for step in range(3):
+            rend = s.renderables.copy()
+            for i in range(len(rend)):
+                if rng.rand() < 0.6:
+                    M = rend["transform"][i].reshape(4, 4).T.astype(np.float64)
+                    M2 = scenes.translate(rng.uniform(-1, 1, 3)) @ scenes.rotate(int(rng.randint(0, 3)), rng.uniform(0, 360)) @ M
+                    if rng.rand() < 0.2:
+                        M2 = M2 @ scenes.scale((-1, 1, 1))
+                    rend["transform"][i] = M2.T.astype(np.float32).ravel()
+            k0 = int(rng.randint(0, len(verts) - 10)); k1 = min(len(verts), k0 + int(rng.randint(1, 200)))
+            verts["pos"][k0:k1] += rng.uniform(-0.05, 0.05, (k1 - k0, 3)).astype(np.float32)
+            for h in (o, e):
+                h.update_vertices(verts[k0:k1], first=k0)
+                h.refit_accel(rend)
+                h.update(-1, rots)
+            for layer in range(ny):
+                parity.compare_records(o.download_ray_records(layer), e.download_ray_records(layer))
+            assert np.array_equal(o.download_atlas(), e.download_atlas()), (seed, step)
+        o.close(); e.close()
