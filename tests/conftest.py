@@ -11,6 +11,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+    config.addinivalue_line("markers", "timeout(seconds): per-test limit (pytest-timeout; a plain marker where the plugin is absent)")
 
 
 @pytest.fixture(scope="session")

@@ -65,3 +65,34 @@ def test_cuda_handle_cull_bits_equal_the_compiled_cull_shader(make_gpu):
     h.update(-1, h.rotations([(0, 10.0), (1, 20.0)]))        # and the rebuilt structure traces
     assert np.isfinite(h.download_atlas().view(np.float16).astype(np.float32)).all()
     h.close()
+
+
+@pytest.mark.timeout(600)
+def test_cuda_seeded_fuzz_matches_oracle(oracle, make_gpu):
+    """A slice of tests/test_fuzz_parity.py on the device (production wavefront kernels): random small scenes, grids, ray counts, cameras,
+    flags; hit ids / barycentrics / shadow masks and the stored atlas bit for bit against the oracle."""
+    from anerend_b200 import scenes
+    for seed in range(5000, 5016):
+        rng = np.random.RandomState(seed)
+        nxz, ny, nr = int(rng.choice([2, 3, 5])), int(rng.choice([1, 2, 3])), int(rng.choice([64, 128, 256]))
+        cam = tuple(rng.uniform(-3, 3, 3) * [1, 0.5, 1] + [0, 1.5, 0])
+        kind = rng.randint(0, 3)
+        if kind == 0:
+            s = scenes.random_soup(seed, ntris=int(rng.choice([300, 1500])), extent=float(rng.uniform(2, 12)), grid=(nxz, ny, nr), camera=cam,
+                                   nlights=int(rng.randint(0, 4)))
+        elif kind == 1:
+            s = scenes.textured_soup(seed, ntris=400, grid=(nxz, ny, nr), camera=cam)
+        else:
+            s = scenes.cornell_box(seed=seed, grid=(nxz, ny, nr), wall_res=6, box_res=2)
+            s.ubo = s.with_camera(cam)
+        p = make_params(nxz, ny, nr, flags=ALL | (L.FLAG_SKIP_DEAD_SHADOW_RAYS if rng.rand() < 0.5 else 0))
+        o, d = oracle.Oracle(p), make_gpu(p)
+        rots = parity.setup_pair(s, (o, d), seed=seed)
+        for it in range(2):
+            for h in (o, d):
+                h.translate()
+                h.update(-1, rots)
+            for layer in range(ny):
+                parity.compare_records(o.download_ray_records(layer), d.download_ray_records(layer))
+            assert np.array_equal(o.download_atlas(), d.download_atlas()), seed
+        o.close(); d.close()
