@@ -2,8 +2,8 @@
 
 The product is the C-ABI library `libanerend_cuda_ddgi.so` (csrc/, include/anerend_cuda_ddgi.h): hand-written
 sm_100a CUDA for the chain IrradianceProbeTrans -> IrradianceProbeRT -> IrradianceProbeConvolve.  This package
-is the thin host side: ctypes binding (`Ddgi`), the reference-shaped pass objects (`passes`), synthetic scene
-generators (`scenes`) and the multi-GPU slab helper (`sharding`).
+is the thin host side: ctypes binding (`Ddgi`), synthetic scene generators (`scenes`) and the multi-GPU slab helper
+(`sharding`); the reference-shaped pass classes are C++ (`include/anerend_ddgi_passes.hpp`).
 
 There is no CPU fallback: creating a `Ddgi` without the built library or without a CUDA device raises.
 """
