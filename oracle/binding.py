@@ -127,6 +127,12 @@ class Oracle(DdgiHandle):
                    f3(view_pos), out)
         return np.array(out[:], np.float32)
 
+    def any_hit(self, origin, direction, tmin=0.1, tmax=50.0):
+        rc = self._fn("any_hit")(self._h, (C.c_float * 3)(*[float(x) for x in origin]), (C.c_float * 3)(*[float(x) for x in direction]),
+                                 C.c_float(tmin), C.c_float(tmax))
+        assert rc >= 0
+        return bool(rc)
+
     def shade_hit(self, prim, u, v, origin, specular=False):
         """(irradiance [3], distance, lit mask) of the probe / mirror-reflection hit shader for one hit."""
         out, lit = (C.c_float * 4)(), C.c_uint32(0)

@@ -1105,6 +1105,12 @@ int ddgi_oracle_get_stats(ddgi_oracle_t* h, anerend_ddgi_stats_t* o) {
 int ddgi_oracle_reset_stats(ddgi_oracle_t* h) { for (auto& s : h->st) s = 0; return 0; }
 
 int ddgi_oracle_make_rotation(int32_t axis, float deg, float out[16]) { if (axis < 0 || axis > 2) return ANEREND_DDGI_E_INVALID; makeRotation(axis, deg, out); return 0; }
+// any-hit query through the oracle's own hierarchy for an arbitrary ray (planning probes: tests/lightspace_probe.py)
+int ddgi_oracle_any_hit(ddgi_oracle_t* h, const float origin[3], const float dir[3], float tmin, float tmax) {
+  if (!h || !h->haveAccel) return ANEREND_DDGI_E_INVALID;
+  uint64_t a = 0, b = 0;
+  return h->anyHit(v3(origin[0], origin[1], origin[2]), v3(dir[0], dir[1], dir[2]), tmin, tmax, a, b) ? 1 : 0;
+}
 int ddgi_oracle_shade_hit(ddgi_oracle_t* h, uint32_t prim, float u, float v, const float origin[3], int32_t specular, float out[4], uint32_t* lit_mask) {
   if (!h || !h->haveAccel || !h->haveUbo || prim >= h->tris.size()) return ANEREND_DDGI_E_INVALID;
   Hit hit{prim, 0.0f, u, v}; uint32_t lit = 0; uint64_t cnt[7] = {0, 0, 0, 0, 0, 0, 0}; V3 hp;

@@ -79,6 +79,8 @@ int ddgi_oracle_set_rays(ddgi_oracle_t* h, int32_t layer, const void* irr_rgba16
 int ddgi_oracle_upload_ray_radiance(ddgi_oracle_t* h, int32_t layer, const void* irr_rgba16f, size_t bytes, const float rot[16]);
 
 /* ---- single shader functions, exported for the known-answer tests ------------------------ */
+/* 1 if anything is hit in (tmin, tmax) along the ray (the shadow-ray query of rchit:48-66 for an arbitrary ray), 0 if not, < 0 on error. */
+int  ddgi_oracle_any_hit(ddgi_oracle_t* h, const float origin[3], const float dir[3], float tmin, float tmax);
 /* The hit shader for one hit (flattened triangle id, barycentrics) of a ray from `origin`: irradiance_probe_update.rchit
  * (specular = 0) or mirror_reflections.rchit (specular = 1) against the handle's current atlas; out = (irradiance, distance from
  * the origin).  The function trace_layer / specular_gi themselves call. */

@@ -86,6 +86,28 @@ def main():
     for nm, v in (("triangles in the ray's cell", in_cell), ("of those on the sun side within (tMin, tMax): exact tests left", ahead)):
         print(f"  {nm}: mean {v.mean():.1f}, median {np.median(v):.0f}, p90 {np.percentile(v, 90):.0f}, max {v.max()}")
 
+    # ---- is the culling conservative?  For a sample of the sun rays: the oracle's exact any-hit answer (its own hierarchy, validated against
+    # brute force) against "any candidate of the ray's grid cell passes the exact Moeller-Trumbore test" — the same ray on both sides, so
+    # every disagreement is a triangle the grid dropped.  The footprints are padded by `pad` cells (fp32 projection vs. the exact test).
+    if "--verify" in sys.argv:
+        o2 = ob.Oracle(make_params(nxz, ny, nr))
+        o2.set_threads(0); o2.upload_scene(scene); o2.set_scene_ubo(scene.ubo); o2.build_accel()
+        tri32 = tris.astype(np.float32)
+        sun32 = sun.astype(np.float32)
+        qs = q[:int(next((a.split("=")[1] for a in sys.argv if a.startswith("--rays=")), 4000))]
+        for pad in (0, 1):
+            c0p, c1p = np.clip(c0 - pad, 0, G - 1), np.clip(c1 + pad, 0, G - 1)
+            miss = 0
+            for i in qs:
+                org = pos[i].astype(np.float32)
+                exact = o2.any_hit(org, sun32)
+                cx, cy = np.clip(((pl[i, :2] - ext_lo) / cell).astype(int), 0, G - 1)
+                ids = np.nonzero((c0p[:, 0] <= cx) & (cx <= c1p[:, 0]) & (c0p[:, 1] <= cy) & (cy <= c1p[:, 1]) & (hi[:, 2] > pl[i, 2] + tmin - 1e-3))[0]
+                culled = any(ob.intersect(org, sun32, tri32[k, 0], tri32[k, 1], tri32[k, 2])[0] for k in ids)
+                miss += int(exact != culled)
+            print(f"conservativeness, footprints padded by {pad} cell(s): {miss} disagreements in {len(qs)} sun rays")
+        o2.close()
+
     # ---- point lights (extension E1): rays share their END point, so the analogue is a direction-space structure around each light
     # (e.g. a cube map of triangle lists).  Estimated per query with angular bounding cones instead of building the cube map: a triangle is a
     # candidate when the ray's direction from the light falls inside the triangle's cone widened by one cell (face resolution G), and its
