@@ -100,6 +100,9 @@ class Oracle(DdgiHandle):
     def set_threads(self, n):
         return self._fn("set_threads")(self._h, C.c_int32(n))
 
+    def set_sun_grid(self, resolution):
+        self._call("set_sun_grid", C.c_int32(resolution))
+
     def set_brute_force(self, on):
         self._call("set_brute_force", C.c_int32(1 if on else 0))
 

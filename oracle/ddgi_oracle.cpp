@@ -469,6 +469,70 @@ struct ddgi_oracle {
     return false;
   }
 
+  // ---- light-space grid for the sun's shadow rays (PROTOTYPE of DESIGN.md §8 item 1; off unless set_sun_grid) ----------------
+  // All sun shadow rays share one direction, so in the sun's orthographic space a ray is a POINT (x, y) plus a depth: the triangles it
+  // can hit are those whose footprint covers the point and whose depth interval reaches beyond the origin.  A G x G grid over the scene's
+  // footprint holds per-cell triangle lists (footprints padded by one cell: the projection is rounded, the exact test is not); a query
+  // runs the SAME tri_intersect on the candidates of its cell, so the answer — and with it lit mask and atlas — is bit-identical to the
+  // hierarchy's whenever the lists are a superset, which tests/test_sun_grid.py checks.
+  struct SunGrid {
+    int G = 0; double ax[3], ay[3], az[3]; double x0 = 0, y0 = 0, cw = 1, ch = 1;
+    std::vector<uint32_t> start, ids; std::vector<float> zmax;      // CSR lists + per-triangle far depth (towards the sun)
+  } sun;
+  int sunGridRes = 0;
+  void buildSunGrid() {
+    sun = SunGrid{};
+    if (sunGridRes <= 0 || tris.empty() || !haveUbo) return;
+    const int G = sunGridRes;
+    double d[3] = {-(double)ubo.light_dir[0], -(double)ubo.light_dir[1], -(double)ubo.light_dir[2]};
+    double dl = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]); if (!(dl > 0)) return;
+    for (int k = 0; k < 3; ++k) sun.az[k] = d[k] / dl;
+    double up[3] = {0, 1, 0}; if (std::fabs(sun.az[1]) > 0.99) { up[0] = 1; up[1] = 0; }
+    double a[3] = {sun.az[1] * up[2] - sun.az[2] * up[1], sun.az[2] * up[0] - sun.az[0] * up[2], sun.az[0] * up[1] - sun.az[1] * up[0]};
+    double al = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    for (int k = 0; k < 3; ++k) sun.ax[k] = a[k] / al;
+    sun.ay[0] = sun.az[1] * sun.ax[2] - sun.az[2] * sun.ax[1]; sun.ay[1] = sun.az[2] * sun.ax[0] - sun.az[0] * sun.ax[2]; sun.ay[2] = sun.az[0] * sun.ax[1] - sun.az[1] * sun.ax[0];
+    auto proj = [&](V3 p, double& x, double& y, double& z) {
+      x = sun.ax[0] * p.x + sun.ax[1] * p.y + sun.ax[2] * p.z; y = sun.ay[0] * p.x + sun.ay[1] * p.y + sun.ay[2] * p.z; z = sun.az[0] * p.x + sun.az[1] * p.y + sun.az[2] * p.z; };
+    const size_t n = tris.size();
+    std::vector<double> lox(n), loy(n), hix(n), hiy(n); sun.zmax.resize(n);
+    double ex0 = 1e300, ey0 = 1e300, ex1 = -1e300, ey1 = -1e300;
+    for (size_t i = 0; i < n; ++i) {
+      const WTri& t = tris[i]; V3 vtx[3] = {t.v0, t.v0 + t.e1, t.v0 + t.e2};
+      double zx = -1e300; lox[i] = loy[i] = 1e300; hix[i] = hiy[i] = -1e300;
+      for (int k = 0; k < 3; ++k) { double x, y, z; proj(vtx[k], x, y, z);
+        lox[i] = std::min(lox[i], x); hix[i] = std::max(hix[i], x); loy[i] = std::min(loy[i], y); hiy[i] = std::max(hiy[i], y); zx = std::max(zx, z); }
+      sun.zmax[i] = (float)zx;
+      ex0 = std::min(ex0, lox[i]); ex1 = std::max(ex1, hix[i]); ey0 = std::min(ey0, loy[i]); ey1 = std::max(ey1, hiy[i]);
+    }
+    sun.G = G; sun.x0 = ex0; sun.y0 = ey0; sun.cw = std::max((ex1 - ex0) / G, 1e-9); sun.ch = std::max((ey1 - ey0) / G, 1e-9);
+    auto cellRange = [&](double lo, double hi, double o, double c, int& a0, int& a1) {
+      a0 = std::min(std::max((int)std::floor((lo - o) / c) - 1, 0), G - 1); a1 = std::min(std::max((int)std::floor((hi - o) / c) + 1, 0), G - 1); };
+    std::vector<uint32_t> count((size_t)G * G + 1, 0);
+    for (size_t i = 0; i < n; ++i) { int x0c, x1c, y0c, y1c; cellRange(lox[i], hix[i], sun.x0, sun.cw, x0c, x1c); cellRange(loy[i], hiy[i], sun.y0, sun.ch, y0c, y1c);
+      for (int y = y0c; y <= y1c; ++y) for (int x = x0c; x <= x1c; ++x) ++count[(size_t)y * G + x + 1]; }
+    for (size_t c = 0; c < (size_t)G * G; ++c) count[c + 1] += count[c];
+    sun.start = count; sun.ids.resize(count.back());
+    std::vector<uint32_t> fill(sun.start.begin(), sun.start.end() - 1);
+    for (size_t i = 0; i < n; ++i) { int x0c, x1c, y0c, y1c; cellRange(lox[i], hix[i], sun.x0, sun.cw, x0c, x1c); cellRange(loy[i], hiy[i], sun.y0, sun.ch, y0c, y1c);
+      for (int y = y0c; y <= y1c; ++y) for (int x = x0c; x <= x1c; ++x) sun.ids[fill[(size_t)y * G + x]++] = (uint32_t)i; }   // ascending triangle id per cell
+  }
+  bool anyHitSun(V3 o, V3 d, float tmin, float tmax, uint64_t& cellsV, uint64_t& trisT) const {
+    const double x = sun.ax[0] * o.x + sun.ax[1] * o.y + sun.ax[2] * o.z, y = sun.ay[0] * o.x + sun.ay[1] * o.y + sun.ay[2] * o.z;
+    const double z = sun.az[0] * o.x + sun.az[1] * o.y + sun.az[2] * o.z;
+    const int cx = std::min(std::max((int)std::floor((x - sun.x0) / sun.cw), 0), sun.G - 1), cy = std::min(std::max((int)std::floor((y - sun.y0) / sun.ch), 0), sun.G - 1);
+    const size_t c = (size_t)cy * sun.G + cx; ++cellsV;
+    const float zgate = (float)(z + tmin) - 1e-3f * (1.0f + std::fabs((float)z));     // triangles entirely behind the origin + tMin cannot be hit
+    float t, u, v;
+    for (uint32_t k = sun.start[c]; k < sun.start[c + 1]; ++k) {
+      const uint32_t id = sun.ids[k];
+      if (sun.zmax[id] < zgate) continue;
+      const WTri& tr = tris[id]; ++trisT;
+      if (tri_intersect(o, d, tr.v0, tr.e1, tr.e2, tmin, tmax, t, u, v)) return true;
+    }
+    return false;
+  }
+
   // ---- probe-grid addressing shared by rgen:75-83 and pbr_light.glsl:294-301 -------------------------
   // Bake mode (UBO_BAKE_MODE_ON_FLAG; rgen:61-73, pbr_light.glsl:274-291): the grid covers the tile bakeTileInfo.xy of size
   // bakeTileInfo.z: origin = tile corner, step = (tSize / nXZ, 1.0, tSize / nXZ) — the y step is 1, not PROBE_STEP.y.
@@ -705,7 +769,7 @@ struct ddgi_oracle {
     bool occluded = true;
     if (!(p.flags & ANEREND_DDGI_FLAG_SKIP_DEAD_SHADOW_RAYS) || dot(normal, shadowDir) > 0.0f) {
       cnt[2]++;
-      occluded = anyHit(pos, shadowDir, p.t_min, p.t_max, cnt[5], cnt[6]);
+      occluded = sun.G ? anyHitSun(pos, shadowDir, p.t_min, p.t_max, cnt[5], cnt[6]) : anyHit(pos, shadowDir, p.t_min, p.t_max, cnt[5], cnt[6]);
     }
     V3 color = P(vv[0]->color) * b0 + P(vv[1]->color) * b1 + P(vv[2]->color) * b2;
     color = toLinear(color);
@@ -952,11 +1016,23 @@ int ddgi_oracle_sample_texture(ddgi_oracle_t* h, int32_t idx, float u, float v, 
   if (idx < 0 || (size_t)idx >= h->textures.size()) return ANEREND_DDGI_E_INVALID;
   h->sampleTexture(idx, u, v, out); return 0;
 }
-int ddgi_oracle_set_scene_ubo(ddgi_oracle_t* h, const anerend_scene_ubo_t* ubo) { h->ubo = *ubo; h->haveUbo = true; return 0; }
+int ddgi_oracle_set_scene_ubo(ddgi_oracle_t* h, const anerend_scene_ubo_t* ubo) {
+  const bool sunMoved = !h->haveUbo || std::memcmp(h->ubo.light_dir, ubo->light_dir, 12) != 0;
+  h->ubo = *ubo; h->haveUbo = true;
+  if (sunMoved && h->haveAccel) h->buildSunGrid();          // the grid lives in the sun's space
+  return 0;
+}
+// Prototype switch: resolution of the light-space grid the sun's shadow rays use instead of the hierarchy (0 = off, the default).
+int ddgi_oracle_set_sun_grid(ddgi_oracle_t* h, int32_t resolution) {
+  if (resolution < 0 || resolution > 4096) return ANEREND_DDGI_E_INVALID;
+  h->sunGridRes = resolution;
+  if (h->haveAccel) h->buildSunGrid();
+  return 0;
+}
 int ddgi_oracle_build_accel(ddgi_oracle_t* h) {
   if (!h->haveScene) { h->err = "build_accel before upload_scene"; return ANEREND_DDGI_E_STATE; }
   int rc = h->buildInstances(); if (rc) return rc;
-  h->bvh.build(h->tris); h->haveAccel = true; return 0;
+  h->bvh.build(h->tris); h->buildSunGrid(); h->haveAccel = true; return 0;
 }
 int ddgi_oracle_update_vertices(ddgi_oracle_t* h, const anerend_vertex_t* v, uint32_t first, uint32_t count) {
   if (!v || (size_t)first + count > h->vertices.size()) { h->err = "vertex range out of bounds"; return ANEREND_DDGI_E_INVALID; }
@@ -970,6 +1046,7 @@ int ddgi_oracle_refit_accel(ddgi_oracle_t* h, const anerend_renderable_t* r, uin
   int rc = h->buildInstances(); if (rc) return rc;
   if (h->tris.size() != nt || h->instances.size() != ninst) { h->err = "visibility changed: rebuild required"; h->haveAccel = false; return ANEREND_DDGI_E_STATE; }
   h->bvh.build(h->tris);   // the oracle simply rebuilds; closest hit does not depend on the tree
+  h->buildSunGrid();
   return 0;
 }
 // cull.comp:241-244,296-303 (withinRangeOfCamera + setCullBit), centre = buildTranslation(model) * vec4(bounds.xyz, 1) (cull.comp:229-239,297)

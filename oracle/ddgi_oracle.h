@@ -34,6 +34,10 @@ int ddgi_oracle_set_threads(ddgi_oracle_t* h, int32_t n);
 /* 1 = brute-force ray/triangle loops instead of the oracle's own BVH (validates that BVH). */
 int ddgi_oracle_set_brute_force(ddgi_oracle_t* h, int32_t on);
 
+/* PROTOTYPE: answer the sun's shadow rays from a resolution x resolution light-space grid of triangle lists instead of
+ * the hierarchy (0 = off).  Same exact triangle test, so results must not change: tests/test_sun_grid.py. */
+int ddgi_oracle_set_sun_grid(ddgi_oracle_t* h, int32_t resolution);
+
 int ddgi_oracle_upload_scene(ddgi_oracle_t* h,
     const anerend_vertex_t* vertices, uint32_t num_vertices,
     const uint32_t* indices, uint32_t num_indices,
