@@ -605,11 +605,145 @@ struct TraceCtx {
   V3 camOff, step, sky, lightDir;
   float tmin, tmax, sunIntensity;
   uint32_t uboFlags, flags;
+  // light maps (below): conservative distance maps around the point lights that answer "certainly unoccluded" shadow rays
+  const int* lmStatic; const int* lmDynamic; const uint32_t* lmNear; uint32_t lmRes;      // lmRes = 0: none
 };
 
 // Row stripe (multi-GPU sharding inside the layers): launched probe `pl` of a layer -> probe index in the layer.  A handle
 // updates the probe rows z = rowOffset + k*rowStride of every layer it launches; (0, 1) = all rows.
 HD int stripe_probe(int pl, int nXZ, int rowOffset, int rowStride) { return ((pl / nXZ) * rowStride + rowOffset) * nXZ + pl % nXZ; }
+
+// ----------------------------------------------------------------------------------------------------
+// Light maps: a pre-filter for the point-light shadow rays of extension E1 (rchit:45-66 composed with calcLight's point branch).
+//
+// Around every enabled point light a cube map (6 faces x R x R) holds, per texel, a LOWER BOUND of the distance from the light
+// to any triangle that reaches into the texel's pyramid of directions.  A shadow ray pos -> light runs along ONE direction from
+// the light and covers the distances (0, dist - tMin) from it; if that interval ends before the bound of the direction's texel,
+// no triangle can intersect the ray, so the ray is unoccluded and is never traced.  Everything else — rays that are occluded,
+// rays that graze a surface, texels with depth complexity in front of the hit — goes through the BVH as before.  The exact
+// Moeller-Trumbore test is never replaced, only skipped where its answer is known, so lit masks and radiance stay bit-identical
+// to the oracle's; the margins (LM_DELTA on the footprints, rho on the plane bound, the slack in lightmap_unoccluded) are orders of
+// magnitude above fp32 rounding of either side.  At C3 (R = 512) 81 % of the unoccluded point-light rays — the ones that walk the
+// most nodes, since nothing ends them early — are answered by one 4-byte read.
+//
+//   face f = 2 * axis + (d[axis] < 0), axis = major axis of d = p - lightPos; in-face coordinates u = d[axis+1] / |d[axis]|,
+//   v = d[axis+2] / |d[axis]| in [-1, 1]; texel X = floor((u + 1) / 2 * R).
+//   static map: all triangles at build_accel time.  dynamic map: the triangles of instances that moved since (refit), rasterised
+//   again at every refit; the bound is the minimum of both (a stale static entry of a mover is only a lower bound that is too low).
+// ----------------------------------------------------------------------------------------------------
+#define LM_EPS_W 1e-4f          // points nearer than this to a face's apex plane are not projected (see LM_NEAR)
+#define LM_NEAR 0.02f           // a triangle this close to a light disables that light's map (lmNear): its projection is unbounded
+#define LM_DELTA 1e-4f          // footprint growth in face coordinates (texel size at R = 512: 3.9e-3)
+#define LM_FAR_BITS 0x7F7F7F7F  // "nothing here" (3.39e38), the byte pattern of the clearing memset
+struct LmTri { V3 r[3]; V3 n; float h, daabb; bool skinny, nearLight; };
+HD float comp3(V3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+// vertices relative to the light -> plane, box distance; false: cannot occlude a ray of this light (beyond its range, or degenerate)
+HD bool lm_tri_setup(V3 r0, V3 r1, V3 r2, float range, LmTri& t) {
+  t.r[0] = r0; t.r[1] = r1; t.r[2] = r2;
+  const V3 lo = min3(min3(r0, r1), r2), hi = max3(max3(r0, r1), r2);
+  const float dx = fmaxf(fmaxf(lo.x, -hi.x), 0.0f), dy = fmaxf(fmaxf(lo.y, -hi.y), 0.0f), dz = fmaxf(fmaxf(lo.z, -hi.z), 0.0f);
+  t.daabb = sqrtf(dx * dx + dy * dy + dz * dz) * 0.999999f;        // distance from the light to the triangle's box: a bound that needs no plane
+  if (t.daabb > range) return false;                               // rays of this light are shorter than its range
+  t.nearLight = t.daabb < LM_NEAR;
+  const V3 e1 = r1 - r0, e2 = r2 - r0;
+  const V3 n = mk3(e1.y * e2.z - e1.z * e2.y, e1.z * e2.x - e1.x * e2.z, e1.x * e2.y - e1.y * e2.x);
+  const float n2 = dot3(n, n);
+  if (!(n2 > 0.0f)) return false;                                  // zero area: det == 0 in the triangle test, never hit
+  t.skinny = n2 < 1e-8f * dot3(e1, e1) * dot3(e2, e2);             // normal too noisy for the plane bound: box bound only
+  const float inv = 1.0f / sqrtf(n2);
+  t.n = n * inv; t.h = fabsf(dot3(t.n, r0));
+  return true;
+}
+// texel rectangle of the triangle's projection on `face`, grown by LM_DELTA; false: the triangle does not reach the face
+HD bool lm_face_rect(const LmTri& t, int face, uint32_t R, int& x0, int& x1, int& y0, int& y1) {
+  const int axis = face >> 1, ab = axis == 2 ? 0 : axis + 1, ac = ab == 2 ? 0 : ab + 1;
+  const float s = (face & 1) ? -1.0f : 1.0f;
+  float w[3], b[3], c[3];
+  for (int k = 0; k < 3; ++k) { w[k] = s * comp3(t.r[k], axis); b[k] = comp3(t.r[k], ab); c[k] = comp3(t.r[k], ac); }
+  const float wmax = fmaxf(fmaxf(w[0], w[1]), w[2]), wmin = fminf(fminf(w[0], w[1]), w[2]);
+  if (!(wmax > LM_EPS_W)) return false;
+  float umin, umax, vmin, vmax;
+  if (wmin > LM_EPS_W) {          // wholly in front of the apex plane: the projection is the triangle of the projected vertices
+    const float u0 = b[0] / w[0], u1 = b[1] / w[1], u2 = b[2] / w[2], v0 = c[0] / w[0], v1 = c[1] / w[1], v2 = c[2] / w[2];
+    umin = fminf(fminf(u0, u1), u2); umax = fmaxf(fmaxf(u0, u1), u2); vmin = fminf(fminf(v0, v1), v2); vmax = fmaxf(fmaxf(v0, v1), v2);
+  } else {                        // straddles the apex plane: interval arithmetic over the box, w clipped to [LM_EPS_W, wmax]
+    const float blo = fminf(fminf(b[0], b[1]), b[2]), bhi = fmaxf(fmaxf(b[0], b[1]), b[2]), clo = fminf(fminf(c[0], c[1]), c[2]), chi = fmaxf(fmaxf(c[0], c[1]), c[2]);
+    const float il = 1.0f / LM_EPS_W, ih = 1.0f / wmax;
+    umin = fminf(fminf(blo * il, blo * ih), fminf(bhi * il, bhi * ih)); umax = fmaxf(fmaxf(blo * il, blo * ih), fmaxf(bhi * il, bhi * ih));
+    vmin = fminf(fminf(clo * il, clo * ih), fminf(chi * il, chi * ih)); vmax = fmaxf(fmaxf(clo * il, clo * ih), fmaxf(chi * il, chi * ih));
+  }
+  umin -= LM_DELTA; umax += LM_DELTA; vmin -= LM_DELTA; vmax += LM_DELTA;
+  if (umax < -1.0f || umin > 1.0f || vmax < -1.0f || vmin > 1.0f) return false;
+  const float fr = (float)R, top = (float)(R - 1u);
+  x0 = (int)fminf(fmaxf(floorf((umin + 1.0f) * 0.5f * fr), 0.0f), top); x1 = (int)fminf(fmaxf(floorf((umax + 1.0f) * 0.5f * fr), 0.0f), top);
+  y0 = (int)fminf(fmaxf(floorf((vmin + 1.0f) * 0.5f * fr), 0.0f), top); y1 = (int)fminf(fmaxf(floorf((vmax + 1.0f) * 0.5f * fr), 0.0f), top);
+  return true;
+}
+// lower bound of the distance from the light to the triangle inside texel (X, Y) of `face`: the triangle's plane cut by the texel's
+// direction nearest to the plane normal (|cos| of the centre direction + the texel's angular radius rho), never below the box distance
+HD float lm_texel_bound(V3 n, float h, float daabb, bool skinny, int face, int X, int Y, uint32_t R, float rho) {
+  const int axis = face >> 1, ab = axis == 2 ? 0 : axis + 1, ac = ab == 2 ? 0 : ab + 1;
+  const float cu = ((float)X + 0.5f) * (2.0f / (float)R) - 1.0f, cv = ((float)Y + 0.5f) * (2.0f / (float)R) - 1.0f;
+  const float s = (face & 1) ? -1.0f : 1.0f;
+  const float inv = 1.0f / sqrtf(1.0f + cu * cu + cv * cv);
+  const float cosn = fabsf(comp3(n, axis) * s + comp3(n, ab) * cu + comp3(n, ac) * cv) * inv;
+  const float plane = h / fminf(1.0f, cosn + rho);
+  return (skinny ? daabb : fmaxf(plane, daabb)) * 0.999996f;
+}
+HD float lm_rho(uint32_t R) { return 1.4143f / (float)R * 1.02f + 2e-5f; }
+// Is the shadow ray pos -> light (tMin, dist) certainly unoccluded?  `dist` = length(lightPos - pos) as the hit shader computes it.
+HD bool lightmap_unoccluded(const TraceCtx& c, uint32_t li, V3 lp, V3 pos, float dist) {
+  if (c.lmRes == 0u || c.lmNear[li] != 0u) return false;
+  const V3 d = pos - lp;
+  const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+  int face; float w, b, cc;
+  if (ax >= ay && ax >= az) { face = d.x < 0.0f ? 1 : 0; w = ax; b = d.y; cc = d.z; }
+  else if (ay >= az) { face = d.y < 0.0f ? 3 : 2; w = ay; b = d.z; cc = d.x; }
+  else { face = d.z < 0.0f ? 5 : 4; w = az; b = d.x; cc = d.y; }
+  if (!(w > 0.0f)) return false;
+  const float fr = (float)c.lmRes, top = (float)(c.lmRes - 1u);
+  const int X = (int)fminf(fmaxf(floorf((b / w + 1.0f) * 0.5f * fr), 0.0f), top), Y = (int)fminf(fmaxf(floorf((cc / w + 1.0f) * 0.5f * fr), 0.0f), top);
+  const size_t o = (((size_t)li * 6u + (size_t)face) * c.lmRes + (size_t)Y) * c.lmRes + (size_t)X;
+  int bits = c.lmStatic[o];
+  if (c.lmDynamic) { const int db = c.lmDynamic[o]; bits = db < bits ? db : bits; }      // positive floats order like their bit patterns
+  return dist - c.tmin < u2f((uint32_t)bits) * 0.9999f - 1e-3f;
+}
+// Rasterisation, one (triangle, light) pair: every face, every texel of the footprint.  The CUDA kernel (k_lightmap_raster,
+// ddgi_api.cu) runs the same setup per thread and spreads the texel loops over the warp.
+struct LmBuildCtx {
+  const float4* wtri; const uint32_t* triInstance; const uint32_t* moved;      // moved: per instance, or null = every triangle
+  const anerend_light_t* lights; uint32_t numTris, numLights, R; float rho;
+  int* depth; uint32_t* nearFlags;
+};
+HD bool lm_pair_setup(const LmBuildCtx& c, uint32_t t, uint32_t li, LmTri& tri) {
+  if (c.moved && !c.moved[c.triInstance[t]]) return false;
+  const anerend_light_t* lt = &c.lights[li];
+  if (!(lt->color[3] > 0.5f)) return false;
+  const float4 a = c.wtri[3 * (size_t)t], b = c.wtri[3 * (size_t)t + 1], cc = c.wtri[3 * (size_t)t + 2];
+  const V3 lp = mk3(lt->world_pos[0], lt->world_pos[1], lt->world_pos[2]);
+  const V3 v0 = mk3(a.x, a.y, a.z), e1 = mk3(a.w, b.x, b.y), e2 = mk3(b.z, b.w, cc.x);
+  return lm_tri_setup(v0 - lp, (v0 + e1) - lp, (v0 + e2) - lp, lt->world_pos[3], tri);
+}
+HD void lightmap_raster_body(uint32_t i, const LmBuildCtx& c) {
+  const uint32_t t = i % c.numTris, li = i / c.numTris;
+  LmTri tri;
+  if (!lm_pair_setup(c, t, li, tri)) return;
+  if (tri.nearLight) c.nearFlags[li] = 1u;
+  for (int face = 0; face < 6; ++face) {
+    int x0, x1, y0, y1;
+    if (!lm_face_rect(tri, face, c.R, x0, x1, y0, y1)) continue;
+    int* dm = c.depth + ((size_t)li * 6u + (size_t)face) * c.R * c.R;
+    for (int y = y0; y <= y1; ++y) for (int x = x0; x <= x1; ++x)
+      atomMin(dm + (size_t)y * c.R + x, (int)f2u(lm_texel_bound(tri.n, tri.h, tri.daabb, tri.skinny, face, x, y, c.R, c.rho)));
+  }
+}
+// instances whose transform differs from the one the static map was rasterised with
+struct LmMovedCtx { const InstXform* xforms; const InstXform* base; uint32_t* moved; };
+HD void lm_moved_body(uint32_t i, const LmMovedCtx& c) {
+  bool m = false;
+  for (int k = 0; k < 12; ++k) m = m || f2u(c.xforms[i].o2w[k]) != f2u(c.base[i].o2w[k]);
+  c.moved[i] = m ? 1u : 0u;
+}
 
 HD float sign_not_zero(float k) { return (k >= 0.0f) ? 1.0f : -1.0f; }            // octahedron_helpers.glsl:1-3
 HD void oct_encode(V3 v, float& ox, float& oy) {                                    // octahedron_helpers.glsl:10-20
@@ -944,8 +1078,10 @@ HD V3 shade_hit_simple(const TraceCtx& c, const Hit& hit, V3 origin, uint32_t& l
       if (!(dist < range)) continue;
       const V3 L = normalize3(lp - pos);
       if (!(dot3(normal, L) > 0.0f)) continue;
-      ++nShadow;
-      if (traverse<true, CNT>(c.nodes, c.bvhTris, c.numNodes, pos, L, c.tmin, dist, sh, cn[1], ct[1])) continue;
+      if (!lightmap_unoccluded(c, li, lp, pos, dist)) {       // else: answered by the light map, not traced
+        ++nShadow;
+        if (traverse<true, CNT>(c.nodes, c.bvhTris, c.numNodes, pos, L, c.tmin, dist, sh, cn[1], ct[1])) continue;
+      }
       lit |= 1u << (1u + li);
       const float dd = fminf(dist, range);
       const float att = (1.0f - dd / range) * (1.0f - dd / range) * 1.0f;

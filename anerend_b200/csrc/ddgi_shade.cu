@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(256) k_probe_convolve_fast(const ConvFastCtx f
   const float* W = f.weights + (size_t)layerLocal * c.N * 64 + texel;
   for (int r0 = 0; r0 < c.N; r0 += CONV_CHUNK) {
     const int nr = min(CONV_CHUNK, c.N - r0);
+    int bad = 0;
     __syncthreads();
     for (int e = (int)threadIdx.x; e < CONV_G * CONV_CHUNK; e += 256) {
       const int g = e / CONV_CHUNK, r = e % CONV_CHUNK;
@@ -185,8 +186,30 @@ __global__ void __launch_bounds__(256) k_probe_convolve_fast(const ConvFastCtx f
         v = make_float4(h2f((uint16_t)(rr.x & 0xFFFFu)), h2f((uint16_t)(rr.x >> 16)), h2f((uint16_t)(rr.y & 0xFFFFu)), 1.0f);
       }
       sRad[e] = v;
+      bad |= !(fabsf(v.x) <= 3.0e38f) || !(fabsf(v.y) <= 3.0e38f) || !(fabsf(v.z) <= 3.0e38f);
     }
-    __syncthreads();
+    // probe_conv.comp:54-57 SKIPS rays with weight <= 1e-6; multiplying by the zeroed weight is the same value unless the
+    // radiance is Inf/NaN (an fp16 overflow of a very bright hit): 0 * Inf = NaN where the shader adds nothing.  Blocks that
+    // staged a non-finite radiance (block-uniform, rare) take the loop with the explicit skip.
+    if (__syncthreads_or(bad)) {
+      const float4* badRad = sRad + sub * CONV_PPT * CONV_CHUNK;
+      for (int r = 0; r < nr; ++r) {
+        const float w = __ldg(W + (size_t)(r0 + r) * 64);
+        accW += w;
+        if (w != 0.0f) {
+#pragma unroll
+          for (int k = 0; k < CONV_PPT; ++k) {
+            const float4 v = badRad[k * CONV_CHUNK + r];
+#ifdef DDGI_SHADE_EXACT
+            acc[k][0] = acc[k][0] + w * v.x; acc[k][1] = acc[k][1] + w * v.y; acc[k][2] = acc[k][2] + w * v.z;
+#else
+            acc[k][0] = fmaf(w, v.x, acc[k][0]); acc[k][1] = fmaf(w, v.y, acc[k][1]); acc[k][2] = fmaf(w, v.z, acc[k][2]);
+#endif
+          }
+        }
+      }
+      continue;
+    }
     const float4* myRad = sRad + sub * CONV_PPT * CONV_CHUNK;
 #pragma unroll 4
     for (int r = 0; r < nr; ++r) {

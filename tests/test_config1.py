@@ -65,3 +65,61 @@ def test_cuda_config1_matches_oracle(kernels, oracle, make_gpu):
     got, rec, dirs = _run(make, oracle)
     assert np.array_equal(got, want) and np.array_equal(dirs, wdirs)
     assert np.array_equal(rec.view(np.uint32), wrec.view(np.uint32))
+
+
+# ---- non-finite radiance (an fp16 overflow of a very bright hit): probe_conv.comp:54-57 SKIPS rays whose weight is <= 1e-6, so an
+# Inf / NaN radiance on a ray facing away from a texel must leave that texel finite; where the ray does contribute, Inf / NaN propagate.
+def _radiance_nonfinite(layer):
+    irr = _radiance(layer)
+    rng = np.random.RandomState(77 + layer)
+    flat = irr.reshape(-1, 4)
+    idx = rng.choice(len(flat), 24, replace=False)
+    flat[idx[:12], rng.randint(0, 3, 12)] = np.float16(np.inf)
+    flat[idx[12:], rng.randint(0, 3, 12)] = np.float16(np.nan)
+    return irr
+
+
+def _run_nonfinite(make, oracle):
+    h = make(make_params(NXZ, NY, NR, flags=L.FLAG_TEXEL_RECORDS))
+    h.set_scene_ubo(scenes.empty_scene(grid=(NXZ, NY, NR)).ubo)
+    rot = oracle.make_rotation(*scenes.rotation_sequence(1, 1)[0])
+    for layer in range(2):
+        h.upload_ray_radiance(layer, _radiance_nonfinite(layer), rot)
+        h.convolve_layer(layer)
+    atlas = h.download_atlas()
+    h.close()
+    return atlas[:2 * 10 * NXZ]
+
+
+def _same_texels(a, b):
+    """Equal bit patterns, NaNs compared as NaN (their payload is not defined by the shader)."""
+    fa, fb = a.view(np.float16), b.view(np.float16)
+    return bool(np.all((a == b) | (np.isnan(fa) & np.isnan(fb))))
+
+
+def test_nonfinite_radiance_is_skipped_on_zero_weight_rays(oracle, make_emu):
+    want = _run_nonfinite(oracle.Oracle, oracle)
+    f = want.view(np.float16)
+    assert np.isnan(f).any() or np.isinf(f).any(), "the fixture must reach some texels"
+    from tests.parity import interior_mask
+    m = interior_mask(NXZ, 2)
+    assert np.isfinite(f[m]).mean() > 0.3, "texels facing away from the overflowing rays stay finite"
+    assert _same_texels(_run_nonfinite(make_emu, oracle), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernels", ["wavefront", "wavefront_fast", "simple"])
+def test_cuda_nonfinite_radiance_matches_oracle(kernels, oracle, make_gpu):
+    want = _run_nonfinite(oracle.Oracle, oracle)
+
+    def make(p):
+        p.flags |= {"simple": L.FLAG_SIMPLE_KERNELS, "wavefront_fast": L.FLAG_FAST_MATH}.get(kernels, 0)
+        return make_gpu(p)
+    got = _run_nonfinite(make, oracle)
+    if kernels == "wavefront_fast":       # same texels finite / non-finite; values within the fast-math bar
+        fw, fg = want.view(np.float16).astype(np.float32), got.view(np.float16).astype(np.float32)
+        assert np.array_equal(np.isfinite(fw), np.isfinite(fg))
+        ok = np.isfinite(fw)
+        assert np.max(np.abs(fw[ok] - fg[ok]) / np.maximum(np.abs(fw[ok]), 1e-3)) < 2e-3
+    else:
+        assert _same_texels(got, want)
