@@ -44,6 +44,8 @@ DDGI_KERNEL(k_indirect_diffuse, indirect_diffuse_body, ConsumerCtx)
 DDGI_KERNEL(k_shadow_rt, shadow_rt_body, ShadowRtCtx)
 DDGI_KERNEL(k_specular_gi, specular_gi_body, SpecularCtx)
 DDGI_KERNEL(k_atlas_clear, clear_body, ClearCtx)
+DDGI_KERNEL(k_lightmap_raster_serial, lightmap_raster_body, LmBuildCtx)
+DDGI_KERNEL(k_lightmap_moved, lm_moved_body, LmMovedCtx)
 
 // ------------------------------------------------------------------------------------------------ handle
 struct anerend_ddgi {
@@ -103,6 +105,9 @@ struct anerend_ddgi {
   // ShadowRT scratch (pixels): staged positions, visibility words, ray queue, counters
   float4* dExtRays = nullptr; float* dExtDist = nullptr; uint32_t extPixels = 0;      // SpecularGIRT: staged rays, hit distances
   float4* dSrtPos = nullptr; uint32_t* dSrtLit = nullptr; uint32_t* dSrtQueue = nullptr; uint32_t* dSrtQcount = nullptr; uint32_t srtPixels = 0; int srtGrid = 0;
+  // light maps (ddgi_kernels.cuh): static + dynamic distance cube maps per point light, the transforms the static map was made with
+  unsigned long long* dLmStatic = nullptr; unsigned long long* dLmDynamic = nullptr; uint32_t* dLmNear = nullptr; InstXform* dLmBase = nullptr; uint32_t* dLmMoved = nullptr;
+  uint32_t lmRes = 0, lmLights = 0; bool lmDynamicValid = false; float lmMs = 0.0f;
   size_t fastRays = 0; uint32_t fastQueues = 0; int gridPrimary[2] = {0, 0}, gridShadow[2] = {0, 0}; uint32_t tune[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int sms = 0;
 
   int rowOffset = 0, rowStride = 1, Pl = 0;                // row stripe (set_row_stripe): probes launched per layer = Pl
@@ -197,6 +202,8 @@ void freeAccel(anerend_ddgi* h) {
   be.free(h->dInstances); be.free(h->dXforms); be.free(h->dTriInstance); be.free(h->dWtri); be.free(h->dTriLo); be.free(h->dTriHi);
   be.free(h->dNodes); be.free(h->dBvhTris); be.free(h->dNodeParent); be.free(h->dNodeLo); be.free(h->dNodeHi); be.free(h->dNodePending); be.free(h->dVisit);
   be.free(h->dShadeTris); h->dShadeTris = nullptr; be.free(h->dShadeUV); h->dShadeUV = nullptr;
+  be.free(h->dLmStatic); be.free(h->dLmDynamic); be.free(h->dLmNear); be.free(h->dLmBase); be.free(h->dLmMoved);
+  h->dLmStatic = nullptr; h->dLmDynamic = nullptr; h->dLmNear = nullptr; h->dLmBase = nullptr; h->dLmMoved = nullptr; h->lmRes = 0; h->lmLights = 0; h->lmDynamicValid = false;
   h->dInstances = nullptr; h->dXforms = nullptr; h->dTriInstance = nullptr; h->dWtri = nullptr; h->dTriLo = nullptr; h->dTriHi = nullptr;
   h->dNodes = nullptr; h->dBvhTris = nullptr; h->dNodeParent = nullptr; h->dNodeLo = nullptr; h->dNodeHi = nullptr; h->dNodePending = nullptr; h->dVisit = nullptr;
   h->haveAccel = false; h->numTris = 0; h->numNodes = 0;
@@ -215,6 +222,91 @@ int clearAtlas(anerend_ddgi* h) {
   if (h->dTexelRecords) BE_CHECK(h, h->be.zero(h->dTexelRecords, (size_t)h->W * h->H * sizeof(float4)));
   BE_CHECK(h, h->be.check());
   return 0;
+}
+
+#ifndef DDGI_HOST_EMU
+// One thread per (triangle, light of blockIdx.y): the setup of lightmap_raster_body per thread, the texel loops of the
+// footprints spread over the warp (a footprint is a few dozen texels at R = 512, but a triangle next to a light covers a
+// whole face: per-thread loops would leave one lane running for milliseconds).
+__global__ void __launch_bounds__(256) k_lightmap_raster(const LmBuildCtx c) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, li = blockIdx.y, lane = threadIdx.x & 31u;
+  LmTri tri;
+  tri.n = mk3(0.0f); tri.h = 0.0f; tri.daabb = 0.0f; tri.skinny = false; tri.nearLight = false;
+  const bool ok = t < c.numTris && lm_pair_setup(c, t, li, tri);
+  if (ok && tri.nearLight) c.nearFlags[li] = 1u;
+  for (int face = 0; face < 6; ++face) {
+    int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
+    const bool reach = ok && lm_face_rect(tri, face, c.R, x0, x1, y0, y1);
+    unsigned long long* dm = c.depth + ((size_t)li * 6u + (size_t)face) * c.R * c.R;
+    for (uint32_t m = __ballot_sync(0xFFFFFFFFu, reach); m != 0u; m &= m - 1u) {
+      const int src = __ffs((int)m) - 1;
+      const int bx0 = __shfl_sync(0xFFFFFFFFu, x0, src), bx1 = __shfl_sync(0xFFFFFFFFu, x1, src);
+      const int by0 = __shfl_sync(0xFFFFFFFFu, y0, src), by1 = __shfl_sync(0xFFFFFFFFu, y1, src);
+      const V3 n = mk3(__shfl_sync(0xFFFFFFFFu, tri.n.x, src), __shfl_sync(0xFFFFFFFFu, tri.n.y, src), __shfl_sync(0xFFFFFFFFu, tri.n.z, src));
+      const float hh = __shfl_sync(0xFFFFFFFFu, tri.h, src), da = __shfl_sync(0xFFFFFFFFu, tri.daabb, src);
+      const bool sk = __shfl_sync(0xFFFFFFFFu, tri.skinny ? 1 : 0, src) != 0;
+      const uint32_t tid = __shfl_sync(0xFFFFFFFFu, t, src);
+      const int wdt = bx1 - bx0 + 1, cnt = wdt * (by1 - by0 + 1);
+      for (int k = (int)lane; k < cnt; k += 32) {
+        const int x = bx0 + k % wdt, y = by0 + k / wdt;
+        atomMin64(dm + (size_t)y * c.R + x, ((unsigned long long)__float_as_uint(lm_texel_bound(n, hh, da, sk, face, x, y, c.R, c.rho)) << 32) | tid);
+      }
+    }
+  }
+}
+#endif
+uint32_t lightMapResolution(const anerend_ddgi* h) {
+  if (!(h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) || (h->p.flags & ANEREND_DDGI_FLAG_NO_LIGHT_MAPS) || h->numLights == 0 || h->numTris == 0) return 0;
+  uint32_t r = 512;
+  if (const char* e = getenv("DDGI_LM_RES")) r = (uint32_t)atoi(e);          // sweeps only; 0 disables the maps
+  return r > 4096u ? 4096u : r;
+}
+// Rasterises the triangles into the light maps: all of them into the static map (after build_accel, or when vertices
+// changed), or only those of moved instances into the dynamic map (refit).
+int rasterLightMap(anerend_ddgi* h, unsigned long long* target, const uint32_t* moved) {
+  Backend& be = h->be;
+  const size_t texels = (size_t)h->lmLights * 6u * h->lmRes * h->lmRes;
+  BE_CHECK(h, be.fill(target, 0x7F, texels * sizeof(unsigned long long)));
+  LmBuildCtx c{};
+  c.wtri = h->dWtri; c.triInstance = h->dTriInstance; c.moved = moved; c.lights = h->dLights; c.numTris = h->numTris; c.numLights = h->lmLights;
+  c.R = h->lmRes; c.rho = lm_rho(h->lmRes); c.depth = target; c.nearFlags = h->dLmNear;
+#ifndef DDGI_HOST_EMU
+  k_lightmap_raster<<<dim3((h->numTris + 255u) / 256u, h->lmLights), 256, 0, be.stream>>>(c);
+  ++be.launches;
+#else
+  DDGI_LAUNCH(be, k_lightmap_raster_serial, lightmap_raster_body, h->numTris * h->lmLights, c, 256);
+#endif
+  BE_CHECK(h, be.check());
+  return 0;
+}
+int buildLightMaps(anerend_ddgi* h) {
+  Backend& be = h->be;
+  const uint32_t R = lightMapResolution(h);
+  if (R == 0) { h->lmRes = 0; return 0; }
+  const size_t texels = (size_t)h->numLights * 6u * R * R, ni = h->instances.size();
+  if (h->lmRes != R || h->lmLights != h->numLights || !h->dLmStatic) {
+    be.free(h->dLmStatic); be.free(h->dLmDynamic); be.free(h->dLmNear); be.free(h->dLmBase); be.free(h->dLmMoved);
+    h->dLmStatic = nullptr; h->dLmDynamic = nullptr; h->dLmNear = nullptr; h->dLmBase = nullptr; h->dLmMoved = nullptr;
+    BE_CHECK(h, be.alloc(&h->dLmStatic, texels)); BE_CHECK(h, be.alloc(&h->dLmNear, h->numLights));
+    BE_CHECK(h, be.alloc(&h->dLmBase, ni)); BE_CHECK(h, be.alloc(&h->dLmMoved, ni));
+    h->lmRes = R; h->lmLights = h->numLights;
+  }
+  BE_CHECK(h, be.zero(h->dLmNear, h->numLights * sizeof(uint32_t)));
+  BE_CHECK(h, be.d2d(h->dLmBase, h->dXforms, ni * sizeof(InstXform)));
+  h->lmDynamicValid = false;
+  return rasterLightMap(h, h->dLmStatic, nullptr);
+}
+// after a refit: instances whose transform left the one of the static map go into the dynamic map at their new place
+int refitLightMaps(anerend_ddgi* h, bool verticesChanged) {
+  Backend& be = h->be;
+  if (h->lmRes == 0) return 0;
+  if (verticesChanged) return buildLightMaps(h);          // deformed meshes: every triangle may have moved
+  const uint32_t ni = (uint32_t)h->instances.size();
+  if (!h->dLmDynamic) BE_CHECK(h, be.alloc(&h->dLmDynamic, (size_t)h->lmLights * 6u * h->lmRes * h->lmRes));
+  LmMovedCtx mc{h->dXforms, h->dLmBase, h->dLmMoved};
+  DDGI_LAUNCH(be, k_lightmap_moved, lm_moved_body, ni, mc, 128);
+  h->lmDynamicValid = true;
+  return rasterLightMap(h, h->dLmDynamic, h->dLmMoved);
 }
 
 // flatten + LBVH + BVH8 collapse
@@ -313,6 +405,7 @@ int buildAccel(anerend_ddgi* h) {
     qlen = counters[2]; std::swap(qa, qb); ++depth;
     if (depth > 1000) break;
   }
+  { int rcl = buildLightMaps(h); if (rcl) { freeScratch(); return rcl; } }
   be.mark(5);
   int bounds[6];
   bool okc = be.d2h(bounds, h->dSceneBounds, sizeof(bounds));
@@ -332,6 +425,7 @@ int refitAccel(anerend_ddgi* h) {
   if (h->numTris == 0) return 0;
   BuildCtx c = buildCtx(h);
   c.sceneBounds = nullptr;
+  const bool verticesChanged = h->verticesDirty;
   if (h->verticesDirty) { c.shadeTris = h->dShadeTris; c.shadeUV = h->dShadeUV; h->verticesDirty = false; }   // deformed meshes: refresh the shading records too
   be.mark(4);
   DDGI_LAUNCH(be, k_inst_xform, inst_xform_body, (uint32_t)h->instances.size(), c, 128);
@@ -339,6 +433,7 @@ int refitAccel(anerend_ddgi* h) {
   DDGI_LAUNCH(be, k_refit_tris, refit_tris_body, h->numTris, c, 256);
   BE_CHECK(h, be.zero(h->dVisit, ((size_t)h->numTris + 1) * sizeof(uint32_t)));
   DDGI_LAUNCH(be, k_refit_nodes, refit_node_body, h->numNodes, c, 128);
+  { int rcl = refitLightMaps(h, verticesChanged); if (rcl) return rcl; }
   be.mark(5);
   BE_CHECK(h, be.check());
   h->timed[3] = true;
@@ -541,6 +636,8 @@ TraceCtx sceneTraceCtx(anerend_ddgi* h) {
   c.lightDir = mk3(h->ubo.light_dir[0], h->ubo.light_dir[1], h->ubo.light_dir[2]);
   c.tmin = h->p.t_min; c.tmax = h->p.t_max; c.sunIntensity = h->ubo.sun_intensity;
   c.uboFlags = h->ubo.flags; c.flags = h->p.flags;
+  c.lmRes = h->lmRes; c.lmStatic = h->dLmStatic; c.lmDynamic = h->lmDynamicValid ? h->dLmDynamic : nullptr; c.lmNear = h->dLmNear;
+  c.lmTris = h->dWtri; c.lmNumTris = h->numTris;
   return c;
 }
 
@@ -710,11 +807,11 @@ int DDGI_API(create)(const anerend_ddgi_params_t* params, anerend_ddgi_t** out) 
   const size_t texels = (size_t)h->W * h->H, rays = (size_t)h->nY * h->P * h->N;
   bool ok = be.alloc(&h->dAtlas, texels) && be.alloc(&h->dTemp, texels) && be.alloc(&h->dRayIrr, rays) &&
             be.alloc(&h->dDirs, (size_t)h->nY * h->N) && be.allocHostPinned(&h->hDirs, (size_t)h->nY * h->N) &&
-            be.alloc(&h->dSceneBounds, 6) && be.alloc(&h->dCounters, 4) && be.alloc(&h->dStats, 8) &&
+            be.alloc(&h->dSceneBounds, 6) && be.alloc(&h->dCounters, 4) && be.alloc(&h->dStats, 16) &&
             be.alloc(&h->dConvW, (size_t)h->nY * h->N * 64) && be.alloc(&h->dLayerMap, (size_t)h->nY) && be.allocHostPinned(&h->hLayerMap, (size_t)h->nY);
   if (ok && (q.flags & ANEREND_DDGI_FLAG_RAY_RECORDS)) ok = be.alloc(&h->dRecords, rays);
   if (ok && (q.flags & ANEREND_DDGI_FLAG_TEXEL_RECORDS)) ok = be.alloc(&h->dTexelRecords, texels);
-  if (ok) ok = be.zero(h->dStats, 8 * sizeof(unsigned long long)) && be.zero(h->dRayIrr, rays * sizeof(uint2));
+  if (ok) ok = be.zero(h->dStats, 16 * sizeof(unsigned long long)) && be.zero(h->dRayIrr, rays * sizeof(uint2));
   if (!ok) { destroyHandle(h); return ANEREND_DDGI_E_CUDA; }
   memset(h->hDirs, 0, (size_t)h->nY * h->N * sizeof(float4));      // rows of layers never traced travel with their neighbours
   h->fib.resize((size_t)h->N * 3);
@@ -1403,13 +1500,13 @@ int DDGI_API(get_timings)(anerend_ddgi_t* h, anerend_ddgi_timings_t* o) {
 }
 int DDGI_API(get_stats)(anerend_ddgi_t* h, anerend_ddgi_stats_t* o) {
   if (!h) return ANEREND_DDGI_E_INVALID;
-  unsigned long long s[8];
+  unsigned long long s[16];
   BE_CHECK(h, h->be.d2h(s, h->dStats, sizeof(s)));
   o->primary_rays = s[0]; o->primary_hits = s[1]; o->shadow_rays = s[2]; o->primary_nodes_visited = s[3]; o->primary_tris_tested = s[4];
-  o->shadow_nodes_visited = s[5]; o->shadow_tris_tested = s[6];
+  o->shadow_nodes_visited = s[5]; o->shadow_tris_tested = s[6]; o->shadow_rays_prefiltered = s[7]; o->shadow_rays_candidate = s[8];
   return 0;
 }
-int DDGI_API(reset_stats)(anerend_ddgi_t* h) { if (!h) return ANEREND_DDGI_E_INVALID; BE_CHECK(h, h->be.zero(h->dStats, 8 * sizeof(unsigned long long))); return 0; }
+int DDGI_API(reset_stats)(anerend_ddgi_t* h) { if (!h) return ANEREND_DDGI_E_INVALID; BE_CHECK(h, h->be.zero(h->dStats, 16 * sizeof(unsigned long long))); return 0; }
 
 // glm::rotate(mat4(1), radians(deg), axis) (IrradianceProbeRayTracingPass.cpp:133; glm/ext/matrix_transform.inl:18-46)
 int DDGI_API(make_rotation)(int32_t axisIdx, float deg, float out[16]) {

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
   r.ox = r.oy = r.oz = 0.0f; r.idx = r.idy = r.idz = 1.0f;
   bool active = false, exhausted = (total == 0u);
   uint32_t chunkNext = 0, chunkEnd = 0, staged = 0, stagedPos = 0;      // warp-uniform
-  uint32_t cn = 0, ct = 0, nRays = 0, nHits = 0;
+  uint32_t cn = 0, ct = 0, nRays = 0, nHits = 0, nCand = 0;
   for (;;) {
     // ---------------------------------------------------------------- refill idle lanes from the staged batch
     uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
@@ -179,7 +179,33 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
           chunkNext = base; chunkEnd = min(base + (uint32_t)FAST_CHUNK, total);
         }
         const uint32_t n = min(32u, chunkEnd - chunkNext);
+        uint32_t nStaged = n;
         __syncwarp();
+        if (ANY) {
+          // shadow rays: set-up, then the light map's shortcuts (ddgi_kernels.cuh "Light maps") 32 lanes wide — the far end of a
+          // point-light ray is cut back to where geometry can begin, and the texel's triangle (the nearest one to the light in the
+          // ray's direction) gets the exact test first: a hit ends the ray here, occluded, before it ever enters the hierarchy
+          bool keep = false; V3 pos = mk3(0.0f), dir = mk3(0.0f, 0.0f, 1.0f); float tmax = 0.0f; uint32_t ray = 0u, q = 0u;
+          if (lane < n) {
+            const uint32_t w = chunkNext + lane;
+            while (q + 1 < c.numQueues && sPrefix[q + 1] <= w) ++q;
+            ray = c.queues[(size_t)q * c.totalRays + (w - sPrefix[q])];
+            const float4 s0 = c.surf[(size_t)c.surfStride * ray];
+            pos = mk3(s0.x, s0.y, s0.z); dir = sunL; tmax = t.tmax; keep = true;
+            if (q > 0) {
+              const anerend_light_t* lt = &t.lights[q - 1];
+              const V3 lp = mk3(lt->world_pos[0], lt->world_pos[1], lt->world_pos[2]);
+              const V3 dv = lp - pos; const float dist = sqrtf(dot3(dv, dv)); dir = normalize3(lp - pos);
+              const LmEntry e = lightmap_lookup(t, q - 1, lp, pos);
+              tmax = lightmap_tmax(e, dist);
+              keep = !lightmap_candidate_occludes(t, e, pos, dir, t.tmin, dist);
+            }
+          }
+          const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
+          if (keep) ray_stage(&sRay[warp][__popc(km & ltMask)][0], pos, dir, tmax, ray, q);
+          nStaged = (uint32_t)__popc(km);
+          if (CNT) { nRays += (lane < n) ? 1u : 0u; nCand += (lane < n && !keep) ? 1u : 0u; }
+        } else
         if (lane < n) {                                             // ray set-up, one ray per lane
           const uint32_t w = chunkNext + lane;
           float4* dst = &sRay[warp][lane][0];
@@ -194,22 +220,10 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
             const V3 origin = mk3((float)(probe % t.nXZ), (float)layer, (float)(probe / t.nXZ)) * t.step + t.camOff;
             const float4 d4 = __ldg(&t.dirs[(size_t)layer * t.N + ray]);
             ray_stage(dst, origin, mk3(d4.x, d4.y, d4.z), t.tmax, w, 0u);
-          } else {
-            uint32_t q = 0; while (q + 1 < c.numQueues && sPrefix[q + 1] <= w) ++q;
-            const uint32_t ray = c.queues[(size_t)q * c.totalRays + (w - sPrefix[q])];
-            const float4 s0 = c.surf[(size_t)c.surfStride * ray];
-            const V3 pos = mk3(s0.x, s0.y, s0.z);
-            V3 dir = sunL; float tmax = t.tmax;
-            if (q > 0) {
-              const anerend_light_t* lt = &t.lights[q - 1];
-              const V3 lp = mk3(lt->world_pos[0], lt->world_pos[1], lt->world_pos[2]);
-              const V3 dv = lp - pos; tmax = sqrtf(dot3(dv, dv)); dir = normalize3(lp - pos);
-            }
-            ray_stage(dst, pos, dir, tmax, ray, q);
           }
         }
         __syncwarp();
-        chunkNext += n; staged = n; stagedPos = 0;
+        chunkNext += n; staged = nStaged; stagedPos = 0;
       }
       const uint32_t take = min((uint32_t)__popc(idle), staged), rank = (uint32_t)__popc(idle & ltMask);
       if (!active && rank < take) {
@@ -222,7 +236,7 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
         r.ng = make_uint2(0u, 0x80000000u); r.sp = 0; r.npend = 0;
         *myDir = b;                                                 // (d.xyz, tag)
         *myRes = make_float4(0.0f, 0.0f, 0.0f, ANY ? cc.w : __uint_as_float(DDGI_MISS));
-        if (CNT) ++nRays;
+        if (CNT && !ANY) ++nRays;
         if (!ANY && t.numNodes == 0u) c.hits[__float_as_uint(b.w)] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(DDGI_MISS));
         else active = true;
       }
@@ -291,11 +305,13 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
   }
   if (CNT && t.stats) {
     for (int o = 16; o; o >>= 1) { cn += __shfl_xor_sync(0xFFFFFFFFu, cn, o); ct += __shfl_xor_sync(0xFFFFFFFFu, ct, o);
-                                   nRays += __shfl_xor_sync(0xFFFFFFFFu, nRays, o); nHits += __shfl_xor_sync(0xFFFFFFFFu, nHits, o); }
+                                   nRays += __shfl_xor_sync(0xFFFFFFFFu, nRays, o); nHits += __shfl_xor_sync(0xFFFFFFFFu, nHits, o);
+                                   nCand += __shfl_xor_sync(0xFFFFFFFFu, nCand, o); }
     if (lane == 0) {
       if (!ANY) { atomicAdd(&t.stats[0], (unsigned long long)nRays); atomicAdd(&t.stats[1], (unsigned long long)nHits);
                   atomicAdd(&t.stats[3], (unsigned long long)cn); atomicAdd(&t.stats[4], (unsigned long long)ct); }
-      else { atomicAdd(&t.stats[2], (unsigned long long)nRays); atomicAdd(&t.stats[5], (unsigned long long)cn); atomicAdd(&t.stats[6], (unsigned long long)ct); }
+      else { atomicAdd(&t.stats[2], (unsigned long long)nRays); atomicAdd(&t.stats[5], (unsigned long long)cn); atomicAdd(&t.stats[6], (unsigned long long)ct);
+             if (nCand) atomicAdd(&t.stats[8], (unsigned long long)nCand); }
     }
   }
 }
@@ -395,7 +411,7 @@ __global__ void __launch_bounds__(PREP_BLOCK, 2048 / PREP_BLOCK) k_shade_prep(co
   }
   // Which queues does this ray enter?  bit q: shadow ray towards light q (0 = sun, rchit:45-66: every hit; point
   // lights, extension E1: only where the light can contribute); bit 32: the compacted hit list k_shade runs over.
-  uint32_t needMask = isHit ? 1u : 0u;
+  uint32_t needMask = isHit ? 1u : 0u, preLit = 0u;
   if (isHit && (t.flags & ANEREND_DDGI_FLAG_SKIP_DEAD_SHADOW_RAYS) && !(dot3(normal, normalize3(-t.lightDir)) > 0.0f)) needMask = 0u;
   if (isHit && (t.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS)) {
     for (uint32_t li = 0; li < t.numLights; ++li) {
@@ -412,9 +428,14 @@ __global__ void __launch_bounds__(PREP_BLOCK, 2048 / PREP_BLOCK) k_shade_prep(co
           bool facing;
           if (d2 > 1e-30f && fabsf(sgn) > 1e-5f * mag) facing = sgn > 0.0f;
           else { const V3 L = normalize3(lp - pos); facing = dot3(normal, L) > 0.0f; }
-          if (facing) needMask |= 1u << (1u + li);
+          // the light map answers the rays that certainly reach the light (ddgi_kernels.cuh "Light maps"): lit without a traversal
+          if (facing) { if (lightmap_unoccluded(lightmap_lookup(t, li, lp, pos), dist, t.tmin)) preLit |= 1u << (1u + li); else needMask |= 1u << (1u + li); }
         }
       }
+    }
+    if (preLit) {
+      c.lit[idx] = preLit;
+      if ((t.flags & ANEREND_DDGI_FLAG_COUNTERS) && t.stats) atomicAdd(&t.stats[7], (unsigned long long)__popc(preLit));
     }
   }
   // block-aggregated append: one atomic per queue per block (a per-warp atomic on nine neighbouring counters was the

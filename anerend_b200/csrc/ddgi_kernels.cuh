@@ -606,7 +606,8 @@ struct TraceCtx {
   float tmin, tmax, sunIntensity;
   uint32_t uboFlags, flags;
   // light maps (below): conservative distance maps around the point lights that answer "certainly unoccluded" shadow rays
-  const int* lmStatic; const int* lmDynamic; const uint32_t* lmNear; uint32_t lmRes;      // lmRes = 0: none
+  const unsigned long long* lmStatic; const unsigned long long* lmDynamic; const uint32_t* lmNear; uint32_t lmRes;      // lmRes = 0: none
+  const float4* lmTris; uint32_t lmNumTris;      // world triangles by global id (the candidates the map entries name)
 };
 
 // Row stripe (multi-GPU sharding inside the layers): launched probe `pl` of a layer -> probe index in the layer.  A handle
@@ -617,24 +618,30 @@ HD int stripe_probe(int pl, int nXZ, int rowOffset, int rowStride) { return ((pl
 // Light maps: a pre-filter for the point-light shadow rays of extension E1 (rchit:45-66 composed with calcLight's point branch).
 //
 // Around every enabled point light a cube map (6 faces x R x R) holds, per texel, a LOWER BOUND of the distance from the light
-// to any triangle that reaches into the texel's pyramid of directions.  A shadow ray pos -> light runs along ONE direction from
-// the light and covers the distances (0, dist - tMin) from it; if that interval ends before the bound of the direction's texel,
-// no triangle can intersect the ray, so the ray is unoccluded and is never traced.  Everything else — rays that are occluded,
-// rays that graze a surface, texels with depth complexity in front of the hit — goes through the BVH as before.  The exact
-// Moeller-Trumbore test is never replaced, only skipped where its answer is known, so lit masks and radiance stay bit-identical
-// to the oracle's; the margins (LM_DELTA on the footprints, rho on the plane bound, the slack in lightmap_unoccluded) are orders of
-// magnitude above fp32 rounding of either side.  At C3 (R = 512) 81 % of the unoccluded point-light rays — the ones that walk the
-// most nodes, since nothing ends them early — are answered by one 4-byte read.
+// to any triangle that reaches into the texel's pyramid of directions, and the id of the triangle that set it.  A shadow ray
+// pos -> light runs along ONE direction from the light and covers the distances (0, dist - tMin) from it:
+//   * if that interval ends before the bound of the direction's texel, no triangle can intersect the ray: it is unoccluded and is
+//     never traced (lightmap_unoccluded);
+//   * otherwise the texel's triangle — the nearest one to the light in that direction, what a shadow map would hold — is the likely
+//     occluder: the ray is put through the exact Moeller-Trumbore test against it first, and a hit ends it (any-hit semantics: WHICH
+//     triangle occludes never reaches the result);
+//   * the ray's far end is cut back to where geometry can begin (dist - bound), which only prunes box tests.
+// Everything else — rays that graze a surface, depth complexity in front of the hit — goes through the BVH as before.  The exact
+// triangle test is never replaced, only skipped where its answer is known, so lit masks and radiance stay bit-identical to the
+// oracle's; the margins (LM_DELTA on the footprints, rho on the plane bound, the slack in lightmap_unoccluded) are orders of
+// magnitude above fp32 rounding of either side.  At C3 (R = 512) 81 % of the unoccluded point-light rays are answered by one read.
 //
 //   face f = 2 * axis + (d[axis] < 0), axis = major axis of d = p - lightPos; in-face coordinates u = d[axis+1] / |d[axis]|,
-//   v = d[axis+2] / |d[axis]| in [-1, 1]; texel X = floor((u + 1) / 2 * R).
+//   v = d[axis+2] / |d[axis]| in [-1, 1]; texel X = floor((u + 1) / 2 * R).  Entry = bound (fp32 bits) << 32 | triangle id, kept
+//   minimal by 64-bit atomicMin.
 //   static map: all triangles at build_accel time.  dynamic map: the triangles of instances that moved since (refit), rasterised
-//   again at every refit; the bound is the minimum of both (a stale static entry of a mover is only a lower bound that is too low).
+//   again at every refit; the entry is the minimum of both (a stale static entry of a mover is only a bound that is too low, and a
+//   candidate that misses).
 // ----------------------------------------------------------------------------------------------------
 #define LM_EPS_W 1e-4f          // points nearer than this to a face's apex plane are not projected (see LM_NEAR)
 #define LM_NEAR 0.02f           // a triangle this close to a light disables that light's map (lmNear): its projection is unbounded
 #define LM_DELTA 1e-4f          // footprint growth in face coordinates (texel size at R = 512: 3.9e-3)
-#define LM_FAR_BITS 0x7F7F7F7F  // "nothing here" (3.39e38), the byte pattern of the clearing memset
+#define LM_FAR_BITS 0x7F7F7F7Fu // "nothing here" (3.39e38; as a triangle id: none), the byte pattern of the clearing memset
 struct LmTri { V3 r[3]; V3 n; float h, daabb; bool skinny, nearLight; };
 HD float comp3(V3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
 // vertices relative to the light -> plane, box distance; false: cannot occlude a ray of this light (beyond its range, or degenerate)
@@ -691,29 +698,48 @@ HD float lm_texel_bound(V3 n, float h, float daabb, bool skinny, int face, int X
   return (skinny ? daabb : fmaxf(plane, daabb)) * 0.999996f;
 }
 HD float lm_rho(uint32_t R) { return 1.4143f / (float)R * 1.02f + 2e-5f; }
-// Is the shadow ray pos -> light (tMin, dist) certainly unoccluded?  `dist` = length(lightPos - pos) as the hit shader computes it.
-HD bool lightmap_unoccluded(const TraceCtx& c, uint32_t li, V3 lp, V3 pos, float dist) {
-  if (c.lmRes == 0u || c.lmNear[li] != 0u) return false;
+// The entry of the texel the direction light -> pos falls in.
+struct LmEntry { float bound; uint32_t cand; };
+HD LmEntry lightmap_lookup(const TraceCtx& c, uint32_t li, V3 lp, V3 pos) {
+  LmEntry e; e.bound = 0.0f; e.cand = LM_FAR_BITS;
+  if (c.lmRes == 0u || c.lmNear[li] != 0u) return e;
   const V3 d = pos - lp;
   const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
   int face; float w, b, cc;
   if (ax >= ay && ax >= az) { face = d.x < 0.0f ? 1 : 0; w = ax; b = d.y; cc = d.z; }
   else if (ay >= az) { face = d.y < 0.0f ? 3 : 2; w = ay; b = d.z; cc = d.x; }
   else { face = d.z < 0.0f ? 5 : 4; w = az; b = d.x; cc = d.y; }
-  if (!(w > 0.0f)) return false;
+  if (!(w > 0.0f)) return e;
+#ifdef __CUDA_ARCH__
+  const float iw = __fdividef(1.0f, w);      // texel choice: any rounding far below LM_DELTA will do
+#else
+  const float iw = 1.0f / w;
+#endif
   const float fr = (float)c.lmRes, top = (float)(c.lmRes - 1u);
-  const int X = (int)fminf(fmaxf(floorf((b / w + 1.0f) * 0.5f * fr), 0.0f), top), Y = (int)fminf(fmaxf(floorf((cc / w + 1.0f) * 0.5f * fr), 0.0f), top);
+  const int X = (int)fminf(fmaxf(floorf((b * iw + 1.0f) * 0.5f * fr), 0.0f), top), Y = (int)fminf(fmaxf(floorf((cc * iw + 1.0f) * 0.5f * fr), 0.0f), top);
   const size_t o = (((size_t)li * 6u + (size_t)face) * c.lmRes + (size_t)Y) * c.lmRes + (size_t)X;
-  int bits = c.lmStatic[o];
-  if (c.lmDynamic) { const int db = c.lmDynamic[o]; bits = db < bits ? db : bits; }      // positive floats order like their bit patterns
-  return dist - c.tmin < u2f((uint32_t)bits) * 0.9999f - 1e-3f;
+  unsigned long long v = c.lmStatic[o];
+  if (c.lmDynamic) { const unsigned long long dv = c.lmDynamic[o]; v = dv < v ? dv : v; }      // positive floats order like their bit patterns
+  e.bound = u2f((uint32_t)(v >> 32)); e.cand = (uint32_t)v;
+  return e;
+}
+// Is the shadow ray pos -> light (tMin, dist) certainly unoccluded?  `dist` = length(lightPos - pos) as the hit shader computes it.
+HD bool lightmap_unoccluded(const LmEntry& e, float dist, float tmin) { return dist - tmin < e.bound * 0.9999f - 1e-3f; }
+// no triangle lies nearer to the light than the bound: intersections have t <= dist - bound
+HD float lightmap_tmax(const LmEntry& e, float dist) { return fminf(dist, dist - e.bound * 0.9999f + 1e-3f); }
+// the exact test against the texel's triangle (same operands as the traversal would hand it)
+HD bool lightmap_candidate_occludes(const TraceCtx& c, const LmEntry& e, V3 pos, V3 dir, float tmin, float dist) {
+  if (e.cand >= c.lmNumTris) return false;
+  const float4 a = c.lmTris[3 * (size_t)e.cand], b = c.lmTris[3 * (size_t)e.cand + 1], cc = c.lmTris[3 * (size_t)e.cand + 2];
+  float t, u, v;
+  return tri_intersect(pos, dir, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), mk3(b.z, b.w, cc.x), tmin, dist, t, u, v);
 }
 // Rasterisation, one (triangle, light) pair: every face, every texel of the footprint.  The CUDA kernel (k_lightmap_raster,
 // ddgi_api.cu) runs the same setup per thread and spreads the texel loops over the warp.
 struct LmBuildCtx {
   const float4* wtri; const uint32_t* triInstance; const uint32_t* moved;      // moved: per instance, or null = every triangle
   const anerend_light_t* lights; uint32_t numTris, numLights, R; float rho;
-  int* depth; uint32_t* nearFlags;
+  unsigned long long* depth; uint32_t* nearFlags;
 };
 HD bool lm_pair_setup(const LmBuildCtx& c, uint32_t t, uint32_t li, LmTri& tri) {
   if (c.moved && !c.moved[c.triInstance[t]]) return false;
@@ -732,9 +758,9 @@ HD void lightmap_raster_body(uint32_t i, const LmBuildCtx& c) {
   for (int face = 0; face < 6; ++face) {
     int x0, x1, y0, y1;
     if (!lm_face_rect(tri, face, c.R, x0, x1, y0, y1)) continue;
-    int* dm = c.depth + ((size_t)li * 6u + (size_t)face) * c.R * c.R;
+    unsigned long long* dm = c.depth + ((size_t)li * 6u + (size_t)face) * c.R * c.R;
     for (int y = y0; y <= y1; ++y) for (int x = x0; x <= x1; ++x)
-      atomMin(dm + (size_t)y * c.R + x, (int)f2u(lm_texel_bound(tri.n, tri.h, tri.daabb, tri.skinny, face, x, y, c.R, c.rho)));
+      atomMin64(dm + (size_t)y * c.R + x, ((unsigned long long)f2u(lm_texel_bound(tri.n, tri.h, tri.daabb, tri.skinny, face, x, y, c.R, c.rho)) << 32) | t);
   }
 }
 // instances whose transform differs from the one the static map was rasterised with
@@ -1028,7 +1054,7 @@ HD void shadow_rt_body(uint32_t i, const ShadowRtCtx& c) {
 // rchit main for one hit (irradiance_probe_update.rchit:24-111; SPECULAR: mirror_reflections.rchit:24-118, which differs in the
 // normal transform and in the flag that gates the indirect term).  origin = gl_WorldRayOriginEXT.
 template <bool CNT, bool SPECULAR>
-HD V3 shade_hit_simple(const TraceCtx& c, const Hit& hit, V3 origin, uint32_t& lit, uint32_t& nShadow, uint32_t* cn, uint32_t* ct, V3& hitPos) {
+HD V3 shade_hit_simple(const TraceCtx& c, const Hit& hit, V3 origin, uint32_t& lit, uint32_t& nShadow, uint32_t& nPre, uint32_t& nCand, uint32_t* cn, uint32_t* ct, V3& hitPos) {
   const uint32_t ii = c.triInstance[hit.prim];
   const DInstance in = c.instances[ii];
   const InstXform& xf = c.xforms[ii];
@@ -1078,9 +1104,12 @@ HD V3 shade_hit_simple(const TraceCtx& c, const Hit& hit, V3 origin, uint32_t& l
       if (!(dist < range)) continue;
       const V3 L = normalize3(lp - pos);
       if (!(dot3(normal, L) > 0.0f)) continue;
-      if (!lightmap_unoccluded(c, li, lp, pos, dist)) {       // else: answered by the light map, not traced
+      const LmEntry lme = lightmap_lookup(c, li, lp, pos);
+      if (lightmap_unoccluded(lme, dist, c.tmin)) ++nPre;      // answered by the light map, not traced
+      else {
         ++nShadow;
-        if (traverse<true, CNT>(c.nodes, c.bvhTris, c.numNodes, pos, L, c.tmin, dist, sh, cn[1], ct[1])) continue;
+        if (lightmap_candidate_occludes(c, lme, pos, L, c.tmin, dist)) { ++nCand; continue; }
+        if (traverse<true, CNT>(c.nodes, c.bvhTris, c.numNodes, pos, L, c.tmin, lightmap_tmax(lme, dist), sh, cn[1], ct[1])) continue;
       }
       lit |= 1u << (1u + li);
       const float dd = fminf(dist, range);
@@ -1117,11 +1146,11 @@ HD void specular_gi_body(uint32_t i, const SpecularCtx& c) {
   const V3 vv = normalize3(pos - c.cameraPos);
   const float dn = dot3(normal, vv);
   const V3 dir = vv - (2.0f * dn) * normal;                                                      // reflect(v, normal)
-  Hit hit; uint32_t cn[2] = {0, 0}, ct[2] = {0, 0}, lit = 0, nShadow = 0;
+  Hit hit; uint32_t cn[2] = {0, 0}, ct[2] = {0, 0}, lit = 0, nShadow = 0, nPre = 0, nCand = 0;
   V3 rad; float dist;
   if (traverse<false, false>(c.t.nodes, c.t.bvhTris, c.t.numNodes, pos, dir, 0.1f, 50.0f, hit, cn[0], ct[0])) {
     V3 hp;
-    rad = shade_hit_simple<false, true>(c.t, hit, pos, lit, nShadow, cn, ct, hp);
+    rad = shade_hit_simple<false, true>(c.t, hit, pos, lit, nShadow, nPre, nCand, cn, ct, hp);
     const V3 dd = hp - pos; dist = sqrtf(dot3(dd, dd));                                          // distance(pos, gl_WorldRayOriginEXT)
   } else { rad = c.t.sky; dist = 1e6f; }                                                         // mirror_reflections.rmiss
   c.out[i] = make_uint2((uint32_t)f2h(rad.x) | ((uint32_t)f2h(rad.y) << 16), (uint32_t)f2h(rad.z) | ((uint32_t)f2h(dist) << 16));
@@ -1139,12 +1168,12 @@ HD void trace_ray_body(uint32_t idx, const TraceCtx& c) {
   const V3 origin = mk3((float)probeX, (float)layer, (float)probeZ) * c.step + c.camOff;      // rgen:83
   const float4 d4 = c.dirs[(size_t)layer * c.N + ray];
   const V3 d = mk3(d4.x, d4.y, d4.z);
-  uint32_t cn[2] = {0, 0}, ct[2] = {0, 0}, nShadow = 0, lit = 0;
+  uint32_t cn[2] = {0, 0}, ct[2] = {0, 0}, nShadow = 0, nPre = 0, nCand = 0, lit = 0;
   Hit hit;
   V3 rad;
   if (traverse<false, CNT>(c.nodes, c.bvhTris, c.numNodes, origin, d, c.tmin, c.tmax, hit, cn[0], ct[0])) {
     V3 hitPos;
-    rad = shade_hit_simple<CNT, false>(c, hit, origin, lit, nShadow, cn, ct, hitPos);
+    rad = shade_hit_simple<CNT, false>(c, hit, origin, lit, nShadow, nPre, nCand, cn, ct, hitPos);
   } else {
     rad = c.sky;                                                                                      // rmiss:20
   }
@@ -1159,6 +1188,8 @@ HD void trace_ray_body(uint32_t idx, const TraceCtx& c) {
   if (CNT && c.stats) {
     atomAdd64(&c.stats[0], 1ull); atomAdd64(&c.stats[1], hit.prim != DDGI_MISS ? 1ull : 0ull); atomAdd64(&c.stats[2], nShadow);
     atomAdd64(&c.stats[3], cn[0]); atomAdd64(&c.stats[4], ct[0]); atomAdd64(&c.stats[5], cn[1]); atomAdd64(&c.stats[6], ct[1]);
+    if (nPre) atomAdd64(&c.stats[7], nPre);
+    if (nCand) atomAdd64(&c.stats[8], nCand);
   }
 }
 

@@ -93,6 +93,13 @@ HD void atomMin(int* p, int v) {
   if (v < *p) *p = v;
 #endif
 }
+HD void atomMin64(unsigned long long* p, unsigned long long v) {
+#ifdef __CUDA_ARCH__
+  if (v < *p) atomicMin(p, v);
+#else
+  if (v < *p) *p = v;
+#endif
+}
 HD void atomMax(int* p, int v) {
 #ifdef __CUDA_ARCH__
   atomicMax(p, v);

@@ -46,6 +46,7 @@ FLAG_COUNTERS = 1 << 3
 FLAG_SIMPLE_KERNELS = 1 << 4
 FLAG_FAST_MATH = 1 << 5
 FLAG_SKIP_DEAD_SHADOW_RAYS = 1 << 6
+FLAG_NO_LIGHT_MAPS = 1 << 7
 
 MISS = 0xFFFFFFFF
 

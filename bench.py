@@ -629,7 +629,11 @@ def main():
                     "nodes_per_shadow_ray": stats["shadow_nodes_visited"] / max(1, stats["shadow_rays"]),
                     "tris_per_shadow_ray": stats["shadow_tris_tested"] / max(1, stats["shadow_rays"]),
                     "shadow_rays_per_primary": stats["shadow_rays"] / max(1, stats["primary_rays"]),
-                    "hit_fraction": stats["primary_hits"] / max(1, stats["primary_rays"])}
+                    "hit_fraction": stats["primary_hits"] / max(1, stats["primary_rays"]),
+                    # light maps (csrc/ddgi_kernels.cuh): shadow rays answered without a traversal / ended by the candidate triangle
+                    "shadow_rays_needed": stats["shadow_rays"] + stats["shadow_rays_prefiltered"],
+                    "shadow_rays_prefiltered": stats["shadow_rays_prefiltered"], "shadow_rays_traced": stats["shadow_rays"],
+                    "shadow_rays_ended_by_candidate": stats["shadow_rays_candidate"]}
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             layers = list(range(ny)) if name != "c5" else list(range(0, ny, 8))

@@ -45,6 +45,9 @@ extern "C" {
 #define ANEREND_DDGI_FLAG_SKIP_DEAD_SHADOW_RAYS (1u << 6) /* do not trace the sun shadow ray (rchit:45-66) where dot(N, L) <= 0:
                                                      calcLight multiplies by max(N.L, 0) = 0 there (pbr_light.glsl:161), so the
                                                      radiance is unchanged; lit_mask bit 0 reads 0 and shadow_rays counts traced rays */
+#define ANEREND_DDGI_FLAG_NO_LIGHT_MAPS (1u << 7) /* trace every point-light shadow ray: do not build the conservative distance maps
+                                                     around the lights that answer "certainly unoccluded" rays without a traversal
+                                                     (same lit masks either way; A/B measurements and tests)                        */
 #define ANEREND_DDGI_FLAG_FAST_MATH     (1u << 5) /* radiance + convolution with contracted / approximate fp32 (<= 1e-4 relative per
                                                      update instead of bit-identical to the oracle's defined arithmetic); hit ids,
                                                      shadow-ray results and hit positions are unaffected                            */
@@ -97,6 +100,8 @@ typedef struct anerend_ddgi_stats {
   uint64_t primary_tris_tested;
   uint64_t shadow_nodes_visited;
   uint64_t shadow_tris_tested;
+  uint64_t shadow_rays_prefiltered; /* shadow rays answered by the light maps instead of a traversal (not in shadow_rays) */
+  uint64_t shadow_rays_candidate;   /* of shadow_rays: ended by the exact test against the light map's candidate triangle */
 } anerend_ddgi_stats_t;
 
 typedef struct anerend_ddgi_bvh_info {
