@@ -46,6 +46,7 @@ DDGI_KERNEL(k_specular_gi, specular_gi_body, SpecularCtx)
 DDGI_KERNEL(k_atlas_clear, clear_body, ClearCtx)
 DDGI_KERNEL(k_lightmap_raster_serial, lightmap_raster_body, LmBuildCtx)
 DDGI_KERNEL(k_lightmap_moved, lm_moved_body, LmMovedCtx)
+DDGI_KERNEL(k_sunmap_raster_serial, sunmap_raster_body, SunMapCtx)
 
 // ------------------------------------------------------------------------------------------------ handle
 struct anerend_ddgi {
@@ -108,6 +109,8 @@ struct anerend_ddgi {
   // light maps (ddgi_kernels.cuh): static + dynamic distance cube maps per point light, the transforms the static map was made with
   unsigned long long* dLmStatic = nullptr; unsigned long long* dLmDynamic = nullptr; uint32_t* dLmNear = nullptr; InstXform* dLmBase = nullptr; uint32_t* dLmMoved = nullptr;
   uint32_t lmRes = 0, lmLights = 0; bool lmDynamicValid = false; float lmMs = 0.0f;
+  unsigned long long* dSmStatic = nullptr; unsigned long long* dSmDynamic = nullptr; uint32_t smRes = 0; bool smValid = false, smDynamicValid = false, lmMovedValid = false;
+  float smDir[3] = {0, 0, 0}; SunMapCtx sm{};      // the lightDir the sun's map was made for, its frame
   size_t fastRays = 0; uint32_t fastQueues = 0; int gridPrimary[2] = {0, 0}, gridShadow[2] = {0, 0}; uint32_t tune[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int sms = 0;
 
   int rowOffset = 0, rowStride = 1, Pl = 0;                // row stripe (set_row_stripe): probes launched per layer = Pl
@@ -204,6 +207,7 @@ void freeAccel(anerend_ddgi* h) {
   be.free(h->dShadeTris); h->dShadeTris = nullptr; be.free(h->dShadeUV); h->dShadeUV = nullptr;
   be.free(h->dLmStatic); be.free(h->dLmDynamic); be.free(h->dLmNear); be.free(h->dLmBase); be.free(h->dLmMoved);
   h->dLmStatic = nullptr; h->dLmDynamic = nullptr; h->dLmNear = nullptr; h->dLmBase = nullptr; h->dLmMoved = nullptr; h->lmRes = 0; h->lmLights = 0; h->lmDynamicValid = false;
+  be.free(h->dSmStatic); be.free(h->dSmDynamic); h->dSmStatic = nullptr; h->dSmDynamic = nullptr; h->smRes = 0; h->smValid = false; h->smDynamicValid = false; h->lmMovedValid = false;
   h->dInstances = nullptr; h->dXforms = nullptr; h->dTriInstance = nullptr; h->dWtri = nullptr; h->dTriLo = nullptr; h->dTriHi = nullptr;
   h->dNodes = nullptr; h->dBvhTris = nullptr; h->dNodeParent = nullptr; h->dNodeLo = nullptr; h->dNodeHi = nullptr; h->dNodePending = nullptr; h->dVisit = nullptr;
   h->haveAccel = false; h->numTris = 0; h->numNodes = 0;
@@ -227,36 +231,78 @@ int clearAtlas(anerend_ddgi* h) {
 #ifndef DDGI_HOST_EMU
 // One thread per (triangle, light of blockIdx.y): the setup of lightmap_raster_body per thread, the texel loops of the
 // footprints spread over the warp (a footprint is a few dozen texels at R = 512, but a triangle next to a light covers a
-// whole face: per-thread loops would leave one lane running for milliseconds).
+// whole face: per-thread loops would leave one lane running for milliseconds).  The lane whose footprint is being filled
+// hands its parameters to the warp through shared memory.
+struct LmItem { int x0, x1, y0, y1; V3 n; float h, daabb; uint32_t skinny, tid; LmEdges ed; };
 __global__ void __launch_bounds__(256) k_lightmap_raster(const LmBuildCtx c) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, li = blockIdx.y, lane = threadIdx.x & 31u;
+  __shared__ LmItem sItem[8];
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, li = blockIdx.y, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   LmTri tri;
   tri.n = mk3(0.0f); tri.h = 0.0f; tri.daabb = 0.0f; tri.skinny = false; tri.nearLight = false;
   const bool ok = t < c.numTris && lm_pair_setup(c, t, li, tri);
   if (ok && tri.nearLight) c.nearFlags[li] = 1u;
   for (int face = 0; face < 6; ++face) {
-    int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
-    const bool reach = ok && lm_face_rect(tri, face, c.R, x0, x1, y0, y1);
+    LmItem it; it.x0 = 0; it.x1 = -1; it.y0 = 0; it.y1 = -1; it.ed.use = false;
+    const bool reach = ok && lm_face_rect(tri, face, c.R, it.x0, it.x1, it.y0, it.y1, it.ed);
     unsigned long long* dm = c.depth + ((size_t)li * 6u + (size_t)face) * c.R * c.R;
     for (uint32_t m = __ballot_sync(0xFFFFFFFFu, reach); m != 0u; m &= m - 1u) {
-      const int src = __ffs((int)m) - 1;
-      const int bx0 = __shfl_sync(0xFFFFFFFFu, x0, src), bx1 = __shfl_sync(0xFFFFFFFFu, x1, src);
-      const int by0 = __shfl_sync(0xFFFFFFFFu, y0, src), by1 = __shfl_sync(0xFFFFFFFFu, y1, src);
-      const V3 n = mk3(__shfl_sync(0xFFFFFFFFu, tri.n.x, src), __shfl_sync(0xFFFFFFFFu, tri.n.y, src), __shfl_sync(0xFFFFFFFFu, tri.n.z, src));
-      const float hh = __shfl_sync(0xFFFFFFFFu, tri.h, src), da = __shfl_sync(0xFFFFFFFFu, tri.daabb, src);
-      const bool sk = __shfl_sync(0xFFFFFFFFu, tri.skinny ? 1 : 0, src) != 0;
-      const uint32_t tid = __shfl_sync(0xFFFFFFFFu, t, src);
-      const int wdt = bx1 - bx0 + 1, cnt = wdt * (by1 - by0 + 1);
+      const uint32_t src = (uint32_t)__ffs((int)m) - 1u;
+      __syncwarp();
+      if (lane == src) { it.n = tri.n; it.h = tri.h; it.daabb = tri.daabb; it.skinny = tri.skinny ? 1u : 0u; it.tid = t; sItem[warp] = it; }
+      __syncwarp();
+      const LmItem& w = sItem[warp];
+      const int bx0 = w.x0, by0 = w.y0, wdt = w.x1 - w.x0 + 1, cnt = wdt * (w.y1 - w.y0 + 1);
+      const V3 n = w.n; const float hh = w.h, da = w.daabb; const bool sk = w.skinny != 0u; const uint32_t tid = w.tid;
+      const LmEdges ed = w.ed;
       for (int k = (int)lane; k < cnt; k += 32) {
-        const int x = bx0 + k % wdt, y = by0 + k / wdt;
-        atomMin64(dm + (size_t)y * c.R + x, ((unsigned long long)__float_as_uint(lm_texel_bound(n, hh, da, sk, face, x, y, c.R, c.rho)) << 32) | tid);
+        const int lx = k % wdt, ly = k / wdt;
+        if (lm_edges_touch(ed, lx, ly))
+          atomMin64(dm + (size_t)(by0 + ly) * c.R + (bx0 + lx), ((unsigned long long)__float_as_uint(lm_texel_bound(n, hh, da, sk, face, bx0 + lx, by0 + ly, c.R, c.rho)) << 32) | tid);
       }
     }
   }
 }
+struct SmItem { int x0, x1, y0, y1; float smax, ga, gb, pa0, pb0, ps0; uint32_t flat, tid; LmEdges ed; };
+__global__ void __launch_bounds__(256) k_sunmap_raster(const SunMapCtx c) {
+  __shared__ SmItem sItem[8];
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  SmTri tri; SmItem it; it.x0 = 0; it.x1 = -1; it.y0 = 0; it.y1 = -1; it.ed.use = false;
+  tri.smax = 0.0f; tri.ga = 0.0f; tri.gb = 0.0f; tri.flat = false; tri.pa[0] = 0.0f; tri.pb[0] = 0.0f; tri.ps[0] = 0.0f;
+  const bool reach = t < c.numTris && sm_tri_setup(c, t, tri, it.x0, it.x1, it.y0, it.y1, it.ed);
+  for (uint32_t m = __ballot_sync(0xFFFFFFFFu, reach); m != 0u; m &= m - 1u) {
+    const uint32_t src = (uint32_t)__ffs((int)m) - 1u;
+    __syncwarp();
+    if (lane == src) { it.smax = tri.smax; it.ga = tri.ga; it.gb = tri.gb; it.pa0 = tri.pa[0]; it.pb0 = tri.pb[0]; it.ps0 = tri.ps[0]; it.flat = tri.flat ? 1u : 0u; it.tid = t; sItem[warp] = it; }
+    __syncwarp();
+    const SmItem& w = sItem[warp];
+    const int bx0 = w.x0, by0 = w.y0, wdt = w.x1 - w.x0 + 1, cnt = wdt * (w.y1 - w.y0 + 1);
+    const float smax = w.smax, ga = w.ga, gb = w.gb, pa0 = w.pa0, pb0 = w.pb0, ps0 = w.ps0; const bool flat = w.flat != 0u; const uint32_t tid = w.tid;
+    const LmEdges ed = w.ed;
+    for (int k = (int)lane; k < cnt; k += 32) {
+      const int lx = k % wdt, ly = k / wdt;
+      if (lm_edges_touch(ed, lx, ly))
+        atomMax64(c.height + (size_t)(by0 + ly) * c.R + (bx0 + lx), sm_pack(sm_texel_bound(smax, ga, gb, pa0, pb0, ps0, flat, bx0 + lx, by0 + ly, c.orgA, c.orgB, c.cell), c.base, tid));
+    }
+  }
+}
 #endif
+bool mapsEnabled(const anerend_ddgi* h) { return !(h->p.flags & ANEREND_DDGI_FLAG_NO_LIGHT_MAPS) && h->numTris != 0; }
+int rasterSunMap(anerend_ddgi* h, unsigned long long* target, const uint32_t* moved) {
+  Backend& be = h->be;
+  BE_CHECK(h, be.zero(target, (size_t)h->smRes * h->smRes * sizeof(unsigned long long)));
+  SunMapCtx c = h->sm;
+  c.wtri = h->dWtri; c.triInstance = h->dTriInstance; c.moved = moved; c.numTris = h->numTris; c.R = h->smRes; c.height = target;
+#ifndef DDGI_HOST_EMU
+  k_sunmap_raster<<<(h->numTris + 255u) / 256u, 256, 0, be.stream>>>(c);
+  ++be.launches;
+#else
+  DDGI_LAUNCH(be, k_sunmap_raster_serial, sunmap_raster_body, h->numTris, c, 256);
+#endif
+  BE_CHECK(h, be.check());
+  return 0;
+}
 uint32_t lightMapResolution(const anerend_ddgi* h) {
-  if (!(h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) || (h->p.flags & ANEREND_DDGI_FLAG_NO_LIGHT_MAPS) || h->numLights == 0 || h->numTris == 0) return 0;
+  if (!(h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) || !mapsEnabled(h) || h->numLights == 0) return 0;
   uint32_t r = 512;
   if (const char* e = getenv("DDGI_LM_RES")) r = (uint32_t)atoi(e);          // sweeps only; 0 disables the maps
   return r > 4096u ? 4096u : r;
@@ -281,32 +327,84 @@ int rasterLightMap(anerend_ddgi* h, unsigned long long* target, const uint32_t* 
 }
 int buildLightMaps(anerend_ddgi* h) {
   Backend& be = h->be;
+  h->lmDynamicValid = false; h->smDynamicValid = false; h->lmMovedValid = false;
+  h->smValid = false;                                     // the sun's map is made at the next trace, for the lightDir of that frame (ensureSunMap)
+  if (!mapsEnabled(h)) { h->lmRes = 0; return 0; }
+  const size_t ni = h->instances.size();
+  if (!h->dLmBase) { BE_CHECK(h, be.alloc(&h->dLmBase, ni)); BE_CHECK(h, be.alloc(&h->dLmMoved, ni)); }
+  BE_CHECK(h, be.d2d(h->dLmBase, h->dXforms, ni * sizeof(InstXform)));      // the pose both static maps are made with
   const uint32_t R = lightMapResolution(h);
   if (R == 0) { h->lmRes = 0; return 0; }
-  const size_t texels = (size_t)h->numLights * 6u * R * R, ni = h->instances.size();
+  const size_t texels = (size_t)h->numLights * 6u * R * R;
   if (h->lmRes != R || h->lmLights != h->numLights || !h->dLmStatic) {
-    be.free(h->dLmStatic); be.free(h->dLmDynamic); be.free(h->dLmNear); be.free(h->dLmBase); be.free(h->dLmMoved);
-    h->dLmStatic = nullptr; h->dLmDynamic = nullptr; h->dLmNear = nullptr; h->dLmBase = nullptr; h->dLmMoved = nullptr;
+    be.free(h->dLmStatic); be.free(h->dLmDynamic); be.free(h->dLmNear);
+    h->dLmStatic = nullptr; h->dLmDynamic = nullptr; h->dLmNear = nullptr;
     BE_CHECK(h, be.alloc(&h->dLmStatic, texels)); BE_CHECK(h, be.alloc(&h->dLmNear, h->numLights));
-    BE_CHECK(h, be.alloc(&h->dLmBase, ni)); BE_CHECK(h, be.alloc(&h->dLmMoved, ni));
     h->lmRes = R; h->lmLights = h->numLights;
   }
   BE_CHECK(h, be.zero(h->dLmNear, h->numLights * sizeof(uint32_t)));
-  BE_CHECK(h, be.d2d(h->dLmBase, h->dXforms, ni * sizeof(InstXform)));
-  h->lmDynamicValid = false;
   return rasterLightMap(h, h->dLmStatic, nullptr);
 }
-// after a refit: instances whose transform left the one of the static map go into the dynamic map at their new place
+// after a refit: instances whose transform left the pose of the static maps go into the dynamic maps at their new place
 int refitLightMaps(anerend_ddgi* h, bool verticesChanged) {
   Backend& be = h->be;
-  if (h->lmRes == 0) return 0;
+  if (!mapsEnabled(h)) return 0;
   if (verticesChanged) return buildLightMaps(h);          // deformed meshes: every triangle may have moved
   const uint32_t ni = (uint32_t)h->instances.size();
-  if (!h->dLmDynamic) BE_CHECK(h, be.alloc(&h->dLmDynamic, (size_t)h->lmLights * 6u * h->lmRes * h->lmRes));
   LmMovedCtx mc{h->dXforms, h->dLmBase, h->dLmMoved};
   DDGI_LAUNCH(be, k_lightmap_moved, lm_moved_body, ni, mc, 128);
-  h->lmDynamicValid = true;
-  return rasterLightMap(h, h->dLmDynamic, h->dLmMoved);
+  h->lmMovedValid = true;
+  if (h->lmRes) {
+    if (!h->dLmDynamic) BE_CHECK(h, be.alloc(&h->dLmDynamic, (size_t)h->lmLights * 6u * h->lmRes * h->lmRes));
+    h->lmDynamicValid = true;
+    int rc = rasterLightMap(h, h->dLmDynamic, h->dLmMoved); if (rc) return rc;
+  }
+  if (h->smValid) {
+    if (!h->dSmDynamic) BE_CHECK(h, be.alloc(&h->dSmDynamic, (size_t)h->smRes * h->smRes));
+    h->smDynamicValid = true;
+    int rc = rasterSunMap(h, h->dSmDynamic, h->dLmMoved); if (rc) return rc;
+  }
+  return 0;
+}
+// The sun's map follows ubo.lightDir: (re)made at the first trace after build_accel and whenever the direction changed.
+int ensureSunMap(anerend_ddgi* h) {
+  Backend& be = h->be;
+  if (!mapsEnabled(h) || !h->haveUbo) { h->smValid = false; return 0; }
+  uint32_t R = 2048;
+  if (const char* e = getenv("DDGI_SM_RES")) R = (uint32_t)atoi(e);          // sweeps only; 0 disables the map
+  if (R > 8192u) R = 8192u;
+  if (R == 0) { h->smValid = false; return 0; }
+  const float* ld = h->ubo.light_dir;
+  if (h->smValid && h->smRes == R && ld[0] == h->smDir[0] && ld[1] == h->smDir[1] && ld[2] == h->smDir[2]) return 0;
+  h->smValid = false;
+  const V3 sdir = normalize3(-mk3(ld[0], ld[1], ld[2]));
+  if (!(fabsf(sdir.x) <= 1.0f && fabsf(sdir.y) <= 1.0f && fabsf(sdir.z) <= 1.0f)) return 0;      // zero / non-finite lightDir: no map
+  // instances away from the pose of the static maps: make that pose the current one first (both static maps then hold
+  // every triangle where it is now, and the next refit measures "moved" from here)
+  if (h->lmMovedValid) { int rc = buildLightMaps(h); if (rc) return rc; }
+  const V3 up = fabsf(sdir.y) < 0.9f ? mk3(0.0f, 1.0f, 0.0f) : mk3(1.0f, 0.0f, 0.0f);
+  const V3 a = normalize3(mk3(sdir.y * up.z - sdir.z * up.y, sdir.z * up.x - sdir.x * up.z, sdir.x * up.y - sdir.y * up.x));
+  const V3 b = mk3(sdir.y * a.z - sdir.z * a.y, sdir.z * a.x - sdir.x * a.z, sdir.x * a.y - sdir.y * a.x);
+  float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+  for (int k = 0; k < 8; ++k) {
+    const V3 p = mk3((k & 1) ? h->boundsMax[0] : h->boundsMin[0], (k & 2) ? h->boundsMax[1] : h->boundsMin[1], (k & 4) ? h->boundsMax[2] : h->boundsMin[2]);
+    const float q[3] = {dot3(p, a), dot3(p, b), dot3(p, sdir)};
+    for (int j = 0; j < 3; ++j) { lo[j] = fminf(lo[j], q[j]); hi[j] = fmaxf(hi[j], q[j]); }
+  }
+  const float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), 1e-3f) * 1.001f + 0.01f;
+  if (h->smRes != R || !h->dSmStatic) {
+    be.free(h->dSmStatic); be.free(h->dSmDynamic); h->dSmStatic = nullptr; h->dSmDynamic = nullptr;
+    BE_CHECK(h, be.alloc(&h->dSmStatic, (size_t)R * R));
+    h->smRes = R;
+  }
+  h->sm = SunMapCtx{};
+  h->sm.a = a; h->sm.b = b; h->sm.s = sdir; h->sm.cell = ext / (float)R; h->sm.invCell = (float)R / ext;
+  h->sm.orgA = lo[0] - 0.005f; h->sm.orgB = lo[1] - 0.005f; h->sm.base = lo[2] - 1.0f;
+  for (int k = 0; k < 3; ++k) h->smDir[k] = ld[k];
+  h->smDynamicValid = false;
+  int rc = rasterSunMap(h, h->dSmStatic, nullptr); if (rc) return rc;
+  h->smValid = true;
+  return 0;
 }
 
 // flatten + LBVH + BVH8 collapse
@@ -513,7 +611,16 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   be.mark(6);
   if (cnt) k_trace<false, true><<<gp, 128, 0, be.stream>>>(f); else k_trace<false, false><<<gp, 128, 0, be.stream>>>(f);
   be.mark(7);
-  if (prepBlock == 128) k_shade_prep<128><<<(n + 127u) / 128u, 128, 0, be.stream>>>(f);
+  // default: 32 registers (2048 resident threads per SM), light-map look-ups two at a time — g7 sweep at C3: 0.125 ms against 0.128
+  // (look-ups one by one), 0.136 (40 registers), 0.173 (56 registers), 0.156 / 0.176 (hits compacted per block first, 128 / 256 threads)
+  static const int prepVariant = getenv("DDGI_PREP_VARIANT") ? atoi(getenv("DDGI_PREP_VARIANT")) : 1;                  // sweeps only
+  if (prepVariant == 1 && prepBlock == 256) k_shade_prep<256, false, 2048, true><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
+  else if (prepVariant == 2) k_shade_prep<256, false, 1536, false><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
+  else if (prepVariant == 3) k_shade_prep<256, false, 1536, true><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
+  else if (prepVariant == 4) k_shade_prep<256, false, 1024, true><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
+  else if (prepVariant == 5) k_shade_prep_compact<256><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
+  else if (prepVariant == 6) k_shade_prep_compact<128><<<(n + 127u) / 128u, 128, 0, be.stream>>>(f);
+  else if (prepBlock == 128) k_shade_prep<128><<<(n + 127u) / 128u, 128, 0, be.stream>>>(f);
   else if (prepBlock == 512) k_shade_prep<512><<<(n + 511u) / 512u, 512, 0, be.stream>>>(f);
   else k_shade_prep<256><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
   be.mark(8);
@@ -638,6 +745,11 @@ TraceCtx sceneTraceCtx(anerend_ddgi* h) {
   c.uboFlags = h->ubo.flags; c.flags = h->p.flags;
   c.lmRes = h->lmRes; c.lmStatic = h->dLmStatic; c.lmDynamic = h->lmDynamicValid ? h->dLmDynamic : nullptr; c.lmNear = h->dLmNear;
   c.lmTris = h->dWtri; c.lmNumTris = h->numTris;
+  // the sun's map only while it is the map of THIS frame's lightDir (ensureSunMap runs in front of the probe trace)
+  if (h->smValid && h->ubo.light_dir[0] == h->smDir[0] && h->ubo.light_dir[1] == h->smDir[1] && h->ubo.light_dir[2] == h->smDir[2]) {
+    c.smRes = h->smRes; c.smStatic = h->dSmStatic; c.smDynamic = h->smDynamicValid ? h->dSmDynamic : nullptr;
+    c.smA = h->sm.a; c.smB = h->sm.b; c.smS = h->sm.s; c.smOrgA = h->sm.orgA; c.smOrgB = h->sm.orgB; c.smInvCell = h->sm.invCell; c.smBase = h->sm.base;
+  } else { c.smRes = 0; c.smS = mk3(0.0f, 1.0f, 0.0f); }
   return c;
 }
 
@@ -696,6 +808,7 @@ int traceLayers(anerend_ddgi* h, const int* layers, int numLayers, const float* 
   BE_CHECK(h, be.h2d(h->dLayerMap, h->hLayerMap, (size_t)numLayers * sizeof(int)));
 #endif
   h->numLaunchLayers = numLayers;
+  { int rcs = ensureSunMap(h); if (rcs) return rcs; }
   TraceCtx c = sceneTraceCtx(h); c.numLayers = numLayers;
   const uint32_t n = (uint32_t)numLayers * (uint32_t)h->Pl * (uint32_t)h->N;
 #ifndef DDGI_HOST_EMU

@@ -199,6 +199,10 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
               const LmEntry e = lightmap_lookup(t, q - 1, lp, pos);
               tmax = lightmap_tmax(e, dist);
               keep = !lightmap_candidate_occludes(t, e, pos, dir, t.tmin, dist);
+            } else if (t.smRes != 0u && !c.rawSunDir) {
+              const SmEntry e = sunmap_lookup(t, pos);
+              tmax = sunmap_tmax(e, dot3(pos, t.smS), t.tmax);
+              keep = !sunmap_candidate_occludes(t, e, pos, dir, t.tmin, t.tmax);
             }
           }
           const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
@@ -333,8 +337,10 @@ __device__ __noinline__ float4 prep_textured_surface(const TexCtx tex, const flo
   *roughnessOut = sf.roughness;
   return make_float4(sf.albedo.x, sf.albedo.y, sf.albedo.z, sf.metallic);
 }
-template <int PREP_BLOCK, bool EXT = false>
-__global__ void __launch_bounds__(PREP_BLOCK, 2048 / PREP_BLOCK) k_shade_prep(const FastCtx c) {
+// One thread per ray; MINT = resident threads per SM the register budget must allow (2048: 32 registers — the kernel waits on
+// scattered reads (shading records, light-map texels), so threads in flight count for more than a few spills).
+template <int PREP_BLOCK, bool EXT = false, int MINT = 2048, bool BATCH = false>
+__global__ void __launch_bounds__(PREP_BLOCK, MINT / PREP_BLOCK) k_shade_prep(const FastCtx c) {
   constexpr int PREP_WARPS = PREP_BLOCK / 32;
   const TraceCtx& t = c.t;
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
@@ -413,6 +419,11 @@ __global__ void __launch_bounds__(PREP_BLOCK, 2048 / PREP_BLOCK) k_shade_prep(co
   // lights, extension E1: only where the light can contribute); bit 32: the compacted hit list k_shade runs over.
   uint32_t needMask = isHit ? 1u : 0u, preLit = 0u;
   if (isHit && (t.flags & ANEREND_DDGI_FLAG_SKIP_DEAD_SHADOW_RAYS) && !(dot3(normal, normalize3(-t.lightDir)) > 0.0f)) needMask = 0u;
+  // the sun's map (ddgi_kernels.cuh): its read is issued here and looked at after the point lights' reads are on their way too
+  const bool sunAsk = needMask != 0u && t.smRes != 0u && !c.rawSunDir;
+  SmEntry sunE; sunE.inside = false; sunE.top = 0.0f; sunE.cand = 0u;
+  if (sunAsk) sunE = sunmap_lookup(t, pos);
+  uint32_t askMask = 0u;                         // BATCH: lights whose ray exists (in range and facing), looked up two at a time below
   if (isHit && (t.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS)) {
     for (uint32_t li = 0; li < t.numLights; ++li) {
       const anerend_light_t* lt = &t.lights[li];
@@ -429,20 +440,211 @@ __global__ void __launch_bounds__(PREP_BLOCK, 2048 / PREP_BLOCK) k_shade_prep(co
           if (d2 > 1e-30f && fabsf(sgn) > 1e-5f * mag) facing = sgn > 0.0f;
           else { const V3 L = normalize3(lp - pos); facing = dot3(normal, L) > 0.0f; }
           // the light map answers the rays that certainly reach the light (ddgi_kernels.cuh "Light maps"): lit without a traversal
-          if (facing) { if (lightmap_unoccluded(lightmap_lookup(t, li, lp, pos), dist, t.tmin)) preLit |= 1u << (1u + li); else needMask |= 1u << (1u + li); }
+          if (facing) {
+            if (BATCH) askMask |= 1u << (1u + li);
+            else if (lightmap_unoccluded(lightmap_lookup(t, li, lp, pos), dist, t.tmin)) preLit |= 1u << (1u + li); else needMask |= 1u << (1u + li);
+          }
         }
       }
     }
-    if (preLit) {
-      c.lit[idx] = preLit;
-      if ((t.flags & ANEREND_DDGI_FLAG_COUNTERS) && t.stats) atomicAdd(&t.stats[7], (unsigned long long)__popc(preLit));
+  }
+  if (BATCH) {
+    // two look-ups per round so their (scattered, mostly L2-missing) reads overlap
+    if (t.lmRes == 0u) needMask |= askMask;
+    else for (uint32_t m = askMask; m != 0u;) {
+      const uint32_t b0 = (uint32_t)__ffs((int)m) - 1u; m &= m - 1u;
+      const bool two = m != 0u;
+      const uint32_t b1 = two ? (uint32_t)__ffs((int)m) - 1u : b0; m &= m - 1u;
+      const anerend_light_t* l0 = &t.lights[b0 - 1u]; const anerend_light_t* l1 = &t.lights[b1 - 1u];
+      const V3 p0 = mk3(l0->world_pos[0], l0->world_pos[1], l0->world_pos[2]), p1 = mk3(l1->world_pos[0], l1->world_pos[1], l1->world_pos[2]);
+      const LmEntry e0 = lightmap_lookup(t, b0 - 1u, p0, pos), e1 = lightmap_lookup(t, b1 - 1u, p1, pos);
+      const V3 d0 = p0 - pos, d1 = p1 - pos;
+      if (lightmap_unoccluded(e0, sqrtf(dot3(d0, d0)), t.tmin)) preLit |= 1u << b0; else needMask |= 1u << b0;
+      if (two) { if (lightmap_unoccluded(e1, sqrtf(dot3(d1, d1)), t.tmin)) preLit |= 1u << b1; else needMask |= 1u << b1; }
     }
+  }
+  if (sunAsk && sunmap_unoccluded(sunE, dot3(pos, t.smS), t.tmin)) { needMask &= ~1u; preLit |= 1u; }
+  if (preLit) {
+    c.lit[idx] = preLit;
+    if ((t.flags & ANEREND_DDGI_FLAG_COUNTERS) && t.stats) atomicAdd(&t.stats[7], (unsigned long long)__popc(preLit));
   }
   // block-aggregated append: one atomic per queue per block (a per-warp atomic on nine neighbouring counters was the
   // whole cost of this kernel), order inside the block = ray order
   __shared__ uint32_t sCnt[33][PREP_WARPS];
   __shared__ uint32_t sBase[33];
   const uint32_t warp = threadIdx.x >> 5, nq = c.numQueues;
+  for (uint32_t q = 0; q <= nq; ++q) {
+    const bool need = q < nq ? ((needMask >> q) & 1u) != 0u : isHit;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, need);
+    if (lane == 0) sCnt[q][warp] = (uint32_t)__popc(m);
+  }
+  __syncthreads();
+  if (threadIdx.x <= nq) {
+    const uint32_t q = threadIdx.x;
+    uint32_t sum = 0;
+    for (uint32_t w = 0; w < PREP_WARPS; ++w) { const uint32_t v = sCnt[q][w]; sCnt[q][w] = sum; sum += v; }
+    sBase[q] = sum ? atomicAdd(&c.qcount[q < nq ? FAST_QC(q) : FAST_QC_HITS], sum) : 0u;
+  }
+  __syncthreads();
+  for (uint32_t q = 0; q <= nq; ++q) {
+    const bool need = q < nq ? ((needMask >> q) & 1u) != 0u : isHit;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, need);
+    if (need) {
+      const uint32_t o = sBase[q] + sCnt[q][warp] + (uint32_t)__popc(m & ((1u << lane) - 1u));
+      if (q < nq) c.queues[(size_t)q * c.totalRays + o] = idx; else c.hitq[o] = idx;
+    }
+  }
+}
+
+// Block layout: every thread looks at one ray and the MISSES are finished on the spot (sky, rmiss:20); the hits of the block are
+// compacted (ray order kept) and the surface / light work runs over the compacted list, so its warps are full although only about
+// half of the probe rays hit anything.
+template <int PREP_BLOCK, bool EXT = false>
+__global__ void __launch_bounds__(PREP_BLOCK, 1024 / PREP_BLOCK) k_shade_prep_compact(const FastCtx c) {
+  constexpr int PREP_WARPS = PREP_BLOCK / 32;
+  const TraceCtx& t = c.t;
+  const uint32_t ray0 = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const int P = t.nXZ * t.nXZ;
+  __shared__ uint32_t sHitIdx[PREP_BLOCK];
+  __shared__ uint32_t sCnt[33][PREP_WARPS];
+  __shared__ uint32_t sBase[33];
+  bool hit0 = false;
+  if (ray0 < c.totalRays) {
+    const uint32_t hp = __float_as_uint(c.hits[ray0].w);
+    if (hp != DDGI_MISS) hit0 = true;
+    else if (EXT) {
+      // mirror_reflections.rmiss: (sky, 1e6); pixels without a ray are overwritten by the resolve kernel
+      t.rayIrr[ray0] = make_uint2((uint32_t)f2h(t.sky.x) | ((uint32_t)f2h(t.sky.y) << 16), (uint32_t)f2h(t.sky.z) | ((uint32_t)f2h(1e6f) << 16));
+    } else {
+      // rmiss:20 + rgen:109
+      const uint32_t slot = ray0 % (uint32_t)t.N, probeLin = ray0 / (uint32_t)t.N;
+      const int layerLocal = (int)(probeLin / (uint32_t)t.Pl), probe = stripe_probe((int)(probeLin % (uint32_t)t.Pl), t.nXZ, t.rowOffset, t.rowStride);
+      const uint32_t ray = t.rayOrder ? (uint32_t)t.rayOrder[slot] : slot;
+      const size_t o = ((size_t)t.layerMap[layerLocal] * P + probe) * t.N + ray;
+      t.rayIrr[o] = make_uint2((uint32_t)f2h(t.sky.x) | ((uint32_t)f2h(t.sky.y) << 16), (uint32_t)f2h(t.sky.z) | (0x3C00u << 16));
+      if (t.records) { anerend_ddgi_ray_record_t rr; rr.prim = DDGI_MISS; rr.t = 0.0f; rr.u = 0.0f; rr.v = 0.0f;
+                       rr.radiance[0] = t.sky.x; rr.radiance[1] = t.sky.y; rr.radiance[2] = t.sky.z; rr.lit_mask = 0u; t.records[o] = rr; }
+    }
+  }
+  {   // compaction of the block's hits, ray order kept
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit0);
+    if (lane == 0) sCnt[32][warp] = (uint32_t)__popc(m);
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+    for (uint32_t w = 0; w < (uint32_t)PREP_WARPS; ++w) { const uint32_t v = sCnt[32][w]; before += w < warp ? v : 0u; total += v; }
+    if (hit0) sHitIdx[before + (uint32_t)__popc(m & ((1u << lane) - 1u))] = ray0;
+    __syncthreads();
+    if (threadIdx.x == 0) sBase[32] = total;        // read below, after the next barrier
+  }
+  __syncthreads();
+  const uint32_t nHitBlock = sBase[32];
+  const bool isHit = threadIdx.x < nHitBlock;
+  const uint32_t idx = isHit ? sHitIdx[threadIdx.x] : 0u;
+  V3 pos = mk3(0.0f), normal = mk3(0.0f);
+  if (isHit) {
+    const float4 h = c.hits[idx];
+    const uint32_t hp = __float_as_uint(h.w);
+    {
+      // rchit:27-38 through the per-triangle record (five independent 16-byte loads instead of the index/vertex gather)
+      const float4* st = c.shadeTris + 5 * (size_t)hp;
+      const float4 s0 = __ldg(st), s1 = __ldg(st + 1), s2 = __ldg(st + 2), s3 = __ldg(st + 3), s4 = __ldg(st + 4);
+      const uint32_t ii = __float_as_uint(s4.z), material = __float_as_uint(s4.w);
+      const InstXform& xf = t.xforms[ii];
+      const float b0 = 1.0f - h.y - h.z, b1 = h.y, b2 = h.z;
+      pos = mk3(s0.x, s0.y, s0.z) * b0 + mk3(s0.w, s1.x, s1.y) * b1 + mk3(s1.z, s1.w, s2.x) * b2;
+      pos = xform_point(xf.o2w, pos);
+      normal = normalize3(mk3(s2.y, s2.z, s2.w) * b0 + mk3(s3.x, s3.y, s3.z) * b1 + mk3(s3.w, s4.x, s4.y) * b2);
+      if (!EXT)
+        normal = normalize3(mk3(normal.x * xf.w2o[0] + normal.y * xf.w2o[1] + normal.z * xf.w2o[2],
+                                normal.x * xf.w2o[3] + normal.y * xf.w2o[4] + normal.z * xf.w2o[5],
+                                normal.x * xf.w2o[6] + normal.y * xf.w2o[7] + normal.z * xf.w2o[8]));
+      else {                                                          // mirror_reflections.rchit:74 + :86
+        normal = normalize3(mk3(xf.o2w[0] * normal.x + xf.o2w[3] * normal.y + xf.o2w[6] * normal.z,
+                                xf.o2w[1] * normal.x + xf.o2w[4] * normal.y + xf.o2w[7] * normal.z,
+                                xf.o2w[2] * normal.x + xf.o2w[5] * normal.y + xf.o2w[8] * normal.z));
+        const float4 ea = __ldg(&c.extRays[2 * (size_t)idx]);
+        const V3 dd = pos - mk3(ea.x, ea.y, ea.z);
+        c.extDist[idx] = sqrtf(dot3(dd, dd));
+      }
+      const anerend_material_info_t* m = &t.materials[material];
+      V3 albedo;
+      float metallic = m->met_rough[0], roughness = m->met_rough[1];
+      bool textureRough = false;
+      const bool textured = c.shadeUV != nullptr && material_textured(m);
+      if (!textured && m->base_col_fac[0] + m->base_col_fac[1] + m->base_col_fac[2] > 0.1f) albedo = mk3(m->base_col_fac[0], m->base_col_fac[1], m->base_col_fac[2]);
+      else {
+        // vertex colour decides (rchit:71,75; bindless.glsl:187-194): rare, so the colours stay in the vertex buffer
+        const DInstance in = t.instances[ii];
+        const uint32_t prim = hp - in.firstTri;                                                     // gl_PrimitiveID
+        const anerend_vertex_t* v0 = &t.vertices[in.vertexOffset + t.indices[in.indexOffset + 3 * prim + 0]];
+        const anerend_vertex_t* v1 = &t.vertices[in.vertexOffset + t.indices[in.indexOffset + 3 * prim + 1]];
+        const anerend_vertex_t* v2 = &t.vertices[in.vertexOffset + t.indices[in.indexOffset + 3 * prim + 2]];
+        const V3 color = mk3(v0->color[0], v0->color[1], v0->color[2]) * b0 + mk3(v1->color[0], v1->color[1], v1->color[2]) * b1 +
+                         mk3(v2->color[0], v2->color[1], v2->color[2]) * b2;
+        albedo = mk3(to_linear1(color.x), to_linear1(color.y), to_linear1(color.z));
+        if (textured) {
+          const float4 r = prep_textured_surface(t.tex, c.shadeUV, c.emisTex, m, hp, idx, h.y, h.z, make_float3(albedo.x, albedo.y, albedo.z),
+                                                 reinterpret_cast<float*>(&c.surf[3 * (size_t)idx + 2]) + 3);
+          albedo = mk3(r.x, r.y, r.z); metallic = r.w; textureRough = true;
+        }
+      }
+      c.surf[3 * (size_t)idx + 0] = make_float4(pos.x, pos.y, pos.z, normal.x);
+      c.surf[3 * (size_t)idx + 1] = make_float4(normal.y, normal.z, albedo.x, albedo.y);
+      if (textureRough) roughness = c.surf[3 * (size_t)idx + 2].w;       // written by prep_textured_surface
+      c.surf[3 * (size_t)idx + 2] = make_float4(albedo.z, __uint_as_float(material), metallic, roughness);
+    }
+  }
+  // Which queues does this ray enter?  bit q: shadow ray towards light q (0 = sun, rchit:45-66: every hit; point
+  // lights, extension E1: only where the light can contribute); bit 32: the compacted hit list k_shade runs over.
+  uint32_t needMask = isHit ? 1u : 0u, preLit = 0u;
+  if (isHit && (t.flags & ANEREND_DDGI_FLAG_SKIP_DEAD_SHADOW_RAYS) && !(dot3(normal, normalize3(-t.lightDir)) > 0.0f)) needMask = 0u;
+  // the sun's map (ddgi_kernels.cuh): its read is issued here and looked at after the point lights' reads are on their way too
+  const bool sunAsk = needMask != 0u && t.smRes != 0u && !c.rawSunDir;
+  SmEntry sunE; sunE.inside = false; sunE.top = 0.0f; sunE.cand = 0u;
+  if (sunAsk) sunE = sunmap_lookup(t, pos);
+  if (isHit && (t.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS)) {
+    uint32_t askMask = 0u;                         // lights whose ray exists: in range and facing
+    for (uint32_t li = 0; li < t.numLights; ++li) {
+      const anerend_light_t* lt = &t.lights[li];
+      if (lt->color[3] > 0.5f) {
+        const V3 lp = mk3(lt->world_pos[0], lt->world_pos[1], lt->world_pos[2]);
+        const V3 dv = lp - pos; const float d2 = dot3(dv, dv), range = lt->world_pos[3];
+        // the decisions below are the oracle's (dist < range, dot(normal, normalize(dv)) > 0); the two filters only
+        // skip the sqrt / normalise where rounding cannot change the outcome (margins >> the fp32 error of either side)
+        if (d2 > range * range * 1.00001f) continue;
+        const float dist = sqrtf(d2);
+        if (dist < range) {
+          const float sgn = dot3(normal, dv), mag = fabsf(normal.x * dv.x) + fabsf(normal.y * dv.y) + fabsf(normal.z * dv.z);
+          bool facing;
+          if (d2 > 1e-30f && fabsf(sgn) > 1e-5f * mag) facing = sgn > 0.0f;
+          else { const V3 L = normalize3(lp - pos); facing = dot3(normal, L) > 0.0f; }
+          if (facing) askMask |= 1u << (1u + li);
+        }
+      }
+    }
+    // the light maps answer the rays that certainly reach their light (ddgi_kernels.cuh "Light maps"): lit without a traversal.
+    // Two look-ups per round so their (scattered, mostly L2-missing) reads overlap.
+    if (t.lmRes == 0u) needMask |= askMask;
+    else for (uint32_t m = askMask; m != 0u;) {
+      const uint32_t b0 = (uint32_t)__ffs((int)m) - 1u; m &= m - 1u;
+      const bool two = m != 0u;
+      const uint32_t b1 = two ? (uint32_t)__ffs((int)m) - 1u : b0; m &= m - 1u;
+      const anerend_light_t* l0 = &t.lights[b0 - 1u]; const anerend_light_t* l1 = &t.lights[b1 - 1u];
+      const V3 p0 = mk3(l0->world_pos[0], l0->world_pos[1], l0->world_pos[2]), p1 = mk3(l1->world_pos[0], l1->world_pos[1], l1->world_pos[2]);
+      const LmEntry e0 = lightmap_lookup(t, b0 - 1u, p0, pos), e1 = lightmap_lookup(t, b1 - 1u, p1, pos);
+      const V3 d0 = p0 - pos, d1 = p1 - pos;
+      if (lightmap_unoccluded(e0, sqrtf(dot3(d0, d0)), t.tmin)) preLit |= 1u << b0; else needMask |= 1u << b0;
+      if (two) { if (lightmap_unoccluded(e1, sqrtf(dot3(d1, d1)), t.tmin)) preLit |= 1u << b1; else needMask |= 1u << b1; }
+    }
+  }
+  if (sunAsk && sunmap_unoccluded(sunE, dot3(pos, t.smS), t.tmin)) { needMask &= ~1u; preLit |= 1u; }
+  if (isHit) {
+    c.lit[idx] = preLit;
+    if (preLit && (t.flags & ANEREND_DDGI_FLAG_COUNTERS) && t.stats) atomicAdd(&t.stats[7], (unsigned long long)__popc(preLit));
+  }
+  // block-aggregated append: one atomic per queue per block (a per-warp atomic on nine neighbouring counters was the
+  // whole cost of this kernel), order inside the block = ray order
+  const uint32_t nq = c.numQueues;
   for (uint32_t q = 0; q <= nq; ++q) {
     const bool need = q < nq ? ((needMask >> q) & 1u) != 0u : isHit;
     const uint32_t m = __ballot_sync(0xFFFFFFFFu, need);

@@ -608,6 +608,9 @@ struct TraceCtx {
   // light maps (below): conservative distance maps around the point lights that answer "certainly unoccluded" shadow rays
   const unsigned long long* lmStatic; const unsigned long long* lmDynamic; const uint32_t* lmNear; uint32_t lmRes;      // lmRes = 0: none
   const float4* lmTris; uint32_t lmNumTris;      // world triangles by global id (the candidates the map entries name)
+  // the sun's map: orthographic, along normalize(-lightDir); entry = (height above smBase, fp32 bits) << 32 | triangle id, kept maximal
+  const unsigned long long* smStatic; const unsigned long long* smDynamic; uint32_t smRes;      // smRes = 0: none
+  V3 smA, smB, smS; float smOrgA, smOrgB, smInvCell, smBase;
 };
 
 // Row stripe (multi-GPU sharding inside the layers): launched probe `pl` of a layer -> probe index in the layer.  A handle
@@ -661,8 +664,32 @@ HD bool lm_tri_setup(V3 r0, V3 r1, V3 r2, float range, LmTri& t) {
   t.n = n * inv; t.h = fabsf(dot3(t.n, r0));
   return true;
 }
+// Conservative rasterisation inside the footprint rectangle: a texel is touched unless its whole square (grown by the same margin as
+// the rectangle) lies outside one edge of the projected triangle.  Edge functions in texel coordinates relative to the rectangle's
+// corner (x0, y0): inside <=> A*x + B*y + C >= 0 at the texel centre, the half-texel reach and the margins folded into C.
+// `use` is false (rectangle only) where the projection is not a triangle with well-conditioned edges: straddling the apex plane,
+// nearly edge-on, or vertices projected far outside the map.
+struct LmEdges { float A[3], B[3], C[3]; bool use; };
+HD void lm_edges(const float* px, const float* py, float x0, float y0, float slackTexels, float limit, LmEdges& e) {
+  const float area2 = (px[1] - px[0]) * (py[2] - py[0]) - (py[1] - py[0]) * (px[2] - px[0]);
+  e.use = fabsf(area2) > 1e-3f;
+  for (int k = 0; k < 3; ++k) e.use = e.use && fabsf(px[k]) <= limit && fabsf(py[k]) <= limit;
+  const float sgn = area2 > 0.0f ? 1.0f : -1.0f;
+  for (int i = 0; i < 3; ++i) {
+    const int j = i == 2 ? 0 : i + 1;
+    const float dx = px[j] - px[i], dy = py[j] - py[i];
+    e.A[i] = -dy * sgn; e.B[i] = dx * sgn;
+    e.C[i] = (dy * (px[i] - x0) - dx * (py[i] - y0)) * sgn + (0.5f + slackTexels) * (fabsf(dx) + fabsf(dy));
+  }
+}
+HD bool lm_edges_touch(const LmEdges& e, int lx, int ly) {        // lx, ly: texel relative to (x0, y0)
+  if (!e.use) return true;
+  const float xc = (float)lx + 0.5f, yc = (float)ly + 0.5f;
+  return e.A[0] * xc + e.B[0] * yc + e.C[0] >= 0.0f && e.A[1] * xc + e.B[1] * yc + e.C[1] >= 0.0f && e.A[2] * xc + e.B[2] * yc + e.C[2] >= 0.0f;
+}
+#define LM_EDGE_SLACK 4e-3f      // texels per unit of |dx| + |dy|: above the fp32 rounding of the edge functions for vertices within `limit`
 // texel rectangle of the triangle's projection on `face`, grown by LM_DELTA; false: the triangle does not reach the face
-HD bool lm_face_rect(const LmTri& t, int face, uint32_t R, int& x0, int& x1, int& y0, int& y1) {
+HD bool lm_face_rect(const LmTri& t, int face, uint32_t R, int& x0, int& x1, int& y0, int& y1, LmEdges& edges) {
   const int axis = face >> 1, ab = axis == 2 ? 0 : axis + 1, ac = ab == 2 ? 0 : ab + 1;
   const float s = (face & 1) ? -1.0f : 1.0f;
   float w[3], b[3], c[3];
@@ -670,9 +697,15 @@ HD bool lm_face_rect(const LmTri& t, int face, uint32_t R, int& x0, int& x1, int
   const float wmax = fmaxf(fmaxf(w[0], w[1]), w[2]), wmin = fminf(fminf(w[0], w[1]), w[2]);
   if (!(wmax > LM_EPS_W)) return false;
   float umin, umax, vmin, vmax;
-  if (wmin > LM_EPS_W) {          // wholly in front of the apex plane: the projection is the triangle of the projected vertices
+  float px[3] = {0.0f, 0.0f, 0.0f}, py[3] = {0.0f, 0.0f, 0.0f};
+  const bool front = wmin > LM_EPS_W;
+  edges.use = false;
+  if (front) {                    // wholly in front of the apex plane: the projection is the triangle of the projected vertices
     const float u0 = b[0] / w[0], u1 = b[1] / w[1], u2 = b[2] / w[2], v0 = c[0] / w[0], v1 = c[1] / w[1], v2 = c[2] / w[2];
     umin = fminf(fminf(u0, u1), u2); umax = fmaxf(fmaxf(u0, u1), u2); vmin = fminf(fminf(v0, v1), v2); vmax = fmaxf(fmaxf(v0, v1), v2);
+    const float half = 0.5f * (float)R;
+    px[0] = (u0 + 1.0f) * half; px[1] = (u1 + 1.0f) * half; px[2] = (u2 + 1.0f) * half;
+    py[0] = (v0 + 1.0f) * half; py[1] = (v1 + 1.0f) * half; py[2] = (v2 + 1.0f) * half;
   } else {                        // straddles the apex plane: interval arithmetic over the box, w clipped to [LM_EPS_W, wmax]
     const float blo = fminf(fminf(b[0], b[1]), b[2]), bhi = fmaxf(fmaxf(b[0], b[1]), b[2]), clo = fminf(fminf(c[0], c[1]), c[2]), chi = fmaxf(fmaxf(c[0], c[1]), c[2]);
     const float il = 1.0f / LM_EPS_W, ih = 1.0f / wmax;
@@ -684,6 +717,7 @@ HD bool lm_face_rect(const LmTri& t, int face, uint32_t R, int& x0, int& x1, int
   const float fr = (float)R, top = (float)(R - 1u);
   x0 = (int)fminf(fmaxf(floorf((umin + 1.0f) * 0.5f * fr), 0.0f), top); x1 = (int)fminf(fmaxf(floorf((umax + 1.0f) * 0.5f * fr), 0.0f), top);
   y0 = (int)fminf(fmaxf(floorf((vmin + 1.0f) * 0.5f * fr), 0.0f), top); y1 = (int)fminf(fmaxf(floorf((vmax + 1.0f) * 0.5f * fr), 0.0f), top);
+  if (front) lm_edges(px, py, (float)x0, (float)y0, LM_DELTA * 0.5f * fr + LM_EDGE_SLACK, 3.0f * fr, edges);
   return true;
 }
 // lower bound of the distance from the light to the triangle inside texel (X, Y) of `face`: the triangle's plane cut by the texel's
@@ -756,13 +790,85 @@ HD void lightmap_raster_body(uint32_t i, const LmBuildCtx& c) {
   if (!lm_pair_setup(c, t, li, tri)) return;
   if (tri.nearLight) c.nearFlags[li] = 1u;
   for (int face = 0; face < 6; ++face) {
-    int x0, x1, y0, y1;
-    if (!lm_face_rect(tri, face, c.R, x0, x1, y0, y1)) continue;
+    int x0, x1, y0, y1; LmEdges ed;
+    if (!lm_face_rect(tri, face, c.R, x0, x1, y0, y1, ed)) continue;
     unsigned long long* dm = c.depth + ((size_t)li * 6u + (size_t)face) * c.R * c.R;
     for (int y = y0; y <= y1; ++y) for (int x = x0; x <= x1; ++x)
-      atomMin64(dm + (size_t)y * c.R + x, ((unsigned long long)f2u(lm_texel_bound(tri.n, tri.h, tri.daabb, tri.skinny, face, x, y, c.R, c.rho)) << 32) | t);
+      if (lm_edges_touch(ed, x - x0, y - y0)) atomMin64(dm + (size_t)y * c.R + x, ((unsigned long long)f2u(lm_texel_bound(tri.n, tri.h, tri.daabb, tri.skinny, face, x, y, c.R, c.rho)) << 32) | t);
   }
 }
+// ---- the sun (rchit:45-66): all its shadow rays run along smS = normalize(-lightDir), so the map is an orthographic height field over
+// the plane (smA, smB): per texel an UPPER bound of s = dot(p, smS) over every triangle that reaches into the texel's column, and
+// the triangle that set it.  A ray from pos covers s in (s(pos) + tMin, s(pos) + tMax): above the bound it is unoccluded.
+#define SM_DELTA 2e-4f          // footprint growth in metres (fp32 rounding of the projections: ~1e-5 at scene scale)
+struct SunMapCtx {
+  const float4* wtri; const uint32_t* triInstance; const uint32_t* moved; uint32_t numTris, R;
+  V3 a, b, s; float orgA, orgB, invCell, cell, base;
+  unsigned long long* height;
+};
+struct SmTri { float pa[3], pb[3], ps[3]; float smax, ga, gb; bool flat; };     // flat: plane usable, s = ps[0] + ga * (a - pa[0]) + gb * (b - pb[0])
+HD bool sm_tri_setup(const SunMapCtx& c, uint32_t t, SmTri& tri, int& x0, int& x1, int& y0, int& y1, LmEdges& edges) {
+  if (c.moved && !c.moved[c.triInstance[t]]) return false;
+  const float4 A = c.wtri[3 * (size_t)t], B = c.wtri[3 * (size_t)t + 1], C = c.wtri[3 * (size_t)t + 2];
+  const V3 v0 = mk3(A.x, A.y, A.z), e1 = mk3(A.w, B.x, B.y), e2 = mk3(B.z, B.w, C.x);
+  const V3 v[3] = {v0, v0 + e1, v0 + e2};
+  for (int k = 0; k < 3; ++k) { tri.pa[k] = dot3(v[k], c.a); tri.pb[k] = dot3(v[k], c.b); tri.ps[k] = dot3(v[k], c.s); }
+  const float amin = fminf(fminf(tri.pa[0], tri.pa[1]), tri.pa[2]) - SM_DELTA, amax = fmaxf(fmaxf(tri.pa[0], tri.pa[1]), tri.pa[2]) + SM_DELTA;
+  const float bmin = fminf(fminf(tri.pb[0], tri.pb[1]), tri.pb[2]) - SM_DELTA, bmax = fmaxf(fmaxf(tri.pb[0], tri.pb[1]), tri.pb[2]) + SM_DELTA;
+  tri.smax = fmaxf(fmaxf(tri.ps[0], tri.ps[1]), tri.ps[2]);
+  const float fr = (float)c.R;
+  const float fx0 = floorf((amin - c.orgA) * c.invCell), fx1 = floorf((amax - c.orgA) * c.invCell), fy0 = floorf((bmin - c.orgB) * c.invCell), fy1 = floorf((bmax - c.orgB) * c.invCell);
+  if (fx1 < 0.0f || fy1 < 0.0f || fx0 >= fr || fy0 >= fr) return false;             // wholly outside the map: rays there are not answered by it
+  x0 = (int)fmaxf(fx0, 0.0f); x1 = (int)fminf(fx1, fr - 1.0f); y0 = (int)fmaxf(fy0, 0.0f); y1 = (int)fminf(fy1, fr - 1.0f);
+  { float px[3], py[3];
+    for (int k = 0; k < 3; ++k) { px[k] = (tri.pa[k] - c.orgA) * c.invCell; py[k] = (tri.pb[k] - c.orgB) * c.invCell; }
+    lm_edges(px, py, (float)x0, (float)y0, SM_DELTA * c.invCell + LM_EDGE_SLACK, 3.0f * fr, edges); }
+  // plane in map coordinates through the three projected vertices: s = k + ga * a + gb * b
+  const float ua = tri.pa[1] - tri.pa[0], ub = tri.pb[1] - tri.pb[0], us = tri.ps[1] - tri.ps[0];
+  const float va = tri.pa[2] - tri.pa[0], vb = tri.pb[2] - tri.pb[0], vs = tri.ps[2] - tri.ps[0];
+  const float det = ua * vb - ub * va;
+  const float scale = (fabsf(ua) + fabsf(ub)) * (fabsf(va) + fabsf(vb));
+  tri.flat = fabsf(det) > 1e-4f * scale && scale > 0.0f;                            // else: (nearly) edge-on to the sun, highest vertex only
+  if (tri.flat) {
+    const float inv = 1.0f / det;
+    tri.ga = (us * vb - ub * vs) * inv; tri.gb = (ua * vs - us * va) * inv;
+  } else { tri.ga = 0.0f; tri.gb = 0.0f; }
+  return true;
+}
+// upper bound of s over the part of the triangle's plane above texel (X, Y), evaluated relative to vertex 0 (no cancellation)
+HD float sm_texel_bound(float smax, float ga, float gb, float pa0, float pb0, float ps0, bool flat, int X, int Y, float orgA, float orgB, float cell) {
+  if (!flat) return smax;
+  const float ca = orgA + ((float)X + 0.5f) * cell, cb = orgB + ((float)Y + 0.5f) * cell;
+  const float top = ps0 + ga * (ca - pa0) + gb * (cb - pb0) + (fabsf(ga) + fabsf(gb)) * (0.5f * cell + SM_DELTA);
+  return fminf(smax, top + 1e-4f + 1e-5f * fabsf(top));
+}
+HD unsigned long long sm_pack(float bound, float base, uint32_t t) { return ((unsigned long long)f2u(fmaxf(bound - base, 0.0f)) << 32) | t; }
+HD void sunmap_raster_body(uint32_t t, const SunMapCtx& c) {
+  SmTri tri; int x0, x1, y0, y1; LmEdges ed;
+  if (!sm_tri_setup(c, t, tri, x0, x1, y0, y1, ed)) return;
+  for (int y = y0; y <= y1; ++y) for (int x = x0; x <= x1; ++x)
+    if (lm_edges_touch(ed, x - x0, y - y0)) atomMax64(c.height + (size_t)y * c.R + x, sm_pack(sm_texel_bound(tri.smax, tri.ga, tri.gb, tri.pa[0], tri.pb[0], tri.ps[0], tri.flat, x, y, c.orgA, c.orgB, c.cell), c.base, t));
+}
+struct SmEntry { float top; uint32_t cand; bool inside; };
+HD SmEntry sunmap_lookup(const TraceCtx& c, V3 pos) {
+  SmEntry e; e.top = 0.0f; e.cand = LM_FAR_BITS; e.inside = false;
+  if (c.smRes == 0u) return e;
+  const float fx = floorf((dot3(pos, c.smA) - c.smOrgA) * c.smInvCell), fy = floorf((dot3(pos, c.smB) - c.smOrgB) * c.smInvCell), fr = (float)c.smRes;
+  if (!(fx >= 0.0f && fy >= 0.0f && fx < fr && fy < fr)) return e;
+  const size_t o = (size_t)fy * c.smRes + (size_t)fx;
+  unsigned long long v = c.smStatic[o];
+  if (c.smDynamic) { const unsigned long long dv = c.smDynamic[o]; v = dv > v ? dv : v; }
+  e.inside = true; e.cand = v ? (uint32_t)v : LM_FAR_BITS;                          // 0 = empty column
+  e.top = v ? u2f((uint32_t)(v >> 32)) + c.smBase : -3.0e38f;
+  return e;
+}
+HD bool sunmap_unoccluded(const SmEntry& e, float sPos, float tmin) { return e.inside && sPos + tmin > e.top + 1e-3f + 1e-4f * fabsf(e.top); }
+HD float sunmap_tmax(const SmEntry& e, float sPos, float tmax) { return e.inside ? fminf(tmax, (e.top - sPos) + 2e-3f + 2e-4f * fabsf(e.top)) : tmax; }
+HD bool sunmap_candidate_occludes(const TraceCtx& c, const SmEntry& e, V3 pos, V3 dir, float tmin, float tmax) {
+  LmEntry le; le.bound = 0.0f; le.cand = e.cand;
+  return lightmap_candidate_occludes(c, le, pos, dir, tmin, tmax);
+}
+
 // instances whose transform differs from the one the static map was rasterised with
 struct LmMovedCtx { const InstXform* xforms; const InstXform* base; uint32_t* moved; };
 HD void lm_moved_body(uint32_t i, const LmMovedCtx& c) {
@@ -1089,8 +1195,14 @@ HD V3 shade_hit_simple(const TraceCtx& c, const Hit& hit, V3 origin, uint32_t& l
   Hit sh;
   bool occluded = true;
   if (!(c.flags & ANEREND_DDGI_FLAG_SKIP_DEAD_SHADOW_RAYS) || dot3(normal, sunL) > 0.0f) {
-    ++nShadow;
-    occluded = traverse<true, CNT>(c.nodes, c.bvhTris, c.numNodes, pos, sunL, c.tmin, c.tmax, sh, cn[1], ct[1]);
+    const SmEntry sme = sunmap_lookup(c, pos);
+    const float sPos = dot3(pos, c.smS);
+    if (sunmap_unoccluded(sme, sPos, c.tmin)) { ++nPre; occluded = false; }        // answered by the sun's map, not traced
+    else {
+      ++nShadow;
+      if (sunmap_candidate_occludes(c, sme, pos, sunL, c.tmin, c.tmax)) ++nCand;
+      else occluded = traverse<true, CNT>(c.nodes, c.bvhTris, c.numNodes, pos, sunL, c.tmin, sunmap_tmax(sme, sPos, c.tmax), sh, cn[1], ct[1]);
+    }
   }
   V3 irradiance = mk3(0.0f);
   if (!occluded) { lit |= 1u; irradiance = calc_light(normal, albedo, metallic, roughness, pos, origin, sunL, c.sunIntensity * mk3(1.0f) * 1.0f); }

@@ -157,11 +157,12 @@ __global__ void __launch_bounds__(128) k_conv_weights(const ConvFastCtx f) {
   out[2 * j + 1] = make_float4(w[4], w[5], w[6], w[7]);
 }
 
-#define CONV_PPT 4                    // probes per thread
-#define CONV_G (4 * CONV_PPT)         // probes per block (256 threads = 64 texels x 4 probe groups)
 #define CONV_CHUNK 128                // rays staged per pass through shared memory
 
+// CONV_PPT probes per thread, CONV_G = 4 * CONV_PPT probes per block (256 threads = 64 texels x 4 probe groups)
+template <int CONV_PPT>
 __global__ void __launch_bounds__(256) k_probe_convolve_fast(const ConvFastCtx f) {
+  constexpr int CONV_G = 4 * CONV_PPT;
   const ConvCtx& c = f.c;
   __shared__ float4 sRad[CONV_G * CONV_CHUNK];                      // 32 KB
   const int P = c.nXZ * c.nXZ;
@@ -267,8 +268,13 @@ static cudaError_t launch_convolve_impl(const ConvFastCtx& f, cudaStream_t s) {
   const uint32_t nw = (uint32_t)c.numLayers * (uint32_t)c.N;
   if (nw == 0) return cudaSuccess;
   k_conv_weights<<<(8u * nw + 127u) / 128u, 128, 0, s>>>(f);
-  const uint32_t blocks = (uint32_t)c.numLayers * (uint32_t)((c.Pl + CONV_G - 1) / CONV_G);
-  k_probe_convolve_fast<<<blocks, 256, 0, s>>>(f);
+  static int ppt = 0;              // probes per thread: sweeps only (DDGI_CONV_PPT)
+  if (!ppt) { const char* e = getenv("DDGI_CONV_PPT"); ppt = e ? atoi(e) : 4; }
+  const int G = 4 * (ppt == 2 ? 2 : ppt == 1 ? 1 : 4);
+  const uint32_t blocks = (uint32_t)c.numLayers * (uint32_t)((c.Pl + G - 1) / G);
+  if (ppt == 2) k_probe_convolve_fast<2><<<blocks, 256, 0, s>>>(f);
+  else if (ppt == 1) k_probe_convolve_fast<1><<<blocks, 256, 0, s>>>(f);
+  else k_probe_convolve_fast<4><<<blocks, 256, 0, s>>>(f);
   return cudaGetLastError();
 }
 

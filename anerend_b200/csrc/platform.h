@@ -100,6 +100,13 @@ HD void atomMin64(unsigned long long* p, unsigned long long v) {
   if (v < *p) *p = v;
 #endif
 }
+HD void atomMax64(unsigned long long* p, unsigned long long v) {
+#ifdef __CUDA_ARCH__
+  if (v > *p) atomicMax(p, v);
+#else
+  if (v > *p) *p = v;
+#endif
+}
 HD void atomMax(int* p, int v) {
 #ifdef __CUDA_ARCH__
   atomicMax(p, v);

@@ -73,7 +73,8 @@ def test_full_update_matches_oracle(name, kernels, oracle, make_gpu):
     st = g.stats()
     assert st["primary_rays"] == 3 * nxz * nxz * ny * nr
     so = o.stats()
-    assert st["primary_hits"] == so["primary_hits"] and st["shadow_rays"] == so["shadow_rays"]
+    # every shadow ray of the oracle is either traced or answered by a light map (csrc/ddgi_kernels.cuh "Light maps")
+    assert st["primary_hits"] == so["primary_hits"] and st["shadow_rays"] + st["shadow_rays_prefiltered"] == so["shadow_rays"]
     o.close()
     g.close()
 

@@ -201,3 +201,58 @@ def test_cuda_maps_equal_the_serial_rasteriser(make_gpu, make_emu):
     assert e.stats()["shadow_rays_prefiltered"] == g.stats()["shadow_rays_prefiltered"]
     e.close()
     g.close()
+
+
+# ------------------------------------------------------------------------------------------------------------ the sun's map
+def _sun_sequence(scene, grid, make_o, make_p, dirs, move=False):
+    """Updates under a changing sun direction (the map is re-made for each), optionally with moving instances in between."""
+    nxz, ny, nr = grid
+    p = make_params(nxz, ny, nr, flags=FLAGS)
+    o, g = make_o(p), make_p(p)
+    rots = parity.setup_pair(scene, (o, g), seed=11)
+    for k, d in enumerate(dirs):
+        ubo = scene.ubo.copy()
+        ubo["light_dir"][0][:3] = d
+        rend = scene.animated_renderables(0.3 * (k + 1)) if move else None
+        for h in (o, g):
+            h.set_scene_ubo(ubo)
+            if move:
+                h.refit_accel(rend)
+            h.update(-1, rots)
+        for layer in range(ny):
+            ro, rg = o.download_ray_records(layer), g.download_ray_records(layer)
+            assert np.array_equal(ro["prim"], rg["prim"]) and np.array_equal(ro["lit_mask"], rg["lit_mask"]), f"sun direction {d}: lit masks differ"
+        assert np.array_equal(o.download_atlas(), g.download_atlas())
+    st = g.stats()
+    o.close()
+    g.close()
+    return st
+
+
+SUN_DIRS = [(0.3, -1.0, 0.2), (0.0, -1.0, 0.0), (-0.7, -0.4, 0.6), (1.0, -0.05, 0.0), (0.2, 1.0, 0.1), (0.0, 0.0, 0.0)]
+
+
+def test_sun_map_follows_the_light_direction(oracle, make_emu):
+    """Steep, vertical (the frame's up-vector switches), grazing, from-below and zero directions; sun-only flags so every answered
+    ray is the sun's."""
+    scene = scenes.sponza_like(seed=8, grid=(6, 3, 64), curtain_res=8)
+    st = _sun_sequence(scene, (6, 3, 64), oracle.Oracle, make_emu, SUN_DIRS)
+    assert st["shadow_rays_prefiltered"] > 0
+
+
+def test_sun_map_with_moving_instances_and_a_moving_sun(oracle, make_emu):
+    scene = scenes.sponza_like(seed=4, grid=(6, 3, 64), movers=6, curtain_res=6)
+    _sun_sequence(scene, (6, 3, 64), oracle.Oracle, make_emu, [(0.3, -1.0, 0.2), (0.3, -1.0, 0.2), (0.35, -1.0, 0.2), (0.35, -1.0, 0.2), (-0.5, -0.6, 0.1)], move=True)
+
+
+@pytest.mark.gpu
+def test_cuda_sun_map_follows_the_light_direction(oracle, make_gpu):
+    scene = scenes.sponza_like(seed=8, grid=(6, 3, 64), curtain_res=8)
+    st = _sun_sequence(scene, (6, 3, 64), oracle.Oracle, make_gpu, SUN_DIRS)
+    assert st["shadow_rays_prefiltered"] > 0
+
+
+@pytest.mark.gpu
+def test_cuda_sun_map_with_moving_instances_and_a_moving_sun(oracle, make_gpu):
+    scene = scenes.sponza_like(seed=4, grid=(6, 3, 64), movers=6, curtain_res=6)
+    _sun_sequence(scene, (6, 3, 64), oracle.Oracle, make_gpu, [(0.3, -1.0, 0.2), (0.3, -1.0, 0.2), (0.35, -1.0, 0.2), (0.35, -1.0, 0.2), (-0.5, -0.6, 0.1)], move=True)
