@@ -259,6 +259,10 @@ class DdgiHandle:
         self._call("download_atlas_stripe", _ptr(out), C.c_size_t(out.nbytes))
         return out
 
+    def download_atlas_stripe_async(self, out):
+        """The same stripe on the read-back stream (download_wait() blocks until it has landed); `out` page-locked."""
+        self._call("download_atlas_stripe_async", _ptr(out), C.c_size_t(out.nbytes))
+
     def download_atlas_layers(self, layers, out=None):
         """Atlas rows of the given Y-layers, packed: uint16 [len(layers), 10*nXZ, W, 4]."""
         layers = _c(layers, np.int32).reshape(-1)

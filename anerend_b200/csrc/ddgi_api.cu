@@ -46,6 +46,7 @@ DDGI_KERNEL(k_specular_gi, specular_gi_body, SpecularCtx)
 DDGI_KERNEL(k_atlas_clear, clear_body, ClearCtx)
 DDGI_KERNEL(k_lightmap_raster_serial, lightmap_raster_body, LmBuildCtx)
 DDGI_KERNEL(k_lightmap_moved, lm_moved_body, LmMovedCtx)
+DDGI_KERNEL(k_vis_changed, vis_changed_body, VisCtx)
 DDGI_KERNEL(k_sunmap_raster_serial, sunmap_raster_body, SunMapCtx)
 
 // ------------------------------------------------------------------------------------------------ handle
@@ -106,6 +107,8 @@ struct anerend_ddgi {
   // ShadowRT scratch (pixels): staged positions, visibility words, ray queue, counters
   float4* dExtRays = nullptr; float* dExtDist = nullptr; uint32_t extPixels = 0;      // SpecularGIRT: staged rays, hit distances
   float4* dSrtPos = nullptr; uint32_t* dSrtLit = nullptr; uint32_t* dSrtQueue = nullptr; uint32_t* dSrtQcount = nullptr; uint32_t srtPixels = 0; int srtGrid = 0;
+  void* dBigItems = nullptr; uint32_t* dBigCount = nullptr;           // queue of large light-map footprints (k_lightmap_raster_big)
+  uint32_t* dSelected = nullptr; uint32_t* dVisChanged = nullptr;      // per renderable: in the structure (tlas_update.comp:41-47); device flag of refit_accel_device
   // light maps (ddgi_kernels.cuh): static + dynamic distance cube maps per point light, the transforms the static map was made with
   unsigned long long* dLmStatic = nullptr; unsigned long long* dLmDynamic = nullptr; uint32_t* dLmNear = nullptr; InstXform* dLmBase = nullptr; uint32_t* dLmMoved = nullptr;
   uint32_t lmRes = 0, lmLights = 0; bool lmDynamicValid = false; float lmMs = 0.0f;
@@ -233,68 +236,133 @@ int clearAtlas(anerend_ddgi* h) {
 // footprints spread over the warp (a footprint is a few dozen texels at R = 512, but a triangle next to a light covers a
 // whole face: per-thread loops would leave one lane running for milliseconds).  The lane whose footprint is being filled
 // hands its parameters to the warp through shared memory.
-struct LmItem { int x0, x1, y0, y1; V3 n; float h, daabb; uint32_t skinny, tid; LmEdges ed; };
-__global__ void __launch_bounds__(256) k_lightmap_raster(const LmBuildCtx c) {
-  __shared__ LmItem sItem[8];
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, li = blockIdx.y, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+// Footprints of more than LM_BIG_TEXELS texels (a triangle next to a light covers a whole face, a wall made of two triangles
+// thousands of texels of the sun's map; a mover among the lights hundreds) are not filled by the warp that found them — it would run for milliseconds while the
+// rest of the GPU idles — but appended to a queue that a second launch fills with one block per footprint.
+#define LM_BIG_TEXELS 256
+#define LM_BIG_CAP 65536u
+struct LmItem { int x0, x1, y0, y1; V3 n; float h, daabb; uint32_t skinny, tid, face, light; LmEdges ed; };
+struct SmItem { int x0, x1, y0, y1; float smax, ga, gb, pa0, pb0, ps0; uint32_t flat, tid; LmEdges ed; };
+struct BigQueue { void* items; uint32_t* count; };
+__device__ __forceinline__ void lm_fill(const LmItem& w, const LmBuildCtx& c, uint32_t first, uint32_t step) {
+  unsigned long long* dm = c.depth + ((size_t)w.light * 6u + (size_t)w.face) * c.R * c.R;
+  const int wdt = w.x1 - w.x0 + 1, cnt = wdt * (w.y1 - w.y0 + 1);
+  for (int k = (int)first; k < cnt; k += (int)step) {
+    const int lx = k % wdt, ly = k / wdt;
+    if (lm_edges_touch(w.ed, lx, ly))
+      atomMin64(dm + (size_t)(w.y0 + ly) * c.R + (w.x0 + lx),
+                ((unsigned long long)__float_as_uint(lm_texel_bound(w.n, w.h, w.daabb, w.skinny != 0u, (int)w.face, w.x0 + lx, w.y0 + ly, c.R, c.rho)) << 32) | w.tid);
+  }
+}
+__device__ __forceinline__ void lm_raster_thread(const LmBuildCtx& c, const BigQueue& big, uint32_t t, bool valid, uint32_t li, LmItem* sItem) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   LmTri tri;
   tri.n = mk3(0.0f); tri.h = 0.0f; tri.daabb = 0.0f; tri.skinny = false; tri.nearLight = false;
-  const bool ok = t < c.numTris && lm_pair_setup(c, t, li, tri);
+  const bool ok = valid && lm_pair_setup(c, t, li, tri);
   if (ok && tri.nearLight) c.nearFlags[li] = 1u;
   for (int face = 0; face < 6; ++face) {
     LmItem it; it.x0 = 0; it.x1 = -1; it.y0 = 0; it.y1 = -1; it.ed.use = false;
-    const bool reach = ok && lm_face_rect(tri, face, c.R, it.x0, it.x1, it.y0, it.y1, it.ed);
-    unsigned long long* dm = c.depth + ((size_t)li * 6u + (size_t)face) * c.R * c.R;
+    bool reach = ok && lm_face_rect(tri, face, c.R, it.x0, it.x1, it.y0, it.y1, it.ed);
+    if (reach) { it.n = tri.n; it.h = tri.h; it.daabb = tri.daabb; it.skinny = tri.skinny ? 1u : 0u; it.tid = t; it.face = (uint32_t)face; it.light = li; }
+    if (reach && (it.x1 - it.x0 + 1) * (it.y1 - it.y0 + 1) > LM_BIG_TEXELS) {
+      const uint32_t slot = atomicAdd(big.count, 1u);
+      if (slot < LM_BIG_CAP) { reinterpret_cast<LmItem*>(big.items)[slot] = it; reach = false; }      // queue full: filled here after all
+    }
     for (uint32_t m = __ballot_sync(0xFFFFFFFFu, reach); m != 0u; m &= m - 1u) {
       const uint32_t src = (uint32_t)__ffs((int)m) - 1u;
       __syncwarp();
-      if (lane == src) { it.n = tri.n; it.h = tri.h; it.daabb = tri.daabb; it.skinny = tri.skinny ? 1u : 0u; it.tid = t; sItem[warp] = it; }
+      if (lane == src) sItem[warp] = it;
       __syncwarp();
-      const LmItem& w = sItem[warp];
-      const int bx0 = w.x0, by0 = w.y0, wdt = w.x1 - w.x0 + 1, cnt = wdt * (w.y1 - w.y0 + 1);
-      const V3 n = w.n; const float hh = w.h, da = w.daabb; const bool sk = w.skinny != 0u; const uint32_t tid = w.tid;
-      const LmEdges ed = w.ed;
-      for (int k = (int)lane; k < cnt; k += 32) {
-        const int lx = k % wdt, ly = k / wdt;
-        if (lm_edges_touch(ed, lx, ly))
-          atomMin64(dm + (size_t)(by0 + ly) * c.R + (bx0 + lx), ((unsigned long long)__float_as_uint(lm_texel_bound(n, hh, da, sk, face, bx0 + lx, by0 + ly, c.R, c.rho)) << 32) | tid);
-      }
+      lm_fill(sItem[warp], c, lane, 32u);
     }
   }
 }
-struct SmItem { int x0, x1, y0, y1; float smax, ga, gb, pa0, pb0, ps0; uint32_t flat, tid; LmEdges ed; };
-__global__ void __launch_bounds__(256) k_sunmap_raster(const SunMapCtx c) {
-  __shared__ SmItem sItem[8];
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+// one thread per (triangle, light of blockIdx.y); the dynamic pass runs over all triangles too and the threads of instances that have
+// not moved leave at once (a launch over the movers only — one block per instance — was slower: the fill is latency bound and a
+// few blocks keep too few warps in flight)
+__global__ void __launch_bounds__(256) k_lightmap_raster(const LmBuildCtx c, const BigQueue big) {
+  __shared__ LmItem sItem[8];
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  lm_raster_thread(c, big, t, t < c.numTris, blockIdx.y, sItem);
+}
+__global__ void __launch_bounds__(256) k_lightmap_raster_big(const LmBuildCtx c, const BigQueue big) {
+  __shared__ LmItem sIt;
+  const uint32_t n = min(*big.count, LM_BIG_CAP);
+  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x == 0) sIt = reinterpret_cast<const LmItem*>(big.items)[i];
+    __syncthreads();
+    lm_fill(sIt, c, threadIdx.x, blockDim.x);
+  }
+}
+__device__ __forceinline__ void sm_fill(const SmItem& w, const SunMapCtx& c, uint32_t first, uint32_t step) {
+  const int wdt = w.x1 - w.x0 + 1, cnt = wdt * (w.y1 - w.y0 + 1);
+  for (int k = (int)first; k < cnt; k += (int)step) {
+    const int lx = k % wdt, ly = k / wdt;
+    if (lm_edges_touch(w.ed, lx, ly))
+      atomMax64(c.height + (size_t)(w.y0 + ly) * c.R + (w.x0 + lx),
+                sm_pack(sm_texel_bound(w.smax, w.ga, w.gb, w.pa0, w.pb0, w.ps0, w.flat != 0u, w.x0 + lx, w.y0 + ly, c.orgA, c.orgB, c.cell), c.base, w.tid));
+  }
+}
+__device__ __forceinline__ void sm_raster_thread(const SunMapCtx& c, const BigQueue& big, uint32_t t, bool valid, SmItem* sItem) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   SmTri tri; SmItem it; it.x0 = 0; it.x1 = -1; it.y0 = 0; it.y1 = -1; it.ed.use = false;
   tri.smax = 0.0f; tri.ga = 0.0f; tri.gb = 0.0f; tri.flat = false; tri.pa[0] = 0.0f; tri.pb[0] = 0.0f; tri.ps[0] = 0.0f;
-  const bool reach = t < c.numTris && sm_tri_setup(c, t, tri, it.x0, it.x1, it.y0, it.y1, it.ed);
+  bool reach = valid && sm_tri_setup(c, t, tri, it.x0, it.x1, it.y0, it.y1, it.ed);
+  if (reach) { it.smax = tri.smax; it.ga = tri.ga; it.gb = tri.gb; it.pa0 = tri.pa[0]; it.pb0 = tri.pb[0]; it.ps0 = tri.ps[0]; it.flat = tri.flat ? 1u : 0u; it.tid = t; }
+  if (reach && (it.x1 - it.x0 + 1) * (it.y1 - it.y0 + 1) > LM_BIG_TEXELS) {
+    const uint32_t slot = atomicAdd(big.count, 1u);
+    if (slot < LM_BIG_CAP) { reinterpret_cast<SmItem*>(big.items)[slot] = it; reach = false; }
+  }
   for (uint32_t m = __ballot_sync(0xFFFFFFFFu, reach); m != 0u; m &= m - 1u) {
     const uint32_t src = (uint32_t)__ffs((int)m) - 1u;
     __syncwarp();
-    if (lane == src) { it.smax = tri.smax; it.ga = tri.ga; it.gb = tri.gb; it.pa0 = tri.pa[0]; it.pb0 = tri.pb[0]; it.ps0 = tri.ps[0]; it.flat = tri.flat ? 1u : 0u; it.tid = t; sItem[warp] = it; }
+    if (lane == src) sItem[warp] = it;
     __syncwarp();
-    const SmItem& w = sItem[warp];
-    const int bx0 = w.x0, by0 = w.y0, wdt = w.x1 - w.x0 + 1, cnt = wdt * (w.y1 - w.y0 + 1);
-    const float smax = w.smax, ga = w.ga, gb = w.gb, pa0 = w.pa0, pb0 = w.pb0, ps0 = w.ps0; const bool flat = w.flat != 0u; const uint32_t tid = w.tid;
-    const LmEdges ed = w.ed;
-    for (int k = (int)lane; k < cnt; k += 32) {
-      const int lx = k % wdt, ly = k / wdt;
-      if (lm_edges_touch(ed, lx, ly))
-        atomMax64(c.height + (size_t)(by0 + ly) * c.R + (bx0 + lx), sm_pack(sm_texel_bound(smax, ga, gb, pa0, pb0, ps0, flat, bx0 + lx, by0 + ly, c.orgA, c.orgB, c.cell), c.base, tid));
-    }
+    sm_fill(sItem[warp], c, lane, 32u);
   }
+}
+__global__ void __launch_bounds__(256) k_sunmap_raster(const SunMapCtx c, const BigQueue big) {
+  __shared__ SmItem sItem[8];
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  sm_raster_thread(c, big, t, t < c.numTris, sItem);
+}
+__global__ void __launch_bounds__(256) k_sunmap_raster_big(const SunMapCtx c, const BigQueue big) {
+  __shared__ SmItem sIt;
+  const uint32_t n = min(*big.count, LM_BIG_CAP);
+  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x == 0) sIt = reinterpret_cast<const SmItem*>(big.items)[i];
+    __syncthreads();
+    sm_fill(sIt, c, threadIdx.x, blockDim.x);
+  }
+}
+#endif
+#ifndef DDGI_HOST_EMU
+__global__ void __launch_bounds__(256) k_zero_words(uint32_t* p, uint32_t n);
+int ensureBigQueue(anerend_ddgi* h) {
+  if (h->dBigItems) return 0;
+  const size_t itemBytes = sizeof(LmItem) > sizeof(SmItem) ? sizeof(LmItem) : sizeof(SmItem);
+  BE_CHECK(h, h->be.alloc((uint8_t**)&h->dBigItems, itemBytes * LM_BIG_CAP)); BE_CHECK(h, h->be.alloc(&h->dBigCount, 1));
+  if (h->sms == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, dev); }
+  return 0;
 }
 #endif
 bool mapsEnabled(const anerend_ddgi* h) { return !(h->p.flags & ANEREND_DDGI_FLAG_NO_LIGHT_MAPS) && h->numTris != 0; }
 int rasterSunMap(anerend_ddgi* h, unsigned long long* target, const uint32_t* moved) {
   Backend& be = h->be;
-  BE_CHECK(h, be.zero(target, (size_t)h->smRes * h->smRes * sizeof(unsigned long long)));
+  const uint32_t R = moved ? h->smRes >> LM_DYN_SHIFT : h->smRes;          // the dynamic map is coarser: same frame, cells 2^shift times as wide
+  BE_CHECK(h, be.zero(target, (size_t)R * R * sizeof(unsigned long long)));
   SunMapCtx c = h->sm;
-  c.wtri = h->dWtri; c.triInstance = h->dTriInstance; c.moved = moved; c.numTris = h->numTris; c.R = h->smRes; c.height = target;
+  if (moved) { c.cell = h->sm.cell * (float)(1u << LM_DYN_SHIFT); c.invCell = h->sm.invCell / (float)(1u << LM_DYN_SHIFT); }
+  c.wtri = h->dWtri; c.triInstance = h->dTriInstance; c.moved = moved; c.numTris = h->numTris; c.R = R; c.height = target;
 #ifndef DDGI_HOST_EMU
-  k_sunmap_raster<<<(h->numTris + 255u) / 256u, 256, 0, be.stream>>>(c);
-  ++be.launches;
+  { int rq = ensureBigQueue(h); if (rq) return rq; }
+  const BigQueue big{h->dBigItems, h->dBigCount};
+  k_zero_words<<<1, 32, 0, be.stream>>>(h->dBigCount, 1u);
+  k_sunmap_raster<<<(h->numTris + 255u) / 256u, 256, 0, be.stream>>>(c, big);
+  k_sunmap_raster_big<<<4 * (h->sms > 0 ? h->sms : 148), 256, 0, be.stream>>>(c, big);
+  be.launches += 3;
 #else
   DDGI_LAUNCH(be, k_sunmap_raster_serial, sunmap_raster_body, h->numTris, c, 256);
 #endif
@@ -305,20 +373,26 @@ uint32_t lightMapResolution(const anerend_ddgi* h) {
   if (!(h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) || !mapsEnabled(h) || h->numLights == 0) return 0;
   uint32_t r = 512;
   if (const char* e = getenv("DDGI_LM_RES")) r = (uint32_t)atoi(e);          // sweeps only; 0 disables the maps
-  return r > 4096u ? 4096u : r;
+  r = r > 4096u ? 4096u : r;
+  return r & ~((1u << LM_DYN_SHIFT) - 1u) ? (r & ~((1u << LM_DYN_SHIFT) - 1u)) : 0u;      // a multiple of the dynamic maps' coarsening
 }
 // Rasterises the triangles into the light maps: all of them into the static map (after build_accel, or when vertices
 // changed), or only those of moved instances into the dynamic map (refit).
 int rasterLightMap(anerend_ddgi* h, unsigned long long* target, const uint32_t* moved) {
   Backend& be = h->be;
-  const size_t texels = (size_t)h->lmLights * 6u * h->lmRes * h->lmRes;
+  const uint32_t R = moved ? h->lmRes >> LM_DYN_SHIFT : h->lmRes;          // the dynamic map is coarser (LM_DYN_SHIFT)
+  const size_t texels = (size_t)h->lmLights * 6u * R * R;
   BE_CHECK(h, be.fill(target, 0x7F, texels * sizeof(unsigned long long)));
   LmBuildCtx c{};
   c.wtri = h->dWtri; c.triInstance = h->dTriInstance; c.moved = moved; c.lights = h->dLights; c.numTris = h->numTris; c.numLights = h->lmLights;
-  c.R = h->lmRes; c.rho = lm_rho(h->lmRes); c.depth = target; c.nearFlags = h->dLmNear;
+  c.R = R; c.rho = lm_rho(R); c.depth = target; c.nearFlags = h->dLmNear;
 #ifndef DDGI_HOST_EMU
-  k_lightmap_raster<<<dim3((h->numTris + 255u) / 256u, h->lmLights), 256, 0, be.stream>>>(c);
-  ++be.launches;
+  { int rq = ensureBigQueue(h); if (rq) return rq; }
+  const BigQueue big{h->dBigItems, h->dBigCount};
+  k_zero_words<<<1, 32, 0, be.stream>>>(h->dBigCount, 1u);
+  k_lightmap_raster<<<dim3((h->numTris + 255u) / 256u, h->lmLights), 256, 0, be.stream>>>(c, big);
+  k_lightmap_raster_big<<<4 * (h->sms > 0 ? h->sms : 148), 256, 0, be.stream>>>(c, big);
+  be.launches += 3;
 #else
   DDGI_LAUNCH(be, k_lightmap_raster_serial, lightmap_raster_body, h->numTris * h->lmLights, c, 256);
 #endif
@@ -355,12 +429,12 @@ int refitLightMaps(anerend_ddgi* h, bool verticesChanged) {
   DDGI_LAUNCH(be, k_lightmap_moved, lm_moved_body, ni, mc, 128);
   h->lmMovedValid = true;
   if (h->lmRes) {
-    if (!h->dLmDynamic) BE_CHECK(h, be.alloc(&h->dLmDynamic, (size_t)h->lmLights * 6u * h->lmRes * h->lmRes));
+    if (!h->dLmDynamic) BE_CHECK(h, be.alloc(&h->dLmDynamic, (size_t)h->lmLights * 6u * (h->lmRes >> LM_DYN_SHIFT) * (h->lmRes >> LM_DYN_SHIFT)));
     h->lmDynamicValid = true;
     int rc = rasterLightMap(h, h->dLmDynamic, h->dLmMoved); if (rc) return rc;
   }
   if (h->smValid) {
-    if (!h->dSmDynamic) BE_CHECK(h, be.alloc(&h->dSmDynamic, (size_t)h->smRes * h->smRes));
+    if (!h->dSmDynamic) BE_CHECK(h, be.alloc(&h->dSmDynamic, (size_t)(h->smRes >> LM_DYN_SHIFT) * (h->smRes >> LM_DYN_SHIFT)));
     h->smDynamicValid = true;
     int rc = rasterSunMap(h, h->dSmDynamic, h->dLmMoved); if (rc) return rc;
   }
@@ -373,6 +447,7 @@ int ensureSunMap(anerend_ddgi* h) {
   uint32_t R = 2048;
   if (const char* e = getenv("DDGI_SM_RES")) R = (uint32_t)atoi(e);          // sweeps only; 0 disables the map
   if (R > 8192u) R = 8192u;
+  R &= ~((1u << LM_DYN_SHIFT) - 1u);
   if (R == 0) { h->smValid = false; return 0; }
   const float* ld = h->ubo.light_dir;
   if (h->smValid && h->smRes == R && ld[0] == h->smDir[0] && ld[1] == h->smDir[1] && ld[2] == h->smDir[2]) return 0;
@@ -415,6 +490,13 @@ int buildAccel(anerend_ddgi* h) {
   int rc = selectInstances(h, inst, n); if (rc) return rc;
   h->instances = inst; h->numTris = n;
   const uint32_t ni = (uint32_t)inst.size();
+  { // the selection this structure is built from, for refit_accel_device's check of GPU-written visibility / cull bits
+    std::vector<uint32_t> sel(h->renderables.size());
+    for (size_t i = 0; i < sel.size(); ++i) { const uint32_t v = h->renderables[i].visible; sel[i] = ((v & 1u) && !((v >> 1) & 1u)) ? 1u : 0u; }
+    be.free(h->dSelected); h->dSelected = nullptr;
+    BE_CHECK(h, be.alloc(&h->dSelected, sel.size()));
+    if (!h->dVisChanged) BE_CHECK(h, be.alloc(&h->dVisChanged, 1));
+    BE_CHECK(h, be.h2d(h->dSelected, sel.data(), sel.size() * sizeof(uint32_t))); BE_CHECK(h, be.sync()); }
   BE_CHECK(h, be.alloc(&h->dInstances, ni)); BE_CHECK(h, be.alloc(&h->dXforms, ni)); BE_CHECK(h, be.alloc(&h->dTriInstance, n));
   BE_CHECK(h, be.h2d(h->dInstances, inst.data(), ni * sizeof(DInstance)));
   { std::vector<uint32_t> ti(n); for (uint32_t i = 0; i < ni; ++i) for (uint32_t t = 0; t < inst[i].numTris; ++t) ti[inst[i].firstTri + t] = i;
@@ -744,7 +826,7 @@ TraceCtx sceneTraceCtx(anerend_ddgi* h) {
   c.tmin = h->p.t_min; c.tmax = h->p.t_max; c.sunIntensity = h->ubo.sun_intensity;
   c.uboFlags = h->ubo.flags; c.flags = h->p.flags;
   c.lmRes = h->lmRes; c.lmStatic = h->dLmStatic; c.lmDynamic = h->lmDynamicValid ? h->dLmDynamic : nullptr; c.lmNear = h->dLmNear;
-  c.lmTris = h->dWtri; c.lmNumTris = h->numTris;
+  c.lmTris = h->dWtri; c.lmNumTris = h->numTris; c.lmDynShift = LM_DYN_SHIFT; c.smDynShift = LM_DYN_SHIFT;
   // the sun's map only while it is the map of THIS frame's lightDir (ensureSunMap runs in front of the probe trace)
   if (h->smValid && h->ubo.light_dir[0] == h->smDir[0] && h->ubo.light_dir[1] == h->smDir[1] && h->ubo.light_dir[2] == h->smDir[2]) {
     c.smRes = h->smRes; c.smStatic = h->dSmStatic; c.smDynamic = h->smDynamicValid ? h->dSmDynamic : nullptr;
@@ -885,7 +967,7 @@ void destroyHandle(anerend_ddgi* h) {
   be.waitDownload();
   be.sync();
   exchangeDisconnect(h);
-  be.free(h->dXflags); be.free(h->dXerr);
+  be.free(h->dXflags); be.free(h->dXerr); be.free(h->dSelected); be.free(h->dVisChanged); be.free(h->dBigItems); be.free(h->dBigCount);
   freeAccel(h); freeScene(h);
   be.free(h->dAtlas); be.free(h->dTemp); be.free(h->dRayIrr); be.free(h->dDirs); be.free(h->dFib); be.freeHostPinned(h->hDirs); be.free(h->dRayOrder);
   be.free(h->dLayerMap); be.freeHostPinned(h->hLayerMap);
@@ -898,6 +980,12 @@ void destroyHandle(anerend_ddgi* h) {
   delete h;
 }
 
+// The per-layer entry points (the frame-graph adapter's) carry no cross-GPU barriers: with peers connected a push would land in an
+// atlas another rank is still tracing against.  Sharded updates go through _update / _update_layers, which bracket the exchange.
+int refuseWithPeers(anerend_ddgi* h, const char* what) {
+  if (h->numPeers > 0 || h->xworld > 1) return fail(h, ANEREND_DDGI_E_STATE, std::string(what) + " while a peer exchange is connected: use _update or _update_layers");
+  return 0;
+}
 void beginCall(anerend_ddgi* h) { h->be.launches = 0; h->timed[0] = h->timed[1] = h->timed[2] = false; h->timedKernels = false; h->be.mark(0); }
 
 }  // namespace
@@ -912,6 +1000,9 @@ int DDGI_API(create)(const anerend_ddgi_params_t* params, anerend_ddgi_t** out) 
   int sx, sy; if (rayTile(q.rays_per_probe, sx, sy)) return ANEREND_DDGI_E_INVALID;
   if (q.slab_begin < 0 || q.slab_end > q.num_probes_y || q.slab_begin >= q.slab_end) return ANEREND_DDGI_E_INVALID;
   if (!(q.probe_step[0] > 0.0f && q.probe_step[1] > 0.0f && q.probe_step[2] > 0.0f)) return ANEREND_DDGI_E_INVALID;
+  // ray indices, atlas addresses and queue offsets are 32-bit on the device
+  if ((uint64_t)q.num_probes_xz * q.num_probes_xz * q.num_probes_y * q.rays_per_probe >= (1ull << 31) ||
+      (uint64_t)q.num_probes_xz * q.num_probes_xz * q.num_probes_y * 100ull >= (1ull << 31)) return ANEREND_DDGI_E_INVALID;
   anerend_ddgi* h = new anerend_ddgi();
   h->p = q; h->nXZ = q.num_probes_xz; h->nY = q.num_probes_y; h->N = q.rays_per_probe; h->Sx = sx; h->Sy = sy;
   h->W = 10 * h->nXZ; h->H = 10 * h->nXZ * h->nY; h->P = h->nXZ * h->nXZ; h->Pl = h->P;
@@ -1036,7 +1127,6 @@ int DDGI_API(upload_scene)(anerend_ddgi_t* h,
     if (ti < 0 || (uint32_t)ti >= h->numTextures) return fail(h, ANEREND_DDGI_E_INVALID, "material refers to a texture that was not uploaded (upload_textures first)");
     textured = true; emisTex = emisTex || k == 3;
   }
-  h->texturedScene = textured; h->emissiveTextures = emisTex; h->texturesStale = false;
   if ((h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) && nl > 31) return fail(h, ANEREND_DDGI_E_INVALID, "at most 31 point lights with FLAG_POINT_LIGHTS");
   for (uint32_t i = 0; i < nm; ++i) {
     if ((uint64_t)meshes[i].index_offset + meshNumIndices[i] > ni) return fail(h, ANEREND_DDGI_E_INVALID, "mesh index range exceeds the index buffer");
@@ -1046,6 +1136,8 @@ int DDGI_API(upload_scene)(anerend_ddgi_t* h,
       for (uint32_t k = 0; k < meshNumIndices[m]; ++k) if ((uint64_t)vo + indices[meshes[m].index_offset + k] >= nv) return fail(h, ANEREND_DDGI_E_INVALID, "vertex index out of range"); } }
   BE_CHECK(h, be.sync());
   freeAccel(h); freeScene(h);
+  // everything validated: only now does the new scene (and what was learnt about its textures) replace the old one
+  h->texturedScene = textured; h->emissiveTextures = emisTex; h->texturesStale = false;
   BE_CHECK(h, be.alloc(&h->dVertices, nv)); BE_CHECK(h, be.alloc(&h->dIndices, ni)); BE_CHECK(h, be.alloc(&h->dMaterials, nmat));
   BE_CHECK(h, be.alloc(&h->dRenderables, nr)); BE_CHECK(h, be.alloc(&h->dLights, nl));
   BE_CHECK(h, be.h2d(h->dVertices, vertices, (size_t)nv * sizeof(*vertices))); BE_CHECK(h, be.h2d(h->dIndices, indices, (size_t)ni * 4));
@@ -1115,9 +1207,22 @@ int DDGI_API(refit_accel_device)(anerend_ddgi_t* h, const void* dRenderables, ui
   if (!h) return ANEREND_DDGI_E_INVALID;
   if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "refit before build_accel");
   if (!dRenderables || nr != h->renderables.size()) return fail(h, ANEREND_DDGI_E_INVALID, "renderable count changed");
-  // device-written RenderableBuffer (cull.comp:303, particle_update.comp:84-85): transforms are taken as they are,
-  // visibility is assumed unchanged since build_accel
-  BE_CHECK(h, h->be.d2d(h->dRenderables, dRenderables, (size_t)nr * sizeof(anerend_renderable_t)));
+  // device-written RenderableBuffer (cull.comp:296-303 sets the cull bit there every frame, particle_update.comp:84-85 the
+  // transforms): the visible / cull bits are compared with the selection the structure was built from (4 bytes come back); where a
+  // renderable entered or left, the host copy is refreshed and the structure is rebuilt — what UpdateTLASPass.cpp:198-228 does every
+  // frame — otherwise the topology is kept and refitted.
+  Backend& be = h->be;
+  BE_CHECK(h, be.d2d(h->dRenderables, dRenderables, (size_t)nr * sizeof(anerend_renderable_t)));
+  uint32_t changed = 0;
+  BE_CHECK(h, be.zero(h->dVisChanged, sizeof(uint32_t)));
+  VisCtx vc{h->dRenderables, h->dSelected, h->dVisChanged};
+  DDGI_LAUNCH(be, k_vis_changed, vis_changed_body, nr, vc, 128);
+  BE_CHECK(h, be.check()); BE_CHECK(h, be.d2h(&changed, h->dVisChanged, sizeof(uint32_t)));
+  if (changed) {
+    BE_CHECK(h, be.d2h(h->renderables.data(), h->dRenderables, (size_t)nr * sizeof(anerend_renderable_t)));
+    return buildAccel(h);
+  }
+  // transforms of the host copy are not refreshed here: instance selection reads visibility, meshes and materials only
   return refitAccel(h);
 }
 
@@ -1183,6 +1288,7 @@ int DDGI_API(trace_layer)(anerend_ddgi_t* h, int32_t layer, const float rot[16])
   if (!h) return ANEREND_DDGI_E_INVALID;
   if (h->haveUbo && !ddgiOn(h)) return 0;
   if (layer < 0 || layer >= h->nY || !rot) return fail(h, ANEREND_DDGI_E_INVALID, "layer out of range");
+  { int rp = refuseWithPeers(h, "trace_layer"); if (rp) return rp; }
   beginCall(h); h->be.mark(1);
   const int one = layer;
   int rc = traceLayers(h, &one, 1, rot, false); h->be.mark(2); h->timed[1] = true;
@@ -1192,6 +1298,7 @@ int DDGI_API(convolve_layer)(anerend_ddgi_t* h, int32_t layer) {
   if (!h) return ANEREND_DDGI_E_INVALID;
   if (h->haveUbo && !ddgiOn(h)) return 0;
   if (layer < 0 || layer >= h->nY) return fail(h, ANEREND_DDGI_E_INVALID, "layer out of range");
+  { int rp = refuseWithPeers(h, "convolve_layer"); if (rp) return rp; }
   beginCall(h); h->be.mark(2);
   const int one = layer;
   int rc = convolveLayers(h, &one, 1); h->be.mark(3); h->timed[2] = true;
@@ -1234,6 +1341,7 @@ int DDGI_API(update_layers)(anerend_ddgi_t* h, const int32_t* layerList, uint32_
 }
 int DDGI_API(frame)(anerend_ddgi_t* h, const float rot[16], int32_t* layerOut) {
   if (!h) return ANEREND_DDGI_E_INVALID;
+  { int rp = refuseWithPeers(h, "frame"); if (rp) return rp; }
   beginCall(h);
   int rc = translate(h); h->be.mark(1); h->timed[0] = true;
   if (rc) return rc;
@@ -1451,6 +1559,16 @@ int DDGI_API(download_atlas_stripe)(anerend_ddgi_t* h, void* out, size_t bytes) 
       return fail(h, ANEREND_DDGI_E_CUDA, std::string("download_atlas_stripe: ") + h->be.errStr());
   BE_CHECK(h, h->be.sync()); return 0;
 }
+// The stripe on the read-back stream (see _download_atlas_async).  Allowed while a peer exchange is connected: the rows of this
+// handle's stripe are written by its own convolution only (the peers push THEIR rows), and that convolution waits for the copy.
+int DDGI_API(download_atlas_stripe_async)(anerend_ddgi_t* h, void* out, size_t bytes) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
+  const size_t rowBytes = (size_t)10 * h->W * 8, rows = (size_t)(h->Pl / h->nXZ);
+  if (!out || bytes != rowBytes * rows * h->nY) return fail(h, ANEREND_DDGI_E_INVALID, "stripe size mismatch");
+  BE_CHECK(h, h->be.d2hStridedBackground(out, rowBytes * rows, rowBytes, (const char*)h->dAtlas + rowBytes * h->rowOffset, rowBytes * h->nXZ,
+                                         rowBytes * h->rowStride, rowBytes, rows, (size_t)h->nY));
+  return 0;
+}
 int DDGI_API(download_atlas_layers)(anerend_ddgi_t* h, const int32_t* layers, uint32_t n, void* out, size_t bytes) {
   if (!h) return ANEREND_DDGI_E_INVALID;
   const size_t layerBytes = (size_t)h->W * h->W * 8;       // 10*nXZ rows of 10*nXZ RGBA16F texels
@@ -1467,7 +1585,7 @@ int DDGI_API(download_atlas_layers)(anerend_ddgi_t* h, const int32_t* layers, ui
 int DDGI_API(download_atlas_async)(anerend_ddgi_t* h, void* out, size_t bytes) {
   if (!h) return ANEREND_DDGI_E_INVALID;
   if (!out || bytes != (size_t)h->W * h->H * 8) return fail(h, ANEREND_DDGI_E_INVALID, "atlas size mismatch");
-  if (h->xworld > 1) return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "asynchronous read-back with a connected exchange (peers write this atlas)");
+  if (h->xworld > 1 || h->numPeers > 0) return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "asynchronous read-back of the whole atlas while peers write it (use _download_atlas_stripe_async)");
   BE_CHECK(h, h->be.d2hBackground(out, h->dAtlas, bytes)); return 0;
 }
 int DDGI_API(download_wait)(anerend_ddgi_t* h) { if (!h) return ANEREND_DDGI_E_INVALID; BE_CHECK(h, h->be.waitDownload()); return 0; }

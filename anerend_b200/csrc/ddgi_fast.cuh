@@ -21,9 +21,9 @@ namespace ddgi {
 // Tunables of the persistent traversal kernels (FastCtx::tune; DDGI_TUNE="a,b,c" overrides them for sweeps)
 #define TUNE_NODE_STEPS 3           // box-test steps per loop iteration before the triangle rounds
 #define TUNE_REFILL_MIN 4           // refill from the staged batch once this many lanes are idle
-#define TUNE_STEP_MIN 16            // (nodeSteps > 1) keep stepping only while this many lanes can
+#define TUNE_STEP_MIN 12            // (nodeSteps > 1) keep stepping only while this many lanes can
 #define TUNE_TRI_MIN 8              // (nodeSteps > 1) keep running triangle rounds only while this many lanes hold triangles
-#define FAST_CHUNK 64               // ray indices taken per atomic on the global cursor (two staged batches)
+#define FAST_CHUNK 32               // ray indices taken per atomic on the global cursor (one staged batch: shorter tail at the end of the launch)
 
 // Node-phase state of a ray lives in registers; everything only the triangle rounds touch (direction, parked triangle
 // groups, hit attributes, ray tag) lives in shared memory, so the box test keeps 8 blocks of 128 threads on an SM.
@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
   const uint32_t nodeSteps = max(1u, c.tune[0]), refillMin = max(1u, ANY ? c.tune[2] : c.tune[1]);
   const uint32_t stepMin = max(1u, c.tune[4]), triMin = max(1u, c.tune[5]);
   const uint32_t k64 = c.tune[3];          // 0x64646464, opaque to ptxas on purpose (see planes2)
+  const uint32_t chunk = c.tune[6] ? c.tune[6] : (uint32_t)FAST_CHUNK;
   float4* myDir = &sLane[warp][LS_DIR][lane];
   float4* myRes = &sLane[warp][LS_RES][lane];
   uint4* myPend = reinterpret_cast<uint4*>(&sLane[warp][LS_PEND_A][lane]);      // slot B = myPend + 32
@@ -173,10 +174,10 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
       if (staged == 0u) {
         if (chunkNext == chunkEnd) {
           uint32_t base = 0;
-          if (lane == 0) base = atomicAdd(cursor, (uint32_t)FAST_CHUNK);
+          if (lane == 0) base = atomicAdd(cursor, chunk);
           base = __shfl_sync(0xFFFFFFFFu, base, 0);
           if (base >= total) { exhausted = true; break; }
-          chunkNext = base; chunkEnd = min(base + (uint32_t)FAST_CHUNK, total);
+          chunkNext = base; chunkEnd = min(base + chunk, total);
         }
         const uint32_t n = min(32u, chunkEnd - chunkNext);
         uint32_t nStaged = n;

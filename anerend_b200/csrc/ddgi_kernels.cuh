@@ -608,6 +608,7 @@ struct TraceCtx {
   // light maps (below): conservative distance maps around the point lights that answer "certainly unoccluded" shadow rays
   const unsigned long long* lmStatic; const unsigned long long* lmDynamic; const uint32_t* lmNear; uint32_t lmRes;      // lmRes = 0: none
   const float4* lmTris; uint32_t lmNumTris;      // world triangles by global id (the candidates the map entries name)
+  uint32_t lmDynShift, smDynShift;               // the dynamic maps are coarser: resolution R >> shift (re-made at every refit, see LM_DYN_SHIFT)
   // the sun's map: orthographic, along normalize(-lightDir); entry = (height above smBase, fp32 bits) << 32 | triangle id, kept maximal
   const unsigned long long* smStatic; const unsigned long long* smDynamic; uint32_t smRes;      // smRes = 0: none
   V3 smA, smB, smS; float smOrgA, smOrgB, smInvCell, smBase;
@@ -644,6 +645,8 @@ HD int stripe_probe(int pl, int nXZ, int rowOffset, int rowStride) { return ((pl
 #define LM_EPS_W 1e-4f          // points nearer than this to a face's apex plane are not projected (see LM_NEAR)
 #define LM_NEAR 0.02f           // a triangle this close to a light disables that light's map (lmNear): its projection is unbounded
 #define LM_DELTA 1e-4f          // footprint growth in face coordinates (texel size at R = 512: 3.9e-3)
+#define LM_DYN_SHIFT 2u         // dynamic maps at a quarter of the resolution: movers near a light cover thousands of fine texels each, and their
+                                // maps are re-made at every refit (C4: 16 boxes among the lights, 1.1 ms per refit at full resolution, 0.08 at a quarter)
 #define LM_FAR_BITS 0x7F7F7F7Fu // "nothing here" (3.39e38; as a triangle id: none), the byte pattern of the clearing memset
 struct LmTri { V3 r[3]; V3 n; float h, daabb; bool skinny, nearLight; };
 HD float comp3(V3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
@@ -753,7 +756,11 @@ HD LmEntry lightmap_lookup(const TraceCtx& c, uint32_t li, V3 lp, V3 pos) {
   const int X = (int)fminf(fmaxf(floorf((b * iw + 1.0f) * 0.5f * fr), 0.0f), top), Y = (int)fminf(fmaxf(floorf((cc * iw + 1.0f) * 0.5f * fr), 0.0f), top);
   const size_t o = (((size_t)li * 6u + (size_t)face) * c.lmRes + (size_t)Y) * c.lmRes + (size_t)X;
   unsigned long long v = c.lmStatic[o];
-  if (c.lmDynamic) { const unsigned long long dv = c.lmDynamic[o]; v = dv < v ? dv : v; }      // positive floats order like their bit patterns
+  if (c.lmDynamic) {                                                                            // positive floats order like their bit patterns
+    const uint32_t rd = c.lmRes >> c.lmDynShift;
+    const unsigned long long dv = c.lmDynamic[(((size_t)li * 6u + (size_t)face) * rd + (size_t)(Y >> c.lmDynShift)) * rd + (size_t)(X >> c.lmDynShift)];
+    v = dv < v ? dv : v;
+  }
   e.bound = u2f((uint32_t)(v >> 32)); e.cand = (uint32_t)v;
   return e;
 }
@@ -857,7 +864,10 @@ HD SmEntry sunmap_lookup(const TraceCtx& c, V3 pos) {
   if (!(fx >= 0.0f && fy >= 0.0f && fx < fr && fy < fr)) return e;
   const size_t o = (size_t)fy * c.smRes + (size_t)fx;
   unsigned long long v = c.smStatic[o];
-  if (c.smDynamic) { const unsigned long long dv = c.smDynamic[o]; v = dv > v ? dv : v; }
+  if (c.smDynamic) {
+    const unsigned long long dv = c.smDynamic[(size_t)((uint32_t)fy >> c.smDynShift) * (c.smRes >> c.smDynShift) + (size_t)((uint32_t)fx >> c.smDynShift)];
+    v = dv > v ? dv : v;
+  }
   e.inside = true; e.cand = v ? (uint32_t)v : LM_FAR_BITS;                          // 0 = empty column
   e.top = v ? u2f((uint32_t)(v >> 32)) + c.smBase : -3.0e38f;
   return e;
@@ -867,6 +877,15 @@ HD float sunmap_tmax(const SmEntry& e, float sPos, float tmax) { return e.inside
 HD bool sunmap_candidate_occludes(const TraceCtx& c, const SmEntry& e, V3 pos, V3 dir, float tmin, float tmax) {
   LmEntry le; le.bound = 0.0f; le.cand = e.cand;
   return lightmap_candidate_occludes(c, le, pos, dir, tmin, tmax);
+}
+
+// tlas_update.comp:41-47: a renderable is in the acceleration structure iff it is visible and not culled.  Compares that test on the
+// (GPU-written) renderable buffer with the selection the structure was built from.
+struct VisCtx { const anerend_renderable_t* renderables; const uint32_t* selected; uint32_t* changed; };
+HD void vis_changed_body(uint32_t i, const VisCtx& c) {
+  const uint32_t v = c.renderables[i].visible;
+  const uint32_t sel = ((v & 1u) != 0u && ((v >> 1) & 1u) == 0u) ? 1u : 0u;
+  if (sel != c.selected[i]) *c.changed = 1u;
 }
 
 // instances whose transform differs from the one the static map was rasterised with

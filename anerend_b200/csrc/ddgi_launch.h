@@ -48,6 +48,14 @@ struct Backend {
     downloadPending = true;
     return ok(cudaEventRecord(evDownload, dlStream));
   }
+  // the same for `blocks` strided pieces (rows x width bytes each; source / destination advance by sstep / dstep per block)
+  bool d2hStridedBackground(void* dst, size_t dstep, size_t dpitch, const void* src, size_t sstep, size_t spitch, size_t width, size_t rows, size_t blocks) {
+    if (!ok(cudaEventRecord(evResult, stream)) || !ok(cudaStreamWaitEvent(dlStream, evResult, 0))) return false;
+    for (size_t b = 0; b < blocks; ++b)
+      if (rows && !ok(cudaMemcpy2DAsync((char*)dst + dstep * b, dpitch, (const char*)src + sstep * b, spitch, width, rows, cudaMemcpyDeviceToHost, dlStream))) return false;
+    downloadPending = true;
+    return ok(cudaEventRecord(evDownload, dlStream));
+  }
   bool fenceDownload() { return !downloadPending || ok(cudaStreamWaitEvent(stream, evDownload, 0)); }   // device-side: stream waits, host does not
   bool waitDownload() { if (!downloadPending) return true; downloadPending = false; return ok(cudaEventSynchronize(evDownload)); }
   void destroy() {
@@ -119,6 +127,10 @@ struct Backend {
   void waitCopy() {}
   void markCopy() {}
   bool d2hBackground(void* d, const void* s, size_t b) { if (b) memcpy(d, s, b); return true; }
+  bool d2hStridedBackground(void* d, size_t dstep, size_t dp, const void* s, size_t sstep, size_t sp, size_t w, size_t rows, size_t blocks) {
+    for (size_t b = 0; b < blocks; ++b) d2hStrided((char*)d + dstep * b, dp, (const char*)s + sstep * b, sp, w, rows);
+    return true;
+  }
   bool fenceDownload() { return true; }
   bool waitDownload() { return true; }
   template <class T> bool alloc(T** p, size_t count) { *p = (T*)calloc(count ? count : 1, sizeof(T)); return *p != nullptr; }

@@ -95,14 +95,14 @@ HD void atomMin(int* p, int v) {
 }
 HD void atomMin64(unsigned long long* p, unsigned long long v) {
 #ifdef __CUDA_ARCH__
-  if (v < *p) atomicMin(p, v);
+  atomicMin(p, v);              // result unused: a fire-and-forget reduction, no round trip to wait for
 #else
   if (v < *p) *p = v;
 #endif
 }
 HD void atomMax64(unsigned long long* p, unsigned long long v) {
 #ifdef __CUDA_ARCH__
-  if (v > *p) atomicMax(p, v);
+  atomicMax(p, v);
 #else
   if (v > *p) *p = v;
 #endif

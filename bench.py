@@ -47,7 +47,9 @@ def workload_desc(name, scene, grid, world):
     return {"workload": name, "scene": scene.name, "triangles": int(scene.num_triangles),
             "probes": f"{nxz}x{ny}x{nxz}", "rays_per_probe": nr, "primary_rays_per_update": nxz * nxz * ny * nr,
             "lights": int(len(scene.lights)), "point_lights_E1": True, "multi_bounce": True, "dead_shadow_rays_skipped": True,
-            "mode": "jacobi full-grid update", "parallelism": f"probe layers dealt to {world} ranks" if world > 1 else "single GPU"}
+            "mode": "jacobi full-grid update", "parallelism": f"probe layers dealt to {world} ranks" if world > 1 else "single GPU",
+            # timing rule of the CUDA arm (the CPU arm has no device cache to flush; the key is kept so both arms print the same config)
+            "l2": "working set larger than L2, no flush" if name == "c5" else "flushed between timed iterations (256 MiB write)"}
 
 
 def peaks():
@@ -186,10 +188,16 @@ def run_config1(dev, cpu_baseline=True):
     return out
 
 
+def sample_layers(name, ny):
+    """The Y-layers one CPU step covers: the whole grid where that takes about a second (c2, c3, c4), every 8th layer of c5 (an
+    equal-weight sample over the height of the volume).  Used by BOTH CPU figures (--impl reference and cpu_baseline)."""
+    return list(range(ny)) if name != "c5" else list(range(0, ny, 8))
+
+
 def reference_arm(args, rank, world):
     """The reference's CPU implementation of the path = the oracle (the path itself — GLSL + Vulkan RT — cannot be built here;
-    oracle/_ref only holds the reference's struct headers and glm::rotate).  Rank 0 alone runs; each step is a bounded sample
-    (one Y-layer) of the workload."""
+    oracle/_ref only holds the reference's struct headers and glm::rotate).  Rank 0 alone runs; each step is one pass over
+    sample_layers() of the workload — the same measurement as the `cpu_baseline` leg of the CUDA arm."""
     if rank != 0:
         return
     name = args.workload or ("c3" if world == 1 else "c5")
@@ -203,20 +211,26 @@ def reference_arm(args, rank, world):
     o.set_scene_ubo(scene.ubo)
     o.build_accel()
     rots = o.rotations(scenes.rotation_sequence(scene.seed, ny))
-    per_step = nxz * nxz * nr
-    for w in range(args.warmup):
-        o.update(w % ny, rots[w % ny])
+    layers = sample_layers(name, ny)
+    per_step = len(layers) * nxz * nxz * nr
+    steps, warmup = min(args.steps, 20), min(args.warmup, 3)       # bounded: a step is 0.3 - 5 s of CPU work
+    for w in range(warmup):
+        for layer in layers:
+            o.update(layer, rots[layer])
     t0 = time.perf_counter()
-    for k in range(args.steps):
-        o.update(k % ny, rots[k % ny])
+    for k in range(steps):
+        for layer in layers:
+            o.update(layer, rots[layer])
     dt = time.perf_counter() - t0
-    value = per_step * args.steps / dt / 1e6
-    sample = f"{args.steps} steps x 1 Y-layer ({per_step} primary rays + their shadow rays) of {name}"
+    value = per_step * steps / dt / 1e6
+    sample = (f"{steps} steps x {len(layers)} of {ny} Y-layers ({per_step} primary rays + their shadow rays per step) of {name}, "
+              f"multithreaded C++ oracle (shader transliteration)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_desc(name, scene, grid, 1),
+            "warmup": args.warmup, "ms_per_step": dt / steps * 1e3 * (ny / len(layers)), "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_desc(name, scene, grid, world),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "steps_timed": steps, "note": "ms_per_step is scaled to a full-grid update where a step covers a sample of the layers"}
     print(json.dumps(line), flush=True)
 
 
@@ -430,14 +444,15 @@ def main():
     for k in range(e2e_steps):
         step(args.warmup + (k % args.steps))
         if stripes:
-            h.download_atlas_stripe(own_np)
+            # own stripe on the read-back stream: overlaps the next step's tracing; the next own convolution waits for it on the device
+            h.download_atlas_stripe_async(own_np)
         elif world > 1:
             h.download_atlas_layers(my_layers, own_np)
         else:
             # D2H of every step's result into pinned memory on the library's copy stream: it overlaps the next step's
             # tracing, and the next convolution waits for it on the device (anerend_cuda_ddgi_download_atlas_async)
             h.download_atlas_async(host_np)
-    if world == 1:
+    if world == 1 or stripes:
         h.download_wait()
     h.sync()
     e2e_s = time.perf_counter() - t0
@@ -461,6 +476,20 @@ def main():
                "convolve_ms": float(np.mean(acv)), "steps": asteps}
         close_handle(ha, fused)
 
+    # ---- the faithful subset: what rchit:85-94 shades — the sun only, no point lights (extension E1 off) — and the same with the light
+    # maps off (every shadow ray traced), so the headline can be read as reference work + E1 + what the maps save
+    subsets = None
+    if world == 1 and not args.no_alt:
+        subsets = {}
+        for key, fl in (("sun_only_faithful", flags & ~L.FLAG_POINT_LIGHTS), ("sun_only_no_light_maps", (flags & ~L.FLAG_POINT_LIGHTS) | L.FLAG_NO_LIGHT_MAPS),
+                        ("point_lights_no_light_maps", flags | L.FLAG_NO_LIGHT_MAPS)):
+            hs = make_handle(fl, slab)
+            ssteps = max(3, min(args.steps, 20))
+            sms_, srt, scv, _, _ = timed(hs, ssteps, 3, False, False)
+            subsets[key] = {"ms_per_step": sms_ / ssteps, "value": all_rays / (sms_ / ssteps * 1e-3) / 1e6, "unit": UNIT, "trace_ms": float(np.mean(srt)),
+                            "kernels_ms_avg": [round(float(v), 4) for v in np.mean(np.asarray(hs.kernel_ms, dtype=np.float64), axis=0)], "steps": ssteps}
+            close_handle(hs)
+
     # ---- strong-scaling base: the SAME workload on one GPU (rank 0 alone), so the N-GPU figure has its own denominator
     base1 = None
     verified = None
@@ -477,8 +506,19 @@ def main():
             h.download_atlas(multi)
             hb = make_handle(flags, (0, ny), striped=False)
             bsteps = 3
-            bms, _, _, _, _ = timed(hb, bsteps, 1, False, False)
+            bms, _, _, _, bstep = timed(hb, bsteps, 1, False, False)
             base1 = {"n_gpus": 1, "ms_per_step": bms / bsteps, "value": all_rays / (bms / bsteps * 1e-3) / 1e6, "unit": UNIT, "steps": bsteps}
+            # the same workload end to end on one GPU (host buffers in, whole atlas back to pinned memory every step, wall clock): the
+            # denominator of the N-GPU e2e figure
+            hb.sync()
+            tb = time.perf_counter()
+            for k in range(bsteps):
+                bstep(k)
+                hb.download_atlas_async(host_np)
+            hb.download_wait()
+            hb.sync()
+            base1["e2e_ms_per_step"] = (time.perf_counter() - tb) / bsteps * 1e3
+            base1["e2e_value"] = all_rays / (base1["e2e_ms_per_step"] * 1e-3) / 1e6
             if name != "c4":
                 hb.reset()
                 for k in range(2):
@@ -622,8 +662,9 @@ def main():
                     "rt_pass": {"launches": 4, "algorithmic_bytes": abytes, "ms_avg": rt_avg,
                                 "achieved": abytes / (rt_avg * 1e-3) / 1e9, "frac": abytes / (rt_avg * 1e-3) / 1e9 / peak,
                                 "share_of_step": rt_avg / ms_per_step},
-                    "note": "the traversal is L2-resident and instruction-issue bound (profiles/): HBM is the bound "
-                            "north_star names, not the limiter ncu shows",
+                    "frac_meaning": "ALGORITHMIC bytes (80 B per BVH8 node visited + 48 B per triangle tested + per-ray records) / HBM peak, the figure "
+                                    "north_star asks for; it is NOT DRAM utilisation: `traffic` (ncu dram__bytes) is a few per cent of it, the working set "
+                                    "is L2-resident and the kernel is instruction-issue bound (profiles/)",
                     "nodes_per_primary_ray": stats["primary_nodes_visited"] / max(1, stats["primary_rays"]),
                     "tris_per_primary_ray": stats["primary_tris_tested"] / max(1, stats["primary_rays"]),
                     "nodes_per_shadow_ray": stats["shadow_nodes_visited"] / max(1, stats["shadow_rays"]),
@@ -636,18 +677,20 @@ def main():
                     "shadow_rays_ended_by_candidate": stats["shadow_rays_candidate"]}
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
-            layers = list(range(ny)) if name != "c5" else list(range(0, ny, 8))
+            layers = sample_layers(name, ny)
             rays, secs, threads = run_oracle_sample(scene, grid, layers)
             cpu_baseline = {"value": rays / secs / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
                             "sample": f"{len(layers)} of {ny} Y-layers of {name} ({rays} primary rays + shadow rays), "
                                       f"{secs:.2f} s, multithreaded C++ oracle (shader transliteration)"}
         cfg = workload_desc(name, scene, grid, world)
+        deal_desc = None
         if balanced is not None:
-            cfg["parallelism"] = f"probe layers dealt to {world} ranks by measured per-layer cost (LPT)"
+            deal_desc = f"probe layers dealt to {world} ranks by measured per-layer cost (LPT)"
         if stripes:
-            cfg["parallelism"] = f"row stripes: rank r updates the probe rows z = r mod {world} of every layer"
-        cfg.update({"l2": "flushed between timed iterations (256 MiB write)" if flush else "working set larger than L2, no flush",
-                    "bvh8_nodes": int(info.num_nodes), "accel_build_ms": accel_ms,
+            deal_desc = f"row stripes: rank r updates the probe rows z = r mod {world} of every layer"
+        details = {}
+        assert flush == (name != "c5"), "config.l2 (workload_desc) must state what the timed loop does"
+        details.update({"bvh8_nodes": int(info.num_nodes), "accel_build_ms": accel_ms,
                     "atlas_exchange": ("peer push: after the convolution a copy kernel stores this rank's atlas rows into all peers' atlases "
                                        "over NVLink (cudaIpc-mapped), device-side barrier before and after; no collective" if fused else
                                        "nccl all_gather of the packed stripe rows on the handle's stream" if stripes else
@@ -656,13 +699,13 @@ def main():
                                        else "nccl all_gather of contiguous slabs, in place") if world > 1 else "none"})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": clocks,
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "details": dict(details, deal=deal_desc), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "update_ms": {"trace": rt_avg, "convolve": float(np.mean(conv_ms)), "full_grid": ms_per_step},
                 "arithmetic": "fast_math (1e-4 relative per update)" if args.fast_math else "exact (atlas bit-identical to the oracle)",
-                "other_build": alt, "strong_scaling_base": base1, "exchange_check_vs_1gpu": verified, "layer_deal": balanced, "per_rank_ms": per_rank, "atlas_consumer": consumer, "shadow_rt": shadow_rt, "multi_gpu_series_base": series_base,
+                "other_build": alt, "subsets": subsets, "strong_scaling_base": base1, "exchange_check_vs_1gpu": verified, "layer_deal": balanced, "per_rank_ms": per_rank, "atlas_consumer": consumer, "shadow_rt": shadow_rt, "multi_gpu_series_base": series_base,
                 "config1_conv_only": config1, "vulkan_reference": vulkan_reference_status()}
     close_handle(h, fused)
     if world > 1:

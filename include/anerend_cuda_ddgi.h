@@ -132,8 +132,10 @@ int anerend_cuda_ddgi_sync(anerend_ddgi_t* h);
 /* ---- scene (bindless set 0: bindings 2,3,6,7,8,9,10,11; bindless.glsl:123-179) ---------- */
 
 /* mesh_num_indices carries InternalMesh::_numIndices (internal/InternalMesh.h:12), which GPUMeshInfo lacks
- * (primitiveCount = _numIndices/3, VulkanRenderer.cpp:1313).  Materials must be texture-free
- * (bindless_indices == -1) — bindless textures are outside this path's scope (E_UNSUPPORTED). */
+ * (primitiveCount = _numIndices/3, VulkanRenderer.cpp:1313).  Materials may refer to bindless textures
+ * (bindless_indices[0,1,3]; [2], the normal map, is never sampled on this path): upload the array with
+ * _upload_textures FIRST — an index outside it is E_INVALID.  The call validates everything before it replaces
+ * the previous scene; a rejected upload leaves the previous scene and its texture state as they were. */
 int anerend_cuda_ddgi_upload_scene(anerend_ddgi_t* h,
     const anerend_vertex_t* vertices, uint32_t num_vertices,
     const uint32_t* indices, uint32_t num_indices,
@@ -260,12 +262,16 @@ int anerend_cuda_ddgi_specular_gi_device(anerend_ddgi_t* h, const void* d_depth,
  * this handle's rows of all layers, packed (layer, row): num_probes_y * rows * 10 * width * 8 bytes. */
 int anerend_cuda_ddgi_set_row_stripe(anerend_ddgi_t* h, int32_t offset, int32_t stride);
 int anerend_cuda_ddgi_download_atlas_stripe(anerend_ddgi_t* h, void* rgba16f, size_t bytes);
+/* The same stripe on the read-back stream (see _download_atlas_async; _download_wait blocks until it has landed).  Allowed while a
+ * peer exchange is connected: a handle's own rows are written by its own convolution only, and that convolution waits for the copy. */
+int anerend_cuda_ddgi_download_atlas_stripe_async(anerend_ddgi_t* h, void* rgba16f, size_t bytes);
 /* The atlas rows of `num_layers` Y-layers (10*nXZ rows each), packed in the order given: what one rank of a sharded
  * update reads back (its own layers); bytes = num_layers * (10*nXZ)^2 * 8. */
 int anerend_cuda_ddgi_download_atlas_layers(anerend_ddgi_t* h, const int32_t* layers, uint32_t num_layers, void* rgba16f, size_t bytes);
 /* Asynchronous read-back: returns at once; the copy starts when the work queued so far is done and overlaps the next update's
  * tracing (the next writer of the atlas waits for it on the device).  `rgba16f` should be page-locked.  _download_wait blocks
- * until the bytes have landed.  Not available while a peer exchange is connected. */
+ * until the bytes have landed.  Not available while peers write this atlas (connected exchange, _set_peer_atlases): read the own
+ * stripe with _download_atlas_stripe_async instead. */
 int anerend_cuda_ddgi_download_atlas_async(anerend_ddgi_t* h, void* rgba16f, size_t bytes);
 int anerend_cuda_ddgi_download_wait(anerend_ddgi_t* h);
 int anerend_cuda_ddgi_upload_atlas(anerend_ddgi_t* h, const void* rgba16f, size_t bytes);

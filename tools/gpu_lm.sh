@@ -11,7 +11,7 @@ for R in $RES; do
 import json
 try:
     d=json.load(open("gpurun_out/${TAG}_c3_r$R.json")); r=d["roofline"]
-    print("R=$R ms_per_step=%.4f e2e_ms=%.4f build=%.2f shadow/primary=%.3f nodes/shadow=%.2f kernels=%s" % (d["ms_per_step"], d["e2e"]["ms_per_step"], d["config"]["accel_build_ms"], r["shadow_rays_per_primary"], r["nodes_per_shadow_ray"], [round(v,4) for v in r["kernels_ms_avg"].values()]), "prefiltered", r.get("shadow_rays_prefiltered"), "candidate", r.get("shadow_rays_ended_by_candidate"), "traced", r.get("shadow_rays_traced"))
+    print("R=$R ms_per_step=%.4f e2e_ms=%.4f build=%.2f shadow/primary=%.3f nodes/shadow=%.2f kernels=%s" % (d["ms_per_step"], d["e2e"]["ms_per_step"], d["details"]["accel_build_ms"], r["shadow_rays_per_primary"], r["nodes_per_shadow_ray"], [round(v,4) for v in r["kernels_ms_avg"].values()]), "prefiltered", r.get("shadow_rays_prefiltered"), "candidate", r.get("shadow_rays_ended_by_candidate"), "traced", r.get("shadow_rays_traced"))
 except Exception as e:
     print("R=$R failed", e); print(open("gpurun_out/${TAG}_c3_r$R.err").read()[-1500:])
 PY
