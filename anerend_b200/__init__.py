@@ -52,6 +52,10 @@ class Ddgi(DdgiHandle):
         self._call("stream", _C.byref(s))
         return s.value or 0
 
+    def export_atlas_device(self, d_dst, pitch_bytes):
+        """Publishes the atlas into engine-owned device memory (the frame-graph image "ProbeRaysConvTex", linear rows)."""
+        self._call("export_atlas_device", _C.c_void_p(d_dst), _C.c_size_t(pitch_bytes))
+
     def set_peer_atlases(self, ptrs):
         arr = (_C.c_void_p * len(ptrs))(*ptrs)
         self._call("set_peer_atlases", arr, _C.c_uint32(len(ptrs)))

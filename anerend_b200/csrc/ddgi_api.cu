@@ -1595,6 +1595,18 @@ int DDGI_API(upload_atlas)(anerend_ddgi_t* h, const void* in, size_t bytes) {
   BE_CHECK(h, h->be.waitDownload()); BE_CHECK(h, h->be.sync()); BE_CHECK(h, h->be.h2d(h->dAtlas, in, bytes)); BE_CHECK(h, h->be.sync()); return 0;
 }
 int DDGI_API(atlas_device_ptr)(anerend_ddgi_t* h, void** p, size_t* bytes) { if (!h) return ANEREND_DDGI_E_INVALID; *p = h->dAtlas; *bytes = (size_t)h->W * h->H * 8; return 0; }
+int DDGI_API(export_atlas_device)(anerend_ddgi_t* h, void* dDst, size_t pitch) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
+  const size_t rowBytes = (size_t)h->W * 8;
+  if (!dDst || pitch < rowBytes) return fail(h, ANEREND_DDGI_E_INVALID, "export_atlas_device: null destination or pitch below the row size");
+#ifndef DDGI_HOST_EMU
+  BE_CHECK(h, h->be.ok(cudaMemcpy2DAsync(dDst, pitch, h->dAtlas, rowBytes, rowBytes, (size_t)h->H, cudaMemcpyDeviceToDevice, h->be.stream)));
+#else
+  for (int y = 0; y < h->H; ++y) memcpy((char*)dDst + pitch * y, (const char*)h->dAtlas + rowBytes * y, rowBytes);
+#endif
+  ++h->be.launches;
+  return 0;
+}
 int DDGI_API(set_peer_atlases)(anerend_ddgi_t* h, void* const* peers, uint32_t n) {
   if (!h) return ANEREND_DDGI_E_INVALID;
   if (n > 8) return fail(h, ANEREND_DDGI_E_INVALID, "at most 8 peers");

@@ -278,6 +278,12 @@ int anerend_cuda_ddgi_upload_atlas(anerend_ddgi_t* h, const void* rgba16f, size_
 /* Device pointer of the atlas for consumers on the same device (deferred lighting, NCCL all-gather of slabs).
  * Rows [10*nXZ*slab_begin, 10*nXZ*slab_end) are the rows this handle writes. */
 int anerend_cuda_ddgi_atlas_device_ptr(anerend_ddgi_t* h, void** d_ptr, size_t* bytes);
+/* Publishes the atlas into device memory the ENGINE owns — the frame-graph image "ProbeRaysConvTex" its consumers sample
+ * (DeferredLightingRenderPass.cpp:192-200, DebugViewRenderPass.cpp:225), imported into CUDA as linear RGBA16F rows of `pitch_bytes`
+ * (>= width * 8): a device-to-device pitched copy ordered after the work queued so far on the handle's stream.  The pass adapter
+ * (anerend_ddgi_passes.hpp) calls it after the convolution, after a translation and after (re-)registration, where the reference
+ * clears the image (clearConvTex, IrradianceProbeConvolvePass.cpp:9-47). */
+int anerend_cuda_ddgi_export_atlas_device(anerend_ddgi_t* h, void* d_dst, size_t pitch_bytes);
 /* Fused atlas all-gather: device pointers to the peers' atlases (cudaIpc-opened or P2P-enabled).  When set,
  * the convolution stores every finished texel into all peers as well, replacing the separate collective. */
 int anerend_cuda_ddgi_set_peer_atlases(anerend_ddgi_t* h, void* const* d_peers, uint32_t num_peers);

@@ -9,8 +9,22 @@
 // The classes are templates over an `Engine` traits struct so the same header compiles against the real engine headers
 //   struct Engine { using RenderPass = render::RenderPass; using FrameGraphBuilder = render::FrameGraphBuilder;
 //                   using RenderContext = render::RenderContext; using RenderExeParams = render::RenderExeParams;
-//                   using RenderPassRegisterInfo = render::RenderPassRegisterInfo; using ResourceUsage = render::ResourceUsage; };
-// or against the Vulkan-free stub used by tests/cpp/test_passes.cpp.  What the engine must provide is exactly what the
+//                   using RenderPassRegisterInfo = render::RenderPassRegisterInfo; using ResourceUsage = render::ResourceUsage;
+//                   using Access = render::Access; using Stage = render::Stage; using Type = render::Type;
+//                   using ImageInitialCreateInfo = render::ImageInitialCreateInfo;
+//                   static constexpr auto kFormatRGBA16F = VK_FORMAT_R16G16B16A16_SFLOAT; static constexpr auto kFormatR32F = VK_FORMAT_R32_SFLOAT;
+//                   static constexpr auto kLayoutShaderReadOnly = VK_IMAGE_LAYOUT_SHADER_READ_ONLY_OPTIMAL;
+//                   static auto clearConvTexCb() { return clearConvTex; } };      // IrradianceProbeConvolvePass.cpp:9-47, moved to a header
+// or against the Vulkan-free stub used by tests/cpp/test_passes.cpp.
+//
+// Frame-graph resources.  The three passes declare the SAME four resources, with the same access / stage / type and the same
+// ImageInitialCreateInfo, as the reference passes (IrradianceProbeRayTracingPass.cpp:42-81, IrradianceProbeConvolvePass.cpp:66-98,
+// IrradianceProbeTranslationPass.cpp:29-51), so the frame graph creates "ProbeRaysConvTex" exactly as before and the passes that
+// consume it (DeferredLightingRenderPass.cpp:192-200, SpecularGIRTPass.cpp:66, DebugViewRenderPass.cpp:225) find their producer.
+// The CUDA side keeps its own working atlas; after every convolution, translation and (re-)registration the adapter publishes it
+// into the engine's image through rc->cudaResource("ProbeRaysConvTex") + anerend_cuda_ddgi_export_atlas_device (see INTEGRATION.md
+// for how the engine imports that image's memory and orders the CUDA stream against its queue).  "ProbeRaysIrrTex" / "ProbeRaysDirTex"
+// / "TempProbeTex" stay declared — the graph's barriers and the debug view keep their names — and are backed by CUDA buffers.  What the engine must provide is exactly what the
 // reference passes already use: rc->getNumIrradianceProbesXZ/Y(), rc->getRenderOptions(), rc->isBaking(),
 // rc->blackboardValueInt / setBlackboardValueInt (RenderContext.h:85-188), fgb.registerRenderPass / registerRenderPassExe
 // (FrameGraphBuilder.h:178-179), and one addition: rc->sceneUbo() returning the GPUSceneData the renderer already fills
@@ -51,7 +65,31 @@ struct Volume {
     if (rc != 0) { handle = nullptr; error = "anerend_cuda_ddgi_create failed (no CUDA device?)"; std::printf("%s\n", error.c_str()); return false; }
     return true;
   }
+  // The engine's "ProbeRaysConvTex" follows the CUDA atlas: called after whatever changed it (convolution, translation, clear).
+  template <class RC> void publish(RC* rc) {
+    if (!handle) return;
+    void* img = rc->cudaResource(ANEREND_RES_CONV);
+    if (!img) return;                                              // engine without the import: consumers see the image as the graph cleared it
+    if (anerend_cuda_ddgi_export_atlas_device(handle, img, (size_t)(8 + 2) * params.num_probes_xz * 8) != 0) std::printf("%s\n", anerend_cuda_ddgi_last_error(handle));
+  }
 };
+
+// the reference's resource declarations, shared by the three passes
+template <class Engine>
+typename Engine::ResourceUsage probeUsage(const char* name, typename Engine::Access access, typename Engine::Stage stage, typename Engine::Type type) {
+  typename Engine::ResourceUsage u{};
+  u._resourceName = name;
+  u._access.set((std::size_t)access);
+  u._stage.set((std::size_t)stage);
+  u._type = type;
+  return u;
+}
+template <class Engine>
+typename Engine::ImageInitialCreateInfo probeImage(uint32_t width, uint32_t height) {
+  typename Engine::ImageInitialCreateInfo ci{};
+  ci._initialWidth = width; ci._initialHeight = height; ci._intialFormat = Engine::kFormatRGBA16F;
+  return ci;
+}
 
 template <class Engine>
 class IrradianceProbeTranslationPass : public Engine::RenderPass {
@@ -61,14 +99,23 @@ public:
     typename Engine::RenderPassRegisterInfo info{};
     info._name = ANEREND_PASS_TRANS;
     info._group = ANEREND_PASS_GROUP;
+    const uint32_t width = (8 + 2) * (uint32_t)rc->getNumIrradianceProbesXZ(), height = width * (uint32_t)rc->getNumIrradianceProbesY();
+    {  // IrradianceProbeTranslationPass.cpp:29-44: the copy target, created here
+      auto u = probeUsage<Engine>(ANEREND_RES_TEMP, Engine::Access::Write, Engine::Stage::Transfer, Engine::Type::ImageTransferDst);
+      u._imageCreateInfo = probeImage<Engine>(width, height);
+      info._resourceUsages.emplace_back(std::move(u));
+    }
+    info._resourceUsages.emplace_back(probeUsage<Engine>(ANEREND_RES_CONV, Engine::Access::Read, Engine::Stage::Transfer, Engine::Type::ImageTransferSrc));   // :45-51
     fgb.registerRenderPass(std::move(info));
     _vol->ensure((int)rc->getNumIrradianceProbesXZ(), (int)rc->getNumIrradianceProbesY());
+    _vol->publish(rc);                                             // the cleared atlas (clearConvTex) reaches the engine's image as well
     fgb.registerRenderPassExe(ANEREND_PASS_TRANS, [this](typename Engine::RenderExeParams exeParams) {
       if (!_vol->handle) return;
       if (!exeParams.rc->getRenderOptions().ddgiEnabled) return;   // IrradianceProbeTranslationPass.cpp:57
       if (exeParams.rc->isBaking()) return;                        // :58
       anerend_cuda_ddgi_set_scene_ubo(_vol->handle, exeParams.rc->sceneUbo());
       if (anerend_cuda_ddgi_translate(_vol->handle) != 0) std::printf("%s\n", anerend_cuda_ddgi_last_error(_vol->handle));
+      // no publish here: nothing samples the atlas between this pass and IrradianceProbeConvolve, which publishes it
     });
   }
 private:
@@ -83,6 +130,15 @@ public:
     typename Engine::RenderPassRegisterInfo info{};
     info._name = ANEREND_PASS_RT;
     info._group = ANEREND_PASS_GROUP;
+    {  // IrradianceProbeRayTracingPass.cpp:42-81 (sqrtNumRays = 16: NUM_RAYS_PER_PROBE = 256)
+      const uint32_t side = 16u * (uint32_t)rc->getNumIrradianceProbesXZ();
+      for (const char* n : {ANEREND_RES_RAYS_IRR, ANEREND_RES_RAYS_DIR}) {
+        auto u = probeUsage<Engine>(n, Engine::Access::Write, Engine::Stage::RayTrace, Engine::Type::ImageStorage);
+        u._imageCreateInfo = probeImage<Engine>(side, side);
+        info._resourceUsages.emplace_back(std::move(u));
+      }
+      info._resourceUsages.emplace_back(probeUsage<Engine>(ANEREND_RES_CONV, Engine::Access::Read, Engine::Stage::RayTrace, Engine::Type::SampledTexture));
+    }
     fgb.registerRenderPass(std::move(info));
     const int numProbesHeight = (int)rc->getNumIrradianceProbesY();
     _currentLayer = 0;                                             // IrradianceProbeRayTracingPass.cpp:39
@@ -115,10 +171,21 @@ template <class Engine>
 class IrradianceProbeConvolvePass : public Engine::RenderPass {
 public:
   explicit IrradianceProbeConvolvePass(std::shared_ptr<Volume> v) : _vol(std::move(v)) {}
-  void registerToGraph(typename Engine::FrameGraphBuilder& fgb, typename Engine::RenderContext*) override final {
+  void registerToGraph(typename Engine::FrameGraphBuilder& fgb, typename Engine::RenderContext* rc) override final {
     typename Engine::RenderPassRegisterInfo info{};
     info._name = ANEREND_PASS_CONVOLVE;
     info._group = ANEREND_PASS_GROUP;
+    {  // IrradianceProbeConvolvePass.cpp:66-98: the atlas is CREATED by this pass's usage (initial layout shader-read, cleared by clearConvTex)
+      info._resourceUsages.emplace_back(probeUsage<Engine>(ANEREND_RES_RAYS_IRR, Engine::Access::Read, Engine::Stage::Compute, Engine::Type::ImageStorage));
+      info._resourceUsages.emplace_back(probeUsage<Engine>(ANEREND_RES_RAYS_DIR, Engine::Access::Read, Engine::Stage::Compute, Engine::Type::ImageStorage));
+      auto u = probeUsage<Engine>(ANEREND_RES_CONV, Engine::Access::Write, Engine::Stage::Compute, Engine::Type::ImageStorage);
+      const uint32_t width = (8 + 2) * (uint32_t)rc->getNumIrradianceProbesXZ();
+      auto ci = probeImage<Engine>(width, width * (uint32_t)rc->getNumIrradianceProbesY());
+      ci._initialLayout = Engine::kLayoutShaderReadOnly;           // "hack since this is used in a pass before this one" (:90)
+      ci._initialDataCb = Engine::clearConvTexCb();
+      u._imageCreateInfo = ci;
+      info._resourceUsages.emplace_back(std::move(u));
+    }
     fgb.registerRenderPass(std::move(info));
     fgb.registerRenderPassExe(ANEREND_PASS_CONVOLVE, [this](typename Engine::RenderExeParams exeParams) {
       if (!_vol->handle) return;
@@ -126,6 +193,7 @@ public:
       if (!exeParams.rc->getRenderOptions().ddgiEnabled) return;         // :112
       uint32_t probeLayer = (uint32_t)exeParams.rc->blackboardValueInt(ANEREND_BLACKBOARD_LAYER);   // :126
       if (anerend_cuda_ddgi_convolve_layer(_vol->handle, (int32_t)probeLayer) != 0) std::printf("%s\n", anerend_cuda_ddgi_last_error(_vol->handle));
+      _vol->publish(exeParams.rc);                                 // the consumers' "ProbeRaysConvTex" (deferred lighting, debug view) follows
     });
   }
 private:
@@ -143,11 +211,17 @@ template <class Engine>
 class ShadowRayTracingPass : public Engine::RenderPass {          // src/anerend/render/passes/ShadowRayTracingPass.{h,cpp}, "ShadowRT"
 public:
   explicit ShadowRayTracingPass(std::shared_ptr<Volume> v) : _vol(std::move(v)) {}
-  void registerToGraph(typename Engine::FrameGraphBuilder& fgb, typename Engine::RenderContext*) override final {
+  void registerToGraph(typename Engine::FrameGraphBuilder& fgb, typename Engine::RenderContext* rc) override final {
     typename Engine::RenderPassRegisterInfo info{};
     info._name = "ShadowRT";
-    { typename Engine::ResourceUsage u{}; u._resourceName = "GeometryDepthImage"; info._resourceUsages.emplace_back(std::move(u)); }   // :22
-    { typename Engine::ResourceUsage u{}; u._resourceName = "RTShadowImage"; info._resourceUsages.emplace_back(std::move(u)); }        // :30
+    info._resourceUsages.emplace_back(probeUsage<Engine>("GeometryDepthImage", Engine::Access::Read, Engine::Stage::RayTrace, Engine::Type::SampledDepthTexture));   // :22
+    {  // :30-41: created here, r32f of the swap-chain extent
+      auto u = probeUsage<Engine>("RTShadowImage", Engine::Access::Write, Engine::Stage::RayTrace, Engine::Type::ImageStorage);
+      typename Engine::ImageInitialCreateInfo ci{};
+      ci._initialWidth = rc->screenWidth(); ci._initialHeight = rc->screenHeight(); ci._intialFormat = Engine::kFormatR32F;
+      u._imageCreateInfo = ci;
+      info._resourceUsages.emplace_back(std::move(u));
+    }
     fgb.registerRenderPass(std::move(info));
     fgb.registerRenderPassExe("ShadowRT", [this](typename Engine::RenderExeParams exeParams) {
       if (!_vol->handle) return;
@@ -167,13 +241,18 @@ template <class Engine>
 class SpecularGIRTPass : public Engine::RenderPass {              // src/anerend/render/passes/SpecularGIRTPass.{h,cpp}, "SpecularGIRT"
 public:
   explicit SpecularGIRTPass(std::shared_ptr<Volume> v) : _vol(std::move(v)) {}
-  void registerToGraph(typename Engine::FrameGraphBuilder& fgb, typename Engine::RenderContext*) override final {
+  void registerToGraph(typename Engine::FrameGraphBuilder& fgb, typename Engine::RenderContext* rc) override final {
     typename Engine::RenderPassRegisterInfo info{};
     info._name = "SpecularGIRT";
     info._group = "SpecularGI";
-    for (const char* n : {"ReflectTex", "GeometryDepthImage", "Geometry0Image", ANEREND_RES_CONV, "Geometry1Image", "SpecularBRDFLutTex"}) {   // :30-82
-      typename Engine::ResourceUsage u{}; u._resourceName = n; info._resourceUsages.emplace_back(std::move(u));
+    {  // :30-46: created here, rgba16f ("needs to be HDR") of the swap-chain extent
+      auto u = probeUsage<Engine>("ReflectTex", Engine::Access::Write, Engine::Stage::RayTrace, Engine::Type::ImageStorage);
+      u._imageCreateInfo = probeImage<Engine>(rc->screenWidth(), rc->screenHeight());
+      info._resourceUsages.emplace_back(std::move(u));
     }
+    info._resourceUsages.emplace_back(probeUsage<Engine>("GeometryDepthImage", Engine::Access::Read, Engine::Stage::RayTrace, Engine::Type::SampledDepthTexture));   // :49
+    for (const char* n : {"Geometry0Image", ANEREND_RES_CONV, "Geometry1Image", "SpecularBRDFLutTex"})                                                            // :57-85
+      info._resourceUsages.emplace_back(probeUsage<Engine>(n, Engine::Access::Read, Engine::Stage::RayTrace, Engine::Type::SampledTexture));
     fgb.registerRenderPass(std::move(info));
     fgb.registerRenderPassExe("SpecularGIRT", [this](typename Engine::RenderExeParams exeParams) {
       if (!_vol->handle) return;
@@ -209,9 +288,15 @@ public:
   void registerToGraph(typename Engine::FrameGraphBuilder& fgb, typename Engine::RenderContext*) override final {
     typename Engine::RenderPassRegisterInfo info{};
     info._name = "TLASUpdate";
-    for (const char* n : {"TLASInstanceBuf", "TLASCounterBuf", "RenderableBuffer"}) {        // UpdateTLASPass.cpp:80-117
-      typename Engine::ResourceUsage u{}; u._resourceName = n; info._resourceUsages.emplace_back(std::move(u));
+    // UpdateTLASPass.cpp:80-117.  The two buffers the compute shader filled stay declared (other passes and the graph's barriers know
+    // their names) but carry no create info here: nothing on the CUDA side needs them, so they are marked engine-owned.
+    for (const char* n : {"TLASInstanceBuf", "TLASCounterBuf"}) {
+      auto u = probeUsage<Engine>(n, Engine::Access::Write, Engine::Stage::Compute, Engine::Type::SSBO);
+      u._ownedByEngine = true;
+      info._resourceUsages.emplace_back(std::move(u));
     }
+    { auto u = probeUsage<Engine>("RenderableBuffer", Engine::Access::Read, Engine::Stage::Compute, Engine::Type::SSBO);
+      u._multiBuffered = true; u._ownedByEngine = true; info._resourceUsages.emplace_back(std::move(u)); }
     fgb.registerRenderPass(std::move(info));
     fgb.registerRenderPassExe("TLASUpdate", [this](typename Engine::RenderExeParams exeParams) {
       if (!_vol->handle) return;
@@ -239,7 +324,8 @@ public:
   void registerToGraph(typename Engine::FrameGraphBuilder& fgb, typename Engine::RenderContext*) override final {
     typename Engine::RenderPassRegisterInfo info{};
     info._name = "BLASUpdate";
-    { typename Engine::ResourceUsage u{}; u._resourceName = "GigaVtxBuffer"; info._resourceUsages.emplace_back(std::move(u)); }   // UpdateBlasPass.cpp:24-32
+    { auto u = probeUsage<Engine>("GigaVtxBuffer", Engine::Access::Read, Engine::Stage::Vertex, Engine::Type::SSBO);               // UpdateBlasPass.cpp:24-32
+      u._ownedByEngine = true; info._resourceUsages.emplace_back(std::move(u)); }
     fgb.registerRenderPass(std::move(info));
     fgb.registerRenderPassExe("BLASUpdate", [this](typename Engine::RenderExeParams exeParams) {
       if (!_vol->handle) return;

@@ -2,8 +2,10 @@
 // RenderContext.h:85-188, RenderOptions.h:7-28), enough to register the three CUDA DDGI passes into a "frame graph",
 // execute it for a number of frames in submission order and print a checksum of the atlas.
 //   usage: test_passes <frames> <seed> [scene.bin]     (scene.bin written by tests/test_passes_adapter.py)
+#include <bitset>
 #include <cstdint>
 #include <cstdio>
+#include <optional>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -34,7 +36,18 @@ struct RenderContext {
   uint32_t screenHeight() { return ubo.screen_height; }
 };
 struct RenderExeParams { RenderContext* rc; };
-struct ResourceUsage { std::string _resourceName; };
+// FrameGraphBuilder.h:44-176, the fields the passes set
+enum class Access { Read, Write, Count };
+enum class Stage { Transfer, Compute, IndirectDraw, Vertex, Fragment, Irrelevant, RayTrace, Count };
+enum class Type { ColorAttachment, DepthAttachment, Present, SampledTexture, SampledDepthTexture, UBO, SSBO, Irrelevant, ImageStorage, ImageTransferSrc, ImageTransferDst, Count };
+struct ImageInitialCreateInfo {
+  std::uint32_t _initialWidth = 0, _initialHeight = 0; int _intialFormat = 0; int _initialLayout = 0;
+  std::function<void(RenderContext*, void*&)> _initialDataCb = nullptr;
+};
+struct ResourceUsage {
+  std::bitset<(std::size_t)Access::Count> _access; std::bitset<(std::size_t)Stage::Count> _stage; Type _type = Type::Irrelevant;
+  bool _ownedByEngine = false, _multiBuffered = false; std::string _resourceName; std::optional<ImageInitialCreateInfo> _imageCreateInfo;
+};
 struct RenderPassRegisterInfo { std::string _name; std::string _group; std::vector<ResourceUsage> _resourceUsages; };
 struct FrameGraphBuilder {
   std::vector<RenderPassRegisterInfo> passes; std::map<std::string, std::function<void(RenderExeParams)>> exes;
@@ -42,14 +55,44 @@ struct FrameGraphBuilder {
   void registerRenderPassExe(const std::string& n, std::function<void(RenderExeParams)> f) { exes[n] = std::move(f); }
   void executeGraph(RenderContext* rc) { for (auto& p : passes) exes[p._name](RenderExeParams{rc}); }   // submission order, FrameGraphBuilder.cpp:1197-1228
   void reset() { passes.clear(); exes.clear(); }
+  // What building the graph checks first (FrameGraphBuilder.cpp, resource creation): every resource a pass touches is either owned by the
+  // engine or created by exactly one usage that carries a create info.  Returns the first offending "pass:resource", or "" if the graph is sound.
+  std::string validate(RenderContext* rc) {
+    std::map<std::string, int> creators;
+    for (auto& p : passes) for (auto& u : p._resourceUsages) if (u._imageCreateInfo) {
+      creators[u._resourceName]++;
+      if (u._imageCreateInfo->_initialWidth == 0 || u._imageCreateInfo->_initialHeight == 0 || u._imageCreateInfo->_intialFormat == 0) return p._name + ":" + u._resourceName + " (empty create info)";
+      if (u._imageCreateInfo->_initialDataCb) { void* img = nullptr; u._imageCreateInfo->_initialDataCb(rc, img); }
+    }
+    for (auto& p : passes) for (auto& u : p._resourceUsages) {
+      if (u._ownedByEngine) continue;
+      if (u._access.none() || u._stage.none() || u._type == Type::Irrelevant) return p._name + ":" + u._resourceName + " (no access / stage / type)";
+      if (creators[u._resourceName] != 1) return p._name + ":" + u._resourceName + (creators[u._resourceName] ? " (created twice)" : " (no producer)");
+    }
+    return "";
+  }
 };
 struct RenderPass {
   virtual ~RenderPass() = default;
   virtual void registerToGraph(FrameGraphBuilder&, RenderContext*) = 0;
 };
+static int g_convCleared = 0;
 struct Engine {
   using RenderPass = stub::RenderPass; using FrameGraphBuilder = stub::FrameGraphBuilder; using RenderContext = stub::RenderContext;
   using RenderExeParams = stub::RenderExeParams; using RenderPassRegisterInfo = stub::RenderPassRegisterInfo; using ResourceUsage = stub::ResourceUsage;
+  using Access = stub::Access; using Stage = stub::Stage; using Type = stub::Type; using ImageInitialCreateInfo = stub::ImageInitialCreateInfo;
+  static constexpr int kFormatRGBA16F = 97, kFormatR32F = 100, kLayoutShaderReadOnly = 5;        // the VkFormat / VkImageLayout values
+  static std::function<void(RenderContext*, void*&)> clearConvTexCb() { return [](RenderContext*, void*&) { ++g_convCleared; }; }   // clearConvTex stand-in
+};
+// a consumer of the atlas as the reference declares it (DeferredLightingRenderPass.cpp:192-200): sampled in a compute pass
+struct DeferredLightingStub : RenderPass {
+  void registerToGraph(FrameGraphBuilder& fgb, RenderContext*) override {
+    RenderPassRegisterInfo info{}; info._name = "DeferredLighting";
+    ResourceUsage u{}; u._resourceName = "ProbeRaysConvTex"; u._access.set((std::size_t)Access::Read); u._stage.set((std::size_t)Stage::Compute); u._type = Type::SampledTexture;
+    info._resourceUsages.emplace_back(std::move(u));
+    fgb.registerRenderPass(std::move(info));
+    fgb.registerRenderPassExe("DeferredLighting", [](RenderExeParams) {});
+  }
 };
 }  // namespace stub
 
@@ -90,6 +133,43 @@ int main(int argc, char** argv) {
     if (!vol->topologyDirty) { printf("FAIL accel gating\n"); return 1; }
   }
   std::vector<stub::RenderPass*> passes = {&trans, &rt, &conv};              // VulkanRenderer.cpp:4473-4475
+  {  // frame-graph soundness: with the three passes registered, a consumer of "ProbeRaysConvTex" finds its producer (and the image its
+     // create info + clear callback); without them it does not, and the stub graph says so
+    stub::DeferredLightingStub deferred;
+    stub::FrameGraphBuilder alone; deferred.registerToGraph(alone, &rc);
+    if (alone.validate(&rc) != "DeferredLighting:ProbeRaysConvTex (no producer)") { printf("FAIL the stub graph accepts a consumer without a producer\n"); return 1; }
+    stub::FrameGraphBuilder g5;
+    for (auto* p : passes) p->registerToGraph(g5, &rc);
+    deferred.registerToGraph(g5, &rc);
+    const std::string bad = g5.validate(&rc);
+    if (!bad.empty()) { printf("FAIL frame graph: %s\n", bad.c_str()); return 1; }
+    if (stub::g_convCleared != 1) { printf("FAIL clearConvTex not attached to the atlas' create info\n"); return 1; }
+    const auto& cu = g5.passes[2]._resourceUsages;                          // IrradianceProbeConvolvePass.cpp:66-98
+    if (cu.size() != 3 || cu[2]._resourceName != "ProbeRaysConvTex" || !cu[2]._imageCreateInfo || cu[2]._imageCreateInfo->_initialWidth != 10 * rc.nXZ ||
+        cu[2]._imageCreateInfo->_initialHeight != 10 * rc.nXZ * rc.nY || cu[2]._imageCreateInfo->_initialLayout != stub::Engine::kLayoutShaderReadOnly ||
+        !cu[2]._access.test((std::size_t)stub::Access::Write) || cu[2]._type != stub::Type::ImageStorage) { printf("FAIL atlas create info\n"); return 1; }
+    const auto& ru = g5.passes[1]._resourceUsages;                          // IrradianceProbeRayTracingPass.cpp:42-81
+    if (ru.size() != 3 || ru[0]._resourceName != "ProbeRaysIrrTex" || ru[1]._resourceName != "ProbeRaysDirTex" || !ru[0]._imageCreateInfo ||
+        ru[0]._imageCreateInfo->_initialWidth != 16 * rc.nXZ || ru[2]._type != stub::Type::SampledTexture) { printf("FAIL ray image usages\n"); return 1; }
+    const auto& tu = g5.passes[0]._resourceUsages;                          // IrradianceProbeTranslationPass.cpp:29-51
+    if (tu.size() != 2 || tu[0]._resourceName != "TempProbeTex" || tu[0]._type != stub::Type::ImageTransferDst || tu[1]._type != stub::Type::ImageTransferSrc) { printf("FAIL translation usages\n"); return 1; }
+    // the whole set the adapter provides, wired to the engine-owned inputs they declare
+    stub::FrameGraphBuilder g6;
+    blas.registerToGraph(g6, &rc); tlas.registerToGraph(g6, &rc);
+    for (auto* p : passes) p->registerToGraph(g6, &rc);
+    for (const char* n : {"GeometryDepthImage", "Geometry0Image", "Geometry1Image", "SpecularBRDFLutTex"}) {       // produced by the G-buffer passes
+      stub::RenderPassRegisterInfo gi{}; gi._name = std::string("Producer_") + n;
+      stub::ResourceUsage u{}; u._resourceName = n; u._access.set((std::size_t)stub::Access::Write); u._stage.set((std::size_t)stub::Stage::Fragment); u._type = stub::Type::ColorAttachment;
+      stub::ImageInitialCreateInfo ci{}; ci._initialWidth = 4; ci._initialHeight = 4; ci._intialFormat = 1; u._imageCreateInfo = ci;
+      gi._resourceUsages.emplace_back(std::move(u)); g6.registerRenderPass(std::move(gi));
+    }
+    rc.ubo.screen_width = 64; rc.ubo.screen_height = 32;
+    shadowRt.registerToGraph(g6, &rc); specRt.registerToGraph(g6, &rc);
+    const std::string bad6 = g6.validate(&rc);
+    if (!bad6.empty()) { printf("FAIL full frame graph: %s\n", bad6.c_str()); return 1; }
+    rc.ubo.screen_width = 0; rc.ubo.screen_height = 0;
+    if (vol->handle) anerend_cuda_ddgi_reset(vol->handle);
+  }
   for (auto* p : passes) p->registerToGraph(fgb, &rc);
   if (fgb.passes.size() != 3 || fgb.passes[0]._name != "IrradianceProbeTrans" || fgb.passes[1]._name != "IrradianceProbeRT" ||
       fgb.passes[2]._name != "IrradianceProbeConvolve" || fgb.passes[1]._group != "IrradianceProbe") { printf("FAIL names\n"); return 1; }
@@ -113,6 +193,13 @@ int main(int argc, char** argv) {
     if (vol->topologyDirty || anerend_cuda_ddgi_get_bvh_info(vol->handle, &bi) != 0 || bi.num_triangles == 0) { printf("FAIL TLASUpdate build\n"); return 1; }
     g4.executeGraph(&rc);                                                      // no device RenderableBuffer in the stub: the refit no-ops
   }
+  // the engine's "ProbeRaysConvTex": device memory of the same size (here: the atlas allocation of a second, otherwise unused handle);
+  // the adapter publishes the CUDA atlas into it after every convolution
+  anerend_ddgi_t* engineImage = nullptr;
+  if (anerend_cuda_ddgi_create(&vol->params, &engineImage) == 0) {
+    void* img = nullptr; size_t bytes = 0; anerend_cuda_ddgi_atlas_device_ptr(engineImage, &img, &bytes);
+    rc.cuda["ProbeRaysConvTex"] = img;
+  }
   rt.seed(seed);
   for (int fr = 0; fr < frames; ++fr) {
     rc.ubo.camera_pos[0] += 0.37f;                                             // drifts across probe cells: translation fires
@@ -125,6 +212,13 @@ int main(int argc, char** argv) {
   anerend_cuda_ddgi_download_atlas(vol->handle, atlas.data(), atlas.size() * 2);
   uint64_t sum = 1469598103934665603ull; for (uint16_t v : atlas) { sum ^= v; sum *= 1099511628211ull; }
   printf("OK frames=%d atlas=%dx%d fnv=%016llx\n", frames, w, h, (unsigned long long)sum);
+  if (engineImage) {                                                          // what a consumer of the engine's image would sample
+    anerend_cuda_ddgi_sync(vol->handle);
+    std::vector<uint16_t> pub(atlas.size());
+    anerend_cuda_ddgi_download_atlas(engineImage, pub.data(), pub.size() * 2);
+    if (pub != atlas) { printf("FAIL the published ProbeRaysConvTex differs from the atlas\n"); return 1; }
+    printf("OK published\n");
+  }
   fgb.reset();
   for (auto* p : passes) p->registerToGraph(fgb, &rc);
   anerend_cuda_ddgi_download_atlas(vol->handle, atlas.data(), atlas.size() * 2);
