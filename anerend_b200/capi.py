@@ -250,10 +250,16 @@ class DdgiHandle:
         self._call("set_row_stripe", C.c_int32(offset), C.c_int32(stride))
         self.stripe = (int(offset), int(stride))
 
+    def set_row_block(self, first, count):
+        """This handle updates only the probe rows z in [first, first + count) of every layer."""
+        self._call("set_row_block", C.c_int32(first), C.c_int32(count))
+        self.stripe = (int(first), 1)
+        self.stripe_rows = int(count)
+
     def download_atlas_stripe(self, out=None):
         """Atlas rows of this handle's stripe in all layers: uint16 [n_y, rows, 10, W, 4]."""
         off, stride = getattr(self, "stripe", (0, 1))
-        rows = (self.n_xz - off + stride - 1) // stride
+        rows = getattr(self, "stripe_rows", None) or (self.n_xz - off + stride - 1) // stride
         if out is None:
             out = np.empty((self.n_y, rows, 10, self.atlas_width, 4), np.uint16)
         self._call("download_atlas_stripe", _ptr(out), C.c_size_t(out.nbytes))

@@ -905,7 +905,9 @@ int traceLayers(anerend_ddgi* h, const int* layers, int numLayers, const float* 
   return 0;
 }
 
-int convolveLayers(anerend_ddgi* h, const int* layers, int numLayers) {
+bool texelStoreExchange() { static const bool on = getenv("DDGI_EXCHANGE_TEXEL") != nullptr; return on; }      // A/B measurements only
+// `push`: store the fresh layers into the peers' atlases right after the convolution (the caller has made sure no peer still reads them)
+int convolveLayers(anerend_ddgi* h, const int* layers, int numLayers, bool push = true) {
   Backend& be = h->be;
   BE_CHECK(h, be.fenceDownload());          // a background read-back of the previous atlas must finish before it is overwritten
   for (int l = 0; l < numLayers; ++l) if (!h->layerTraced[layers[l]]) return fail(h, ANEREND_DDGI_E_STATE, "convolve before trace of this layer");
@@ -922,7 +924,7 @@ int convolveLayers(anerend_ddgi* h, const int* layers, int numLayers) {
   c.rayIrr = h->dRayIrr; c.dirs = h->dDirs; c.layerMap = h->dLayerMap; c.atlas = h->dAtlas; c.texelRecords = h->dTexelRecords;
   // peers: whole layer blocks are pushed after the convolution (pushLayers); DDGI_EXCHANGE_TEXEL=1 keeps the first
   // version, per-texel peer stores from inside the convolution, for A/B measurements
-  static const bool texelStores = getenv("DDGI_EXCHANGE_TEXEL") != nullptr;
+  const bool texelStores = texelStoreExchange();
   for (int i = 0; i < h->numPeers; ++i) c.peers[i] = h->peers[i];
   c.numPeers = texelStores ? h->numPeers : 0;
   c.nXZ = h->nXZ; c.nY = h->nY; c.N = h->N; c.Sx = h->Sx; c.Sy = h->Sy; c.W = h->W; c.H = h->H; c.numLayers = numLayers;
@@ -937,8 +939,24 @@ int convolveLayers(anerend_ddgi* h, const int* layers, int numLayers) {
 #endif
   DDGI_LAUNCH(be, k_probe_convolve, conv_texel_body, (uint32_t)numLayers * (uint32_t)h->Pl * 64u, c, 128);
   BE_CHECK(h, be.check());
-  if (!texelStores) return pushLayers(h, numLayers);
+  if (!texelStores && push) return pushLayers(h, numLayers);
   return 0;
+}
+// The exchange of a sharded update.  The convolution only writes this handle's OWN rows, which no peer reads or writes, so it runs as
+// soon as the own trace is done; the first barrier (every rank has finished tracing against the previous atlas) is only needed in
+// front of the push into the peers' atlases — the ranks that finish tracing first convolve while they wait for the slowest one.
+// The second barrier: every rank's rows have landed here before the next trace samples them.
+int convolveAndExchange(anerend_ddgi* h, const int* layers, int numLayers) {
+  int rc;
+  if (texelStoreExchange()) {             // per-texel peer stores from inside the convolution: the barrier has to come first
+    if ((rc = peerBarrier(h))) return rc;
+    if ((rc = convolveLayers(h, layers, numLayers))) return rc;
+    return peerBarrier(h);
+  }
+  if ((rc = convolveLayers(h, layers, numLayers, false))) return rc;
+  if ((rc = peerBarrier(h))) return rc;
+  if ((rc = pushLayers(h, numLayers))) return rc;
+  return peerBarrier(h);
 }
 
 int translate(anerend_ddgi* h) {
@@ -1314,9 +1332,7 @@ int DDGI_API(update)(anerend_ddgi_t* h, int32_t layer, const float* rots) {
   int rc = traceLayers(h, layers.data(), (int)layers.size(), rots, layer < 0);
   h->be.mark(2); h->timed[1] = true;
   if (rc) return rc;
-  if ((rc = peerBarrier(h))) return rc;          // connected exchange: every rank has finished reading the previous atlas
-  rc = convolveLayers(h, layers.data(), (int)layers.size());
-  if (!rc) rc = peerBarrier(h);                  // ... and every rank's texels have landed in this atlas
+  rc = convolveAndExchange(h, layers.data(), (int)layers.size());
   h->be.mark(3); h->timed[2] = true;
   return rc;
 }
@@ -1333,9 +1349,7 @@ int DDGI_API(update_layers)(anerend_ddgi_t* h, const int32_t* layerList, uint32_
   int rc = traceLayers(h, layerList, (int)n, rots, true);
   h->be.mark(2); h->timed[1] = true;
   if (rc) return rc;
-  if ((rc = peerBarrier(h))) return rc;
-  rc = convolveLayers(h, layerList, (int)n);
-  if (!rc) rc = peerBarrier(h);
+  rc = convolveAndExchange(h, layerList, (int)n);
   h->be.mark(3); h->timed[2] = true;
   return rc;
 }
@@ -1546,6 +1560,14 @@ int DDGI_API(set_row_stripe)(anerend_ddgi_t* h, int32_t offset, int32_t stride) 
   if (stride < 1 || offset < 0 || offset >= stride || offset >= h->nXZ) return fail(h, ANEREND_DDGI_E_INVALID, "row stripe out of range");
   h->rowOffset = offset; h->rowStride = stride;
   h->Pl = ((h->nXZ - offset + stride - 1) / stride) * h->nXZ;
+  return 0;
+}
+// Contiguous variant: the probe rows z in [first, first + count) of every layer — a spatially compact share (the handle's rays stay
+// in one part of the scene, so its share of the hierarchy stays cached) where the scene's cost is even along z.
+int DDGI_API(set_row_block)(anerend_ddgi_t* h, int32_t first, int32_t count) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
+  if (first < 0 || count < 1 || first + count > h->nXZ) return fail(h, ANEREND_DDGI_E_INVALID, "row block out of range");
+  h->rowOffset = first; h->rowStride = 1; h->Pl = count * h->nXZ;
   return 0;
 }
 // The atlas rows of this handle's stripe in all layers, packed in (layer, row) order: rows * nY blocks of 10 atlas rows.

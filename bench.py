@@ -245,7 +245,7 @@ def main():
     ap.add_argument("--fast-math", action="store_true", help="time the FAST_MATH build as the headline (default: exact build)")
     ap.add_argument("--no-extras", action="store_true", help="skip the atlas-consumer / ShadowRT / SpecularGIRT figures and the C5 1-GPU base")
     ap.add_argument("--no-alt", action="store_true", help="skip the second-build and 1-GPU strong-scaling-base measurements")
-    ap.add_argument("--deal", default=None, choices=["stripes", "measured", "static"],
+    ap.add_argument("--deal", default=None, choices=["stripes", "blocks", "measured", "static"],
                     help="N>1, fused exchange: every rank takes the probe rows z = rank mod N of every layer (default; needs nXZ "
                          "divisible by N), or whole layers dealt by measured per-layer cost, or by the static mirrored/zigzag rule")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
@@ -277,6 +277,9 @@ def main():
     interleaved = world > 1 and (mirrored or ny % world == 0)
     if args.deal is None:                      # peer push: row stripes; NCCL: the static mirrored slabs (the measured collective baseline)
         args.deal = "stripes" if args.exchange == "fused" else "static"
+    blocks = args.deal == "blocks"              # contiguous probe rows per rank instead of interleaved ones (same code path otherwise)
+    if blocks:
+        args.deal = "stripes"
     stripes = world > 1 and args.deal == "stripes" and nxz % world == 0
     measured_deal = world > 1 and args.exchange == "fused" and (args.deal == "measured" or (args.deal == "stripes" and not stripes))
     slab = (0, ny) if (interleaved or measured_deal or stripes) else sharding.slab_for_rank(ny, rank, world)
@@ -300,8 +303,14 @@ def main():
 
     def make_handle(hflags, hslab, connect=False, striped=True):
         hh = A.Ddgi(A.make_params(nxz, ny, nr, flags=hflags, slab=hslab, device=local_rank))
+        if world == 1 and os.environ.get("DDGI_BENCH_STRIPE"):      # profiling aid: ONE rank's share of an R-GPU run on one GPU, no exchange ("r,R")
+            r_, R_ = (int(v) for v in os.environ["DDGI_BENCH_STRIPE"].split(","))
+            hh.set_row_stripe(r_, R_)
         if stripes and striped:
-            hh.set_row_stripe(rank, world)
+            if blocks:
+                hh.set_row_block(rank * (nxz // world), nxz // world)
+            else:
+                hh.set_row_stripe(rank, world)
         hh.upload_scene(scene)
         hh.set_scene_ubo(scene.ubo)
         hh.build_accel()
@@ -687,7 +696,8 @@ def main():
         if balanced is not None:
             deal_desc = f"probe layers dealt to {world} ranks by measured per-layer cost (LPT)"
         if stripes:
-            deal_desc = f"row stripes: rank r updates the probe rows z = r mod {world} of every layer"
+            deal_desc = (f"row blocks: rank r updates the probe rows z in [r*{nxz // world}, (r+1)*{nxz // world}) of every layer" if blocks else
+                         f"row stripes: rank r updates the probe rows z = r mod {world} of every layer")
         details = {}
         assert flush == (name != "c5"), "config.l2 (workload_desc) must state what the timed loop does"
         details.update({"bvh8_nodes": int(info.num_nodes), "accel_build_ms": accel_ms,

@@ -261,6 +261,9 @@ int anerend_cuda_ddgi_specular_gi_device(anerend_ddgi_t* h, const void* d_depth,
  * share of every layer, so the ranks finish together whatever the scene looks like.  _download_atlas_stripe returns
  * this handle's rows of all layers, packed (layer, row): num_probes_y * rows * 10 * width * 8 bytes. */
 int anerend_cuda_ddgi_set_row_stripe(anerend_ddgi_t* h, int32_t offset, int32_t stride);
+/* The contiguous variant: the probe rows z in [first, first + count) of every layer (a spatially compact share; _download_atlas_stripe
+ * and the peer exchange follow it like a stripe). */
+int anerend_cuda_ddgi_set_row_block(anerend_ddgi_t* h, int32_t first, int32_t count);
 int anerend_cuda_ddgi_download_atlas_stripe(anerend_ddgi_t* h, void* rgba16f, size_t bytes);
 /* The same stripe on the read-back stream (see _download_atlas_async; _download_wait blocks until it has landed).  Allowed while a
  * peer exchange is connected: a handle's own rows are written by its own convolution only, and that convolution waits for the copy. */
