@@ -23,6 +23,7 @@ using namespace ddgi;
 
 // ------------------------------------------------------------------------------------------------ kernels
 DDGI_KERNEL(k_inst_xform, inst_xform_body, BuildCtx)
+DDGI_KERNEL(k_tri_instance, tri_instance_body, BuildCtx)
 DDGI_KERNEL(k_flatten_scene, flatten_tri_body, BuildCtx)
 DDGI_KERNEL(k_morton_codes, morton_body, BuildCtx)
 DDGI_KERNEL(k_lbvh_hierarchy, karras_body, BuildCtx)
@@ -71,6 +72,7 @@ struct anerend_ddgi {
   DInstance* dInstances = nullptr; InstXform* dXforms = nullptr; uint32_t* dTriInstance = nullptr;
   // acceleration structure
   uint32_t numTris = 0, numNodes = 0, bvhDepth = 0;
+  uint32_t capTris = 0, capInstances = 0; bool capTextured = false;      // what the buffers of the structure were allocated for (reused by rebuilds)
   float4* dWtri = nullptr; float4* dTriLo = nullptr; float4* dTriHi = nullptr; int* dSceneBounds = nullptr;
   uint4* dNodes = nullptr; float4* dBvhTris = nullptr; uint32_t* dNodeParent = nullptr; float4* dNodeLo = nullptr; float4* dNodeHi = nullptr;
   uint32_t* dNodePending = nullptr; uint32_t* dVisit = nullptr; uint32_t* dCounters = nullptr;
@@ -213,7 +215,7 @@ void freeAccel(anerend_ddgi* h) {
   be.free(h->dSmStatic); be.free(h->dSmDynamic); h->dSmStatic = nullptr; h->dSmDynamic = nullptr; h->smRes = 0; h->smValid = false; h->smDynamicValid = false; h->lmMovedValid = false;
   h->dInstances = nullptr; h->dXforms = nullptr; h->dTriInstance = nullptr; h->dWtri = nullptr; h->dTriLo = nullptr; h->dTriHi = nullptr;
   h->dNodes = nullptr; h->dBvhTris = nullptr; h->dNodeParent = nullptr; h->dNodeLo = nullptr; h->dNodeHi = nullptr; h->dNodePending = nullptr; h->dVisit = nullptr;
-  h->haveAccel = false; h->numTris = 0; h->numNodes = 0;
+  h->haveAccel = false; h->numTris = 0; h->numNodes = 0; h->capTris = 0; h->capInstances = 0;
 }
 void freeScene(anerend_ddgi* h) {
   Backend& be = h->be;
@@ -405,7 +407,7 @@ int buildLightMaps(anerend_ddgi* h) {
   h->smValid = false;                                     // the sun's map is made at the next trace, for the lightDir of that frame (ensureSunMap)
   if (!mapsEnabled(h)) { h->lmRes = 0; return 0; }
   const size_t ni = h->instances.size();
-  if (!h->dLmBase) { BE_CHECK(h, be.alloc(&h->dLmBase, ni)); BE_CHECK(h, be.alloc(&h->dLmMoved, ni)); }
+  if (!h->dLmBase) { BE_CHECK(h, be.alloc(&h->dLmBase, (size_t)h->capInstances)); BE_CHECK(h, be.alloc(&h->dLmMoved, (size_t)h->capInstances)); }
   BE_CHECK(h, be.d2d(h->dLmBase, h->dXforms, ni * sizeof(InstXform)));      // the pose both static maps are made with
   const uint32_t R = lightMapResolution(h);
   if (R == 0) { h->lmRes = 0; return 0; }
@@ -482,41 +484,93 @@ int ensureSunMap(anerend_ddgi* h) {
   return 0;
 }
 
+#ifndef DDGI_HOST_EMU
+// The last PLOC rounds in ONE block: once at most PLOC_TAIL clusters are left (after ~24 of ~52 rounds at C3) a round is a few
+// microseconds of work behind five launches; here the same round bodies run back to back with block barriers, the compaction
+// scan done in shared memory.  Does nothing while more clusters are left, so the host can launch it blindly after every batch.
+#define PLOC_TAIL 2048
+__global__ void __launch_bounds__(1024) k_ploc_tail(BuildCtx c, uint32_t* refA, float4* loA, float4* hiA, uint32_t* refB, float4* loB, float4* hiB) {
+  __shared__ uint32_t sWarp[32];
+  __shared__ uint32_t sM;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  if (tid == 0) sM = c.numTris - c.counters[3];
+  __syncthreads();
+  if (sM > PLOC_TAIL) return;
+  const uint32_t lim = min((uint32_t)PLOC_TAIL, c.numTris);      // the cluster arrays hold numTris entries
+  int cur = 0;
+  for (uint32_t guard = 0; guard < 4096u; ++guard) {
+    const uint32_t m = sM;
+    if (m <= 1u) break;
+    c.clRef = cur ? refB : refA; c.clLo = cur ? loB : loA; c.clHi = cur ? hiB : hiA;
+    c.clRefOut = cur ? refA : refB; c.clLoOut = cur ? loA : loB; c.clHiOut = cur ? hiA : hiB;
+    for (uint32_t i = tid; i < m; i += 1024u) ploc_nn_body(i, c);
+    __syncthreads();
+    for (uint32_t i = tid; i < lim; i += 1024u) ploc_merge_body(i, c);             // beyond m: keep = 0
+    __syncthreads();
+    // exclusive scan of keep[0 .. PLOC_TAIL): two consecutive entries per thread
+    const uint32_t k0 = 2u * tid < lim ? c.clKeep[2u * tid] : 0u, k1 = 2u * tid + 1u < lim ? c.clKeep[2u * tid + 1u] : 0u;
+    uint32_t v = k0 + k1;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, v, o); if (lane >= (uint32_t)o) v += u; }
+    if (lane == 31u) sWarp[warp] = v;
+    __syncthreads();
+    if (warp == 0) { uint32_t w = sWarp[lane]; for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, w, o); if (lane >= (uint32_t)o) w += u; } sWarp[lane] = w; }
+    __syncthreads();
+    const uint32_t base = (warp ? sWarp[warp - 1u] : 0u) + v - (k0 + k1);
+    if (2u * tid < lim) const_cast<uint32_t*>(c.clPos)[2u * tid] = base;
+    if (2u * tid + 1u < lim) const_cast<uint32_t*>(c.clPos)[2u * tid + 1u] = base + k0;
+    __syncthreads();
+    for (uint32_t i = tid; i < m; i += 1024u) ploc_compact_body(i, c);
+    __syncthreads();
+    if (tid == 0) sM = c.numTris - c.counters[3];
+    cur ^= 1;
+    __syncthreads();
+  }
+}
+#endif
+
 // flatten + LBVH + BVH8 collapse
 int buildAccel(anerend_ddgi* h) {
   Backend& be = h->be;
-  freeAccel(h);
   std::vector<DInstance> inst; uint32_t n = 0;
   int rc = selectInstances(h, inst, n); if (rc) return rc;
-  h->instances = inst; h->numTris = n;
   const uint32_t ni = (uint32_t)inst.size();
+  // A rebuild (visibility or cull bits flipped) of about the same size keeps every buffer, light maps included: no allocation, no
+  // device-wide synchronisation inside the frame.  Otherwise everything is released and allocated with some head room.
+  const bool reuse = h->capTris >= n && h->capInstances >= ni && h->capTris != 0 && h->capTextured == h->texturedScene;
+  if (!reuse) freeAccel(h);
+  h->haveAccel = false; h->numNodes = 0;
+  h->instances = inst; h->numTris = n;
   { // the selection this structure is built from, for refit_accel_device's check of GPU-written visibility / cull bits
     std::vector<uint32_t> sel(h->renderables.size());
     for (size_t i = 0; i < sel.size(); ++i) { const uint32_t v = h->renderables[i].visible; sel[i] = ((v & 1u) && !((v >> 1) & 1u)) ? 1u : 0u; }
-    be.free(h->dSelected); h->dSelected = nullptr;
-    BE_CHECK(h, be.alloc(&h->dSelected, sel.size()));
+    if (!reuse || !h->dSelected) { be.free(h->dSelected); h->dSelected = nullptr; BE_CHECK(h, be.alloc(&h->dSelected, sel.size())); }
     if (!h->dVisChanged) BE_CHECK(h, be.alloc(&h->dVisChanged, 1));
     BE_CHECK(h, be.h2d(h->dSelected, sel.data(), sel.size() * sizeof(uint32_t))); BE_CHECK(h, be.sync()); }
-  BE_CHECK(h, be.alloc(&h->dInstances, ni)); BE_CHECK(h, be.alloc(&h->dXforms, ni)); BE_CHECK(h, be.alloc(&h->dTriInstance, n));
+  const uint32_t capN = reuse ? h->capTris : n + n / 8u + 64u, capI = reuse ? h->capInstances : ni + ni / 8u + 16u;
+  if (!reuse) { BE_CHECK(h, be.alloc(&h->dInstances, capI)); BE_CHECK(h, be.alloc(&h->dXforms, capI)); BE_CHECK(h, be.alloc(&h->dTriInstance, capN)); }
   BE_CHECK(h, be.h2d(h->dInstances, inst.data(), ni * sizeof(DInstance)));
-  { std::vector<uint32_t> ti(n); for (uint32_t i = 0; i < ni; ++i) for (uint32_t t = 0; t < inst[i].numTris; ++t) ti[inst[i].firstTri + t] = i;
-    BE_CHECK(h, be.h2d(h->dTriInstance, ti.data(), n * sizeof(uint32_t))); BE_CHECK(h, be.sync()); }
+  BE_CHECK(h, be.sync());          // `inst` (pageable) has been staged
   if (n == 0) { h->numNodes = 0; h->bvhDepth = 0; h->haveAccel = true; return 0; }
+  { BuildCtx tc{}; tc.instances = h->dInstances; tc.numInstances = ni; tc.numTris = n; tc.triInstanceOut = h->dTriInstance;      // triangle -> instance, on the device
+    DDGI_LAUNCH(be, k_tri_instance, tri_instance_body, n, tc, 256); }
   const uint32_t nodeCap = n;   // every BVH8 node has >= 4 triangles below it and >= 2 children
-  BE_CHECK(h, be.alloc(&h->dWtri, 3 * (size_t)n)); BE_CHECK(h, be.alloc(&h->dTriLo, n)); BE_CHECK(h, be.alloc(&h->dTriHi, n));
-  BE_CHECK(h, be.alloc(&h->dNodes, 5 * (size_t)nodeCap)); BE_CHECK(h, be.alloc(&h->dBvhTris, 3 * (size_t)n));
-  BE_CHECK(h, be.alloc(&h->dNodeParent, nodeCap)); BE_CHECK(h, be.alloc(&h->dNodeLo, nodeCap)); BE_CHECK(h, be.alloc(&h->dNodeHi, nodeCap));
-  BE_CHECK(h, be.alloc(&h->dNodePending, nodeCap)); BE_CHECK(h, be.alloc(&h->dVisit, (size_t)n + 1));
-  BE_CHECK(h, be.alloc(&h->dShadeTris, 5 * (size_t)n));
-  if (h->texturedScene) BE_CHECK(h, be.alloc(&h->dShadeUV, 2 * (size_t)n));
+  if (!reuse) {
+    BE_CHECK(h, be.alloc(&h->dWtri, 3 * (size_t)capN)); BE_CHECK(h, be.alloc(&h->dTriLo, capN)); BE_CHECK(h, be.alloc(&h->dTriHi, capN));
+    BE_CHECK(h, be.alloc(&h->dNodes, 5 * (size_t)capN)); BE_CHECK(h, be.alloc(&h->dBvhTris, 3 * (size_t)capN));
+    BE_CHECK(h, be.alloc(&h->dNodeParent, capN)); BE_CHECK(h, be.alloc(&h->dNodeLo, capN)); BE_CHECK(h, be.alloc(&h->dNodeHi, capN));
+    BE_CHECK(h, be.alloc(&h->dNodePending, capN)); BE_CHECK(h, be.alloc(&h->dVisit, (size_t)capN + 1));
+    BE_CHECK(h, be.alloc(&h->dShadeTris, 5 * (size_t)capN));
+    if (h->texturedScene) BE_CHECK(h, be.alloc(&h->dShadeUV, 2 * (size_t)capN));
+    h->capTris = capN; h->capInstances = capI; h->capTextured = h->texturedScene;
+  }
   // build-only scratch
   uint32_t *keys = nullptr, *ids = nullptr, *skeys = nullptr, *sids = nullptr, *left = nullptr, *right = nullptr, *parent = nullptr, *rf = nullptr, *rl = nullptr;
   float4 *blo = nullptr, *bhi = nullptr; CItem *qa = nullptr, *qb = nullptr;
-  BE_CHECK(h, be.alloc(&keys, n)); BE_CHECK(h, be.alloc(&ids, n)); BE_CHECK(h, be.alloc(&skeys, n)); BE_CHECK(h, be.alloc(&sids, n));
-  BE_CHECK(h, be.alloc(&left, n)); BE_CHECK(h, be.alloc(&right, n)); BE_CHECK(h, be.alloc(&parent, 2 * (size_t)n)); BE_CHECK(h, be.alloc(&rf, n)); BE_CHECK(h, be.alloc(&rl, n));
-  BE_CHECK(h, be.alloc(&blo, 2 * (size_t)n)); BE_CHECK(h, be.alloc(&bhi, 2 * (size_t)n)); BE_CHECK(h, be.alloc(&qa, n)); BE_CHECK(h, be.alloc(&qb, n));
-  auto freeScratch = [&]() { be.free(keys); be.free(ids); be.free(skeys); be.free(sids); be.free(left); be.free(right); be.free(parent); be.free(rf); be.free(rl);
-                             be.free(blo); be.free(bhi); be.free(qa); be.free(qb); };
+  BE_CHECK(h, be.allocScratch(&keys, n)); BE_CHECK(h, be.allocScratch(&ids, n)); BE_CHECK(h, be.allocScratch(&skeys, n)); BE_CHECK(h, be.allocScratch(&sids, n));
+  BE_CHECK(h, be.allocScratch(&left, n)); BE_CHECK(h, be.allocScratch(&right, n)); BE_CHECK(h, be.allocScratch(&parent, 2 * (size_t)n)); BE_CHECK(h, be.allocScratch(&rf, n)); BE_CHECK(h, be.allocScratch(&rl, n));
+  BE_CHECK(h, be.allocScratch(&blo, 2 * (size_t)n)); BE_CHECK(h, be.allocScratch(&bhi, 2 * (size_t)n)); BE_CHECK(h, be.allocScratch(&qa, n)); BE_CHECK(h, be.allocScratch(&qb, n));
+  auto freeScratch = [&]() { be.freeScratch(keys); be.freeScratch(ids); be.freeScratch(skeys); be.freeScratch(sids); be.freeScratch(left); be.freeScratch(right); be.freeScratch(parent);
+                             be.freeScratch(rf); be.freeScratch(rl); be.freeScratch(blo); be.freeScratch(bhi); be.freeScratch(qa); be.freeScratch(qb); };
   int initBounds[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
   BE_CHECK(h, be.h2d(h->dSceneBounds, initBounds, sizeof(initBounds)));
   BuildCtx c = buildCtx(h);
@@ -526,7 +580,8 @@ int buildAccel(anerend_ddgi* h) {
   DDGI_LAUNCH(be, k_inst_xform, inst_xform_body, ni, c, 128);
   DDGI_LAUNCH(be, k_flatten_scene, flatten_tri_body, n, c, 256);
   DDGI_LAUNCH(be, k_morton_codes, morton_body, n, c, 256);
-  if (!be.sortPairs(keys, skeys, ids, sids, n)) { freeScratch(); return fail(h, ANEREND_DDGI_E_CUDA, std::string("radix sort: ") + be.errStr()); }
+  void* sortTmp = nullptr;         // scratch of the radix sort: freed after the build's final synchronisation
+  if (!be.sortPairs(keys, skeys, ids, sids, n, &sortTmp)) { be.freeScratch(sortTmp); freeScratch(); return fail(h, ANEREND_DDGI_E_CUDA, std::string("radix sort: ") + be.errStr()); }
   uint32_t plocRadius = PLOC_RADIUS;
   if (const char* e = getenv("DDGI_PLOC_RADIUS")) plocRadius = (uint32_t)atoi(e);     // builder sweeps only (0 = plain LBVH); not part of the ABI
   if (plocRadius == 0) {
@@ -537,58 +592,79 @@ int buildAccel(anerend_ddgi* h) {
     // PLOC over the Morton order; scratch: two cluster arrays, neighbour / keep / scan words, subtree counts
     uint32_t *clRef[2] = {nullptr, nullptr}, *nn = nullptr, *keep = nullptr, *pos = nullptr, *sub = nullptr; float4 *clLo[2] = {nullptr, nullptr}, *clHi[2] = {nullptr, nullptr};
     void* scanTmp = nullptr; const size_t scanBytes = be.scanTempBytes(n);
-    bool okA = be.alloc(&clRef[0], n) && be.alloc(&clRef[1], n) && be.alloc(&clLo[0], n) && be.alloc(&clLo[1], n) && be.alloc(&clHi[0], n) && be.alloc(&clHi[1], n) &&
-               be.alloc(&nn, n) && be.alloc(&keep, n) && be.alloc(&pos, n) && be.alloc(&sub, 2 * (size_t)n) && be.alloc((uint8_t**)&scanTmp, scanBytes);
-    auto freePloc = [&]() { for (int k = 0; k < 2; ++k) { be.free(clRef[k]); be.free(clLo[k]); be.free(clHi[k]); } be.free(nn); be.free(keep); be.free(pos); be.free(sub); be.free(scanTmp); };
+    bool okA = be.allocScratch(&clRef[0], n) && be.allocScratch(&clRef[1], n) && be.allocScratch(&clLo[0], n) && be.allocScratch(&clLo[1], n) && be.allocScratch(&clHi[0], n) && be.allocScratch(&clHi[1], n) &&
+               be.allocScratch(&nn, n) && be.allocScratch(&keep, n) && be.allocScratch(&pos, n) && be.allocScratch(&sub, 2 * (size_t)n) && be.allocScratch((uint8_t**)&scanTmp, scanBytes);
+    auto freePloc = [&]() { for (int k = 0; k < 2; ++k) { be.freeScratch(clRef[k]); be.freeScratch(clLo[k]); be.freeScratch(clHi[k]); } be.freeScratch(nn); be.freeScratch(keep); be.freeScratch(pos); be.freeScratch(sub); be.freeScratch(scanTmp); };
     uint32_t zero = 0;      // parent[] = MISS everywhere: the root (ref 0) keeps it
     bool okP = okA && be.fill(parent, 0xFF, 2 * (size_t)n * sizeof(uint32_t)) && be.h2d(h->dCounters + 3, &zero, sizeof(uint32_t));
     c.clNN = nn; c.clKeep = keep; c.clPos = pos; c.subCount = sub; c.plocRadius = plocRadius;
     c.clRef = clRef[0]; c.clLo = clLo[0]; c.clHi = clHi[0];
     if (okP) DDGI_LAUNCH(be, k_ploc_init, ploc_init_body, n, c, 256);
+    // Rounds are launched in batches without a host round trip: every kernel takes the live cluster count from the device
+    // (numTris - counters[3]) and is launched over the last count the host has seen; rounds past the end of the hierarchy do nothing.
     uint32_t m = n, merged = 0; int cur = 0, rounds = 0;
+    const int batch = 8;
     while (okP && m > 1) {
-      c.numClusters = m;
-      c.clRef = clRef[cur]; c.clLo = clLo[cur]; c.clHi = clHi[cur]; c.clRefOut = clRef[cur ^ 1]; c.clLoOut = clLo[cur ^ 1]; c.clHiOut = clHi[cur ^ 1];
-      DDGI_LAUNCH(be, k_ploc_nn, ploc_nn_body, m, c, 128);
-      DDGI_LAUNCH(be, k_ploc_merge, ploc_merge_body, m, c, 128);
-      okP = be.exclusiveSum(scanTmp, scanBytes, keep, pos, m);
-      DDGI_LAUNCH(be, k_ploc_compact, ploc_compact_body, m, c, 256);
+      for (int k = 0; k < batch && okP; ++k) {
+        c.numClusters = m;
+        c.clRef = clRef[cur]; c.clLo = clLo[cur]; c.clHi = clHi[cur]; c.clRefOut = clRef[cur ^ 1]; c.clLoOut = clLo[cur ^ 1]; c.clHiOut = clHi[cur ^ 1];
+        DDGI_LAUNCH(be, k_ploc_nn, ploc_nn_body, m, c, 128);
+        DDGI_LAUNCH(be, k_ploc_merge, ploc_merge_body, m, c, 128);
+        okP = be.exclusiveSum(scanTmp, scanBytes, keep, pos, m);
+        DDGI_LAUNCH(be, k_ploc_compact, ploc_compact_body, m, c, 256);
+        cur ^= 1; ++rounds;
+      }
+#ifndef DDGI_HOST_EMU
+      if (okP && n > 1) {           // finishes the hierarchy in one launch once few clusters are left (a no-op before that)
+        k_ploc_tail<<<1, 1024, 0, be.stream>>>(c, clRef[cur], clLo[cur], clHi[cur], clRef[cur ^ 1], clLo[cur ^ 1], clHi[cur ^ 1]);
+        ++be.launches;
+      }
+#endif
       uint32_t total = 0;
       okP = okP && be.check() && be.d2h(&total, h->dCounters + 3, sizeof(uint32_t));
-      if (total <= merged) { okP = false; break; }     // no mutual pair: cannot happen with a consistent tie-break
-      m -= total - merged; merged = total; cur ^= 1; ++rounds;
+      if (total <= merged) { okP = false; break; }     // no mutual pair in a whole batch: cannot happen with a consistent tie-break
+      m = n - total; merged = total;
     }
     if (okP) {
       c.leafMap = keys; c.orderedIds = ids;            // the unsorted key/id arrays are free after the sort
       DDGI_LAUNCH(be, k_ploc_order, ploc_order_body, 2 * n - 1, c, 256);
       if (n > 1) DDGI_LAUNCH(be, k_ploc_relabel, ploc_relabel_body, n - 1, c, 256);
       c.sortedIds = ids;
-      okP = be.check() && be.sync();
+      okP = be.check();
     }
-    freePloc();
+    freePloc();            // stream-ordered: released when the kernels above have run
     if (!okP) { freeScratch(); return fail(h, ANEREND_DDGI_E_CUDA, std::string("ploc build: ") + be.errStr()); }
     h->plocRounds = rounds;
   }
-  // collapse, one launch per BVH8 level
-  uint32_t counters[3] = {1u, 0u, 0u};
-  BE_CHECK(h, be.h2d(h->dCounters, counters, sizeof(counters)));
+  // collapse, one launch per BVH8 level.  The queue length of every level is counted on the device (counters[CNT_LEVEL0 + level]); the
+  // host launches a batch of levels over an upper bound (8^level, at most one item per node) and looks once per batch whether
+  // the last level still produced work.
+  std::vector<uint32_t> counters(CNT_SIZE, 0u);
+  counters[0] = 1u; counters[CNT_LEVEL0] = 1u;
+  BE_CHECK(h, be.h2d(h->dCounters, counters.data(), CNT_SIZE * sizeof(uint32_t)));
   CItem root; root.ref = 0u; root.node = 0u;
   BE_CHECK(h, be.h2d(qa, &root, sizeof(root)));
   uint32_t missParent = DDGI_MISS;
   BE_CHECK(h, be.h2d(h->dNodeParent, &missParent, sizeof(uint32_t)));
-  uint32_t qlen = 1, depth = 0;
-  while (qlen > 0) {
-    uint32_t zero = 0; BE_CHECK(h, be.h2d(h->dCounters + 2, &zero, sizeof(uint32_t)));
-    c.qin = qa; c.qout = qb;
-    DDGI_LAUNCH(be, k_bvh8_collapse, collapse_body, qlen, c, 64);
-    if (!be.check() || !be.d2h(counters, h->dCounters, sizeof(counters))) { freeScratch(); return fail(h, ANEREND_DDGI_E_CUDA, std::string("bvh8 collapse: ") + be.errStr()); }
-    qlen = counters[2]; std::swap(qa, qb); ++depth;
-    if (depth > 1000) break;
+  uint32_t depth = 0;
+  for (bool more = true; more;) {
+    const uint32_t stop = std::min<uint32_t>(depth + 12u, (uint32_t)CNT_LEVELS);
+    for (; depth < stop; ++depth) {
+      uint64_t bound = 1; for (uint32_t k = 0; k < depth && bound < nodeCap; ++k) bound *= 8u;
+      c.qin = qa; c.qout = qb; c.level = depth;
+      DDGI_LAUNCH(be, k_bvh8_collapse, collapse_body, (uint32_t)std::min<uint64_t>(bound, nodeCap), c, 64);
+      std::swap(qa, qb);
+    }
+    if (!be.check() || !be.d2h(counters.data(), h->dCounters, CNT_SIZE * sizeof(uint32_t))) { freeScratch(); return fail(h, ANEREND_DDGI_E_CUDA, std::string("bvh8 collapse: ") + be.errStr()); }
+    more = counters[CNT_LEVEL0 + depth] != 0u && depth < (uint32_t)CNT_LEVELS;
   }
+  if (counters[CNT_LEVEL0 + depth] != 0u) { freeScratch(); return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "BVH8 deeper than the collapse supports"); }
+  depth = 0; while (depth < (uint32_t)CNT_LEVELS && counters[CNT_LEVEL0 + depth] != 0u) ++depth;        // levels that held work
   { int rcl = buildLightMaps(h); if (rcl) { freeScratch(); return rcl; } }
   be.mark(5);
   int bounds[6];
   bool okc = be.d2h(bounds, h->dSceneBounds, sizeof(bounds));
+  be.freeScratch(sortTmp);
   freeScratch();
   if (!okc) return fail(h, ANEREND_DDGI_E_CUDA, std::string("build: ") + be.errStr());
   for (int k = 0; k < 3; ++k) { h->boundsMin[k] = ordered_to_float(bounds[k]); h->boundsMax[k] = ordered_to_float(bounds[3 + k]); }
@@ -1029,7 +1105,7 @@ int DDGI_API(create)(const anerend_ddgi_params_t* params, anerend_ddgi_t** out) 
   const size_t texels = (size_t)h->W * h->H, rays = (size_t)h->nY * h->P * h->N;
   bool ok = be.alloc(&h->dAtlas, texels) && be.alloc(&h->dTemp, texels) && be.alloc(&h->dRayIrr, rays) &&
             be.alloc(&h->dDirs, (size_t)h->nY * h->N) && be.allocHostPinned(&h->hDirs, (size_t)h->nY * h->N) &&
-            be.alloc(&h->dSceneBounds, 6) && be.alloc(&h->dCounters, 4) && be.alloc(&h->dStats, 16) &&
+            be.alloc(&h->dSceneBounds, 6) && be.alloc(&h->dCounters, CNT_SIZE) && be.alloc(&h->dStats, 16) &&
             be.alloc(&h->dConvW, (size_t)h->nY * h->N * 64) && be.alloc(&h->dLayerMap, (size_t)h->nY) && be.allocHostPinned(&h->hLayerMap, (size_t)h->nY);
   if (ok && (q.flags & ANEREND_DDGI_FLAG_RAY_RECORDS)) ok = be.alloc(&h->dRecords, rays);
   if (ok && (q.flags & ANEREND_DDGI_FLAG_TEXEL_RECORDS)) ok = be.alloc(&h->dTexelRecords, texels);

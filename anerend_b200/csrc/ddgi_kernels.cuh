@@ -78,8 +78,17 @@ struct BuildCtx {
   uint32_t* clNN; uint32_t* clKeep; const uint32_t* clPos;  // nearest neighbour, survives-this-round flag, its exclusive scan
   uint32_t* subCount;         // triangles below each of the 2n-1 binary refs
   uint32_t* leafMap; uint32_t* orderedIds;                  // Morton position -> depth-first position; triangle ids in that order
-  uint32_t numClusters, plocRadius;
+  uint32_t numClusters, plocRadius;      // numClusters: upper bound of the launch; the live count is numTris - counters[3] (read on the device)
+  uint32_t* triInstanceOut;              // k_tri_instance: triangle -> index of the instance whose range [firstTri, firstTri + numTris) holds it
+  uint32_t level;                        // BVH8 collapse: queue length of this level = counters[CNT_LEVEL0 + level], the next level's is counted beside it
 };
+// counters[]: [0] BVH8 nodes allocated, [1] triangle slots allocated, [2] -, [3] PLOC merges so far, [4] clusters of the current PLOC round,
+// [CNT_LEVEL0 + L] work items of collapse level L.  Everything the build loops depend on stays on the device: the host launches
+// whole batches of rounds / levels sized by an upper bound and reads a counter back once per batch.
+#define CNT_ROUND_M 4
+#define CNT_LEVEL0 8
+#define CNT_LEVELS 64
+#define CNT_SIZE (CNT_LEVEL0 + CNT_LEVELS + 1)
 
 // ----------------------------------------------------------------------------------------------------
 // instance transforms + flatten (replaces tlas_update.comp's instance write and the driver BLAS/TLAS build inputs)
@@ -110,6 +119,12 @@ HD V3 xform_point(const float* o2w, V3 p) {
              o2w[2] * p.x + o2w[5] * p.y + o2w[8] * p.z + o2w[11]);
 }
 
+// instances are laid out in order of firstTri (selectInstances): upper-bound search, skipping instances without triangles
+HD void tri_instance_body(uint32_t t, const BuildCtx& c) {
+  uint32_t lo = 0, hi = c.numInstances;            // last instance with firstTri <= t
+  while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (c.instances[mid].firstTri <= t) lo = mid; else hi = mid; }
+  c.triInstanceOut[t] = lo;
+}
 HD int float_to_ordered(float f) { int i = (int)f2u(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
 HD float ordered_to_float(int i) { return u2f((uint32_t)(i >= 0 ? i : i ^ 0x7FFFFFFF)); }
 
@@ -251,7 +266,9 @@ HD float ploc_union_area(float4 alo, float4 ahi, float4 blo, float4 bhi) {
   return ex * ey + ey * ez + ez * ex;
 }
 HD void ploc_nn_body(uint32_t i, const BuildCtx& c) {
-  const int m = (int)c.numClusters, r = (int)c.plocRadius, ii = (int)i;
+  const int m = (int)(c.numTris - c.counters[3]), r = (int)c.plocRadius, ii = (int)i;      // counters[3] is at rest while this kernel runs
+  if (i == 0u) c.counters[CNT_ROUND_M] = (uint32_t)m;                                       // ... and is kept for the merge / compaction of the round
+  if (ii >= m) return;
   const float4 lo = c.clLo[i], hi = c.clHi[i];
   int b = ii - r < 0 ? 0 : ii - r, e = ii + r > m - 1 ? m - 1 : ii + r;
   float best = 3.0e38f; int bj = ii;
@@ -263,6 +280,7 @@ HD void ploc_nn_body(uint32_t i, const BuildCtx& c) {
   c.clNN[i] = (uint32_t)bj;
 }
 HD void ploc_merge_body(uint32_t i, const BuildCtx& c) {
+  if (i >= c.counters[CNT_ROUND_M]) { c.clKeep[i] = 0u; return; }      // beyond the live clusters: nothing for the scan to count
   uint32_t j = c.clNN[i];
   if (j == i || c.clNN[j] != i) { c.clKeep[i] = 1u; return; }
   if (j < i) { c.clKeep[i] = 0u; return; }   // absorbed by the lower partner
@@ -276,7 +294,7 @@ HD void ploc_merge_body(uint32_t i, const BuildCtx& c) {
   c.clRef[i] = id; c.clLo[i] = lo; c.clHi[i] = hi; c.clKeep[i] = 1u;
 }
 HD void ploc_compact_body(uint32_t i, const BuildCtx& c) {
-  if (!c.clKeep[i]) return;
+  if (i >= c.counters[CNT_ROUND_M] || !c.clKeep[i]) return;
   uint32_t o = c.clPos[i];
   c.clRefOut[o] = c.clRef[i]; c.clLoOut[o] = c.clLo[i]; c.clHiOut[o] = c.clHi[i];
 }
@@ -355,6 +373,7 @@ HD float half_area(V3 lo, V3 hi) { V3 e = hi - lo; return e.x * e.y + e.y * e.z 
 // traversal can order them with a XOR (Ylitie 2017 §3.2); internal children and leaf triangles are stored contiguously.
 HD void collapse_body(uint32_t i, const BuildCtx& c) {
   const uint32_t n = c.numTris;
+  if (i >= c.counters[CNT_LEVEL0 + c.level]) return;
   const CItem it = c.qin[i];
   auto isInternal = [&](uint32_t r) { return r < n - 1; };
   auto count = [&](uint32_t r) -> uint32_t { return isInternal(r) ? c.rangeLast[r] - c.rangeFirst[r] + 1u : 1u; };
@@ -405,7 +424,7 @@ HD void collapse_body(uint32_t i, const BuildCtx& c) {
     if (imask & (1u << s)) {
       uint32_t child = childBase + rank++;
       c.nodeParent[child] = it.node;
-      uint32_t qi = atomAdd(&c.counters[2], 1u);
+      uint32_t qi = atomAdd(&c.counters[CNT_LEVEL0 + c.level + 1u], 1u);
       CItem o; o.ref = r; o.node = child; c.qout[qi] = o;
     } else {
       uint32_t cnt = count(r), first = isInternal(r) ? c.rangeFirst[r] : r - (n - 1);

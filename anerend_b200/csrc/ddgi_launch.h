@@ -37,6 +37,9 @@ struct Backend {
     if (!ok(cudaGetDeviceCount(&cnt)) || cnt == 0) return false;
     if (device >= 0 && !ok(cudaSetDevice(device))) return false;
     if (!ok(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking))) return false;
+    { int dev = 0; cudaMemPool_t pool = nullptr; unsigned long long keep = ~0ull;           // freed scratch stays with the process
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      cudaGetLastError(); }
     for (auto& e : ev) if (!ok(cudaEventCreate(&e))) return false;
     if (!ok(cudaStreamCreateWithFlags(&dlStream, cudaStreamNonBlocking))) return false;
     if (!ok(cudaEventCreateWithFlags(&evResult, cudaEventDisableTiming)) || !ok(cudaEventCreateWithFlags(&evDownload, cudaEventDisableTiming))) return false;
@@ -67,6 +70,9 @@ struct Backend {
   void markCopy() { cudaEventRecord(evCopy, stream); copyPending = true; }
   template <class T> bool alloc(T** p, size_t count) { *p = nullptr; return ok(cudaMalloc((void**)p, (count ? count : 1) * sizeof(T))); }
   void free(void* p) { if (p) cudaFree(p); }
+  // stream-ordered scratch (build-only buffers): no device synchronisation, memory is kept in the pool between builds
+  template <class T> bool allocScratch(T** p, size_t count) { *p = nullptr; return ok(cudaMallocAsync((void**)p, (count ? count : 1) * sizeof(T), stream)); }
+  void freeScratch(void* p) { if (p) cudaFreeAsync(p, stream); }
   template <class T> bool allocHostPinned(T** p, size_t count) { return ok(cudaMallocHost((void**)p, (count ? count : 1) * sizeof(T))); }
   void freeHostPinned(void* p) { if (p) cudaFreeHost(p); }
   bool h2d(void* dst, const void* src, size_t bytes) { return bytes == 0 || ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream)); }
@@ -84,15 +90,14 @@ struct Backend {
   bool check() { return ok(cudaGetLastError()); }
   void mark(int i) { cudaEventRecord(ev[i], stream); }
   float elapsed(int a, int b) { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev[a], ev[b]) != cudaSuccess) { cudaGetLastError(); return 0.0f; } return ms; }
-  bool sortPairs(const uint32_t* kin, uint32_t* kout, const uint32_t* vin, uint32_t* vout, uint32_t n) {
+  // *tmpOut: the sort's scratch, to be freed by the caller once the stream has drained (no synchronisation here)
+  bool sortPairs(const uint32_t* kin, uint32_t* kout, const uint32_t* vin, uint32_t* vout, uint32_t n, void** tmpOut) {
     // 30-bit Morton keys.  CUB's DeviceRadixSort is the onesweep (single-pass, decoupled look-back) radix sort.
-    size_t bytes = 0; void* tmp = nullptr;
+    size_t bytes = 0; *tmpOut = nullptr;
     if (!ok(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, (int)n, 0, 30, stream))) return false;
-    if (!ok(cudaMalloc(&tmp, bytes ? bytes : 1))) return false;
-    bool r = ok(cub::DeviceRadixSort::SortPairs(tmp, bytes, kin, kout, vin, vout, (int)n, 0, 30, stream));
+    if (!ok(cudaMallocAsync(tmpOut, bytes ? bytes : 1, stream))) return false;
     launches += 4;
-    cudaStreamSynchronize(stream); cudaFree(tmp);
-    return r;
+    return ok(cub::DeviceRadixSort::SortPairs(*tmpOut, bytes, kin, kout, vin, vout, (int)n, 0, 30, stream));
   }
   // exclusive prefix sum (CUB decoupled look-back scan); `tmp` is caller-provided scratch of scanTempBytes(n)
   size_t scanTempBytes(uint32_t n) {
@@ -137,6 +142,8 @@ struct Backend {
   void free(void* p) { ::free(p); }
   template <class T> bool allocHostPinned(T** p, size_t count) { return alloc(p, count); }
   void freeHostPinned(void* p) { ::free(p); }
+  template <class T> bool allocScratch(T** p, size_t count) { return alloc(p, count); }
+  void freeScratch(void* p) { ::free(p); }
   bool h2d(void* d, const void* s, size_t b) { if (b) memcpy(d, s, b); return true; }
   bool d2h(void* d, const void* s, size_t b) { if (b) memcpy(d, s, b); return true; }
   bool d2hAsync(void* d, const void* s, size_t b) { if (b) memcpy(d, s, b); return true; }
@@ -151,7 +158,8 @@ struct Backend {
   bool check() { return true; }
   void mark(int i) { tp[i] = std::chrono::steady_clock::now(); }
   float elapsed(int a, int b) { return std::chrono::duration<float, std::milli>(tp[b] - tp[a]).count(); }
-  bool sortPairs(const uint32_t* kin, uint32_t* kout, const uint32_t* vin, uint32_t* vout, uint32_t n) {
+  bool sortPairs(const uint32_t* kin, uint32_t* kout, const uint32_t* vin, uint32_t* vout, uint32_t n, void** tmpOut) {
+    *tmpOut = nullptr;
     std::vector<uint32_t> idx(n); std::iota(idx.begin(), idx.end(), 0u);
     std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return kin[a] < kin[b]; });
     for (uint32_t i = 0; i < n; ++i) { kout[i] = kin[idx[i]]; vout[i] = vin[idx[i]]; }
