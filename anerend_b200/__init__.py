@@ -71,6 +71,9 @@ class Ddgi(DdgiHandle):
         assert len(data) == 128 * world
         self._call("exchange_connect", _C.c_char_p(data), _C.c_uint32(world), _C.c_uint32(rank))
 
+    def exchange_fence(self):
+        self._call("exchange_fence")
+
     def exchange_disconnect(self):
         self._call("exchange_disconnect")
 

@@ -414,6 +414,13 @@ def main():
             cv.append(t["convolve_ms"])
             hh.kernel_ms.append(t["rt_kernel_ms"])
             nl += t["kernel_launches"]          # our kernels only (the NCCL collective and torch's pack/unpack copies are not counted)
+        if multi and fused:
+            # the last update's push into the peers runs on the exchange stream: the timed region ends when it has landed
+            tail0, tail1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tail0.record(stream)
+            hh.exchange_fence()
+            tail1.record(stream)
+            ev.append((tail0, tail1))
         torch.cuda.synchronize()
         if multi:
             dist.barrier()

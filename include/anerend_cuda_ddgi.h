@@ -302,6 +302,11 @@ int anerend_cuda_ddgi_set_peer_atlases(anerend_ddgi_t* h, void* const* d_peers, 
 #define ANEREND_DDGI_EXCHANGE_BLOB_BYTES 128
 int anerend_cuda_ddgi_exchange_export(anerend_ddgi_t* h, void* blob, size_t bytes);
 int anerend_cuda_ddgi_exchange_connect(anerend_ddgi_t* h, const void* blobs, uint32_t world, uint32_t rank);
+/* With a connected exchange the push of an update's rows into the peers runs on a second stream, under the next update's tracing (only
+ * the hit shading samples the atlas, and waits for it).  _exchange_fence makes the handle's stream wait for the rows of the last update:
+ * call it before reading the atlas on that stream from outside the library (the library's own readers do), or to time a sequence of
+ * updates to its true end.  _sync waits for both streams. */
+int anerend_cuda_ddgi_exchange_fence(anerend_ddgi_t* h);
 int anerend_cuda_ddgi_exchange_disconnect(anerend_ddgi_t* h);
 /* CUDA stream (cudaStream_t) all work of this handle is issued on. */
 int anerend_cuda_ddgi_stream(anerend_ddgi_t* h, void** stream);
