@@ -101,7 +101,7 @@ struct anerend_ddgi {
 #endif
   // wavefront (fast) path scratch: hit records, surface records, visibility masks, per-light shadow queues
   float4* dHits = nullptr; float4* dSurf = nullptr; uint32_t* dLit = nullptr; uint32_t* dQueues = nullptr; uint32_t* dQcount = nullptr;
-  uint32_t* dHitq = nullptr; float4* dShadeTris = nullptr; float* dConvW = nullptr;
+  uint32_t* dHitq = nullptr; uint32_t* dHitqSorted = nullptr; float4* dShadeTris = nullptr; float* dConvW = nullptr;
   // bindless textures: descriptor table, texel pool, decode table (sRGB EOTF + UNORM); per-triangle uv records and per-ray
   // emissive exist only while some material is textured
   int32_t* dTileInfos = nullptr; uint32_t numTiles = 0;     // tileInfoBuffer (baked atlases of the paged tiles)
@@ -727,6 +727,7 @@ int ensureFastScratch(anerend_ddgi* h, size_t need, uint32_t nq) {
     h->dHits = nullptr; h->dSurf = nullptr; h->dLit = nullptr; h->dQueues = nullptr; h->dQcount = nullptr; h->dHitq = nullptr; h->fastRays = 0;
     BE_CHECK(h, be.alloc(&h->dHits, need)); BE_CHECK(h, be.alloc(&h->dSurf, 3 * need)); BE_CHECK(h, be.alloc(&h->dLit, need));
     BE_CHECK(h, be.alloc(&h->dQueues, (size_t)nq * need)); BE_CHECK(h, be.alloc(&h->dQcount, FAST_QC_SIZE)); BE_CHECK(h, be.alloc(&h->dHitq, need));
+    be.free(h->dHitqSorted); h->dHitqSorted = nullptr; BE_CHECK(h, be.alloc(&h->dHitqSorted, need));
     h->fastRays = need; h->fastQueues = nq;
     be.free(h->dEmisTex); h->dEmisTex = nullptr;
   }
@@ -790,6 +791,13 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   be.mark(8);
   if (cnt) k_trace<true, true><<<gs, 128, 0, be.stream>>>(f); else k_trace<true, false><<<gs, 128, 0, be.stream>>>(f);
   be.mark(9);
+  static const bool bucketHits = !getenv("DDGI_NO_HIT_BUCKETS");          // A/B measurements only
+  if (bucketHits && (h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) && h->numLights > 1u) {
+    f.hitqSorted = h->dHitqSorted;
+    k_hit_bucket<0><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
+    k_hit_bucket<1><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
+    be.launches += 2;
+  }
   { int rf = fenceExchange(h); if (rf) return rf; }      // the only kernel of the pass that samples the atlas
   BE_CHECK(h, be.ok((h->p.flags & ANEREND_DDGI_FLAG_FAST_MATH) ? launch_shade_fast(f, be.stream) : launch_shade_exact(f, be.stream)));
   be.mark(10);
@@ -1107,7 +1115,7 @@ void destroyHandle(anerend_ddgi* h) {
   be.free(h->dExtRays); be.free(h->dExtDist);
   be.free(h->dSrtPos); be.free(h->dSrtLit); be.free(h->dSrtQueue); be.free(h->dSrtQcount);
   be.free(h->dRecords); be.free(h->dTexelRecords); be.free(h->dStats); be.free(h->dSceneBounds); be.free(h->dCounters);
-  be.free(h->dHits); be.free(h->dSurf); be.free(h->dLit); be.free(h->dQueues); be.free(h->dQcount); be.free(h->dHitq); be.free(h->dConvW);
+  be.free(h->dHits); be.free(h->dSurf); be.free(h->dLit); be.free(h->dQueues); be.free(h->dQcount); be.free(h->dHitq); be.free(h->dHitqSorted); be.free(h->dConvW);
   be.destroy();
   delete h;
 }

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(128, MINB) k_shade(const FastCtx c) {
   const int P = t.nXZ * t.nXZ;
   const V3 sunL = normalize3x(-t.lightDir);
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nHits; i += gridDim.x * blockDim.x) {
-    const uint32_t idx = c.hitq[i];
+    const uint32_t idx = c.hitqSorted ? c.hitqSorted[i] : c.hitq[i];
     int layer = 0, probe = 0; uint32_t ray = 0; V3 origin;
     if (!EXT) {
       const uint32_t slot = idx % (uint32_t)t.N, probeLin = idx / (uint32_t)t.N;

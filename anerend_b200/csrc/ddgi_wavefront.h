@@ -32,7 +32,8 @@ static_assert(sizeof(ShadeTri) == 80, "ShadeTri is five float4");
 #define FAST_QC_PRIMARY FAST_QC(32)
 #define FAST_QC_SHADOW FAST_QC(33)
 #define FAST_QC_HITS FAST_QC(34)
-#define FAST_QC_SIZE FAST_QC(35)
+#define FAST_QC_BUCKET FAST_QC(35)      // 33 totals of the hit list's classes (number of unoccluded lights of a hit), then 33 scatter cursors
+#define FAST_QC_SIZE (FAST_QC(35) + 128)
 
 struct FastCtx {
   TraceCtx t;
@@ -44,6 +45,7 @@ struct FastCtx {
   uint32_t* lit;            // [rays] visibility bits written by k_trace_shadow
   uint32_t* queues;         // [numQueues][rays] ray indices needing a shadow ray towards light q (0 = sun)
   uint32_t* hitq;           // [rays] compacted indices of the rays that hit (k_shade runs over these with full warps)
+  uint32_t* hitqSorted;     // [rays] the same list grouped by the number of unoccluded lights (k_hit_bucket), or null
   uint32_t* qcount;         // FAST_QC_SIZE counters
   uint32_t totalRays, numQueues;
   // external-ray mode (SpecularGIRT: one ray per pixel instead of the probe rays; kernels instantiated with EXT = true)
