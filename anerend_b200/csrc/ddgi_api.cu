@@ -778,8 +778,13 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   be.mark(7);
   // default: 32 registers (2048 resident threads per SM), light-map look-ups two at a time — g7 sweep at C3: 0.125 ms against 0.128
   // (look-ups one by one), 0.136 (40 registers), 0.173 (56 registers), 0.156 / 0.176 (hits compacted per block first, 128 / 256 threads)
-  static const int prepVariant = getenv("DDGI_PREP_VARIANT") ? atoi(getenv("DDGI_PREP_VARIANT")) : 1;                  // sweeps only
+  // blocks of 128: the queue append ends in a block barrier, and a block waits for its slowest warp (0.117 ms against 0.123 with 256).
+  // A 16-bit copy of the bounds for these look-ups (25 MB instead of 100 MB behind them) was tried: 0.118 ms, the same — the look-ups wait
+  // for latency, not for bandwidth or L2 space.
+  static const int prepVariant = getenv("DDGI_PREP_VARIANT") ? atoi(getenv("DDGI_PREP_VARIANT")) : 7;                  // sweeps only
   if (prepVariant == 1 && prepBlock == 256) k_shade_prep<256, false, 2048, true><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
+  else if (prepVariant == 7) k_shade_prep<128, false, 2048, true><<<(n + 127u) / 128u, 128, 0, be.stream>>>(f);
+  else if (prepVariant == 8) k_shade_prep<64, false, 2048, true><<<(n + 63u) / 64u, 64, 0, be.stream>>>(f);
   else if (prepVariant == 2) k_shade_prep<256, false, 1536, false><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
   else if (prepVariant == 3) k_shade_prep<256, false, 1536, true><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
   else if (prepVariant == 4) k_shade_prep<256, false, 1024, true><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
