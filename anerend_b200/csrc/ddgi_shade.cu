@@ -159,10 +159,10 @@ __global__ void __launch_bounds__(128) k_conv_weights(const ConvFastCtx f) {
 
 #define CONV_CHUNK 128                // rays staged per pass through shared memory
 
-// CONV_PPT probes per thread, CONV_G = 4 * CONV_PPT probes per block (256 threads = 64 texels x 4 probe groups)
-template <int CONV_PPT>
-__global__ void __launch_bounds__(256) k_probe_convolve_fast(const ConvFastCtx f) {
-  constexpr int CONV_G = 4 * CONV_PPT;
+// CONV_PPT probes per thread, GROUPS probe groups per block (64 * GROUPS threads = 64 texels x GROUPS), CONV_G = GROUPS * CONV_PPT probes per block
+template <int CONV_PPT, int GROUPS = 4>
+__global__ void __launch_bounds__(64 * GROUPS) k_probe_convolve_fast(const ConvFastCtx f) {
+  constexpr int CONV_G = GROUPS * CONV_PPT, THREADS = 64 * GROUPS;
   const ConvCtx& c = f.c;
   __shared__ float4 sRad[CONV_G * CONV_CHUNK];                      // 32 KB
   const int P = c.nXZ * c.nXZ;
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) k_probe_convolve_fast(const ConvFastCtx f
     const int nr = min(CONV_CHUNK, c.N - r0);
     int bad = 0;
     __syncthreads();
-    for (int e = (int)threadIdx.x; e < CONV_G * CONV_CHUNK; e += 256) {
+    for (int e = (int)threadIdx.x; e < CONV_G * CONV_CHUNK; e += THREADS) {
       const int g = e / CONV_CHUNK, r = e % CONV_CHUNK;
       float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       if (g0 + g < c.Pl && r < nr) {
@@ -268,13 +268,23 @@ static cudaError_t launch_convolve_impl(const ConvFastCtx& f, cudaStream_t s) {
   const uint32_t nw = (uint32_t)c.numLayers * (uint32_t)c.N;
   if (nw == 0) return cudaSuccess;
   k_conv_weights<<<(8u * nw + 127u) / 128u, 128, 0, s>>>(f);
-  static int ppt = 0;              // probes per thread: sweeps only (DDGI_CONV_PPT)
-  if (!ppt) { const char* e = getenv("DDGI_CONV_PPT"); ppt = e ? atoi(e) : 4; }
-  const int G = 4 * (ppt == 2 ? 2 : ppt == 1 ? 1 : 4);
+  static int ppt = 0, groups = 0;  // probes per thread, probe groups per block: sweeps only (DDGI_CONV_PPT, DDGI_CONV_GROUPS)
+  if (!ppt) { const char* e = getenv("DDGI_CONV_PPT"); ppt = e ? atoi(e) : 4; const char* g = getenv("DDGI_CONV_GROUPS"); groups = g ? atoi(g) : 1; }      // 64-thread blocks of 4 probes: 0.062 ms at C3 against 0.069 with 256 threads / 16 probes
+  const int pp = ppt == 2 ? 2 : ppt == 1 ? 1 : ppt == 8 ? 8 : 4, gg = groups == 2 ? 2 : groups == 1 ? 1 : 4;
+  const int G = gg * pp;
   const uint32_t blocks = (uint32_t)c.numLayers * (uint32_t)((c.Pl + G - 1) / G);
-  if (ppt == 2) k_probe_convolve_fast<2><<<blocks, 256, 0, s>>>(f);
-  else if (ppt == 1) k_probe_convolve_fast<1><<<blocks, 256, 0, s>>>(f);
-  else k_probe_convolve_fast<4><<<blocks, 256, 0, s>>>(f);
+  if (gg == 4) {
+    if (pp == 2) k_probe_convolve_fast<2, 4><<<blocks, 256, 0, s>>>(f);
+    else if (pp == 1) k_probe_convolve_fast<1, 4><<<blocks, 256, 0, s>>>(f);
+    else k_probe_convolve_fast<4, 4><<<blocks, 256, 0, s>>>(f);
+  } else if (gg == 2) {
+    if (pp == 2) k_probe_convolve_fast<2, 2><<<blocks, 128, 0, s>>>(f);
+    else if (pp == 8) k_probe_convolve_fast<8, 2><<<blocks, 128, 0, s>>>(f);
+    else k_probe_convolve_fast<4, 2><<<blocks, 128, 0, s>>>(f);
+  } else {
+    if (pp == 8) k_probe_convolve_fast<8, 1><<<blocks, 64, 0, s>>>(f);
+    else k_probe_convolve_fast<4, 1><<<blocks, 64, 0, s>>>(f);
+  }
   return cudaGetLastError();
 }
 

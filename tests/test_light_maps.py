@@ -229,6 +229,34 @@ def _sun_sequence(scene, grid, make_o, make_p, dirs, move=False):
     return st
 
 
+def _sun_only(scene, grid, make_o, make_p):
+    """The faithful subset (no point lights, rchit:85-94): only the sun's map is in play."""
+    nxz, ny, nr = grid
+    fl = L.FLAG_RAY_RECORDS | L.FLAG_COUNTERS | L.FLAG_SKIP_DEAD_SHADOW_RAYS
+    o, g = make_o(make_params(nxz, ny, nr, flags=fl)), make_p(make_params(nxz, ny, nr, flags=fl))
+    rots = parity.setup_pair(scene, (o, g), seed=12)
+    for _ in range(2):
+        for h in (o, g):
+            h.update(-1, rots)
+    for layer in range(ny):
+        ro, rg = o.download_ray_records(layer), g.download_ray_records(layer)
+        assert np.array_equal(ro["prim"], rg["prim"]) and np.array_equal(ro["lit_mask"], rg["lit_mask"])
+    assert np.array_equal(o.download_atlas(), g.download_atlas())
+    so, sg = o.stats(), g.stats()
+    assert sg["shadow_rays"] + sg["shadow_rays_prefiltered"] == so["shadow_rays"] and sg["shadow_rays_prefiltered"] > 0
+    o.close()
+    g.close()
+
+
+def test_sun_only_faithful_subset(oracle, make_emu):
+    _sun_only(scenes.sponza_like(seed=8, grid=(6, 3, 64), curtain_res=8), (6, 3, 64), oracle.Oracle, make_emu)
+
+
+@pytest.mark.gpu
+def test_cuda_sun_only_faithful_subset(oracle, make_gpu):
+    _sun_only(scenes.sponza_like(seed=8, grid=(6, 3, 64), curtain_res=8), (6, 3, 64), oracle.Oracle, make_gpu)
+
+
 SUN_DIRS = [(0.3, -1.0, 0.2), (0.0, -1.0, 0.0), (-0.7, -0.4, 0.6), (1.0, -0.05, 0.0), (0.2, 1.0, 0.1), (0.0, 0.0, 0.0)]
 
 
