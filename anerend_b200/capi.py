@@ -39,6 +39,12 @@ class BvhInfo(C.Structure):
                 ("bounds_min", C.c_float * 3), ("bounds_max", C.c_float * 3)]
 
 
+class TwoLevelInfo(C.Structure):       # anerend_ddgi_two_level_info_t
+    _fields_ = [("num_meshes", C.c_uint32), ("stored_triangles", C.c_uint32), ("blas_nodes", C.c_uint32), ("tlas_nodes", C.c_uint32),
+                ("tlas_depth", C.c_uint32), ("blas_depth_max", C.c_uint32), ("accel_bytes", C.c_uint64), ("tlas_build_ms", C.c_float),
+                ("_pad", C.c_uint32)]
+
+
 class TextureDesc(C.Structure):        # anerend_texture_desc_t
     _fields_ = [("pixels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_uint32), ("clamp_to_edge", C.c_uint32)]
 
@@ -178,6 +184,11 @@ class DdgiHandle:
     def bvh_info(self):
         b = BvhInfo()
         self._call("get_bvh_info", C.byref(b))
+        return b
+
+    def two_level_info(self):
+        b = TwoLevelInfo()
+        self._call("get_two_level_info", C.byref(b))
         return b
 
     # ---- passes ----------------------------------------------------------------------------------

@@ -37,6 +37,9 @@ DDGI_KERNEL(k_ploc_relabel, ploc_relabel_body, BuildCtx)
 DDGI_KERNEL(k_bvh8_collapse, collapse_body, BuildCtx)
 DDGI_KERNEL(k_refit_tris, refit_tris_body, BuildCtx)
 DDGI_KERNEL(k_refit_nodes, refit_node_body, BuildCtx)
+DDGI_KERNEL(k_blas_prims, blas_prim_body, BlasPrimCtx)
+DDGI_KERNEL(k_blas_reloc, blas_reloc_body, BlasRelocCtx)
+DDGI_KERNEL(k_tlas_prims, tlas_prim_body, TlasPrimCtx)
 DDGI_KERNEL(k_probe_trace, trace_ray_body<false>, TraceCtx)
 DDGI_KERNEL(k_probe_trace_counted, trace_ray_body<true>, TraceCtx)
 DDGI_KERNEL(k_probe_convolve, conv_texel_body, ConvCtx)
@@ -77,6 +80,12 @@ struct anerend_ddgi {
   uint4* dNodes = nullptr; float4* dBvhTris = nullptr; uint32_t* dNodeParent = nullptr; float4* dNodeLo = nullptr; float4* dNodeHi = nullptr;
   uint32_t* dNodePending = nullptr; uint32_t* dVisit = nullptr; uint32_t* dCounters = nullptr;
   float boundsMin[3] = {0, 0, 0}, boundsMax[3] = {0, 0, 0};
+  // two-level structure (ANEREND_DDGI_FLAG_TWO_LEVEL): one hierarchy per distinct mesh behind the instance level's slots of the
+  // node / leaf arrays; numTris stays the number of flattened triangle ids, numNodes the nodes of the instance level
+  struct MeshBlas { uint32_t mesh, numTris, triBase, root, nodes, depth; };
+  std::vector<MeshBlas> blas; std::vector<uint32_t> tlasList;
+  uint2* dInstBlas = nullptr; uint32_t* dTlasList = nullptr;
+  uint32_t tlasCap = 0, blasTris = 0, blasNodes = 0, tlasDepth = 0, blasDepthMax = 0, primCap = 0; bool twoBuilt = false; float tlasMs = 0.0f;
 
   // pass resources
   uint2* dAtlas = nullptr; uint2* dTemp = nullptr;        // ProbeRaysConvTex, TempProbeTex
@@ -100,7 +109,7 @@ struct anerend_ddgi {
   cudaStream_t xStream = nullptr; cudaEvent_t evConv = nullptr, evXDone = nullptr; bool exchangePending = false;
 #endif
   // wavefront (fast) path scratch: hit records, surface records, visibility masks, per-light shadow queues
-  float4* dHits = nullptr; float4* dSurf = nullptr; uint32_t* dLit = nullptr; uint32_t* dQueues = nullptr; uint32_t* dQcount = nullptr;
+  float4* dHits = nullptr; float4* dSurf = nullptr; uint32_t* dLit = nullptr; uint32_t* dQueues = nullptr; uint32_t* dQcount = nullptr; uint32_t* dHitInst = nullptr;
   uint32_t* dHitq = nullptr; uint32_t* dHitqSorted = nullptr; float4* dShadeTris = nullptr; float* dConvW = nullptr;
   // bindless textures: descriptor table, texel pool, decode table (sRGB EOTF + UNORM); per-triangle uv records and per-ray
   // emissive exist only while some material is textured
@@ -221,6 +230,8 @@ void freeAccel(anerend_ddgi* h) {
   h->dInstances = nullptr; h->dXforms = nullptr; h->dTriInstance = nullptr; h->dWtri = nullptr; h->dTriLo = nullptr; h->dTriHi = nullptr;
   h->dNodes = nullptr; h->dBvhTris = nullptr; h->dNodeParent = nullptr; h->dNodeLo = nullptr; h->dNodeHi = nullptr; h->dNodePending = nullptr; h->dVisit = nullptr;
   h->haveAccel = false; h->numTris = 0; h->numNodes = 0; h->capTris = 0; h->capInstances = 0;
+  be.free(h->dInstBlas); be.free(h->dTlasList); h->dInstBlas = nullptr; h->dTlasList = nullptr;
+  h->blas.clear(); h->tlasList.clear(); h->twoBuilt = false; h->tlasCap = 0; h->blasTris = 0; h->blasNodes = 0; h->primCap = 0;
 }
 void freeScene(anerend_ddgi* h) {
   Backend& be = h->be;
@@ -356,7 +367,9 @@ int ensureBigQueue(anerend_ddgi* h) {
   return 0;
 }
 #endif
-bool mapsEnabled(const anerend_ddgi* h) { return !(h->p.flags & ANEREND_DDGI_FLAG_NO_LIGHT_MAPS) && h->numTris != 0; }
+bool twoLevel(const anerend_ddgi* h) { return (h->p.flags & ANEREND_DDGI_FLAG_TWO_LEVEL) != 0; }
+// the maps are rasterised from the world-space triangle copies, which a two-level structure does not keep
+bool mapsEnabled(const anerend_ddgi* h) { return !(h->p.flags & ANEREND_DDGI_FLAG_NO_LIGHT_MAPS) && h->numTris != 0 && !twoLevel(h); }
 int rasterSunMap(anerend_ddgi* h, unsigned long long* target, const uint32_t* moved) {
   Backend& be = h->be;
   const uint32_t R = moved ? h->smRes >> LM_DYN_SHIFT : h->smRes;          // the dynamic map is coarser: same frame, cells 2^shift times as wide
@@ -534,41 +547,12 @@ __global__ void __launch_bounds__(1024) k_ploc_tail(BuildCtx c, uint32_t* refA, 
 }
 #endif
 
-// flatten + LBVH + BVH8 collapse
-int buildAccel(anerend_ddgi* h) {
+// Morton codes -> radix sort -> PLOC (or Karras) hierarchy -> BVH8 collapse over `n` primitives whose boxes (c.triLo / c.triHi), 48-byte
+// leaf payloads (c.wtri) and bounds (c.sceneBounds) are in place.  c.nodes, c.bvhTris and the per-node arrays point at the first node /
+// leaf slot of THIS hierarchy (indices in the nodes are relative to them): the scene's one hierarchy, or one level of a two-level one.
+int buildHierarchy(anerend_ddgi* h, BuildCtx c, uint32_t n, uint32_t* numNodesOut, uint32_t* depthOut) {
   Backend& be = h->be;
-  std::vector<DInstance> inst; uint32_t n = 0;
-  int rc = selectInstances(h, inst, n); if (rc) return rc;
-  const uint32_t ni = (uint32_t)inst.size();
-  // A rebuild (visibility or cull bits flipped) of about the same size keeps every buffer, light maps included: no allocation, no
-  // device-wide synchronisation inside the frame.  Otherwise everything is released and allocated with some head room.
-  const bool reuse = h->capTris >= n && h->capInstances >= ni && h->capTris != 0 && h->capTextured == h->texturedScene;
-  if (!reuse) freeAccel(h);
-  h->haveAccel = false; h->numNodes = 0;
-  h->instances = inst; h->numTris = n;
-  { // the selection this structure is built from, for refit_accel_device's check of GPU-written visibility / cull bits
-    std::vector<uint32_t> sel(h->renderables.size());
-    for (size_t i = 0; i < sel.size(); ++i) { const uint32_t v = h->renderables[i].visible; sel[i] = ((v & 1u) && !((v >> 1) & 1u)) ? 1u : 0u; }
-    if (!reuse || !h->dSelected) { be.free(h->dSelected); h->dSelected = nullptr; BE_CHECK(h, be.alloc(&h->dSelected, sel.size())); }
-    if (!h->dVisChanged) BE_CHECK(h, be.alloc(&h->dVisChanged, 1));
-    BE_CHECK(h, be.h2d(h->dSelected, sel.data(), sel.size() * sizeof(uint32_t))); BE_CHECK(h, be.sync()); }
-  const uint32_t capN = reuse ? h->capTris : n + n / 8u + 64u, capI = reuse ? h->capInstances : ni + ni / 8u + 16u;
-  if (!reuse) { BE_CHECK(h, be.alloc(&h->dInstances, capI)); BE_CHECK(h, be.alloc(&h->dXforms, capI)); BE_CHECK(h, be.alloc(&h->dTriInstance, capN)); }
-  BE_CHECK(h, be.h2d(h->dInstances, inst.data(), ni * sizeof(DInstance)));
-  BE_CHECK(h, be.sync());          // `inst` (pageable) has been staged
-  if (n == 0) { h->numNodes = 0; h->bvhDepth = 0; h->haveAccel = true; return 0; }
-  { BuildCtx tc{}; tc.instances = h->dInstances; tc.numInstances = ni; tc.numTris = n; tc.triInstanceOut = h->dTriInstance;      // triangle -> instance, on the device
-    DDGI_LAUNCH(be, k_tri_instance, tri_instance_body, n, tc, 256); }
-  const uint32_t nodeCap = n;   // every BVH8 node has >= 4 triangles below it and >= 2 children
-  if (!reuse) {
-    BE_CHECK(h, be.alloc(&h->dWtri, 3 * (size_t)capN)); BE_CHECK(h, be.alloc(&h->dTriLo, capN)); BE_CHECK(h, be.alloc(&h->dTriHi, capN));
-    BE_CHECK(h, be.alloc(&h->dNodes, 5 * (size_t)capN)); BE_CHECK(h, be.alloc(&h->dBvhTris, 3 * (size_t)capN));
-    BE_CHECK(h, be.alloc(&h->dNodeParent, capN)); BE_CHECK(h, be.alloc(&h->dNodeLo, capN)); BE_CHECK(h, be.alloc(&h->dNodeHi, capN));
-    BE_CHECK(h, be.alloc(&h->dNodePending, capN)); BE_CHECK(h, be.alloc(&h->dVisit, (size_t)capN + 1));
-    BE_CHECK(h, be.alloc(&h->dShadeTris, 5 * (size_t)capN));
-    if (h->texturedScene) BE_CHECK(h, be.alloc(&h->dShadeUV, 2 * (size_t)capN));
-    h->capTris = capN; h->capInstances = capI; h->capTextured = h->texturedScene;
-  }
+  const uint32_t nodeCap = n;   // every BVH8 node has >= 2 primitives below it and >= 2 children
   // build-only scratch
   uint32_t *keys = nullptr, *ids = nullptr, *skeys = nullptr, *sids = nullptr, *left = nullptr, *right = nullptr, *parent = nullptr, *rf = nullptr, *rl = nullptr;
   float4 *blo = nullptr, *bhi = nullptr; CItem *qa = nullptr, *qb = nullptr;
@@ -577,21 +561,15 @@ int buildAccel(anerend_ddgi* h) {
   BE_CHECK(h, be.allocScratch(&blo, 2 * (size_t)n)); BE_CHECK(h, be.allocScratch(&bhi, 2 * (size_t)n)); BE_CHECK(h, be.allocScratch(&qa, n)); BE_CHECK(h, be.allocScratch(&qb, n));
   auto freeScratch = [&]() { be.freeScratch(keys); be.freeScratch(ids); be.freeScratch(skeys); be.freeScratch(sids); be.freeScratch(left); be.freeScratch(right); be.freeScratch(parent);
                              be.freeScratch(rf); be.freeScratch(rl); be.freeScratch(blo); be.freeScratch(bhi); be.freeScratch(qa); be.freeScratch(qb); };
-  int initBounds[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
-  BE_CHECK(h, be.h2d(h->dSceneBounds, initBounds, sizeof(initBounds)));
-  BuildCtx c = buildCtx(h);
   c.mortonKeys = keys; c.triIds = ids; c.sortedKeys = skeys; c.sortedIds = sids; c.left = left; c.right = right; c.parent = parent;
-  c.rangeFirst = rf; c.rangeLast = rl; c.blo = blo; c.bhi = bhi; c.shadeTris = h->dShadeTris; c.shadeUV = h->dShadeUV;
-  be.mark(4);
-  DDGI_LAUNCH(be, k_inst_xform, inst_xform_body, ni, c, 128);
-  DDGI_LAUNCH(be, k_flatten_scene, flatten_tri_body, n, c, 256);
+  c.rangeFirst = rf; c.rangeLast = rl; c.blo = blo; c.bhi = bhi;
   DDGI_LAUNCH(be, k_morton_codes, morton_body, n, c, 256);
   void* sortTmp = nullptr;         // scratch of the radix sort: freed after the build's final synchronisation
   if (!be.sortPairs(keys, skeys, ids, sids, n, &sortTmp)) { be.freeScratch(sortTmp); freeScratch(); return fail(h, ANEREND_DDGI_E_CUDA, std::string("radix sort: ") + be.errStr()); }
   uint32_t plocRadius = PLOC_RADIUS;
   if (const char* e = getenv("DDGI_PLOC_RADIUS")) plocRadius = (uint32_t)atoi(e);     // builder sweeps only (0 = plain LBVH); not part of the ABI
   if (plocRadius == 0) {
-    BE_CHECK(h, be.zero(h->dVisit, ((size_t)n + 1) * sizeof(uint32_t)));
+    BE_CHECK(h, be.zero(c.visit, ((size_t)n + 1) * sizeof(uint32_t)));
     if (n > 1) DDGI_LAUNCH(be, k_lbvh_hierarchy, karras_body, n - 1, c, 256);
     DDGI_LAUNCH(be, k_lbvh_fit, fit_body, n, c, 256);
   } else {
@@ -651,7 +629,7 @@ int buildAccel(anerend_ddgi* h) {
   CItem root; root.ref = 0u; root.node = 0u;
   BE_CHECK(h, be.h2d(qa, &root, sizeof(root)));
   uint32_t missParent = DDGI_MISS;
-  BE_CHECK(h, be.h2d(h->dNodeParent, &missParent, sizeof(uint32_t)));
+  BE_CHECK(h, be.h2d(c.nodeParent, &missParent, sizeof(uint32_t)));
   uint32_t depth = 0;
   for (bool more = true; more;) {
     const uint32_t stop = std::min<uint32_t>(depth + 12u, (uint32_t)CNT_LEVELS);
@@ -666,16 +644,176 @@ int buildAccel(anerend_ddgi* h) {
   }
   if (counters[CNT_LEVEL0 + depth] != 0u) { freeScratch(); return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "BVH8 deeper than the collapse supports"); }
   depth = 0; while (depth < (uint32_t)CNT_LEVELS && counters[CNT_LEVEL0 + depth] != 0u) ++depth;        // levels that held work
-  { int rcl = buildLightMaps(h); if (rcl) { freeScratch(); return rcl; } }
-  be.mark(5);
-  int bounds[6];
-  bool okc = be.d2h(bounds, h->dSceneBounds, sizeof(bounds));
   be.freeScratch(sortTmp);
   freeScratch();
-  if (!okc) return fail(h, ANEREND_DDGI_E_CUDA, std::string("build: ") + be.errStr());
+  if (counters[1] != n) return fail(h, ANEREND_DDGI_E_CUDA, "bvh8 collapse lost primitives");
+  *numNodesOut = counters[0]; *depthOut = depth;
+  return 0;
+}
+
+// ---- two-level structure (ANEREND_DDGI_FLAG_TWO_LEVEL; ddgi_kernels.cuh "Two-level structure") --------------------------------
+// The instance level: transforms from the renderable buffer (tlas_update.comp:93-98), world boxes of the meshes' root boxes, and a
+// BVH8 with one instance per leaf slot over them.  This is all a moved, shown, hidden or culled instance costs
+// (UpdateTLASPass.cpp:198-228 rebuilds the TLAS every frame too).
+int rebuildTlas(anerend_ddgi* h) {
+  Backend& be = h->be;
+  const uint32_t ni = (uint32_t)h->instances.size(), nt = (uint32_t)h->tlasList.size();
+  be.mark(4);
+  std::vector<uint2> ib(ni);
+  for (uint32_t i = 0; i < ni; ++i) {
+    const anerend_ddgi::MeshBlas* mb = nullptr;
+    for (const auto& b : h->blas) if (b.mesh == h->instances[i].mesh) { mb = &b; break; }
+    ib[i] = mb ? make_uint2(mb->root, mb->triBase) : make_uint2(0u, 0u);
+  }
+  BE_CHECK(h, be.h2d(h->dInstances, h->instances.data(), ni * sizeof(DInstance)));
+  BE_CHECK(h, be.h2d(h->dInstBlas, ib.data(), ni * sizeof(uint2)));
+  BE_CHECK(h, be.h2d(h->dTlasList, h->tlasList.data(), nt * sizeof(uint32_t)));
+  int initBounds[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+  BE_CHECK(h, be.h2d(h->dSceneBounds, initBounds, sizeof(initBounds)));
+  BE_CHECK(h, be.sync());          // the staging vectors are pageable
+  BuildCtx c{};
+  c.renderables = h->dRenderables; c.instances = h->dInstances; c.xforms = h->dXforms; c.numInstances = ni;
+  DDGI_LAUNCH(be, k_inst_xform, inst_xform_body, ni, c, 128);
+  h->numNodes = 0; h->tlasDepth = 0;
+  if (nt == 0) { h->haveAccel = true; return 0; }
+  TlasPrimCtx tp{};
+  tp.instances = h->dInstances; tp.xforms = h->dXforms; tp.instBlas = h->dInstBlas; tp.tlasList = h->dTlasList; tp.nodeLo = h->dNodeLo; tp.nodeHi = h->dNodeHi;
+  tp.numInstances = nt; tp.wtri = h->dWtri; tp.triLo = h->dTriLo; tp.triHi = h->dTriHi; tp.sceneBounds = h->dSceneBounds;
+  DDGI_LAUNCH(be, k_tlas_prims, tlas_prim_body, nt, tp, 128);
+  c.numTris = nt; c.wtri = h->dWtri; c.triLo = h->dTriLo; c.triHi = h->dTriHi; c.sceneBounds = h->dSceneBounds;
+  c.nodes = h->dNodes; c.bvhTris = h->dBvhTris; c.nodeParent = h->dNodeParent; c.nodeLo = h->dNodeLo; c.nodeHi = h->dNodeHi;
+  c.nodePending = h->dNodePending; c.visit = h->dVisit; c.counters = h->dCounters; c.leafMax = 1u;
+  uint32_t nodes = 0, depth = 0;
+  { int rch = buildHierarchy(h, c, nt, &nodes, &depth); if (rch) return rch; }
+  be.mark(5);
+  int bounds[6];
+  if (!be.d2h(bounds, h->dSceneBounds, sizeof(bounds))) return fail(h, ANEREND_DDGI_E_CUDA, std::string("build: ") + be.errStr());
   for (int k = 0; k < 3; ++k) { h->boundsMin[k] = ordered_to_float(bounds[k]); h->boundsMax[k] = ordered_to_float(bounds[3 + k]); }
-  h->numNodes = counters[0]; h->bvhDepth = depth;
-  if (counters[1] != n) return fail(h, ANEREND_DDGI_E_CUDA, "bvh8 collapse lost triangles");
+  h->numNodes = nodes; h->tlasDepth = depth; h->bvhDepth = depth + h->blasDepthMax;
+  // worst case of the traversal stack: per instance level the remaining siblings and the node's own children, eight instance
+  // entries, the RESTORE entry, one entry per level of a mesh's hierarchy
+  if (2u * depth + 9u + h->blasDepthMax > (uint32_t)DDGI_STACK) return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "two-level structure deeper than the traversal stack");
+  h->tlasMs = be.elapsed(4, 5);
+  h->haveAccel = true;
+  return 0;
+}
+int buildAccelTwoLevel(anerend_ddgi* h) {
+  Backend& be = h->be;
+  std::vector<DInstance> inst; uint32_t n = 0;
+  int rc = selectInstances(h, inst, n); if (rc) return rc;
+  const uint32_t ni = (uint32_t)inst.size();
+  // the distinct meshes, in order of first use
+  std::vector<anerend_ddgi::MeshBlas> um; std::vector<uint32_t> list;
+  uint32_t total = 0, maxMesh = 0;
+  for (uint32_t i = 0; i < ni; ++i) {
+    if (inst[i].numTris == 0) continue;
+    list.push_back(i);
+    bool seen = false;
+    for (const auto& b : um) if (b.mesh == inst[i].mesh) { seen = true; break; }
+    if (seen) continue;
+    anerend_ddgi::MeshBlas b{}; b.mesh = inst[i].mesh; b.numTris = inst[i].numTris; b.triBase = total;
+    total += b.numTris; maxMesh = std::max(maxMesh, b.numTris); um.push_back(b);
+  }
+  // the meshes' hierarchies are kept while the same meshes (unchanged vertices) are in use: then only the instance level is rebuilt
+  bool reuse = h->twoBuilt && !h->verticesDirty && h->tlasCap >= ni && um.size() == h->blas.size() && h->capTextured == h->texturedScene;
+  for (size_t u = 0; reuse && u < um.size(); ++u) reuse = um[u].mesh == h->blas[u].mesh && um[u].numTris == h->blas[u].numTris;
+  h->haveAccel = false; h->numNodes = 0;
+  if (!reuse) {
+    freeAccel(h);
+    const uint32_t capI = ni + ni / 8u + 16u; const size_t all = (size_t)capI + total; const uint32_t primCap = std::max(capI, maxMesh);
+    BE_CHECK(h, be.alloc(&h->dInstances, capI)); BE_CHECK(h, be.alloc(&h->dXforms, capI)); BE_CHECK(h, be.alloc(&h->dInstBlas, capI)); BE_CHECK(h, be.alloc(&h->dTlasList, capI));
+    BE_CHECK(h, be.alloc(&h->dWtri, 3 * (size_t)primCap)); BE_CHECK(h, be.alloc(&h->dTriLo, primCap)); BE_CHECK(h, be.alloc(&h->dTriHi, primCap));
+    BE_CHECK(h, be.alloc(&h->dNodes, 5 * all)); BE_CHECK(h, be.alloc(&h->dBvhTris, 3 * all));
+    BE_CHECK(h, be.alloc(&h->dNodeParent, all)); BE_CHECK(h, be.alloc(&h->dNodeLo, all)); BE_CHECK(h, be.alloc(&h->dNodeHi, all));
+    BE_CHECK(h, be.alloc(&h->dNodePending, all)); BE_CHECK(h, be.alloc(&h->dVisit, (size_t)primCap + 1));
+    BE_CHECK(h, be.alloc(&h->dShadeTris, 5 * (size_t)total));
+    if (h->texturedScene) BE_CHECK(h, be.alloc(&h->dShadeUV, 2 * (size_t)total));
+    h->tlasCap = capI; h->capInstances = capI; h->primCap = primCap; h->blasTris = total; h->capTextured = h->texturedScene;
+    if (!h->dVisChanged) BE_CHECK(h, be.alloc(&h->dVisChanged, 1));
+    be.free(h->dSelected); h->dSelected = nullptr; BE_CHECK(h, be.alloc(&h->dSelected, h->renderables.size()));
+    h->blasNodes = 0; h->blasDepthMax = 0;
+    for (auto& b : um) {
+      const anerend_mesh_info_t& mi = h->meshes[b.mesh];
+      int initBounds[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+      BE_CHECK(h, be.h2d(h->dSceneBounds, initBounds, sizeof(initBounds)));
+      BE_CHECK(h, be.sync());
+      const size_t base = (size_t)capI + b.triBase;
+      BlasPrimCtx bp{};
+      bp.vertices = h->dVertices; bp.indices = h->dIndices; bp.vertexOffset = mi.vertex_offset; bp.indexOffset = mi.index_offset; bp.numTris = b.numTris;
+      bp.wtri = h->dWtri; bp.triLo = h->dTriLo; bp.triHi = h->dTriHi; bp.sceneBounds = h->dSceneBounds;
+      bp.shadeTris = h->dShadeTris + 5 * (size_t)b.triBase; bp.shadeUV = h->dShadeUV ? h->dShadeUV + 2 * (size_t)b.triBase : nullptr;
+      DDGI_LAUNCH(be, k_blas_prims, blas_prim_body, b.numTris, bp, 256);
+      BuildCtx c{};
+      c.numTris = b.numTris; c.wtri = h->dWtri; c.triLo = h->dTriLo; c.triHi = h->dTriHi; c.sceneBounds = h->dSceneBounds;
+      c.nodes = h->dNodes + 5 * base; c.bvhTris = h->dBvhTris + 3 * base; c.nodeParent = h->dNodeParent + base; c.nodeLo = h->dNodeLo + base; c.nodeHi = h->dNodeHi + base;
+      c.nodePending = h->dNodePending + base; c.visit = h->dVisit; c.counters = h->dCounters;
+      { int rch = buildHierarchy(h, c, b.numTris, &b.nodes, &b.depth); if (rch) return rch; }
+      BlasRelocCtx rl{h->dNodes, (uint32_t)base, (uint32_t)base};
+      DDGI_LAUNCH(be, k_blas_reloc, blas_reloc_body, b.nodes, rl, 256);
+      b.root = (uint32_t)base; h->blasNodes += b.nodes; h->blasDepthMax = std::max(h->blasDepthMax, b.depth);
+    }
+    BE_CHECK(h, be.check());
+    h->blas = um; h->twoBuilt = true; h->verticesDirty = false;
+  }
+  h->instances = inst; h->numTris = n; h->tlasList = list;
+  { std::vector<uint32_t> sel(h->renderables.size());
+    for (size_t i = 0; i < sel.size(); ++i) { const uint32_t v = h->renderables[i].visible; sel[i] = ((v & 1u) && !((v >> 1) & 1u)) ? 1u : 0u; }
+    BE_CHECK(h, be.h2d(h->dSelected, sel.data(), sel.size() * sizeof(uint32_t))); BE_CHECK(h, be.sync()); }
+  rc = rebuildTlas(h);
+  h->accelMs = h->tlasMs;
+  return rc;
+}
+
+// flatten + LBVH + BVH8 collapse
+int buildAccel(anerend_ddgi* h) {
+  if (twoLevel(h)) return buildAccelTwoLevel(h);
+  Backend& be = h->be;
+  std::vector<DInstance> inst; uint32_t n = 0;
+  int rc = selectInstances(h, inst, n); if (rc) return rc;
+  const uint32_t ni = (uint32_t)inst.size();
+  // A rebuild (visibility or cull bits flipped) of about the same size keeps every buffer, light maps included: no allocation, no
+  // device-wide synchronisation inside the frame.  Otherwise everything is released and allocated with some head room.
+  const bool reuse = h->capTris >= n && h->capInstances >= ni && h->capTris != 0 && h->capTextured == h->texturedScene;
+  if (!reuse) freeAccel(h);
+  h->haveAccel = false; h->numNodes = 0;
+  h->instances = inst; h->numTris = n;
+  { // the selection this structure is built from, for refit_accel_device's check of GPU-written visibility / cull bits
+    std::vector<uint32_t> sel(h->renderables.size());
+    for (size_t i = 0; i < sel.size(); ++i) { const uint32_t v = h->renderables[i].visible; sel[i] = ((v & 1u) && !((v >> 1) & 1u)) ? 1u : 0u; }
+    if (!reuse || !h->dSelected) { be.free(h->dSelected); h->dSelected = nullptr; BE_CHECK(h, be.alloc(&h->dSelected, sel.size())); }
+    if (!h->dVisChanged) BE_CHECK(h, be.alloc(&h->dVisChanged, 1));
+    BE_CHECK(h, be.h2d(h->dSelected, sel.data(), sel.size() * sizeof(uint32_t))); BE_CHECK(h, be.sync()); }
+  const uint32_t capN = reuse ? h->capTris : n + n / 8u + 64u, capI = reuse ? h->capInstances : ni + ni / 8u + 16u;
+  if (!reuse) { BE_CHECK(h, be.alloc(&h->dInstances, capI)); BE_CHECK(h, be.alloc(&h->dXforms, capI)); BE_CHECK(h, be.alloc(&h->dTriInstance, capN)); }
+  BE_CHECK(h, be.h2d(h->dInstances, inst.data(), ni * sizeof(DInstance)));
+  BE_CHECK(h, be.sync());          // `inst` (pageable) has been staged
+  if (n == 0) { h->numNodes = 0; h->bvhDepth = 0; h->haveAccel = true; return 0; }
+  { BuildCtx tc{}; tc.instances = h->dInstances; tc.numInstances = ni; tc.numTris = n; tc.triInstanceOut = h->dTriInstance;      // triangle -> instance, on the device
+    DDGI_LAUNCH(be, k_tri_instance, tri_instance_body, n, tc, 256); }
+  if (!reuse) {
+    BE_CHECK(h, be.alloc(&h->dWtri, 3 * (size_t)capN)); BE_CHECK(h, be.alloc(&h->dTriLo, capN)); BE_CHECK(h, be.alloc(&h->dTriHi, capN));
+    BE_CHECK(h, be.alloc(&h->dNodes, 5 * (size_t)capN)); BE_CHECK(h, be.alloc(&h->dBvhTris, 3 * (size_t)capN));
+    BE_CHECK(h, be.alloc(&h->dNodeParent, capN)); BE_CHECK(h, be.alloc(&h->dNodeLo, capN)); BE_CHECK(h, be.alloc(&h->dNodeHi, capN));
+    BE_CHECK(h, be.alloc(&h->dNodePending, capN)); BE_CHECK(h, be.alloc(&h->dVisit, (size_t)capN + 1));
+    BE_CHECK(h, be.alloc(&h->dShadeTris, 5 * (size_t)capN));
+    if (h->texturedScene) BE_CHECK(h, be.alloc(&h->dShadeUV, 2 * (size_t)capN));
+    h->capTris = capN; h->capInstances = capI; h->capTextured = h->texturedScene;
+  }
+  int initBounds[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+  BE_CHECK(h, be.h2d(h->dSceneBounds, initBounds, sizeof(initBounds)));
+  BuildCtx c = buildCtx(h);
+  c.shadeTris = h->dShadeTris; c.shadeUV = h->dShadeUV;
+  be.mark(4);
+  DDGI_LAUNCH(be, k_inst_xform, inst_xform_body, ni, c, 128);
+  DDGI_LAUNCH(be, k_flatten_scene, flatten_tri_body, n, c, 256);
+  uint32_t numNodes = 0, depth = 0;
+  { int rch = buildHierarchy(h, c, n, &numNodes, &depth); if (rch) return rch; }
+  { int rcl = buildLightMaps(h); if (rcl) return rcl; }
+  be.mark(5);
+  int bounds[6];
+  if (!be.d2h(bounds, h->dSceneBounds, sizeof(bounds))) return fail(h, ANEREND_DDGI_E_CUDA, std::string("build: ") + be.errStr());
+  for (int k = 0; k < 3; ++k) { h->boundsMin[k] = ordered_to_float(bounds[k]); h->boundsMax[k] = ordered_to_float(bounds[3 + k]); }
+  h->numNodes = numNodes; h->bvhDepth = depth;
   if (depth > DDGI_STACK) return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "BVH8 deeper than the traversal stack");
   h->accelMs = be.elapsed(4, 5);
   h->haveAccel = true; h->verticesDirty = false;
@@ -685,6 +823,11 @@ int buildAccel(anerend_ddgi* h) {
 int refitAccel(anerend_ddgi* h) {
   Backend& be = h->be;
   if (h->numTris == 0) return 0;
+  if (twoLevel(h)) {          // moved instances: the instance level is rebuilt; deformed vertices: their meshes' hierarchies too
+    int rc2 = h->verticesDirty ? buildAccelTwoLevel(h) : rebuildTlas(h);
+    h->timed[3] = true;
+    return rc2;
+  }
   BuildCtx c = buildCtx(h);
   c.sceneBounds = nullptr;
   const bool verticesChanged = h->verticesDirty;
@@ -728,6 +871,7 @@ int ensureFastScratch(anerend_ddgi* h, size_t need, uint32_t nq) {
     BE_CHECK(h, be.alloc(&h->dHits, need)); BE_CHECK(h, be.alloc(&h->dSurf, 3 * need)); BE_CHECK(h, be.alloc(&h->dLit, need));
     BE_CHECK(h, be.alloc(&h->dQueues, (size_t)nq * need)); BE_CHECK(h, be.alloc(&h->dQcount, FAST_QC_SIZE)); BE_CHECK(h, be.alloc(&h->dHitq, need));
     be.free(h->dHitqSorted); h->dHitqSorted = nullptr; BE_CHECK(h, be.alloc(&h->dHitqSorted, need));
+    be.free(h->dHitInst); h->dHitInst = nullptr; if (twoLevel(h)) BE_CHECK(h, be.alloc(&h->dHitInst, need));
     h->fastRays = need; h->fastQueues = nq;
     be.free(h->dEmisTex); h->dEmisTex = nullptr;
   }
@@ -740,10 +884,17 @@ int ensureFastGrids(anerend_ddgi* h) {
     int dev = 0, sms = 0, nb = 0;
     BE_CHECK(h, be.ok(cudaGetDevice(&dev))); BE_CHECK(h, be.ok(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)));
     h->sms = sms;
+    if (twoLevel(h)) {
+      BE_CHECK(h, be.ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<false, false, false, true>, 128, 0))); h->gridPrimary[0] = sms * (nb > 0 ? nb : 1);
+      BE_CHECK(h, be.ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<false, true, false, true>, 128, 0))); h->gridPrimary[1] = sms * (nb > 0 ? nb : 1);
+      BE_CHECK(h, be.ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<true, false, false, true>, 128, 0))); h->gridShadow[0] = sms * (nb > 0 ? nb : 1);
+      BE_CHECK(h, be.ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<true, true, false, true>, 128, 0))); h->gridShadow[1] = sms * (nb > 0 ? nb : 1);
+    } else {
     BE_CHECK(h, be.ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<false, false>, 128, 0))); h->gridPrimary[0] = sms * (nb > 0 ? nb : 1);
     BE_CHECK(h, be.ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<false, true>, 128, 0))); h->gridPrimary[1] = sms * (nb > 0 ? nb : 1);
     BE_CHECK(h, be.ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<true, false>, 128, 0))); h->gridShadow[0] = sms * (nb > 0 ? nb : 1);
     BE_CHECK(h, be.ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<true, true>, 128, 0))); h->gridShadow[1] = sms * (nb > 0 ? nb : 1);
+    }
     h->tune[0] = TUNE_NODE_STEPS; h->tune[1] = TUNE_REFILL_MIN; h->tune[2] = TUNE_REFILL_MIN; h->tune[3] = 0;
     h->tune[4] = TUNE_STEP_MIN; h->tune[5] = TUNE_TRI_MIN; h->tune[6] = 0; h->tune[7] = 0;
     if (const char* e = getenv("DDGI_TUNE")) {          // kernel-tuning sweeps only (tools/); not part of the ABI
@@ -762,7 +913,7 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   { int rcg = ensureFastGrids(h); if (rcg) return rcg; }
   FastCtx f{};
   f.t = c; f.shadeTris = h->dShadeTris; f.shadeUV = h->dShadeUV; f.emisTex = h->dEmisTex; f.hits = h->dHits; f.surf = h->dSurf; f.lit = h->dLit; f.queues = h->dQueues; f.hitq = h->dHitq;
-  f.qcount = h->dQcount; f.totalRays = n; f.numQueues = nq;
+  f.qcount = h->dQcount; f.totalRays = n; f.numQueues = nq; f.hitInst = h->dHitInst;
   f.surfStride = 3u; f.rawSunDir = 0u;
   for (int k = 0; k < 8; ++k) f.tune[k] = h->tune[k];
   f.tune[3] = 0x64646464u;                 // planes2: the PRMT constant travels as a kernel argument so the selector can be the immediate
@@ -773,8 +924,10 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   const bool cnt = (h->p.flags & ANEREND_DDGI_FLAG_COUNTERS) != 0;
   static const int prepBlock = getenv("DDGI_PREP_BLOCK") ? atoi(getenv("DDGI_PREP_BLOCK")) : PREP_BLOCK_DEFAULT;     // sweeps only
   const int gp = h->gridPrimary[cnt ? 1 : 0], gs = h->gridShadow[cnt ? 1 : 0];
+  const bool two = twoLevel(h);
   be.mark(6);
-  if (cnt) k_trace<false, true><<<gp, 128, 0, be.stream>>>(f); else k_trace<false, false><<<gp, 128, 0, be.stream>>>(f);
+  if (two) { if (cnt) k_trace<false, true, false, true><<<gp, 128, 0, be.stream>>>(f); else k_trace<false, false, false, true><<<gp, 128, 0, be.stream>>>(f); }
+  else if (cnt) k_trace<false, true><<<gp, 128, 0, be.stream>>>(f); else k_trace<false, false><<<gp, 128, 0, be.stream>>>(f);
   be.mark(7);
   // default: 32 registers (2048 resident threads per SM), light-map look-ups two at a time — g7 sweep at C3: 0.125 ms against 0.128
   // (look-ups one by one), 0.136 (40 registers), 0.173 (56 registers), 0.156 / 0.176 (hits compacted per block first, 128 / 256 threads)
@@ -782,7 +935,8 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   // A 16-bit copy of the bounds for these look-ups (25 MB instead of 100 MB behind them) was tried: 0.118 ms, the same — the look-ups wait
   // for latency, not for bandwidth or L2 space.
   static const int prepVariant = getenv("DDGI_PREP_VARIANT") ? atoi(getenv("DDGI_PREP_VARIANT")) : 7;                  // sweeps only
-  if (prepVariant == 1 && prepBlock == 256) k_shade_prep<256, false, 2048, true><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
+  if (two) k_shade_prep<128, false, 2048, true, true><<<(n + 127u) / 128u, 128, 0, be.stream>>>(f);
+  else if (prepVariant == 1 && prepBlock == 256) k_shade_prep<256, false, 2048, true><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
   else if (prepVariant == 7) k_shade_prep<128, false, 2048, true><<<(n + 127u) / 128u, 128, 0, be.stream>>>(f);
   else if (prepVariant == 8) k_shade_prep<64, false, 2048, true><<<(n + 63u) / 64u, 64, 0, be.stream>>>(f);
   else if (prepVariant == 2) k_shade_prep<256, false, 1536, false><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
@@ -794,7 +948,8 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   else if (prepBlock == 512) k_shade_prep<512><<<(n + 511u) / 512u, 512, 0, be.stream>>>(f);
   else k_shade_prep<256><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
   be.mark(8);
-  if (cnt) k_trace<true, true><<<gs, 128, 0, be.stream>>>(f); else k_trace<true, false><<<gs, 128, 0, be.stream>>>(f);
+  if (two) { if (cnt) k_trace<true, true, false, true><<<gs, 128, 0, be.stream>>>(f); else k_trace<true, false, false, true><<<gs, 128, 0, be.stream>>>(f); }
+  else if (cnt) k_trace<true, true><<<gs, 128, 0, be.stream>>>(f); else k_trace<true, false><<<gs, 128, 0, be.stream>>>(f);
   be.mark(9);
   static const bool bucketHits = !getenv("DDGI_NO_HIT_BUCKETS");          // A/B measurements only
   if (bucketHits && (h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) && h->numLights > 1u) {
@@ -913,7 +1068,7 @@ int texturesUsable(anerend_ddgi* h) {
 }
 TraceCtx sceneTraceCtx(anerend_ddgi* h) {
   TraceCtx c{};
-  c.nodes = h->dNodes; c.bvhTris = h->dBvhTris; c.numNodes = h->numNodes;
+  c.nodes = h->dNodes; c.bvhTris = h->dBvhTris; c.numNodes = h->numNodes; c.twoLevel = twoLevel(h) ? 1u : 0u;
   c.vertices = h->dVertices; c.indices = h->dIndices; c.materials = h->dMaterials;
   c.tex.textures = h->dTextures; c.tex.texPool = h->dTexPool; c.tex.srgbLut = h->dSrgbLut; c.tex.numTextures = h->numTextures;
   c.tex.tileInfos = h->dTileInfos; c.tex.numTiles = h->numTiles;
@@ -1120,7 +1275,7 @@ void destroyHandle(anerend_ddgi* h) {
   be.free(h->dExtRays); be.free(h->dExtDist);
   be.free(h->dSrtPos); be.free(h->dSrtLit); be.free(h->dSrtQueue); be.free(h->dSrtQcount);
   be.free(h->dRecords); be.free(h->dTexelRecords); be.free(h->dStats); be.free(h->dSceneBounds); be.free(h->dCounters);
-  be.free(h->dHits); be.free(h->dSurf); be.free(h->dLit); be.free(h->dQueues); be.free(h->dQcount); be.free(h->dHitq); be.free(h->dHitqSorted); be.free(h->dConvW);
+  be.free(h->dHits); be.free(h->dSurf); be.free(h->dLit); be.free(h->dQueues); be.free(h->dQcount); be.free(h->dHitq); be.free(h->dHitqSorted); be.free(h->dConvW); be.free(h->dHitInst);
   be.destroy();
   delete h;
 }
@@ -1414,6 +1569,16 @@ int DDGI_API(get_bvh_info)(anerend_ddgi_t* h, anerend_ddgi_bvh_info_t* o) {
   for (int k = 0; k < 3; ++k) { o->bounds_min[k] = h->boundsMin[k]; o->bounds_max[k] = h->boundsMax[k]; }
   return 0;
 }
+int DDGI_API(get_two_level_info)(anerend_ddgi_t* h, anerend_ddgi_two_level_info_t* o) {
+  if (!h || !o) return ANEREND_DDGI_E_INVALID;
+  memset(o, 0, sizeof(*o));
+  if (!twoLevel(h) || !h->twoBuilt) return 0;
+  o->num_meshes = (uint32_t)h->blas.size(); o->stored_triangles = h->blasTris; o->blas_nodes = h->blasNodes; o->tlas_nodes = h->numNodes;
+  o->tlas_depth = h->tlasDepth; o->blas_depth_max = h->blasDepthMax; o->tlas_build_ms = h->tlasMs;
+  const uint64_t ni = h->instances.size();
+  o->accel_bytes = 80ull * (h->blasNodes + h->numNodes) + 48ull * (h->blasTris + h->tlasList.size()) + 80ull * h->blasTris + (sizeof(InstXform) + sizeof(DInstance)) * ni;
+  return 0;
+}
 int DDGI_API(download_instances)(anerend_ddgi_t* h, anerend_ddgi_instance_t* out, size_t count) {
   if (!h) return ANEREND_DDGI_E_INVALID;
   if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "no acceleration structure");
@@ -1425,6 +1590,7 @@ int DDGI_API(download_instances)(anerend_ddgi_t* h, anerend_ddgi_instance_t* out
 int DDGI_API(download_bvh)(anerend_ddgi_t* h, void* nodes, size_t nb, void* tris, size_t tb) {
   if (!h) return ANEREND_DDGI_E_INVALID;
   if (!h->haveAccel) return fail(h, ANEREND_DDGI_E_STATE, "no acceleration structure");
+  if (twoLevel(h)) return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "download_bvh reads a one-level structure");
   if (nb != (size_t)h->numNodes * 80 || tb != (size_t)h->numTris * 48) return fail(h, ANEREND_DDGI_E_INVALID, "size mismatch");
   BE_CHECK(h, h->be.d2h(nodes, h->dNodes, nb)); BE_CHECK(h, h->be.d2h(tris, h->dBvhTris, tb));
   return 0;
@@ -1514,12 +1680,13 @@ int shadowRt(anerend_ddgi* h, const float* dDepth, uint32_t width, uint32_t heig
   if (n == 0) return 0;
   ShadowRtCtx c{};
   c.nodes = h->dNodes; c.bvhTris = h->dBvhTris; c.numNodes = h->numNodes; c.depth = dDepth; c.out = dOut; c.width = (int)width; c.height = (int)height;
+  c.xforms = h->dXforms; c.twoLevel = twoLevel(h) ? 1u : 0u;
   for (int k = 0; k < 16; ++k) c.invViewProj[k] = h->ubo.inv_view_proj[k];
   c.lightDir = mk3(h->ubo.light_dir[0], h->ubo.light_dir[1], h->ubo.light_dir[2]);
   c.tmin = 0.1f; c.tmax = 50.0f;                                        // literals of shadow.rgen:64-65
   c.screenW = (float)h->ubo.screen_width; c.screenH = (float)h->ubo.screen_height;
 #ifndef DDGI_HOST_EMU
-  if (!(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS) && h->numNodes > 0) {
+  if (!(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS) && h->numNodes > 0 && !twoLevel(h)) {
     // the persistent any-hit kernel over one queue of pixels; scratch of its own (a frame buffer is not a probe layer)
     if (h->srtPixels < n) {
       BE_CHECK(h, be.sync());
@@ -1592,7 +1759,7 @@ int specularGi(anerend_ddgi* h, const float* dDepth, const float4* dGeom0, uint3
   c.screenW = (float)h->ubo.screen_width; c.screenH = (float)h->ubo.screen_height;
 #ifndef DDGI_HOST_EMU
   static const bool specWavefront = getenv("DDGI_SPECULAR_SIMPLE") == nullptr;      // A/B switch: the one-thread-per-pixel kernel (5.9 ms vs 1.17 ms at 1080p)
-  if (specWavefront && !(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS) && h->numNodes > 0) {
+  if (specWavefront && !(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS) && h->numNodes > 0 && !twoLevel(h)) {
     // the wavefront kernels in external-ray mode: one reflected ray per pixel instead of the probe rays
     Backend& be = h->be;
     const uint32_t nq = 1u + ((h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) ? h->numLights : 0u);

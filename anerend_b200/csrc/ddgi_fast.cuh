@@ -34,6 +34,9 @@ struct RayState {
   uint2 ng;                         // current node group: child base | hit-children bits (ray order) << 24 | imask
   int sp;
   uint32_t npend;                   // parked triangle groups (0..2)
+  // two-level structures (TWO): the instance whose mesh is being walked (DDGI_MISS: instance level) — ox.. / idx.. / octm then
+  // describe the ray in its object space — and the slack of the slab parameters there (ObjRay::pad)
+  uint32_t inst; float px, py, pz;
 };
 
 #define LS_DIR 0                    // per-lane shared state, SoA [field][lane] of 16 bytes: (d.xyz, tag)
@@ -41,6 +44,7 @@ struct RayState {
 #define LS_PEND_A 2                 //   (triBase, hit bits, triMask, -)
 #define LS_PEND_B 3
 #define LS_FIELDS 4
+#define LS_ORG 4                    //   TWO only: (world-space origin, instance of the closest hit so far)
 
 // staged ray (shared memory, 3 x float4): (o.xyz, tmax) (d.xyz, tag) (1/d.xyz, aux)
 __device__ __forceinline__ void ray_stage(float4* s, V3 o, V3 d, float tmax, uint32_t tag, uint32_t aux) {
@@ -100,6 +104,7 @@ __device__ __forceinline__ uint32_t octant_permute(uint32_t x, uint32_t octm) {
 // 8 quantised child boxes against the ray; near/far planes are picked by the direction sign, so no per-child min/max
 // between lo and hi is needed.  Consumes the front child of r.ng (ray order), leaves the hit internal children in r.ng
 // and returns (triBase, hit triangle bits, triMask).
+template <bool TWO = false>
 __device__ __forceinline__ uint4 node_step(const uint4* __restrict__ nodes, RayState& r, uint2* stack, const float tmin, const uint32_t k64) {
   const int bit = 31 - __clz((int)r.ng.y);
   r.ng.y &= ~(1u << bit);
@@ -117,11 +122,13 @@ __device__ __forceinline__ uint4 node_step(const uint4* __restrict__ nodes, RayS
   const float ax = __uint_as_float((n0.w & 0xFFu) << 23) * r.idx;
   const float ay = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * r.idy;
   const float az = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * r.idz;
-  const float bx = fmaf(-1024.0f, ax, (__uint_as_float(n0.x) - r.ox) * r.idx);
-  const float by = fmaf(-1024.0f, ay, (__uint_as_float(n0.y) - r.oy) * r.idy);
-  const float bz = fmaf(-1024.0f, az, (__uint_as_float(n0.z) - r.oz) * r.idz);
+  float bx = fmaf(-1024.0f, ax, (__uint_as_float(n0.x) - r.ox) * r.idx);
+  float by = fmaf(-1024.0f, ay, (__uint_as_float(n0.y) - r.oy) * r.idy);
+  float bz = fmaf(-1024.0f, az, (__uint_as_float(n0.z) - r.oz) * r.idz);
   const float kF = 1.0000004f;          // far side widened: conservative against rounding in the slab arithmetic
-  const float axf = ax * kF, ayf = ay * kF, azf = az * kF, bxf = bx * kF, byf = by * kF, bzf = bz * kF;
+  const float axf = ax * kF, ayf = ay * kF, azf = az * kF;
+  float bxf = bx * kF, byf = by * kF, bzf = bz * kF;
+  if (TWO) { bx -= r.px; by -= r.py; bz -= r.pz; bxf += r.px; byf += r.py; bzf += r.pz; }      // object space: what the transforms may have lost
   const uint32_t acc = four_children<0>(nearx0, neary0, nearz0, farx0, fary0, farz0, ax, ay, az, bx, by, bz, axf, ayf, azf, bxf, byf, bzf, tmin, r.tmax, k64) |
                        four_children<1>(nearx1, neary1, nearz1, farx1, fary1, farz1, ax, ay, az, bx, by, bz, axf, ayf, azf, bxf, byf, bzf, tmin, r.tmax, k64);
   const uint32_t imask = n0.w >> 24;
@@ -138,11 +145,11 @@ __device__ __forceinline__ uint4 node_step(const uint4* __restrict__ nodes, RayS
 // shared memory (two groups per lane) and tested one per lane per iteration in a separate, short section, so lanes
 // that found none keep stepping through nodes instead of idling in a per-lane triangle loop.
 // ------------------------------------------------------------------------------------------------------------
-template <bool ANY, bool CNT, bool EXT = false>
-__global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
+template <bool ANY, bool CNT, bool EXT = false, bool TWO = false>
+__global__ void __launch_bounds__(128, TWO ? 6 : 8) k_trace(const FastCtx c) {
   const TraceCtx& t = c.t;
   __shared__ float4 sRay[4][32][3];
-  __shared__ float4 sLane[4][LS_FIELDS][32];
+  __shared__ float4 sLane[4][LS_FIELDS + (TWO ? 1 : 0)][32];
   __shared__ uint32_t sPrefix[34];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, ltMask = (1u << lane) - 1u;
   uint32_t total = c.totalRays;
@@ -160,8 +167,10 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
   float4* myDir = &sLane[warp][LS_DIR][lane];
   float4* myRes = &sLane[warp][LS_RES][lane];
   uint4* myPend = reinterpret_cast<uint4*>(&sLane[warp][LS_PEND_A][lane]);      // slot B = myPend + 32
+  float4* myOrg = &sLane[warp][TWO ? LS_ORG : LS_DIR][lane];                     // TWO only
   uint2 stack[DDGI_STACK];
   RayState r; r.sp = 0; r.npend = 0; r.ng = make_uint2(0, 0); r.tmax = 0.0f; r.octm = 0;
+  r.inst = DDGI_MISS; r.px = r.py = r.pz = 0.0f;
   r.ox = r.oy = r.oz = 0.0f; r.idx = r.idy = r.idz = 1.0f;
   bool active = false, exhausted = (total == 0u);
   uint32_t chunkNext = 0, chunkEnd = 0, staged = 0, stagedPos = 0;      // warp-uniform
@@ -241,6 +250,7 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
         r.ng = make_uint2(0u, 0x80000000u); r.sp = 0; r.npend = 0;
         *myDir = b;                                                 // (d.xyz, tag)
         *myRes = make_float4(0.0f, 0.0f, 0.0f, ANY ? cc.w : __uint_as_float(DDGI_MISS));
+        if (TWO) { *myOrg = make_float4(a.x, a.y, a.z, __uint_as_float(DDGI_MISS)); r.inst = DDGI_MISS; r.px = r.py = r.pz = 0.0f; }
         if (CNT && !ANY) ++nRays;
         if (!ANY && t.numNodes == 0u) c.hits[__float_as_uint(b.w)] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(DDGI_MISS));
         else active = true;
@@ -257,10 +267,45 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
       const bool hasNode = (r.ng.y & 0xFF000000u) != 0u || r.sp > 0;
       if (active && !finished) {
         if (hasNode && r.npend < 2u) {
-          if ((r.ng.y & 0xFF000000u) == 0u) r.ng = stack[--r.sp];
-          const uint4 tg = node_step(t.nodes, r, stack, t.tmin, k64);
-          if (CNT) ++cn;
-          if (tg.y) { myPend[32u * r.npend] = tg; ++r.npend; }
+          bool step = true;
+          if ((r.ng.y & 0xFF000000u) == 0u) {
+            const uint2 e = stack[--r.sp];
+            if (TWO && e.y == 0u) {
+              // two-level structure (ddgi_kernels.cuh traverse2): back to the world-space ray, or into an instance's object space
+              step = false;
+              const float4 o4 = *myOrg, d4 = *myDir;
+              if (e.x == TWO_RESTORE) {
+                r.ox = o4.x; r.oy = o4.y; r.oz = o4.z;
+                r.idx = 1.0f / safe_dir(d4.x); r.idy = 1.0f / safe_dir(d4.y); r.idz = 1.0f / safe_dir(d4.z);
+                r.px = r.py = r.pz = 0.0f; r.inst = DDGI_MISS;
+              } else {
+                r.inst = e.x & ~TWO_INSTANCE;
+                const InstXform& xf = t.xforms[r.inst];
+                const ObjRay q = object_ray(xf, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), r.tmax);
+                r.ox = q.o.x; r.oy = q.o.y; r.oz = q.o.z; r.idx = q.id.x; r.idy = q.id.y; r.idz = q.id.z; r.px = q.pad.x; r.py = q.pad.y; r.pz = q.pad.z;
+                stack[r.sp++] = make_uint2(TWO_RESTORE, 0u);
+                r.ng = make_uint2(__float_as_uint(xf._pad[0]), 0x80000000u);
+              }
+              const uint32_t octinv = 7u - ((r.idx < 0.0f ? 1u : 0u) | (r.idy < 0.0f ? 2u : 0u) | (r.idz < 0.0f ? 4u : 0u));
+              r.octm = ((octinv & 1u) ? 0x55u : 0u) | ((octinv & 2u) ? 0x3300u : 0u) | ((octinv & 4u) ? 0x0F0000u : 0u) | (octinv << 24);
+            } else r.ng = e;
+          }
+          if (step) {
+            const uint4 tg = node_step<TWO>(t.nodes, r, stack, t.tmin, k64);
+            if (CNT) ++cn;
+            if (TWO && r.inst == DDGI_MISS) {
+              // instance level: the instances met become stack entries, in front of this node's remaining children
+              if (tg.y) {
+                if (r.ng.y & 0xFF000000u) stack[r.sp++] = r.ng;
+                r.ng.y &= 0x00FFFFFFu;
+                for (uint32_t m = tg.y; m != 0u; m &= m - 1u) {
+                  const uint32_t bb = (uint32_t)__ffs((int)m) - 1u;
+                  const uint32_t rec = tg.x + (uint32_t)__popc(tg.z & ((1u << bb) - 1u));
+                  stack[r.sp++] = make_uint2(TWO_INSTANCE | __float_as_uint(__ldg(t.bvhTris + 3 * (size_t)rec).x), 0u);
+                }
+              }
+            } else if (tg.y) { myPend[32u * r.npend] = TWO ? make_uint4(tg.x, tg.y, tg.z, r.inst) : tg; ++r.npend; }
+          }
         } else if (!hasNode && r.npend == 0u) finished = true;
       }
       if (++k >= nodeSteps) break;
@@ -280,14 +325,24 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
         else { if (r.npend == 2u) myPend[0] = myPend[32]; --r.npend; }
         if (CNT) ++ct;
         float tt, u, v;
-        if (tri_intersect(mk3(r.ox, r.oy, r.oz), mk3(d4.x, d4.y, d4.z), mk3(a.x, a.y, a.z), mk3(a.w, bb.x, bb.y), mk3(bb.z, bb.w, cc.x),
-                          t.tmin, ANY ? r.tmax : 3.0e38f, tt, u, v)) {
-          const uint32_t prim = __float_as_uint(cc.y);
+        V3 ro = mk3(r.ox, r.oy, r.oz), v0 = mk3(a.x, a.y, a.z), e1 = mk3(a.w, bb.x, bb.y), e2 = mk3(bb.z, bb.w, cc.x);
+        uint32_t prim = __float_as_uint(cc.y);
+        if (TWO) {
+          // the record holds OBJECT-space vertices: the test runs in world space on the operands of the one-level structure
+          const InstXform& xf = t.xforms[g.w];
+          world_triangle(xf.o2w, a, bb, cc, v0, e1, e2);
+          const float4 o4 = *myOrg; ro = mk3(o4.x, o4.y, o4.z);
+          prim += __float_as_uint(xf._pad[1]);
+        }
+        if (tri_intersect(ro, mk3(d4.x, d4.y, d4.z), v0, e1, e2, t.tmin, ANY ? r.tmax : 3.0e38f, tt, u, v)) {
           if (ANY) { myRes->x = 1.0f; finished = true; }
           else {
             // closest hit: r.tmax is the best t so far (initially the ray's tMax, exclusive); ties -> lowest triangle id
             const uint32_t best = __float_as_uint(myRes->w);
-            if (tt < r.tmax || (tt == r.tmax && best != DDGI_MISS && prim < best)) { r.tmax = tt; *myRes = make_float4(tt, u, v, cc.y); }
+            if (tt < r.tmax || (tt == r.tmax && best != DDGI_MISS && prim < best)) {
+              r.tmax = tt; *myRes = make_float4(tt, u, v, __uint_as_float(prim));
+              if (TWO) myOrg->w = __uint_as_float(g.w);
+            }
           }
         }
         if (!finished) finished = r.npend == 0u && (r.ng.y & 0xFF000000u) == 0u && r.sp == 0;
@@ -304,6 +359,7 @@ __global__ void __launch_bounds__(128, 8) k_trace(const FastCtx c) {
       const uint32_t tag = __float_as_uint(myDir->w);
       if (!ANY) {
         c.hits[tag] = res;                                           // (t, u, v, prim); (0,0,0,MISS) for a miss
+        if (TWO) c.hitInst[tag] = __float_as_uint(myOrg->w);
         if (CNT && __float_as_uint(res.w) != DDGI_MISS) ++nHits;
       } else if (res.x == 0.0f) atomicOr(&c.lit[tag], 1u << __float_as_uint(res.w));      // miss shader: shadow = 0 -> lit
     }
@@ -340,7 +396,7 @@ __device__ __noinline__ float4 prep_textured_surface(const TexCtx tex, const flo
 }
 // One thread per ray; MINT = resident threads per SM the register budget must allow (2048: 32 registers — the kernel waits on
 // scattered reads (shading records, light-map texels), so threads in flight count for more than a few spills).
-template <int PREP_BLOCK, bool EXT = false, int MINT = 2048, bool BATCH = false>
+template <int PREP_BLOCK, bool EXT = false, int MINT = 2048, bool BATCH = false, bool TWO = false>
 __global__ void __launch_bounds__(PREP_BLOCK, MINT / PREP_BLOCK) k_shade_prep(const FastCtx c) {
   constexpr int PREP_WARPS = PREP_BLOCK / 32;
   const TraceCtx& t = c.t;
@@ -355,9 +411,12 @@ __global__ void __launch_bounds__(PREP_BLOCK, MINT / PREP_BLOCK) k_shade_prep(co
     if (hp != DDGI_MISS) {
       isHit = true;
       // rchit:27-38 through the per-triangle record (five independent 16-byte loads instead of the index/vertex gather)
-      const float4* st = c.shadeTris + 5 * (size_t)hp;
+      // two-level structure: the records are per MESH triangle, the instance comes with the hit
+      uint32_t rec = hp, hitInst = 0u;
+      if (TWO) { hitInst = c.hitInst[idx]; const InstXform& x0 = t.xforms[hitInst]; rec = __float_as_uint(x0._pad[2]) + (hp - __float_as_uint(x0._pad[1])); }
+      const float4* st = c.shadeTris + 5 * (size_t)rec;
       const float4 s0 = __ldg(st), s1 = __ldg(st + 1), s2 = __ldg(st + 2), s3 = __ldg(st + 3), s4 = __ldg(st + 4);
-      const uint32_t ii = __float_as_uint(s4.z), material = __float_as_uint(s4.w);
+      const uint32_t ii = TWO ? hitInst : __float_as_uint(s4.z), material = TWO ? t.instances[hitInst].material : __float_as_uint(s4.w);
       const InstXform& xf = t.xforms[ii];
       const float b0 = 1.0f - h.y - h.z, b1 = h.y, b2 = h.z;
       pos = mk3(s0.x, s0.y, s0.z) * b0 + mk3(s0.w, s1.x, s1.y) * b1 + mk3(s1.z, s1.w, s2.x) * b2;
@@ -392,7 +451,7 @@ __global__ void __launch_bounds__(PREP_BLOCK, MINT / PREP_BLOCK) k_shade_prep(co
                          mk3(v2->color[0], v2->color[1], v2->color[2]) * b2;
         albedo = mk3(to_linear1(color.x), to_linear1(color.y), to_linear1(color.z));
         if (textured) {
-          const float4 r = prep_textured_surface(t.tex, c.shadeUV, c.emisTex, m, hp, idx, h.y, h.z, make_float3(albedo.x, albedo.y, albedo.z),
+          const float4 r = prep_textured_surface(t.tex, c.shadeUV, c.emisTex, m, rec, idx, h.y, h.z, make_float3(albedo.x, albedo.y, albedo.z),
                                                  reinterpret_cast<float*>(&c.surf[3 * (size_t)idx + 2]) + 3);
           albedo = mk3(r.x, r.y, r.z); metallic = r.w; textureRough = true;
         }

@@ -81,6 +81,7 @@ struct BuildCtx {
   uint32_t numClusters, plocRadius;      // numClusters: upper bound of the launch; the live count is numTris - counters[3] (read on the device)
   uint32_t* triInstanceOut;              // k_tri_instance: triangle -> index of the instance whose range [firstTri, firstTri + numTris) holds it
   uint32_t level;                        // BVH8 collapse: queue length of this level = counters[CNT_LEVEL0 + level], the next level's is counted beside it
+  uint32_t leafMax;                      // primitives per leaf slot (0 = 3, triangles; 1 for the instance level of a two-level structure)
 };
 // counters[]: [0] BVH8 nodes allocated, [1] triangle slots allocated, [2] -, [3] PLOC merges so far, [4] clusters of the current PLOC round,
 // [CNT_LEVEL0 + L] work items of collapse level L.  Everything the build loops depend on stays on the device: the host launches
@@ -377,6 +378,7 @@ HD void collapse_body(uint32_t i, const BuildCtx& c) {
   const CItem it = c.qin[i];
   auto isInternal = [&](uint32_t r) { return r < n - 1; };
   auto count = [&](uint32_t r) -> uint32_t { return isInternal(r) ? c.rangeLast[r] - c.rangeFirst[r] + 1u : 1u; };
+  const uint32_t leafMax = c.leafMax ? c.leafMax : 3u;
   uint32_t ch[8]; int nch = 1; ch[0] = it.ref;
   for (int phase = 0; phase < 2; ++phase) {
     const uint32_t minCount = phase == 0 ? 4u : 2u;
@@ -411,7 +413,7 @@ HD void collapse_body(uint32_t i, const BuildCtx& c) {
   for (int k = 0; k < nch; ++k) childAt[slotOf[k]] = k;
   uint32_t nInternal = 0, nLeafTris = 0, imask = 0;
   for (int s = 0; s < 8; ++s) { int k = childAt[s]; if (k < 0) continue;
-    if (isInternal(ch[k]) && count(ch[k]) >= 4u) { imask |= 1u << s; ++nInternal; } else nLeafTris += count(ch[k]); }
+    if (isInternal(ch[k]) && count(ch[k]) > leafMax) { imask |= 1u << s; ++nInternal; } else nLeafTris += count(ch[k]); }
   uint32_t childBase = nInternal ? atomAdd(&c.counters[0], nInternal) : 0u;
   uint32_t triBase = nLeafTris ? atomAdd(&c.counters[1], nLeafTris) : 0u;
   V3 clo[8], chi[8];
@@ -502,9 +504,91 @@ HD void refit_node_body(uint32_t node0, const BuildCtx& c) {
 }
 
 // ----------------------------------------------------------------------------------------------------
+// Two-level structure (ANEREND_DDGI_FLAG_TWO_LEVEL): what the reference builds — one bottom-level structure per
+// MESH in object space (VulkanRenderer.cpp:1267-1417), one top-level structure over the instances tlas_update.comp:55-98 writes
+// (UpdateTLASPass.cpp:198-228, rebuilt every frame) — instead of one hierarchy over a world-space copy of every instance's
+// triangles.  Both levels are BVH8s made by the builder above (the instance level with one instance per leaf slot); they live in
+// one node array, the instance level first.  The leaf records of the instance level name the instance; InstXform carries the
+// root of its mesh's hierarchy, its first flattened triangle id and the base of its mesh's shading records.
+// ----------------------------------------------------------------------------------------------------
+struct BlasPrimCtx {
+  const anerend_vertex_t* vertices; const uint32_t* indices; uint32_t vertexOffset, indexOffset, numTris;
+  float4* wtri;                 // (p0, p1.x) (p1.yz, p2.xy) (p2.z, primitive, 0, 0): OBJECT-space vertices, not (v0, e1, e2)
+  float4* triLo; float4* triHi; int* sceneBounds;
+  float4* shadeTris; float4* shadeUV;       // per mesh triangle (instance / material words unused)
+};
+HD void blas_prim_body(uint32_t t, const BlasPrimCtx& c) {
+  V3 p[3]; float sr[18];
+  for (int k = 0; k < 3; ++k) {
+    const anerend_vertex_t& v = c.vertices[c.vertexOffset + c.indices[c.indexOffset + 3 * t + k]];
+    p[k] = mk3(v.pos[0], v.pos[1], v.pos[2]);
+    sr[3 * k] = v.pos[0]; sr[3 * k + 1] = v.pos[1]; sr[3 * k + 2] = v.pos[2];
+    sr[9 + 3 * k] = v.normal[0]; sr[9 + 3 * k + 1] = v.normal[1]; sr[9 + 3 * k + 2] = v.normal[2];
+  }
+  if (c.shadeTris) {
+    float4* o = c.shadeTris + 5 * (size_t)t;
+    o[0] = make_float4(sr[0], sr[1], sr[2], sr[3]); o[1] = make_float4(sr[4], sr[5], sr[6], sr[7]);
+    o[2] = make_float4(sr[8], sr[9], sr[10], sr[11]); o[3] = make_float4(sr[12], sr[13], sr[14], sr[15]);
+    o[4] = make_float4(sr[16], sr[17], 0.0f, 0.0f);
+  }
+  if (c.shadeUV) {
+    float uv[6];
+    for (int k = 0; k < 3; ++k) { const float* q = c.vertices[c.vertexOffset + c.indices[c.indexOffset + 3 * t + k]].uv; uv[2 * k] = q[0]; uv[2 * k + 1] = q[1]; }
+    c.shadeUV[2 * (size_t)t] = make_float4(uv[0], uv[1], uv[2], uv[3]);
+    c.shadeUV[2 * (size_t)t + 1] = make_float4(uv[4], uv[5], 0.0f, 0.0f);
+  }
+  c.wtri[3 * (size_t)t + 0] = make_float4(p[0].x, p[0].y, p[0].z, p[1].x);
+  c.wtri[3 * (size_t)t + 1] = make_float4(p[1].y, p[1].z, p[2].x, p[2].y);
+  c.wtri[3 * (size_t)t + 2] = make_float4(p[2].z, u2f(t), 0.0f, 0.0f);
+  V3 lo = min3(p[0], min3(p[1], p[2])), hi = max3(p[0], max3(p[1], p[2]));
+  V3 pad = mk3(1e-5f * fmaxf(1.0f, fmaxf(fabsf(lo.x), fabsf(hi.x))), 1e-5f * fmaxf(1.0f, fmaxf(fabsf(lo.y), fabsf(hi.y))),
+               1e-5f * fmaxf(1.0f, fmaxf(fabsf(lo.z), fabsf(hi.z))));
+  lo = lo - pad; hi = hi + pad;
+  c.triLo[t] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+  c.triHi[t] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+  atomMin(&c.sceneBounds[0], float_to_ordered(lo.x)); atomMin(&c.sceneBounds[1], float_to_ordered(lo.y)); atomMin(&c.sceneBounds[2], float_to_ordered(lo.z));
+  atomMax(&c.sceneBounds[3], float_to_ordered(hi.x)); atomMax(&c.sceneBounds[4], float_to_ordered(hi.y)); atomMax(&c.sceneBounds[5], float_to_ordered(hi.z));
+}
+// a mesh's hierarchy was built with indices relative to its own first node / first triangle slot: move them to where it lives
+struct BlasRelocCtx { uint4* nodes; uint32_t nodeBase, triBase; };
+HD void blas_reloc_body(uint32_t i, const BlasRelocCtx& c) {
+  uint4* w1 = c.nodes + 5 * ((size_t)c.nodeBase + i) + 1;
+  uint4 v = *w1; v.x += c.nodeBase; v.y += c.triBase; *w1 = v;
+}
+// the instances as the primitives of the top level: world box of the mesh's root box, leaf record = instance index
+struct TlasPrimCtx {
+  const DInstance* instances; InstXform* xforms; const uint2* instBlas;      // instBlas[i] = (root node of the mesh's hierarchy, base of its shading records)
+  const uint32_t* tlasList;     // primitive j of the instance level -> instance (those with triangles)
+  const float4* nodeLo; const float4* nodeHi; uint32_t numInstances;
+  float4* wtri; float4* triLo; float4* triHi; int* sceneBounds;
+};
+HD void tlas_prim_body(uint32_t j, const TlasPrimCtx& c) {
+  const uint32_t i = c.tlasList[j];
+  const uint2 ib = c.instBlas[i];
+  InstXform& xf = c.xforms[i];
+  xf._pad[0] = u2f(ib.x); xf._pad[1] = u2f(c.instances[i].firstTri); xf._pad[2] = u2f(ib.y);
+  const V3 blo = f4v(c.nodeLo[ib.x]), bhi = f4v(c.nodeHi[ib.x]);
+  V3 lo = mk3(3.0e38f), hi = mk3(-3.0e38f);
+  for (int k = 0; k < 8; ++k) {
+    const V3 w = xform_point(xf.o2w, mk3((k & 1) ? bhi.x : blo.x, (k & 2) ? bhi.y : blo.y, (k & 4) ? bhi.z : blo.z));
+    lo = min3(lo, w); hi = max3(hi, w);
+  }
+  V3 pad = mk3(1e-5f * fmaxf(1.0f, fmaxf(fabsf(lo.x), fabsf(hi.x))), 1e-5f * fmaxf(1.0f, fmaxf(fabsf(lo.y), fabsf(hi.y))),
+               1e-5f * fmaxf(1.0f, fmaxf(fabsf(lo.z), fabsf(hi.z))));
+  lo = lo - pad; hi = hi + pad;
+  c.wtri[3 * (size_t)j + 0] = make_float4(u2f(i), 0.0f, 0.0f, 0.0f);
+  c.wtri[3 * (size_t)j + 1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  c.wtri[3 * (size_t)j + 2] = make_float4(0.0f, u2f(j), 0.0f, 0.0f);
+  c.triLo[j] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+  c.triHi[j] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+  atomMin(&c.sceneBounds[0], float_to_ordered(lo.x)); atomMin(&c.sceneBounds[1], float_to_ordered(lo.y)); atomMin(&c.sceneBounds[2], float_to_ordered(lo.z));
+  atomMax(&c.sceneBounds[3], float_to_ordered(hi.x)); atomMax(&c.sceneBounds[4], float_to_ordered(hi.y)); atomMax(&c.sceneBounds[5], float_to_ordered(hi.z));
+}
+
+// ----------------------------------------------------------------------------------------------------
 // traversal (replaces traceRayEXT, rgen:96 and rchit:55).  Per-thread short-stack walk of the BVH8.
 // ----------------------------------------------------------------------------------------------------
-struct Hit { float t, u, v; uint32_t prim; };
+struct Hit { float t, u, v; uint32_t prim; uint32_t inst; };      // inst: two-level structures only
 
 HD float dotF(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
 HD V3 crossF(V3 a, V3 b) { return mk3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x))); }
@@ -594,6 +678,125 @@ HD bool traverse(const uint4* __restrict__ nodes, const float4* __restrict__ tri
   return hit.prim != DDGI_MISS;
 }
 
+// Two-level traversal (see "Two-level structure" above).  The walk starts in the instance level with the world-space ray; a leaf
+// hit there pushes an entry per instance; popping one moves the ray into the instance's object space (same parameter t: the
+// direction is not re-normalised) and walks the mesh's hierarchy, a RESTORE entry underneath brings the world-space ray back.
+// Boxes only cull: the ray/triangle test runs in WORLD space on the vertices transformed exactly as flatten_tri_body does, so
+// (t, u, v), the winning triangle and its flattened id are bit-identical to the one-level structure's and the oracle's.
+// Object-space box tests are widened by what fp32 loses in the transforms (TWO_PAD_K x the magnitudes involved).
+#define TWO_RESTORE 0x7FFFFFFFu
+#define TWO_INSTANCE 0x80000000u
+#define TWO_PAD_K 1e-5f
+struct ObjRay { V3 o, d, id, pad; uint32_t octinv; };      // pad: slack of the slab parameters per axis (t units)
+HD ObjRay object_ray(const InstXform& xf, V3 o, V3 d, float tmax) {
+  ObjRay r;
+  const float* m = xf.w2o; const float* c3 = xf.o2w + 9;
+  const V3 q = mk3(o.x - c3[0], o.y - c3[1], o.z - c3[2]);
+  r.o = mk3(m[0] * q.x + m[3] * q.y + m[6] * q.z, m[1] * q.x + m[4] * q.y + m[7] * q.z, m[2] * q.x + m[5] * q.y + m[8] * q.z);
+  r.d = mk3(m[0] * d.x + m[3] * d.y + m[6] * d.z, m[1] * d.x + m[4] * d.y + m[7] * d.z, m[2] * d.x + m[5] * d.y + m[8] * d.z);
+  r.id = mk3(1.0f / safe_dir(r.d.x), 1.0f / safe_dir(r.d.y), 1.0f / safe_dir(r.d.z));
+  r.octinv = 7u - ((r.id.x < 0.0f ? 1u : 0u) | (r.id.y < 0.0f ? 2u : 0u) | (r.id.z < 0.0f ? 4u : 0u));
+  // what the object-space point at parameter t <= tmax can be off by: rounding of the two products, of o - c3, of the world
+  // vertices, and the mismatch of w2o with the exact inverse of o2w
+  const V3 w = mk3(fabsf(o.x) + fabsf(c3[0]) + tmax * fabsf(d.x), fabsf(o.y) + fabsf(c3[1]) + tmax * fabsf(d.y), fabsf(o.z) + fabsf(c3[2]) + tmax * fabsf(d.z));
+  const float own = fmaxf(fmaxf(fabsf(r.o.x), fabsf(r.o.y)), fabsf(r.o.z)) + tmax * fmaxf(fmaxf(fabsf(r.d.x), fabsf(r.d.y)), fabsf(r.d.z));
+  const V3 e = mk3(fabsf(m[0]) * w.x + fabsf(m[3]) * w.y + fabsf(m[6]) * w.z + own, fabsf(m[1]) * w.x + fabsf(m[4]) * w.y + fabsf(m[7]) * w.z + own,
+                   fabsf(m[2]) * w.x + fabsf(m[5]) * w.y + fabsf(m[8]) * w.z + own);
+  r.pad = mk3(TWO_PAD_K * e.x * fabsf(r.id.x), TWO_PAD_K * e.y * fabsf(r.id.y), TWO_PAD_K * e.z * fabsf(r.id.z));
+  return r;
+}
+// world-space (v0, e1, e2) of an object-space triangle record, the operations of flatten_tri_body
+HD void world_triangle(const float* o2w, float4 a, float4 bb, float4 cc, V3& v0, V3& e1, V3& e2) {
+  const V3 w0 = xform_point(o2w, mk3(a.x, a.y, a.z)), w1 = xform_point(o2w, mk3(a.w, bb.x, bb.y)), w2 = xform_point(o2w, mk3(bb.z, bb.w, cc.x));
+  v0 = w0; e1 = w1 - w0; e2 = w2 - w0;
+}
+template <bool ANY, bool CNT>
+HD bool traverse2(const uint4* __restrict__ nodes, const float4* __restrict__ tris, uint32_t numNodes, const InstXform* __restrict__ xforms, V3 o, V3 d,
+                  float tmin, float tmax, Hit& hit, uint32_t& cntNodes, uint32_t& cntTris) {
+  hit.prim = DDGI_MISS; hit.t = tmax; hit.u = 0.0f; hit.v = 0.0f; hit.inst = DDGI_MISS;
+  if (numNodes == 0u) return false;
+  ObjRay w;                                      // the world-space ray in the same form
+  w.o = o; w.d = d; w.id = mk3(1.0f / safe_dir(d.x), 1.0f / safe_dir(d.y), 1.0f / safe_dir(d.z)); w.pad = mk3(0.0f);
+  w.octinv = 7u - ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
+  ObjRay r = w;
+  uint32_t inst = DDGI_MISS;                     // MISS: in the instance level
+  uint2 stack[DDGI_STACK]; int sp = 0;
+  uint2 ng = make_uint2(0u, 0x80000000u);
+  for (;;) {
+    uint2 tg; uint32_t tgAll;
+    {
+      const int bit = msb32(ng.y);
+      ng.y &= ~(1u << bit);
+      if (ng.y & 0xFF000000u) { if (sp < DDGI_STACK) stack[sp++] = ng; }
+      const uint32_t slot = ((uint32_t)bit - 24u) ^ r.octinv;
+      const uint32_t rel = (uint32_t)popc32(ng.y & ~(0xFFFFFFFFu << slot) & 0xFFu);
+      const uint4* nd = nodes + 5 * (size_t)(ng.x + rel);
+      const uint4 n0 = nd[0], n1 = nd[1], n2 = nd[2], n3 = nd[3], n4 = nd[4];
+      if (CNT) ++cntNodes;
+      const float adjx = u2f((n0.w & 0xFFu) << 23) * r.id.x, adjy = u2f(((n0.w >> 8) & 0xFFu) << 23) * r.id.y, adjz = u2f(((n0.w >> 16) & 0xFFu) << 23) * r.id.z;
+      const float orgx = (u2f(n0.x) - r.o.x) * r.id.x, orgy = (u2f(n0.y) - r.o.y) * r.id.y, orgz = (u2f(n0.z) - r.o.z) * r.id.z;
+      const float tcur = ANY ? tmax : hit.t;
+      uint32_t hitmask = 0;
+      const uint32_t imask = n0.w >> 24, triMask = n1.z;
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t leafBits = (triMask >> (3 * i)) & 7u;
+        if (!leafBits && !((imask >> i) & 1u)) continue;
+        const float tlx = fmaf((float)byte_of(n2.x, n2.y, i), adjx, orgx), thx = fmaf((float)byte_of(n3.z, n3.w, i), adjx, orgx);
+        const float tly = fmaf((float)byte_of(n2.z, n2.w, i), adjy, orgy), thy = fmaf((float)byte_of(n4.x, n4.y, i), adjy, orgy);
+        const float tlz = fmaf((float)byte_of(n3.x, n3.y, i), adjz, orgz), thz = fmaf((float)byte_of(n4.z, n4.w, i), adjz, orgz);
+        const float tn = fmaxf(fmaxf(fminf(tlx, thx) - r.pad.x, fminf(tly, thy) - r.pad.y), fmaxf(fminf(tlz, thz) - r.pad.z, tmin));
+        const float tfb = fminf(fminf(fmaxf(tlx, thx) + r.pad.x, fmaxf(tly, thy) + r.pad.y), fmaxf(tlz, thz) + r.pad.z) * 1.0000004f;
+        const float tf = fminf(tfb, tcur);
+        if (tn <= tf) {
+          if ((imask >> i) & 1u) hitmask |= 1u << (24u + ((uint32_t)i ^ r.octinv));
+          else hitmask |= leafBits << (3 * i);
+        }
+      }
+      ng = make_uint2(n1.x, (hitmask & 0xFF000000u) | (n0.w >> 24));
+      tg = make_uint2(n1.y, hitmask & 0x00FFFFFFu);
+      tgAll = triMask;
+    }
+    if (inst == DDGI_MISS) {
+      if (tg.y) {                                // instances met: they come before this node's remaining children
+        if (ng.y & 0xFF000000u) { if (sp < DDGI_STACK) stack[sp++] = ng; }
+        ng.y &= 0x00FFFFFFu;
+        while (tg.y) {
+          const int b = msb32(tg.y & (0u - tg.y));
+          tg.y &= tg.y - 1u;
+          const uint32_t rec = tg.x + (uint32_t)popc32(tgAll & ((1u << b) - 1u));
+          if (sp < DDGI_STACK) stack[sp++] = make_uint2(TWO_INSTANCE | f2u(tris[3 * (size_t)rec].x), 0u);
+        }
+      }
+    } else {
+      const InstXform& xf = xforms[inst];
+      while (tg.y) {
+        const int b = msb32(tg.y & (0u - tg.y));
+        tg.y &= tg.y - 1u;
+        const float4* tp = tris + 3 * (size_t)(tg.x + (uint32_t)popc32(tgAll & ((1u << b) - 1u)));
+        const float4 a = tp[0], bb = tp[1], cc = tp[2];
+        if (CNT) ++cntTris;
+        V3 v0, e1, e2; world_triangle(xf.o2w, a, bb, cc, v0, e1, e2);
+        float t, u, v;
+        if (tri_intersect(o, d, v0, e1, e2, tmin, tmax, t, u, v)) {
+          const uint32_t prim = f2u(xf._pad[1]) + f2u(cc.y);
+          if (ANY) { hit.t = t; hit.prim = prim; hit.inst = inst; return true; }
+          if (t < hit.t || (t == hit.t && prim < hit.prim)) { hit.t = t; hit.u = u; hit.v = v; hit.prim = prim; hit.inst = inst; }
+        }
+      }
+    }
+    while ((ng.y & 0xFF000000u) == 0u) {
+      if (sp == 0) return hit.prim != DDGI_MISS;
+      const uint2 e = stack[--sp];
+      if (e.y != 0u) { ng = e; break; }
+      if (e.x == TWO_RESTORE) { r = w; inst = DDGI_MISS; continue; }
+      inst = e.x & ~TWO_INSTANCE;
+      r = object_ray(xforms[inst], o, d, ANY ? tmax : hit.t);
+      if (sp < DDGI_STACK) stack[sp++] = make_uint2(TWO_RESTORE, 0u);
+      ng = make_uint2(f2u(xforms[inst]._pad[0]), 0x80000000u);
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------------
 // shading: irradiance_probe_update.rchit + pbr_light.glsl + bindless.glsl + octahedron_helpers.glsl
 // ----------------------------------------------------------------------------------------------------
@@ -605,6 +808,7 @@ struct TexCtx { const DTexture* textures; const uint8_t* texPool; const float* s
 
 struct TraceCtx {
   const uint4* nodes; const float4* bvhTris; uint32_t numNodes;
+  uint32_t twoLevel;           // ANEREND_DDGI_FLAG_TWO_LEVEL: instance level + per-mesh hierarchies (traverse2), no triInstance
   const anerend_vertex_t* vertices; const uint32_t* indices; const anerend_material_info_t* materials;
   const DInstance* instances; const InstXform* xforms; const uint32_t* triInstance;
   const anerend_light_t* lights; uint32_t numLights;
@@ -636,6 +840,11 @@ struct TraceCtx {
 // Row stripe (multi-GPU sharding inside the layers): launched probe `pl` of a layer -> probe index in the layer.  A handle
 // updates the probe rows z = rowOffset + k*rowStride of every layer it launches; (0, 1) = all rows.
 HD int stripe_probe(int pl, int nXZ, int rowOffset, int rowStride) { return ((pl / nXZ) * rowStride + rowOffset) * nXZ + pl % nXZ; }
+template <bool ANY, bool CNT>
+HD bool traverse_scene(const TraceCtx& c, V3 o, V3 d, float tmin, float tmax, Hit& hit, uint32_t& cn, uint32_t& ct) {
+  if (c.twoLevel) return traverse2<ANY, CNT>(c.nodes, c.bvhTris, c.numNodes, c.xforms, o, d, tmin, tmax, hit, cn, ct);
+  return traverse<ANY, CNT>(c.nodes, c.bvhTris, c.numNodes, o, d, tmin, tmax, hit, cn, ct);
+}
 
 // ----------------------------------------------------------------------------------------------------
 // Light maps: a pre-filter for the point-light shadow rays of extension E1 (rchit:45-66 composed with calcLight's point branch).
@@ -1173,6 +1382,7 @@ HD void indirect_diffuse_body(uint32_t i, const ConsumerCtx& c) {
 // any-hit ray towards -lightDir (NOT normalised, as in the shader), r32f result: 1 = lit or sky, 0 = shadowed.
 struct ShadowRtCtx {
   const uint4* nodes; const float4* bvhTris; uint32_t numNodes;
+  const InstXform* xforms; uint32_t twoLevel;      // two-level structure (traverse2)
   const float* depth; float* out; int width, height;
   float invViewProj[16]; V3 lightDir; float tmin, tmax; float screenW, screenH;
 };
@@ -1191,7 +1401,8 @@ HD void shadow_rt_body(uint32_t i, const ShadowRtCtx& c) {
   if (depthSamp == 1.0f) { c.out[i] = 1.0f; return; }      // sky (shadow.rgen:45-48)
   const V3 origin = shadow_rt_world_pos(c, px, py, depthSamp);
   Hit sh; uint32_t cn = 0, ct = 0;
-  const bool occluded = traverse<true, false>(c.nodes, c.bvhTris, c.numNodes, origin, -c.lightDir, c.tmin, c.tmax, sh, cn, ct);
+  const bool occluded = c.twoLevel ? traverse2<true, false>(c.nodes, c.bvhTris, c.numNodes, c.xforms, origin, -c.lightDir, c.tmin, c.tmax, sh, cn, ct)
+                                   : traverse<true, false>(c.nodes, c.bvhTris, c.numNodes, origin, -c.lightDir, c.tmin, c.tmax, sh, cn, ct);
   c.out[i] = occluded ? 0.0f : 1.0f;                       // payload starts at 0, shadow.rmiss sets 1
 }
 
@@ -1199,7 +1410,7 @@ HD void shadow_rt_body(uint32_t i, const ShadowRtCtx& c) {
 // normal transform and in the flag that gates the indirect term).  origin = gl_WorldRayOriginEXT.
 template <bool CNT, bool SPECULAR>
 HD V3 shade_hit_simple(const TraceCtx& c, const Hit& hit, V3 origin, uint32_t& lit, uint32_t& nShadow, uint32_t& nPre, uint32_t& nCand, uint32_t* cn, uint32_t* ct, V3& hitPos) {
-  const uint32_t ii = c.triInstance[hit.prim];
+  const uint32_t ii = c.twoLevel ? hit.inst : c.triInstance[hit.prim];
   const DInstance in = c.instances[ii];
   const InstXform& xf = c.xforms[ii];
   const uint32_t prim = hit.prim - in.firstTri;                                            // gl_PrimitiveID
@@ -1239,7 +1450,7 @@ HD V3 shade_hit_simple(const TraceCtx& c, const Hit& hit, V3 origin, uint32_t& l
     else {
       ++nShadow;
       if (sunmap_candidate_occludes(c, sme, pos, sunL, c.tmin, c.tmax)) ++nCand;
-      else occluded = traverse<true, CNT>(c.nodes, c.bvhTris, c.numNodes, pos, sunL, c.tmin, sunmap_tmax(sme, sPos, c.tmax), sh, cn[1], ct[1]);
+      else occluded = traverse_scene<true, CNT>(c, pos, sunL, c.tmin, sunmap_tmax(sme, sPos, c.tmax), sh, cn[1], ct[1]);
     }
   }
   V3 irradiance = mk3(0.0f);
@@ -1259,7 +1470,7 @@ HD V3 shade_hit_simple(const TraceCtx& c, const Hit& hit, V3 origin, uint32_t& l
       else {
         ++nShadow;
         if (lightmap_candidate_occludes(c, lme, pos, L, c.tmin, dist)) { ++nCand; continue; }
-        if (traverse<true, CNT>(c.nodes, c.bvhTris, c.numNodes, pos, L, c.tmin, lightmap_tmax(lme, dist), sh, cn[1], ct[1])) continue;
+        if (traverse_scene<true, CNT>(c, pos, L, c.tmin, lightmap_tmax(lme, dist), sh, cn[1], ct[1])) continue;
       }
       lit |= 1u << (1u + li);
       const float dd = fminf(dist, range);
@@ -1298,7 +1509,7 @@ HD void specular_gi_body(uint32_t i, const SpecularCtx& c) {
   const V3 dir = vv - (2.0f * dn) * normal;                                                      // reflect(v, normal)
   Hit hit; uint32_t cn[2] = {0, 0}, ct[2] = {0, 0}, lit = 0, nShadow = 0, nPre = 0, nCand = 0;
   V3 rad; float dist;
-  if (traverse<false, false>(c.t.nodes, c.t.bvhTris, c.t.numNodes, pos, dir, 0.1f, 50.0f, hit, cn[0], ct[0])) {
+  if (traverse_scene<false, false>(c.t, pos, dir, 0.1f, 50.0f, hit, cn[0], ct[0])) {
     V3 hp;
     rad = shade_hit_simple<false, true>(c.t, hit, pos, lit, nShadow, nPre, nCand, cn, ct, hp);
     const V3 dd = hp - pos; dist = sqrtf(dot3(dd, dd));                                          // distance(pos, gl_WorldRayOriginEXT)
@@ -1321,7 +1532,7 @@ HD void trace_ray_body(uint32_t idx, const TraceCtx& c) {
   uint32_t cn[2] = {0, 0}, ct[2] = {0, 0}, nShadow = 0, nPre = 0, nCand = 0, lit = 0;
   Hit hit;
   V3 rad;
-  if (traverse<false, CNT>(c.nodes, c.bvhTris, c.numNodes, origin, d, c.tmin, c.tmax, hit, cn[0], ct[0])) {
+  if (traverse_scene<false, CNT>(c, origin, d, c.tmin, c.tmax, hit, cn[0], ct[0])) {
     V3 hitPos;
     rad = shade_hit_simple<CNT, false>(c, hit, origin, lit, nShadow, nPre, nCand, cn, ct, hitPos);
   } else {

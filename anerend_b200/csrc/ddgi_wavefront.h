@@ -41,6 +41,7 @@ struct FastCtx {
   const float4* shadeUV;    // [numTris][2] texture coordinates of the three vertices, or null (no textured material)
   float4* emisTex;          // [rays] emissive of hits on emissive-textured materials, or null
   float4* hits;             // [rays] t,u,v,prim   (launch order: idx = (layerLocal*P + probe)*N + slot)
+  uint32_t* hitInst;        // [rays] instance of the hit: two-level structures only (no triangle -> instance table there)
   float4* surf;             // [rays][3] pos.xyz,n.x | n.yz,albedo.xy | albedo.z,material,metallic,roughness
   uint32_t* lit;            // [rays] visibility bits written by k_trace_shadow
   uint32_t* queues;         // [numQueues][rays] ray indices needing a shadow ray towards light q (0 = sun)

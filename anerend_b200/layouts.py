@@ -47,6 +47,7 @@ FLAG_SIMPLE_KERNELS = 1 << 4
 FLAG_FAST_MATH = 1 << 5
 FLAG_SKIP_DEAD_SHADOW_RAYS = 1 << 6
 FLAG_NO_LIGHT_MAPS = 1 << 7
+FLAG_TWO_LEVEL = 1 << 8
 
 MISS = 0xFFFFFFFF
 

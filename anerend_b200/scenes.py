@@ -420,6 +420,33 @@ def large_volume(seed=5, grid=(64, 32, 256), terrain_res=707, props=500):
     return b.finish((0.0, 30.0, 0.0), grid)
 
 
+def instanced_field(seed, instances=1024, grid=(16, 8, 128), extent=24.0, seg=(32, 16), nlights=4):
+    """Many instances of a few meshes (what the reference's TLAS is for, tlas_update.comp:55-98): a ground plane and `instances`
+    rigid props — spheres, tori, cylinders, boxes of ~1-2k triangles each, random rotations, non-uniform scales down to a few
+    centimetres — some of them on sinusoidal paths (`movers`).  Flattened, the scene holds instances x mesh triangles."""
+    b = SceneBuilder("instanced_field", seed)
+    rng = b.rng
+    mats = [b.add_material(rng.uniform(0.1, 0.9, 3), float(rng.rand() < 0.2), rng.uniform(0.2, 1.0),
+                           (*rng.uniform(0.5, 1, 3), 1.5) if k % 8 == 5 else (0, 0, 0, 0)) for k in range(16)]
+    ground = b.add_mesh(*grid_plane(8, 8))
+    props = [b.add_mesh(*sphere(seg[0], seg[1])), b.add_mesh(*torus(seg[0], max(4, seg[1] // 2))), b.add_mesh(*cylinder(seg[0], seg[1])),
+             b.add_mesh(*box(max(2, seg[1] // 2)))]
+    h = extent / 2
+    b.add_renderable(frame((-h, 0.0, -h), (extent, 0, 0), (0, 1, 0), (0, 0, extent)), ground, mats[0])
+    for k in range(instances):
+        p = (rng.uniform(-h + 1, h - 1), rng.uniform(0.3, 0.6 * h), rng.uniform(-h + 1, h - 1))
+        s = rng.uniform(0.3, 1.6, 3) * (0.05 if k % 37 == 36 else 1.0)
+        M = translate(p) @ rotate(k % 3, rng.uniform(0, 360)) @ rotate((k + 1) % 3, rng.uniform(0, 360)) @ scale(s)
+        r = b.add_renderable(M, props[k % 4], mats[rng.randint(0, 16)])
+        if k % 16 == 3:
+            base = rotate(k % 3, rng.uniform(0, 360)) @ scale(s)
+            b.add_mover(r, base, np.asarray(p), rng.uniform(0.2, 1.0, 3), rng.uniform(0.5, 2.5, 3), rng.uniform(0, 6.28, 3))
+    for k in range(nlights):
+        b.add_light((rng.uniform(-h / 2, h / 2), rng.uniform(2.0, 0.5 * h), rng.uniform(-h / 2, h / 2)), rng.uniform(8.0, 15.0),
+                    tuple(rng.uniform(2.0, 8.0, 3)))
+    return b.finish((0.0, 3.0, 0.0), grid)
+
+
 def random_soup(seed, ntris=2000, extent=6.0, grid=(4, 3, 64), camera=(0.3, 2.0, -0.2), nmat=5, nlights=2):
     """Unstructured triangle soup with several meshes/instances, non-white vertex colours and odd transforms:
     a small adversarial scene for parity tests."""

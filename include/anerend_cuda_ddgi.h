@@ -48,6 +48,13 @@ extern "C" {
 #define ANEREND_DDGI_FLAG_NO_LIGHT_MAPS (1u << 7) /* trace every point-light shadow ray: do not build the conservative distance maps
                                                      around the lights that answer "certainly unoccluded" rays without a traversal
                                                      (same lit masks either way; A/B measurements and tests)                        */
+#define ANEREND_DDGI_FLAG_TWO_LEVEL     (1u << 8) /* acceleration structure as the reference builds it (tlas_update.comp:55-98,
+                                                     VulkanRenderer.cpp:1267-1417): one hierarchy per MESH in object space, shared by
+                                                     its instances, under a hierarchy over the instances that _refit_accel rebuilds —
+                                                     instead of one hierarchy over a world-space copy of every instance's triangles.
+                                                     Results are bit-identical to the one-level structure (the ray/triangle test still
+                                                     runs in world space on the same operands); memory and rebuild cost follow the
+                                                     number of distinct meshes and of instances.  Light maps are not built.          */
 #define ANEREND_DDGI_FLAG_FAST_MATH     (1u << 5) /* radiance + convolution with contracted / approximate fp32 (<= 1e-4 relative per
                                                      update instead of bit-identical to the oracle's defined arithmetic); hit ids,
                                                      shadow-ray results and hit positions are unaffected                            */
@@ -113,6 +120,18 @@ typedef struct anerend_ddgi_bvh_info {
   float    bounds_min[3];
   float    bounds_max[3];
 } anerend_ddgi_bvh_info_t;
+
+/* What a two-level structure (ANEREND_DDGI_FLAG_TWO_LEVEL) holds; zeros on a one-level handle. */
+typedef struct anerend_ddgi_two_level_info {
+  uint32_t num_meshes;        /* distinct meshes = bottom-level hierarchies (VulkanRenderer.cpp:1267-1417: one BLAS per mesh) */
+  uint32_t stored_triangles;  /* triangles kept, each mesh once (bvh_info.num_triangles counts every instance's)               */
+  uint32_t blas_nodes;        /* BVH8 nodes of all bottom-level hierarchies                                                     */
+  uint32_t tlas_nodes;        /* BVH8 nodes of the instance level (tlas_update.comp:55-98 + UpdateTLASPass.cpp:198-228)        */
+  uint32_t tlas_depth, blas_depth_max;
+  uint64_t accel_bytes;       /* nodes + leaf records + shading records + instance transforms                                   */
+  float    tlas_build_ms;     /* device time of the last rebuild of the instance level                                          */
+  uint32_t _pad;
+} anerend_ddgi_two_level_info_t;
 
 typedef struct anerend_ddgi anerend_ddgi_t;
 
@@ -182,6 +201,7 @@ int anerend_cuda_ddgi_refit_accel_device(anerend_ddgi_t* h, const void* d_render
  * acceleration structure is invalid until the next _build_accel. */
 int anerend_cuda_ddgi_apply_camera_cull(anerend_ddgi_t* h, float range, uint32_t* changed);
 int anerend_cuda_ddgi_get_bvh_info(anerend_ddgi_t* h, anerend_ddgi_bvh_info_t* out);
+int anerend_cuda_ddgi_get_two_level_info(anerend_ddgi_t* h, anerend_ddgi_two_level_info_t* out);
 /* The instances _build_accel selected, in the order they were emitted: what tlas_update.comp:54-98 writes to its InstanceBuffer
  * when its invocations run in renderable order (custom index = material | mesh << 10, tlas_update.comp:88-91), plus the range of
  * flattened triangle ids the instance owns.  count must equal bvh_info.num_instances.  Inspection only (tests/test_golden_tlas.py). */

@@ -1,0 +1,155 @@
+"""Two-level acceleration structure (ANEREND_DDGI_FLAG_TWO_LEVEL) on the GPU: the CUDA kernels behind the C ABI —
+wavefront (k_trace<.., TWO>, k_shade_prep<.., TWO>) and the one-thread-per-ray kernel — against the oracle, which flattens every
+instance and knows nothing of the structure.  Everything bit-exact: flattened hit ids, (t, u, v), lit masks, radiance, atlas.
+Each size test appends what it observed to gpurun_out/r02_parity.txt."""
+import os
+import time
+
+import numpy as np
+import pytest
+
+from anerend_b200 import layouts as L, make_params, scenes
+from tests import parity
+from tests.test_two_level import SCENES
+
+pytestmark = pytest.mark.gpu
+ALL = L.FLAG_RAY_RECORDS | L.FLAG_POINT_LIGHTS | L.FLAG_TEXEL_RECORDS | L.FLAG_COUNTERS
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KERNELS = {"wavefront": 0, "wavefront_skip_dead": L.FLAG_SKIP_DEAD_SHADOW_RAYS, "simple": L.FLAG_SIMPLE_KERNELS}
+
+
+def _report(line):
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "r02_parity.txt"), "a") as f:
+        f.write(line + "\n")
+    print(line)
+
+
+def _bit_exact(o, g, ny):
+    mism = 0
+    for layer in range(ny):
+        ro, rg = o.download_ray_records(layer), g.download_ray_records(layer)
+        mism += int((ro["prim"] != rg["prim"]).sum())
+        for k in ("t", "u", "v", "lit_mask"):
+            assert np.array_equal(ro[k], rg[k]), k
+        assert np.array_equal(ro["radiance"].view(np.uint32), rg["radiance"].view(np.uint32))
+    assert mism == 0
+    assert np.array_equal(o.download_atlas(), g.download_atlas())
+
+
+@pytest.mark.parametrize("kernels", sorted(KERNELS))
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_two_level_update_matches_oracle(name, kernels, oracle, make_gpu):
+    scene, (nxz, ny, nr) = SCENES[name]()
+    o = oracle.Oracle(make_params(nxz, ny, nr, flags=ALL | KERNELS[kernels]))
+    g = make_gpu(make_params(nxz, ny, nr, flags=ALL | KERNELS[kernels] | L.FLAG_TWO_LEVEL))
+    rots = parity.setup_pair(scene, (o, g), seed=3)
+    assert g.bvh_info().num_triangles == scene.num_triangles
+    for _ in range(3):
+        for h in (o, g):
+            h.translate()
+            h.update(-1, rots)
+        _bit_exact(o, g, ny)
+    so, sg = o.stats(), g.stats()
+    assert sg["primary_hits"] == so["primary_hits"] and sg["shadow_rays"] == so["shadow_rays"]      # no light maps: every shadow ray is traced
+    o.close()
+    g.close()
+
+
+def test_two_level_equals_one_level_on_the_gpu(make_gpu):
+    """The same handle parameters with and without the flag: identical ray records and atlas, far fewer stored triangles."""
+    scene = scenes.instanced_field(5, instances=600, grid=(8, 4, 128))
+    flags = L.FLAG_RAY_RECORDS | L.FLAG_POINT_LIGHTS
+    a, b = make_gpu(make_params(8, 4, 128, flags=flags)), make_gpu(make_params(8, 4, 128, flags=flags | L.FLAG_TWO_LEVEL))
+    rots = parity.setup_pair(scene, (a, b), seed=9)
+    for _ in range(2):
+        for h in (a, b):
+            h.update(-1, rots)
+        _bit_exact(a, b, 4)
+    info = b.two_level_info()
+    assert info.num_meshes == 5 and info.stored_triangles * 50 < scene.num_triangles
+    a.close()
+    b.close()
+
+
+@pytest.mark.timeout(600)
+def test_two_level_instanced_scene_with_movers(oracle, make_gpu):
+    """1024 instances of four props (tiny ones included), 64 of them moving: refit = rebuild of the instance level only; the
+    oracle re-flattens.  Hidden and culled instances drop out through refit_accel_device's check of the GPU-written bits."""
+    scene = scenes.instanced_field(3, instances=1024, grid=(12, 4, 128))
+    flags = L.FLAG_RAY_RECORDS | L.FLAG_POINT_LIGHTS | L.FLAG_SKIP_DEAD_SHADOW_RAYS
+    o, g = oracle.Oracle(make_params(12, 4, 128, flags=flags)), make_gpu(make_params(12, 4, 128, flags=flags | L.FLAG_TWO_LEVEL))
+    rots = parity.setup_pair(scene, (o, g), seed=4)
+    info0 = g.two_level_info()
+    t0 = time.time()
+    for k in range(4):
+        rend = scene.animated_renderables(0.25 * (k + 1))
+        if k == 3:
+            rend["visible"][5:40:3] = 0                       # hidden
+            rend["visible"][41:90:5] |= 2                     # cull bit (cull.comp:296-303)
+        for h in (o, g):
+            if k == 3:
+                scene.renderables = rend
+                h.upload_scene(scene)
+                h.build_accel()
+            else:
+                h.refit_accel(rend)
+            h.update(-1, rots)
+        _bit_exact(o, g, 4)
+    info = g.two_level_info()
+    assert info.num_meshes == info0.num_meshes and info.stored_triangles == info0.stored_triangles
+    _report(f"two-level, instanced_field (1024 instances, {scene.num_triangles} flattened / {info.stored_triangles} stored triangles, {info.num_meshes} meshes, "
+            f"instance level {info.tlas_nodes} nodes, depth {info.tlas_depth}+{info.blas_depth_max}): 4 updates with moving / hidden / culled instances, "
+            f"hit-id / lit-mask / radiance / atlas mismatches 0; instance-level rebuild {info.tlas_build_ms:.3f} ms  ({time.time() - t0:.0f} s)")
+    o.close()
+    g.close()
+
+
+@pytest.mark.timeout(900)
+def test_two_level_config3_scene_bit_exact(oracle, make_gpu):
+    """The C3 scene (265k flattened triangles: 161 instances of 10 meshes, 56k triangles stored) through the two-level structure: four layers of the
+    full-size grid ray by ray, and the atlas of those layers."""
+    scene = scenes.sponza_like()
+    flags = L.FLAG_RAY_RECORDS | L.FLAG_POINT_LIGHTS | L.FLAG_SKIP_DEAD_SHADOW_RAYS
+    o, g = oracle.Oracle(make_params(24, 12, 256, flags=flags)), make_gpu(make_params(24, 12, 256, flags=flags | L.FLAG_TWO_LEVEL))
+    rots = parity.setup_pair(scene, (o, g), seed=3)
+    layers = [0, 3, 6, 11]
+    t0 = time.time()
+    rays = mism = lit = rad = 0
+    for h in (o, g):
+        h.update_layers(layers, rots)
+    for layer in layers:
+        ro, rg = o.download_ray_records(layer), g.download_ray_records(layer)
+        rays += ro.size
+        mism += int((ro["prim"] != rg["prim"]).sum())
+        lit += int((ro["lit_mask"] != rg["lit_mask"]).sum())
+        rad += int((ro["radiance"].view(np.uint32) != rg["radiance"].view(np.uint32)).sum())
+    texels = int((o.download_atlas() != g.download_atlas()).sum())
+    info = g.two_level_info()
+    _report(f"two-level, C3 scene ({scene.num_triangles} flattened / {info.stored_triangles} stored triangles, {info.num_meshes} meshes): {rays} rays in layers {layers}: "
+            f"hit-id mismatches {mism}, lit-mask mismatches {lit}, radiance words differing {rad}, atlas values differing {texels}  ({time.time() - t0:.0f} s)")
+    assert mism == 0 and lit == 0 and rad == 0 and texels == 0
+    o.close()
+    g.close()
+
+
+def test_two_level_shadow_rt_and_specular_gi(oracle, make_gpu):
+    from tests import shadow_inputs as SI
+    scene = scenes.random_soup(21, ntris=800)
+    o = oracle.Oracle(make_params(4, 3, 64, flags=L.FLAG_POINT_LIGHTS))
+    g = make_gpu(make_params(4, 3, 64, flags=L.FLAG_POINT_LIGHTS | L.FLAG_TWO_LEVEL))
+    rots = parity.setup_pair(scene, (o, g), seed=5)
+    for h in (o, g):
+        h.update(-1, rots)
+    W, H = 64, 40
+    depth, geom0 = SI.depth_buffer(W, H, seed=3), SI.gbuffer_normals(W, H, seed=4)
+    ivp = SI.perspective_inv_view_proj(2)
+    for h in (o, g):
+        h.set_scene_ubo(SI.with_shadow_camera(scene.ubo, ivp, W, H))
+    assert np.array_equal(o.shadow_rt(depth), g.shadow_rt(depth))
+    for h in (o, g):
+        h.set_scene_ubo(SI.with_specular_camera(scene.ubo, ivp, W, H))
+    assert np.array_equal(o.specular_gi(depth, geom0), g.specular_gi(depth, geom0))
+    o.close()
+    g.close()
