@@ -655,10 +655,10 @@ int buildHierarchy(anerend_ddgi* h, BuildCtx c, uint32_t n, uint32_t* numNodesOu
 // The instance level: transforms from the renderable buffer (tlas_update.comp:93-98), world boxes of the meshes' root boxes, and a
 // BVH8 with one instance per leaf slot over them.  This is all a moved, shown, hidden or culled instance costs
 // (UpdateTLASPass.cpp:198-228 rebuilds the TLAS every frame too).
-int rebuildTlas(anerend_ddgi* h) {
+// what the instance level is built from, staged once per instance set (a refit keeps it)
+int uploadTlasInputs(anerend_ddgi* h) {
   Backend& be = h->be;
   const uint32_t ni = (uint32_t)h->instances.size(), nt = (uint32_t)h->tlasList.size();
-  be.mark(4);
   std::vector<uint2> ib(ni);
   for (uint32_t i = 0; i < ni; ++i) {
     const anerend_ddgi::MeshBlas* mb = nullptr;
@@ -668,9 +668,15 @@ int rebuildTlas(anerend_ddgi* h) {
   BE_CHECK(h, be.h2d(h->dInstances, h->instances.data(), ni * sizeof(DInstance)));
   BE_CHECK(h, be.h2d(h->dInstBlas, ib.data(), ni * sizeof(uint2)));
   BE_CHECK(h, be.h2d(h->dTlasList, h->tlasList.data(), nt * sizeof(uint32_t)));
+  BE_CHECK(h, be.sync());          // the staging vectors are pageable
+  return 0;
+}
+int rebuildTlas(anerend_ddgi* h) {
+  Backend& be = h->be;
+  const uint32_t ni = (uint32_t)h->instances.size(), nt = (uint32_t)h->tlasList.size();
+  be.mark(4);
   int initBounds[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
   BE_CHECK(h, be.h2d(h->dSceneBounds, initBounds, sizeof(initBounds)));
-  BE_CHECK(h, be.sync());          // the staging vectors are pageable
   BuildCtx c{};
   c.renderables = h->dRenderables; c.instances = h->dInstances; c.xforms = h->dXforms; c.numInstances = ni;
   DDGI_LAUNCH(be, k_inst_xform, inst_xform_body, ni, c, 128);
@@ -759,6 +765,7 @@ int buildAccelTwoLevel(anerend_ddgi* h) {
   { std::vector<uint32_t> sel(h->renderables.size());
     for (size_t i = 0; i < sel.size(); ++i) { const uint32_t v = h->renderables[i].visible; sel[i] = ((v & 1u) && !((v >> 1) & 1u)) ? 1u : 0u; }
     BE_CHECK(h, be.h2d(h->dSelected, sel.data(), sel.size() * sizeof(uint32_t))); BE_CHECK(h, be.sync()); }
+  if ((rc = uploadTlasInputs(h))) return rc;
   rc = rebuildTlas(h);
   h->accelMs = h->tlasMs;
   return rc;

@@ -379,19 +379,21 @@ HD void collapse_body(uint32_t i, const BuildCtx& c) {
   auto isInternal = [&](uint32_t r) { return r < n - 1; };
   auto count = [&](uint32_t r) -> uint32_t { return isInternal(r) ? c.rangeLast[r] - c.rangeFirst[r] + 1u : 1u; };
   const uint32_t leafMax = c.leafMax ? c.leafMax : 3u;
-  uint32_t ch[8]; int nch = 1; ch[0] = it.ref;
+  // area and size of every candidate are looked up once, when it enters the list (the loads of a level are one dependent chain)
+  uint32_t ch[8], cnt[8]; float area[8]; int nch = 1;
+  ch[0] = it.ref; cnt[0] = count(it.ref); area[0] = half_area(f4v(c.blo[it.ref]), f4v(c.bhi[it.ref]));
   for (int phase = 0; phase < 2; ++phase) {
     const uint32_t minCount = phase == 0 ? 4u : 2u;
     while (nch < 8) {
       int best = -1; float bestA = -1.0f;
       for (int k = 0; k < nch; ++k) {
-        if (!isInternal(ch[k]) || count(ch[k]) < minCount) continue;
-        float a = half_area(f4v(c.blo[ch[k]]), f4v(c.bhi[ch[k]]));
-        if (a > bestA) { bestA = a; best = k; }
+        if (!isInternal(ch[k]) || cnt[k] < minCount) continue;
+        if (area[k] > bestA) { bestA = area[k]; best = k; }
       }
       if (best < 0) break;
-      uint32_t r = ch[best];
-      ch[best] = c.left[r]; ch[nch++] = c.right[r];
+      const uint32_t r = ch[best], l = c.left[r], rr = c.right[r];
+      ch[best] = l; cnt[best] = count(l); area[best] = half_area(f4v(c.blo[l]), f4v(c.bhi[l]));
+      ch[nch] = rr; cnt[nch] = count(rr); area[nch] = half_area(f4v(c.blo[rr]), f4v(c.bhi[rr])); ++nch;
     }
   }
   V3 nlo = f4v(c.blo[it.ref]), nhi = f4v(c.bhi[it.ref]);

@@ -639,6 +639,18 @@ def main():
         except Exception as e:      # the headline line must not depend on this extra
             series_base = {"workload": "c5", "error": f"{type(e).__name__}: {e}"[:200]}
 
+    # ---- two-level acceleration structure (FLAG_TWO_LEVEL): memory, build, per-frame cost of moving instances and
+    # full-grid update against the one-level structure on a scene of 4096 instances of 5 meshes, and on the C3 scene
+    two_level = None
+    if world == 1 and args.workload is None and not args.no_extras:
+        import subprocess
+        try:
+            outp = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "two_level_bench.py"), "instanced4096", "c3"],
+                                  capture_output=True, text=True, timeout=600)
+            two_level = [json.loads(ln) for ln in outp.stdout.splitlines() if ln.startswith("{")]
+        except Exception as e:      # the headline line must not depend on this extra
+            two_level = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     line = None
     if rank == 0:
         # ---- roofline of the dominant kernel: counted, untimed run of the same update ----------
@@ -723,7 +735,7 @@ def main():
                 "update_ms": {"trace": rt_avg, "convolve": float(np.mean(conv_ms)), "full_grid": ms_per_step},
                 "arithmetic": "fast_math (1e-4 relative per update)" if args.fast_math else "exact (atlas bit-identical to the oracle)",
                 "other_build": alt, "subsets": subsets, "strong_scaling_base": base1, "exchange_check_vs_1gpu": verified, "layer_deal": balanced, "per_rank_ms": per_rank, "atlas_consumer": consumer, "shadow_rt": shadow_rt, "multi_gpu_series_base": series_base,
-                "config1_conv_only": config1, "vulkan_reference": vulkan_reference_status()}
+                "two_level_structure": two_level, "config1_conv_only": config1, "vulkan_reference": vulkan_reference_status()}
     close_handle(h, fused)
     if world > 1:
         dist.barrier()
