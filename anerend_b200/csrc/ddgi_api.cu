@@ -117,6 +117,8 @@ struct anerend_ddgi {
   DTexture* dTextures = nullptr; uint8_t* dTexPool = nullptr; float* dSrgbLut = nullptr; uint32_t numTextures = 0;
   std::vector<DTexture> textures; bool texturedScene = false, emissiveTextures = false;
   bool verticesDirty = false;      // update_vertices since the last build / refit
+  std::vector<std::pair<uint32_t, uint32_t>> dirtyVerts;      // ... and which vertex ranges (two-level: only the meshes they touch are rebuilt)
+  std::vector<uint32_t> meshNumVertices;                      // highest index of each mesh + 1
   bool texturesStale = false;      // the texture array was replaced after the scene that refers to it was validated
   float4* dShadeUV = nullptr; float4* dEmisTex = nullptr;
   // ShadowRT scratch (pixels): staged positions, visibility words, ray queue, counters
@@ -721,9 +723,43 @@ int buildAccelTwoLevel(anerend_ddgi* h) {
     total += b.numTris; maxMesh = std::max(maxMesh, b.numTris); um.push_back(b);
   }
   // the meshes' hierarchies are kept while the same meshes (unchanged vertices) are in use: then only the instance level is rebuilt
-  bool reuse = h->twoBuilt && !h->verticesDirty && h->tlasCap >= ni && um.size() == h->blas.size() && h->capTextured == h->texturedScene;
+  bool reuse = h->twoBuilt && h->tlasCap >= ni && um.size() == h->blas.size() && h->capTextured == h->texturedScene;
   for (size_t u = 0; reuse && u < um.size(); ++u) reuse = um[u].mesh == h->blas[u].mesh && um[u].numTris == h->blas[u].numTris;
   h->haveAccel = false; h->numNodes = 0;
+  // one mesh's hierarchy, into its own slots behind the instance level's (UpdateBlasPass.cpp:60-175 / VulkanRenderer.cpp:1267-1417)
+  auto buildBlas = [&](anerend_ddgi::MeshBlas& b, uint32_t capI) -> int {
+    const anerend_mesh_info_t& mi = h->meshes[b.mesh];
+    int initBounds[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+    BE_CHECK(h, be.h2d(h->dSceneBounds, initBounds, sizeof(initBounds)));
+    const size_t base = (size_t)capI + b.triBase;
+    BlasPrimCtx bp{};
+    bp.vertices = h->dVertices; bp.indices = h->dIndices; bp.vertexOffset = mi.vertex_offset; bp.indexOffset = mi.index_offset; bp.numTris = b.numTris;
+    bp.wtri = h->dWtri; bp.triLo = h->dTriLo; bp.triHi = h->dTriHi; bp.sceneBounds = h->dSceneBounds;
+    bp.shadeTris = h->dShadeTris + 5 * (size_t)b.triBase; bp.shadeUV = h->dShadeUV ? h->dShadeUV + 2 * (size_t)b.triBase : nullptr;
+    DDGI_LAUNCH(be, k_blas_prims, blas_prim_body, b.numTris, bp, 256);
+    BuildCtx c{};
+    c.numTris = b.numTris; c.wtri = h->dWtri; c.triLo = h->dTriLo; c.triHi = h->dTriHi; c.sceneBounds = h->dSceneBounds;
+    c.nodes = h->dNodes + 5 * base; c.bvhTris = h->dBvhTris + 3 * base; c.nodeParent = h->dNodeParent + base; c.nodeLo = h->dNodeLo + base; c.nodeHi = h->dNodeHi + base;
+    c.nodePending = h->dNodePending + base; c.visit = h->dVisit; c.counters = h->dCounters;
+    { int rch = buildHierarchy(h, c, b.numTris, &b.nodes, &b.depth); if (rch) return rch; }
+    BlasRelocCtx rl{h->dNodes, (uint32_t)base, (uint32_t)base};
+    DDGI_LAUNCH(be, k_blas_reloc, blas_reloc_body, b.nodes, rl, 256);
+    b.root = (uint32_t)base;
+    return 0;
+  };
+  if (reuse && h->verticesDirty) {
+    // deformed meshes (update_vertices): only the hierarchies whose vertex range was written are rebuilt, in place
+    for (auto& b : h->blas) {
+      const uint32_t v0 = h->meshes[b.mesh].vertex_offset, v1 = v0 + (b.mesh < h->meshNumVertices.size() ? h->meshNumVertices[b.mesh] : 0u);
+      bool touched = false;
+      for (const auto& d : h->dirtyVerts) touched = touched || (d.first < v1 && d.first + d.second > v0);
+      if (touched) { int rcb = buildBlas(b, h->tlasCap); if (rcb) return rcb; }
+    }
+    h->blasNodes = 0; h->blasDepthMax = 0;
+    for (const auto& b : h->blas) { h->blasNodes += b.nodes; h->blasDepthMax = std::max(h->blasDepthMax, b.depth); }
+    BE_CHECK(h, be.check());
+    h->verticesDirty = false; h->dirtyVerts.clear();
+  }
   if (!reuse) {
     freeAccel(h);
     const uint32_t capI = ni + ni / 8u + 16u; const size_t all = (size_t)capI + total; const uint32_t primCap = std::max(capI, maxMesh);
@@ -739,27 +775,11 @@ int buildAccelTwoLevel(anerend_ddgi* h) {
     be.free(h->dSelected); h->dSelected = nullptr; BE_CHECK(h, be.alloc(&h->dSelected, h->renderables.size()));
     h->blasNodes = 0; h->blasDepthMax = 0;
     for (auto& b : um) {
-      const anerend_mesh_info_t& mi = h->meshes[b.mesh];
-      int initBounds[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
-      BE_CHECK(h, be.h2d(h->dSceneBounds, initBounds, sizeof(initBounds)));
-      BE_CHECK(h, be.sync());
-      const size_t base = (size_t)capI + b.triBase;
-      BlasPrimCtx bp{};
-      bp.vertices = h->dVertices; bp.indices = h->dIndices; bp.vertexOffset = mi.vertex_offset; bp.indexOffset = mi.index_offset; bp.numTris = b.numTris;
-      bp.wtri = h->dWtri; bp.triLo = h->dTriLo; bp.triHi = h->dTriHi; bp.sceneBounds = h->dSceneBounds;
-      bp.shadeTris = h->dShadeTris + 5 * (size_t)b.triBase; bp.shadeUV = h->dShadeUV ? h->dShadeUV + 2 * (size_t)b.triBase : nullptr;
-      DDGI_LAUNCH(be, k_blas_prims, blas_prim_body, b.numTris, bp, 256);
-      BuildCtx c{};
-      c.numTris = b.numTris; c.wtri = h->dWtri; c.triLo = h->dTriLo; c.triHi = h->dTriHi; c.sceneBounds = h->dSceneBounds;
-      c.nodes = h->dNodes + 5 * base; c.bvhTris = h->dBvhTris + 3 * base; c.nodeParent = h->dNodeParent + base; c.nodeLo = h->dNodeLo + base; c.nodeHi = h->dNodeHi + base;
-      c.nodePending = h->dNodePending + base; c.visit = h->dVisit; c.counters = h->dCounters;
-      { int rch = buildHierarchy(h, c, b.numTris, &b.nodes, &b.depth); if (rch) return rch; }
-      BlasRelocCtx rl{h->dNodes, (uint32_t)base, (uint32_t)base};
-      DDGI_LAUNCH(be, k_blas_reloc, blas_reloc_body, b.nodes, rl, 256);
-      b.root = (uint32_t)base; h->blasNodes += b.nodes; h->blasDepthMax = std::max(h->blasDepthMax, b.depth);
+      int rcb = buildBlas(b, capI); if (rcb) return rcb;
+      h->blasNodes += b.nodes; h->blasDepthMax = std::max(h->blasDepthMax, b.depth);
     }
     BE_CHECK(h, be.check());
-    h->blas = um; h->twoBuilt = true; h->verticesDirty = false;
+    h->blas = um; h->twoBuilt = true; h->verticesDirty = false; h->dirtyVerts.clear();
   }
   h->instances = inst; h->numTris = n; h->tlasList = list;
   { std::vector<uint32_t> sel(h->renderables.size());
@@ -823,7 +843,7 @@ int buildAccel(anerend_ddgi* h) {
   h->numNodes = numNodes; h->bvhDepth = depth;
   if (depth > DDGI_STACK) return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "BVH8 deeper than the traversal stack");
   h->accelMs = be.elapsed(4, 5);
-  h->haveAccel = true; h->verticesDirty = false;
+  h->haveAccel = true; h->verticesDirty = false; h->dirtyVerts.clear();
   return 0;
 }
 
@@ -838,7 +858,7 @@ int refitAccel(anerend_ddgi* h) {
   BuildCtx c = buildCtx(h);
   c.sceneBounds = nullptr;
   const bool verticesChanged = h->verticesDirty;
-  if (h->verticesDirty) { c.shadeTris = h->dShadeTris; c.shadeUV = h->dShadeUV; h->verticesDirty = false; }   // deformed meshes: refresh the shading records too
+  if (h->verticesDirty) { c.shadeTris = h->dShadeTris; c.shadeUV = h->dShadeUV; h->verticesDirty = false; h->dirtyVerts.clear(); }   // deformed meshes: refresh the shading records too
   be.mark(4);
   DDGI_LAUNCH(be, k_inst_xform, inst_xform_body, (uint32_t)h->instances.size(), c, 128);
   DDGI_LAUNCH(be, k_flatten_scene, flatten_tri_body, h->numTris, c, 256);
@@ -923,6 +943,7 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   f.qcount = h->dQcount; f.totalRays = n; f.numQueues = nq; f.hitInst = h->dHitInst;
   f.surfStride = 3u; f.rawSunDir = 0u;
   for (int k = 0; k < 8; ++k) f.tune[k] = h->tune[k];
+  { static const bool skipKnown = getenv("DDGI_SKIP_KNOWN_MISSES") != nullptr; if (skipKnown) f.tune[7] = 1u; }      // EXPERIMENT
   f.tune[3] = 0x64646464u;                 // planes2: the PRMT constant travels as a kernel argument so the selector can be the immediate
   // queue counters and cursors: cleared by a kernel, not cudaMemsetAsync (a memset may be scheduled on a copy engine, where
   // it waits behind a background read-back of the atlas)
@@ -1445,9 +1466,13 @@ int DDGI_API(upload_scene)(anerend_ddgi_t* h,
   for (uint32_t i = 0; i < nm; ++i) {
     if ((uint64_t)meshes[i].index_offset + meshNumIndices[i] > ni) return fail(h, ANEREND_DDGI_E_INVALID, "mesh index range exceeds the index buffer");
   }
+  std::vector<uint32_t> meshVerts;
   { // every index must address a vertex inside the giga vertex buffer
+    meshVerts.assign(nm, 0u);
     for (uint32_t m = 0; m < nm; ++m) { const uint32_t vo = meshes[m].vertex_offset;
-      for (uint32_t k = 0; k < meshNumIndices[m]; ++k) if ((uint64_t)vo + indices[meshes[m].index_offset + k] >= nv) return fail(h, ANEREND_DDGI_E_INVALID, "vertex index out of range"); } }
+      for (uint32_t k = 0; k < meshNumIndices[m]; ++k) { const uint32_t ix = indices[meshes[m].index_offset + k];
+        if ((uint64_t)vo + ix >= nv) return fail(h, ANEREND_DDGI_E_INVALID, "vertex index out of range");
+        meshVerts[m] = std::max(meshVerts[m], ix + 1u); } } }
   BE_CHECK(h, be.sync());
   freeAccel(h); freeScene(h);
   // everything validated: only now does the new scene (and what was learnt about its textures) replace the old one
@@ -1461,6 +1486,7 @@ int DDGI_API(upload_scene)(anerend_ddgi_t* h,
   h->renderables.assign(renderables, renderables + nr); h->meshes.assign(meshes, meshes + nm);
   h->meshNumIndices.assign(meshNumIndices, meshNumIndices + nm); h->modelIdx.assign(modelIdx, modelIdx + nmi); h->matIdx.assign(matIdx, matIdx + nmti);
   h->numVertices = nv; h->numIndices = ni; h->numMaterials = nmat; h->numLights = nl;
+  h->meshNumVertices = meshVerts; h->dirtyVerts.clear(); h->verticesDirty = false;
   h->haveScene = true;
   return 0;
 }
@@ -1495,7 +1521,7 @@ int DDGI_API(update_vertices)(anerend_ddgi_t* h, const anerend_vertex_t* vertice
   if (!vertices || (uint64_t)first + count > h->numVertices) return fail(h, ANEREND_DDGI_E_INVALID, "vertex range out of bounds");
   BE_CHECK(h, h->be.sync());
   BE_CHECK(h, h->be.h2d(h->dVertices + first, vertices, (size_t)count * sizeof(anerend_vertex_t)));
-  h->verticesDirty = true;
+  h->verticesDirty = true; h->dirtyVerts.emplace_back(first, count);
   return 0;
 }
 int DDGI_API(update_vertices_device)(anerend_ddgi_t* h, const void* dVertices, uint32_t first, uint32_t count) {
@@ -1503,7 +1529,7 @@ int DDGI_API(update_vertices_device)(anerend_ddgi_t* h, const void* dVertices, u
   if (!h->haveScene) return fail(h, ANEREND_DDGI_E_STATE, "update_vertices before upload_scene");
   if (!dVertices || (uint64_t)first + count > h->numVertices) return fail(h, ANEREND_DDGI_E_INVALID, "vertex range out of bounds");
   BE_CHECK(h, h->be.d2d(h->dVertices + first, dVertices, (size_t)count * sizeof(anerend_vertex_t)));
-  h->verticesDirty = true;
+  h->verticesDirty = true; h->dirtyVerts.emplace_back(first, count);
   return 0;
 }
 int DDGI_API(refit_accel)(anerend_ddgi_t* h, const anerend_renderable_t* renderables, uint32_t nr) {

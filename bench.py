@@ -336,6 +336,8 @@ def main():
     accel_ms = h.timings()["accel_ms"]
     info = h.bvh_info()
     rots = h.rotations(seq).reshape(total_steps, ny, 16)
+    if os.environ.get("DDGI_BENCH_FIXED_ROT"):        # experiments only: the same rotations in every step
+        rots[:] = rots[0]
     balanced = None
     if measured_deal:
         # measured-cost deal of the layers (sharding.balanced_layers): every rank times one update of each layer alone on

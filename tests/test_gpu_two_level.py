@@ -160,3 +160,27 @@ def test_two_level_shadow_rt_and_specular_gi(oracle, make_gpu):
     assert np.array_equal(o.specular_gi(depth, geom0), g.specular_gi(depth, geom0))
     o.close()
     g.close()
+
+
+@pytest.mark.parametrize("kernels", ["wavefront", "simple"])
+def test_two_level_deforming_mesh(kernels, oracle, make_gpu):
+    """update_vertices + refit: only the hierarchies of the meshes written to are rebuilt (UpdateBlasPass.cpp:60-175)."""
+    scene, (nxz, ny, nr) = SCENES["textured"]()
+    o = oracle.Oracle(make_params(nxz, ny, nr, flags=ALL | KERNELS[kernels]))
+    g = make_gpu(make_params(nxz, ny, nr, flags=ALL | KERNELS[kernels] | L.FLAG_TWO_LEVEL))
+    rots = parity.setup_pair(scene, (o, g), seed=3)
+    rng = np.random.RandomState(4)
+    nv = len(scene.vertices)
+    first, count = nv // 4, nv // 2
+    for it in range(3):
+        v = scene.vertices[first:first + count].copy()
+        v["pos"] += rng.uniform(-0.03, 0.03, v["pos"].shape).astype(np.float32) * (it + 1)
+        v["normal"] += rng.uniform(-0.2, 0.2, v["normal"].shape).astype(np.float32)
+        v["uv"] += np.float32(0.1 * (it + 1))
+        for h in (o, g):
+            h.update_vertices(v, first)
+            h.refit_accel()
+            h.update(-1, rots)
+        _bit_exact(o, g, ny, radiance_bits=False)
+    o.close()
+    g.close()

@@ -116,3 +116,29 @@ def test_two_level_shadow_rt_and_specular_gi(oracle, make_emu):
     assert np.array_equal(o.specular_gi(depth, geom0), e.specular_gi(depth, geom0))
     o.close()
     e.close()
+
+
+def test_two_level_deforming_mesh_rebuilds_only_its_hierarchy(oracle, make_emu):
+    """Skinned / deforming meshes (UpdateBlasPass.cpp:60-175): new vertices into the giga vertex buffer, then refit — the hierarchies
+    of the meshes whose vertices were written are rebuilt in place, the others and the shading records of untouched meshes are
+    kept; three deformation steps bit-identical to the oracle (which re-flattens everything)."""
+    scene, (nxz, ny, nr) = SCENES["textured"]()
+    o, e = oracle.Oracle(make_params(nxz, ny, nr, flags=ALL)), make_emu(make_params(nxz, ny, nr, flags=ALL | L.FLAG_TWO_LEVEL))
+    rots = parity.setup_pair(scene, (o, e), seed=3)
+    rng = np.random.RandomState(4)
+    nv = len(scene.vertices)
+    first, count = nv // 4, nv // 2
+    for it in range(3):
+        v = scene.vertices[first:first + count].copy()
+        v["pos"] += rng.uniform(-0.03, 0.03, v["pos"].shape).astype(np.float32) * (it + 1)
+        v["normal"] += rng.uniform(-0.2, 0.2, v["normal"].shape).astype(np.float32)
+        v["uv"] += np.float32(0.1 * (it + 1))
+        for h in (o, e):
+            h.update_vertices(v, first)
+            h.refit_accel()
+            h.update(-1, rots)
+        for layer in range(ny):
+            assert parity.compare_records(o.download_ray_records(layer), e.download_ray_records(layer)) == 0
+        assert np.array_equal(o.download_atlas(), e.download_atlas())
+    o.close()
+    e.close()
