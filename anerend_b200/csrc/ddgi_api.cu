@@ -943,7 +943,6 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   f.qcount = h->dQcount; f.totalRays = n; f.numQueues = nq; f.hitInst = h->dHitInst;
   f.surfStride = 3u; f.rawSunDir = 0u;
   for (int k = 0; k < 8; ++k) f.tune[k] = h->tune[k];
-  { static const bool skipKnown = getenv("DDGI_SKIP_KNOWN_MISSES") != nullptr; if (skipKnown) f.tune[7] = 1u; }      // EXPERIMENT
   f.tune[3] = 0x64646464u;                 // planes2: the PRMT constant travels as a kernel argument so the selector can be the immediate
   // queue counters and cursors: cleared by a kernel, not cudaMemsetAsync (a memset may be scheduled on a copy engine, where
   // it waits behind a background read-back of the atlas)

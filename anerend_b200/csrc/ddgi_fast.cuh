@@ -219,23 +219,6 @@ __global__ void __launch_bounds__(128, TWO ? 6 : 8) k_trace(const FastCtx c) {
           if (keep) ray_stage(&sRay[warp][__popc(km & ltMask)][0], pos, dir, tmax, ray, q);
           nStaged = (uint32_t)__popc(km);
           if (CNT) { nRays += (lane < n) ? 1u : 0u; nCand += (lane < n && !keep) ? 1u : 0u; }
-        } else if (!EXT && c.tune[7] == 1u) {
-          // EXPERIMENT (DDGI_SKIP_KNOWN_MISSES): rays that missed in the previous update of the same rotation are not traced
-          bool keep = false; V3 origin = mk3(0.0f), dd = mk3(0.0f, 0.0f, 1.0f); uint32_t w = 0u;
-          if (lane < n) {
-            w = chunkNext + lane;
-            const uint32_t slot = w % (uint32_t)t.N, probeLin = w / (uint32_t)t.N;
-            const int layerLocal = (int)(probeLin / (uint32_t)t.Pl), probe = stripe_probe((int)(probeLin % (uint32_t)t.Pl), t.nXZ, t.rowOffset, t.rowStride);
-            const uint32_t ray = t.rayOrder ? (uint32_t)t.rayOrder[slot] : slot;
-            const int layer = __ldg(&t.layerMap[layerLocal]);
-            origin = mk3((float)(probe % t.nXZ), (float)layer, (float)(probe / t.nXZ)) * t.step + t.camOff;
-            const float4 d4 = __ldg(&t.dirs[(size_t)layer * t.N + ray]);
-            dd = mk3(d4.x, d4.y, d4.z);
-            keep = __float_as_uint(c.hits[w].w) != DDGI_MISS;
-          }
-          const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
-          if (keep) ray_stage(&sRay[warp][__popc(km & ltMask)][0], origin, dd, t.tmax, w, 0u);
-          nStaged = (uint32_t)__popc(km);
         } else
         if (lane < n) {                                             // ray set-up, one ray per lane
           const uint32_t w = chunkNext + lane;
