@@ -27,7 +27,7 @@ class Stats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("primary_hits", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("primary_nodes_visited", C.c_uint64), ("primary_tris_tested", C.c_uint64),
                 ("shadow_nodes_visited", C.c_uint64), ("shadow_tris_tested", C.c_uint64), ("shadow_rays_prefiltered", C.c_uint64),
-                ("shadow_rays_candidate", C.c_uint64)]
+                ("shadow_rays_candidate", C.c_uint64), ("primary_level_changes", C.c_uint64), ("shadow_level_changes", C.c_uint64)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}

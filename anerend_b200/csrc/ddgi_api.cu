@@ -2115,6 +2115,7 @@ int DDGI_API(get_stats)(anerend_ddgi_t* h, anerend_ddgi_stats_t* o) {
   BE_CHECK(h, h->be.d2h(s, h->dStats, sizeof(s)));
   o->primary_rays = s[0]; o->primary_hits = s[1]; o->shadow_rays = s[2]; o->primary_nodes_visited = s[3]; o->primary_tris_tested = s[4];
   o->shadow_nodes_visited = s[5]; o->shadow_tris_tested = s[6]; o->shadow_rays_prefiltered = s[7]; o->shadow_rays_candidate = s[8];
+  o->primary_level_changes = s[9]; o->shadow_level_changes = s[10];
   return 0;
 }
 int DDGI_API(reset_stats)(anerend_ddgi_t* h) { if (!h) return ANEREND_DDGI_E_INVALID; BE_CHECK(h, h->be.zero(h->dStats, 16 * sizeof(unsigned long long))); return 0; }

@@ -36,7 +36,7 @@ struct RayState {
   uint32_t npend;                   // parked triangle groups (0..2)
   // two-level structures (TWO): the instance whose mesh is being walked (DDGI_MISS: instance level) — ox.. / idx.. / octm then
   // describe the ray in its object space — and the slack of the slab parameters there (ObjRay::pad)
-  uint32_t inst; float px, py, pz;
+  uint32_t inst; float pad;         // pad: object units (ObjRay::padLen); the slab parameters of axis k move by pad * |1/d'_k|
 };
 
 #define LS_DIR 0                    // per-lane shared state, SoA [field][lane] of 16 bytes: (d.xyz, tag)
@@ -128,7 +128,10 @@ __device__ __forceinline__ uint4 node_step(const uint4* __restrict__ nodes, RayS
   const float kF = 1.0000004f;          // far side widened: conservative against rounding in the slab arithmetic
   const float axf = ax * kF, ayf = ay * kF, azf = az * kF;
   float bxf = bx * kF, byf = by * kF, bzf = bz * kF;
-  if (TWO) { bx -= r.px; by -= r.py; bz -= r.pz; bxf += r.px; byf += r.py; bzf += r.pz; }      // object space: what the transforms may have lost
+  if (TWO) {      // object space: what the transforms may have lost
+    const float px = r.pad * fabsf(r.idx), py = r.pad * fabsf(r.idy), pz = r.pad * fabsf(r.idz);
+    bx -= px; by -= py; bz -= pz; bxf += px; byf += py; bzf += pz;
+  }
   const uint32_t acc = four_children<0>(nearx0, neary0, nearz0, farx0, fary0, farz0, ax, ay, az, bx, by, bz, axf, ayf, azf, bxf, byf, bzf, tmin, r.tmax, k64) |
                        four_children<1>(nearx1, neary1, nearz1, farx1, fary1, farz1, ax, ay, az, bx, by, bz, axf, ayf, azf, bxf, byf, bzf, tmin, r.tmax, k64);
   const uint32_t imask = n0.w >> 24;
@@ -146,7 +149,7 @@ __device__ __forceinline__ uint4 node_step(const uint4* __restrict__ nodes, RayS
 // that found none keep stepping through nodes instead of idling in a per-lane triangle loop.
 // ------------------------------------------------------------------------------------------------------------
 template <bool ANY, bool CNT, bool EXT = false, bool TWO = false>
-__global__ void __launch_bounds__(128, TWO ? 6 : 8) k_trace(const FastCtx c) {
+__global__ void __launch_bounds__(128, TWO ? 7 : 8) k_trace(const FastCtx c) {
   const TraceCtx& t = c.t;
   __shared__ float4 sRay[4][32][3];
   __shared__ float4 sLane[4][LS_FIELDS + (TWO ? 1 : 0)][32];
@@ -170,11 +173,11 @@ __global__ void __launch_bounds__(128, TWO ? 6 : 8) k_trace(const FastCtx c) {
   float4* myOrg = &sLane[warp][TWO ? LS_ORG : LS_DIR][lane];                     // TWO only
   uint2 stack[DDGI_STACK];
   RayState r; r.sp = 0; r.npend = 0; r.ng = make_uint2(0, 0); r.tmax = 0.0f; r.octm = 0;
-  r.inst = DDGI_MISS; r.px = r.py = r.pz = 0.0f;
+  r.inst = DDGI_MISS; r.pad = 0.0f;
   r.ox = r.oy = r.oz = 0.0f; r.idx = r.idy = r.idz = 1.0f;
-  bool active = false, exhausted = (total == 0u);
+  bool active = false, exhausted = (total == 0u), wantChange = false;      // wantChange (TWO): the top of the lane's stack is a level change
   uint32_t chunkNext = 0, chunkEnd = 0, staged = 0, stagedPos = 0;      // warp-uniform
-  uint32_t cn = 0, ct = 0, nRays = 0, nHits = 0, nCand = 0;
+  uint32_t cn = 0, ct = 0, nRays = 0, nHits = 0, nCand = 0, cs = 0;      // cs: level changes of a two-level walk (instance entries + returns)
   for (;;) {
     // ---------------------------------------------------------------- refill idle lanes from the staged batch
     uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(128, TWO ? 6 : 8) k_trace(const FastCtx c) {
         r.ng = make_uint2(0u, 0x80000000u); r.sp = 0; r.npend = 0;
         *myDir = b;                                                 // (d.xyz, tag)
         *myRes = make_float4(0.0f, 0.0f, 0.0f, ANY ? cc.w : __uint_as_float(DDGI_MISS));
-        if (TWO) { *myOrg = make_float4(a.x, a.y, a.z, __uint_as_float(DDGI_MISS)); r.inst = DDGI_MISS; r.px = r.py = r.pz = 0.0f; }
+        if (TWO) { *myOrg = make_float4(a.x, a.y, a.z, __uint_as_float(DDGI_MISS)); r.inst = DDGI_MISS; r.pad = 0.0f; wantChange = false; }
         if (CNT && !ANY) ++nRays;
         if (!ANY && t.numNodes == 0u) c.hits[__float_as_uint(b.w)] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(DDGI_MISS));
         else active = true;
@@ -266,29 +269,15 @@ __global__ void __launch_bounds__(128, TWO ? 6 : 8) k_trace(const FastCtx c) {
     for (uint32_t k = 0;;) {
       const bool hasNode = (r.ng.y & 0xFF000000u) != 0u || r.sp > 0;
       if (active && !finished) {
-        if (hasNode && r.npend < 2u) {
+        if (hasNode && r.npend < 2u && !(TWO && wantChange)) {
           bool step = true;
           if ((r.ng.y & 0xFF000000u) == 0u) {
-            const uint2 e = stack[--r.sp];
-            if (TWO && e.y == 0u) {
-              // two-level structure (ddgi_kernels.cuh traverse2): back to the world-space ray, or into an instance's object space
-              step = false;
-              const float4 o4 = *myOrg, d4 = *myDir;
-              if (e.x == TWO_RESTORE) {
-                r.ox = o4.x; r.oy = o4.y; r.oz = o4.z;
-                r.idx = 1.0f / safe_dir(d4.x); r.idy = 1.0f / safe_dir(d4.y); r.idz = 1.0f / safe_dir(d4.z);
-                r.px = r.py = r.pz = 0.0f; r.inst = DDGI_MISS;
-              } else {
-                r.inst = e.x & ~TWO_INSTANCE;
-                const InstXform& xf = t.xforms[r.inst];
-                const ObjRay q = object_ray(xf, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), r.tmax);
-                r.ox = q.o.x; r.oy = q.o.y; r.oz = q.o.z; r.idx = q.id.x; r.idy = q.id.y; r.idz = q.id.z; r.px = q.pad.x; r.py = q.pad.y; r.pz = q.pad.z;
-                stack[r.sp++] = make_uint2(TWO_RESTORE, 0u);
-                r.ng = make_uint2(__float_as_uint(xf._pad[0]), 0x80000000u);
-              }
-              const uint32_t octinv = 7u - ((r.idx < 0.0f ? 1u : 0u) | (r.idy < 0.0f ? 2u : 0u) | (r.idz < 0.0f ? 4u : 0u));
-              r.octm = ((octinv & 1u) ? 0x55u : 0u) | ((octinv & 2u) ? 0x3300u : 0u) | ((octinv & 4u) ? 0x0F0000u : 0u) | (octinv << 24);
-            } else r.ng = e;
+            const uint2 e = stack[r.sp - 1];
+            // two-level structure: an entry without child bits moves the lane between the spaces; it stays on the stack and the
+            // lane sits out the rest of this node phase — the level changes of a warp are worked off together below (taken one by
+            // one inside the box-test steps they ran at 4 of 32 lanes and were a sixth of the kernel's instructions)
+            if (TWO && e.y == 0u) { step = false; wantChange = true; }
+            else { r.ng = e; --r.sp; }
           }
           if (step) {
             const uint4 tg = node_step<TWO>(t.nodes, r, stack, t.tmin, k64);
@@ -309,8 +298,34 @@ __global__ void __launch_bounds__(128, TWO ? 6 : 8) k_trace(const FastCtx c) {
         } else if (!hasNode && r.npend == 0u) finished = true;
       }
       if (++k >= nodeSteps) break;
-      const uint32_t can = __ballot_sync(0xFFFFFFFFu, active && !finished && r.npend < 2u && ((r.ng.y & 0xFF000000u) != 0u || r.sp > 0));
+      const uint32_t can = __ballot_sync(0xFFFFFFFFu, active && !finished && r.npend < 2u && !(TWO && wantChange) && ((r.ng.y & 0xFF000000u) != 0u || r.sp > 0));
       if ((uint32_t)__popc(can) < stepMin) break;
+    }
+    // ---------------------------------------------------------------- level changes (two-level structures, ddgi_kernels.cuh traverse2):
+    // back to the world-space ray, or into an instance's object space
+    if (TWO && __ballot_sync(0xFFFFFFFFu, wantChange) != 0u) {
+      if (wantChange) {
+        wantChange = false;
+        if (CNT) ++cs;
+        uint2 e = stack[--r.sp];
+        // a return directly followed by the next instance: enter it without the detour through the world-space ray
+        if (e.x == TWO_RESTORE && r.sp > 0) { const uint2 e2 = stack[r.sp - 1]; if (e2.y == 0u) { e = e2; --r.sp; } }
+        const float4 o4 = *myOrg, d4 = *myDir;
+        if (e.x == TWO_RESTORE) {
+          r.ox = o4.x; r.oy = o4.y; r.oz = o4.z;
+          r.idx = 1.0f / safe_dir(d4.x); r.idy = 1.0f / safe_dir(d4.y); r.idz = 1.0f / safe_dir(d4.z);
+          r.pad = 0.0f; r.inst = DDGI_MISS;
+        } else {
+          r.inst = e.x & ~TWO_INSTANCE;
+          const InstXform& xf = t.xforms[r.inst];
+          const ObjRay q = object_ray(xf, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), r.tmax);
+          r.ox = q.o.x; r.oy = q.o.y; r.oz = q.o.z; r.idx = q.id.x; r.idy = q.id.y; r.idz = q.id.z; r.pad = q.padLen;
+          stack[r.sp++] = make_uint2(TWO_RESTORE, 0u);
+          r.ng = make_uint2(__float_as_uint(xf._pad[0]), 0x80000000u);
+        }
+        const uint32_t octinv = 7u - ((r.idx < 0.0f ? 1u : 0u) | (r.idy < 0.0f ? 2u : 0u) | (r.idz < 0.0f ? 4u : 0u));
+        r.octm = ((octinv & 1u) ? 0x55u : 0u) | ((octinv & 2u) ? 0x3300u : 0u) | ((octinv & 4u) ? 0x0F0000u : 0u) | (octinv << 24);
+      }
     }
     // ---------------------------------------------------------------- triangle rounds: one parked triangle per lane and round
     for (uint32_t pend = __ballot_sync(0xFFFFFFFFu, active && !finished && r.npend != 0u); pend != 0u;) {
@@ -367,12 +382,12 @@ __global__ void __launch_bounds__(128, TWO ? 6 : 8) k_trace(const FastCtx c) {
   if (CNT && t.stats) {
     for (int o = 16; o; o >>= 1) { cn += __shfl_xor_sync(0xFFFFFFFFu, cn, o); ct += __shfl_xor_sync(0xFFFFFFFFu, ct, o);
                                    nRays += __shfl_xor_sync(0xFFFFFFFFu, nRays, o); nHits += __shfl_xor_sync(0xFFFFFFFFu, nHits, o);
-                                   nCand += __shfl_xor_sync(0xFFFFFFFFu, nCand, o); }
+                                   nCand += __shfl_xor_sync(0xFFFFFFFFu, nCand, o); cs += __shfl_xor_sync(0xFFFFFFFFu, cs, o); }
     if (lane == 0) {
       if (!ANY) { atomicAdd(&t.stats[0], (unsigned long long)nRays); atomicAdd(&t.stats[1], (unsigned long long)nHits);
-                  atomicAdd(&t.stats[3], (unsigned long long)cn); atomicAdd(&t.stats[4], (unsigned long long)ct); }
+                  atomicAdd(&t.stats[3], (unsigned long long)cn); atomicAdd(&t.stats[4], (unsigned long long)ct); if (cs) atomicAdd(&t.stats[9], (unsigned long long)cs); }
       else { atomicAdd(&t.stats[2], (unsigned long long)nRays); atomicAdd(&t.stats[5], (unsigned long long)cn); atomicAdd(&t.stats[6], (unsigned long long)ct);
-             if (nCand) atomicAdd(&t.stats[8], (unsigned long long)nCand); }
+             if (nCand) atomicAdd(&t.stats[8], (unsigned long long)nCand); if (cs) atomicAdd(&t.stats[10], (unsigned long long)cs); }
     }
   }
 }

@@ -689,7 +689,7 @@ HD bool traverse(const uint4* __restrict__ nodes, const float4* __restrict__ tri
 #define TWO_RESTORE 0x7FFFFFFFu
 #define TWO_INSTANCE 0x80000000u
 #define TWO_PAD_K 1e-5f
-struct ObjRay { V3 o, d, id, pad; uint32_t octinv; };      // pad: slack of the slab parameters per axis (t units)
+struct ObjRay { V3 o, d, id, pad; float padLen; uint32_t octinv; };      // pad: slack of the slab parameters per axis (t units) = padLen' * |id|, padLen' <= padLen (object units)
 HD ObjRay object_ray(const InstXform& xf, V3 o, V3 d, float tmax) {
   ObjRay r;
   const float* m = xf.w2o; const float* c3 = xf.o2w + 9;
@@ -705,6 +705,7 @@ HD ObjRay object_ray(const InstXform& xf, V3 o, V3 d, float tmax) {
   const V3 e = mk3(fabsf(m[0]) * w.x + fabsf(m[3]) * w.y + fabsf(m[6]) * w.z + own, fabsf(m[1]) * w.x + fabsf(m[4]) * w.y + fabsf(m[7]) * w.z + own,
                    fabsf(m[2]) * w.x + fabsf(m[5]) * w.y + fabsf(m[8]) * w.z + own);
   r.pad = mk3(TWO_PAD_K * e.x * fabsf(r.id.x), TWO_PAD_K * e.y * fabsf(r.id.y), TWO_PAD_K * e.z * fabsf(r.id.z));
+  r.padLen = TWO_PAD_K * fmaxf(fmaxf(e.x, e.y), e.z);
   return r;
 }
 // world-space (v0, e1, e2) of an object-space triangle record, the operations of flatten_tri_body
@@ -718,7 +719,7 @@ HD bool traverse2(const uint4* __restrict__ nodes, const float4* __restrict__ tr
   hit.prim = DDGI_MISS; hit.t = tmax; hit.u = 0.0f; hit.v = 0.0f; hit.inst = DDGI_MISS;
   if (numNodes == 0u) return false;
   ObjRay w;                                      // the world-space ray in the same form
-  w.o = o; w.d = d; w.id = mk3(1.0f / safe_dir(d.x), 1.0f / safe_dir(d.y), 1.0f / safe_dir(d.z)); w.pad = mk3(0.0f);
+  w.o = o; w.d = d; w.id = mk3(1.0f / safe_dir(d.x), 1.0f / safe_dir(d.y), 1.0f / safe_dir(d.z)); w.pad = mk3(0.0f); w.padLen = 0.0f;
   w.octinv = 7u - ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u));
   ObjRay r = w;
   uint32_t inst = DDGI_MISS;                     // MISS: in the instance level

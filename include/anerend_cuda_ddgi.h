@@ -109,6 +109,8 @@ typedef struct anerend_ddgi_stats {
   uint64_t shadow_tris_tested;
   uint64_t shadow_rays_prefiltered; /* shadow rays answered by the light maps instead of a traversal (not in shadow_rays) */
   uint64_t shadow_rays_candidate;   /* of shadow_rays: ended by the exact test against the light map's candidate triangle */
+  uint64_t primary_level_changes;   /* two-level structure: instance entries + returns of the closest-hit rays (wavefront kernels) */
+  uint64_t shadow_level_changes;
 } anerend_ddgi_stats_t;
 
 typedef struct anerend_ddgi_bvh_info {

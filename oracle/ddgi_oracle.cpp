@@ -1177,7 +1177,8 @@ int ddgi_oracle_download_texel_records(ddgi_oracle_t* h, float* out, size_t byte
 }
 int ddgi_oracle_get_stats(ddgi_oracle_t* h, anerend_ddgi_stats_t* o) {
   o->primary_rays = h->st[0]; o->primary_hits = h->st[1]; o->shadow_rays = h->st[2]; o->primary_nodes_visited = h->st[3];
-  o->primary_tris_tested = h->st[4]; o->shadow_nodes_visited = h->st[5]; o->shadow_tris_tested = h->st[6]; o->shadow_rays_prefiltered = 0; o->shadow_rays_candidate = 0; return 0;
+  o->primary_tris_tested = h->st[4]; o->shadow_nodes_visited = h->st[5]; o->shadow_tris_tested = h->st[6]; o->shadow_rays_prefiltered = 0; o->shadow_rays_candidate = 0;
+  o->primary_level_changes = 0; o->shadow_level_changes = 0; return 0;
 }
 int ddgi_oracle_reset_stats(ddgi_oracle_t* h) { for (auto& s : h->st) s = 0; return 0; }
 
