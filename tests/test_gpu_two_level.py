@@ -184,3 +184,31 @@ def test_two_level_deforming_mesh(kernels, oracle, make_gpu):
         _bit_exact(o, g, ny, radiance_bits=False)
     o.close()
     g.close()
+
+
+def test_two_level_row_stripes_assemble_the_one_level_atlas(make_gpu):
+    """The multi-GPU sharding (row stripes) on two-level handles: the merged rows equal the atlas of one one-level
+    handle bit for bit, update after update."""
+    nxz, ny, nr, world = 8, 4, 64, 4
+    scene = scenes.instanced_field(11, instances=200, grid=(nxz, ny, nr), extent=10.0)
+    flags = L.FLAG_POINT_LIGHTS | L.FLAG_SKIP_DEAD_SHADOW_RAYS
+    full = make_gpu(make_params(nxz, ny, nr, flags=flags))
+    parts = [make_gpu(make_params(nxz, ny, nr, flags=flags | L.FLAG_TWO_LEVEL)) for _ in range(world)]
+    rots = parity.setup_pair(scene, [full] + parts, seed=8)
+    for r, h in enumerate(parts):
+        h.set_row_stripe(r, world)
+    for it in range(3):
+        full.update(-1, rots)
+        for h in parts:
+            h.update(-1, rots)
+        slabs = [h.download_atlas() for h in parts]
+        merged = slabs[0].copy()
+        for y in range(ny):
+            for z in range(nxz):
+                r0 = 10 * nxz * y + 10 * z
+                merged[r0:r0 + 10] = slabs[z % world][r0:r0 + 10]
+        for h in parts:
+            h.upload_atlas(merged)
+        assert np.array_equal(merged, full.download_atlas())
+    for h in [full] + parts:
+        h.close()
