@@ -1718,7 +1718,7 @@ int shadowRt(anerend_ddgi* h, const float* dDepth, uint32_t width, uint32_t heig
   c.tmin = 0.1f; c.tmax = 50.0f;                                        // literals of shadow.rgen:64-65
   c.screenW = (float)h->ubo.screen_width; c.screenH = (float)h->ubo.screen_height;
 #ifndef DDGI_HOST_EMU
-  if (!(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS) && h->numNodes > 0 && !twoLevel(h)) {
+  if (!(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS) && h->numNodes > 0) {
     // the persistent any-hit kernel over one queue of pixels; scratch of its own (a frame buffer is not a probe layer)
     if (h->srtPixels < n) {
       BE_CHECK(h, be.sync());
@@ -1727,20 +1727,18 @@ int shadowRt(anerend_ddgi* h, const float* dDepth, uint32_t width, uint32_t heig
       if (!h->dSrtQcount) BE_CHECK(h, be.alloc(&h->dSrtQcount, FAST_QC_SIZE));
       h->srtPixels = n;
     }
-    if (h->gridShadow[0] == 0) {
-      int dev = 0, sms = 0, nb = 0;
-      BE_CHECK(h, be.ok(cudaGetDevice(&dev))); BE_CHECK(h, be.ok(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)));
-      BE_CHECK(h, be.ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace<true, false>, 128, 0)));
-      h->srtGrid = sms * (nb > 0 ? nb : 1);
-    } else h->srtGrid = h->gridShadow[0];
+    { int rcg = ensureFastGrids(h); if (rcg) return rcg; }
+    h->srtGrid = h->gridShadow[0];
     k_zero_words<<<(FAST_QC_SIZE + 255u) / 256u, 256, 0, be.stream>>>(h->dSrtQcount, (uint32_t)FAST_QC_SIZE);
     k_shadowrt_stage<<<(n + 255u) / 256u, 256, 0, be.stream>>>(c, h->dSrtPos, h->dSrtLit, h->dSrtQueue, h->dSrtQcount + FAST_QC(0));
     FastCtx f{};
     f.t.nodes = h->dNodes; f.t.bvhTris = h->dBvhTris; f.t.numNodes = h->numNodes; f.t.lightDir = c.lightDir; f.t.tmin = c.tmin; f.t.tmax = c.tmax;
+    f.t.xforms = h->dXforms; f.t.twoLevel = c.twoLevel;
     f.surf = h->dSrtPos; f.lit = h->dSrtLit; f.queues = h->dSrtQueue; f.qcount = h->dSrtQcount; f.totalRays = n; f.numQueues = 1u;
     f.surfStride = 1u; f.rawSunDir = 1u;
     f.tune[0] = TUNE_NODE_STEPS; f.tune[1] = f.tune[2] = TUNE_REFILL_MIN; f.tune[3] = 0x64646464u; f.tune[4] = TUNE_STEP_MIN; f.tune[5] = TUNE_TRI_MIN;
-    k_trace<true, false><<<h->srtGrid, 128, 0, be.stream>>>(f);
+    if (twoLevel(h)) k_trace<true, false, false, true><<<h->srtGrid, 128, 0, be.stream>>>(f);
+    else k_trace<true, false><<<h->srtGrid, 128, 0, be.stream>>>(f);
     k_shadowrt_resolve<<<(n + 255u) / 256u, 256, 0, be.stream>>>(dDepth, h->dSrtLit, dOut, n);
     be.launches += 4;
     BE_CHECK(h, be.check());
@@ -1791,7 +1789,7 @@ int specularGi(anerend_ddgi* h, const float* dDepth, const float4* dGeom0, uint3
   c.screenW = (float)h->ubo.screen_width; c.screenH = (float)h->ubo.screen_height;
 #ifndef DDGI_HOST_EMU
   static const bool specWavefront = getenv("DDGI_SPECULAR_SIMPLE") == nullptr;      // A/B switch: the one-thread-per-pixel kernel (5.9 ms vs 1.17 ms at 1080p)
-  if (specWavefront && !(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS) && h->numNodes > 0 && !twoLevel(h)) {
+  if (specWavefront && !(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS) && h->numNodes > 0) {
     // the wavefront kernels in external-ray mode: one reflected ray per pixel instead of the probe rays
     Backend& be = h->be;
     const uint32_t nq = 1u + ((h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) ? h->numLights : 0u);
@@ -1806,15 +1804,21 @@ int specularGi(anerend_ddgi* h, const float* dDepth, const float4* dGeom0, uint3
     FastCtx f{};
     f.t = c.t; f.t.rayIrr = dOut; f.t.layerMap = nullptr; f.t.rayOrder = nullptr;
     f.shadeTris = h->dShadeTris; f.shadeUV = h->dShadeUV; f.emisTex = h->dEmisTex; f.hits = h->dHits; f.surf = h->dSurf; f.lit = h->dLit;
-    f.queues = h->dQueues; f.hitq = h->dHitq; f.qcount = h->dQcount; f.totalRays = n; f.numQueues = nq;
+    f.queues = h->dQueues; f.hitq = h->dHitq; f.qcount = h->dQcount; f.totalRays = n; f.numQueues = nq; f.hitInst = h->dHitInst;
     f.surfStride = 3u; f.rawSunDir = 0u; f.extRays = h->dExtRays; f.extDist = h->dExtDist;
     for (int k = 0; k < 8; ++k) f.tune[k] = h->tune[k];
     f.tune[3] = 0x64646464u;
     k_zero_words<<<(FAST_QC_SIZE + 255u) / 256u, 256, 0, be.stream>>>(h->dQcount, (uint32_t)FAST_QC_SIZE);
     k_specular_stage<<<(n + 255u) / 256u, 256, 0, be.stream>>>(c, h->dExtRays);
-    k_trace<false, false, true><<<h->gridPrimary[0], 128, 0, be.stream>>>(f);
-    k_shade_prep<256, true><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
-    k_trace<true, false><<<h->gridShadow[0], 128, 0, be.stream>>>(f);
+    if (twoLevel(h)) {
+      k_trace<false, false, true, true><<<h->gridPrimary[0], 128, 0, be.stream>>>(f);
+      k_shade_prep<256, true, 2048, false, true><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
+      k_trace<true, false, false, true><<<h->gridShadow[0], 128, 0, be.stream>>>(f);
+    } else {
+      k_trace<false, false, true><<<h->gridPrimary[0], 128, 0, be.stream>>>(f);
+      k_shade_prep<256, true><<<(n + 255u) / 256u, 256, 0, be.stream>>>(f);
+      k_trace<true, false><<<h->gridShadow[0], 128, 0, be.stream>>>(f);
+    }
     BE_CHECK(h, be.ok((h->p.flags & ANEREND_DDGI_FLAG_FAST_MATH) ? launch_shade_ext_fast(f, be.stream) : launch_shade_ext_exact(f, be.stream)));
     k_specular_resolve<<<(n + 255u) / 256u, 256, 0, be.stream>>>(dDepth, dOut, n);
     be.launches += 7;
