@@ -641,6 +641,22 @@ def main():
         except Exception as e:      # the headline line must not depend on this extra
             series_base = {"workload": "c5", "error": f"{type(e).__name__}: {e}"[:200]}
 
+    # ---- the other single-GPU BASELINE configurations next to the C3 headline: C2 (Cornell box) and C4 (camera scroll: translation +
+    # refit of 16 movers + dynamic light maps every step), each a short run of this script
+    other_workloads = None
+    if world == 1 and args.workload is None and not args.no_extras:
+        import subprocess
+        other_workloads = {}
+        for wl in ("c2", "c4"):
+            try:
+                outp = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", wl, "--steps", "20", "--warmup", "3", "--no-alt",
+                                       "--no-cpu-baseline", "--no-extras"], capture_output=True, text=True, timeout=600)
+                dw = json.loads([ln for ln in outp.stdout.splitlines() if ln.startswith("{")][-1])
+                other_workloads[wl] = {"value": dw["value"], "unit": UNIT, "ms_per_step": dw["ms_per_step"], "e2e_ms_per_step": dw["e2e"]["ms_per_step"],
+                                       "steps": dw["steps"], "probes": dw["config"]["probes"], "triangles": dw["config"]["triangles"]}
+            except Exception as e:      # the headline line must not depend on this extra
+                other_workloads[wl] = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     # ---- two-level acceleration structure (FLAG_TWO_LEVEL): memory, build, per-frame cost of moving instances and
     # full-grid update against the one-level structure on a scene of 4096 instances of 5 meshes, and on the C3 scene
     two_level = None
@@ -737,7 +753,7 @@ def main():
                 "update_ms": {"trace": rt_avg, "convolve": float(np.mean(conv_ms)), "full_grid": ms_per_step},
                 "arithmetic": "fast_math (1e-4 relative per update)" if args.fast_math else "exact (atlas bit-identical to the oracle)",
                 "other_build": alt, "subsets": subsets, "strong_scaling_base": base1, "exchange_check_vs_1gpu": verified, "layer_deal": balanced, "per_rank_ms": per_rank, "atlas_consumer": consumer, "shadow_rt": shadow_rt, "multi_gpu_series_base": series_base,
-                "two_level_structure": two_level, "config1_conv_only": config1, "vulkan_reference": vulkan_reference_status()}
+                "other_workloads": other_workloads, "two_level_structure": two_level, "config1_conv_only": config1, "vulkan_reference": vulkan_reference_status()}
     close_handle(h, fused)
     if world > 1:
         dist.barrier()
