@@ -79,6 +79,7 @@ struct anerend_ddgi {
   float4* dWtri = nullptr; float4* dTriLo = nullptr; float4* dTriHi = nullptr; int* dSceneBounds = nullptr;
   uint4* dNodes = nullptr; float4* dBvhTris = nullptr; uint32_t* dNodeParent = nullptr; float4* dNodeLo = nullptr; float4* dNodeHi = nullptr;
   uint32_t* dNodePending = nullptr; uint32_t* dVisit = nullptr; uint32_t* dCounters = nullptr;
+  uint32_t* dInstChanged = nullptr;      // refit: instances whose transform changed since the last one
   float boundsMin[3] = {0, 0, 0}, boundsMax[3] = {0, 0, 0};
   // two-level structure (ANEREND_DDGI_FLAG_TWO_LEVEL): one hierarchy per distinct mesh behind the instance level's slots of the
   // node / leaf arrays; numTris stays the number of flattened triangle ids, numNodes the nodes of the instance level
@@ -125,6 +126,7 @@ struct anerend_ddgi {
   float4* dExtRays = nullptr; float* dExtDist = nullptr; uint32_t extPixels = 0;      // SpecularGIRT: staged rays, hit distances
   float4* dSrtPos = nullptr; uint32_t* dSrtLit = nullptr; uint32_t* dSrtQueue = nullptr; uint32_t* dSrtQcount = nullptr; uint32_t srtPixels = 0; int srtGrid = 0;
   void* dBigItems = nullptr; uint32_t* dBigCount = nullptr;           // queue of large light-map footprints (k_lightmap_raster_big)
+  uint32_t* dMovedTris = nullptr; uint32_t* dMovedCount = nullptr; uint32_t movedCap = 0;      // refit: triangles of the instances that moved (k_moved_tris)
   uint32_t* dSelected = nullptr; uint32_t* dVisChanged = nullptr;      // per renderable: in the structure (tlas_update.comp:41-47); device flag of refit_accel_device
   // light maps (ddgi_kernels.cuh): static + dynamic distance cube maps per point light, the transforms the static map was made with
   unsigned long long* dLmStatic = nullptr; unsigned long long* dLmDynamic = nullptr; uint32_t* dLmNear = nullptr; InstXform* dLmBase = nullptr; uint32_t* dLmMoved = nullptr;
@@ -226,6 +228,7 @@ void freeAccel(anerend_ddgi* h) {
   be.free(h->dInstances); be.free(h->dXforms); be.free(h->dTriInstance); be.free(h->dWtri); be.free(h->dTriLo); be.free(h->dTriHi);
   be.free(h->dNodes); be.free(h->dBvhTris); be.free(h->dNodeParent); be.free(h->dNodeLo); be.free(h->dNodeHi); be.free(h->dNodePending); be.free(h->dVisit);
   be.free(h->dShadeTris); h->dShadeTris = nullptr; be.free(h->dShadeUV); h->dShadeUV = nullptr;
+  be.free(h->dInstChanged); h->dInstChanged = nullptr;
   be.free(h->dLmStatic); be.free(h->dLmDynamic); be.free(h->dLmNear); be.free(h->dLmBase); be.free(h->dLmMoved);
   h->dLmStatic = nullptr; h->dLmDynamic = nullptr; h->dLmNear = nullptr; h->dLmBase = nullptr; h->dLmMoved = nullptr; h->lmRes = 0; h->lmLights = 0; h->lmDynamicValid = false;
   be.free(h->dSmStatic); be.free(h->dSmDynamic); h->dSmStatic = nullptr; h->dSmDynamic = nullptr; h->smRes = 0; h->smValid = false; h->smDynamicValid = false; h->lmMovedValid = false;
@@ -358,6 +361,59 @@ __global__ void __launch_bounds__(256) k_sunmap_raster_big(const SunMapCtx c, co
     sm_fill(sIt, c, threadIdx.x, blockDim.x);
   }
 }
+// Refit: the dynamic maps hold the triangles of the instances that moved — a few thousand of a few hundred thousand.  One thread per
+// (triangle, light) left all the work to the few warps that hold a mover's triangles, 32 footprints x 6 faces in a row each (C4:
+// 117 us for the lights, 25 us for the sun).  Here the movers' triangles are compacted first and every (triangle, light) pair gets a
+// thread (a warp per pair was tried: every lane repeats the set-up, 186 M warp instructions, slower): at the dynamic maps' resolution a
+// footprint is a handful of texels, which the thread fills itself; the rare large one (a mover next to a light) goes to the queue
+// that k_lightmap_raster_big fills one block per footprint.
+__global__ void __launch_bounds__(256) k_moved_tris(const uint32_t* triInstance, const uint32_t* moved, uint32_t numTris, uint32_t* list, uint32_t* count) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
+  const bool m = t < numTris && moved[triInstance[t]] != 0u;
+  const uint32_t b = __ballot_sync(0xFFFFFFFFu, m);
+  if (b == 0u) return;
+  const int leader = __ffs((int)b) - 1;
+  uint32_t base = 0;
+  if ((int)lane == leader) base = atomicAdd(count, (uint32_t)__popc(b));
+  base = __shfl_sync(0xFFFFFFFFu, base, leader);
+  if (m) list[base + (uint32_t)__popc(b & ((1u << lane) - 1u))] = t;
+}
+#define LM_OWN_TEXELS 64
+__global__ void __launch_bounds__(128) k_lightmap_raster_list(const LmBuildCtx c, const BigQueue big, const uint32_t* list, const uint32_t* count) {
+  const uint32_t n = *count * c.numLights;
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
+    const uint32_t t = list[w / c.numLights], li = w % c.numLights;
+    LmTri tri;
+    tri.n = mk3(0.0f); tri.h = 0.0f; tri.daabb = 0.0f; tri.skinny = false; tri.nearLight = false;
+    if (!lm_pair_setup(c, t, li, tri)) continue;
+    if (tri.nearLight) c.nearFlags[li] = 1u;
+    for (int face = 0; face < 6; ++face) {
+      LmItem it; it.x0 = 0; it.x1 = -1; it.y0 = 0; it.y1 = -1; it.ed.use = false;
+      if (!lm_face_rect(tri, face, c.R, it.x0, it.x1, it.y0, it.y1, it.ed)) continue;
+      it.n = tri.n; it.h = tri.h; it.daabb = tri.daabb; it.skinny = tri.skinny ? 1u : 0u; it.tid = t; it.face = (uint32_t)face; it.light = li;
+      if ((it.x1 - it.x0 + 1) * (it.y1 - it.y0 + 1) > LM_OWN_TEXELS) {
+        const uint32_t slot = atomicAdd(big.count, 1u);
+        if (slot < LM_BIG_CAP) { reinterpret_cast<LmItem*>(big.items)[slot] = it; continue; }      // queue full: filled here after all
+      }
+      lm_fill(it, c, 0u, 1u);
+    }
+  }
+}
+__global__ void __launch_bounds__(128) k_sunmap_raster_list(const SunMapCtx c, const BigQueue big, const uint32_t* list, const uint32_t* count) {
+  const uint32_t n = *count;
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
+    const uint32_t t = list[w];
+    SmTri tri; SmItem it; it.x0 = 0; it.x1 = -1; it.y0 = 0; it.y1 = -1; it.ed.use = false;
+    tri.smax = 0.0f; tri.ga = 0.0f; tri.gb = 0.0f; tri.flat = false; tri.pa[0] = 0.0f; tri.pb[0] = 0.0f; tri.ps[0] = 0.0f;
+    if (!sm_tri_setup(c, t, tri, it.x0, it.x1, it.y0, it.y1, it.ed)) continue;
+    it.smax = tri.smax; it.ga = tri.ga; it.gb = tri.gb; it.pa0 = tri.pa[0]; it.pb0 = tri.pb[0]; it.ps0 = tri.ps[0]; it.flat = tri.flat ? 1u : 0u; it.tid = t;
+    if ((it.x1 - it.x0 + 1) * (it.y1 - it.y0 + 1) > LM_OWN_TEXELS) {
+      const uint32_t slot = atomicAdd(big.count, 1u);
+      if (slot < LM_BIG_CAP) { reinterpret_cast<SmItem*>(big.items)[slot] = it; continue; }
+    }
+    sm_fill(it, c, 0u, 1u);
+  }
+}
 #endif
 #ifndef DDGI_HOST_EMU
 __global__ void __launch_bounds__(256) k_zero_words(uint32_t* p, uint32_t n);
@@ -382,10 +438,17 @@ int rasterSunMap(anerend_ddgi* h, unsigned long long* target, const uint32_t* mo
 #ifndef DDGI_HOST_EMU
   { int rq = ensureBigQueue(h); if (rq) return rq; }
   const BigQueue big{h->dBigItems, h->dBigCount};
+  if (moved && h->dMovedTris) {          // refit: a thread per triangle of a moved instance (compacted by refitLightMaps)
+    k_zero_words<<<1, 32, 0, be.stream>>>(h->dBigCount, 1u);
+    k_sunmap_raster_list<<<8 * (h->sms > 0 ? h->sms : 148), 128, 0, be.stream>>>(c, big, h->dMovedTris, h->dMovedCount);
+    k_sunmap_raster_big<<<2 * (h->sms > 0 ? h->sms : 148), 256, 0, be.stream>>>(c, big);
+    be.launches += 3;
+  } else {
   k_zero_words<<<1, 32, 0, be.stream>>>(h->dBigCount, 1u);
   k_sunmap_raster<<<(h->numTris + 255u) / 256u, 256, 0, be.stream>>>(c, big);
   k_sunmap_raster_big<<<4 * (h->sms > 0 ? h->sms : 148), 256, 0, be.stream>>>(c, big);
   be.launches += 3;
+  }
 #else
   DDGI_LAUNCH(be, k_sunmap_raster_serial, sunmap_raster_body, h->numTris, c, 256);
 #endif
@@ -412,10 +475,17 @@ int rasterLightMap(anerend_ddgi* h, unsigned long long* target, const uint32_t* 
 #ifndef DDGI_HOST_EMU
   { int rq = ensureBigQueue(h); if (rq) return rq; }
   const BigQueue big{h->dBigItems, h->dBigCount};
+  if (moved && h->dMovedTris) {
+    k_zero_words<<<1, 32, 0, be.stream>>>(h->dBigCount, 1u);
+    k_lightmap_raster_list<<<8 * (h->sms > 0 ? h->sms : 148), 128, 0, be.stream>>>(c, big, h->dMovedTris, h->dMovedCount);
+    k_lightmap_raster_big<<<2 * (h->sms > 0 ? h->sms : 148), 256, 0, be.stream>>>(c, big);
+    be.launches += 3;
+  } else {
   k_zero_words<<<1, 32, 0, be.stream>>>(h->dBigCount, 1u);
   k_lightmap_raster<<<dim3((h->numTris + 255u) / 256u, h->lmLights), 256, 0, be.stream>>>(c, big);
   k_lightmap_raster_big<<<4 * (h->sms > 0 ? h->sms : 148), 256, 0, be.stream>>>(c, big);
   be.launches += 3;
+  }
 #else
   DDGI_LAUNCH(be, k_lightmap_raster_serial, lightmap_raster_body, h->numTris * h->lmLights, c, 256);
 #endif
@@ -451,6 +521,19 @@ int refitLightMaps(anerend_ddgi* h, bool verticesChanged) {
   LmMovedCtx mc{h->dXforms, h->dLmBase, h->dLmMoved};
   DDGI_LAUNCH(be, k_lightmap_moved, lm_moved_body, ni, mc, 128);
   h->lmMovedValid = true;
+#ifndef DDGI_HOST_EMU
+  if (h->lmRes || h->smValid) {
+    if (h->movedCap < h->capTris) {
+      be.free(h->dMovedTris); h->dMovedTris = nullptr;
+      BE_CHECK(h, be.alloc(&h->dMovedTris, h->capTris)); h->movedCap = h->capTris;
+      if (!h->dMovedCount) BE_CHECK(h, be.alloc(&h->dMovedCount, 1));
+    }
+    { int rq = ensureBigQueue(h); if (rq) return rq; }      // also learns the SM count
+    k_zero_words<<<1, 32, 0, be.stream>>>(h->dMovedCount, 1u);
+    k_moved_tris<<<(h->numTris + 255u) / 256u, 256, 0, be.stream>>>(h->dTriInstance, h->dLmMoved, h->numTris, h->dMovedTris, h->dMovedCount);
+    be.launches += 2;
+  }
+#endif
   if (h->lmRes) {
     if (!h->dLmDynamic) BE_CHECK(h, be.alloc(&h->dLmDynamic, (size_t)h->lmLights * 6u * (h->lmRes >> LM_DYN_SHIFT) * (h->lmRes >> LM_DYN_SHIFT)));
     h->lmDynamicValid = true;
@@ -859,11 +942,16 @@ int refitAccel(anerend_ddgi* h) {
   c.sceneBounds = nullptr;
   const bool verticesChanged = h->verticesDirty;
   if (h->verticesDirty) { c.shadeTris = h->dShadeTris; c.shadeUV = h->dShadeUV; h->verticesDirty = false; h->dirtyVerts.clear(); }   // deformed meshes: refresh the shading records too
+  else {
+    // moving nodes only: triangles and leaf copies are recomputed where an instance's transform changed (C4: 16 movers of 161 instances)
+    if (!h->dInstChanged) BE_CHECK(h, be.alloc(&h->dInstChanged, (size_t)h->capInstances));
+    c.instChanged = h->dInstChanged;
+  }
   be.mark(4);
   DDGI_LAUNCH(be, k_inst_xform, inst_xform_body, (uint32_t)h->instances.size(), c, 128);
   DDGI_LAUNCH(be, k_flatten_scene, flatten_tri_body, h->numTris, c, 256);
   DDGI_LAUNCH(be, k_refit_tris, refit_tris_body, h->numTris, c, 256);
-  BE_CHECK(h, be.zero(h->dVisit, ((size_t)h->numTris + 1) * sizeof(uint32_t)));
+  BE_CHECK(h, be.zero(h->dVisit, ((size_t)h->numNodes + 1) * sizeof(uint32_t)));
   DDGI_LAUNCH(be, k_refit_nodes, refit_node_body, h->numNodes, c, 128);
   { int rcl = refitLightMaps(h, verticesChanged); if (rcl) return rcl; }
   be.mark(5);
@@ -1295,6 +1383,7 @@ void destroyHandle(anerend_ddgi* h) {
   if (h->xStream) { cudaStreamDestroy(h->xStream); cudaEventDestroy(h->evConv); cudaEventDestroy(h->evXDone); h->xStream = nullptr; }
 #endif
   be.free(h->dXflags); be.free(h->dXerr); be.free(h->dSelected); be.free(h->dVisChanged); be.free(h->dBigItems); be.free(h->dBigCount);
+  be.free(h->dMovedTris); be.free(h->dMovedCount);
   freeAccel(h); freeScene(h);
   be.free(h->dAtlas); be.free(h->dTemp); be.free(h->dRayIrr); be.free(h->dDirs); be.free(h->dFib); be.freeHostPinned(h->hDirs); be.free(h->dRayOrder);
   be.free(h->dLayerMap); be.freeHostPinned(h->hLayerMap);

@@ -82,6 +82,8 @@ struct BuildCtx {
   uint32_t* triInstanceOut;              // k_tri_instance: triangle -> index of the instance whose range [firstTri, firstTri + numTris) holds it
   uint32_t level;                        // BVH8 collapse: queue length of this level = counters[CNT_LEVEL0 + level], the next level's is counted beside it
   uint32_t leafMax;                      // primitives per leaf slot (0 = 3, triangles; 1 for the instance level of a two-level structure)
+  // refit of moving nodes: which instances' transforms changed since the last build / refit (k_inst_xform compares); null = all
+  uint32_t* instChanged;
 };
 // counters[]: [0] BVH8 nodes allocated, [1] triangle slots allocated, [2] -, [3] PLOC merges so far, [4] clusters of the current PLOC round,
 // [CNT_LEVEL0 + L] work items of collapse level L.  Everything the build loops depend on stays on the device: the host launches
@@ -110,6 +112,12 @@ HD void inst_xform_body(uint32_t i, const BuildCtx& c) {
   x.w2o[3] = r01; x.w2o[4] = r11; x.w2o[5] = r21;
   x.w2o[6] = r02; x.w2o[7] = r12; x.w2o[8] = r22;
   x._pad[0] = x._pad[1] = x._pad[2] = 0.0f;
+  if (c.instChanged) {
+    const InstXform& old = c.xforms[i];
+    bool same = true;
+    for (int k = 0; k < 12; ++k) same = same && f2u(old.o2w[k]) == f2u(x.o2w[k]);
+    c.instChanged[i] = same ? 0u : 1u;
+  }
   c.xforms[i] = x;
 }
 
@@ -131,6 +139,7 @@ HD float ordered_to_float(int i) { return u2f((uint32_t)(i >= 0 ? i : i ^ 0x7FFF
 
 HD void flatten_tri_body(uint32_t t, const BuildCtx& c) {
   uint32_t ii = c.triInstance[t];
+  if (c.instChanged && !c.instChanged[ii]) return;      // refit: the triangle is where it was
   const DInstance in = c.instances[ii];
   const float* o2w = c.xforms[ii].o2w;
   uint32_t prim = t - in.firstTri;
@@ -453,12 +462,14 @@ HD void collapse_body(uint32_t i, const BuildCtx& c) {
 // ----------------------------------------------------------------------------------------------------
 HD void refit_tris_body(uint32_t slot, const BuildCtx& c) {
   uint32_t gid = f2u(c.bvhTris[3 * (size_t)slot + 2].y);
+  if (c.instChanged && !c.instChanged[c.triInstance[gid]]) return;
   c.bvhTris[3 * (size_t)slot + 0] = c.wtri[3 * (size_t)gid + 0];
   c.bvhTris[3 * (size_t)slot + 1] = c.wtri[3 * (size_t)gid + 1];
   c.bvhTris[3 * (size_t)slot + 2] = c.wtri[3 * (size_t)gid + 2];
 }
 // thread per BVH8 node; nodes without internal children start, the last child to finish continues with the parent.
-// c.visit[node] (zeroed before launch) counts finished internal children.
+// c.visit[node] (zeroed before launch) counts finished internal children.  (Skipping the nodes nothing moved under was measured:
+// the launch is as long as the recomputation along ONE path from a mover's leaf to the root, a serial chain through the levels.)
 HD void refit_node_body(uint32_t node0, const BuildCtx& c) {
   if (c.nodePending[node0] != 0u) return;
   uint32_t node = node0;
