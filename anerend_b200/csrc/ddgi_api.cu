@@ -365,8 +365,8 @@ __global__ void __launch_bounds__(256) k_sunmap_raster_big(const SunMapCtx c, co
 // (triangle, light) left all the work to the few warps that hold a mover's triangles, 32 footprints x 6 faces in a row each (C4:
 // 117 us for the lights, 25 us for the sun).  Here the movers' triangles are compacted first and every (triangle, light) pair gets a
 // thread (a warp per pair was tried: every lane repeats the set-up, 186 M warp instructions, slower): at the dynamic maps' resolution a
-// footprint is a handful of texels, which the thread fills itself; the rare large one (a mover next to a light) goes to the queue
-// that k_lightmap_raster_big fills one block per footprint.
+// footprint is a handful of texels, which the thread fills itself (up to LM_OWN_TEXELS: a thread that fills 64 texels on several faces
+// IS the duration of the launch); larger ones go to the queue that k_lightmap_raster_big fills, here one warp per footprint.
 __global__ void __launch_bounds__(256) k_moved_tris(const uint32_t* triInstance, const uint32_t* moved, uint32_t numTris, uint32_t* list, uint32_t* count) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
   const bool m = t < numTris && moved[triInstance[t]] != 0u;
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256) k_moved_tris(const uint32_t* triInstance,
   base = __shfl_sync(0xFFFFFFFFu, base, leader);
   if (m) list[base + (uint32_t)__popc(b & ((1u << lane) - 1u))] = t;
 }
-#define LM_OWN_TEXELS 64
+#define LM_OWN_TEXELS 12
 __global__ void __launch_bounds__(128) k_lightmap_raster_list(const LmBuildCtx c, const BigQueue big, const uint32_t* list, const uint32_t* count) {
   const uint32_t n = *count * c.numLights;
   for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
@@ -441,7 +441,7 @@ int rasterSunMap(anerend_ddgi* h, unsigned long long* target, const uint32_t* mo
   if (moved && h->dMovedTris) {          // refit: a thread per triangle of a moved instance (compacted by refitLightMaps)
     k_zero_words<<<1, 32, 0, be.stream>>>(h->dBigCount, 1u);
     k_sunmap_raster_list<<<8 * (h->sms > 0 ? h->sms : 148), 128, 0, be.stream>>>(c, big, h->dMovedTris, h->dMovedCount);
-    k_sunmap_raster_big<<<2 * (h->sms > 0 ? h->sms : 148), 256, 0, be.stream>>>(c, big);
+    k_sunmap_raster_big<<<32 * (h->sms > 0 ? h->sms : 148), 32, 0, be.stream>>>(c, big);
     be.launches += 3;
   } else {
   k_zero_words<<<1, 32, 0, be.stream>>>(h->dBigCount, 1u);
@@ -478,7 +478,7 @@ int rasterLightMap(anerend_ddgi* h, unsigned long long* target, const uint32_t* 
   if (moved && h->dMovedTris) {
     k_zero_words<<<1, 32, 0, be.stream>>>(h->dBigCount, 1u);
     k_lightmap_raster_list<<<8 * (h->sms > 0 ? h->sms : 148), 128, 0, be.stream>>>(c, big, h->dMovedTris, h->dMovedCount);
-    k_lightmap_raster_big<<<2 * (h->sms > 0 ? h->sms : 148), 256, 0, be.stream>>>(c, big);
+    k_lightmap_raster_big<<<32 * (h->sms > 0 ? h->sms : 148), 32, 0, be.stream>>>(c, big);          // footprints of a few dozen texels: a warp each
     be.launches += 3;
   } else {
   k_zero_words<<<1, 32, 0, be.stream>>>(h->dBigCount, 1u);

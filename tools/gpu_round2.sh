@@ -18,6 +18,8 @@ for WL in c2 c4 c5; do
 done
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err
 python tools/build_time.py c2 c3 c5 > gpurun_out/${TAG}_build_time.txt 2>&1
+python tools/two_level_bench.py instanced4096 c3 c5 > gpurun_out/${TAG}_two_level.jsonl 2> gpurun_out/${TAG}_two_level.err
+python tools/two_level_stats.py c3 instanced4096 > gpurun_out/${TAG}_two_level_stats.txt 2>&1
 python - <<PY
 import json
 for f in ("bench_default", "bench_c2", "bench_c4", "bench_c5", "bench_reference"):
