@@ -672,8 +672,12 @@ int buildHierarchy(anerend_ddgi* h, BuildCtx c, uint32_t n, uint32_t* numNodesOu
     // Rounds are launched in batches without a host round trip: every kernel takes the live cluster count from the device
     // (numTris - counters[3]) and is launched over the last count the host has seen; rounds past the end of the hierarchy do nothing.
     uint32_t m = n, merged = 0; int cur = 0, rounds = 0;
-    const int batch = 8;
     while (okP && m > 1) {
+#ifndef DDGI_HOST_EMU
+      const int batch = m <= (uint32_t)PLOC_TAIL ? 0 : 8;      // few clusters (the instance level, a small mesh): the one-block tail does it all
+#else
+      const int batch = 8;
+#endif
       for (int k = 0; k < batch && okP; ++k) {
         c.numClusters = m;
         c.clRef = clRef[cur]; c.clLo = clLo[cur]; c.clHi = clHi[cur]; c.clRefOut = clRef[cur ^ 1]; c.clLoOut = clLo[cur ^ 1]; c.clHiOut = clHi[cur ^ 1];
@@ -716,8 +720,10 @@ int buildHierarchy(anerend_ddgi* h, BuildCtx c, uint32_t n, uint32_t* numNodesOu
   uint32_t missParent = DDGI_MISS;
   BE_CHECK(h, be.h2d(c.nodeParent, &missParent, sizeof(uint32_t)));
   uint32_t depth = 0;
+  uint32_t levelBatch = 4u;      // levels launched per look at the counters: a hierarchy of n primitives is rarely deeper than log8(n) + 3
+  for (uint64_t cap8 = 8; cap8 < n && levelBatch < 12u; cap8 *= 8u) ++levelBatch;
   for (bool more = true; more;) {
-    const uint32_t stop = std::min<uint32_t>(depth + 12u, (uint32_t)CNT_LEVELS);
+    const uint32_t stop = std::min<uint32_t>(depth + levelBatch, (uint32_t)CNT_LEVELS);
     for (; depth < stop; ++depth) {
       uint64_t bound = 1; for (uint32_t k = 0; k < depth && bound < nodeCap; ++k) bound *= 8u;
       c.qin = qa; c.qout = qb; c.level = depth;
