@@ -751,10 +751,11 @@ int uploadTlasInputs(anerend_ddgi* h) {
   Backend& be = h->be;
   const uint32_t ni = (uint32_t)h->instances.size(), nt = (uint32_t)h->tlasList.size();
   std::vector<uint2> ib(ni);
+  std::vector<int> slot(h->meshes.size(), -1);              // mesh -> its hierarchy
+  for (size_t u = 0; u < h->blas.size(); ++u) slot[h->blas[u].mesh] = (int)u;
   for (uint32_t i = 0; i < ni; ++i) {
-    const anerend_ddgi::MeshBlas* mb = nullptr;
-    for (const auto& b : h->blas) if (b.mesh == h->instances[i].mesh) { mb = &b; break; }
-    ib[i] = mb ? make_uint2(mb->root, mb->triBase) : make_uint2(0u, 0u);
+    const int u = slot[h->instances[i].mesh];
+    ib[i] = u >= 0 ? make_uint2(h->blas[u].root, h->blas[u].triBase) : make_uint2(0u, 0u);
   }
   BE_CHECK(h, be.h2d(h->dInstances, h->instances.data(), ni * sizeof(DInstance)));
   BE_CHECK(h, be.h2d(h->dInstBlas, ib.data(), ni * sizeof(uint2)));
@@ -801,13 +802,13 @@ int buildAccelTwoLevel(anerend_ddgi* h) {
   const uint32_t ni = (uint32_t)inst.size();
   // the distinct meshes, in order of first use
   std::vector<anerend_ddgi::MeshBlas> um; std::vector<uint32_t> list;
+  std::vector<uint8_t> seenMesh(h->meshes.size(), 0);
   uint32_t total = 0, maxMesh = 0;
   for (uint32_t i = 0; i < ni; ++i) {
     if (inst[i].numTris == 0) continue;
     list.push_back(i);
-    bool seen = false;
-    for (const auto& b : um) if (b.mesh == inst[i].mesh) { seen = true; break; }
-    if (seen) continue;
+    if (seenMesh[inst[i].mesh]) continue;
+    seenMesh[inst[i].mesh] = 1;
     anerend_ddgi::MeshBlas b{}; b.mesh = inst[i].mesh; b.numTris = inst[i].numTris; b.triBase = total;
     total += b.numTris; maxMesh = std::max(maxMesh, b.numTris); um.push_back(b);
   }
@@ -1692,7 +1693,7 @@ int DDGI_API(apply_camera_cull)(anerend_ddgi_t* h, float range, uint32_t* change
 int DDGI_API(get_bvh_info)(anerend_ddgi_t* h, anerend_ddgi_bvh_info_t* o) {
   if (!h) return ANEREND_DDGI_E_INVALID;
   memset(o, 0, sizeof(*o));
-  o->num_triangles = h->numTris; o->num_nodes = h->numNodes; o->node_bytes = 80; o->tri_bytes = 48; o->num_instances = (uint32_t)h->instances.size();
+  o->num_triangles = h->numTris; o->num_nodes = h->numNodes + (twoLevel(h) ? h->blasNodes : 0u); o->node_bytes = 80; o->tri_bytes = 48; o->num_instances = (uint32_t)h->instances.size();
   for (int k = 0; k < 3; ++k) { o->bounds_min[k] = h->boundsMin[k]; o->bounds_max[k] = h->boundsMax[k]; }
   return 0;
 }

@@ -115,7 +115,7 @@ typedef struct anerend_ddgi_stats {
 
 typedef struct anerend_ddgi_bvh_info {
   uint32_t num_triangles;     /* flattened world triangles                                   */
-  uint32_t num_nodes;         /* BVH8 nodes                                                  */
+  uint32_t num_nodes;         /* BVH8 nodes (two-level structure: instance level + all meshes) */
   uint32_t node_bytes;        /* bytes per compressed node (80)                              */
   uint32_t tri_bytes;         /* bytes per traversal triangle record (48)                    */
   uint32_t num_instances;     /* (renderable, mesh) pairs that passed tlas_update.comp's test */
