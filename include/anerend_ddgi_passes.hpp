@@ -47,6 +47,9 @@ struct Volume {
   anerend_ddgi_params_t params{};
   std::string error;
   bool topologyDirty = true;      // set by the engine when instances appear / disappear / flip visibility: TLASUpdate rebuilds instead of refitting
+  uint32_t flags = 0;             // ANEREND_DDGI_FLAG_* for the handle, set before the first registerToGraph; ANEREND_DDGI_FLAG_TWO_LEVEL gives
+                                  // the reference's own structure: one hierarchy per mesh (VulkanRenderer.cpp:1267-1417) and an instance level
+                                  // that "TLASUpdate" rebuilds every frame (UpdateTLASPass.cpp:198-228)
   ~Volume() { if (handle) anerend_cuda_ddgi_destroy(handle); }
   // Called from registerToGraph: the reference re-registers the same pass objects on swap-chain recreation
   // (VulkanRenderer.cpp:1962-2000), re-creating and re-clearing the atlas and resetting _currentLayer.
@@ -60,7 +63,7 @@ struct Volume {
     params.probe_step[0] = 1.0f; params.probe_step[1] = 2.0f; params.probe_step[2] = 1.0f;   // probe_helpers.glsl:3
     params.t_min = 0.1f; params.t_max = 50.0f;                     // rgen:91-92
     params.hysteresis = 0.96f;                                     // probe_conv.comp:85
-    params.slab_begin = 0; params.slab_end = numProbesY; params.device = -1;
+    params.slab_begin = 0; params.slab_end = numProbesY; params.device = -1; params.flags = flags;
     int rc = anerend_cuda_ddgi_create(&params, &handle);
     if (rc != 0) { handle = nullptr; error = "anerend_cuda_ddgi_create failed (no CUDA device?)"; std::printf("%s\n", error.c_str()); return false; }
     return true;

@@ -106,6 +106,7 @@ int main(int argc, char** argv) {
   int frames = argc > 1 ? atoi(argv[1]) : 4; uint32_t seed = argc > 2 ? (uint32_t)atoi(argv[2]) : 1u;
   stub::RenderContext rc; stub::FrameGraphBuilder fgb;
   auto vol = std::make_shared<Volume>();
+  if (const char* e = getenv("DDGI_TEST_FLAGS")) vol->flags = (uint32_t)strtoul(e, nullptr, 0);      // e.g. ANEREND_DDGI_FLAG_TWO_LEVEL
   IrradianceProbeTranslationPass<stub::Engine> trans(vol);
   IrradianceProbeRayTracingPass<stub::Engine> rt(vol);
   IrradianceProbeConvolvePass<stub::Engine> conv(vol);

@@ -50,3 +50,8 @@ def test_adapter_runs_the_frame_cadence(tmp_path, make_gpu):
     import random  # noqa: F401  (the C++ side draws rotations from std::mt19937; replay its axis/angle stream here)
     fnv = [l for l in out.stdout.splitlines() if l.startswith("OK frames")][0].split("fnv=")[1]
     assert len(fnv) == 16
+    # the same frames on the two-level structure (the reference's TLAS / BLAS shape): the same atlas, bit for bit
+    from anerend_b200 import layouts as L
+    out2 = subprocess.run([exe, "6", "7", path], capture_output=True, text=True, timeout=300, env=dict(os.environ, DDGI_TEST_FLAGS=str(L.FLAG_TWO_LEVEL)))
+    assert out2.returncode == 0, out2.stdout + out2.stderr
+    assert [l for l in out2.stdout.splitlines() if l.startswith("OK frames")][0].split("fnv=")[1] == fnv
