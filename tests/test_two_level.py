@@ -142,3 +142,70 @@ def test_two_level_deforming_mesh_rebuilds_only_its_hierarchy(oracle, make_emu):
         assert np.array_equal(o.download_atlas(), e.download_atlas())
     o.close()
     e.close()
+
+
+def test_two_level_random_scenes_bit_exact(oracle, make_emu):
+    """Seeded fuzz (a slice of tests/test_fuzz_parity.py with the flag set): random soups / textured soups / Cornell boxes / instanced
+    fields, random grids, ray counts, cameras and flags — two updates each, everything bit for bit."""
+    for seed in range(5000, 5032):
+        rng = np.random.RandomState(seed)
+        nxz, ny, nr = int(rng.choice([1, 2, 3, 5])), int(rng.choice([1, 2, 3])), int(rng.choice([32, 64, 128, 256]))
+        cam = tuple(rng.uniform(-3, 3, 3) * [1, 0.5, 1] + [0, 1.5, 0])
+        kind = rng.randint(0, 4)
+        if kind == 0:
+            s = scenes.random_soup(seed, ntris=int(rng.choice([40, 300, 1500])), extent=float(rng.uniform(2, 12)), grid=(nxz, ny, nr), camera=cam,
+                                   nlights=int(rng.randint(0, 4)))
+        elif kind == 1:
+            s = scenes.textured_soup(seed, ntris=int(rng.choice([60, 400])), grid=(nxz, ny, nr), camera=cam)
+        elif kind == 2:
+            s = scenes.cornell_box(seed=seed, grid=(nxz, ny, nr), wall_res=int(rng.choice([2, 6])), box_res=2)
+            s.ubo = s.with_camera(cam)
+        else:
+            s = scenes.instanced_field(seed, instances=int(rng.choice([3, 30, 120])), grid=(nxz, ny, nr), extent=float(rng.uniform(4, 16)), seg=(8, 4),
+                                       nlights=int(rng.randint(0, 4)))
+        if rng.rand() < 0.3:
+            s.ubo["flags"] &= ~np.uint32(L.UBO_DDGI_MULTI_FLAG)
+        extra = L.FLAG_SKIP_DEAD_SHADOW_RAYS if rng.rand() < 0.5 else 0
+        o, e = oracle.Oracle(make_params(nxz, ny, nr, flags=ALL | extra)), make_emu(make_params(nxz, ny, nr, flags=ALL | extra | L.FLAG_TWO_LEVEL))
+        rots = parity.setup_pair(s, (o, e), seed=seed)
+        for it in range(2):
+            for h in (o, e):
+                h.translate()
+                h.update(-1, rots)
+            for layer in range(ny):
+                assert parity.compare_records(o.download_ray_records(layer), e.download_ray_records(layer)) == 0, seed
+            assert np.array_equal(o.download_atlas(), e.download_atlas()), seed
+        o.close()
+        e.close()
+
+
+def test_two_level_random_refits_and_vertex_updates_bit_exact(oracle, make_emu):
+    """Moving instances (random rigid steps, now and then mirrored) and deforming vertex ranges, refit after each step."""
+    for seed in range(6000, 6012):
+        rng = np.random.RandomState(seed)
+        nxz, ny, nr = int(rng.choice([2, 3])), int(rng.choice([1, 2])), 64
+        s = scenes.random_soup(seed, ntris=int(rng.choice([100, 600])), grid=(nxz, ny, nr))
+        o, e = oracle.Oracle(make_params(nxz, ny, nr, flags=ALL)), make_emu(make_params(nxz, ny, nr, flags=ALL | L.FLAG_TWO_LEVEL))
+        rots = parity.setup_pair(s, (o, e), seed=seed)
+        verts = s.vertices.copy()
+        for step in range(3):
+            rend = s.renderables.copy()
+            for i in range(len(rend)):
+                if rng.rand() < 0.6:
+                    M = rend["transform"][i].reshape(4, 4).T.astype(np.float64)
+                    M2 = scenes.translate(rng.uniform(-1, 1, 3)) @ scenes.rotate(int(rng.randint(0, 3)), rng.uniform(0, 360)) @ M
+                    if rng.rand() < 0.2:
+                        M2 = M2 @ scenes.scale((-1, 1, 1))
+                    rend["transform"][i] = M2.T.astype(np.float32).ravel()
+            k0 = int(rng.randint(0, len(verts) - 10))
+            k1 = min(len(verts), k0 + int(rng.randint(1, 200)))
+            verts["pos"][k0:k1] += rng.uniform(-0.05, 0.05, (k1 - k0, 3)).astype(np.float32)
+            for h in (o, e):
+                h.update_vertices(verts[k0:k1], first=k0)
+                h.refit_accel(rend)
+                h.update(-1, rots)
+            for layer in range(ny):
+                assert parity.compare_records(o.download_ray_records(layer), e.download_ray_records(layer)) == 0, (seed, step)
+            assert np.array_equal(o.download_atlas(), e.download_atlas()), (seed, step)
+        o.close()
+        e.close()
