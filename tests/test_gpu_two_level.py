@@ -212,3 +212,35 @@ def test_two_level_row_stripes_assemble_the_one_level_atlas(make_gpu):
         assert np.array_equal(merged, full.download_atlas())
     for h in [full] + parts:
         h.close()
+
+
+def test_two_level_random_scenes_on_the_wavefront_kernels(oracle, make_gpu):
+    """Seeded fuzz of k_trace<.., TWO> / k_shade_prep<.., TWO>: random soups, Cornell boxes and instanced fields (tiny, rotated,
+    non-uniformly scaled instances), random grids / ray counts / cameras / light counts; hit ids, (t, u, v), lit masks and the atlas
+    bit for bit, radiance to the pow ulps of DESIGN.md §2."""
+    for seed in range(8000, 8024):
+        rng = np.random.RandomState(seed)
+        nxz, ny, nr = int(rng.choice([2, 3, 5, 8])), int(rng.choice([1, 2, 3])), int(rng.choice([32, 64, 128, 256]))
+        cam = tuple(rng.uniform(-3, 3, 3) * [1, 0.5, 1] + [0, 1.5, 0])
+        kind = rng.randint(0, 3)
+        if kind == 0:
+            s = scenes.random_soup(seed, ntris=int(rng.choice([300, 1500, 6000])), extent=float(rng.uniform(2, 12)), grid=(nxz, ny, nr), camera=cam,
+                                   nlights=int(rng.randint(0, 4)))
+        elif kind == 1:
+            s = scenes.instanced_field(seed, instances=int(rng.choice([30, 200, 900])), grid=(nxz, ny, nr), extent=float(rng.uniform(3, 20)),
+                                       seg=(int(rng.choice([6, 12])), 4), nlights=int(rng.randint(0, 4)))
+            s.ubo = s.with_camera(cam)
+        else:
+            s = scenes.cornell_box(seed=seed, grid=(nxz, ny, nr), wall_res=int(rng.choice([2, 6, 12])), box_res=2)
+            s.ubo = s.with_camera(cam)
+        extra = L.FLAG_SKIP_DEAD_SHADOW_RAYS if rng.rand() < 0.5 else 0
+        flags = L.FLAG_RAY_RECORDS | L.FLAG_POINT_LIGHTS | extra
+        o, g = oracle.Oracle(make_params(nxz, ny, nr, flags=flags)), make_gpu(make_params(nxz, ny, nr, flags=flags | L.FLAG_TWO_LEVEL))
+        rots = parity.setup_pair(s, (o, g), seed=seed)
+        for it in range(2):
+            for h in (o, g):
+                h.translate()
+                h.update(-1, rots)
+            _bit_exact(o, g, ny, radiance_bits=False)
+        o.close()
+        g.close()
