@@ -186,6 +186,10 @@ class DdgiHandle:
         self._call("get_bvh_info", C.byref(b))
         return b
 
+    def set_timers(self, level):
+        """0 none, 1 around the passes (default), 2 also around every kernel of the RT pass (timings()['rt_kernel_ms'])."""
+        self._call("set_timers", C.c_int32(level))
+
     def two_level_info(self):
         b = TwoLevelInfo()
         self._call("get_two_level_info", C.byref(b))

@@ -1083,7 +1083,7 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   { int rf = fenceExchange(h); if (rf) return rf; }      // the only kernel of the pass that samples the atlas
   BE_CHECK(h, be.ok((h->p.flags & ANEREND_DDGI_FLAG_FAST_MATH) ? launch_shade_fast(f, be.stream) : launch_shade_exact(f, be.stream)));
   be.mark(10);
-  h->timedKernels = true;
+  h->timedKernels = be.timerLevel >= 2;
   be.launches += 5;
   BE_CHECK(h, be.check());
   return 0;
@@ -1431,6 +1431,7 @@ int DDGI_API(create)(const anerend_ddgi_params_t* params, anerend_ddgi_t** out) 
   h->W = 10 * h->nXZ; h->H = 10 * h->nXZ * h->nY; h->P = h->nXZ * h->nXZ; h->Pl = h->P;
   Backend& be = h->be;
   if (!be.init(q.device)) { delete h; return ANEREND_DDGI_E_CUDA; }   // no CUDA device: there is no CPU fallback
+
   const size_t texels = (size_t)h->W * h->H, rays = (size_t)h->nY * h->P * h->N;
   bool ok = be.alloc(&h->dAtlas, texels) && be.alloc(&h->dTemp, texels) && be.alloc(&h->dRayIrr, rays) &&
             be.alloc(&h->dDirs, (size_t)h->nY * h->N) && be.allocHostPinned(&h->hDirs, (size_t)h->nY * h->N) &&
@@ -2195,10 +2196,18 @@ int DDGI_API(download_texel_records)(anerend_ddgi_t* h, float* out, size_t bytes
   BE_CHECK(h, h->be.d2h(out, h->dTexelRecords, bytes)); return 0;
 }
 
+int DDGI_API(set_timers)(anerend_ddgi_t* h, int32_t level) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
+  if (level < 0 || level > 2) return fail(h, ANEREND_DDGI_E_INVALID, "timer level: 0 none, 1 passes, 2 passes + kernels");
+  h->be.timerLevel = level;
+  h->timed[0] = h->timed[1] = h->timed[2] = h->timed[3] = false; h->timedKernels = false;
+  return 0;
+}
 int DDGI_API(get_timings)(anerend_ddgi_t* h, anerend_ddgi_timings_t* o) {
   if (!h) return ANEREND_DDGI_E_INVALID;
   BE_CHECK(h, h->be.sync());
   memset(o, 0, sizeof(*o));
+  if (h->be.timerLevel == 0) { o->accel_ms = h->accelMs; o->kernel_launches = h->be.launches; return 0; }
   if (h->timed[0]) o->trans_ms = h->be.elapsed(0, 1);
   if (h->timed[1]) o->rt_ms = h->be.elapsed(1, 2);
   if (h->timed[2]) o->convolve_ms = h->be.elapsed(2, 3);

@@ -88,7 +88,11 @@ struct Backend {
   bool fill(void* p, int byte, size_t bytes) { return bytes == 0 || ok(cudaMemsetAsync(p, byte, bytes, stream)); }
   bool sync() { return ok(cudaStreamSynchronize(stream)); }
   bool check() { return ok(cudaGetLastError()); }
-  void mark(int i) { cudaEventRecord(ev[i], stream); }
+  // timing events (anerend_cuda_ddgi_set_timers): 0 none, 1 around the passes (what FrameGraphBuilder's timers measure), 2 also around
+  // every kernel of the RT pass (events 6..10).  A timing event between two launches is not free: eleven of them cost an update of C3
+  // 26 us, and their time-stamp writes queue up behind a read-back of the atlas that is in flight (0.96 instead of 0.87 ms end to end).
+  int timerLevel = 1;
+  void mark(int i) { if (timerLevel >= (i >= 6 ? 2 : 1)) cudaEventRecord(ev[i], stream); }
   float elapsed(int a, int b) { float ms = 0.0f; if (cudaEventElapsedTime(&ms, ev[a], ev[b]) != cudaSuccess) { cudaGetLastError(); return 0.0f; } return ms; }
   // *tmpOut: the sort's scratch, to be freed by the caller once the stream has drained (no synchronisation here)
   bool sortPairs(const uint32_t* kin, uint32_t* kout, const uint32_t* vin, uint32_t* vout, uint32_t n, void** tmpOut) {
@@ -157,6 +161,7 @@ struct Backend {
   bool sync() { return true; }
   bool check() { return true; }
   void mark(int i) { tp[i] = std::chrono::steady_clock::now(); }
+  int timerLevel = 1;
   float elapsed(int a, int b) { return std::chrono::duration<float, std::milli>(tp[b] - tp[a]).count(); }
   bool sortPairs(const uint32_t* kin, uint32_t* kout, const uint32_t* vin, uint32_t* vout, uint32_t n, void** tmpOut) {
     *tmpOut = nullptr;

@@ -202,6 +202,10 @@ int anerend_cuda_ddgi_refit_accel_device(anerend_ddgi_t* h, const void* d_render
  * run the Vulkan cull pass; the reference uses range = 50.  *changed = number of renderables whose bit flipped; if it is not 0 the
  * acceleration structure is invalid until the next _build_accel. */
 int anerend_cuda_ddgi_apply_camera_cull(anerend_ddgi_t* h, float range, uint32_t* changed);
+/* Timing events behind _get_timings: level 0 none, 1 (default) around the passes — what FrameGraphBuilder's per-pass GPU timers
+ * measure (FrameGraphBuilder.cpp:276-278) — 2 also around every kernel of the RT pass (rt_kernel_ms).  Events between launches cost
+ * time (C3: 26 us per update at level 2, and a read-back of the atlas in flight delays them further), so production runs at 0 or 1. */
+int anerend_cuda_ddgi_set_timers(anerend_ddgi_t* h, int32_t level);
 int anerend_cuda_ddgi_get_bvh_info(anerend_ddgi_t* h, anerend_ddgi_bvh_info_t* out);
 int anerend_cuda_ddgi_get_two_level_info(anerend_ddgi_t* h, anerend_ddgi_two_level_info_t* out);
 /* The instances _build_accel selected, in the order they were emitted: what tlas_update.comp:54-98 writes to its InstanceBuffer

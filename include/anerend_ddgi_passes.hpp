@@ -66,6 +66,7 @@ struct Volume {
     params.slab_begin = 0; params.slab_end = numProbesY; params.device = -1; params.flags = flags;
     int rc = anerend_cuda_ddgi_create(&params, &handle);
     if (rc != 0) { handle = nullptr; error = "anerend_cuda_ddgi_create failed (no CUDA device?)"; std::printf("%s\n", error.c_str()); return false; }
+    anerend_cuda_ddgi_set_timers(handle, 0);      // FrameGraphBuilder times the exes itself (FrameGraphBuilder.cpp:276-278): no events of our own between the launches
     return true;
   }
   // The engine's "ProbeRaysConvTex" follows the CUDA atlas: called after whatever changed it (convolution, translation, clear).

@@ -7,6 +7,7 @@ from anerend_b200 import layouts as L, scenes
 scene = scenes.sponza_like(); nxz, ny, nr = 24, 12, 256
 h = A.Ddgi(A.make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS | L.FLAG_SKIP_DEAD_SHADOW_RAYS))
 h.upload_scene(scene); h.set_scene_ubo(scene.ubo); h.build_accel()
+h.set_timers(int(os.environ.get("DDGI_TIMERS", "0")))      # 0 none (production), 1 passes, 2 passes + kernels
 rots = h.rotations(scenes.rotation_sequence(3, ny * 60)).reshape(60, ny, 16)
 host = torch.empty((h.atlas_height, h.atlas_width, 4), dtype=torch.int16, pin_memory=True).numpy().view(np.uint16)
 for mode in ("no_download", "async", "sync"):

@@ -38,6 +38,7 @@ def run(name, label, flags, steps=10):
     h = A.Ddgi(A.make_params(nxz, ny, nr, flags=flags))
     h.upload_scene(scene)
     h.set_scene_ubo(scene.ubo)
+    h.set_timers(2)                 # events around every kernel: the update times below include their cost
     m1 = mem_used()
     build = []
     for _ in range(3):

@@ -16,6 +16,7 @@ for name in (sys.argv[1:] or ["c3"]):
         h.upload_scene(scene)
         h.set_scene_ubo(scene.ubo)
         h.build_accel()
+        h.set_timers(2)
         h.update(-1, h.rotations(scenes.rotation_sequence(seed, ny)))
         s = h.stats()
         pr, sr = max(1, s["primary_rays"]), max(1, s["shadow_rays"])
