@@ -186,6 +186,10 @@ class DdgiHandle:
         self._call("get_bvh_info", C.byref(b))
         return b
 
+    def set_pipeline(self, on):
+        """Closest-hit trace of an update on its own stream, under the previous update's tail (results unchanged); needs set_timers(0)."""
+        self._call("set_pipeline", C.c_int32(1 if on else 0))
+
     def set_timers(self, level):
         """0 none, 1 around the passes (default), 2 also around every kernel of the RT pass (timings()['rt_kernel_ms'])."""
         self._call("set_timers", C.c_int32(level))

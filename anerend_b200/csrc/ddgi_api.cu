@@ -108,6 +108,14 @@ struct anerend_ddgi {
 #ifndef DDGI_HOST_EMU
   // the push of an update runs on its own stream under the NEXT update's tracing: only the hit shading samples the atlas
   cudaStream_t xStream = nullptr; cudaEvent_t evConv = nullptr, evXDone = nullptr; bool exchangePending = false;
+  // Pipelined updates (anerend_cuda_ddgi_set_pipeline): the closest-hit trace of an update reads nothing the previous update writes
+  // (ray generation and traversal need the rotation and the acceleration structure; only the hit shading samples the atlas), so it
+  // runs on a stream of its own as soon as the call is made — under the tail of the previous update's kernels — with its own copies
+  // of the direction table / layer map, its own fetch cursor and a second hit-record buffer; the rest of the update waits for it.
+  bool pipeline = false, pipeStateDirty = true, pipeDoneValid[2] = {false, false};
+  cudaStream_t pStream = nullptr; cudaEvent_t evTrace[2] = {nullptr, nullptr}, evHitsFree[2] = {nullptr, nullptr}, evState = nullptr;
+  float4* dHits2 = nullptr; uint32_t* dHitInst2 = nullptr; float4* dDirsP[2] = {nullptr, nullptr}; int* dLayerMapP[2] = {nullptr, nullptr}; uint32_t* dCursorP = nullptr;
+  uint32_t pipeIdx = 0;
 #endif
   // wavefront (fast) path scratch: hit records, surface records, visibility masks, per-light shadow queues
   float4* dHits = nullptr; float4* dSurf = nullptr; uint32_t* dLit = nullptr; uint32_t* dQueues = nullptr; uint32_t* dQcount = nullptr; uint32_t* dHitInst = nullptr;
@@ -815,6 +823,9 @@ int rebuildTlas(anerend_ddgi* h) {
   if (!be.d2h(bounds, h->dSceneBounds, sizeof(bounds))) return fail(h, ANEREND_DDGI_E_CUDA, std::string("build: ") + be.errStr());
   for (int k = 0; k < 3; ++k) { h->boundsMin[k] = ordered_to_float(bounds[k]); h->boundsMax[k] = ordered_to_float(bounds[3 + k]); }
   h->numNodes = nodes; h->tlasDepth = depth; h->bvhDepth = depth + h->blasDepthMax;
+#ifndef DDGI_HOST_EMU
+  h->pipeStateDirty = true;
+#endif
   // worst case of the traversal stack: per instance level the remaining siblings and the node's own children, eight instance
   // entries, the RESTORE entry, one entry per level of a mesh's hierarchy
   if (2u * depth + 9u + h->blasDepthMax > (uint32_t)DDGI_STACK) return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "two-level structure deeper than the traversal stack");
@@ -961,12 +972,18 @@ int buildAccel(anerend_ddgi* h) {
   if (depth > DDGI_STACK) return fail(h, ANEREND_DDGI_E_UNSUPPORTED, "BVH8 deeper than the traversal stack");
   h->accelMs = be.elapsed(4, 5);
   h->haveAccel = true; h->verticesDirty = false; h->dirtyVerts.clear();
+#ifndef DDGI_HOST_EMU
+  h->pipeStateDirty = true;
+#endif
   return 0;
 }
 
 int refitAccel(anerend_ddgi* h) {
   Backend& be = h->be;
   if (h->numTris == 0) return 0;
+#ifndef DDGI_HOST_EMU
+  h->pipeStateDirty = true;          // the next pipelined trace waits for this refit
+#endif
   if (twoLevel(h)) {          // moved instances: the instance level is rebuilt; deformed vertices: their meshes' hierarchies too
     int rc2 = h->verticesDirty ? buildAccelTwoLevel(h) : rebuildTlas(h);
     h->timed[3] = true;
@@ -1021,6 +1038,8 @@ int ensureFastScratch(anerend_ddgi* h, size_t need, uint32_t nq) {
     BE_CHECK(h, be.alloc(&h->dQueues, (size_t)nq * need)); BE_CHECK(h, be.alloc(&h->dQcount, FAST_QC_SIZE)); BE_CHECK(h, be.alloc(&h->dHitq, need));
     be.free(h->dHitqSorted); h->dHitqSorted = nullptr; BE_CHECK(h, be.alloc(&h->dHitqSorted, need));
     be.free(h->dHitInst); h->dHitInst = nullptr; if (twoLevel(h)) BE_CHECK(h, be.alloc(&h->dHitInst, need));
+    if (h->pStream) BE_CHECK(h, be.ok(cudaStreamSynchronize(h->pStream)));
+    be.free(h->dHits2); be.free(h->dHitInst2); h->dHits2 = nullptr; h->dHitInst2 = nullptr; h->pipeDoneValid[0] = h->pipeDoneValid[1] = false;
     h->fastRays = need; h->fastQueues = nq;
     be.free(h->dEmisTex); h->dEmisTex = nullptr;
   }
@@ -1054,8 +1073,28 @@ int ensureFastGrids(anerend_ddgi* h) {
   }
   return 0;
 }
+// Pipelined updates: see the handle.  Off while anything needs the kernels of an update in one stream order (per-kernel or per-pass
+// timers, counters, a connected peer exchange).
+bool usePipeline(const anerend_ddgi* h) {
+  return h->pipeline && h->be.timerLevel == 0 && h->xworld < 2 && h->numPeers == 0 && !(h->p.flags & (ANEREND_DDGI_FLAG_SIMPLE_KERNELS | ANEREND_DDGI_FLAG_COUNTERS));
+}
+int ensurePipeline(anerend_ddgi* h) {
+  Backend& be = h->be;
+  if (!h->pStream) {
+    BE_CHECK(h, be.ok(cudaStreamCreateWithFlags(&h->pStream, cudaStreamNonBlocking)));
+    for (int k = 0; k < 2; ++k) {
+      BE_CHECK(h, be.ok(cudaEventCreateWithFlags(&h->evTrace[k], cudaEventDisableTiming))); BE_CHECK(h, be.ok(cudaEventCreateWithFlags(&h->evHitsFree[k], cudaEventDisableTiming)));
+      BE_CHECK(h, be.alloc(&h->dDirsP[k], (size_t)h->nY * h->N)); BE_CHECK(h, be.alloc(&h->dLayerMapP[k], (size_t)h->nY));
+    }
+    BE_CHECK(h, be.ok(cudaEventCreateWithFlags(&h->evState, cudaEventDisableTiming)));
+    BE_CHECK(h, be.alloc(&h->dCursorP, 128));
+  }
+  if (!h->dHits2) { BE_CHECK(h, be.alloc(&h->dHits2, h->fastRays)); if (twoLevel(h)) BE_CHECK(h, be.alloc(&h->dHitInst2, h->fastRays)); }
+  return 0;
+}
 // Wavefront path: k_trace_primary -> k_shade_prep -> k_trace_shadow -> k_shade (ddgi_fast.cuh)
-int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
+// pbuf >= 0: pipelined — the closest-hit trace runs on the pipeline stream with buffer set pbuf (traceLayers has put its directions there)
+int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n, int pbuf = -1) {
   Backend& be = h->be;
   const uint32_t nq = 1u + ((h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) ? h->numLights : 0u);
   { int rcs = ensureFastScratch(h, n, nq); if (rcs) return rcs; }
@@ -1063,6 +1102,7 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   FastCtx f{};
   f.t = c; f.shadeTris = h->dShadeTris; f.shadeUV = h->dShadeUV; f.emisTex = h->dEmisTex; f.hits = h->dHits; f.surf = h->dSurf; f.lit = h->dLit; f.queues = h->dQueues; f.hitq = h->dHitq;
   f.qcount = h->dQcount; f.totalRays = n; f.numQueues = nq; f.hitInst = h->dHitInst;
+  if (pbuf == 1) { f.hits = h->dHits2; f.hitInst = h->dHitInst2; }
   f.surfStride = 3u; f.rawSunDir = 0u;
   for (int k = 0; k < 8; ++k) f.tune[k] = h->tune[k];
   f.tune[3] = 0x64646464u;                 // planes2: the PRMT constant travels as a kernel argument so the selector can be the immediate
@@ -1075,6 +1115,15 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   const int gp = h->gridPrimary[cnt ? 1 : 0], gs = h->gridShadow[cnt ? 1 : 0];
   const bool two = twoLevel(h);
   be.mark(6);
+  if (pbuf >= 0) {
+    FastCtx fb = f;
+    fb.t.dirs = h->dDirsP[pbuf]; fb.t.layerMap = h->dLayerMapP[pbuf]; fb.primaryCursor = h->dCursorP + 64 * pbuf;
+    k_zero_words<<<1, 32, 0, h->pStream>>>(fb.primaryCursor, 1u);
+    if (two) k_trace<false, false, false, true><<<gp, 128, 0, h->pStream>>>(fb); else k_trace<false, false><<<gp, 128, 0, h->pStream>>>(fb);
+    ++be.launches;
+    BE_CHECK(h, be.ok(cudaEventRecord(h->evTrace[pbuf], h->pStream)));
+    BE_CHECK(h, be.ok(cudaStreamWaitEvent(be.stream, h->evTrace[pbuf], 0)));
+  } else
   if (two) { if (cnt) k_trace<false, true, false, true><<<gp, 128, 0, be.stream>>>(f); else k_trace<false, false, false, true><<<gp, 128, 0, be.stream>>>(f); }
   else if (cnt) k_trace<false, true><<<gp, 128, 0, be.stream>>>(f); else k_trace<false, false><<<gp, 128, 0, be.stream>>>(f);
   be.mark(7);
@@ -1109,6 +1158,7 @@ int traceFast(anerend_ddgi* h, const TraceCtx& c, uint32_t n) {
   }
   { int rf = fenceExchange(h); if (rf) return rf; }      // the only kernel of the pass that samples the atlas
   BE_CHECK(h, be.ok((h->p.flags & ANEREND_DDGI_FLAG_FAST_MATH) ? launch_shade_fast(f, be.stream) : launch_shade_exact(f, be.stream)));
+  if (pbuf >= 0) { BE_CHECK(h, be.ok(cudaEventRecord(h->evHitsFree[pbuf], be.stream))); h->pipeDoneValid[pbuf] = true; }      // the hit records of this set are free again
   be.mark(10);
   h->timedKernels = be.timerLevel >= 2;
   be.launches += 5;
@@ -1282,6 +1332,18 @@ int traceLayers(anerend_ddgi* h, const int* layers, int numLayers, const float* 
   // no host memory is read at the start of an update.  (A host->device copy, or a kernel reading page-locked memory,
   // queues up behind a background read-back of the atlas — PCIe reads may not pass the posted writes of that copy — and
   // held the whole update back by the length of the copy, 85 us at C3.)  Same fp32 operations as rotateDirs, no contraction.
+  int pbuf = -1;
+  if (usePipeline(h) && h->haveAccel) {
+    const uint32_t np = (uint32_t)numLayers * (uint32_t)h->Pl * (uint32_t)h->N, nq = 1u + ((h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) ? h->numLights : 0u);
+    { int rcs = ensureFastScratch(h, np, nq); if (rcs) return rcs; }
+    { int rcp = ensurePipeline(h); if (rcp) return rcp; }
+    pbuf = (int)(h->pipeIdx++ & 1u);
+    if (h->pipeDoneValid[pbuf]) BE_CHECK(h, be.ok(cudaStreamWaitEvent(h->pStream, h->evHitsFree[pbuf], 0)));      // the update before last has read its hit records
+    if (h->pipeStateDirty) {      // the acceleration structure was (re)built or refitted on the main stream since the last trace
+      BE_CHECK(h, be.ok(cudaEventRecord(h->evState, be.stream))); BE_CHECK(h, be.ok(cudaStreamWaitEvent(h->pStream, h->evState, 0)));
+      h->pipeStateDirty = false;
+    }
+  }
   for (int l0 = 0; l0 < numLayers; l0 += DIRS_BATCH) {
     DirsCtx dc{};
     dc.fib = h->dFib; dc.dDirs = h->dDirs; dc.dLayerMap = h->dLayerMap; dc.N = (uint32_t)h->N; dc.first = (uint32_t)l0;
@@ -1294,6 +1356,11 @@ int traceLayers(anerend_ddgi* h, const int* layers, int numLayers, const float* 
     }
     k_make_dirs<<<dim3(((uint32_t)h->N + 127u) / 128u, dc.count), 128, 0, be.stream>>>(dc);
     ++be.launches;
+    if (pbuf >= 0) {      // the closest-hit trace's own copy, on its stream
+      dc.dDirs = h->dDirsP[pbuf]; dc.dLayerMap = h->dLayerMapP[pbuf];
+      k_make_dirs<<<dim3(((uint32_t)h->N + 127u) / 128u, dc.count), 128, 0, h->pStream>>>(dc);
+      ++be.launches;
+    }
   }
 #else
   if (hiLayer >= loLayer)
@@ -1305,7 +1372,7 @@ int traceLayers(anerend_ddgi* h, const int* layers, int numLayers, const float* 
   TraceCtx c = sceneTraceCtx(h); c.numLayers = numLayers;
   const uint32_t n = (uint32_t)numLayers * (uint32_t)h->Pl * (uint32_t)h->N;
 #ifndef DDGI_HOST_EMU
-  if (!(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS)) { int rc = traceFast(h, c, n); if (rc) return rc; } else
+  if (!(h->p.flags & ANEREND_DDGI_FLAG_SIMPLE_KERNELS)) { int rc = traceFast(h, c, n, pbuf); if (rc) return rc; } else
 #endif
   {
     { int rf = fenceExchange(h); if (rf) return rf; }
@@ -1415,6 +1482,12 @@ void destroyHandle(anerend_ddgi* h) {
   exchangeDisconnect(h);
 #ifndef DDGI_HOST_EMU
   if (h->xStream) { cudaStreamDestroy(h->xStream); cudaEventDestroy(h->evConv); cudaEventDestroy(h->evXDone); h->xStream = nullptr; }
+  if (h->pStream) {
+    cudaStreamSynchronize(h->pStream); cudaStreamDestroy(h->pStream); h->pStream = nullptr;
+    for (int k = 0; k < 2; ++k) { cudaEventDestroy(h->evTrace[k]); cudaEventDestroy(h->evHitsFree[k]); be.free(h->dDirsP[k]); be.free(h->dLayerMapP[k]); }
+    cudaEventDestroy(h->evState); be.free(h->dCursorP);
+  }
+  be.free(h->dHits2); be.free(h->dHitInst2);
 #endif
   be.free(h->dXflags); be.free(h->dXerr); be.free(h->dSelected); be.free(h->dVisChanged); be.free(h->dBigItems); be.free(h->dBigCount);
   be.free(h->dMovedTris); be.free(h->dMovedCount);
@@ -1511,6 +1584,7 @@ int DDGI_API(sync)(anerend_ddgi_t* h) {
   BE_CHECK(h, h->be.sync());
 #ifndef DDGI_HOST_EMU
   if (h->xStream) BE_CHECK(h, h->be.ok(cudaStreamSynchronize(h->xStream)));      // the exchange of the last update
+  if (h->pStream) BE_CHECK(h, h->be.ok(cudaStreamSynchronize(h->pStream)));
 #endif
   return peerCheck(h);
 }
@@ -2223,6 +2297,14 @@ int DDGI_API(download_texel_records)(anerend_ddgi_t* h, float* out, size_t bytes
   BE_CHECK(h, h->be.d2h(out, h->dTexelRecords, bytes)); return 0;
 }
 
+int DDGI_API(set_pipeline)(anerend_ddgi_t* h, int32_t on) {
+  if (!h) return ANEREND_DDGI_E_INVALID;
+#ifndef DDGI_HOST_EMU
+  if (!on && h->pStream) BE_CHECK(h, h->be.ok(cudaStreamSynchronize(h->pStream)));
+  h->pipeline = on != 0; h->pipeStateDirty = true;
+#endif
+  return 0;
+}
 int DDGI_API(set_timers)(anerend_ddgi_t* h, int32_t level) {
   if (!h) return ANEREND_DDGI_E_INVALID;
   if (level < 0 || level > 2) return fail(h, ANEREND_DDGI_E_INVALID, "timer level: 0 none, 1 passes, 2 passes + kernels");

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(128, TWO ? 7 : 8) k_trace(const FastCtx c) {
     __syncthreads();
     total = sPrefix[c.numQueues];
   }
-  uint32_t* cursor = &c.qcount[ANY ? FAST_QC_SHADOW : FAST_QC_PRIMARY];
+  uint32_t* cursor = (!ANY && c.primaryCursor) ? c.primaryCursor : &c.qcount[ANY ? FAST_QC_SHADOW : FAST_QC_PRIMARY];
   const V3 sunL = c.rawSunDir ? -t.lightDir : normalize3(-t.lightDir);
   const uint32_t nodeSteps = max(1u, c.tune[0]), refillMin = max(1u, ANY ? c.tune[2] : c.tune[1]);
   const uint32_t stepMin = max(1u, c.tune[4]), triMin = max(1u, c.tune[5]);

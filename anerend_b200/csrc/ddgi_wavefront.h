@@ -48,6 +48,7 @@ struct FastCtx {
   uint32_t* hitq;           // [rays] compacted indices of the rays that hit (k_shade runs over these with full warps)
   uint32_t* hitqSorted;     // [rays] the same list grouped by the number of unoccluded lights (k_hit_bucket), or null
   uint32_t* qcount;         // FAST_QC_SIZE counters
+  uint32_t* primaryCursor;  // fetch cursor of the closest-hit kernel when it runs on the pipeline stream (null: qcount[FAST_QC_PRIMARY])
   uint32_t totalRays, numQueues;
   // external-ray mode (SpecularGIRT: one ray per pixel instead of the probe rays; kernels instantiated with EXT = true)
   const float4* extRays;    // [rays][2] (origin.xyz, tMax; 0 = no ray) (dir.xyz, -)

@@ -206,6 +206,12 @@ int anerend_cuda_ddgi_apply_camera_cull(anerend_ddgi_t* h, float range, uint32_t
  * measure (FrameGraphBuilder.cpp:276-278) — 2 also around every kernel of the RT pass (rt_kernel_ms).  Events between launches cost
  * time (C3: 26 us per update at level 2, and a read-back of the atlas in flight delays them further), so production runs at 0 or 1. */
 int anerend_cuda_ddgi_set_timers(anerend_ddgi_t* h, int32_t level);
+/* Pipelined updates (off by default).  Ray generation and the closest-hit traversal of an update read the rotation and the
+ * acceleration structure, never the atlas (only the hit shading samples it, rchit:98-107), so with on = 1 they run on a stream of
+ * their own as soon as _update / _trace_layer / _frame is called — under the tail of the previous update's kernels — and the rest
+ * of the update waits for them on the device.  Results are unchanged.  Active only with _set_timers(h, 0), without counters and
+ * without a connected peer exchange; builds and refits are waited for. */
+int anerend_cuda_ddgi_set_pipeline(anerend_ddgi_t* h, int32_t on);
 int anerend_cuda_ddgi_get_bvh_info(anerend_ddgi_t* h, anerend_ddgi_bvh_info_t* out);
 int anerend_cuda_ddgi_get_two_level_info(anerend_ddgi_t* h, anerend_ddgi_two_level_info_t* out);
 /* The instances _build_accel selected, in the order they were emitted: what tlas_update.comp:54-98 writes to its InstanceBuffer
