@@ -8,6 +8,7 @@ scene = scenes.sponza_like(); nxz, ny, nr = 24, 12, 256
 h = A.Ddgi(A.make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS | L.FLAG_SKIP_DEAD_SHADOW_RAYS))
 h.upload_scene(scene); h.set_scene_ubo(scene.ubo); h.build_accel()
 h.set_timers(int(os.environ.get("DDGI_TIMERS", "0")))      # 0 none (production), 1 passes, 2 passes + kernels
+h.set_pipeline(os.environ.get("DDGI_PIPELINE", "0") == "1")  # closest-hit trace of the next update under the tail of this one
 rots = h.rotations(scenes.rotation_sequence(3, ny * 60)).reshape(60, ny, 16)
 host = torch.empty((h.atlas_height, h.atlas_width, 4), dtype=torch.int16, pin_memory=True).numpy().view(np.uint16)
 for mode in ("no_download", "async", "sync"):
