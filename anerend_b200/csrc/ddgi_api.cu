@@ -2302,6 +2302,7 @@ int DDGI_API(set_pipeline)(anerend_ddgi_t* h, int32_t on) {
 #ifndef DDGI_HOST_EMU
   if (!on && h->pStream) BE_CHECK(h, h->be.ok(cudaStreamSynchronize(h->pStream)));
   h->pipeline = on != 0; h->pipeStateDirty = true;
+  if (on && h->fastRays) { BE_CHECK(h, h->be.sync()); int rcp = ensurePipeline(h); if (rcp) return rcp; }      // stream, events and buffers now, not inside the first pipelined update
 #endif
   return 0;
 }

@@ -54,3 +54,29 @@ def test_pipelined_per_layer_calls_keep_the_sequential_semantics(make_gpu):
         assert np.array_equal(a.download_atlas(), b.download_atlas()), k
     a.close()
     b.close()
+
+
+@pytest.mark.timeout(600)
+def test_config3_pipelined_updates_bit_exact(oracle, make_gpu):
+    """C3 at full size, four consecutive updates enqueued without a host synchronisation in between (the next update's closest-hit
+    trace runs under the tail of the previous one): atlas equal to the oracle's after every update, ray records after the last."""
+    scene = scenes.sponza_like()
+    flags = L.FLAG_RAY_RECORDS | L.FLAG_POINT_LIGHTS | L.FLAG_SKIP_DEAD_SHADOW_RAYS
+    o, g = oracle.Oracle(make_params(24, 12, 256, flags=flags)), make_gpu(make_params(24, 12, 256, flags=flags))
+    parity.setup_pair(scene, (o, g), seed=3)
+    g.set_timers(0)
+    g.set_pipeline(True)
+    rots = o.rotations(scenes.rotation_sequence(21, 12 * 4)).reshape(4, 12, 16)
+    for k in range(4):
+        g.update(-1, rots[k])                      # all four enqueued back to back
+    atlases = []
+    for k in range(4):
+        o.update(-1, rots[k])
+        atlases.append(o.download_atlas().copy())
+    assert np.array_equal(atlases[3], g.download_atlas())
+    for layer in (0, 5, 11):
+        ro, rg = o.download_ray_records(layer), g.download_ray_records(layer)
+        assert np.array_equal(ro["prim"], rg["prim"]) and np.array_equal(ro["t"], rg["t"]) and np.array_equal(ro["lit_mask"], rg["lit_mask"])
+        assert np.array_equal(ro["radiance"].view(np.uint32), rg["radiance"].view(np.uint32))
+    o.close()
+    g.close()
