@@ -1343,7 +1343,7 @@ int traceLayers(anerend_ddgi* h, const int* layers, int numLayers, const float* 
       BE_CHECK(h, be.ok(cudaEventRecord(h->evState, be.stream))); BE_CHECK(h, be.ok(cudaStreamWaitEvent(h->pStream, h->evState, 0)));
       h->pipeStateDirty = false;
     }
-  }
+  } else h->pipeStateDirty = true;      // an update whose trace ran on the main stream used hit-record set 0 there: the next pipelined one waits for it
   for (int l0 = 0; l0 < numLayers; l0 += DIRS_BATCH) {
     DirsCtx dc{};
     dc.fib = h->dFib; dc.dDirs = h->dDirs; dc.dLayerMap = h->dLayerMap; dc.N = (uint32_t)h->N; dc.first = (uint32_t)l0;
@@ -1993,6 +1993,7 @@ int specularGi(anerend_ddgi* h, const float* dDepth, const float4* dGeom0, uint3
     const uint32_t nq = 1u + ((h->p.flags & ANEREND_DDGI_FLAG_POINT_LIGHTS) ? h->numLights : 0u);
     { int rcs = ensureFastScratch(h, n, nq); if (rcs) return rcs; }
     { int rcg = ensureFastGrids(h); if (rcg) return rcg; }
+    h->pipeStateDirty = true;             // this pass uses hit-record set 0 on the main stream
     if (h->extPixels < n) {
       BE_CHECK(h, be.sync());
       be.free(h->dExtRays); be.free(h->dExtDist); h->dExtRays = nullptr; h->dExtDist = nullptr; h->extPixels = 0;
