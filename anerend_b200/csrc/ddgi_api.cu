@@ -1076,7 +1076,8 @@ int ensureFastGrids(anerend_ddgi* h) {
 // Pipelined updates: see the handle.  Off while anything needs the kernels of an update in one stream order (per-kernel or per-pass
 // timers, counters, a connected peer exchange).
 bool usePipeline(const anerend_ddgi* h) {
-  return h->pipeline && h->be.timerLevel == 0 && h->xworld < 2 && h->numPeers == 0 && !(h->p.flags & (ANEREND_DDGI_FLAG_SIMPLE_KERNELS | ANEREND_DDGI_FLAG_COUNTERS));
+  // (with a connected peer exchange too: the closest-hit trace touches neither the atlas nor the barrier flags)
+  return h->pipeline && h->be.timerLevel == 0 && !(h->p.flags & (ANEREND_DDGI_FLAG_SIMPLE_KERNELS | ANEREND_DDGI_FLAG_COUNTERS));
 }
 int ensurePipeline(anerend_ddgi* h) {
   Backend& be = h->be;

@@ -402,6 +402,9 @@ def main():
         # free (C3: +26 us per update), which is why (A) is the headline.
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         hh.set_timers(0)
+        # N > 1 (C5: no L2 flush, the steps follow each other on the stream): consecutive updates pipelined, as in the e2e loop — the K
+        # steps still lie between two synchronisations; one GPU keeps every step on its own between two events with the flush in between
+        hh.set_pipeline(multi and not flush)
         for k in range(warmup):
             step(k)
         hh.sync()
@@ -431,6 +434,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt.item())
         # (B) per-pass / per-kernel times
+        hh.set_pipeline(False)
         hh.set_timers(2)
         rt, cv, nl = [], [], 0
         hh.kernel_ms = []                        # per step: (closest-hit trace, shade_prep, any-hit trace, shade) in ms
@@ -780,7 +784,8 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "details": dict(details, deal=deal_desc), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
-                        "pipelined": "closest-hit trace of update k+1 under the tail of update k (set_pipeline)" if world == 1 else "no (peer exchange connected)"},
+                        "pipelined": "closest-hit trace of update k+1 under the tail of update k (set_pipeline)"},
+                "pipelined_value": bool(world > 1 and not flush),
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "update_ms": {"trace": rt_avg, "convolve": float(np.mean(conv_ms)), "full_grid": ms_per_step,
                               "full_grid_with_kernel_timers": float(h.ms_with_kernel_timers)},

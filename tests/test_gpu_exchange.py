@@ -21,7 +21,7 @@ def _scene_and_rots():
     return scene, scenes.rotation_sequence(7, GRID[1] * UPDATES)
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, pipelined=False):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -40,6 +40,9 @@ def _worker(rank, world, port, out_dir):
     blobs = [None] * world
     dist.all_gather_object(blobs, h.exchange_export())
     h.exchange_connect(blobs, world, rank)
+    if pipelined:                                # the next update's closest-hit trace under the exchange of this one
+        h.set_timers(0)
+        h.set_pipeline(True)
     dist.barrier()
     rots = h.rotations(seq).reshape(UPDATES, ny, 16)
     layers = sharding.layers_for_rank(ny, rank, world)
@@ -56,14 +59,15 @@ def _worker(rank, world, port, out_dir):
 
 
 @pytest.mark.gpu
-def test_two_processes_assemble_the_atlas_through_peer_stores(tmp_path, make_gpu):
+@pytest.mark.parametrize("pipelined", [False, True], ids=["plain", "pipelined"])
+def test_two_processes_assemble_the_atlas_through_peer_stores(pipelined, tmp_path, make_gpu):
     import torch.multiprocessing as mp
     from anerend_b200 import layouts as L, make_params
     world = 2
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), pipelined), nprocs=world, join=True)
     nxz, ny, nr = GRID
     scene, seq = _scene_and_rots()
     h = make_gpu(make_params(nxz, ny, nr, flags=L.FLAG_POINT_LIGHTS))
