@@ -209,8 +209,8 @@ int anerend_cuda_ddgi_set_timers(anerend_ddgi_t* h, int32_t level);
 /* Pipelined updates (off by default).  Ray generation and the closest-hit traversal of an update read the rotation and the
  * acceleration structure, never the atlas (only the hit shading samples it, rchit:98-107), so with on = 1 they run on a stream of
  * their own as soon as _update / _trace_layer / _frame is called — under the tail of the previous update's kernels — and the rest
- * of the update waits for them on the device.  Results are unchanged.  Active only with _set_timers(h, 0), without counters and
- * without a connected peer exchange; builds and refits are waited for. */
+ * of the update waits for them on the device.  Results are unchanged.  Active only with _set_timers(h, 0) and without counters;
+ * builds and refits are waited for. */
 int anerend_cuda_ddgi_set_pipeline(anerend_ddgi_t* h, int32_t on);
 int anerend_cuda_ddgi_get_bvh_info(anerend_ddgi_t* h, anerend_ddgi_bvh_info_t* out);
 int anerend_cuda_ddgi_get_two_level_info(anerend_ddgi_t* h, anerend_ddgi_two_level_info_t* out);
