@@ -402,3 +402,33 @@ def test_deforming_mesh_update_vertices_and_refit(oracle, make_emu):
         e.update_vertices(scene.vertices, 1)                      # range runs past the buffer
     o.close()
     e.close()
+
+
+def test_timer_levels_and_pipeline_switch(make_emu):
+    """anerend_cuda_ddgi_set_timers: level 0 reports no pass times, level 1 (the default) the three passes; bad levels are refused.
+    set_pipeline is accepted by the host harness (it has one 'stream': nothing to overlap) and leaves the results alone."""
+    from anerend_b200.capi import Timings
+    import ctypes
+    scene, (nxz, ny, nr) = SCENES["quad"]()
+    a, b = make_emu(make_params(nxz, ny, nr)), make_emu(make_params(nxz, ny, nr))
+    rots = parity.setup_pair(scene, (a, b), seed=3)
+
+    def timings(h):
+        t = Timings()
+        h._call("get_timings", ctypes.byref(t))
+        return t
+    a.update(-1, rots)
+    assert timings(a).rt_ms > 0.0
+    b.set_timers(0)
+    b.set_pipeline(True)
+    b.update(-1, rots)
+    t = timings(b)
+    assert t.rt_ms == 0.0 and t.convolve_ms == 0.0 and t.kernel_launches > 0
+    assert np.array_equal(a.download_atlas(), b.download_atlas())
+    b.set_timers(1)
+    b.update(-1, rots)
+    assert timings(b).rt_ms > 0.0
+    with pytest.raises(Exception):
+        b.set_timers(3)
+    a.close()
+    b.close()
