@@ -80,3 +80,25 @@ def test_config3_pipelined_updates_bit_exact(oracle, make_gpu):
         assert np.array_equal(ro["radiance"].view(np.uint32), rg["radiance"].view(np.uint32))
     o.close()
     g.close()
+
+
+def test_timer_levels_on_the_device(make_gpu):
+    """Level 2: a time for every kernel of the RT pass; level 1 (default): the passes only; level 0: nothing — and the same atlas."""
+    scene = scenes.cornell_box(grid=(8, 4, 64), wall_res=10, box_res=3)
+    a, b = make_gpu(make_params(8, 4, 64, flags=L.FLAG_POINT_LIGHTS)), make_gpu(make_params(8, 4, 64, flags=L.FLAG_POINT_LIGHTS))
+    rots = parity.setup_pair(scene, (a, b), seed=2)
+    a.set_timers(2)
+    a.update(-1, rots)
+    t = a.timings()
+    assert t["rt_ms"] > 0.0 and all(v > 0.0 for v in t["rt_kernel_ms"]), t
+    b.update(-1, rots)
+    t = b.timings()
+    assert t["rt_ms"] > 0.0 and all(v == 0.0 for v in t["rt_kernel_ms"]), t
+    b.set_timers(0)
+    b.update(-1, rots)
+    a.update(-1, rots)
+    t = b.timings()
+    assert t["rt_ms"] == 0.0 and t["kernel_launches"] > 0, t
+    assert np.array_equal(a.download_atlas(), b.download_atlas())
+    a.close()
+    b.close()
